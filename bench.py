@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""Headline benchmark: BA iterations/s on BASELINE.json configs[1]
+(synthetic Pinhole reconstruction, 1k cameras / 100k points / 1M observations).
+
+  python bench.py --gpus N --steps K --warmup W          our arm (CUDA path through the C-ABI)
+  python bench.py --impl reference --gpus N ...          the reference's CPU algorithm (oracle restatement,
+                                                          all host cores) on the same workload/metric
+
+A "step" is one Levenberg-Marquardt iteration of BundleAdjustReconstruction (Jacobian evaluation, Schur
+complement build, reduced-camera-system solve, back-substitution, candidate cost) with tolerances 0 so
+that exactly K iterations run (the reference summary has no iteration counter, bundle_adjustment.h:170-178).
+BA does not shard: with --gpus N every rank runs an independent replica ("replicas only").
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "BA iterations/s (1k cams, 100k pts, 1M obs)"
+UNIT = "iterations/s"
+
+
+def workload_config(args):
+    return {"workload": "C2 synthetic Pinhole BundleAdjustReconstruction: %d cams / %d pts / %d obs" % (
+                int(round(1000 * args.scale)), int(round(100000 * args.scale)), int(round(1000000 * args.scale))),
+            "intrinsics_to_optimize": "NONE", "loss": "TRIVIAL", "use_homogeneous_point_parametrization": True,
+            "use_inner_iterations": False, "linear_solver": "SCHUR + dense Cholesky (exact)",
+            "tolerances": 0.0, "l2": "working set (J planes 160 MB + S 290 MB) exceeds the 126 MB L2",
+            "parallelism": "replicas only (BA is single-GPU)"}
+
+
+def make_options(lib_or_oracle_default, iters):
+    o = lib_or_oracle_default
+    o.function_tolerance = 0.0
+    o.gradient_tolerance = 0.0
+    o.parameter_tolerance = 0.0
+    o.max_num_iterations = iters
+    return o
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi SM clock / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def algorithmic_bytes_k1(prob):
+    """per observation 40 B in + 160 B out; each camera (48 + 7*8 B) and point (32 B) once."""
+    return prob.num_observations * 200 + prob.num_cameras * 104 + prob.num_points * 32
+
+
+def measured_peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles():
+    """dram bytes per K1 launch from the committed ncu summary, if any."""
+    path = os.path.join(ROOT, "profiles", "k1_dram_bytes.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["dram_bytes_per_launch"])
+        except Exception:  # noqa: BLE001
+            return None
+    return None
+
+
+def cpu_baseline(prob, iters=2):
+    """The oracle (CPU restatement of the reference algorithm, OpenMP over all host cores) on the same
+    workload for `iters` LM iterations: a reported baseline, not the target."""
+    from oracle import oracle_py
+    p = prob.copy()
+    o = make_options(oracle_py.default_options(), iters)
+    s = oracle_py.ba_solve(p, o)
+    cores = os.cpu_count() or 1
+    return {"value": iters / s["solve_time_in_seconds"], "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d LM iterations of the full C2 workload (oracle/ba_oracle.cc, %d OpenMP threads)" % (iters, cores)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path cannot be built here (Ceres/Eigen/glog absent),
+    so the oracle port stands in for it, on all host cores. Rank 0 only."""
+    if rank != 0:
+        return
+    from pytheiasfm_b200 import synthetic
+    from oracle import oracle_py
+    prob, _ = synthetic.config_c2(scale=args.scale)
+    if args.warmup > 0:
+        oracle_py.ba_solve(prob.copy(), make_options(oracle_py.default_options(), min(args.warmup, 1)))
+    t0 = time.time()
+    s = oracle_py.ba_solve(prob.copy(), make_options(oracle_py.default_options(), args.steps))
+    wall = time.time() - t0
+    secs = s["solve_time_in_seconds"]
+    value = args.steps / secs
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d LM iterations of the full workload, oracle port of the reference algorithm "
+                                       "(the reference itself needs Ceres+Eigen, absent here), wall %.1f s" % (args.steps, wall)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pytheiasfm_b200 import capi, synthetic
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load_library()  # raises if the CUDA library is missing: no fallback
+
+    prob, _ = synthetic.config_c2(scale=args.scale)  # every rank: an identical replica
+    W, K = max(args.warmup, 3), args.steps
+    opts = make_options(capi.default_options(lib), W + K)
+    stream = torch.cuda.current_stream()
+    sptr = C.c_void_p(stream.cuda_stream)
+
+    # ---- device-resident arm: inputs already in HBM when the timed region starts ----
+    dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
+    p = prob.struct()
+    p.memory_space = capi.THB_MEM_DEVICE
+    for k, v in dev.items():
+        setattr(p, k, None if v is None else v.data_ptr())
+    sess = C.c_void_p()
+    capi.check(lib.thb_ba_create(C.byref(p), C.byref(opts), sptr, C.byref(sess)))
+    ran = C.c_int32(0)
+    capi.check(lib.thb_ba_iterate(sess, W, C.byref(ran)))
+    assert ran.value == W, ran.value
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    capi.check(lib.thb_ba_iterate(sess, K, C.byref(ran)))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    assert ran.value == K, ran.value
+    ms = e0.elapsed_time(e1)
+    sampler.stop_flag.set()
+    sampler.join()
+    # roofline of the dominant HBM-bound kernel (K1), timed alone with an L2 flush between launches
+    k1_ms = C.c_double(0.0)
+    capi.check(lib.thb_ba_time_jacobian(sess, 20, 1, C.byref(k1_ms)))
+    summ = capi.ThbBaSummary()
+    capi.check(lib.thb_ba_finish(sess, C.byref(summ)))
+    launches_timed = int(round(summ.gpu_launches * K / float(W + K)))
+
+    # ---- end-to-end arm: the call a user makes, host buffers, H2D + setup + K iterations + D2H timed ----
+    pin = {k: (None if v is None else torch.from_numpy(v.copy()).pin_memory()) for k, v in prob.a.items()}
+    ph = prob.struct()
+    for k, v in pin.items():
+        setattr(ph, k, None if v is None else v.data_ptr())
+    oe = make_options(capi.default_options(lib), K)
+    se = capi.ThbBaSummary()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    capi.check(lib.thb_ba_solve(C.byref(ph), C.byref(oe), C.byref(se), sptr))
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = sum(v.numel() * v.element_size() for v in pin.values() if v is not None)
+    d2h = pin["cam_ext"].numel() * 8 + pin["pts"].numel() * 8 + 64
+    assert se.num_iterations == K
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_max = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        ab = algorithmic_bytes_k1(prob)
+        achieved = ab / (k1_ms.value * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                    "note": "one thb_ba_solve call with host buffers: H2D + point/camera-major reorder + K iterations + D2H"},
+            "gpu_launches": launches_timed,
+            "roofline": {"bound": "hbm", "kernel": "k_jacobian (K1, materialised tangent-space Jacobian planes)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic_from_profiles(), "peak_source": peak_src + ", burst",
+                         "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},
+            "phase_ms_per_step": {"jacobian": summ.ms_jacobian / (W + K), "normal_equations": summ.ms_normal / (W + K),
+                                  "reduced_solve": summ.ms_solve / (W + K), "update_and_cost": summ.ms_update / (W + K)},
+            "final_cost": summ.final_cost, "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(prob, iters=2)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

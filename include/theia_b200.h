@@ -1,0 +1,221 @@
+/*
+ * theia_b200.h — C-ABI of the B200-native bundle-adjustment / RANSAC hot paths.
+ *
+ * The reference (urbste/pyTheiaSfM) has no FFI seam for these paths: its seam is the
+ * C++ free-function layer theia::BundleAdjust* / theia::Estimate*.  The entry points
+ * declared here are what an adapter for that layer binds (gather -> C-ABI -> scatter);
+ * each one names the reference function it stands behind (paths relative to
+ * /root/reference/src/theia).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * All arithmetic is FP64 (the reference is FP64 throughout); ids are int32.
+ * Every function returns THB_OK (0) or a negative THB_E_* code.  Nothing aborts or
+ * throws across this boundary (the reference CHECK-aborts on contract violations,
+ * e.g. sfm/bundle_adjustment/bundle_adjuster.cc:95,117).
+ */
+#ifndef THEIA_B200_H_
+#define THEIA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THB_OK 0
+#define THB_E_INVALID_ARGUMENT (-1) /* null pointer, bad size, index out of range      */
+#define THB_E_UNSUPPORTED (-2)      /* option combination the path does not implement  */
+#define THB_E_CUDA (-3)             /* CUDA runtime error; see thb_last_error()        */
+#define THB_E_NO_DEVICE (-4)        /* no sm_100 device visible: there is NO CPU path  */
+#define THB_E_NUMERICAL (-5)        /* evaluation failed at the initial point          */
+
+#define THB_MEM_HOST 0
+#define THB_MEM_DEVICE 1
+
+/* sfm/camera/camera_intrinsics_model_type.h:46-56 */
+#define THB_MODEL_PINHOLE 0
+#define THB_MODEL_PINHOLE_RADIAL_TANGENTIAL 1 /* not on the hot path: rejected */
+#define THB_MODEL_FISHEYE 2
+#define THB_MODEL_FOV 3
+#define THB_MODEL_DIVISION_UNDISTORTION 4
+#define THB_MODEL_DOUBLE_SPHERE 5
+#define THB_MODEL_EXTENDED_UNIFIED 6
+
+/* Intrinsics blocks are padded to this many doubles per group
+ * (largest named model: FISHEYE, 9; sfm/camera/fisheye_camera_model.h:67-77). */
+#define THB_INTR_STRIDE 10
+
+/* sfm/bundle_adjustment/create_loss_function.h:51-59 */
+#define THB_LOSS_TRIVIAL 0
+#define THB_LOSS_HUBER 1
+#define THB_LOSS_SOFTLONE 2
+#define THB_LOSS_CAUCHY 3
+#define THB_LOSS_ARCTAN 4
+#define THB_LOSS_TUKEY 5
+#define THB_LOSS_TRUNCATED 6
+
+/* How the reduced camera system is solved (ceres::LinearSolverType as exposed by
+ * BundleAdjustmentOptions::linear_solver_type, bundle_adjustment.h:98-100). */
+#define THB_SOLVER_SCHUR_CHOLESKY 0 /* exact: DENSE_SCHUR / SPARSE_SCHUR / DENSE_QR   */
+#define THB_SOLVER_SCHUR_PCG 1      /* ITERATIVE_SCHUR with SCHUR_JACOBI              */
+
+/* Camera extrinsics constness bits (bundle_adjuster.cc:357-380, 478-507). */
+#define THB_CAM_CONST_POSITION 1
+#define THB_CAM_CONST_ORIENTATION 2
+#define THB_CAM_CONST_ALL 3
+
+/* ceres::TerminationType values reported in ThbBaSummary.termination_type */
+#define THB_TERM_CONVERGENCE 0
+#define THB_TERM_NO_CONVERGENCE 1
+#define THB_TERM_FAILURE 2
+
+/*
+ * A bundle-adjustment problem in structure-of-arrays form: what
+ * BundleAdjuster::AddView/AddTrack (bundle_adjuster.cc:116-221) would have registered
+ * with ceres::Problem, flattened.  One observation = one ReprojectionError residual
+ * block (sfm/camera/reprojection_error.h:49-114) on (cam_ext[obs_cam], intr[group],
+ * pts[obs_pt]).  Parameter arrays are updated IN PLACE, like the reference mutates
+ * Camera::camera_parameters_ / Track::point_ through raw double* (bundle_adjuster.cc:585-591).
+ */
+typedef struct ThbBaProblem {
+  int32_t num_cameras;
+  int32_t num_groups; /* shared intrinsics blocks (reconstruction.cc:129-140)        */
+  int32_t num_points;
+  int32_t num_observations;
+  int32_t memory_space; /* THB_MEM_HOST or THB_MEM_DEVICE for EVERY pointer below    */
+  int32_t reserved0;
+
+  double* cam_ext;           /* [num_cameras*6]  [C(3), angle-axis(3)]  camera.h:202-204   */
+  const uint8_t* cam_const;  /* [num_cameras]    THB_CAM_CONST_* bits; may be NULL (=0)    */
+  const int32_t* cam_group;  /* [num_cameras]    index into intr / intr_model              */
+  double* intr;              /* [num_groups*THB_INTR_STRIDE]  per-model layout, SURVEY B   */
+  const int32_t* intr_model; /* [num_groups]     THB_MODEL_*                               */
+  const uint16_t* intr_const;/* [num_groups]     bit k set => parameter k held constant;   */
+                             /*                  all K bits set => block constant; NULL => all constant */
+  double* pts;               /* [num_points*4]   homogeneous [X,Y,Z,W]   track.h           */
+  const uint8_t* pt_const;   /* [num_points]     1 => constant point; may be NULL (=0)     */
+
+  const int32_t* obs_cam;    /* [num_observations] */
+  const int32_t* obs_pt;     /* [num_observations] */
+  const double* obs_xy;      /* [num_observations*2]  Feature::point_                      */
+  const double* obs_sqrt_info;/*[num_observations*2]  1/sqrt(cov(0,0)), 1/sqrt(cov(1,1));  */
+                             /*                  NULL => 1 (reprojection_error.h:96-103)   */
+} ThbBaProblem;
+
+/* BundleAdjustmentOptions (bundle_adjustment.h:87-167) restricted to what reaches
+ * ceres::Solver::Options (bundle_adjuster.cc:63-89), plus the Ceres trust-region
+ * defaults Theia leaves untouched. Fill with thb_ba_default_options. */
+typedef struct ThbBaOptions {
+  int32_t loss_function_type; /* THB_LOSS_*                                           */
+  int32_t linear_solver;      /* THB_SOLVER_*                                         */
+  int32_t use_homogeneous_point_parametrization; /* SphereManifold<4> on points       */
+  int32_t use_inner_iterations; /* must be 0: THB_E_UNSUPPORTED otherwise */
+  int32_t max_num_iterations;
+  int32_t jacobi_scaling;     /* Ceres default true                                   */
+  int32_t verbose;
+  int32_t max_num_consecutive_invalid_steps; /* Ceres default 5                       */
+  double robust_loss_width;
+  double function_tolerance;
+  double gradient_tolerance;
+  double parameter_tolerance;
+  double max_trust_region_radius;
+  double initial_trust_region_radius; /* 1e4   */
+  double min_trust_region_radius;     /* 1e-32 */
+  double min_relative_decrease;       /* 1e-3  */
+  double min_lm_diagonal;             /* 1e-6  */
+  double max_lm_diagonal;             /* 1e32  */
+  double max_solver_time_in_seconds;
+  /* THB_SOLVER_SCHUR_PCG only */
+  double pcg_tolerance;               /* relative residual; default 1e-12              */
+  int32_t pcg_max_iterations;         /* default 500                                   */
+  int32_t reserved0;
+} ThbBaOptions;
+
+#define THB_MAX_ITER_LOG 256
+
+/* BundleAdjustmentSummary (bundle_adjustment.h:170-178) + the iteration record the
+ * reference does not expose, + device timings for the roofline report. */
+typedef struct ThbBaSummary {
+  int32_t success;          /* ceres IsSolutionUsable()  bundle_adjuster.cc:352        */
+  int32_t termination_type; /* THB_TERM_*                                              */
+  int32_t num_iterations;   /* LM iterations attempted (excl. iteration 0)             */
+  int32_t num_successful_steps;
+  int32_t num_jacobian_evaluations;
+  int32_t num_cost_evaluations;
+  int32_t num_linear_solves;
+  int32_t gpu_launches;     /* kernels launched by this call                           */
+  double initial_cost;      /* 0.5 * sum rho(|r|^2)                                     */
+  double final_cost;
+  double setup_time_in_seconds;
+  double solve_time_in_seconds;
+  /* device time (CUDA events on the caller's stream), milliseconds, summed over calls */
+  double ms_jacobian;       /* K1 residual+Jacobian kernel                             */
+  double ms_normal;         /* K2/K3 block assembly + Schur complement build           */
+  double ms_solve;          /* K4 reduced camera system factor/solve                   */
+  double ms_update;         /* K5 back-substitution, Plus, cost evaluation             */
+  int32_t iter_log_count;
+  int32_t reserved0;
+  double iter_cost[THB_MAX_ITER_LOG];   /* cost after each iteration (index 0 = initial) */
+  double iter_radius[THB_MAX_ITER_LOG]; /* trust-region radius after each iteration      */
+} ThbBaSummary;
+
+/* Version / diagnostics. */
+int thb_version(void);
+const char* thb_last_error(void); /* thread-local text of the last THB_E_* */
+int thb_device_count(void);
+
+void thb_ba_default_options(ThbBaOptions* options);
+
+/*
+ * One-shot solve: theia::BundleAdjust{Reconstruction,PartialReconstruction,View(s),
+ * Track(s)} after the adapter has flattened the Reconstruction
+ * (bundle_adjustment.cc:111-143,188-217,220-258,261-285); the work done is that of
+ * BundleAdjuster::Optimize -> ceres::Solve (bundle_adjuster.cc:315-355).
+ * With THB_MEM_HOST pointers the H2D/D2H copies are part of the call.
+ * cuda_stream: a cudaStream_t (may be NULL for the default stream).
+ */
+int thb_ba_solve(const ThbBaProblem* problem, const ThbBaOptions* options,
+                 ThbBaSummary* summary, void* cuda_stream);
+
+/*
+ * Session form of the same solve, for callers that keep the problem resident in HBM
+ * (benchmark drivers; incremental pipelines that re-run BA on a growing reconstruction).
+ *   create  : validate, upload/alias inputs, build the point-major observation order,
+ *             evaluate iteration 0 (cost, Jacobian, gradient).
+ *   iterate : run up to n further LM iterations (stops early on convergence/failure);
+ *             returns the number actually run in *ran.
+ *   finish  : write parameters back to the problem's arrays, fill the summary, free.
+ */
+typedef struct ThbBaSession ThbBaSession;
+int thb_ba_create(const ThbBaProblem* problem, const ThbBaOptions* options,
+                  void* cuda_stream, ThbBaSession** session);
+int thb_ba_iterate(ThbBaSession* session, int32_t n, int32_t* ran);
+int thb_ba_finish(ThbBaSession* session, ThbBaSummary* summary);
+
+/*
+ * Kernel-level entry used by the parity tests and the roofline measurement: evaluate
+ * every ReprojectionError block at the given parameters (reprojection_error.h:49-114
+ * through create_reprojection_error_cost_function.h:54-136).  Outputs (host or device
+ * as problem->memory_space; any may be NULL), in the caller's observation order:
+ *   residuals [num_obs*2]
+ *   jac_cam   [num_obs*2*6]   d r / d cam_ext           (row-major 2x6, ambient)
+ *   jac_intr  [num_obs*2*THB_INTR_STRIDE] d r / d intr  (row-major 2xSTRIDE, zero padded)
+ *   jac_pt    [num_obs*2*4]   d r / d point             (row-major 2x4, ambient)
+ *   ok        [num_obs]       1 if the functor returned true
+ * No loss function and no manifold are applied here (those are ceres-side).
+ */
+int thb_ba_evaluate(const ThbBaProblem* problem, double* residuals, double* jac_cam,
+                    double* jac_intr, double* jac_pt, uint8_t* ok, void* cuda_stream);
+
+/*
+ * Time the production K1 kernel (tangent-space residual+Jacobian into the solver's
+ * plane layout) `repeats` times on the session's stream with CUDA events; returns the
+ * average milliseconds per launch.  flush_l2 != 0 rewrites a >L2-sized buffer between
+ * launches.  Used only for roofline reporting.
+ */
+int thb_ba_time_jacobian(ThbBaSession* session, int32_t repeats, int32_t flush_l2,
+                         double* avg_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THEIA_B200_H_ */

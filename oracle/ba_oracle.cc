@@ -1,0 +1,814 @@
+// ORACLE — test infrastructure only. Nothing under pytheiasfm_b200/ may include, link or
+// call this. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs use it, as the checker and the CPU baseline.
+//
+// CPU restatement of the reference's bundle-adjustment hot path:
+//   theia::BundleAdjuster::Optimize -> ceres::Solve   (sfm/bundle_adjustment/bundle_adjuster.cc:315-355)
+// over residual blocks ReprojectionError<Model>        (sfm/camera/reprojection_error.h:49-114)
+// with the loss functions of create_loss_function.cc:44-76 / loss_functions.cc:40-44, the
+// SubsetManifold / SphereManifold<4> parameterisations of bundle_adjuster.cc:357-460,538-545
+// and Schur elimination of the point blocks (groups 0 | 1,2; bundle_adjuster.cc:547-577).
+//
+// PARITY UNPINNED: Ceres Solver (>= 2.2) and Eigen (>= 3.4) are un-vendored, un-pinned
+// third-party dependencies absent from /root/reference and from this image.
+// The trust-region policy below restates Ceres' published TrustRegionMinimizer /
+// LevenbergMarquardtStrategy / Corrector / SphereManifold; it is pinned
+// only by the reference's own property tests (bundle_adjustment_test.cc:76-258) and by an
+// independent scipy.optimize.least_squares cross-check (tests/test_oracle_ba.py).
+//
+// Input/Output use the structs of include/theia_b200.h (host pointers only).
+
+#include <omp.h>
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "../include/theia_b200.h"
+#include "camera_models.h"
+#include "dense_linalg.h"
+
+namespace oracle {
+namespace {
+
+constexpr int KS = THB_INTR_STRIDE;
+constexpr double kMaxDouble = std::numeric_limits<double>::max();
+
+// ceres::LossFunction::Evaluate for the losses selected by create_loss_function.cc:44-76.
+// Formulas: ceres/loss_function.cc (external; Tukey in the Ceres >= 2.1 scaling).
+inline void EvaluateLoss(int type, double a, double s, double rho[3]) {
+  const double b = a * a;
+  switch (type) {
+    case THB_LOSS_HUBER:
+      if (s > b) {
+        const double r = std::sqrt(s);
+        rho[0] = 2.0 * a * r - b;
+        rho[1] = std::max(std::numeric_limits<double>::min(), a / r);
+        rho[2] = -rho[1] / (2.0 * s);
+      } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+      return;
+    case THB_LOSS_SOFTLONE: {
+      const double c = 1.0 / b, sum = 1.0 + s * c, tmp = std::sqrt(sum);
+      rho[0] = 2.0 * b * (tmp - 1.0);
+      rho[1] = std::max(std::numeric_limits<double>::min(), 1.0 / tmp);
+      rho[2] = -(c * rho[1]) / (2.0 * sum);
+      return;
+    }
+    case THB_LOSS_CAUCHY: {
+      const double c = 1.0 / b, sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = b * std::log(sum);
+      rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+      rho[2] = -c * (inv * inv);
+      return;
+    }
+    case THB_LOSS_ARCTAN: {
+      const double bb = 1.0 / b, sum = 1.0 + s * s * bb, inv = 1.0 / sum;
+      rho[0] = a * std::atan2(s, a);
+      rho[1] = std::max(std::numeric_limits<double>::min(), inv);
+      rho[2] = -2.0 * s * bb * (inv * inv);
+      return;
+    }
+    case THB_LOSS_TUKEY:
+      if (s <= b) {
+        const double value = 1.0 - s / b, value_sq = value * value;
+        rho[0] = b / 3.0 * (1.0 - value_sq * value);
+        rho[1] = value_sq;
+        rho[2] = -2.0 / b * value;
+      } else { rho[0] = b / 3.0; rho[1] = 0.0; rho[2] = 0.0; }
+      return;
+    case THB_LOSS_TRUNCATED:  // loss_functions.cc:40-44
+      rho[0] = std::min(s, b); rho[1] = s < b ? 1.0 : 0.0; rho[2] = 0.0;
+      return;
+    default:
+      rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
+  }
+}
+
+// ceres::internal::ComputeHouseholderVector for the 4-vector point (SphereManifold<4>,
+// bundle_adjuster.cc:538-545): H = I - beta v v^T, H x = |x| e_4, v[3] = 1.
+inline void HouseholderVector4(const double x[4], double v[4], double* beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  v[0] = x[0]; v[1] = x[1]; v[2] = x[2]; v[3] = 1.0;
+  *beta = 0.0;
+  const double xp = x[3];
+  if (sigma <= std::numeric_limits<double>::epsilon()) {
+    if (xp < 0.0) *beta = 2.0;
+    return;
+  }
+  const double mu = std::sqrt(xp * xp + sigma);
+  double vp = 1.0;
+  if (xp <= 0.0) vp = xp - mu; else vp = -sigma / (xp + mu);
+  *beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp; v[1] /= vp; v[2] /= vp;
+}
+
+// SphereManifold<4>::PlusJacobian: |x| * H[:, 0:3]   (row-major 4x3)
+inline void SpherePlusJacobian(const double x[4], double J[12]) {
+  double v[4], beta;
+  HouseholderVector4(x, v, &beta);
+  const double nx = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  for (int i = 0; i < 3; ++i) {
+    for (int r = 0; r < 4; ++r) J[r * 3 + i] = -beta * v[i] * v[r];
+    J[i * 3 + i] += 1.0;
+  }
+  for (int k = 0; k < 12; ++k) J[k] *= nx;
+}
+
+// SphereManifold<4>::Plus
+inline void SpherePlus(const double x[4], const double d[3], double out[4]) {
+  const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (nd == 0.0) { for (int i = 0; i < 4; ++i) out[i] = x[i]; return; }
+  double v[4], beta;
+  HouseholderVector4(x, v, &beta);
+  const double sbd = std::sin(nd) / nd;
+  const double y[4] = {sbd * d[0], sbd * d[1], sbd * d[2], std::cos(nd)};
+  const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + v[3] * y[3];
+  const double nx = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+  for (int i = 0; i < 4; ++i) out[i] = nx * (y[i] - v[i] * (beta * vty));
+}
+
+struct State {
+  std::vector<double> cam, intr, pts;
+};
+
+class BaOracle {
+ public:
+  BaOracle(const ThbBaProblem& p, const ThbBaOptions& o) : P(p), O(o) {}
+
+  int Init() {
+    nc = P.num_cameras; ng = P.num_groups; np = P.num_points; no = P.num_observations;
+    if (nc < 0 || ng < 0 || np < 0 || no < 0) return THB_E_INVALID_ARGUMENT;
+    if (P.memory_space != THB_MEM_HOST) return THB_E_INVALID_ARGUMENT;
+    if (no > 0 && (!P.cam_ext || !P.cam_group || !P.intr || !P.intr_model || !P.pts || !P.obs_cam ||
+                   !P.obs_pt || !P.obs_xy)) return THB_E_INVALID_ARGUMENT;
+    if (O.use_inner_iterations) return THB_E_UNSUPPORTED;
+    for (int g = 0; g < ng; ++g) if (NumIntrinsics(P.intr_model[g]) < 0) return THB_E_UNSUPPORTED;
+    for (int c = 0; c < nc; ++c) if (P.cam_group[c] < 0 || P.cam_group[c] >= ng) return THB_E_INVALID_ARGUMENT;
+    for (int i = 0; i < no; ++i)
+      if (P.obs_cam[i] < 0 || P.obs_cam[i] >= nc || P.obs_pt[i] < 0 || P.obs_pt[i] >= np)
+        return THB_E_INVALID_ARGUMENT;
+    x.cam.assign(P.cam_ext, P.cam_ext + (size_t)nc * 6);
+    x.intr.assign(P.intr, P.intr + (size_t)ng * KS);
+    x.pts.assign(P.pts, P.pts + (size_t)np * 4);
+
+    std::vector<char> cam_used(nc, 0), grp_used(ng, 0), pt_used(np, 0);
+    for (int i = 0; i < no; ++i) { cam_used[P.obs_cam[i]] = 1; grp_used[P.cam_group[P.obs_cam[i]]] = 1; pt_used[P.obs_pt[i]] = 1; }
+
+    // Tangent structure. SubsetManifold drops constant coordinates (bundle_adjuster.cc:429-441,
+    // 478-507); a fully constant block is removed from the program.
+    cam_td.assign(nc, 0); cam_idx.assign(nc, {});
+    for (int c = 0; c < nc; ++c) {
+      const int m = P.cam_const ? P.cam_const[c] : 0;
+      int t = 0;
+      if (cam_used[c]) {
+        if (!(m & THB_CAM_CONST_POSITION)) for (int k = 0; k < 3; ++k) cam_idx[c][t++] = k;
+        if (!(m & THB_CAM_CONST_ORIENTATION)) for (int k = 3; k < 6; ++k) cam_idx[c][t++] = k;
+      }
+      cam_td[c] = t;
+    }
+    intr_td.assign(ng, 0); intr_idx.assign(ng, {}); intr_K.assign(ng, 0);
+    for (int g = 0; g < ng; ++g) {
+      const int K = NumIntrinsics(P.intr_model[g]);
+      intr_K[g] = K;
+      int t = 0;
+      if (grp_used[g] && P.intr_const) {
+        for (int k = 0; k < K; ++k) if (!((P.intr_const[g] >> k) & 1)) intr_idx[g][t++] = k;
+      }
+      intr_td[g] = t;
+    }
+    pt_td.assign(np, 0);
+    for (int p = 0; p < np; ++p) {
+      const bool c = (P.pt_const && P.pt_const[p]) || !pt_used[p];
+      pt_td[p] = c ? 0 : (O.use_homogeneous_point_parametrization ? 3 : 4);
+    }
+    // Tangent vector layout: [points | intrinsics | cameras] (Schur groups 0 | 1 | 2).
+    int off = 0;
+    pt_off.assign(np, -1); for (int p = 0; p < np; ++p) if (pt_td[p]) { pt_off[p] = off; off += pt_td[p]; }
+    n_pt_tan = off;
+    intr_off.assign(ng, -1); for (int g = 0; g < ng; ++g) if (intr_td[g]) { intr_off[g] = off; off += intr_td[g]; }
+    cam_off.assign(nc, -1); for (int c = 0; c < nc; ++c) if (cam_td[c]) { cam_off[c] = off; off += cam_td[c]; }
+    n_tan = off; n_red = n_tan - n_pt_tan;
+
+    // Residual blocks whose parameter blocks are all constant are dropped by Ceres and their
+    // cost goes to Summary::fixed_cost.
+    fixed.assign(no, 0);
+    for (int i = 0; i < no; ++i) {
+      const int c = P.obs_cam[i];
+      if (!cam_td[c] && !intr_td[P.cam_group[c]] && !pt_td[P.obs_pt[i]]) fixed[i] = 1;
+    }
+    // point -> observations
+    pt_start.assign(np + 1, 0);
+    for (int i = 0; i < no; ++i) pt_start[P.obs_pt[i] + 1]++;
+    for (int p = 0; p < np; ++p) pt_start[p + 1] += pt_start[p];
+    pt_list.resize(no);
+    { std::vector<int> cur(pt_start.begin(), pt_start.end() - 1);
+      for (int i = 0; i < no; ++i) pt_list[cur[P.obs_pt[i]]++] = i; }
+
+    // Bounds (bundle_adjuster.cc:396-427) exist on every non-constant intrinsics block.
+    is_constrained = false;
+    for (int g = 0; g < ng; ++g) if (intr_td[g]) is_constrained = true;
+
+    res.assign((size_t)no * 2, 0.0); Jc.assign((size_t)no * 12, 0.0); Ji.assign((size_t)no * 2 * KS, 0.0);
+    Jp.assign((size_t)no * 8, 0.0);
+    grad.assign(n_tan, 0.0); scale.assign(n_tan, 1.0);
+    return THB_OK;
+  }
+
+  // ---- Evaluation of one observation with Jets of width 6+K+4 (as AutoDiffCostFunction
+  // <ReprojectionError<Model>, 2, 6, K, 4>, create_reprojection_error_cost_function.h:63-128).
+  template <int K>
+  bool EvalObsJet(int model, const double* ext, const double* Kp, const double* X, const double obs[2],
+                  const double si[2], double r[2], double jc[12], double ji[2 * KS], double jp[8]) const {
+    constexpr int N = 6 + K + 4;
+    typedef Jet<N> J;
+    J e[6], k[K], xx[4], rr[2];
+    for (int i = 0; i < 6; ++i) e[i] = J(ext[i], i);
+    for (int i = 0; i < K; ++i) k[i] = J(Kp[i], 6 + i);
+    for (int i = 0; i < 4; ++i) xx[i] = J(X[i], 6 + K + i);
+    const bool ok = ReprojectionError<J>(model, e, k, xx, obs, si, rr);
+    if (!ok) return false;
+    for (int a = 0; a < 2; ++a) {
+      r[a] = rr[a].a;
+      for (int i = 0; i < 6; ++i) jc[a * 6 + i] = rr[a].v[i];
+      for (int i = 0; i < KS; ++i) ji[a * KS + i] = i < K ? rr[a].v[6 + i] : 0.0;
+      for (int i = 0; i < 4; ++i) jp[a * 4 + i] = rr[a].v[6 + K + i];
+    }
+    return true;
+  }
+
+  bool EvalObsAmbient(const State& s, int i, bool want_jac, double r[2], double jc[12], double ji[2 * KS],
+                      double jp[8]) const {
+    const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
+    const int model = P.intr_model[g];
+    const double* ext = &s.cam[(size_t)c * 6];
+    const double* Kp = &s.intr[(size_t)g * KS];
+    const double* X = &s.pts[(size_t)p * 4];
+    const double obs[2] = {P.obs_xy[2 * (size_t)i], P.obs_xy[2 * (size_t)i + 1]};
+    const double si[2] = {P.obs_sqrt_info ? P.obs_sqrt_info[2 * (size_t)i] : 1.0,
+                          P.obs_sqrt_info ? P.obs_sqrt_info[2 * (size_t)i + 1] : 1.0};
+    if (!want_jac) return ReprojectionError<double>(model, ext, Kp, X, obs, si, r);
+    switch (intr_K[g]) {
+      case 5: return EvalObsJet<5>(model, ext, Kp, X, obs, si, r, jc, ji, jp);
+      case 7: return EvalObsJet<7>(model, ext, Kp, X, obs, si, r, jc, ji, jp);
+      case 9: return EvalObsJet<9>(model, ext, Kp, X, obs, si, r, jc, ji, jp);
+      default: return false;
+    }
+  }
+
+  // ProgramEvaluator::Evaluate: cost = sum 0.5*rho(|r|^2); tangent-space Jacobian blocks
+  // (ambient * PlusJacobian), Corrector applied; gradient = J^T r (before Jacobi scaling).
+  // Writes into res/Jc/Ji/Jp/grad members when want_jac. Returns false if any block fails.
+  bool Evaluate(const State& s, bool want_jac, double* cost, bool only_fixed = false) {
+    double total = 0.0;
+    bool all_ok = true;
+    if (want_jac) std::fill(grad.begin(), grad.end(), 0.0);
+    const int nth = omp_get_max_threads();
+    std::vector<std::vector<double>> gth;
+    if (want_jac) gth.assign(nth, std::vector<double>(n_red, 0.0));
+#pragma omp parallel for schedule(static) reduction(+ : total) reduction(&& : all_ok)
+    for (int p = 0; p < np; ++p) {
+      double PJ[12];
+      bool have_pj = false;
+      double gp[4] = {0, 0, 0, 0};
+      std::vector<double>& gt = want_jac ? gth[omp_get_thread_num()] : grad;
+      for (int q = pt_start[p]; q < pt_start[p + 1]; ++q) {
+        const int i = pt_list[q];
+        if ((fixed[i] != 0) != only_fixed) continue;
+        double r[2], jc[12], ji[2 * KS], jp[8];
+        const bool ok = EvalObsAmbient(s, i, want_jac, r, jc, ji, jp);
+        if (!ok) { all_ok = false; continue; }
+        const double sq = r[0] * r[0] + r[1] * r[1];
+        double rho[3];
+        EvaluateLoss(O.loss_function_type, O.robust_loss_width, sq, rho);
+        total += 0.5 * rho[0];
+        if (!want_jac) continue;
+        const int c = P.obs_cam[i], g = P.cam_group[c];
+        // tangent blocks
+        double tc[12], ti[2 * KS], tp[8];
+        const int dc = cam_td[c], di = intr_td[g], dp = pt_td[p];
+        for (int a = 0; a < 2; ++a) {
+          for (int t = 0; t < dc; ++t) tc[a * 6 + t] = jc[a * 6 + cam_idx[c][t]];
+          for (int t = 0; t < di; ++t) ti[a * KS + t] = ji[a * KS + intr_idx[g][t]];
+        }
+        if (dp == 3) {
+          if (!have_pj) { SpherePlusJacobian(&s.pts[(size_t)p * 4], PJ); have_pj = true; }
+          for (int a = 0; a < 2; ++a)
+            for (int t = 0; t < 3; ++t) {
+              double v = 0.0;
+              for (int k = 0; k < 4; ++k) v += jp[a * 4 + k] * PJ[k * 3 + t];
+              tp[a * 4 + t] = v;
+            }
+        } else if (dp == 4) {
+          for (int k = 0; k < 8; ++k) tp[k] = jp[k];
+        }
+        // ceres::internal::Corrector (corrector.cc; external)
+        const double sqrt_rho1 = std::sqrt(rho[1]);
+        double residual_scaling, alpha_sq_norm;
+        if (sq == 0.0 || rho[2] <= 0.0) { residual_scaling = sqrt_rho1; alpha_sq_norm = 0.0; }
+        else {
+          const double D = 1.0 + 2.0 * sq * rho[2] / rho[1];
+          const double alpha = 1.0 - std::sqrt(D);
+          residual_scaling = sqrt_rho1 / (1 - alpha);
+          alpha_sq_norm = alpha / sq;
+        }
+        auto correct = [&](double* blk, int stride, int d) {
+          for (int t = 0; t < d; ++t) {
+            if (alpha_sq_norm == 0.0) { blk[t] *= sqrt_rho1; blk[stride + t] *= sqrt_rho1; }
+            else {
+              const double rtj = blk[t] * r[0] + blk[stride + t] * r[1];
+              blk[t] = sqrt_rho1 * (blk[t] - alpha_sq_norm * r[0] * rtj);
+              blk[stride + t] = sqrt_rho1 * (blk[stride + t] - alpha_sq_norm * r[1] * rtj);
+            }
+          }
+        };
+        correct(tc, 6, dc); correct(ti, KS, di); correct(tp, 4, dp);
+        r[0] *= residual_scaling; r[1] *= residual_scaling;
+        res[2 * (size_t)i] = r[0]; res[2 * (size_t)i + 1] = r[1];
+        for (int a = 0; a < 2; ++a) {
+          for (int t = 0; t < 6; ++t) Jc[(size_t)i * 12 + a * 6 + t] = t < dc ? tc[a * 6 + t] : 0.0;
+          for (int t = 0; t < KS; ++t) Ji[(size_t)i * 2 * KS + a * KS + t] = t < di ? ti[a * KS + t] : 0.0;
+          for (int t = 0; t < 4; ++t) Jp[(size_t)i * 8 + a * 4 + t] = t < dp ? tp[a * 4 + t] : 0.0;
+        }
+        for (int t = 0; t < dp; ++t) gp[t] += tp[t] * r[0] + tp[4 + t] * r[1];
+        for (int t = 0; t < dc; ++t) gt[cam_off[c] - n_pt_tan + t] += tc[t] * r[0] + tc[6 + t] * r[1];
+        for (int t = 0; t < di; ++t) gt[intr_off[g] - n_pt_tan + t] += ti[t] * r[0] + ti[KS + t] * r[1];
+      }
+      if (want_jac && pt_td[p]) for (int t = 0; t < pt_td[p]; ++t) grad[pt_off[p] + t] = gp[t];
+    }
+    if (want_jac)
+      for (int t = 0; t < nth; ++t)
+        for (int k = 0; k < n_red; ++k) grad[n_pt_tan + k] += gth[t][k];
+    *cost = total;
+    return all_ok;
+  }
+
+  void ScaleJacobianColumns() {
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < no; ++i) {
+      if (fixed[i]) continue;
+      const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
+      for (int a = 0; a < 2; ++a) {
+        for (int t = 0; t < cam_td[c]; ++t) Jc[(size_t)i * 12 + a * 6 + t] *= scale[cam_off[c] + t];
+        for (int t = 0; t < intr_td[g]; ++t) Ji[(size_t)i * 2 * KS + a * KS + t] *= scale[intr_off[g] + t];
+        for (int t = 0; t < pt_td[p]; ++t) Jp[(size_t)i * 8 + a * 4 + t] *= scale[pt_off[p] + t];
+      }
+    }
+  }
+
+  void SquaredColumnNorm(std::vector<double>* out) const {
+    out->assign(n_tan, 0.0);
+    for (int i = 0; i < no; ++i) {
+      if (fixed[i]) continue;
+      const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
+      for (int a = 0; a < 2; ++a) {
+        for (int t = 0; t < cam_td[c]; ++t) { const double v = Jc[(size_t)i * 12 + a * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
+        for (int t = 0; t < intr_td[g]; ++t) { const double v = Ji[(size_t)i * 2 * KS + a * KS + t]; (*out)[intr_off[g] + t] += v * v; }
+        for (int t = 0; t < pt_td[p]; ++t) { const double v = Jp[(size_t)i * 8 + a * 4 + t]; (*out)[pt_off[p] + t] += v * v; }
+      }
+    }
+  }
+
+  // EvaluateGradientAndJacobian (trust_region_minimizer.cc; external)
+  bool EvaluateGradientAndJacobian(int iteration) {
+    if (!Evaluate(x, true, &x_cost)) return false;
+    ++n_jac_eval;
+    if (O.jacobi_scaling) {
+      if (iteration == 0) {
+        std::vector<double> cn; SquaredColumnNorm(&cn);
+        for (int k = 0; k < n_tan; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
+      }
+      ScaleJacobianColumns();
+    }
+    // unconstrained: max-norm of the gradient; constrained: max |Plus(x,-g) - x|.
+    if (!is_constrained) {
+      gradient_max_norm = 0.0;
+      for (double g : grad) gradient_max_norm = std::max(gradient_max_norm, std::fabs(g));
+    } else {
+      std::vector<double> ng(grad.size());
+      for (size_t k = 0; k < grad.size(); ++k) ng[k] = -grad[k];
+      State y; Plus(x, ng, &y);
+      gradient_max_norm = MaxAbsDiff(x, y);
+    }
+    return true;
+  }
+
+  double MaxAbsDiff(const State& a, const State& b) const {
+    double m = 0.0;
+    for (int c = 0; c < nc; ++c) if (cam_td[c]) for (int k = 0; k < 6; ++k) m = std::max(m, std::fabs(a.cam[c * 6 + k] - b.cam[c * 6 + k]));
+    for (int g = 0; g < ng; ++g) if (intr_td[g]) for (int k = 0; k < intr_K[g]; ++k) m = std::max(m, std::fabs(a.intr[g * KS + k] - b.intr[g * KS + k]));
+    for (int p = 0; p < np; ++p) if (pt_td[p]) for (int k = 0; k < 4; ++k) m = std::max(m, std::fabs(a.pts[(size_t)p * 4 + k] - b.pts[(size_t)p * 4 + k]));
+    return m;
+  }
+  double NormDiff(const State& a, const State* b) const {  // |a - b| (b == nullptr: |a|), non-constant blocks
+    double s = 0.0;
+    auto acc = [&](double u, double v) { const double d = u - v; s += d * d; };
+    for (int c = 0; c < nc; ++c) if (cam_td[c]) for (int k = 0; k < 6; ++k) acc(a.cam[c * 6 + k], b ? b->cam[c * 6 + k] : 0.0);
+    for (int g = 0; g < ng; ++g) if (intr_td[g]) for (int k = 0; k < intr_K[g]; ++k) acc(a.intr[g * KS + k], b ? b->intr[g * KS + k] : 0.0);
+    for (int p = 0; p < np; ++p) if (pt_td[p]) for (int k = 0; k < 4; ++k) acc(a.pts[(size_t)p * 4 + k], b ? b->pts[(size_t)p * 4 + k] : 0.0);
+    return std::sqrt(s);
+  }
+
+  // ParameterBlock::Plus: manifold Plus then projection on the box constraints
+  // (bounds of bundle_adjuster.cc:396-427).
+  void Plus(const State& s, const std::vector<double>& d, State* out) const {
+    *out = s;
+    for (int c = 0; c < nc; ++c) for (int t = 0; t < cam_td[c]; ++t) out->cam[c * 6 + cam_idx[c][t]] += d[cam_off[c] + t];
+    for (int g = 0; g < ng; ++g) {
+      if (!intr_td[g]) continue;
+      double* K = &out->intr[g * KS];
+      for (int t = 0; t < intr_td[g]; ++t) K[intr_idx[g][t]] += d[intr_off[g] + t];
+      K[0] = std::max(K[0], 1.0);  // focal length >= 1 (index 0 in every model)
+      if (P.intr_model[g] == DOUBLE_SPHERE) {
+        K[5] = std::min(std::max(K[5], -1.0), 1.0);
+        K[6] = std::min(std::max(K[6], 0.0), 1.0);
+      } else if (P.intr_model[g] == EXTENDED_UNIFIED) {
+        K[5] = std::min(std::max(K[5], 0.0), 1.0);
+        K[6] = std::max(K[6], 0.1);
+      }
+    }
+    for (int p = 0; p < np; ++p) {
+      if (pt_td[p] == 3) SpherePlus(&s.pts[(size_t)p * 4], &d[pt_off[p]], &out->pts[(size_t)p * 4]);
+      else if (pt_td[p] == 4) for (int k = 0; k < 4; ++k) out->pts[(size_t)p * 4 + k] += d[pt_off[p] + k];
+    }
+  }
+
+  // Exact solve of (J^T J + D^2) y = J^T r by Schur elimination of the point blocks.
+  // Returns false on a non-positive-definite block (LINEAR_SOLVER_FAILURE).
+  bool SchurSolve(const std::vector<double>& D, std::vector<double>* y) {
+    ++n_solves;
+    y->assign(n_tan, 0.0);
+    const int nr = n_red;
+    std::vector<double> S((size_t)nr * nr, 0.0), rhs(nr, 0.0);
+    for (int k = 0; k < nr; ++k) S[(size_t)k * nr + k] = D[n_pt_tan + k] * D[n_pt_tan + k];
+    std::vector<omp_lock_t> locks(std::max(1, nc + ng));
+    for (auto& l : locks) omp_init_lock(&l);
+    std::vector<double> Vinv((size_t)np * 16, 0.0), gpv((size_t)np * 4, 0.0);
+    bool ok = true;
+    // reduced-space view of an observation: columns [intr(di) | cam(dc)] with global offsets
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int p = 0; p < np; ++p) {
+      const int n_obs = pt_start[p + 1] - pt_start[p];
+      if (!n_obs) continue;
+      const int dp = pt_td[p];
+      double V[16] = {0}, gp[4] = {0};
+      if (dp) {
+        for (int t = 0; t < dp; ++t) V[t * dp + t] = D[pt_off[p] + t] * D[pt_off[p] + t];
+        for (int q = pt_start[p]; q < pt_start[p + 1]; ++q) {
+          const int i = pt_list[q];
+          if (fixed[i]) continue;
+          const double* jp = &Jp[(size_t)i * 8];
+          const double* r = &res[2 * (size_t)i];
+          for (int a = 0; a < dp; ++a) {
+            gp[a] += jp[a] * r[0] + jp[4 + a] * r[1];
+            for (int b = 0; b < dp; ++b) V[a * dp + b] += jp[a] * jp[b] + jp[4 + a] * jp[4 + b];
+          }
+        }
+        // V^-1 by solving for the identity columns
+        double Vi[16];
+        bool pd = true;
+        for (int col = 0; col < dp && pd; ++col) {
+          double e[4] = {0, 0, 0, 0}, xcol[4];
+          e[col] = 1.0;
+          pd = SmallCholeskySolve(dp, V, e, xcol);
+          for (int a = 0; a < dp; ++a) Vi[a * dp + col] = xcol[a];
+        }
+        if (!pd) {
+#pragma omp atomic write
+          ok = false;
+          continue;
+        }
+        for (int k = 0; k < dp * dp; ++k) Vinv[(size_t)p * 16 + k] = Vi[k];
+        for (int a = 0; a < dp; ++a) gpv[(size_t)p * 4 + a] = gp[a];
+      }
+      if (!nr) continue;
+      // per-observation reduced blocks
+      struct RB { int dim; int idx[6 + KS]; double Jr[2][6 + KS]; double E[(6 + KS) * 4]; double T[(6 + KS) * 4]; int lock_id; };
+      std::vector<RB> rb;
+      rb.reserve(n_obs);
+      for (int q = pt_start[p]; q < pt_start[p + 1]; ++q) {
+        const int i = pt_list[q];
+        if (fixed[i]) continue;
+        const int c = P.obs_cam[i], g = P.cam_group[c];
+        RB b; b.dim = 0; b.lock_id = c;
+        for (int t = 0; t < intr_td[g]; ++t) { b.idx[b.dim] = intr_off[g] - n_pt_tan + t; b.Jr[0][b.dim] = Ji[(size_t)i * 2 * KS + t]; b.Jr[1][b.dim] = Ji[(size_t)i * 2 * KS + KS + t]; ++b.dim; }
+        for (int t = 0; t < cam_td[c]; ++t) { b.idx[b.dim] = cam_off[c] - n_pt_tan + t; b.Jr[0][b.dim] = Jc[(size_t)i * 12 + t]; b.Jr[1][b.dim] = Jc[(size_t)i * 12 + 6 + t]; ++b.dim; }
+        if (!b.dim) continue;
+        const double* r = &res[2 * (size_t)i];
+        const double* jp = &Jp[(size_t)i * 8];
+        // U and g_red contributions
+        omp_set_lock(&locks[0]);  // rhs is tiny: one lock
+        for (int a = 0; a < b.dim; ++a) rhs[b.idx[a]] += b.Jr[0][a] * r[0] + b.Jr[1][a] * r[1];
+        omp_unset_lock(&locks[0]);
+        for (int a = 0; a < b.dim; ++a) {
+          // rows of S are protected per row owner: use lock of (row mod locks)
+          omp_lock_t* lk = &locks[b.idx[a] % locks.size()];
+          omp_set_lock(lk);
+          for (int bb = 0; bb < b.dim; ++bb)
+            if (b.idx[bb] <= b.idx[a]) S[(size_t)b.idx[a] * nr + b.idx[bb]] += b.Jr[0][a] * b.Jr[0][bb] + b.Jr[1][a] * b.Jr[1][bb];
+          omp_unset_lock(lk);
+        }
+        if (dp) {
+          const double* Vi = &Vinv[(size_t)p * 16];
+          for (int a = 0; a < b.dim; ++a)
+            for (int t = 0; t < dp; ++t) b.E[a * 4 + t] = b.Jr[0][a] * jp[t] + b.Jr[1][a] * jp[4 + t];
+          for (int a = 0; a < b.dim; ++a)
+            for (int t = 0; t < dp; ++t) {
+              double v = 0.0;
+              for (int u = 0; u < dp; ++u) v += b.E[a * 4 + u] * Vi[u * dp + t];
+              b.T[a * 4 + t] = v;
+            }
+          rb.push_back(b);
+        }
+      }
+      if (!dp) continue;
+      for (size_t i1 = 0; i1 < rb.size(); ++i1) {
+        const RB& A = rb[i1];
+        omp_set_lock(&locks[0]);
+        for (int a = 0; a < A.dim; ++a) {
+          double v = 0.0;
+          for (int t = 0; t < dp; ++t) v += A.T[a * 4 + t] * gp[t];
+          rhs[A.idx[a]] -= v;
+        }
+        omp_unset_lock(&locks[0]);
+        for (int a = 0; a < A.dim; ++a) {
+          omp_lock_t* lk = &locks[A.idx[a] % locks.size()];
+          omp_set_lock(lk);
+          double* srow = &S[(size_t)A.idx[a] * nr];
+          for (size_t i2 = 0; i2 < rb.size(); ++i2) {
+            const RB& B = rb[i2];
+            for (int bb = 0; bb < B.dim; ++bb) {
+              if (B.idx[bb] > A.idx[a]) continue;
+              double v = 0.0;
+              for (int t = 0; t < dp; ++t) v += A.T[a * 4 + t] * B.E[bb * 4 + t];
+              srow[B.idx[bb]] -= v;
+            }
+          }
+          omp_unset_lock(lk);
+        }
+      }
+    }
+    for (auto& l : locks) omp_destroy_lock(&l);
+    if (!ok) return false;
+    std::vector<double> yr(rhs);
+    if (nr) {
+      if (!CholeskyLower(S.data(), nr)) return false;
+      CholeskySolveLower(S.data(), nr, yr.data());
+      for (int k = 0; k < nr; ++k) (*y)[n_pt_tan + k] = yr[k];
+    }
+    // back substitution: y_p = V^-1 (g_p - sum_i E_i^T y_red)
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < np; ++p) {
+      const int dp = pt_td[p];
+      if (!dp) continue;
+      double b[4];
+      for (int a = 0; a < dp; ++a) b[a] = gpv[(size_t)p * 4 + a];
+      for (int q = pt_start[p]; q < pt_start[p + 1]; ++q) {
+        const int i = pt_list[q];
+        if (fixed[i]) continue;
+        const int c = P.obs_cam[i], g = P.cam_group[c];
+        const double* jp = &Jp[(size_t)i * 8];
+        double jy[2] = {0.0, 0.0};
+        for (int t = 0; t < intr_td[g]; ++t) { const double v = yr[intr_off[g] - n_pt_tan + t]; jy[0] += Ji[(size_t)i * 2 * KS + t] * v; jy[1] += Ji[(size_t)i * 2 * KS + KS + t] * v; }
+        for (int t = 0; t < cam_td[c]; ++t) { const double v = yr[cam_off[c] - n_pt_tan + t]; jy[0] += Jc[(size_t)i * 12 + t] * v; jy[1] += Jc[(size_t)i * 12 + 6 + t] * v; }
+        for (int a = 0; a < dp; ++a) b[a] -= jp[a] * jy[0] + jp[4 + a] * jy[1];
+      }
+      const double* Vi = &Vinv[(size_t)p * 16];
+      for (int a = 0; a < dp; ++a) {
+        double v = 0.0;
+        for (int u = 0; u < dp; ++u) v += Vi[a * dp + u] * b[u];
+        (*y)[pt_off[p] + a] = v;
+      }
+    }
+    for (double v : *y) if (!std::isfinite(v)) return false;
+    return true;
+  }
+
+  // model_cost_change = -(J step)^T (r + J step / 2)
+  double ModelCostChange(const std::vector<double>& step) const {
+    double acc = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : acc)
+    for (int i = 0; i < no; ++i) {
+      if (fixed[i]) continue;
+      const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
+      double m[2] = {0.0, 0.0};
+      for (int a = 0; a < 2; ++a) {
+        for (int t = 0; t < cam_td[c]; ++t) m[a] += Jc[(size_t)i * 12 + a * 6 + t] * step[cam_off[c] + t];
+        for (int t = 0; t < intr_td[g]; ++t) m[a] += Ji[(size_t)i * 2 * KS + a * KS + t] * step[intr_off[g] + t];
+        for (int t = 0; t < pt_td[p]; ++t) m[a] += Jp[(size_t)i * 8 + a * 4 + t] * step[pt_off[p] + t];
+      }
+      acc += -(m[0] * (res[2 * (size_t)i] + m[0] / 2.0) + m[1] * (res[2 * (size_t)i + 1] + m[1] / 2.0));
+    }
+    return acc;
+  }
+
+  void Log(ThbBaSummary* s, double cost, double radius) {
+    if (s->iter_log_count < THB_MAX_ITER_LOG) {
+      s->iter_cost[s->iter_log_count] = cost;
+      s->iter_radius[s->iter_log_count] = radius;
+      ++s->iter_log_count;
+    }
+  }
+
+  // TrustRegionMinimizer::Minimize with LevenbergMarquardtStrategy (external).
+  int Solve(ThbBaSummary* sum) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::memset(sum, 0, sizeof(*sum));
+    double fixed_cost = 0.0;
+    bool any_fixed = false;
+    for (int i = 0; i < no; ++i) any_fixed |= fixed[i] != 0;
+    if (any_fixed && !Evaluate(x, false, &fixed_cost, true)) { sum->termination_type = THB_TERM_FAILURE; return THB_E_NUMERICAL; }
+    double radius = O.initial_trust_region_radius, decrease_factor = 2.0;
+    bool reuse_diagonal = false;
+    std::vector<double> diagonal(n_tan, 0.0), lm_diag(n_tan, 0.0), step, delta(n_tan);
+    int num_consecutive_invalid = 0;
+    sum->termination_type = THB_TERM_NO_CONVERGENCE;
+    // IterationZero
+    if (is_constrained) { std::vector<double> z(n_tan, 0.0); State y; Plus(x, z, &y); x = y; }
+    double x_norm = NormDiff(x, nullptr);
+    if (n_tan == 0) {  // nothing to optimise: Ceres returns CONVERGENCE with cost = fixed cost
+      sum->initial_cost = sum->final_cost = fixed_cost; sum->success = 1; sum->termination_type = THB_TERM_CONVERGENCE;
+      return THB_OK;
+    }
+    if (!EvaluateGradientAndJacobian(0)) { sum->termination_type = THB_TERM_FAILURE; sum->success = 0; return THB_E_NUMERICAL; }
+    sum->initial_cost = x_cost + fixed_cost;
+    double min_cost = x_cost;
+    Log(sum, x_cost + fixed_cost, radius);
+    bool step_is_successful = true;  // iteration 0 counts as successful for the gradient test
+    int iteration = 0;
+    const auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    while (true) {
+      // FinalizeIterationAndCheckIfMinimizerCanContinue
+      if (elapsed() >= O.max_solver_time_in_seconds) { sum->termination_type = THB_TERM_NO_CONVERGENCE; break; }
+      if (iteration >= O.max_num_iterations) { sum->termination_type = THB_TERM_NO_CONVERGENCE; break; }
+      if (step_is_successful && gradient_max_norm <= O.gradient_tolerance) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      if (radius <= O.min_trust_region_radius) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      ++iteration;
+      step_is_successful = false;
+      // ComputeTrustRegionStep / LevenbergMarquardtStrategy::ComputeStep
+      if (!reuse_diagonal) {
+        SquaredColumnNorm(&diagonal);
+        for (double& d : diagonal) d = std::min(std::max(d, O.min_lm_diagonal), O.max_lm_diagonal);
+      }
+      for (int k = 0; k < n_tan; ++k) lm_diag[k] = std::sqrt(diagonal[k] / radius);
+      bool step_valid = SchurSolve(lm_diag, &step);
+      reuse_diagonal = true;
+      double model_cost_change = 0.0;
+      if (step_valid) {
+        for (double& v : step) v = -v;
+        model_cost_change = ModelCostChange(step);
+        step_valid = model_cost_change > 0.0;
+      }
+      if (!step_valid) {
+        // HandleInvalidStep
+        if (++num_consecutive_invalid >= O.max_num_consecutive_invalid_steps) { sum->termination_type = THB_TERM_FAILURE; break; }
+        radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+        Log(sum, x_cost + fixed_cost, radius);
+        continue;
+      }
+      num_consecutive_invalid = 0;
+      for (int k = 0; k < n_tan; ++k) delta[k] = step[k] * scale[k];
+      State cand;
+      if (is_constrained) {
+        // DoLineSearch: Armijo, first probe at step size 1. PARTIAL RESTATEMENT: Ceres
+        // contracts the step by polynomial interpolation when the probe fails; here a failed
+        // probe halves delta until the sufficient-decrease test holds (max 20 probes).
+        double gtd = 0.0;
+        for (int k = 0; k < n_tan; ++k) gtd += grad[k] * delta[k];
+        double alpha = 1.0;
+        for (int it = 0; it < 20; ++it) {
+          std::vector<double> sd(delta);
+          for (double& v : sd) v *= alpha;
+          Plus(x, sd, &cand);
+          double c;
+          ++n_cost_eval;
+          if (Evaluate(cand, false, &c) && std::isfinite(c) && c <= x_cost + 1e-4 * gtd * alpha) break;
+          alpha *= 0.5;
+          if (it == 19) alpha = 1.0;  // line search failed: delta unchanged
+        }
+        for (double& v : delta) v *= alpha;
+      }
+      // ComputeCandidatePointAndEvaluateCost
+      Plus(x, delta, &cand);
+      double cand_cost;
+      ++n_cost_eval;
+      if (!Evaluate(cand, false, &cand_cost)) cand_cost = kMaxDouble;
+      // ParameterToleranceReached
+      const double step_norm = NormDiff(x, &cand);
+      if (step_norm <= O.parameter_tolerance * (x_norm + O.parameter_tolerance)) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      // FunctionToleranceReached
+      const double cost_change = x_cost - cand_cost;
+      if (std::fabs(cost_change) <= O.function_tolerance * x_cost) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      // IsStepSuccessful (monotonic steps)
+      const double relative_decrease = cand_cost >= kMaxDouble ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
+      if (relative_decrease > O.min_relative_decrease) {
+        x = cand; x_norm = NormDiff(x, nullptr);
+        if (!EvaluateGradientAndJacobian(iteration)) { sum->termination_type = THB_TERM_FAILURE; break; }
+        step_is_successful = true;
+        ++sum->num_successful_steps;
+        radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+        radius = std::min(O.max_trust_region_radius, radius);
+        decrease_factor = 2.0; reuse_diagonal = false;
+        min_cost = std::min(min_cost, x_cost);
+      } else {
+        radius /= decrease_factor; decrease_factor *= 2.0; reuse_diagonal = true;
+      }
+      Log(sum, x_cost + fixed_cost, radius);
+    }
+    sum->num_iterations = iteration;
+    sum->final_cost = min_cost + fixed_cost;
+    sum->success = sum->termination_type != THB_TERM_FAILURE;
+    sum->num_jacobian_evaluations = n_jac_eval; sum->num_cost_evaluations = n_cost_eval; sum->num_linear_solves = n_solves;
+    sum->solve_time_in_seconds = elapsed();
+    if (sum->success) {
+      std::memcpy(P.cam_ext, x.cam.data(), sizeof(double) * x.cam.size());
+      std::memcpy(P.intr, x.intr.data(), sizeof(double) * x.intr.size());
+      std::memcpy(P.pts, x.pts.data(), sizeof(double) * x.pts.size());
+    }
+    return THB_OK;
+  }
+
+  ThbBaProblem P; ThbBaOptions O;
+  int nc = 0, ng = 0, np = 0, no = 0, n_tan = 0, n_pt_tan = 0, n_red = 0;
+  State x;
+  std::vector<int> cam_td, intr_td, intr_K, pt_td, pt_off, intr_off, cam_off, pt_start, pt_list;
+  std::vector<std::array<int, 6>> cam_idx;
+  std::vector<std::array<int, KS>> intr_idx;
+  std::vector<char> fixed;
+  bool is_constrained = false;
+  std::vector<double> res, Jc, Ji, Jp, grad, scale;
+  double x_cost = 0.0, gradient_max_norm = 0.0;
+  int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0;
+};
+
+}  // namespace
+}  // namespace oracle
+
+extern "C" {
+
+void oracle_ba_default_options(ThbBaOptions* o) {
+  std::memset(o, 0, sizeof(*o));
+  // bundle_adjustment.h:87-167 defaults, except use_inner_iterations
+  o->loss_function_type = THB_LOSS_TRIVIAL; o->robust_loss_width = 2.0;
+  o->linear_solver = THB_SOLVER_SCHUR_CHOLESKY;
+  o->use_homogeneous_point_parametrization = 1; o->use_inner_iterations = 0;
+  o->max_num_iterations = 100; o->jacobi_scaling = 1; o->verbose = 0;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->max_trust_region_radius = 1e12; o->initial_trust_region_radius = 1e4;
+  o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->max_solver_time_in_seconds = 3600.0;
+  o->pcg_tolerance = 1e-12; o->pcg_max_iterations = 500;
+}
+
+int oracle_ba_solve(const ThbBaProblem* p, const ThbBaOptions* o, ThbBaSummary* s) {
+  if (!p || !o || !s) return THB_E_INVALID_ARGUMENT;
+  oracle::BaOracle ba(*p, *o);
+  const int rc = ba.Init();
+  if (rc != THB_OK) return rc;
+  return ba.Solve(s);
+}
+
+// Ambient residuals/Jacobians of every block (same contract as thb_ba_evaluate).
+int oracle_ba_evaluate(const ThbBaProblem* p, double* residuals, double* jac_cam, double* jac_intr,
+                       double* jac_pt, uint8_t* ok) {
+  if (!p) return THB_E_INVALID_ARGUMENT;
+  ThbBaOptions o; oracle_ba_default_options(&o);
+  oracle::BaOracle ba(*p, o);
+  const int rc = ba.Init();
+  if (rc != THB_OK) return rc;
+  for (int i = 0; i < p->num_observations; ++i) {
+    double r[2] = {0, 0}, jc[12] = {0}, ji[2 * THB_INTR_STRIDE] = {0}, jp[8] = {0};
+    const bool good = ba.EvalObsAmbient(ba.x, i, true, r, jc, ji, jp);
+    if (ok) ok[i] = good ? 1 : 0;
+    if (!good) { std::memset(r, 0, sizeof(r)); std::memset(jc, 0, sizeof(jc)); std::memset(ji, 0, sizeof(ji)); std::memset(jp, 0, sizeof(jp)); }
+    if (residuals) std::memcpy(residuals + 2 * (size_t)i, r, sizeof(r));
+    if (jac_cam) std::memcpy(jac_cam + 12 * (size_t)i, jc, sizeof(jc));
+    if (jac_intr) std::memcpy(jac_intr + 2 * THB_INTR_STRIDE * (size_t)i, ji, sizeof(ji));
+    if (jac_pt) std::memcpy(jac_pt + 8 * (size_t)i, jp, sizeof(jp));
+  }
+  return THB_OK;
+}
+
+// Cost 0.5*sum rho(|r|^2) at the given parameters (all blocks, fixed ones included).
+int oracle_ba_cost(const ThbBaProblem* p, const ThbBaOptions* o, double* cost) {
+  if (!p || !o || !cost) return THB_E_INVALID_ARGUMENT;
+  oracle::BaOracle ba(*p, *o);
+  const int rc = ba.Init();
+  if (rc != THB_OK) return rc;
+  double c0 = 0.0, c1 = 0.0;
+  const bool ok0 = ba.Evaluate(ba.x, false, &c0, false);
+  const bool ok1 = ba.Evaluate(ba.x, false, &c1, true);
+  *cost = c0 + c1;
+  return ok0 && ok1 ? THB_OK : THB_E_NUMERICAL;
+}
+
+// SphereManifold<4> helpers exposed for unit tests.
+void oracle_sphere_plus(const double* x, const double* d, double* out) { oracle::SpherePlus(x, d, out); }
+void oracle_sphere_plus_jacobian(const double* x, double* J) { oracle::SpherePlusJacobian(x, J); }
+
+}  // extern "C"

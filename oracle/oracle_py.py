@@ -1,0 +1,66 @@
+"""ctypes loader of oracle/_build/liboracle.so (ORACLE — test infrastructure only)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pytheiasfm_b200 import capi
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", _DIR, "-s"] + (["-B"] if force else []))
+    return LIB_PATH
+
+
+def load():
+    global _lib
+    if _lib is None:
+        build()
+        lib = C.CDLL(LIB_PATH)
+        lib.oracle_ba_default_options.argtypes = [C.POINTER(capi.ThbBaOptions)]
+        lib.oracle_ba_solve.argtypes = [C.POINTER(capi.ThbBaProblem), C.POINTER(capi.ThbBaOptions), C.POINTER(capi.ThbBaSummary)]
+        lib.oracle_ba_evaluate.argtypes = [C.POINTER(capi.ThbBaProblem)] + [C.c_void_p] * 5
+        lib.oracle_ba_cost.argtypes = [C.POINTER(capi.ThbBaProblem), C.POINTER(capi.ThbBaOptions), C.POINTER(C.c_double)]
+        lib.oracle_sphere_plus.argtypes = [C.c_void_p] * 3
+        lib.oracle_sphere_plus_jacobian.argtypes = [C.c_void_p] * 2
+        _lib = lib
+    return _lib
+
+
+def default_options():
+    o = capi.ThbBaOptions()
+    load().oracle_ba_default_options(C.byref(o))
+    return o
+
+
+def ba_solve(prob, opts):
+    """Runs the oracle LM on a HostBaProblem IN PLACE; returns the summary dict."""
+    s = capi.ThbBaSummary()
+    p = prob.struct()
+    rc = load().oracle_ba_solve(C.byref(p), C.byref(opts), C.byref(s))
+    d = s.as_dict()
+    d["rc"] = rc
+    return d
+
+
+def ba_evaluate(prob):
+    n = prob.num_observations
+    r = np.zeros((n, 2)); jc = np.zeros((n, 2, 6)); ji = np.zeros((n, 2, capi.THB_INTR_STRIDE)); jp = np.zeros((n, 2, 4))
+    ok = np.zeros(n, np.uint8)
+    p = prob.struct()
+    rc = load().oracle_ba_evaluate(C.byref(p), *[a.ctypes.data_as(C.c_void_p) for a in (r, jc, ji, jp, ok)])
+    assert rc == 0, rc
+    return r, jc, ji, jp, ok
+
+
+def ba_cost(prob, opts):
+    c = C.c_double(0.0)
+    p = prob.struct()
+    rc = load().oracle_ba_cost(C.byref(p), C.byref(opts), C.byref(c))
+    return rc, c.value

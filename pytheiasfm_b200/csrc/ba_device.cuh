@@ -1,0 +1,282 @@
+// Device data model and the per-observation residual/Jacobian evaluation shared by the BA kernels.
+//
+// Layout in HBM (all FP64 / int32, structure-of-arrays):
+//   parameters        cam[nc][6]   camd[nc][CAMD] (rotation matrix + SO(3) left Jacobian, derived)
+//                     intr[ng][10] pts[np][4]
+//   observations      stored twice, point-major (Schur order) and camera-major (camera-block
+//                     order): cam/pt index, xy (double2), sqrt_info (double2)
+//   Jacobian planes   r[2][no], Jc[12][no], Jp[2*PD][no], Ji[2*NK][no] — plane k of block B is
+//                     the contiguous array B[k*no .. (k+1)*no): every warp store/load is one
+//                     fully coalesced 256-byte segment.
+#ifndef THB_BA_DEVICE_CUH_
+#define THB_BA_DEVICE_CUH_
+
+#include "camera_models.cuh"
+
+namespace thb {
+
+constexpr int CAMD = 20;  // R[9] (row-major), M[9] (row-major), small-angle flag, pad
+
+struct BaState {  // one set of parameter values (current x, or the candidate)
+  double* cam;
+  double* camd;
+  double* intr;
+  double* pts;
+};
+
+struct ObsSoA {  // observations in one ordering
+  const int* cam;
+  const int* pt;
+  const double2* xy;
+  const double2* si;
+};
+
+struct BaConst {  // problem structure, constant over the solve
+  int nc, ng, np, no;
+  const int* cam_group;     // [nc]
+  const int* intr_model;    // [ng]
+  const uint8_t* cam_const; // [nc] THB_CAM_CONST_* (never null on device)
+  const uint16_t* intr_const; // [ng] bit k => constant
+  const uint8_t* pt_const;  // [np]
+  const int* intr_slot;     // [ng] index of the group among variable-intrinsics groups, or -1
+  int loss_type;
+  double loss_width;
+};
+
+// ceres::LossFunction::Evaluate for create_loss_function.cc:44-76 (formulas: ceres/loss_function.cc,
+// external; TRUNCATED: loss_functions.cc:40-44). rho = {rho(s), rho'(s), rho''(s)}.
+__device__ __forceinline__ void eval_loss(int type, double a, double s, double rho[3]) {
+  const double b = a * a;
+  switch (type) {
+    case THB_LOSS_HUBER:
+      if (s > b) {
+        const double r = sqrt(s);
+        rho[0] = 2.0 * a * r - b; rho[1] = fmax(2.2250738585072014e-308, a / r); rho[2] = -rho[1] / (2.0 * s);
+      } else { rho[0] = s; rho[1] = 1.0; rho[2] = 0.0; }
+      return;
+    case THB_LOSS_SOFTLONE: {
+      const double c = 1.0 / b, sum = 1.0 + s * c, tmp = sqrt(sum);
+      rho[0] = 2.0 * b * (tmp - 1.0); rho[1] = fmax(2.2250738585072014e-308, 1.0 / tmp); rho[2] = -(c * rho[1]) / (2.0 * sum);
+      return; }
+    case THB_LOSS_CAUCHY: {
+      const double c = 1.0 / b, sum = 1.0 + s * c, inv = 1.0 / sum;
+      rho[0] = b * log(sum); rho[1] = fmax(2.2250738585072014e-308, inv); rho[2] = -c * (inv * inv);
+      return; }
+    case THB_LOSS_ARCTAN: {
+      const double bb = 1.0 / b, sum = 1.0 + s * s * bb, inv = 1.0 / sum;
+      rho[0] = a * atan2(s, a); rho[1] = fmax(2.2250738585072014e-308, inv); rho[2] = -2.0 * s * bb * (inv * inv);
+      return; }
+    case THB_LOSS_TUKEY:
+      if (s <= b) {
+        const double value = 1.0 - s / b, value_sq = value * value;
+        rho[0] = b / 3.0 * (1.0 - value_sq * value); rho[1] = value_sq; rho[2] = -2.0 / b * value;
+      } else { rho[0] = b / 3.0; rho[1] = 0.0; rho[2] = 0.0; }
+      return;
+    case THB_LOSS_TRUNCATED:
+      rho[0] = fmin(s, b); rho[1] = s < b ? 1.0 : 0.0; rho[2] = 0.0;
+      return;
+    default:
+      rho[0] = s; rho[1] = 1.0; rho[2] = 0.0;
+  }
+}
+
+// Householder vector of the homogeneous point (ceres SphereManifold<4>, bundle_adjuster.cc:538-545):
+// H = I - beta v v^T maps x/|x| to e4, v[3] = 1.
+__device__ __forceinline__ void householder4(const double x[4], double v[3], double* beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1] + x[2] * x[2];
+  v[0] = x[0]; v[1] = x[1]; v[2] = x[2];
+  *beta = 0.0;
+  if (sigma <= 2.220446049250313e-16) {
+    if (x[3] < 0.0) *beta = 2.0;
+    return;
+  }
+  const double mu = sqrt(x[3] * x[3] + sigma);
+  const double vp = (x[3] <= 0.0) ? (x[3] - mu) : (-sigma / (x[3] + mu));
+  *beta = 2.0 * vp * vp / (sigma + vp * vp);
+  const double ivp = 1.0 / vp;
+  v[0] *= ivp; v[1] *= ivp; v[2] *= ivp;
+}
+
+// Residual only: ReprojectionError<Model>::operator() (reprojection_error.h:49-114).
+template <int MODEL>
+__device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S, int c, int p, double2 xy,
+                                              double2 si, double r[2]) {
+  const double* cam = S.cam + (size_t)c * 6;
+  const double* cd = S.camd + (size_t)c * CAMD;
+  const double4 X = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
+  const double ax = X.x - X.w * cam[0], ay = X.y - X.w * cam[1], az = X.z - X.w * cam[2];
+  if (ax * ax + ay * ay + az * az < 1e-8) return false;
+  double pc[3];
+  pc[0] = cd[0] * ax + cd[1] * ay + cd[2] * az;
+  pc[1] = cd[3] * ax + cd[4] * ay + cd[5] * az;
+  pc[2] = cd[6] * ax + cd[7] * ay + cd[8] * az;
+  const int g = K.cam_group[c];
+  double pix[2];
+  if (!project<MODEL, double, double>(K.intr_model[g], S.intr + (size_t)g * KS, pc, pix)) return false;
+  r[0] = si.x * (pix[0] - xy.x);
+  r[1] = si.y * (pix[1] - xy.y);
+  return true;
+}
+
+// Residual + tangent-space Jacobian blocks of one observation, robustified (ceres Corrector) and
+// column-scaled (Jacobi scaling): what ProgramEvaluator hands to the linear solver.
+//   r[2]; jc[2][6] (position | angle-axis); jp[2][PD]; ji[2][NK] (only NK > 0)
+//   *half_rho = 0.5*rho(|r|^2) (cost contribution)
+// cs/ps/is: column scales of the camera, point and intrinsics blocks (may be null => 1).
+template <int MODEL, int PD, int NK>
+__device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int c, int p, double2 xy, double2 si,
+                                         const double* cs, const double* ps, const double* is, double r[2],
+                                         double jc[12], double jp[2 * PD], double* ji, double* half_rho) {
+  constexpr int ND = 3 + NK;
+  typedef Dual<ND> D;
+  const double* cam = S.cam + (size_t)c * 6;
+  const double* cd = S.camd + (size_t)c * CAMD;
+  const double4 X4 = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
+  const double X[4] = {X4.x, X4.y, X4.z, X4.w};
+  const double C[3] = {cam[0], cam[1], cam[2]};
+  const double adj[3] = {X[0] - X[3] * C[0], X[1] - X[3] * C[1], X[2] - X[3] * C[2]};
+  if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
+  double R[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) R[k] = cd[k];
+  double pc[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pc[a] = R[3 * a] * adj[0] + R[3 * a + 1] * adj[1] + R[3 * a + 2] * adj[2];
+
+  const int g = K.cam_group[c];
+  const int model = MODEL >= 0 ? MODEL : K.intr_model[g];
+  const double* Kp = S.intr + (size_t)g * KS;
+  D pd[3], pix[2];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) pd[a] = seed<ND>(pc[a], a);
+  bool ok;
+  if (NK > 0) {
+    D Kd[NK > 0 ? NK : 1];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) Kd[k] = seed<ND>(k < KS ? Kp[k] : 0.0, 3 + k);
+    ok = project<MODEL, D, D>(model, Kd, pd, pix);
+  } else {
+    ok = project<MODEL, double, D>(model, Kp, pd, pix);
+  }
+  if (!ok) return false;
+  r[0] = si.x * (pix[0].a - xy.x);
+  r[1] = si.y * (pix[1].a - xy.y);
+  // A = sqrt_info * dpix/dp (2x3)
+  double A[6];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { A[k] = si.x * pix[0].v[k]; A[3 + k] = si.y * pix[1].v[k]; }
+  // AR = A * R (2x3): d r / d adj
+  double AR[6];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) AR[3 * a + k] = A[3 * a] * R[k] + A[3 * a + 1] * R[3 + k] + A[3 * a + 2] * R[6 + k];
+  const uint8_t cconst = K.cam_const[c];
+  // d r / d C = -w * AR
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) jc[6 * a + k] = (cconst & THB_CAM_CONST_POSITION) ? 0.0 : -X[3] * AR[3 * a + k];
+  // d r / d aa = A * (-[q]x M): q = R adj and M = left Jacobian of SO(3); in Ceres' small-angle
+  // branch (R = I + [aa]x) q = adj and M = I.
+  {
+    const bool small = cd[18] != 0.0;
+    const double q0 = small ? adj[0] : pc[0], q1 = small ? adj[1] : pc[1], q2 = small ? adj[2] : pc[2];
+    // G = A * (-[q]x): row a: -(A_a x q)^T ... (A_a^T [q]x)_k = (q x A_a)_k ; so -A_a [q]x = (A_a x q)... computed explicitly
+    double G[6];
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const double a0 = A[3 * a], a1 = A[3 * a + 1], a2 = A[3 * a + 2];
+      // row vector a^T * (-[q]x), with [q]x = [[0,-q2,q1],[q2,0,-q0],[-q1,q0,0]]
+      G[3 * a + 0] = -(a1 * q2 - a2 * q1);
+      G[3 * a + 1] = -(a2 * q0 - a0 * q2);
+      G[3 * a + 2] = -(a0 * q1 - a1 * q0);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        jc[6 * a + 3 + k] = (cconst & THB_CAM_CONST_ORIENTATION)
+                                ? 0.0
+                                : G[3 * a] * cd[9 + k] + G[3 * a + 1] * cd[12 + k] + G[3 * a + 2] * cd[15 + k];
+  }
+  // d r / d X (2x4) = [AR | -AR*C], then the tangent block
+  const bool pconst = K.pt_const[p] != 0;
+  if (PD == 3) {
+    double v[3], beta;
+    householder4(X, v, &beta);
+    const double nx = sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2] + X[3] * X[3]);
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      const double jw = -(AR[3 * a] * C[0] + AR[3 * a + 1] * C[1] + AR[3 * a + 2] * C[2]);
+      const double jv = AR[3 * a] * v[0] + AR[3 * a + 1] * v[1] + AR[3 * a + 2] * v[2] + jw;  // J_X . v (v[3]=1)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) jp[PD * a + k] = pconst ? 0.0 : nx * (AR[3 * a + k] - beta * v[k] * jv);
+    }
+  } else {
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) jp[PD * a + k] = pconst ? 0.0 : AR[3 * a + k];
+      jp[PD * a + 3] = pconst ? 0.0 : -(AR[3 * a] * C[0] + AR[3 * a + 1] * C[1] + AR[3 * a + 2] * C[2]);
+    }
+  }
+  if (NK > 0) {
+    const uint16_t icm = K.intr_const[g];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const bool kc = (icm >> k) & 1;
+      ji[k] = kc ? 0.0 : si.x * pix[0].v[3 + k];
+      ji[NK + k] = kc ? 0.0 : si.y * pix[1].v[3 + k];
+    }
+  }
+  // loss: cost and Corrector (ceres/corrector.cc, external)
+  const double sq = r[0] * r[0] + r[1] * r[1];
+  double rs = 1.0, js = 1.0, asn = 0.0;
+  if (K.loss_type != THB_LOSS_TRIVIAL) {
+    double rho[3];
+    eval_loss(K.loss_type, K.loss_width, sq, rho);
+    *half_rho = 0.5 * rho[0];
+    js = sqrt(rho[1]);
+    if (sq == 0.0 || rho[2] <= 0.0) {
+      rs = js;
+    } else {
+      const double Dd = 1.0 + 2.0 * sq * rho[2] / rho[1];
+      const double alpha = 1.0 - sqrt(Dd);
+      rs = js / (1.0 - alpha);
+      asn = alpha / sq;
+    }
+  } else {
+    *half_rho = 0.5 * sq;
+  }
+  // correct + scale columns
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    double j0 = jc[k], j1 = jc[6 + k];
+    if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
+    const double s = js * (cs ? cs[(size_t)c * 6 + k] : 1.0);
+    jc[k] = j0 * s; jc[6 + k] = j1 * s;
+  }
+#pragma unroll
+  for (int k = 0; k < PD; ++k) {
+    double j0 = jp[k], j1 = jp[PD + k];
+    if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
+    const double s = js * (ps ? ps[(size_t)p * PD + k] : 1.0);
+    jp[k] = j0 * s; jp[PD + k] = j1 * s;
+  }
+  if (NK > 0) {
+    const int slot = K.intr_slot[g];
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      double j0 = ji[k], j1 = ji[NK + k];
+      if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
+      const double s = js * ((is && slot >= 0) ? is[(size_t)slot * NK + k] : 1.0);
+      ji[k] = slot >= 0 ? j0 * s : 0.0; ji[NK + k] = slot >= 0 ? j1 * s : 0.0;
+    }
+  }
+  r[0] *= rs; r[1] *= rs;
+  return true;
+}
+
+}  // namespace thb
+#endif  // THB_BA_DEVICE_CUH_

@@ -1,0 +1,556 @@
+// BA kernels K1..K5 (see DESIGN.md for the per-kernel roofline and data layout).
+#ifndef THB_BA_KERNELS_CUH_
+#define THB_BA_KERNELS_CUH_
+
+#include "ba_device.cuh"
+
+namespace thb {
+
+// indices into the per-iteration device scalar block
+enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_MCC = 2, SC_STEP2 = 3, SC_XNEW2 = 4, SC_GRADMAX = 5, SC_COUNT = 8 };
+enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 };
+
+// ---------------------------------------------------------------------------------------------
+// Per-camera derived quantities: rotation matrix (ceres::AngleAxisRotatePoint semantics, incl. the
+// first-order branch for theta^2 <= eps) and the SO(3) left Jacobian used for d(R v)/d(aa).
+__global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const double wx = cam[6 * c + 3], wy = cam[6 * c + 4], wz = cam[6 * c + 5];
+  double* o = camd + (size_t)c * CAMD;
+  const double th2 = wx * wx + wy * wy + wz * wz;
+  if (th2 > 2.220446049250313e-16) {
+    const double th = sqrt(th2);
+    double s, co;
+    sincos(th, &s, &co);
+    const double it = 1.0 / th;
+    const double ux = wx * it, uy = wy * it, uz = wz * it;
+    const double oc = 1.0 - co;
+    o[0] = co + oc * ux * ux;      o[1] = oc * ux * uy - s * uz;  o[2] = oc * ux * uz + s * uy;
+    o[3] = oc * ux * uy + s * uz;  o[4] = co + oc * uy * uy;      o[5] = oc * uy * uz - s * ux;
+    o[6] = oc * ux * uz - s * uy;  o[7] = oc * uy * uz + s * ux;  o[8] = co + oc * uz * uz;
+    // left Jacobian J_l = I + A [w]x + B [w]x^2, A = (1-cos)/th^2, B = (th - sin)/th^3
+    double A, B;
+    if (th < 1e-2) {
+      A = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
+      B = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0;
+    } else {
+      const double sh = sin(0.5 * th);
+      A = 2.0 * sh * sh / th2;
+      B = (th - s) / (th2 * th);
+    }
+    // [w]x^2 = w w^T - th2 I
+    o[9]  = 1.0 + B * (wx * wx - th2); o[10] = -A * wz + B * wx * wy;     o[11] = A * wy + B * wx * wz;
+    o[12] = A * wz + B * wx * wy;      o[13] = 1.0 + B * (wy * wy - th2); o[14] = -A * wx + B * wy * wz;
+    o[15] = -A * wy + B * wx * wz;     o[16] = A * wx + B * wy * wz;      o[17] = 1.0 + B * (wz * wz - th2);
+    o[18] = 0.0;
+  } else {
+    o[0] = 1.0; o[1] = -wz; o[2] = wy;
+    o[3] = wz;  o[4] = 1.0; o[5] = -wx;
+    o[6] = -wy; o[7] = wx;  o[8] = 1.0;
+    o[9] = 1.0; o[10] = 0.0; o[11] = 0.0; o[12] = 0.0; o[13] = 1.0; o[14] = 0.0; o[15] = 0.0; o[16] = 0.0; o[17] = 1.0;
+    o[18] = 1.0;
+  }
+  o[19] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: residual + tangent-space Jacobian of every observation, point-major, into the plane layout.
+// One thread per observation. HBM-bound: reads 40 B/obs (+ L2-resident parameter gathers), writes
+// (2 + 12 + 2*PD + 2*NK) * 8 B/obs as fully coalesced plane stores.
+template <int MODEL, int PD, int NK>
+__global__ void __launch_bounds__(256) k_jacobian(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
+                                                  const double* __restrict__ ps, const double* __restrict__ is,
+                                                  double* __restrict__ r_pl, double* __restrict__ jc_pl,
+                                                  double* __restrict__ jp_pl, double* __restrict__ ji_pl,
+                                                  double* __restrict__ scal, int* __restrict__ iflag) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double hc = 0.0;
+  if (i < K.no) {
+    const int c = O.cam[i], p = O.pt[i];
+    double r[2], jc[12], jp[2 * PD], ji[NK > 0 ? 2 * NK : 1];
+    const bool ok = eval_obs<MODEL, PD, NK>(K, S, c, p, O.xy[i], O.si[i], cs, ps, is, r, jc, jp, ji, &hc);
+    if (!ok) {
+      atomicOr(iflag + FL_EVAL_X, 1);
+      hc = 0.0; r[0] = r[1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) jc[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2 * PD; ++k) jp[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2 * NK; ++k) ji[k] = 0.0;
+    }
+    const size_t no = K.no;
+    r_pl[i] = r[0]; r_pl[no + i] = r[1];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) jc_pl[k * no + i] = jc[k];
+#pragma unroll
+    for (int k = 0; k < 2 * PD; ++k) jp_pl[k * no + i] = jp[k];
+#pragma unroll
+    for (int k = 0; k < 2 * NK; ++k) ji_pl[k * no + i] = ji[k];
+  }
+  hc = block_sum(hc, red);
+  if (threadIdx.x == 0) atomicAdd(scal + SC_COST_X, hc);
+}
+
+// Cost only (candidate evaluation): 0.5 * sum rho(|r|^2).
+template <int MODEL>
+__global__ void __launch_bounds__(256) k_cost(BaConst K, BaState S, ObsSoA O, double* __restrict__ scal, int slot,
+                                              int* __restrict__ iflag, int flag_slot) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double hc = 0.0;
+  if (i < K.no) {
+    double r[2];
+    if (eval_residual<MODEL>(K, S, O.cam[i], O.pt[i], O.xy[i], O.si[i], r)) {
+      const double sq = r[0] * r[0] + r[1] * r[1];
+      if (K.loss_type == THB_LOSS_TRIVIAL) hc = 0.5 * sq;
+      else { double rho[3]; eval_loss(K.loss_type, K.loss_width, sq, rho); hc = 0.5 * rho[0]; }
+    } else {
+      atomicOr(iflag + flag_slot, 1);
+    }
+  }
+  hc = block_sum(hc, red);
+  if (threadIdx.x == 0) atomicAdd(scal + slot, hc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small SPD inverse by Cholesky, N in {3,4}; returns false if not positive definite.
+template <int N>
+__device__ __forceinline__ bool spd_inverse(const double* A /*row-major NxN, lower used*/, double* Ainv) {
+  double L[N][N];
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * N + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[i][i] = sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  double Li[N][N];  // inverse of L (lower)
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    Li[j][j] = 1.0 / L[j][j];
+#pragma unroll
+    for (int r = j + 1; r < N; ++r) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = j; k < r; ++k) acc += L[r][k] * Li[k][j];
+      Li[r][j] = -acc / L[r][r];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j <= i; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = i; k < N; ++k) s += Li[k][i] * Li[k][j];
+      Ainv[i * N + j] = s; Ainv[j * N + i] = s;
+    }
+  return true;
+}
+
+// K2a: per point, V = sum Jp^T Jp (+ LM diagonal), g_p = sum Jp^T r, V^-1. One thread per point.
+template <int PD>
+__global__ void __launch_bounds__(128) k_point_pass(int np, int no, const int* __restrict__ pt_start,
+                                                    const double* __restrict__ r_pl, const double* __restrict__ jp_pl,
+                                                    double inv_radius, double min_diag, double max_diag,
+                                                    double* __restrict__ vinv, double* __restrict__ gp,
+                                                    double* __restrict__ pdiag, int* __restrict__ iflag) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  double V[PD * PD] = {}, g[PD] = {};
+  const int q0 = pt_start[p], q1 = pt_start[p + 1];
+  const size_t n = no;
+  for (int q = q0; q < q1; ++q) {
+    double j[2 * PD];
+#pragma unroll
+    for (int k = 0; k < 2 * PD; ++k) j[k] = jp_pl[k * n + q];
+    const double r0 = r_pl[q], r1 = r_pl[n + q];
+#pragma unroll
+    for (int a = 0; a < PD; ++a) {
+      g[a] += j[a] * r0 + j[PD + a] * r1;
+#pragma unroll
+      for (int b = 0; b <= a; ++b) V[a * PD + b] += j[a] * j[b] + j[PD + a] * j[PD + b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < PD; ++a) {
+    const double d = V[a * PD + a];
+    pdiag[(size_t)p * PD + a] = d;
+    V[a * PD + a] = d + fmin(fmax(d, min_diag), max_diag) * inv_radius;
+    gp[(size_t)p * PD + a] = g[a];
+  }
+  double Vi[PD * PD];
+  if (!spd_inverse<PD>(V, Vi)) {
+    atomicOr(iflag + FL_POINT, 1);
+#pragma unroll
+    for (int k = 0; k < PD * PD; ++k) Vi[k] = 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < PD * PD; ++k) vinv[(size_t)p * PD * PD + k] = Vi[k];
+}
+
+// K2b: per camera (camera-major observations, one CTA per camera): U_c = sum Jc^T Jc, b_c = sum Jc^T r,
+// minus the camera's own Schur terms T_i W_i^T and T_i g_p (W_i = Jc^T Jp, T_i = W_i V^-1); plus the LM
+// diagonal. Writes the diagonal 6x6 block of S (lower), the reduced rhs, the raw gradient block and the
+// raw diagonal. No atomics: the block reduction is deterministic.
+template <int MODEL, int PD>
+__global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O, const int* __restrict__ cam_start,
+                                                  const double* __restrict__ cs, const double* __restrict__ ps,
+                                                  const double* __restrict__ vinv, const double* __restrict__ gp,
+                                                  double inv_radius, double min_diag, double max_diag,
+                                                  double* __restrict__ Smat, int ld, double* __restrict__ rhs,
+                                                  double* __restrict__ braw, double* __restrict__ cdiag,
+                                                  int* __restrict__ iflag) {
+  constexpr int NA = 21 + 6 + 6;  // U_total(lower 21), raw b, schur-corrected b  (raw diag = separate 6)
+  __shared__ double red[4][NA + 6];
+  const int c = blockIdx.x;
+  double acc[NA + 6];
+#pragma unroll
+  for (int k = 0; k < NA + 6; ++k) acc[k] = 0.0;
+  for (int q = cam_start[c] + threadIdx.x; q < cam_start[c + 1]; q += blockDim.x) {
+    const int p = O.pt[q];
+    double r[2], jc[12], jp[2 * PD], hc;
+    if (!eval_obs<MODEL, PD, 0>(K, S, c, p, O.xy[q], O.si[q], cs, ps, nullptr, r, jc, jp, nullptr, &hc)) continue;
+    double Vi[PD * PD], g[PD];
+#pragma unroll
+    for (int k = 0; k < PD * PD; ++k) Vi[k] = vinv[(size_t)p * PD * PD + k];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) g[k] = gp[(size_t)p * PD + k];
+    double W[6][PD], T[6][PD];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int t = 0; t < PD; ++t) W[a][t] = jc[a] * jp[t] + jc[6 + a] * jp[PD + t];
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int t = 0; t < PD; ++t) {
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) v += W[a][u] * Vi[u * PD + t];
+        T[a][t] = v;
+      }
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) {
+        double v = jc[a] * jc[b] + jc[6 + a] * jc[6 + b];
+#pragma unroll
+        for (int t = 0; t < PD; ++t) v -= T[a][t] * W[b][t];
+        acc[k++] += v;
+      }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double br = jc[a] * r[0] + jc[6 + a] * r[1];
+      double bs = br;
+#pragma unroll
+      for (int t = 0; t < PD; ++t) bs -= T[a][t] * g[t];
+      acc[21 + a] += br;
+      acc[27 + a] += bs;
+      acc[33 + a] += jc[a] * jc[a] + jc[6 + a] * jc[6 + a];
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NA + 6; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NA + 6) {
+    const int k = threadIdx.x;
+    red[0][k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 21) {
+    int a = 0, k = threadIdx.x;
+    while (k > a) { k -= a + 1; ++a; }  // k-th lower entry -> (a, b=k)
+    const int b = k;
+    double v = red[0][threadIdx.x];
+    if (a == b) v += fmin(fmax(red[0][33 + a], min_diag), max_diag) * inv_radius;
+    Smat[(size_t)(6 * c + a) * ld + 6 * c + b] = v;
+  } else if (threadIdx.x >= 32 && threadIdx.x < 38) {
+    const int a = threadIdx.x - 32;
+    braw[6 * c + a] = red[0][21 + a];
+    rhs[6 * c + a] = red[0][27 + a];
+    cdiag[6 * c + a] = red[0][33 + a];
+  }
+}
+
+// K3: off-diagonal camera-camera blocks of the Schur complement, S[ci,cj] -= T_i W_j^T for every pair of
+// observations (i,j) of a point. Points are grouped on the host into chunks of <= CH observations; W and
+// T of a chunk are staged in shared memory, then the (pair, a, b) work items are spread over the CTA and
+// each issues one FP64 atomic (RED) into the lower triangle of S.
+template <int PD>
+__global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __restrict__ chunk_pt, const int* __restrict__ pt_start,
+                                                       const int* __restrict__ o_cam, const double* __restrict__ jc_pl,
+                                                       const double* __restrict__ jp_pl, const double* __restrict__ vinv,
+                                                       double* __restrict__ Smat, int ld) {
+  constexpr int CH = 64;
+  __shared__ double sW[CH][6 * PD];
+  __shared__ double sT[CH][6 * PD];
+  __shared__ int sC[CH];
+  const int p0 = chunk_pt[blockIdx.x], p1 = chunk_pt[blockIdx.x + 1];
+  const int q0 = pt_start[p0], q1 = pt_start[p1];
+  const int nq = q1 - q0;
+  const size_t n = no;
+  const bool staged = nq <= CH;
+  if (staged) {
+    for (int e = threadIdx.x; e < nq * 6; e += blockDim.x) {
+      const int ql = e / 6, a = e % 6, q = q0 + ql;
+      // point of q: chunk holds few points; find by scan
+      int p = p0;
+      while (pt_start[p + 1] <= q) ++p;
+      const double j0 = jc_pl[a * n + q], j1 = jc_pl[(6 + a) * n + q];
+      double Wr[PD];
+#pragma unroll
+      for (int t = 0; t < PD; ++t) Wr[t] = j0 * jp_pl[t * n + q] + j1 * jp_pl[(PD + t) * n + q];
+#pragma unroll
+      for (int t = 0; t < PD; ++t) {
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) v += Wr[u] * vinv[(size_t)p * PD * PD + u * PD + t];
+        sT[ql][a * PD + t] = v;
+        sW[ql][a * PD + t] = Wr[t];
+      }
+      if (a == 0) sC[ql] = o_cam[q];
+    }
+    __syncthreads();
+  }
+  for (int p = p0; p < p1; ++p) {
+    const int b0 = pt_start[p], np_obs = pt_start[p + 1] - b0;
+    const long long items = (long long)np_obs * (np_obs - 1) / 2 * 36;
+    for (long long e = threadIdx.x; e < items; e += blockDim.x) {
+      const int pair = (int)(e / 36), ab = (int)(e % 36), a = ab / 6, b = ab % 6;
+      // pair index -> (i, j), i < j, row-major over the strict upper triangle
+      const double m = 2.0 * np_obs - 1.0;
+      int i = (int)((m - sqrt(m * m - 8.0 * pair)) * 0.5);
+      while ((long long)(i + 1) * (2 * np_obs - i - 2) / 2 <= pair) ++i;
+      while ((long long)i * (2 * np_obs - i - 1) / 2 > pair) --i;
+      const int j = i + 1 + (pair - (int)((long long)i * (2 * np_obs - i - 1) / 2));
+      double v = 0.0;
+      int ci, cj;
+      if (staged) {
+        const int li = b0 - q0 + i, lj = b0 - q0 + j;
+#pragma unroll
+        for (int t = 0; t < PD; ++t) v += sT[li][a * PD + t] * sW[lj][b * PD + t];
+        ci = sC[li]; cj = sC[lj];
+      } else {
+        const int qi = b0 + i, qj = b0 + j;
+        const double i0 = jc_pl[a * n + qi], i1 = jc_pl[(6 + a) * n + qi];
+        const double k0 = jc_pl[b * n + qj], k1 = jc_pl[(6 + b) * n + qj];
+        double Wi[PD], Wj[PD];
+#pragma unroll
+        for (int t = 0; t < PD; ++t) {
+          Wi[t] = i0 * jp_pl[t * n + qi] + i1 * jp_pl[(PD + t) * n + qi];
+          Wj[t] = k0 * jp_pl[t * n + qj] + k1 * jp_pl[(PD + t) * n + qj];
+        }
+#pragma unroll
+        for (int t = 0; t < PD; ++t) {
+          double ti = 0.0;
+#pragma unroll
+          for (int u = 0; u < PD; ++u) ti += Wi[u] * vinv[(size_t)p * PD * PD + u * PD + t];
+          v += ti * Wj[t];
+        }
+        ci = o_cam[qi]; cj = o_cam[qj];
+      }
+      if (ci > cj) atomicAdd(&Smat[(size_t)(6 * ci + a) * ld + 6 * cj + b], -v);
+      else if (ci < cj) atomicAdd(&Smat[(size_t)(6 * cj + b) * ld + 6 * ci + a], -v);
+      else atomicAdd(&Smat[(size_t)(6 * ci + max(a, b)) * ld + 6 * ci + min(a, b)], a == b ? -2.0 * v : -v);
+    }
+  }
+}
+
+// K5a: back-substitution per point, y_p = V^-1 (g_p - sum_i W_i^T y_ci), and the model cost change
+// -(J step)^T (r + J step / 2) with step = -y. One thread per point.
+template <int PD>
+__global__ void __launch_bounds__(128) k_backsub(int np, int no, const int* __restrict__ pt_start, const int* __restrict__ o_cam,
+                                                 const double* __restrict__ r_pl, const double* __restrict__ jc_pl,
+                                                 const double* __restrict__ jp_pl, const double* __restrict__ vinv,
+                                                 const double* __restrict__ gp, const double* __restrict__ yred,
+                                                 double* __restrict__ yp, double* __restrict__ scal) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double mcc = 0.0;
+  if (p < np) {
+    const size_t n = no;
+    const int q0 = pt_start[p], q1 = pt_start[p + 1];
+    double b[PD];
+#pragma unroll
+    for (int a = 0; a < PD; ++a) b[a] = gp[(size_t)p * PD + a];
+    for (int q = q0; q < q1; ++q) {
+      const int c = o_cam[q];
+      double jy0 = 0.0, jy1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double y = yred[6 * c + k]; jy0 += jc_pl[k * n + q] * y; jy1 += jc_pl[(6 + k) * n + q] * y; }
+#pragma unroll
+      for (int a = 0; a < PD; ++a) b[a] -= jp_pl[a * n + q] * jy0 + jp_pl[(PD + a) * n + q] * jy1;
+    }
+    double y[PD];
+#pragma unroll
+    for (int a = 0; a < PD; ++a) {
+      double v = 0.0;
+#pragma unroll
+      for (int u = 0; u < PD; ++u) v += vinv[(size_t)p * PD * PD + a * PD + u] * b[u];
+      y[a] = v;
+      yp[(size_t)p * PD + a] = v;
+    }
+    for (int q = q0; q < q1; ++q) {
+      const int c = o_cam[q];
+      double m0 = 0.0, m1 = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { const double yc = yred[6 * c + k]; m0 += jc_pl[k * n + q] * yc; m1 += jc_pl[(6 + k) * n + q] * yc; }
+#pragma unroll
+      for (int a = 0; a < PD; ++a) { m0 += jp_pl[a * n + q] * y[a]; m1 += jp_pl[(PD + a) * n + q] * y[a]; }
+      m0 = -m0; m1 = -m1;  // J * step, step = -y
+      mcc -= m0 * (r_pl[q] + 0.5 * m0) + m1 * (r_pl[n + q] + 0.5 * m1);
+    }
+  }
+  mcc = block_sum(mcc, red);
+  if (threadIdx.x == 0) atomicAdd(scal + SC_MCC, mcc);
+}
+
+// K5b: candidate = Plus(x, delta), delta = -scale * y. Cameras: SubsetManifold semantics (constant
+// coordinates have zero Jacobian columns, hence y = 0). Accumulates |x - x_new|^2 and |x_new|^2 over the
+// non-constant blocks (TrustRegionMinimizer::ParameterToleranceReached).
+__global__ void k_update_cams(int nc, const uint8_t* __restrict__ cam_const,
+                              const double* __restrict__ cam, const double* __restrict__ yred,
+                              const double* __restrict__ cs, double* __restrict__ cam_new, double* __restrict__ scal) {
+  __shared__ double red[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double s2 = 0.0, x2 = 0.0;
+  if (c < nc) {
+    const bool variable = cam_const[c] != THB_CAM_CONST_ALL;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double o = cam[6 * c + k];
+      const double d = variable ? -yred[6 * c + k] * cs[6 * c + k] : 0.0;
+      const double v = o + d;
+      cam_new[6 * c + k] = v;
+      if (variable) { s2 += (v - o) * (v - o); x2 += v * v; }
+    }
+  }
+  s2 = block_sum(s2, red);
+  x2 = block_sum(x2, red);
+  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); }
+}
+
+template <int PD>
+__global__ void k_update_pts(int np, const uint8_t* __restrict__ pt_const, const double* __restrict__ pts,
+                             const double* __restrict__ yp, const double* __restrict__ ps,
+                             double* __restrict__ pts_new, double* __restrict__ scal) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double s2 = 0.0, x2 = 0.0;
+  if (p < np) {
+    const double4 X4 = *reinterpret_cast<const double4*>(pts + (size_t)p * 4);
+    const double x[4] = {X4.x, X4.y, X4.z, X4.w};
+    double o[4] = {x[0], x[1], x[2], x[3]};
+    const bool variable = pt_const[p] == 0;
+    if (variable) {
+      double d[PD];
+#pragma unroll
+      for (int k = 0; k < PD; ++k) d[k] = -yp[(size_t)p * PD + k] * ps[(size_t)p * PD + k];
+      if (PD == 3) {
+        // ceres SphereManifold<4>::Plus
+        const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        if (nd != 0.0) {
+          double v[3], beta;
+          householder4(x, v, &beta);
+          const double sbd = sin(nd) / nd;
+          const double y[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cos(nd)};
+          const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + y[3];
+          const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+          o[0] = nx * (y[0] - v[0] * (beta * vty));
+          o[1] = nx * (y[1] - v[1] * (beta * vty));
+          o[2] = nx * (y[2] - v[2] * (beta * vty));
+          o[3] = nx * (y[3] - (beta * vty));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = x[k] + d[k < PD ? k : 0];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { s2 += (o[k] - x[k]) * (o[k] - x[k]); x2 += o[k] * o[k]; }
+    }
+    *reinterpret_cast<double4*>(pts_new + (size_t)p * 4) = make_double4(o[0], o[1], o[2], o[3]);
+  }
+  s2 = block_sum(s2, red);
+  x2 = block_sum(x2, red);
+  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); }
+}
+
+// max-norm of the (unscaled) gradient: g = (Js^T r) / scale
+__global__ void k_grad_max(int n, const double* __restrict__ b, const double* __restrict__ scale, double* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (i < n) v = fabs(b[i] / scale[i]);
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0 && v > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(scal + SC_GRADMAX), (unsigned long long)__double_as_longlong(v));
+}
+
+// Jacobi scaling: scale = 1 / (1 + sqrt(column norm^2))
+__global__ void k_make_scale(int n, const double* __restrict__ diag, double* __restrict__ scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) scale[i] = 1.0 / (1.0 + sqrt(diag[i]));
+}
+
+__global__ void k_fill(int n, double* __restrict__ a, double v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+// x_norm^2 over the non-constant blocks of a state
+__global__ void k_xnorm(int nc, int np, const uint8_t* __restrict__ cam_const,
+                        const uint8_t* __restrict__ pt_const, const double* __restrict__ cam, const double* __restrict__ pts,
+                        double* __restrict__ out) {
+  __shared__ double red[32];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
+  if (i < nc) {
+    if (cam_const[i] != THB_CAM_CONST_ALL)
+      for (int k = 0; k < 6; ++k) s += cam[6 * i + k] * cam[6 * i + k];
+  } else if (i - nc < np) {
+    const int p = i - nc;
+    if (!pt_const[p]) for (int k = 0; k < 4; ++k) s += pts[(size_t)p * 4 + k] * pts[(size_t)p * 4 + k];
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// Ambient (no manifold, no loss) evaluation in the caller's observation order: thb_ba_evaluate.
+__global__ void k_eval_ambient(BaConst K, BaState S, ObsSoA O, double* __restrict__ res, double* __restrict__ jcam,
+                               double* __restrict__ jintr, double* __restrict__ jpt, uint8_t* __restrict__ okv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K.no) return;
+  double r[2], jc[12], jp[8], ji[18], hc;
+  const bool ok = eval_obs<-1, 4, 9>(K, S, O.cam[i], O.pt[i], O.xy[i], O.si[i], nullptr, nullptr, nullptr, r, jc, jp, ji, &hc);
+  if (okv) okv[i] = ok ? 1 : 0;
+  if (!ok) {
+    r[0] = r[1] = 0.0;
+    for (int k = 0; k < 12; ++k) jc[k] = 0.0;
+    for (int k = 0; k < 8; ++k) jp[k] = 0.0;
+    for (int k = 0; k < 18; ++k) ji[k] = 0.0;
+  }
+  if (res) { res[2 * (size_t)i] = r[0]; res[2 * (size_t)i + 1] = r[1]; }
+  if (jcam) for (int k = 0; k < 12; ++k) jcam[12 * (size_t)i + k] = jc[k];
+  if (jpt) for (int k = 0; k < 8; ++k) jpt[8 * (size_t)i + k] = jp[k];
+  if (jintr)
+    for (int a = 0; a < 2; ++a)
+      for (int k = 0; k < KS; ++k) jintr[(2 * (size_t)i + a) * KS + k] = k < 9 ? ji[a * 9 + k] : 0.0;
+}
+
+}  // namespace thb
+#endif  // THB_BA_KERNELS_CUH_

@@ -1,0 +1,732 @@
+// Host side of the BA hot path: the C-ABI of include/theia_b200.h over the kernels of ba_kernels.cuh.
+//
+// Stands behind theia::BundleAdjuster::Optimize -> ceres::Solve
+// (/root/reference/src/theia/sfm/bundle_adjustment/bundle_adjuster.cc:315-355). The trust-region policy
+// (Levenberg-Marquardt, Jacobi scaling, step acceptance, termination tests) restates what ceres::Solve
+// does with the options Theia passes (bundle_adjuster.cc:63-89).
+// The control loop runs on the host; every O(observations) operation is a kernel on the caller's stream.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+
+#include "ba_kernels.cuh"
+#include "dense_chol.cuh"
+
+namespace thb {
+namespace {
+
+thread_local std::string g_last_error;
+
+template <typename T>
+int DevAlloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  THB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return THB_OK;
+}
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+struct PhaseTimer {  // CUDA-event timing of one phase on the solve stream
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  cudaStream_t st = nullptr;
+  size_t used = 0;
+  void Begin() {
+    if (used == ev.size()) {
+      cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); ev.emplace_back(a, b);
+    }
+    cudaEventRecord(ev[used].first, st);
+  }
+  void End() { cudaEventRecord(ev[used].second, st); ++used; }
+  double CollectMs() {  // call after a stream sync
+    double ms = 0.0;
+    for (size_t i = 0; i < used; ++i) { float t = 0.f; cudaEventElapsedTime(&t, ev[i].first, ev[i].second); ms += t; }
+    used = 0;
+    return ms;
+  }
+  void Free() { for (auto& e : ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); } ev.clear(); }
+};
+
+}  // namespace
+
+void SetLastError(const std::string& s) { g_last_error = s; }
+const char* GetLastError() { return g_last_error.c_str(); }
+
+}  // namespace thb
+
+using namespace thb;
+
+struct ThbBaSession {
+  ThbBaProblem prob;
+  ThbBaOptions opt;
+  cudaStream_t st = nullptr;
+  int nc = 0, ng = 0, np = 0, no = 0;
+  int PD = 3, model = -1, n_red = 0;
+  bool red_variable = false;  // any non-constant camera coordinate
+  bool any_variable = false;
+  BaConst K{};
+  BaState X{}, Xc{};
+  ObsSoA Op{}, Oc{};
+  // owned device memory
+  int *d_cam_group = nullptr, *d_intr_model = nullptr, *d_intr_slot = nullptr;
+  uint8_t *d_cam_const = nullptr, *d_pt_const = nullptr;
+  uint16_t* d_intr_const = nullptr;
+  int *d_op_cam = nullptr, *d_op_pt = nullptr, *d_oc_cam = nullptr, *d_oc_pt = nullptr;
+  double2 *d_op_xy = nullptr, *d_op_si = nullptr, *d_oc_xy = nullptr, *d_oc_si = nullptr;
+  int *d_pt_start = nullptr, *d_cam_start = nullptr, *d_chunk_pt = nullptr;
+  int nchunks = 0;
+  double *d_r = nullptr, *d_jc = nullptr, *d_jp = nullptr;
+  double *d_cs = nullptr, *d_ps = nullptr;
+  double *d_vinv = nullptr, *d_gp = nullptr, *d_pdiag = nullptr, *d_braw = nullptr, *d_cdiag = nullptr, *d_yp = nullptr;
+  double* d_scal = nullptr;
+  int* d_flag = nullptr;
+  double* h_scal = nullptr;  // pinned
+  int* h_flag = nullptr;     // pinned
+  void* d_flush = nullptr;
+  DenseChol chol;
+  // trust-region state (ceres TrustRegionMinimizer / LevenbergMarquardtStrategy)
+  double radius = 1e4, decrease_factor = 2.0;
+  double x_cost = 0.0, x_norm = 0.0, min_cost = 0.0, fixed_cost = 0.0, gradient_max_norm = 0.0;
+  int iteration = 0, num_consecutive_invalid = 0;
+  bool step_is_successful = true, finished = false;
+  bool grad_checked = false;
+  ThbBaSummary sum{};
+  PhaseTimer t_jac, t_normal, t_solve, t_update;
+  std::chrono::steady_clock::time_point t_create, t_solve_start;
+  std::vector<int> h_perm_p;  // point-major position -> caller's observation index
+};
+
+namespace {
+
+void FreeSession(ThbBaSession* s) {
+  if (!s) return;
+  cudaFree(s->X.cam); cudaFree(s->X.camd); cudaFree(s->X.intr); cudaFree(s->X.pts);
+  cudaFree(s->Xc.cam); cudaFree(s->Xc.camd); cudaFree(s->Xc.intr); cudaFree(s->Xc.pts);
+  cudaFree(s->d_cam_group); cudaFree(s->d_intr_model); cudaFree(s->d_intr_slot); cudaFree(s->d_cam_const);
+  cudaFree(s->d_pt_const); cudaFree(s->d_intr_const);
+  cudaFree(s->d_op_cam); cudaFree(s->d_op_pt); cudaFree(s->d_oc_cam); cudaFree(s->d_oc_pt);
+  cudaFree(s->d_op_xy); cudaFree(s->d_op_si); cudaFree(s->d_oc_xy); cudaFree(s->d_oc_si);
+  cudaFree(s->d_pt_start); cudaFree(s->d_cam_start); cudaFree(s->d_chunk_pt);
+  cudaFree(s->d_r); cudaFree(s->d_jc); cudaFree(s->d_jp); cudaFree(s->d_cs); cudaFree(s->d_ps);
+  cudaFree(s->d_vinv); cudaFree(s->d_gp); cudaFree(s->d_pdiag); cudaFree(s->d_braw); cudaFree(s->d_cdiag); cudaFree(s->d_yp);
+  cudaFree(s->d_scal); cudaFree(s->d_flag); cudaFree(s->d_flush);
+  if (s->h_scal) cudaFreeHost(s->h_scal);
+  if (s->h_flag) cudaFreeHost(s->h_flag);
+  s->chol.Free();
+  s->t_jac.Free(); s->t_normal.Free(); s->t_solve.Free(); s->t_update.Free();
+  delete s;
+}
+
+// Copy `bytes` from the caller's array (host or device per memory_space) into a host vector.
+template <typename T>
+int FetchToHost(const void* src, size_t count, int space, std::vector<T>* out) {
+  out->resize(count);
+  if (count == 0) return THB_OK;
+  if (space == THB_MEM_HOST) std::memcpy(out->data(), src, count * sizeof(T));
+  else THB_CUDA_CHECK(cudaMemcpy(out->data(), src, count * sizeof(T), cudaMemcpyDeviceToHost));
+  return THB_OK;
+}
+
+struct DevBufs {  // scoped device allocations
+  std::vector<void*> p;
+  ~DevBufs() { for (void* q : p) cudaFree(q); }
+  template <typename T> T* get(size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, std::max<size_t>(1, n) * sizeof(T)) != cudaSuccess) return nullptr;
+    p.push_back(q);
+    return (T*)q;
+  }
+};
+
+int CheckDevice() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) THB_FAIL(THB_E_NO_DEVICE, "no CUDA device visible; libtheia_b200 has no CPU path");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp pr;
+  THB_CUDA_CHECK(cudaGetDeviceProperties(&pr, dev));
+  if (pr.major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
+  return THB_OK;
+}
+
+template <int MODEL, int PD>
+void LaunchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
+  k_jacobian<MODEL, PD, 0><<<cdiv(s->no, 256), 256, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
+                                                               nullptr, s->d_scal, s->d_flag);
+}
+template <int PD>
+void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
+  switch (s->model) {
+    case THB_MODEL_PINHOLE: LaunchJacobian<THB_MODEL_PINHOLE, PD>(s, cs, ps); break;
+    case THB_MODEL_FISHEYE: LaunchJacobian<THB_MODEL_FISHEYE, PD>(s, cs, ps); break;
+    case THB_MODEL_FOV: LaunchJacobian<THB_MODEL_FOV, PD>(s, cs, ps); break;
+    case THB_MODEL_DIVISION_UNDISTORTION: LaunchJacobian<THB_MODEL_DIVISION_UNDISTORTION, PD>(s, cs, ps); break;
+    case THB_MODEL_DOUBLE_SPHERE: LaunchJacobian<THB_MODEL_DOUBLE_SPHERE, PD>(s, cs, ps); break;
+    case THB_MODEL_EXTENDED_UNIFIED: LaunchJacobian<THB_MODEL_EXTENDED_UNIFIED, PD>(s, cs, ps); break;
+    default: LaunchJacobian<-1, PD>(s, cs, ps); break;
+  }
+}
+void RunJacobian(ThbBaSession* s, const double* cs, const double* ps) {
+  if (s->PD == 3) DispatchJacobian<3>(s, cs, ps); else DispatchJacobian<4>(s, cs, ps);
+  ++s->sum.gpu_launches;
+}
+
+template <int MODEL, int PD>
+void LaunchCamPass(ThbBaSession* s, double inv_radius) {
+  k_cam_pass<MODEL, PD><<<s->nc, 128, 0, s->st>>>(s->K, s->X, s->Oc, s->d_cam_start, s->d_cs, s->d_ps, s->d_vinv, s->d_gp, inv_radius,
+                                                 s->opt.min_lm_diagonal, s->opt.max_lm_diagonal, s->chol.A, s->chol.ld,
+                                                 s->chol.RhsRow(), s->d_braw, s->d_cdiag, s->d_flag);
+}
+template <int PD>
+void DispatchCamPass(ThbBaSession* s, double inv_radius) {
+  switch (s->model) {
+    case THB_MODEL_PINHOLE: LaunchCamPass<THB_MODEL_PINHOLE, PD>(s, inv_radius); break;
+    case THB_MODEL_FISHEYE: LaunchCamPass<THB_MODEL_FISHEYE, PD>(s, inv_radius); break;
+    case THB_MODEL_FOV: LaunchCamPass<THB_MODEL_FOV, PD>(s, inv_radius); break;
+    case THB_MODEL_DIVISION_UNDISTORTION: LaunchCamPass<THB_MODEL_DIVISION_UNDISTORTION, PD>(s, inv_radius); break;
+    case THB_MODEL_DOUBLE_SPHERE: LaunchCamPass<THB_MODEL_DOUBLE_SPHERE, PD>(s, inv_radius); break;
+    case THB_MODEL_EXTENDED_UNIFIED: LaunchCamPass<THB_MODEL_EXTENDED_UNIFIED, PD>(s, inv_radius); break;
+    default: LaunchCamPass<-1, PD>(s, inv_radius); break;
+  }
+}
+
+void RunCost(ThbBaSession* s, const BaState& st, int slot, int flag_slot) {
+  const int g = cdiv(s->no, 256);
+  switch (s->model) {
+    case THB_MODEL_PINHOLE: k_cost<THB_MODEL_PINHOLE><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    case THB_MODEL_FISHEYE: k_cost<THB_MODEL_FISHEYE><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    case THB_MODEL_FOV: k_cost<THB_MODEL_FOV><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    case THB_MODEL_DIVISION_UNDISTORTION: k_cost<THB_MODEL_DIVISION_UNDISTORTION><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    case THB_MODEL_DOUBLE_SPHERE: k_cost<THB_MODEL_DOUBLE_SPHERE><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    case THB_MODEL_EXTENDED_UNIFIED: k_cost<THB_MODEL_EXTENDED_UNIFIED><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+    default: k_cost<-1><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
+  }
+  ++s->sum.gpu_launches;
+}
+
+int ReadScalars(ThbBaSession* s) {
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s->st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->h_flag, s->d_flag, sizeof(int) * FL_COUNT, cudaMemcpyDeviceToHost, s->st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  s->sum.ms_jacobian += s->t_jac.CollectMs();
+  s->sum.ms_normal += s->t_normal.CollectMs();
+  s->sum.ms_solve += s->t_solve.CollectMs();
+  s->sum.ms_update += s->t_update.CollectMs();
+  return THB_OK;
+}
+
+void LogIter(ThbBaSession* s) {
+  if (s->sum.iter_log_count < THB_MAX_ITER_LOG) {
+    s->sum.iter_cost[s->sum.iter_log_count] = s->x_cost + s->fixed_cost;
+    s->sum.iter_radius[s->sum.iter_log_count] = s->radius;
+    ++s->sum.iter_log_count;
+  }
+}
+
+// K1 at the current point: cost, residual/Jacobian planes (column-scaled).
+int EvaluateJacobian(ThbBaSession* s) {
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_X, 0, sizeof(double), s->st));
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_EVAL_X, 0, sizeof(int), s->st));
+  s->t_jac.Begin();
+  RunJacobian(s, s->d_cs, s->d_ps);
+  s->t_jac.End();
+  ++s->sum.num_jacobian_evaluations;
+  return THB_OK;
+}
+
+// K2a + K2b (+ gradient max-norm) at the current Jacobian and radius.
+int BuildBlocks(ThbBaSession* s, bool want_grad) {
+  const double inv_radius = 1.0 / s->radius;
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_CHOL, 0, sizeof(int) * 2, s->st));
+  s->t_normal.Begin();
+  if (s->red_variable) { if (s->chol.Clear(s->st) != THB_OK) return THB_E_CUDA; ++s->sum.gpu_launches; }
+  if (s->PD == 3)
+    k_point_pass<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_r, s->d_jp, inv_radius, s->opt.min_lm_diagonal,
+                                                        s->opt.max_lm_diagonal, s->d_vinv, s->d_gp, s->d_pdiag, s->d_flag);
+  else
+    k_point_pass<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_r, s->d_jp, inv_radius, s->opt.min_lm_diagonal,
+                                                        s->opt.max_lm_diagonal, s->d_vinv, s->d_gp, s->d_pdiag, s->d_flag);
+  if (s->PD == 3) DispatchCamPass<3>(s, inv_radius); else DispatchCamPass<4>(s, inv_radius);
+  s->sum.gpu_launches += 2;
+  if (want_grad) {
+    THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_GRADMAX, 0, sizeof(double), s->st));
+    k_grad_max<<<cdiv(s->n_red, 256), 256, 0, s->st>>>(s->n_red, s->d_braw, s->d_cs, s->d_scal);
+    k_grad_max<<<cdiv((long long)s->np * s->PD, 256), 256, 0, s->st>>>(s->np * s->PD, s->d_gp, s->d_ps, s->d_scal);
+    s->sum.gpu_launches += 2;
+  }
+  s->t_normal.End();
+  return THB_OK;
+}
+
+// Schur complement off-diagonal blocks, factor + solve, back-substitution, candidate, candidate cost.
+int SolveAndStep(ThbBaSession* s) {
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_CAND, 0, sizeof(double) * 4, s->st));  // cand, mcc, step2, xnew2
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_EVAL_CAND, 0, sizeof(int), s->st));
+  if (s->red_variable) {
+    s->t_normal.Begin();
+    if (s->PD == 3)
+      k_schur_offdiag<3><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+    else
+      k_schur_offdiag<4><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+    ++s->sum.gpu_launches;
+    s->t_normal.End();
+    s->t_solve.Begin();
+    if (s->chol.FactorAndSolve(s->st, s->d_flag + FL_CHOL, &s->sum.gpu_launches) != THB_OK) return THB_E_CUDA;
+    s->t_solve.End();
+  } else {
+    THB_CUDA_CHECK(cudaMemsetAsync(s->chol.x, 0, sizeof(double) * s->chol.n_pad, s->st));
+  }
+  ++s->sum.num_linear_solves;
+  s->t_update.Begin();
+  if (s->PD == 3) {
+    k_backsub<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_op_cam, s->d_r, s->d_jc, s->d_jp, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
+    k_update_pts<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_ps, s->Xc.pts, s->d_scal);
+  } else {
+    k_backsub<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_op_cam, s->d_r, s->d_jc, s->d_jp, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
+    k_update_pts<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_ps, s->Xc.pts, s->d_scal);
+  }
+  k_update_cams<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_cam_const, s->X.cam, s->chol.x, s->d_cs, s->Xc.cam, s->d_scal);
+  k_cam_derive<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->Xc.cam, s->Xc.camd, s->nc);
+  s->sum.gpu_launches += 4;
+  RunCost(s, s->Xc, SC_COST_CAND, FL_EVAL_CAND);
+  ++s->sum.num_cost_evaluations;
+  s->t_update.End();
+  return THB_OK;
+}
+
+void Terminate(ThbBaSession* s, int type) { s->sum.termination_type = type; s->finished = true; }
+
+// One pass of TrustRegionMinimizer's main loop. Returns THB_OK; sets s->finished on termination.
+int OneIteration(ThbBaSession* s) {
+  const ThbBaOptions& O = s->opt;
+  // FinalizeIterationAndCheckIfMinimizerCanContinue (tests that need no device data)
+  const double elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->t_solve_start).count();
+  if (elapsed >= O.max_solver_time_in_seconds) { Terminate(s, THB_TERM_NO_CONVERGENCE); return THB_OK; }
+  if (s->iteration >= O.max_num_iterations) { Terminate(s, THB_TERM_NO_CONVERGENCE); return THB_OK; }
+  if (s->radius <= O.min_trust_region_radius) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  // The gradient test of the previous (successful) iteration needs b = J^T r at the current point, which
+  // K2 produces anyway: the whole iteration is enqueued and the test is applied when the scalars arrive.
+  const bool want_grad = s->step_is_successful;
+  int rc = BuildBlocks(s, want_grad);
+  if (rc != THB_OK) return rc;
+  rc = SolveAndStep(s);
+  if (rc != THB_OK) return rc;
+  rc = ReadScalars(s);
+  if (rc != THB_OK) return rc;
+  if (want_grad) {
+    s->gradient_max_norm = s->h_scal[SC_GRADMAX];
+    if (s->gradient_max_norm <= O.gradient_tolerance) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  }
+  ++s->iteration;
+  s->step_is_successful = false;
+  const double model_cost_change = s->h_scal[SC_MCC];
+  bool step_valid = !(s->h_flag[FL_CHOL] || s->h_flag[FL_POINT]) && std::isfinite(model_cost_change) && model_cost_change > 0.0;
+  if (!step_valid) {
+    // HandleInvalidStep / LevenbergMarquardtStrategy::StepIsInvalid
+    if (++s->num_consecutive_invalid >= O.max_num_consecutive_invalid_steps) { Terminate(s, THB_TERM_FAILURE); return THB_OK; }
+    s->radius /= s->decrease_factor; s->decrease_factor *= 2.0;
+    LogIter(s);
+    return THB_OK;
+  }
+  s->num_consecutive_invalid = 0;
+  const double cand_cost = s->h_flag[FL_EVAL_CAND] ? std::numeric_limits<double>::max() : s->h_scal[SC_COST_CAND];
+  // ParameterToleranceReached
+  const double step_norm = std::sqrt(s->h_scal[SC_STEP2]);
+  if (step_norm <= O.parameter_tolerance * (s->x_norm + O.parameter_tolerance)) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  // FunctionToleranceReached
+  const double cost_change = s->x_cost - cand_cost;
+  if (std::fabs(cost_change) <= O.function_tolerance * s->x_cost) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  // IsStepSuccessful (monotonic)
+  const double relative_decrease = cand_cost >= std::numeric_limits<double>::max() ? std::numeric_limits<double>::lowest()
+                                                                                   : cost_change / model_cost_change;
+  if (relative_decrease > O.min_relative_decrease) {
+    std::swap(s->X, s->Xc);
+    s->x_norm = std::sqrt(s->h_scal[SC_XNEW2]);
+    rc = EvaluateJacobian(s);  // EvaluateGradientAndJacobian(new_evaluation_point = false)
+    if (rc != THB_OK) return rc;
+    THB_CUDA_CHECK(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s->st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(s->h_flag, s->d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->st));
+    THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+    if (s->h_flag[FL_EVAL_X]) { Terminate(s, THB_TERM_FAILURE); return THB_OK; }
+    s->x_cost = s->h_scal[SC_COST_X];
+    s->step_is_successful = true;
+    ++s->sum.num_successful_steps;
+    s->radius = s->radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * relative_decrease - 1.0, 3));
+    s->radius = std::min(O.max_trust_region_radius, s->radius);
+    s->decrease_factor = 2.0;
+    s->min_cost = std::min(s->min_cost, s->x_cost);
+  } else {
+    s->radius /= s->decrease_factor; s->decrease_factor *= 2.0;
+  }
+  LogIter(s);
+  return THB_OK;
+}
+
+int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream, ThbBaSession** out) {
+  if (!P || !O || !out) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
+  *out = nullptr;
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  if (P->num_cameras < 0 || P->num_groups < 0 || P->num_points < 0 || P->num_observations < 0)
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "negative size");
+  if (P->memory_space != THB_MEM_HOST && P->memory_space != THB_MEM_DEVICE) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad memory_space");
+  if (P->num_observations > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->pts || !P->obs_cam || !P->obs_pt || !P->obs_xy))
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
+  if (O->use_inner_iterations) THB_FAIL(THB_E_UNSUPPORTED, "use_inner_iterations is not implemented (set it to false, as BundleAdjustView/Track do)");
+  if (O->linear_solver != THB_SOLVER_SCHUR_CHOLESKY) THB_FAIL(THB_E_UNSUPPORTED, "only THB_SOLVER_SCHUR_CHOLESKY is implemented");
+  if (O->loss_function_type < THB_LOSS_TRIVIAL || O->loss_function_type > THB_LOSS_TRUNCATED) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad loss type");
+
+  ThbBaSession* s = new ThbBaSession();
+  s->t_create = std::chrono::steady_clock::now();
+  s->prob = *P; s->opt = *O; s->st = (cudaStream_t)stream;
+  s->nc = P->num_cameras; s->ng = P->num_groups; s->np = P->num_points; s->no = P->num_observations;
+  s->PD = O->use_homogeneous_point_parametrization ? 3 : 4;
+  const int nc = s->nc, ng = s->ng, np = s->np, no = s->no, sp = P->memory_space;
+  s->t_jac.st = s->t_normal.st = s->t_solve.st = s->t_update.st = s->st;
+
+#define THB_TRY(expr) do { rc = (expr); if (rc != THB_OK) { FreeSession(s); return rc; } } while (0)
+#define THB_TRY_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { SetLastError(std::string(#expr) + ": " + cudaGetErrorString(_e)); FreeSession(s); return THB_E_CUDA; } } while (0)
+
+  // ---- structure on the host: validation, constness, the two observation orders ----
+  std::vector<int> h_cam_group, h_intr_model, h_obs_cam, h_obs_pt;
+  std::vector<uint8_t> h_cam_const(nc, 0), h_pt_const(np, 0);
+  std::vector<uint16_t> h_intr_const(ng, 0xffff);
+  THB_TRY(FetchToHost(P->cam_group, nc, sp, &h_cam_group));
+  THB_TRY(FetchToHost(P->intr_model, ng, sp, &h_intr_model));
+  THB_TRY(FetchToHost(P->obs_cam, no, sp, &h_obs_cam));
+  THB_TRY(FetchToHost(P->obs_pt, no, sp, &h_obs_pt));
+  if (P->cam_const) THB_TRY(FetchToHost(P->cam_const, nc, sp, &h_cam_const));
+  if (P->pt_const) THB_TRY(FetchToHost(P->pt_const, np, sp, &h_pt_const));
+  if (P->intr_const) THB_TRY(FetchToHost(P->intr_const, ng, sp, &h_intr_const));
+  for (int g = 0; g < ng; ++g) {
+    const int K = num_intrinsics(h_intr_model[g]);
+    if (K < 0) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path"); }
+    if ((h_intr_const[g] & ((1u << K) - 1)) != ((1u << K) - 1)) {
+      FreeSession(s);
+      THB_FAIL(THB_E_UNSUPPORTED, "intrinsics refinement is not implemented yet: every intrinsics parameter must be constant");
+    }
+  }
+  for (int c = 0; c < nc; ++c)
+    if (h_cam_group[c] < 0 || h_cam_group[c] >= ng) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range"); }
+  std::vector<int> pt_start(np + 1, 0), cam_start(nc + 1, 0);
+  for (int i = 0; i < no; ++i) {
+    const int c = h_obs_cam[i], p = h_obs_pt[i];
+    if (c < 0 || c >= nc || p < 0 || p >= np) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range"); }
+    ++pt_start[p + 1]; ++cam_start[c + 1];
+  }
+  // blocks without observations are not part of the problem
+  for (int c = 0; c < nc; ++c) if (cam_start[c + 1] == 0) h_cam_const[c] = THB_CAM_CONST_ALL; else h_cam_const[c] &= THB_CAM_CONST_ALL;
+  for (int p = 0; p < np; ++p) if (pt_start[p + 1] == 0) h_pt_const[p] = 1;
+  for (int p = 0; p < np; ++p) pt_start[p + 1] += pt_start[p];
+  for (int c = 0; c < nc; ++c) cam_start[c + 1] += cam_start[c];
+  std::vector<int> perm_p(no), perm_c(no);
+  {
+    std::vector<int> cur(pt_start.begin(), pt_start.end() - 1);
+    for (int i = 0; i < no; ++i) perm_p[cur[h_obs_pt[i]]++] = i;
+    std::vector<int> cur2(cam_start.begin(), cam_start.end() - 1);
+    for (int i = 0; i < no; ++i) perm_c[cur2[h_obs_cam[i]]++] = i;
+  }
+  s->h_perm_p = perm_p;
+  s->model = ng > 0 ? h_intr_model[0] : THB_MODEL_PINHOLE;
+  for (int g = 1; g < ng; ++g) if (h_intr_model[g] != s->model) s->model = -1;
+  s->red_variable = false; s->any_variable = false;
+  for (int c = 0; c < nc; ++c) if (h_cam_const[c] != THB_CAM_CONST_ALL) s->red_variable = true;
+  for (int p = 0; p < np; ++p) if (!h_pt_const[p]) s->any_variable = true;
+  s->any_variable |= s->red_variable;
+  // Ceres drops residual blocks whose parameter blocks are all constant (their cost is Summary::fixed_cost);
+  // they still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
+  bool has_fixed = false;
+  for (int i = 0; i < no && !has_fixed; ++i) has_fixed = h_cam_const[h_obs_cam[i]] == THB_CAM_CONST_ALL && h_pt_const[h_obs_pt[i]];
+  if (has_fixed && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera and point are both constant are not supported in a problem with free blocks"); }
+  // Schur chunks: consecutive points with <= 64 observations in total
+  std::vector<int> chunk_pt;
+  chunk_pt.push_back(0);
+  for (int p = 0, acc = 0; p < np; ++p) {
+    const int n = pt_start[p + 1] - pt_start[p];
+    if (acc > 0 && acc + n > 64) { chunk_pt.push_back(p); acc = 0; }
+    acc += n;
+  }
+  chunk_pt.push_back(np);
+  s->nchunks = (int)chunk_pt.size() - 1;
+  s->n_red = 6 * nc;
+
+  // ---- device memory ----
+  THB_TRY(DevAlloc(&s->X.cam, (size_t)nc * 6)); THB_TRY(DevAlloc(&s->X.camd, (size_t)nc * CAMD));
+  THB_TRY(DevAlloc(&s->X.intr, (size_t)ng * KS)); THB_TRY(DevAlloc(&s->X.pts, (size_t)np * 4));
+  THB_TRY(DevAlloc(&s->Xc.cam, (size_t)nc * 6)); THB_TRY(DevAlloc(&s->Xc.camd, (size_t)nc * CAMD));
+  THB_TRY(DevAlloc(&s->Xc.intr, (size_t)ng * KS)); THB_TRY(DevAlloc(&s->Xc.pts, (size_t)np * 4));
+  THB_TRY(DevAlloc(&s->d_cam_group, nc)); THB_TRY(DevAlloc(&s->d_intr_model, ng)); THB_TRY(DevAlloc(&s->d_intr_slot, ng));
+  THB_TRY(DevAlloc(&s->d_cam_const, nc)); THB_TRY(DevAlloc(&s->d_pt_const, np)); THB_TRY(DevAlloc(&s->d_intr_const, ng));
+  THB_TRY(DevAlloc(&s->d_op_cam, no)); THB_TRY(DevAlloc(&s->d_op_pt, no)); THB_TRY(DevAlloc(&s->d_oc_cam, no)); THB_TRY(DevAlloc(&s->d_oc_pt, no));
+  THB_TRY(DevAlloc(&s->d_op_xy, no)); THB_TRY(DevAlloc(&s->d_op_si, no)); THB_TRY(DevAlloc(&s->d_oc_xy, no)); THB_TRY(DevAlloc(&s->d_oc_si, no));
+  THB_TRY(DevAlloc(&s->d_pt_start, np + 1)); THB_TRY(DevAlloc(&s->d_cam_start, nc + 1)); THB_TRY(DevAlloc(&s->d_chunk_pt, chunk_pt.size()));
+  THB_TRY(DevAlloc(&s->d_r, (size_t)no * 2)); THB_TRY(DevAlloc(&s->d_jc, (size_t)no * 12)); THB_TRY(DevAlloc(&s->d_jp, (size_t)no * 2 * s->PD));
+  THB_TRY(DevAlloc(&s->d_cs, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_ps, (size_t)np * s->PD));
+  THB_TRY(DevAlloc(&s->d_vinv, (size_t)np * s->PD * s->PD)); THB_TRY(DevAlloc(&s->d_gp, (size_t)np * s->PD)); THB_TRY(DevAlloc(&s->d_pdiag, (size_t)np * s->PD));
+  THB_TRY(DevAlloc(&s->d_braw, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_cdiag, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_yp, (size_t)np * s->PD));
+  THB_TRY(DevAlloc(&s->d_scal, SC_COUNT)); THB_TRY(DevAlloc(&s->d_flag, FL_COUNT));
+  THB_TRY_CUDA(cudaMallocHost(&s->h_scal, sizeof(double) * SC_COUNT));
+  THB_TRY_CUDA(cudaMallocHost(&s->h_flag, sizeof(int) * FL_COUNT));
+  THB_TRY(s->chol.Init(std::max(1, s->n_red)));
+
+  // ---- upload ----
+  const cudaMemcpyKind kin = sp == THB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  cudaStream_t st = s->st;
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.cam, P->cam_ext, sizeof(double) * nc * 6, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.pts, P->pts, sizeof(double) * np * 4, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->Xc.intr, s->X.intr, sizeof(double) * ng * KS, cudaMemcpyDeviceToDevice, st));
+  std::vector<int> slot(ng, -1);
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, h_cam_group.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_model, h_intr_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_slot, slot.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, h_cam_const.data(), nc, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, h_pt_const.data(), np, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_const, h_intr_const.data(), sizeof(uint16_t) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_start, pt_start.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_start, cam_start.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_chunk_pt, chunk_pt.data(), sizeof(int) * chunk_pt.size(), cudaMemcpyHostToDevice, st));
+  {
+    // reorder observations on the host (the reference walks hash maps at this point, bundle_adjuster.cc:116-173)
+    std::vector<double> h_xy, h_si;
+    THB_TRY(FetchToHost(P->obs_xy, (size_t)no * 2, sp, &h_xy));
+    if (P->obs_sqrt_info) THB_TRY(FetchToHost(P->obs_sqrt_info, (size_t)no * 2, sp, &h_si));
+    else h_si.assign((size_t)no * 2, 1.0);
+    std::vector<int> oc(no), op(no);
+    std::vector<double> xy((size_t)no * 2), si((size_t)no * 2);
+    for (int pass = 0; pass < 2; ++pass) {
+      const std::vector<int>& perm = pass == 0 ? perm_p : perm_c;
+      for (int q = 0; q < no; ++q) {
+        const int i = perm[q];
+        oc[q] = h_obs_cam[i]; op[q] = h_obs_pt[i];
+        xy[2 * (size_t)q] = h_xy[2 * (size_t)i]; xy[2 * (size_t)q + 1] = h_xy[2 * (size_t)i + 1];
+        si[2 * (size_t)q] = h_si[2 * (size_t)i]; si[2 * (size_t)q + 1] = h_si[2 * (size_t)i + 1];
+      }
+      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_cam : s->d_oc_cam, oc.data(), sizeof(int) * no, cudaMemcpyHostToDevice));
+      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_pt : s->d_oc_pt, op.data(), sizeof(int) * no, cudaMemcpyHostToDevice));
+      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_xy : s->d_oc_xy, xy.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice));
+      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_si : s->d_oc_si, si.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice));
+    }
+  }
+  s->Op = ObsSoA{s->d_op_cam, s->d_op_pt, s->d_op_xy, s->d_op_si};
+  s->Oc = ObsSoA{s->d_oc_cam, s->d_oc_pt, s->d_oc_xy, s->d_oc_si};
+  s->K = BaConst{nc, ng, np, no, s->d_cam_group, s->d_intr_model, s->d_cam_const, s->d_intr_const, s->d_pt_const, s->d_intr_slot,
+                 O->loss_function_type, O->robust_loss_width};
+
+  // ---- IterationZero ----
+  std::memset(&s->sum, 0, sizeof(s->sum));
+  s->sum.termination_type = THB_TERM_NO_CONVERGENCE;
+  s->radius = O->initial_trust_region_radius; s->decrease_factor = 2.0;
+  if (!s->any_variable || no == 0) {
+    // nothing to optimise: report the cost of the (fixed) residual blocks
+    THB_TRY_CUDA(cudaMemsetAsync(s->d_scal, 0, sizeof(double) * SC_COUNT, st));
+    THB_TRY_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int) * FL_COUNT, st));
+    if (no > 0) {
+      k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(s->X.cam, s->X.camd, nc);
+      RunCost(s, s->X, SC_COST_X, FL_EVAL_X);
+    }
+    THB_TRY(ReadScalars(s));
+    s->fixed_cost = s->h_scal[SC_COST_X]; s->x_cost = 0.0; s->min_cost = 0.0;
+    s->sum.initial_cost = s->fixed_cost;
+    Terminate(s, THB_TERM_CONVERGENCE);
+    s->t_solve_start = std::chrono::steady_clock::now();
+    *out = s;
+    return THB_OK;
+  }
+  THB_TRY_CUDA(cudaMemsetAsync(s->d_scal, 0, sizeof(double) * SC_COUNT, st));
+  THB_TRY_CUDA(cudaMemsetAsync(s->d_flag, 0, sizeof(int) * FL_COUNT, st));
+  k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(s->X.cam, s->X.camd, nc);
+  k_fill<<<cdiv(s->n_red, 256), 256, 0, st>>>(s->n_red, s->d_cs, 1.0);
+  k_fill<<<cdiv((long long)np * s->PD, 256), 256, 0, st>>>(np * s->PD, s->d_ps, 1.0);
+  k_xnorm<<<cdiv((long long)nc + np, 256), 256, 0, st>>>(nc, np, s->d_cam_const, s->d_pt_const, s->X.cam, s->X.pts, s->d_scal + SC_XNEW2);
+  s->sum.gpu_launches += 4;
+  if (O->jacobi_scaling) {
+    // column norms of the unscaled Jacobian -> scale = 1/(1+sqrt(norm^2)), fixed for the whole solve
+    RunJacobian(s, s->d_cs, s->d_ps);
+    THB_TRY(BuildBlocks(s, false));
+    k_make_scale<<<cdiv(s->n_red, 256), 256, 0, st>>>(s->n_red, s->d_cdiag, s->d_cs);
+    k_make_scale<<<cdiv((long long)np * s->PD, 256), 256, 0, st>>>(np * s->PD, s->d_pdiag, s->d_ps);
+    s->sum.gpu_launches += 2;
+    THB_TRY_CUDA(cudaMemsetAsync(s->d_scal + SC_COST_X, 0, sizeof(double), st));
+  }
+  THB_TRY(EvaluateJacobian(s));
+  THB_TRY(ReadScalars(s));
+  if (s->h_flag[FL_EVAL_X]) { FreeSession(s); THB_FAIL(THB_E_NUMERICAL, "initial residual and Jacobian evaluation failed"); }
+  s->x_cost = s->h_scal[SC_COST_X];
+  s->x_norm = std::sqrt(s->h_scal[SC_XNEW2]);
+  s->min_cost = s->x_cost;
+  s->sum.initial_cost = s->x_cost + s->fixed_cost;
+  s->step_is_successful = true; s->iteration = 0;
+  LogIter(s);
+  s->t_solve_start = std::chrono::steady_clock::now();
+  s->sum.setup_time_in_seconds = std::chrono::duration<double>(s->t_solve_start - s->t_create).count();
+  *out = s;
+  return THB_OK;
+#undef THB_TRY
+#undef THB_TRY_CUDA
+}
+
+}  // namespace
+
+extern "C" {
+
+int thb_version(void) { return 100; }
+const char* thb_last_error(void) { return thb::GetLastError(); }
+int thb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+void thb_ba_default_options(ThbBaOptions* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // BundleAdjustmentOptions defaults (bundle_adjustment.h:87-167); use_inner_iterations is forced off
+  o->loss_function_type = THB_LOSS_TRIVIAL; o->robust_loss_width = 2.0;
+  o->linear_solver = THB_SOLVER_SCHUR_CHOLESKY;
+  o->use_homogeneous_point_parametrization = 1; o->use_inner_iterations = 0;
+  o->max_num_iterations = 100; o->jacobi_scaling = 1; o->verbose = 0;
+  o->max_num_consecutive_invalid_steps = 5;
+  o->function_tolerance = 1e-6; o->gradient_tolerance = 1e-10; o->parameter_tolerance = 1e-8;
+  o->max_trust_region_radius = 1e12; o->initial_trust_region_radius = 1e4;
+  o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->max_solver_time_in_seconds = 3600.0;
+  o->pcg_tolerance = 1e-12; o->pcg_max_iterations = 500;
+}
+
+int thb_ba_create(const ThbBaProblem* problem, const ThbBaOptions* options, void* cuda_stream, ThbBaSession** session) {
+  return ValidateAndCreate(problem, options, cuda_stream, session);
+}
+
+int thb_ba_iterate(ThbBaSession* s, int32_t n, int32_t* ran) {
+  if (!s) THB_FAIL(THB_E_INVALID_ARGUMENT, "null session");
+  int done = 0;
+  while (done < n && !s->finished) {
+    const int before = s->iteration;
+    const int rc = OneIteration(s);
+    if (rc != THB_OK) return rc;
+    if (s->iteration > before) ++done;
+  }
+  if (ran) *ran = done;
+  return THB_OK;
+}
+
+int thb_ba_finish(ThbBaSession* s, ThbBaSummary* summary) {
+  if (!s) THB_FAIL(THB_E_INVALID_ARGUMENT, "null session");
+  int rc = THB_OK;
+  s->sum.num_iterations = s->iteration;
+  s->sum.final_cost = s->min_cost + s->fixed_cost;
+  s->sum.success = s->sum.termination_type != THB_TERM_FAILURE;
+  if (s->sum.success && s->any_variable) {
+    const cudaMemcpyKind kout = s->prob.memory_space == THB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    cudaError_t e = cudaMemcpyAsync(s->prob.cam_ext, s->X.cam, sizeof(double) * s->nc * 6, kout, s->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->prob.pts, s->X.pts, sizeof(double) * s->np * 4, kout, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (e != cudaSuccess) { SetLastError(cudaGetErrorString(e)); rc = THB_E_CUDA; }
+  }
+  cudaStreamSynchronize(s->st);
+  s->sum.ms_jacobian += s->t_jac.CollectMs(); s->sum.ms_normal += s->t_normal.CollectMs();
+  s->sum.ms_solve += s->t_solve.CollectMs(); s->sum.ms_update += s->t_update.CollectMs();
+  s->sum.solve_time_in_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - s->t_solve_start).count();
+  if (summary) *summary = s->sum;
+  FreeSession(s);
+  return rc;
+}
+
+int thb_ba_solve(const ThbBaProblem* problem, const ThbBaOptions* options, ThbBaSummary* summary, void* cuda_stream) {
+  ThbBaSession* s = nullptr;
+  int rc = thb_ba_create(problem, options, cuda_stream, &s);
+  if (rc != THB_OK) return rc;
+  rc = thb_ba_iterate(s, std::numeric_limits<int32_t>::max(), nullptr);
+  if (rc != THB_OK) { FreeSession(s); return rc; }
+  return thb_ba_finish(s, summary);
+}
+
+int thb_ba_time_jacobian(ThbBaSession* s, int32_t repeats, int32_t flush_l2, double* avg_ms) {
+  if (!s || !avg_ms || repeats <= 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  const size_t flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+  if (flush_l2 && !s->d_flush) THB_CUDA_CHECK(cudaMalloc(&s->d_flush, flush_bytes));
+  cudaEvent_t a, b;
+  THB_CUDA_CHECK(cudaEventCreate(&a)); THB_CUDA_CHECK(cudaEventCreate(&b));
+  double total = 0.0;
+  for (int i = 0; i < repeats; ++i) {
+    if (flush_l2) THB_CUDA_CHECK(cudaMemsetAsync(s->d_flush, i & 0xff, flush_bytes, s->st));
+    THB_CUDA_CHECK(cudaEventRecord(a, s->st));
+    RunJacobian(s, s->d_cs, s->d_ps);
+    THB_CUDA_CHECK(cudaEventRecord(b, s->st));
+    THB_CUDA_CHECK(cudaEventSynchronize(b));
+    float ms = 0.f;
+    THB_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b));
+    total += ms;
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  // the cost accumulator was bumped by the extra launches: restore it
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_X, 0, sizeof(double), s->st));
+  *avg_ms = total / repeats;
+  return THB_OK;
+}
+
+int thb_ba_evaluate(const ThbBaProblem* P, double* residuals, double* jac_cam, double* jac_intr, double* jac_pt,
+                    uint8_t* ok, void* cuda_stream) {
+  if (!P) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  const int nc = P->num_cameras, ng = P->num_groups, np = P->num_points, no = P->num_observations;
+  if (nc < 0 || ng < 0 || np < 0 || no < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "negative size");
+  if (no == 0) return THB_OK;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool host = P->memory_space == THB_MEM_HOST;
+  const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  std::vector<int> h_group, h_model, h_cam, h_pt;
+  if ((rc = FetchToHost(P->cam_group, nc, P->memory_space, &h_group)) != THB_OK) return rc;
+  if ((rc = FetchToHost(P->intr_model, ng, P->memory_space, &h_model)) != THB_OK) return rc;
+  if ((rc = FetchToHost(P->obs_cam, no, P->memory_space, &h_cam)) != THB_OK) return rc;
+  if ((rc = FetchToHost(P->obs_pt, no, P->memory_space, &h_pt)) != THB_OK) return rc;
+  for (int g = 0; g < ng; ++g) if (num_intrinsics(h_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
+  for (int c = 0; c < nc; ++c) if (h_group[c] < 0 || h_group[c] >= ng) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
+  for (int i = 0; i < no; ++i) if (h_cam[i] < 0 || h_cam[i] >= nc || h_pt[i] < 0 || h_pt[i] >= np) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
+  DevBufs B;
+  BaState X{B.get<double>((size_t)nc * 6), B.get<double>((size_t)nc * CAMD), B.get<double>((size_t)ng * KS), B.get<double>((size_t)np * 4)};
+  int* d_group = B.get<int>(nc); int* d_model = B.get<int>(ng); int* d_slot = B.get<int>(ng);
+  uint8_t* d_cc = B.get<uint8_t>(nc); uint8_t* d_pc = B.get<uint8_t>(np); uint16_t* d_ic = B.get<uint16_t>(ng);
+  int* d_oc = B.get<int>(no); int* d_op = B.get<int>(no);
+  double2* d_xy = B.get<double2>(no); double2* d_si = B.get<double2>(no);
+  double* d_res = B.get<double>((size_t)no * 2); double* d_jc = B.get<double>((size_t)no * 12);
+  double* d_ji = B.get<double>((size_t)no * 2 * KS); double* d_jp = B.get<double>((size_t)no * 8);
+  uint8_t* d_ok = B.get<uint8_t>(no);
+  if (!X.cam || !X.camd || !X.intr || !X.pts || !d_group || !d_model || !d_slot || !d_cc || !d_pc || !d_ic || !d_oc || !d_op || !d_xy ||
+      !d_si || !d_res || !d_jc || !d_ji || !d_jp || !d_ok) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * np * 4, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, h_group.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, h_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  std::vector<int> slot(ng);
+  for (int g = 0; g < ng; ++g) slot[g] = g;
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_slot, slot.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, 0, nc, st)); THB_CUDA_CHECK(cudaMemsetAsync(d_pc, 0, np, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_ic, 0, sizeof(uint16_t) * ng, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_oc, h_cam.data(), sizeof(int) * no, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_op, h_pt.data(), sizeof(int) * no, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_xy, P->obs_xy, sizeof(double) * 2 * no, kin, st));
+  if (P->obs_sqrt_info) THB_CUDA_CHECK(cudaMemcpyAsync(d_si, P->obs_sqrt_info, sizeof(double) * 2 * no, kin, st));
+  else k_fill<<<cdiv(2LL * no, 256), 256, 0, st>>>(2 * no, reinterpret_cast<double*>(d_si), 1.0);
+  BaConst K{nc, ng, np, no, d_group, d_model, d_cc, d_ic, d_pc, d_slot, THB_LOSS_TRIVIAL, 1.0};
+  ObsSoA O{d_oc, d_op, d_xy, d_si};
+  k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc);
+  k_eval_ambient<<<cdiv(no, 128), 128, 0, st>>>(K, X, O, d_res, d_jc, d_ji, d_jp, d_ok);
+  THB_CUDA_CHECK(cudaGetLastError());
+  if (residuals) THB_CUDA_CHECK(cudaMemcpyAsync(residuals, d_res, sizeof(double) * 2 * no, kout, st));
+  if (jac_cam) THB_CUDA_CHECK(cudaMemcpyAsync(jac_cam, d_jc, sizeof(double) * 12 * no, kout, st));
+  if (jac_intr) THB_CUDA_CHECK(cudaMemcpyAsync(jac_intr, d_ji, sizeof(double) * 2 * KS * no, kout, st));
+  if (jac_pt) THB_CUDA_CHECK(cudaMemcpyAsync(jac_pt, d_jp, sizeof(double) * 8 * no, kout, st));
+  if (ok) THB_CUDA_CHECK(cudaMemcpyAsync(ok, d_ok, no, kout, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return THB_OK;
+}
+
+}  // extern "C"

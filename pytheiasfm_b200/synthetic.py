@@ -1,0 +1,218 @@
+"""Deterministic synthetic reconstructions / pair batches for BASELINE.json's configs.
+
+Pure numpy (seeded default_rng); shapes follow SURVEY.md §8(d). The arrays are already
+in the C-ABI layout of include/theia_b200.h.
+"""
+import numpy as np
+
+from . import capi
+
+
+def _rotvec_from_matrix(R):
+    """Batched rotation matrix -> angle-axis (world->camera, Camera::ORIENTATION)."""
+    R = np.asarray(R, dtype=np.float64)
+    tr = np.clip((np.trace(R, axis1=-2, axis2=-1) - 1.0) / 2.0, -1.0, 1.0)
+    th = np.arccos(tr)
+    v = np.stack([R[..., 2, 1] - R[..., 1, 2], R[..., 0, 2] - R[..., 2, 0], R[..., 1, 0] - R[..., 0, 1]], -1)
+    s = 2.0 * np.sin(th)
+    small = np.abs(s) < 1e-12
+    k = np.where(small, 0.5, th / np.where(small, 1.0, s))
+    return v * k[..., None]
+
+
+def rotmat_from_rotvec(w):
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w, axis=-1)
+    out = np.zeros(w.shape[:-1] + (3, 3))
+    K = np.zeros(w.shape[:-1] + (3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -w[..., 2], w[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = w[..., 2], -w[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -w[..., 1], w[..., 0]
+    th2 = th * th
+    a = np.where(th < 1e-8, 1.0 - th2 / 6.0, np.sin(th) / np.where(th < 1e-8, 1.0, th))
+    b = np.where(th < 1e-8, 0.5 - th2 / 24.0, (1.0 - np.cos(th)) / np.where(th < 1e-8, 1.0, th2))
+    out = np.eye(3) + a[..., None, None] * K + b[..., None, None] * (K @ K)
+    return out
+
+
+def _look_at(C, target, up=np.array([0.0, 0.0, 1.0])):
+    z = target - C
+    z /= np.linalg.norm(z, axis=-1, keepdims=True)
+    x = np.cross(z, up)
+    x /= np.linalg.norm(x, axis=-1, keepdims=True)
+    y = np.cross(z, x)
+    return np.stack([x, y, z], axis=-2)  # rows = camera axes in world coords
+
+
+def project(model, K, p):
+    """numpy restatement used ONLY to synthesise observations (double precision)."""
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    if model == capi.MODEL_PINHOLE:
+        nx, ny = x / z, y / z
+        r2 = nx * nx + ny * ny
+        d = 1.0 + r2 * (K[5] + K[6] * r2)
+        dx, dy = nx * d, ny * d
+        return np.stack([K[0] * dx + K[2] * dy + K[3], K[0] * K[1] * dy + K[4]], -1)
+    if model == capi.MODEL_DOUBLE_SPHERE:
+        xi, al = K[5], K[6]
+        d1 = np.sqrt(x * x + y * y + z * z)
+        k = xi * d1 + z
+        d2 = np.sqrt(x * x + y * y + k * k)
+        n = al * d2 + (1 - al) * k
+        dx, dy = x / n, y / n
+        return np.stack([K[0] * dx + K[2] * dy + K[3], K[0] * K[1] * dy + K[4]], -1)
+    if model == capi.MODEL_EXTENDED_UNIFIED:
+        al, be = K[5], K[6]
+        rho = np.sqrt(be * (x * x + y * y) + z * z)
+        n = al * rho + (1 - al) * z
+        dx, dy = x / n, y / n
+        return np.stack([K[0] * dx + K[2] * dy + K[3], K[0] * K[1] * dy + K[4]], -1)
+    if model == capi.MODEL_FISHEYE:
+        r = np.sqrt(x * x + y * y)
+        th = np.arctan2(r, np.abs(z))
+        t2 = th * th
+        td = th * (1 + K[5] * t2 + K[6] * t2 ** 2 + K[7] * t2 ** 3 + K[8] * t2 ** 4)
+        s = np.where(r > 1e-4, td / np.maximum(r, 1e-300), 1.0)
+        dx, dy = x * s, y * s
+        return np.stack([K[0] * dx + K[2] * dy + K[3], K[0] * K[1] * dy + K[4]], -1)
+    if model == capi.MODEL_FOV:
+        nx, ny = x / z, y / z
+        r = np.sqrt(nx * nx + ny * ny)
+        om = K[4]
+        rd = np.arctan(2 * r * np.tan(om / 2)) / np.maximum(r * om, 1e-300)
+        return np.stack([K[0] * rd * nx + K[2], K[0] * K[1] * rd * ny + K[3]], -1)
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        ux, uy = K[0] * x / z, K[0] * K[1] * y / z
+        r2 = ux * ux + uy * uy
+        k = K[4]
+        den = 2 * k * r2
+        sc = np.where(np.abs(den) < 1e-15, 1.0, (1 - np.sqrt(np.maximum(1 - 4 * k * r2, 0))) / np.where(np.abs(den) < 1e-15, 1.0, den))
+        return np.stack([ux * sc + K[2], uy * sc + K[3]], -1)
+    raise ValueError(model)
+
+
+def default_intrinsics(model, f=1000.0, cx=500.0, cy=500.0):
+    K = np.zeros(capi.THB_INTR_STRIDE)
+    if model in (capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION):
+        K[:4] = [f, 1.0, cx, cy]
+        K[4] = 0.75 if model == capi.MODEL_FOV else -1e-8
+    else:
+        K[:5] = [f, 1.0, 0.0, cx, cy]
+        if model == capi.MODEL_PINHOLE:
+            K[5:7] = [0.0, 0.0]
+        elif model == capi.MODEL_DOUBLE_SPHERE:
+            K[5:7] = [-0.27, 0.57]
+        elif model == capi.MODEL_EXTENDED_UNIFIED:
+            K[5:7] = [0.6, 1.1]
+        elif model == capi.MODEL_FISHEYE:
+            K[5:9] = [-0.02, 0.003, 0.0, 0.0]
+    return K
+
+
+def make_ba_problem(num_cameras=10, num_points=500, obs_per_point=4, models=(capi.MODEL_PINHOLE,),
+                    seed=0, pixel_sigma=0.5, pos_sigma=0.02, rot_sigma=0.01, pt_sigma=0.02,
+                    num_rings=1, ring_radius=6.0, box=(2.0, 2.0, 2.0), focal=1000.0, image=1000.0,
+                    intr_const_mask=None, w_scale=False):
+    """Cameras on rings looking at the origin, points uniform in a box, `obs_per_point` random
+    in-frame observers per point, Gaussian pixel noise, perturbed initial parameters.
+    One shared intrinsics group per entry of `models` (cameras are assigned round-robin by halves).
+    Returns (HostBaProblem, ground_truth dict)."""
+    rng = np.random.default_rng(seed)
+    nc, npnt = num_cameras, num_points
+    per_ring = (nc + num_rings - 1) // num_rings
+    idx = np.arange(nc)
+    ring = idx // per_ring
+    ang = 2 * np.pi * (idx % per_ring) / per_ring + 0.37 * ring
+    rad = ring_radius * (1.0 + 0.08 * ring)
+    height = (ring - (num_rings - 1) / 2.0) * (box[2] * 0.35) + 0.0
+    Cw = np.stack([rad * np.cos(ang), rad * np.sin(ang), height + 0.5 * box[2]], -1)
+    target = rng.normal(0.0, 0.05 * min(box[0], box[1]), size=(nc, 3))
+    R = _look_at(Cw, target)
+    aa = _rotvec_from_matrix(R)
+    pts = (rng.random((npnt, 3)) * 2.0 - 1.0) * np.array(box)
+
+    ng = len(models)
+    cam_group = (idx * ng // nc).astype(np.int32)
+    intr = np.stack([default_intrinsics(m, focal if m not in (capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED) else 0.4 * focal,
+                                         image / 2, image / 2) for m in models])
+    intr_model = np.array(models, dtype=np.int32)
+
+    # choose observers: random candidates, keep the first `obs_per_point` that are in frame
+    k = obs_per_point
+    obs_cam = np.empty((npnt, k), dtype=np.int32)
+    filled = np.zeros(npnt, dtype=np.int32)
+    for _ in range(64):
+        todo = np.nonzero(filled < k)[0]
+        if todo.size == 0:
+            break
+        cand = rng.integers(0, nc, size=todo.size).astype(np.int32)
+        pc = np.einsum("nij,nj->ni", R[cand], pts[todo] - Cw[cand])
+        ok = pc[:, 2] > 0.5
+        pix = np.zeros((todo.size, 2))
+        for g, m in enumerate(models):
+            sel = ok & (cam_group[cand] == g)
+            if sel.any():
+                pix[sel] = project(m, intr[g], pc[sel])
+        ok &= np.all((pix > 0.02 * image) & (pix < 0.98 * image), axis=1)
+        # reject duplicates
+        dup = (obs_cam[todo] == cand[:, None]) & (np.arange(k)[None, :] < filled[todo][:, None])
+        ok &= ~dup.any(axis=1)
+        t = todo[ok]
+        obs_cam[t, filled[t]] = cand[ok]
+        filled[t] += 1
+    if (filled < k).any():
+        raise RuntimeError("could not find %d in-frame observers for every point" % k)
+    obs_pt = np.repeat(np.arange(npnt, dtype=np.int32), k)
+    obs_cam = obs_cam.reshape(-1)
+    pc = np.einsum("nij,nj->ni", R[obs_cam], pts[obs_pt] - Cw[obs_cam])
+    xy = np.zeros((obs_cam.size, 2))
+    for g, m in enumerate(models):
+        sel = cam_group[obs_cam] == g
+        xy[sel] = project(m, intr[g], pc[sel])
+    xy += rng.normal(0.0, pixel_sigma, size=xy.shape) if pixel_sigma > 0 else 0.0
+    # shuffle observation order (the reference iterates hash maps: no particular order)
+    perm = rng.permutation(obs_cam.size)
+    obs_cam, obs_pt, xy = obs_cam[perm], obs_pt[perm], xy[perm]
+
+    gt = dict(cam_ext=np.concatenate([Cw, aa], 1), pts=np.concatenate([pts, np.ones((npnt, 1))], 1), intr=intr.copy())
+    cam0 = gt["cam_ext"].copy()
+    cam0[:, :3] += rng.normal(0, pos_sigma, (nc, 3)) if pos_sigma > 0 else 0.0
+    cam0[:, 3:] += rng.normal(0, rot_sigma, (nc, 3)) if rot_sigma > 0 else 0.0
+    pts0 = gt["pts"].copy()
+    pts0[:, :3] += rng.normal(0, pt_sigma, (npnt, 3)) if pt_sigma > 0 else 0.0
+    if w_scale:  # exercise the free homogeneous scale
+        s = rng.uniform(0.5, 2.0, (npnt, 1))
+        pts0 *= s
+    if intr_const_mask is None:
+        intr_const = np.array([(1 << capi.MODEL_NUM_PARAMS[m]) - 1 for m in models], dtype=np.uint16)
+    else:
+        intr_const = np.array(intr_const_mask, dtype=np.uint16)
+    prob = capi.HostBaProblem(dict(
+        cam_ext=cam0, cam_const=np.zeros(nc, np.uint8), cam_group=cam_group, intr=intr, intr_model=intr_model,
+        intr_const=intr_const, pts=pts0, pt_const=np.zeros(npnt, np.uint8),
+        obs_cam=obs_cam, obs_pt=obs_pt, obs_xy=xy, obs_sqrt_info=np.ones_like(xy)))
+    return prob, gt
+
+
+def config_c1(seed=1):
+    """BASELINE.json configs[0]: Pinhole, 10 cams / 500 pts / 2k obs."""
+    return make_ba_problem(10, 500, 4, seed=seed, num_rings=1, ring_radius=6.0, box=(2.0, 2.0, 2.0))
+
+
+def config_c2(seed=2, scale=1.0):
+    """BASELINE.json configs[1]: Pinhole, 1k cams / 100k pts / 1M obs (scale<1 shrinks all three)."""
+    nc = max(10, int(round(1000 * scale)))
+    npnt = max(50, int(round(100000 * scale)))
+    return make_ba_problem(nc, npnt, 10, seed=seed, num_rings=10 if nc >= 100 else 2, ring_radius=24.0,
+                           box=(10.0, 10.0, 3.0))
+
+
+def config_c3(seed=3, scale=1.0):
+    """BASELINE.json configs[2]: DoubleSphere + ExtendedUnified, 500 cams / 50k pts / 8 obs per point,
+    intrinsics_to_optimize = FOCAL_LENGTH | RADIAL_DISTORTION (constant: a, s, cx, cy)."""
+    nc = max(10, int(round(500 * scale)))
+    npnt = max(50, int(round(50000 * scale)))
+    const = 0b0011110  # aspect, skew, cx, cy constant; f, and the two distortion slots free
+    return make_ba_problem(nc, npnt, 8, models=(capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED), seed=seed,
+                           num_rings=5 if nc >= 50 else 2, ring_radius=24.0, box=(10.0, 10.0, 3.0),
+                           intr_const_mask=[const, const])

@@ -1,0 +1,212 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path through the C-ABI vs the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from pytheiasfm_b200 import capi, synthetic
+
+pytestmark = pytest.mark.gpu
+
+ALL_MODELS = [capi.MODEL_PINHOLE, capi.MODEL_FISHEYE, capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION,
+              capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED]
+
+
+def gpu_evaluate(lib, prob):
+    n = prob.num_observations
+    r = np.zeros((n, 2)); jc = np.zeros((n, 2, 6)); ji = np.zeros((n, 2, capi.THB_INTR_STRIDE)); jp = np.zeros((n, 2, 4))
+    ok = np.zeros(n, np.uint8)
+    p = prob.struct()
+    capi.check(lib.thb_ba_evaluate(C.byref(p), *[a.ctypes.data_as(C.c_void_p) for a in (r, jc, ji, jp, ok)], None))
+    return r, jc, ji, jp, ok
+
+
+def gpu_solve(lib, prob, opts):
+    s = capi.ThbBaSummary()
+    p = prob.struct()
+    capi.check(lib.thb_ba_solve(C.byref(p), C.byref(opts), C.byref(s), None))
+    return s.as_dict()
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_k1_residual_jacobian_vs_dual_number_oracle(lib, oracle, model):
+    """K1 against the oracle's Jet (ceres-autodiff-equivalent) Jacobian: <= 1e-12 relative."""
+    prob, _ = synthetic.make_ba_problem(8, 300, 4, models=(model,), seed=20 + model, w_scale=True)
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        prob.a["intr"][0, 4] = -2e-8
+    g = gpu_evaluate(lib, prob)
+    o = oracle.ba_evaluate(prob)
+    assert g[4].all() and o[4].all()
+    for name, a, b in zip(("r", "jc", "ji", "jp"), g[:4], o[:4]):
+        scale = np.abs(b).max()
+        assert np.abs(a - b).max() <= 1e-12 * scale, (name, np.abs(a - b).max() / scale)
+
+
+def test_k1_mixed_models_and_failure_flags(lib, oracle):
+    prob, _ = synthetic.make_ba_problem(10, 200, 4, models=(capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED, capi.MODEL_FISHEYE), seed=31)
+    # put one point behind a double-sphere camera's valid cone and one on top of a camera centre
+    c0 = int(prob.a["obs_cam"][0]); p0 = int(prob.a["obs_pt"][0])
+    prob.a["pts"][p0, :3] = prob.a["cam_ext"][c0, :3]; prob.a["pts"][p0, 3] = 1.0
+    g = gpu_evaluate(lib, prob)
+    o = oracle.ba_evaluate(prob)
+    np.testing.assert_array_equal(g[4], o[4])
+    assert g[4][0] == 0
+    good = o[4].astype(bool)
+    for a, b in zip(g[:4], o[:4]):
+        assert np.abs(a[good] - b[good]).max() <= 1e-12 * np.abs(b[good]).max()
+
+
+def _compare_solves(lib, oracle, prob, opts, rel=1e-6, check_log=True):
+    pg, po = prob.copy(), prob.copy()
+    g = gpu_solve(lib, pg, opts)
+    o = oracle.ba_solve(po, opts)
+    assert o["rc"] == 0
+    assert g["success"] == o["success"] == 1
+    assert abs(g["initial_cost"] - o["initial_cost"]) <= 1e-10 * o["initial_cost"]
+    assert abs(g["final_cost"] - o["final_cost"]) <= rel * max(o["final_cost"], 1e-30), (g["final_cost"], o["final_cost"])
+    assert g["termination_type"] == o["termination_type"]
+    if check_log:
+        assert g["num_iterations"] == o["num_iterations"]
+        np.testing.assert_allclose(g["iter_cost"], o["iter_cost"], rtol=1e-6)
+        np.testing.assert_allclose(g["iter_radius"], o["iter_radius"], rtol=1e-4)
+    assert g["gpu_launches"] > 0
+    return g, o, pg, po
+
+
+def test_c1_full_ba_matches_oracle(lib, oracle):
+    """BASELINE configs[0]: 10 cams / 500 pts / 2k obs, defaults (inner iterations off)."""
+    prob, _ = synthetic.config_c1()
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], atol=1e-6)
+    np.testing.assert_allclose(pg.a["pts"], po.a["pts"], atol=1e-5)
+
+
+def test_c1_forced_iterations_trajectory(lib, oracle):
+    """Tolerances 0, K forced iterations (the benchmark's setting): same cost at every iteration."""
+    prob, _ = synthetic.config_c1(seed=4)
+    o = capi.default_options(lib)
+    o.function_tolerance = 0.0; o.gradient_tolerance = 0.0; o.parameter_tolerance = 0.0; o.max_num_iterations = 12
+    _compare_solves(lib, oracle, prob, o)
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_every_camera_model_full_ba(lib, oracle, model):
+    prob, _ = synthetic.make_ba_problem(12, 400, 4, models=(model,), seed=40 + model)
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        prob.a["intr"][0, 4] = -2e-8
+    _compare_solves(lib, oracle, prob, capi.default_options(lib))
+
+
+@pytest.mark.parametrize("loss", [capi.LOSS_HUBER, capi.LOSS_SOFTLONE, capi.LOSS_CAUCHY, capi.LOSS_ARCTAN, capi.LOSS_TUKEY, capi.LOSS_TRUNCATED])
+def test_robust_losses(lib, oracle, loss):
+    prob, _ = synthetic.make_ba_problem(10, 300, 4, seed=60 + loss)
+    rng = np.random.default_rng(2)
+    bad = rng.choice(prob.num_observations, 50, replace=False)
+    prob.a["obs_xy"][bad] += rng.normal(0, 25, (50, 2))
+    o = capi.default_options(lib); o.loss_function_type = loss; o.robust_loss_width = 2.0
+    _compare_solves(lib, oracle, prob, o, check_log=loss not in (capi.LOSS_TUKEY, capi.LOSS_TRUNCATED))
+
+
+def test_bundle_adjust_view_semantics(lib, oracle):
+    """BundleAdjustView (bundle_adjustment.cc:220-236): one camera free, every point constant."""
+    prob, gt = synthetic.make_ba_problem(1, 100, 1, seed=52, pixel_sigma=0.0, pt_sigma=0.0, pos_sigma=1e-3, rot_sigma=1e-2)
+    prob.a["pt_const"][:] = 1
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib), rel=1e-3, check_log=False)
+    assert np.linalg.norm(pg.a["cam_ext"][0, :3] - gt["cam_ext"][0, :3]) < 1e-4
+
+
+@pytest.mark.parametrize("homogeneous", [1, 0])
+def test_bundle_adjust_tracks_semantics(lib, oracle, homogeneous):
+    """BundleAdjustTracks (bundle_adjustment.cc:389-418): every camera constant, points free."""
+    prob, _ = synthetic.make_ba_problem(4, 100, 3, seed=53, pixel_sigma=0.5, pos_sigma=0.0, rot_sigma=0.0, pt_sigma=0.05)
+    prob.a["cam_const"][:] = capi.CAM_CONST_POSITION | capi.CAM_CONST_ORIENTATION
+    o = capi.default_options(lib); o.use_homogeneous_point_parametrization = homogeneous
+    _compare_solves(lib, oracle, prob, o)
+
+
+@pytest.mark.parametrize("mask", [capi.CAM_CONST_POSITION, capi.CAM_CONST_ORIENTATION])
+def test_constant_position_or_orientation(lib, oracle, mask):
+    """BundleAdjustmentOptions::constant_camera_{position,orientation} (bundle_adjuster.cc:357-380)."""
+    prob, _ = synthetic.make_ba_problem(8, 200, 4, seed=71)
+    before = prob.a["cam_ext"].copy()
+    prob.a["cam_const"][:] = mask
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    sl = slice(0, 3) if mask == capi.CAM_CONST_POSITION else slice(3, 6)
+    np.testing.assert_array_equal(pg.a["cam_ext"][:, sl], before[:, sl])
+
+
+def test_partial_reconstruction_semantics(lib, oracle):
+    """BundleAdjustPartialReconstruction (bundle_adjustment.cc:111-143): some views constant, some tracks constant."""
+    prob, _ = synthetic.make_ba_problem(12, 300, 4, seed=72)
+    prob.a["cam_const"][::3] = 3
+    prob.a["pt_const"][::5] = 1
+    # a constant camera observing a constant point would be a fixed-cost block: drop those observations
+    keep = ~((prob.a["cam_const"][prob.a["obs_cam"]] == 3) & (prob.a["pt_const"][prob.a["obs_pt"]] == 1))
+    arrays = dict(prob.a)
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        arrays[k] = prob.a[k][keep]
+    prob = capi.HostBaProblem(arrays)
+    _compare_solves(lib, oracle, prob, capi.default_options(lib))
+
+
+def test_device_resident_session_matches_one_shot(lib):
+    """thb_ba_create/iterate/finish with THB_MEM_DEVICE pointers == thb_ba_solve with host pointers."""
+    import torch
+    prob, _ = synthetic.config_c1(seed=9)
+    opts = capi.default_options(lib)
+    opts.function_tolerance = 0.0; opts.gradient_tolerance = 0.0; opts.parameter_tolerance = 0.0; opts.max_num_iterations = 8
+    ref = prob.copy()
+    g = gpu_solve(lib, ref, opts)
+    dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
+    p = prob.struct()
+    p.memory_space = capi.THB_MEM_DEVICE
+    for k, v in dev.items():
+        setattr(p, k, None if v is None else v.data_ptr())
+    sess = C.c_void_p()
+    stream = torch.cuda.current_stream().cuda_stream
+    capi.check(lib.thb_ba_create(C.byref(p), C.byref(opts), C.c_void_p(stream), C.byref(sess)))
+    ran = C.c_int32(0)
+    capi.check(lib.thb_ba_iterate(sess, 3, C.byref(ran)))
+    assert ran.value == 3
+    capi.check(lib.thb_ba_iterate(sess, 100, C.byref(ran)))
+    assert ran.value == 5
+    s = capi.ThbBaSummary()
+    capi.check(lib.thb_ba_finish(sess, C.byref(s)))
+    assert s.num_iterations == 8
+    assert abs(s.final_cost - g["final_cost"]) <= 1e-12 * g["final_cost"]
+    np.testing.assert_allclose(dev["cam_ext"].cpu().numpy(), ref.a["cam_ext"], rtol=0, atol=1e-12)
+
+
+def test_c2_scaled_parity_and_full_size_properties(lib, oracle):
+    """configs[1] at 1/20 scale against the oracle; at full size (1k cams / 100k pts / 1M obs) through
+    size-independent properties: monotone cost, noise-floor final cost, idempotence at the optimum."""
+    prob, _ = synthetic.config_c2(scale=0.05)
+    o = capi.default_options(lib)
+    o.function_tolerance = 0.0; o.gradient_tolerance = 0.0; o.parameter_tolerance = 0.0; o.max_num_iterations = 8
+    _compare_solves(lib, oracle, prob, o)
+
+    prob, _ = synthetic.config_c2()
+    assert prob.num_observations == 1000000 and prob.num_cameras == 1000 and prob.num_points == 100000
+    o.max_num_iterations = 20
+    g = gpu_solve(lib, prob, o)
+    assert g["success"] == 1 and g["num_iterations"] == 20
+    costs = np.array(g["iter_cost"])
+    assert np.all(np.diff(costs) <= 1e-9 * costs[:-1])
+    dof = 2 * prob.num_observations - (6 * prob.num_cameras + 3 * prob.num_points - 7)
+    assert abs(g["final_cost"] / (0.5 * 0.25 * dof) - 1.0) < 0.02      # chi^2 noise floor, sigma = 0.5 px
+    o2 = capi.default_options(lib)
+    g2 = gpu_solve(lib, prob, o2)                                       # restart at the optimum: nothing to gain
+    assert g2["num_iterations"] <= 2 and abs(g2["final_cost"] - g["final_cost"]) <= 1e-6 * g["final_cost"]
+
+
+def test_invalid_arguments_are_error_codes(lib):
+    prob, _ = synthetic.make_ba_problem(3, 20, 3, seed=1)
+    s = capi.ThbBaSummary()
+    o = capi.default_options(lib)
+    bad = prob.copy(); bad.a["obs_pt"][3] = 10**6
+    p = bad.struct()
+    assert lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None) == capi.THB_E_INVALID_ARGUMENT
+    o.use_inner_iterations = 1
+    p = prob.struct()
+    assert lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None) == capi.THB_E_UNSUPPORTED
+    assert lib.thb_ba_solve(None, None, None, None) == capi.THB_E_INVALID_ARGUMENT

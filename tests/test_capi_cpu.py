@@ -1,0 +1,62 @@
+"""CPU checks of the boundary: the C-ABI library loads, exports every symbol include/theia_b200.h
+declares, struct sizes match, and compute entry points fail loudly without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from pytheiasfm_b200 import capi, synthetic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "theia_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(thb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = _declared_symbols()
+    assert len(syms) >= 9
+    for name in syms:
+        assert hasattr(lib, name), name
+
+
+def test_default_options_match_reference_defaults(lib):
+    o = capi.default_options(lib)
+    # bundle_adjustment.h:87-167
+    assert o.loss_function_type == capi.LOSS_TRIVIAL and o.robust_loss_width == 2.0
+    assert o.use_homogeneous_point_parametrization == 1
+    assert o.max_num_iterations == 100
+    assert (o.function_tolerance, o.gradient_tolerance, o.parameter_tolerance) == (1e-6, 1e-10, 1e-8)
+    assert o.max_trust_region_radius == 1e12
+    assert o.use_inner_iterations == 0  # deliberately off, see DESIGN.md
+
+
+def test_oracle_and_product_agree_on_default_options(lib, oracle):
+    a = capi.default_options(lib)
+    b = oracle.default_options()
+    assert bytes(a) == bytes(b)
+
+
+def test_no_cpu_fallback(lib):
+    if lib.thb_device_count() > 0:
+        pytest.skip("GPU present")
+    prob, _ = synthetic.make_ba_problem(3, 20, 3, seed=1)
+    s = capi.ThbBaSummary()
+    p = prob.struct()
+    o = capi.default_options(lib)
+    rc = lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None)
+    assert rc == capi.THB_E_NO_DEVICE
+    assert b"no CPU path" in lib.thb_last_error() or b"sm_100" in lib.thb_last_error()
+
+
+def test_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "pytheiasfm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.replace("no oracle", ""), os.path.join(dirpath, f)

@@ -1,0 +1,157 @@
+"""CPU tests of the oracle (the checker): derivative exactness, manifold identities, LM behaviour,
+an independent scipy cross-check of the final cost, and the reference's own BA property tests
+(bundle_adjustment_test.cc:76-258) restated on the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from pytheiasfm_b200 import capi, synthetic
+
+ALL_MODELS = [capi.MODEL_PINHOLE, capi.MODEL_FISHEYE, capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION,
+              capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED]
+
+
+def _fd(oracle, prob, name, idx, eps):
+    a = prob.copy(); a.a[name][idx] += eps
+    b = prob.copy(); b.a[name][idx] -= eps
+    return (oracle.ba_evaluate(a)[0] - oracle.ba_evaluate(b)[0]) / (2 * eps)
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_jet_jacobians_match_central_differences(oracle, model):
+    prob, _ = synthetic.make_ba_problem(6, 60, 3, models=(model,), seed=10 + model)
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        prob.a["intr"][0, 4] = -2e-8
+    r, jc, ji, jp, ok = oracle.ba_evaluate(prob)
+    assert ok.all()
+    K = capi.MODEL_NUM_PARAMS[model]
+    for k in range(6):
+        d = _fd(oracle, prob, "cam_ext", (slice(None), k), 1e-6)
+        np.testing.assert_allclose(jc[:, :, k], d, rtol=2e-5, atol=2e-5 * np.abs(jc).max())
+    for k in range(4):
+        d = _fd(oracle, prob, "pts", (slice(None), k), 1e-6)
+        np.testing.assert_allclose(jp[:, :, k], d, rtol=2e-5, atol=2e-5 * np.abs(jp).max())
+    for k in range(K):
+        h = 1e-6 * max(1.0, abs(prob.a["intr"][0, k]))
+        if model == capi.MODEL_DIVISION_UNDISTORTION and k == 4:
+            h = 1e-10
+        d = _fd(oracle, prob, "intr", (0, k), h)
+        np.testing.assert_allclose(ji[:, :, k], d, rtol=5e-5, atol=5e-5 * np.abs(ji[:, :, k]).max() + 1e-9)
+    assert np.all(ji[:, :, K:] == 0)
+
+
+def test_sphere_manifold_identities(oracle):
+    lib = oracle.load()
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        x = rng.normal(size=4) * rng.uniform(0.1, 5)
+        d = rng.normal(size=3) * 0.3
+        out = np.zeros(4); J = np.zeros((4, 3))
+        lib.oracle_sphere_plus(x.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        lib.oracle_sphere_plus_jacobian(x.ctypes.data_as(C.c_void_p), J.ctypes.data_as(C.c_void_p))
+        assert abs(np.linalg.norm(out) - np.linalg.norm(x)) < 1e-12 * np.linalg.norm(x)   # stays on the sphere
+        np.testing.assert_allclose(J.T @ x, 0, atol=1e-12 * np.linalg.norm(x) ** 2)         # tangent to it
+        eps = 1e-6                                                                          # J = dPlus/ddelta at 0
+        for k in range(3):
+            e = np.zeros(3); e[k] = eps
+            p = np.zeros(4); m = np.zeros(4)
+            lib.oracle_sphere_plus(x.ctypes.data_as(C.c_void_p), e.ctypes.data_as(C.c_void_p), p.ctypes.data_as(C.c_void_p))
+            lib.oracle_sphere_plus(x.ctypes.data_as(C.c_void_p), (-e).ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p))
+            np.testing.assert_allclose((p - m) / (2 * eps), J[:, k], atol=1e-8 * np.linalg.norm(x))
+        z = np.zeros(3)
+        lib.oracle_sphere_plus(x.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        np.testing.assert_array_equal(out, x)
+
+
+def test_c1_converges_to_noise_floor(oracle):
+    prob, gt = synthetic.config_c1()
+    o = oracle.default_options()
+    s = oracle.ba_solve(prob, o)
+    assert s["rc"] == 0 and s["success"] == 1 and s["termination_type"] == capi.TERM_CONVERGENCE
+    dof = 2 * prob.num_observations - (6 * prob.num_cameras + 3 * prob.num_points - 7)
+    expected = 0.5 * 0.25 * dof
+    assert abs(s["final_cost"] - expected) / expected < 0.15
+    costs = s["iter_cost"]
+    assert all(costs[i + 1] <= costs[i] + 1e-9 for i in range(len(costs) - 1))
+
+
+def test_final_cost_matches_scipy_least_squares(oracle):
+    """Independent cross-check: a dense trust-region solver on the same residuals (Euclidean xyz,
+    w fixed at 1) must reach the same minimum as the oracle's LM + Schur + sphere manifold."""
+    from scipy.optimize import least_squares
+    prob, _ = synthetic.make_ba_problem(4, 24, 3, seed=5, pixel_sigma=0.5)
+    base = prob.copy()
+    nc, npnt = base.num_cameras, base.num_points
+
+    def fun(x):
+        q = base.copy()
+        q.a["cam_ext"][:] = x[: nc * 6].reshape(nc, 6)
+        q.a["pts"][:, :3] = x[nc * 6:].reshape(npnt, 3)
+        return oracle.ba_evaluate(q)[0].ravel()
+
+    x0 = np.concatenate([base.a["cam_ext"].ravel(), base.a["pts"][:, :3].ravel()])
+    sol = least_squares(fun, x0, method="trf", xtol=1e-15, ftol=1e-15, gtol=1e-12, max_nfev=400)
+    o = oracle.default_options()
+    o.function_tolerance = 1e-14; o.parameter_tolerance = 1e-14; o.gradient_tolerance = 1e-12; o.max_num_iterations = 200
+    s = oracle.ba_solve(prob, o)
+    assert s["success"] == 1
+    assert abs(s["final_cost"] - sol.cost) <= 1e-7 * sol.cost
+
+
+@pytest.mark.parametrize("loss", [capi.LOSS_HUBER, capi.LOSS_SOFTLONE, capi.LOSS_CAUCHY, capi.LOSS_ARCTAN, capi.LOSS_TUKEY, capi.LOSS_TRUNCATED])
+def test_robust_losses_reduce_cost(oracle, loss):
+    prob, _ = synthetic.make_ba_problem(8, 200, 4, seed=7)
+    rng = np.random.default_rng(1)
+    bad = rng.choice(prob.num_observations, 40, replace=False)
+    prob.a["obs_xy"][bad] += rng.normal(0, 30, (40, 2))  # outliers
+    o = oracle.default_options(); o.loss_function_type = loss; o.robust_loss_width = 2.0
+    rc, c0 = oracle.ba_cost(prob, o)
+    s = oracle.ba_solve(prob, o)
+    assert s["success"] == 1 and s["final_cost"] < c0
+    assert abs(s["initial_cost"] - c0) <= 1e-9 * c0
+
+
+def test_bundle_adjust_view_property(oracle):
+    """bundle_adjustment_test.cc:76-115,212-216: 1 camera, 100 points, points constant, start at the
+    noise-free truth: 2*final_cost/n < 1e-15. With 0.1 px noise (:218-222): < 0.1."""
+    prob, gt = synthetic.make_ba_problem(1, 100, 1, seed=52, pixel_sigma=0.0, pt_sigma=0.0, pos_sigma=0.0, rot_sigma=0.0)
+    prob.a["pt_const"][:] = 1
+    s = oracle.ba_solve(prob, oracle.default_options())
+    assert s["success"] == 1
+    assert 2 * s["final_cost"] / prob.num_observations < 1e-15
+    prob, gt = synthetic.make_ba_problem(1, 100, 1, seed=52, pixel_sigma=0.1, pt_sigma=0.0, pos_sigma=0.0, rot_sigma=0.0)
+    prob.a["pt_const"][:] = 1
+    s = oracle.ba_solve(prob, oracle.default_options())
+    assert s["success"] == 1 and 2 * s["final_cost"] / prob.num_observations < 0.1
+
+
+def test_bundle_adjust_view_recovers_pose(oracle):
+    """pytests/sfm/bundle_adjuster_test.py:6-15: position recovered to 1e-4 after 1e-3 position noise."""
+    prob, gt = synthetic.make_ba_problem(1, 100, 1, seed=52, pixel_sigma=0.0, pt_sigma=0.0, pos_sigma=1e-3, rot_sigma=1e-2)
+    prob.a["pt_const"][:] = 1
+    s = oracle.ba_solve(prob, oracle.default_options())
+    assert s["success"] == 1
+    assert np.linalg.norm(prob.a["cam_ext"][0, :3] - gt["cam_ext"][0, :3]) < 1e-4
+
+
+@pytest.mark.parametrize("homogeneous", [1, 0])
+def test_bundle_adjust_tracks_property(oracle, homogeneous):
+    """bundle_adjustment_test.cc:117-207,224-258: fixed cameras, 100 points observed 3 times, XYZW /
+    XYZW_MANIFOLD, start at the truth: 2*final_cost/n < 1e-15 noise-free, < 0.5 with 0.5 px noise.
+    Plus a perturbed start (ours): converges back to a ~zero cost."""
+    for pix, pt_sigma, bound in [(0.0, 0.0, 1e-15), (0.5, 0.0, 0.5), (0.0, 0.05, 1e-9)]:
+        prob, gt = synthetic.make_ba_problem(4, 100, 3, seed=53, pixel_sigma=pix, pos_sigma=0.0, rot_sigma=0.0, pt_sigma=pt_sigma)
+        prob.a["cam_const"][:] = capi.CAM_CONST_POSITION | capi.CAM_CONST_ORIENTATION
+        o = oracle.default_options(); o.use_homogeneous_point_parametrization = homogeneous
+        s = oracle.ba_solve(prob, o)
+        assert s["success"] == 1
+        assert 2 * s["final_cost"] / prob.num_observations < bound
+
+
+def test_rejects_unsupported_and_invalid(oracle):
+    prob, _ = synthetic.make_ba_problem(3, 20, 3, seed=1)
+    o = oracle.default_options(); o.use_inner_iterations = 1
+    assert oracle.ba_solve(prob.copy(), o)["rc"] == capi.THB_E_UNSUPPORTED
+    bad = prob.copy(); bad.a["obs_cam"][0] = 99
+    assert oracle.ba_solve(bad, oracle.default_options())["rc"] == capi.THB_E_INVALID_ARGUMENT
