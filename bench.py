@@ -34,15 +34,16 @@ def workload_config(args):
                 int(round(1000 * args.scale)), int(round(100000 * args.scale)), int(round(1000000 * args.scale))),
             "intrinsics_to_optimize": "NONE", "loss": "TRIVIAL", "use_homogeneous_point_parametrization": True,
             "use_inner_iterations": False, "linear_solver": "SCHUR + dense Cholesky (exact)",
-            "tolerances": 0.0, "l2": "working set (J planes 160 MB + S 290 MB) exceeds the 126 MB L2",
+            "tolerances": "disabled (forced K iterations)", "l2": "working set (J planes 160 MB + S 290 MB) exceeds the 126 MB L2",
             "parallelism": "replicas only (BA is single-GPU)"}
 
 
 def make_options(lib_or_oracle_default, iters):
     o = lib_or_oracle_default
-    o.function_tolerance = 0.0
-    o.gradient_tolerance = 0.0
-    o.parameter_tolerance = 0.0
+    # negative = test disabled (theia_b200.h): exactly `iters` iterations run even once the cost stops changing
+    o.function_tolerance = -1.0
+    o.gradient_tolerance = -1.0
+    o.parameter_tolerance = -1.0
     o.max_num_iterations = iters
     return o
 

@@ -114,9 +114,9 @@ typedef struct ThbBaOptions {
   int32_t verbose;
   int32_t max_num_consecutive_invalid_steps; /* Ceres default 5                       */
   double robust_loss_width;
-  double function_tolerance;
-  double gradient_tolerance;
-  double parameter_tolerance;
+  double function_tolerance;  /* the three tolerances: Ceres semantics; a NEGATIVE value disables */
+  double gradient_tolerance;  /* the test (extension used by benchmark drivers to force exactly   */
+  double parameter_tolerance; /* max_num_iterations iterations; Ceres itself rejects negatives)   */
   double max_trust_region_radius;
   double initial_trust_region_radius; /* 1e4   */
   double min_trust_region_radius;     /* 1e-32 */
@@ -214,6 +214,14 @@ int thb_ba_evaluate(const ThbBaProblem* problem, double* residuals, double* jac_
  */
 int thb_ba_time_jacobian(ThbBaSession* session, int32_t repeats, int32_t flush_l2,
                          double* avg_ms);
+
+/*
+ * Kernel-level entry for the parity tests of K4: solve the SPD system A x = b with the same dense
+ * FP64 Cholesky the BA path uses for the reduced camera system (the reference delegates this to
+ * Ceres' Schur solvers, bundle_adjuster.cc:65-88). A: n x n row-major (lower triangle read), host
+ * pointers. Returns THB_E_NUMERICAL if A is not positive definite.
+ */
+int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, void* cuda_stream);
 
 #ifdef __cplusplus
 }

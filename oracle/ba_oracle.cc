@@ -645,7 +645,7 @@ class BaOracle {
       // FinalizeIterationAndCheckIfMinimizerCanContinue
       if (elapsed() >= O.max_solver_time_in_seconds) { sum->termination_type = THB_TERM_NO_CONVERGENCE; break; }
       if (iteration >= O.max_num_iterations) { sum->termination_type = THB_TERM_NO_CONVERGENCE; break; }
-      if (step_is_successful && gradient_max_norm <= O.gradient_tolerance) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      if (O.gradient_tolerance >= 0.0 && step_is_successful && gradient_max_norm <= O.gradient_tolerance) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
       if (radius <= O.min_trust_region_radius) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
       ++iteration;
       step_is_successful = false;
@@ -699,10 +699,10 @@ class BaOracle {
       if (!Evaluate(cand, false, &cand_cost)) cand_cost = kMaxDouble;
       // ParameterToleranceReached
       const double step_norm = NormDiff(x, &cand);
-      if (step_norm <= O.parameter_tolerance * (x_norm + O.parameter_tolerance)) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      if (O.parameter_tolerance >= 0.0 && step_norm <= O.parameter_tolerance * (x_norm + O.parameter_tolerance)) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
       // FunctionToleranceReached
       const double cost_change = x_cost - cand_cost;
-      if (std::fabs(cost_change) <= O.function_tolerance * x_cost) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
+      if (O.function_tolerance >= 0.0 && std::fabs(cost_change) <= O.function_tolerance * x_cost) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
       // IsStepSuccessful (monotonic steps)
       const double relative_decrease = cand_cost >= kMaxDouble ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
       if (relative_decrease > O.min_relative_decrease) {

@@ -139,6 +139,8 @@ def load_library():
     lib.thb_ba_evaluate.restype = C.c_int
     lib.thb_ba_time_jacobian.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     lib.thb_ba_time_jacobian.restype = C.c_int
+    lib.thb_dense_spd_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.thb_dense_spd_solve.restype = C.c_int
     _lib = lib
     return lib
 

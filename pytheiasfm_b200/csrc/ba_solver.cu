@@ -318,7 +318,7 @@ int OneIteration(ThbBaSession* s) {
   if (rc != THB_OK) return rc;
   if (want_grad) {
     s->gradient_max_norm = s->h_scal[SC_GRADMAX];
-    if (s->gradient_max_norm <= O.gradient_tolerance) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+    if (O.gradient_tolerance >= 0.0 && s->gradient_max_norm <= O.gradient_tolerance) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
   }
   ++s->iteration;
   s->step_is_successful = false;
@@ -335,10 +335,10 @@ int OneIteration(ThbBaSession* s) {
   const double cand_cost = s->h_flag[FL_EVAL_CAND] ? std::numeric_limits<double>::max() : s->h_scal[SC_COST_CAND];
   // ParameterToleranceReached
   const double step_norm = std::sqrt(s->h_scal[SC_STEP2]);
-  if (step_norm <= O.parameter_tolerance * (s->x_norm + O.parameter_tolerance)) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  if (O.parameter_tolerance >= 0.0 && step_norm <= O.parameter_tolerance * (s->x_norm + O.parameter_tolerance)) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
   // FunctionToleranceReached
   const double cost_change = s->x_cost - cand_cost;
-  if (std::fabs(cost_change) <= O.function_tolerance * s->x_cost) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
+  if (O.function_tolerance >= 0.0 && std::fabs(cost_change) <= O.function_tolerance * s->x_cost) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
   // IsStepSuccessful (monotonic)
   const double relative_decrease = cand_cost >= std::numeric_limits<double>::max() ? std::numeric_limits<double>::lowest()
                                                                                    : cost_change / model_cost_change;
@@ -666,6 +666,31 @@ int thb_ba_time_jacobian(ThbBaSession* s, int32_t repeats, int32_t flush_l2, dou
   // the cost accumulator was bumped by the extra launches: restore it
   THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_X, 0, sizeof(double), s->st));
   *avg_ms = total / repeats;
+  return THB_OK;
+}
+
+int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, void* cuda_stream) {
+  if (!A || !b || !x || n <= 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DenseChol ch;
+  if ((rc = ch.Init(n)) != THB_OK) { ch.Free(); return rc; }
+  DevBufs B;
+  int* d_fail = B.get<int>(1);
+  int launches = 0, h_fail = 0;
+  cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
+  if (e == cudaSuccess) rc = ch.Clear(st);
+  if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpy2DAsync(ch.A, sizeof(double) * ch.ld, A, sizeof(double) * n, sizeof(double) * n, n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpyAsync(ch.RhsRow(), b, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess && rc == THB_OK) rc = ch.FactorAndSolve(st, d_fail, &launches);
+  if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpyAsync(x, ch.x, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == THB_OK) e = cudaStreamSynchronize(st);
+  ch.Free();
+  if (e != cudaSuccess) THB_FAIL(THB_E_CUDA, cudaGetErrorString(e));
+  if (rc != THB_OK) return rc;
+  if (h_fail) THB_FAIL(THB_E_NUMERICAL, "matrix is not positive definite");
   return THB_OK;
 }
 

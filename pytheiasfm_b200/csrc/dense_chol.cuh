@@ -7,17 +7,23 @@
 namespace thb {
 
 struct DenseChol {
-  int n = 0, n_pad = 0, ld = 0, nblk = 0;
-  double* A = nullptr;     // (n_pad + 64) x ld, row-major; lower triangle = S, row n_pad = rhs
+  int n = 0, n_pad = 0, ld = 0, nblk = 0, rows_total = 0, num_sms = 148;
+  double* A = nullptr;     // (n_pad + 1) x ld, row-major; lower triangle = S, row n_pad = rhs
   double* dinv = nullptr;  // nblk inverted 64x64 diagonal factors
+  double* rdiag = nullptr; // 1 / L_kk
   double* x = nullptr;     // n_pad solution
+  int* ready = nullptr;    // per-64-block flags of the backward substitution
 
-  static size_t WorkspaceDoubles(int n);
   int Init(int n);
   void Free();
   int Clear(cudaStream_t st);  // zero A, identity on the padding
   double* RhsRow() { return A + (size_t)n_pad * ld; }
   int FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches);
+
+ private:
+  void PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches);
+  cudaStream_t s2 = nullptr;  // lookahead stream for the diag/panel chain
+  cudaEvent_t ev_start = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_col[2] = {nullptr, nullptr};
 };
 
 }  // namespace thb

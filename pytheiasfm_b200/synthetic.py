@@ -95,7 +95,7 @@ def default_intrinsics(model, f=1000.0, cx=500.0, cy=500.0):
     K = np.zeros(capi.THB_INTR_STRIDE)
     if model in (capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION):
         K[:4] = [f, 1.0, cx, cy]
-        K[4] = 0.75 if model == capi.MODEL_FOV else -1e-8
+        K[4] = 0.75 if model == capi.MODEL_FOV else -5e-7
     else:
         K[:5] = [f, 1.0, 0.0, cx, cy]
         if model == capi.MODEL_PINHOLE:

@@ -22,7 +22,7 @@ def _fd(oracle, prob, name, idx, eps):
 def test_jet_jacobians_match_central_differences(oracle, model):
     prob, _ = synthetic.make_ba_problem(6, 60, 3, models=(model,), seed=10 + model)
     if model == capi.MODEL_DIVISION_UNDISTORTION:
-        prob.a["intr"][0, 4] = -2e-8
+        prob.a["intr"][0, 4] = -5e-7
     r, jc, ji, jp, ok = oracle.ba_evaluate(prob)
     assert ok.all()
     K = capi.MODEL_NUM_PARAMS[model]
