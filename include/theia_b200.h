@@ -223,6 +223,69 @@ int thb_ba_time_jacobian(ThbBaSession* session, int32_t repeats, int32_t flush_l
  */
 int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, void* cuda_stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * RANSAC two-view geometric verification (hot path 2).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* RansacParameters (solvers/sample_consensus_estimator.h:58-126). The reference's `rng` member is a
+ * process-global generator that Python cannot set; here every pair carries its own seed and its
+ * RANSAC run is what the reference does right after `RandomNumberGenerator rng(seed)` (util/random.cc:54-62). */
+typedef struct ThbRansacParams {
+  double error_thresh;        /* on SQUARED errors; must be > 0 (sample_consensus_estimator.h:217)   */
+  double failure_probability; /* in (0, 1)                                                          */
+  double min_inlier_ratio;    /* in [0, 1]                                                          */
+  int32_t min_iterations;
+  int32_t max_iterations;
+  int32_t use_mle;            /* MLEQualityMeasurement instead of InlierSupport                     */
+  int32_t use_lo;             /* must be 0: LO refinement (two-view BA) is "next", THB_E_UNSUPPORTED */
+  int32_t lo_start_iterations;
+  int32_t ransac_type;        /* RansacType: only RANSAC (0) (create_and_initialize_ransac_variant.h:52) */
+} ThbRansacParams;
+
+/* A batch of image pairs: pair p owns correspondences [pair_offset[p], pair_offset[p+1]). */
+typedef struct ThbPairBatch {
+  int32_t num_pairs;
+  int32_t memory_space;       /* THB_MEM_HOST or THB_MEM_DEVICE for every pointer                   */
+  const int64_t* pair_offset; /* [num_pairs + 1]                                                    */
+  const double* corr;         /* [total * 4] normalised x1, y1, x2, y2 (FeatureCorrespondence::feature{1,2}.point_, */
+                              /*             matching/feature_correspondence.h:49-72)               */
+  const uint32_t* seed;       /* [num_pairs]                                                        */
+} ThbPairBatch;
+
+/* RelativePose (sfm/estimators/estimate_relative_pose.h:49-53) + RansacSummary
+ * (sample_consensus_estimator.h:129-144); matrices row-major. */
+typedef struct ThbRelPoseResult {
+  int32_t success;            /* return value of EstimateRelativePose                               */
+  int32_t num_inliers;
+  int32_t num_iterations;
+  int32_t num_input_data_points;
+  double confidence;
+  double best_cost;
+  double essential_matrix[9];
+  double rotation[9];
+  double position[3];
+} ThbRelPoseResult;
+
+void thb_ransac_default_params(ThbRansacParams* params);
+
+/*
+ * theia::EstimateRelativePose (sfm/estimators/estimate_relative_pose.cc:159-172) for every pair of the batch:
+ * SampleConsensusEstimator::Estimate (sample_consensus_estimator.h:299-415) with RandomSampler, the five-point
+ * solver, cheirality-gated Sampson scoring and the adaptive iteration bound, replayed exactly in iteration
+ * order. results: [num_pairs]; inlier_mask: [total] (1 = RansacSummary::inliers contains the index), may be
+ * NULL. Both in the batch's memory space.
+ */
+int thb_ransac_relpose_batch(const ThbPairBatch* batch, const ThbRansacParams* params,
+                             ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream);
+
+/*
+ * theia::FivePointRelativePose (sfm/pose/five_point_relative_pose.cc:212-293), minimal case, for `count`
+ * independent 5-point samples (host pointers): x1, x2 [count*5*2]; E_out [count*10*9] row-major, in the
+ * reference's solution order; num_solutions [count] (0 => the reference returns false).
+ */
+int thb_five_point_relative_pose(const double* x1, const double* x2, int32_t count, double* E_out,
+                                 int32_t* num_solutions, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,16 @@ def load():
         lib.oracle_ba_cost.argtypes = [C.POINTER(capi.ThbBaProblem), C.POINTER(capi.ThbBaOptions), C.POINTER(C.c_double)]
         lib.oracle_sphere_plus.argtypes = [C.c_void_p] * 3
         lib.oracle_sphere_plus_jacobian.argtypes = [C.c_void_p] * 2
+        lib.oracle_ransac_default_params.argtypes = [C.POINTER(capi.ThbRansacParams)]
+        lib.oracle_five_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.oracle_ransac_relpose_batch.argtypes = [C.POINTER(capi.ThbPairBatch), C.POINTER(capi.ThbRansacParams), C.c_void_p, C.c_void_p, C.c_int32]
+        lib.oracle_jacobi_svd3.argtypes = [C.c_void_p] * 4
+        lib.oracle_eigen10.argtypes = [C.c_void_p] * 4
+        lib.oracle_fullpivlu_kernel_5x9.argtypes = [C.c_void_p] * 2
+        lib.oracle_fullpivlu_solve10.argtypes = [C.c_void_p] * 3
+        lib.oracle_sampson.argtypes = [C.c_void_p] * 2
+        lib.oracle_sampson.restype = C.c_double
+        lib.oracle_best_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -64,3 +74,31 @@ def ba_cost(prob, opts):
     p = prob.struct()
     rc = load().oracle_ba_cost(C.byref(p), C.byref(opts), C.byref(c))
     return rc, c.value
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def ransac_default_params():
+    p = capi.ThbRansacParams()
+    load().oracle_ransac_default_params(C.byref(p))
+    return p
+
+
+def five_point(x1, x2):
+    """x1, x2: [count, 5, 2] -> (E [count, 10, 3, 3], num_solutions [count])"""
+    x1 = np.ascontiguousarray(x1, np.float64); x2 = np.ascontiguousarray(x2, np.float64)
+    count = x1.shape[0]
+    E = np.zeros((count, 10, 3, 3)); n = np.zeros(count, np.int32)
+    load().oracle_five_point(_vp(x1), _vp(x2), count, _vp(E), _vp(n))
+    return E, n
+
+
+def ransac_relpose_batch(batch, params, threads=0):
+    """Returns (results structured array [num_pairs], inlier mask [total])."""
+    res = np.zeros(batch.num_pairs, capi.RELPOSE_DTYPE)
+    mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
+    b = batch.struct()
+    rc = load().oracle_ransac_relpose_batch(C.byref(b), C.byref(params), _vp(res), _vp(mask), threads)
+    return rc, res, mask

@@ -97,6 +97,56 @@ class ThbBaSummary(C.Structure):
         return d
 
 
+class ThbRansacParams(C.Structure):
+    _fields_ = [
+        ("error_thresh", C.c_double), ("failure_probability", C.c_double), ("min_inlier_ratio", C.c_double),
+        ("min_iterations", C.c_int32), ("max_iterations", C.c_int32), ("use_mle", C.c_int32), ("use_lo", C.c_int32),
+        ("lo_start_iterations", C.c_int32), ("ransac_type", C.c_int32),
+    ]
+
+
+class ThbPairBatch(C.Structure):
+    _fields_ = [("num_pairs", C.c_int32), ("memory_space", C.c_int32), ("pair_offset", C.c_void_p),
+                ("corr", C.c_void_p), ("seed", C.c_void_p)]
+
+
+class ThbRelPoseResult(C.Structure):
+    _fields_ = [
+        ("success", C.c_int32), ("num_inliers", C.c_int32), ("num_iterations", C.c_int32),
+        ("num_input_data_points", C.c_int32), ("confidence", C.c_double), ("best_cost", C.c_double),
+        ("essential_matrix", C.c_double * 9), ("rotation", C.c_double * 9), ("position", C.c_double * 3),
+    ]
+
+
+RELPOSE_DTYPE = np.dtype([("success", np.int32), ("num_inliers", np.int32), ("num_iterations", np.int32),
+                          ("num_input_data_points", np.int32), ("confidence", np.float64), ("best_cost", np.float64),
+                          ("essential_matrix", np.float64, (3, 3)), ("rotation", np.float64, (3, 3)),
+                          ("position", np.float64, (3,))])
+assert RELPOSE_DTYPE.itemsize == C.sizeof(ThbRelPoseResult)
+
+
+class HostPairBatch:
+    """Correspondences of a batch of image pairs in the C-ABI layout (host memory)."""
+
+    def __init__(self, corr_list, seeds):
+        self.num_pairs = len(corr_list)
+        sizes = [len(c) for c in corr_list]
+        self.pair_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        self.corr = (np.ascontiguousarray(np.concatenate(corr_list, 0), dtype=np.float64) if self.num_pairs and self.pair_offset[-1] > 0
+                     else np.zeros((0, 4)))
+        self.seed = np.ascontiguousarray(seeds, dtype=np.uint32)
+        assert self.corr.shape == (self.pair_offset[-1], 4) and self.seed.shape == (self.num_pairs,)
+
+    def struct(self):
+        b = ThbPairBatch()
+        b.num_pairs = self.num_pairs
+        b.memory_space = THB_MEM_HOST
+        b.pair_offset = _ptr(self.pair_offset)
+        b.corr = _ptr(self.corr)
+        b.seed = _ptr(self.seed)
+        return b
+
+
 class LibraryNotBuilt(RuntimeError):
     pass
 
@@ -139,6 +189,12 @@ def load_library():
     lib.thb_ba_evaluate.restype = C.c_int
     lib.thb_ba_time_jacobian.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     lib.thb_ba_time_jacobian.restype = C.c_int
+    lib.thb_ransac_default_params.argtypes = [C.POINTER(ThbRansacParams)]
+    lib.thb_ransac_default_params.restype = None
+    lib.thb_ransac_relpose_batch.argtypes = [C.POINTER(ThbPairBatch), C.POINTER(ThbRansacParams), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_ransac_relpose_batch.restype = C.c_int
+    lib.thb_five_point_relative_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_five_point_relative_pose.restype = C.c_int
     lib.thb_dense_spd_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.thb_dense_spd_solve.restype = C.c_int
     _lib = lib

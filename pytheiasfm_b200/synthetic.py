@@ -216,3 +216,45 @@ def config_c3(seed=3, scale=1.0):
     return make_ba_problem(nc, npnt, 8, models=(capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED), seed=seed,
                            num_rings=5 if nc >= 50 else 2, ring_radius=24.0, box=(10.0, 10.0, 3.0),
                            intr_const_mask=[const, const])
+
+
+def random_rotation(rng, max_deg):
+    axis = rng.normal(size=3); axis /= np.linalg.norm(axis)
+    return rotmat_from_rotvec(axis * np.deg2rad(rng.uniform(0, max_deg)))
+
+
+def make_pair(rng, n=2000, inlier_ratio=0.6, noise=1e-3, max_rot_deg=15.0):
+    """One image pair in normalised coordinates: inliers from random 3-D points (depth 4-10)
+    under a random rotation and a unit baseline, Gaussian noise; outliers uniform in [-1,1]^2.
+    Returns (corr [n,4], R, position, inlier flags)."""
+    R = random_rotation(rng, max_rot_deg)
+    c = rng.normal(size=3); c /= np.linalg.norm(c)          # camera-2 position (unit baseline)
+    ni = int(round(inlier_ratio * n))
+    X = np.stack([rng.uniform(-3, 3, ni), rng.uniform(-3, 3, ni), rng.uniform(4, 10, ni)], -1)
+    x1 = X[:, :2] / X[:, 2:3]
+    Xc = (X - c) @ R.T
+    x2 = Xc[:, :2] / Xc[:, 2:3]
+    x1 = x1 + rng.normal(0, noise, x1.shape); x2 = x2 + rng.normal(0, noise, x2.shape)
+    out = rng.uniform(-1, 1, (n - ni, 4))
+    corr = np.concatenate([np.concatenate([x1, x2], 1), out], 0)
+    flags = np.concatenate([np.ones(ni, bool), np.zeros(n - ni, bool)])
+    perm = rng.permutation(n)
+    return corr[perm], R, c, flags[perm]
+
+
+def make_pair_batch(num_pairs, n=2000, inlier_ratio=0.6, noise=1e-3, seed=0, base_seed=1000):
+    """BASELINE configs[3]-shaped batch: `num_pairs` pairs x `n` correspondences, per-pair seed = base + index."""
+    rng = np.random.default_rng(seed)
+    corrs, gts = [], []
+    for _ in range(num_pairs):
+        c, R, p, f = make_pair(rng, n, inlier_ratio, noise)
+        corrs.append(c); gts.append((R, p, f))
+    return capi.HostPairBatch(corrs, base_seed + np.arange(num_pairs)), gts
+
+
+def c4_params(lib_or_oracle_params):
+    """RansacParameters of BASELINE configs[3]."""
+    p = lib_or_oracle_params
+    p.error_thresh = (2e-3) ** 2; p.failure_probability = 1e-4; p.min_iterations = 10; p.max_iterations = 1000
+    p.use_mle = 1; p.use_lo = 0; p.min_inlier_ratio = 0.0; p.ransac_type = 0
+    return p

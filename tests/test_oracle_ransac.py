@@ -1,0 +1,198 @@
+"""CPU tests of the RANSAC oracle: the restated Eigen decompositions against numpy, the reference's own
+known-answer tests for the five-point solver (five_point_relative_pose_test.cc:64-200), the relative-pose
+RANSAC property tests (estimate_relative_pose_test.cc:65-279 style) and the libstdc++ RNG replay."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from pytheiasfm_b200 import capi, synthetic
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_jacobi_svd3_matches_numpy(oracle):
+    lib = oracle.load()
+    rng = np.random.default_rng(0)
+    for k in range(200):
+        A = rng.normal(size=(3, 3))
+        if k % 3 == 0:  # essential-matrix-like: two equal singular values and a zero
+            U0, _, V0 = np.linalg.svd(A)
+            A = U0 @ np.diag([1.0, 1.0, 0.0]) @ V0
+        U = np.zeros((3, 3)); S = np.zeros(3); V = np.zeros((3, 3))
+        lib.oracle_jacobi_svd3(_vp(A), _vp(U), _vp(S), _vp(V))
+        np.testing.assert_allclose(S, np.linalg.svd(A, compute_uv=False), atol=1e-13)
+        np.testing.assert_allclose(U @ np.diag(S) @ V.T, A, atol=1e-13)
+        np.testing.assert_allclose(U.T @ U, np.eye(3), atol=1e-13)
+        np.testing.assert_allclose(V.T @ V, np.eye(3), atol=1e-13)
+        assert S[0] >= S[1] >= S[2] >= 0
+
+
+def test_eigensolver10_matches_numpy(oracle):
+    lib = oracle.load()
+    rng = np.random.default_rng(1)
+    for _ in range(100):
+        A = rng.normal(size=(10, 10))
+        re = np.zeros(10); im = np.zeros(10); vec = np.zeros((10, 10))
+        assert lib.oracle_eigen10(_vp(A), _vp(re), _vp(im), _vp(vec)) == 0
+        ref = np.linalg.eigvals(A)
+        got = re + 1j * im
+        assert np.abs(np.sort_complex(got) - np.sort_complex(ref)).max() < 1e-10
+        for j in range(10):
+            if im[j] == 0.0:  # real eigenvalue: unit eigenvector
+                v = vec[:, j]
+                assert abs(np.linalg.norm(v) - 1) < 1e-12
+                assert np.linalg.norm(A @ v - re[j] * v) < 1e-9 * np.linalg.norm(A)
+        # complex eigenvalues come in adjacent conjugate pairs, positive imaginary part first (Eigen's order)
+        j = 0
+        while j < 10:
+            if im[j] != 0.0:
+                assert im[j] > 0 and im[j + 1] == -im[j] and re[j] == re[j + 1]
+                j += 2
+            else:
+                j += 1
+
+
+def test_fullpivlu_kernel_and_solve(oracle):
+    lib = oracle.load()
+    rng = np.random.default_rng(2)
+    for _ in range(100):
+        A = rng.normal(size=(5, 9))
+        ker = np.zeros((9, 4))
+        assert lib.oracle_fullpivlu_kernel_5x9(_vp(A), _vp(ker)) == 4
+        assert np.abs(A @ ker).max() < 1e-12 * np.abs(A).max() * np.abs(ker).max() * 10
+        assert np.linalg.matrix_rank(ker) == 4
+        M = rng.normal(size=(10, 10)); B = rng.normal(size=(10, 10)); X = np.zeros((10, 10))
+        lib.oracle_fullpivlu_solve10(_vp(M), _vp(B), _vp(X))
+        np.testing.assert_allclose(M @ X, B, atol=1e-9)
+    A = rng.normal(size=(5, 9)); A[4] = A[0] + A[1]  # rank deficient: the reference returns false
+    assert lib.oracle_fullpivlu_kernel_5x9(_vp(A), _vp(np.zeros((9, 5)))) == 5
+
+
+FIVE_PT_CASES = [
+    # (points, rotation angle about z [deg], translation, noise, tolerance)  five_point_relative_pose_test.cc:116-187
+    ([(-1, 3, 3), (1, -1, 2), (3, 1, 2.5), (-1, 1, 2), (2, 1, 3)], 13.0, (1, 1, 1), 0.0, 1e-4),
+    ([(-1, 3, 3), (1, -1, 2), (3, 1, 2.5), (-1, 1, 2), (2, 1, 3)], 13.0, (1, 1, 1), 1.0 / 512, 1e-2),
+    ([(-1, 3, 3), (1, -1, 2), (3, 1, 2), (-1, 1, 2), (2, 1, 3)], 13.0, (0, 0, 1), 1.0 / 512, 0.15),
+    ([(-1, 3, 3), (1, -1, 2), (3, 1, 2), (-1, 1, 2), (2, 1, 3)], 0.0, (1, 1, 1), 1.0 / 512, 0.01),
+]
+
+
+def five_point_case(points, deg, t, noise, seed=52):
+    X = np.array(points, float)
+    a = np.deg2rad(deg)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    t = np.array(t, float)
+    x1 = X[:, :2] / X[:, 2:3]
+    P = X @ R.T + t
+    x2 = P[:, :2] / P[:, 2:3]
+    if noise:
+        rng = np.random.default_rng(seed)
+        x1 = x1 + rng.normal(0, noise, x1.shape); x2 = x2 + rng.normal(0, noise, x2.shape)
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    return x1, x2, tx @ R
+
+
+def equal_up_to_scale(a, b, tol):
+    a = a.ravel() / np.linalg.norm(a); b = b.ravel() / np.linalg.norm(b)
+    return min(np.abs(a - b).max(), np.abs(a + b).max()) < tol
+
+
+def sampson(F, x, y):
+    xh = np.append(x, 1.0); yh = np.append(y, 1.0)
+    ex = F @ xh
+    den = (yh @ F[:, 0]) ** 2 + (yh @ F[:, 1]) ** 2 + ex[0] ** 2 + ex[1] ** 2
+    return (yh @ ex) ** 2 / den
+
+
+@pytest.mark.parametrize("case", FIVE_PT_CASES)
+def test_five_point_reference_kats(oracle, case):
+    pts, deg, t, noise, tol = case
+    x1, x2, E_gt = five_point_case(pts, deg, t, noise)
+    E, n = oracle.five_point(x1[None], x2[None])
+    assert 1 <= n[0] <= 10
+    matched = False
+    for k in range(n[0]):
+        for i in range(5):  # every solution satisfies the epipolar constraints of the minimal sample
+            assert sampson(E[0, k], x1[i], x2[i]) < 1e-8
+        matched |= equal_up_to_scale(E[0, k], E_gt, tol)
+    assert matched
+
+
+def test_five_point_solutions_are_essential_matrices(oracle):
+    rng = np.random.default_rng(3)
+    batch, gts = synthetic.make_pair_batch(20, n=5, inlier_ratio=1.0, noise=0.0, seed=4)
+    x = batch.corr.reshape(20, 5, 4)
+    E, n = oracle.five_point(x[:, :, :2], x[:, :, 2:])
+    assert (n >= 1).all()
+    for p in range(20):
+        R, c, _ = gts[p]
+        t = -R @ c
+        E_gt = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+        ok = False
+        for k in range(n[p]):
+            Ek = E[p, k] / np.linalg.norm(E[p, k])
+            s = np.linalg.svd(Ek, compute_uv=False)
+            assert abs(s[0] - s[1]) < 1e-6 and s[2] < 1e-6  # 2 EE^T E - tr(EE^T) E = 0 and det E = 0
+            ok |= equal_up_to_scale(Ek, E_gt, 1e-6)
+        assert ok
+
+
+def test_sampson_and_cheirality_formulas(oracle):
+    lib = oracle.load()
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        F = rng.normal(size=(3, 3)); c = rng.normal(size=4)
+        assert abs(lib.oracle_sampson(_vp(F), _vp(c)) - sampson(F, c[:2], c[2:])) < 1e-12 * max(1.0, sampson(F, c[:2], c[2:]))
+    batch, gts = synthetic.make_pair_batch(10, n=5, inlier_ratio=1.0, noise=0.0, seed=6)
+    for p in range(10):
+        R, c, _ = gts[p]
+        t = -R @ c
+        E = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+        Rb = np.zeros((3, 3)); pb = np.zeros(3)
+        corr = np.ascontiguousarray(batch.corr[5 * p: 5 * p + 5])
+        cnt = lib.oracle_best_pose(_vp(np.ascontiguousarray(E)), _vp(corr), 5, _vp(Rb), _vp(pb))
+        assert cnt == 5
+        np.testing.assert_allclose(Rb, R, atol=1e-9)
+        np.testing.assert_allclose(pb, c / np.linalg.norm(c), atol=1e-9)
+
+
+def test_relative_pose_ransac_recovers_pose(oracle):
+    """estimate_relative_pose_test.cc style: clean data -> exact pose; noisy 60 %-inlier data -> within tolerance."""
+    batch, gts = synthetic.make_pair_batch(6, n=400, inlier_ratio=0.6, noise=1e-3, seed=7)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    rc, res, mask = oracle.ransac_relpose_batch(batch, params)
+    assert rc == 0
+    for p in range(6):
+        R, c, flags = gts[p]
+        assert res["success"][p] == 1 and 10 <= res["num_iterations"][p] <= 1000
+        ang = np.rad2deg(np.arccos(np.clip((np.trace(res["rotation"][p] @ R.T) - 1) / 2, -1, 1)))
+        assert ang < 1.0
+        assert np.rad2deg(np.arccos(np.clip(res["position"][p] @ c, -1, 1))) < 5.0
+        m = mask[batch.pair_offset[p]: batch.pair_offset[p + 1]].astype(bool)
+        assert m.sum() == res["num_inliers"][p]
+        assert (m & flags).sum() >= 0.85 * flags.sum() and (m & ~flags).sum() <= 0.05 * (~flags).sum()
+        assert 0.99 < res["confidence"][p] <= 1.0
+
+
+def test_ransac_is_deterministic_in_the_seed_and_rejects_bad_params(oracle):
+    batch, _ = synthetic.make_pair_batch(3, n=200, seed=8)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    a = oracle.ransac_relpose_batch(batch, params, threads=1)
+    b = oracle.ransac_relpose_batch(batch, params, threads=4)
+    assert a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes()
+    batch.seed[:] += 1
+    c = oracle.ransac_relpose_batch(batch, params)
+    assert c[1].tobytes() != a[1].tobytes()
+    params.error_thresh = -1.0
+    assert oracle.ransac_relpose_batch(batch, params)[0] == capi.THB_E_INVALID_ARGUMENT
+    params = synthetic.c4_params(oracle.ransac_default_params()); params.use_lo = 1
+    assert oracle.ransac_relpose_batch(batch, params)[0] == capi.THB_E_UNSUPPORTED
+
+
+def test_default_ransac_parameters(oracle):
+    p = oracle.ransac_default_params()  # sample_consensus_estimator.h:59-68
+    assert p.error_thresh == -1 and p.failure_probability == 0.01 and p.min_inlier_ratio == 0
+    assert p.min_iterations == 100 and p.max_iterations == 2**31 - 1 and not p.use_mle and not p.use_lo and p.lo_start_iterations == 50
