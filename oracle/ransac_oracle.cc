@@ -143,30 +143,31 @@ inline double Det3(const double* M) {
   return M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
 }
 
-// triangulation.cc:216-232
+// triangulation.cc:216-232. Explicit fma in a fixed order (shared with the device code) so that the
+// cheirality test and the Sampson distance are bit-reproducible across CPU and GPU.
 inline bool InFront(const double* c, const double* R, const double* pos) {
-  const double d1[3] = {c[0], c[1], 1.0};
-  const double f2[3] = {c[2], c[3], 1.0};
-  double d2[3];
-  for (int k = 0; k < 3; ++k) d2[k] = R[0 * 3 + k] * f2[0] + R[1 * 3 + k] * f2[1] + R[2 * 3 + k] * f2[2];  // R^T f2
-  const double dir1_sq = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
-  const double dir2_sq = d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2];
-  const double dir1_dir2 = d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2];
-  const double dir1_pos = d1[0] * pos[0] + d1[1] * pos[1] + d1[2] * pos[2];
-  const double dir2_pos = d2[0] * pos[0] + d2[1] * pos[1] + d2[2] * pos[2];
-  return dir2_sq * dir1_pos - dir1_dir2 * dir2_pos > 0 && dir1_dir2 * dir1_pos - dir1_sq * dir2_pos > 0;
+  const double x1 = c[0], y1 = c[1], x2 = c[2], y2 = c[3];
+  const double d2x = std::fma(R[0], x2, std::fma(R[3], y2, R[6]));  // R^T [x2 y2 1]
+  const double d2y = std::fma(R[1], x2, std::fma(R[4], y2, R[7]));
+  const double d2z = std::fma(R[2], x2, std::fma(R[5], y2, R[8]));
+  const double dir1_sq = std::fma(x1, x1, std::fma(y1, y1, 1.0));
+  const double dir2_sq = std::fma(d2x, d2x, std::fma(d2y, d2y, d2z * d2z));
+  const double dir1_dir2 = std::fma(x1, d2x, std::fma(y1, d2y, d2z));
+  const double dir1_pos = std::fma(x1, pos[0], std::fma(y1, pos[1], pos[2]));
+  const double dir2_pos = std::fma(d2x, pos[0], std::fma(d2y, pos[1], d2z * pos[2]));
+  return std::fma(dir2_sq, dir1_pos, -(dir1_dir2 * dir2_pos)) > 0.0 && std::fma(dir1_dir2, dir1_pos, -(dir1_sq * dir2_pos)) > 0.0;
 }
 
 // pose/util.cc:56-69
 inline double Sampson(const double* F, const double* c) {
   const double x0 = c[0], x1 = c[1], y0 = c[2], y1 = c[3];
-  const double ex0 = F[0] * x0 + F[1] * x1 + F[2];
-  const double ex1 = F[3] * x0 + F[4] * x1 + F[5];
-  const double ex2 = F[6] * x0 + F[7] * x1 + F[8];
-  const double num = y0 * ex0 + y1 * ex1 + ex2;
-  const double dy0 = y0 * F[0] + y1 * F[3] + F[6];
-  const double dy1 = y0 * F[1] + y1 * F[4] + F[7];
-  const double den = dy0 * dy0 + dy1 * dy1 + ex0 * ex0 + ex1 * ex1;
+  const double ex0 = std::fma(F[0], x0, std::fma(F[1], x1, F[2]));
+  const double ex1 = std::fma(F[3], x0, std::fma(F[4], x1, F[5]));
+  const double ex2 = std::fma(F[6], x0, std::fma(F[7], x1, F[8]));
+  const double num = std::fma(y0, ex0, std::fma(y1, ex1, ex2));
+  const double dy0 = std::fma(y0, F[0], std::fma(y1, F[3], F[6]));
+  const double dy1 = std::fma(y0, F[1], std::fma(y1, F[4], F[7]));
+  const double den = std::fma(dy0, dy0, std::fma(dy1, dy1, std::fma(ex0, ex0, ex1 * ex1)));
   return num * num / den;
 }
 
