@@ -15,7 +15,11 @@
 
 namespace thb {
 
-constexpr int CAMD = 20;  // R[9] (row-major), M[9] (row-major), small-angle flag, pad
+// Per-camera record gathered by every observation: one 192-byte, 32-byte-aligned block read with six 256-bit
+// loads (uncoalesced 8-byte gathers are bound by L1 wavefronts, measured):
+//   R[9] | C[3] | M[9] | small-angle flag | column scale[6] | constness | intrinsics group | pad[2]   = 256 bytes
+constexpr int CAMD = 32;
+constexpr int CD_SCALE = 22, CD_CONST = 28, CD_GROUP = 29;
 
 struct BaState {  // one set of parameter values (current x, or the candidate)
   double* cam;
@@ -101,16 +105,16 @@ __device__ __forceinline__ void householder4(const double x[4], double v[3], dou
 template <int MODEL>
 __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S, int c, int p, double2 xy,
                                               double2 si, double r[2]) {
-  const double* cam = S.cam + (size_t)c * 6;
-  const double* cd = S.camd + (size_t)c * CAMD;
+  const double4* cd4 = reinterpret_cast<const double4*>(S.camd + (size_t)c * CAMD);
+  const double4 q0 = cd4[0], q1 = cd4[1], q2 = cd4[2];  // R[0..8], C[0..2]
   const double4 X = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
-  const double ax = X.x - X.w * cam[0], ay = X.y - X.w * cam[1], az = X.z - X.w * cam[2];
+  const double ax = X.x - X.w * q2.y, ay = X.y - X.w * q2.z, az = X.z - X.w * q2.w;
   if (ax * ax + ay * ay + az * az < 1e-8) return false;
   double pc[3];
-  pc[0] = cd[0] * ax + cd[1] * ay + cd[2] * az;
-  pc[1] = cd[3] * ax + cd[4] * ay + cd[5] * az;
-  pc[2] = cd[6] * ax + cd[7] * ay + cd[8] * az;
-  const int g = K.cam_group[c];
+  pc[0] = q0.x * ax + q0.y * ay + q0.z * az;
+  pc[1] = q0.w * ax + q1.x * ay + q1.y * az;
+  pc[2] = q1.z * ax + q1.w * ay + q2.x * az;
+  const int g = (int)S.camd[(size_t)c * CAMD + CD_GROUP];
   double pix[2];
   if (!project<MODEL, double, double>(K.intr_model[g], S.intr + (size_t)g * KS, pc, pix)) return false;
   r[0] = si.x * (pix[0] - xy.x);
@@ -129,11 +133,15 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
                                          double jc[12], double jp[2 * PD], double* ji, double* half_rho) {
   constexpr int ND = 3 + NK;
   typedef Dual<ND> D;
-  const double* cam = S.cam + (size_t)c * 6;
-  const double* cd = S.camd + (size_t)c * CAMD;
+  double cd[CAMD];
+  {
+    const double4* cd4 = reinterpret_cast<const double4*>(S.camd + (size_t)c * CAMD);
+#pragma unroll
+    for (int k = 0; k < CAMD / 4; ++k) { const double4 v = cd4[k]; cd[4 * k] = v.x; cd[4 * k + 1] = v.y; cd[4 * k + 2] = v.z; cd[4 * k + 3] = v.w; }
+  }
   const double4 X4 = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
   const double X[4] = {X4.x, X4.y, X4.z, X4.w};
-  const double C[3] = {cam[0], cam[1], cam[2]};
+  const double C[3] = {cd[9], cd[10], cd[11]};
   const double adj[3] = {X[0] - X[3] * C[0], X[1] - X[3] * C[1], X[2] - X[3] * C[2]};
   if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
   double R[9];
@@ -143,7 +151,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
 #pragma unroll
   for (int a = 0; a < 3; ++a) pc[a] = R[3 * a] * adj[0] + R[3 * a + 1] * adj[1] + R[3 * a + 2] * adj[2];
 
-  const int g = K.cam_group[c];
+  const int g = (int)cd[CD_GROUP];
   const int model = MODEL >= 0 ? MODEL : K.intr_model[g];
   const double* Kp = S.intr + (size_t)g * KS;
   D pd[3], pix[2];
@@ -171,7 +179,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   for (int a = 0; a < 2; ++a)
 #pragma unroll
     for (int k = 0; k < 3; ++k) AR[3 * a + k] = A[3 * a] * R[k] + A[3 * a + 1] * R[3 + k] + A[3 * a + 2] * R[6 + k];
-  const uint8_t cconst = K.cam_const[c];
+  const int cconst = (int)cd[CD_CONST];
   // d r / d C = -w * AR
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -180,7 +188,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   // d r / d aa = A * (-[q]x M): q = R adj and M = left Jacobian of SO(3); in Ceres' small-angle
   // branch (R = I + [aa]x) q = adj and M = I.
   {
-    const bool small = cd[18] != 0.0;
+    const bool small = cd[21] != 0.0;
     const double q0 = small ? adj[0] : pc[0], q1 = small ? adj[1] : pc[1], q2 = small ? adj[2] : pc[2];
     // G = A * (-[q]x): row a: -(A_a x q)^T ... (A_a^T [q]x)_k = (q x A_a)_k ; so -A_a [q]x = (A_a x q)... computed explicitly
     double G[6];
@@ -198,7 +206,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
       for (int k = 0; k < 3; ++k)
         jc[6 * a + 3 + k] = (cconst & THB_CAM_CONST_ORIENTATION)
                                 ? 0.0
-                                : G[3 * a] * cd[9 + k] + G[3 * a + 1] * cd[12 + k] + G[3 * a + 2] * cd[15 + k];
+                                : G[3 * a] * cd[12 + k] + G[3 * a + 1] * cd[15 + k] + G[3 * a + 2] * cd[18 + k];
   }
   // d r / d X (2x4) = [AR | -AR*C], then the tangent block
   const bool pconst = K.pt_const[p] != 0;
@@ -254,7 +262,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   for (int k = 0; k < 6; ++k) {
     double j0 = jc[k], j1 = jc[6 + k];
     if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
-    const double s = js * (cs ? cs[(size_t)c * 6 + k] : 1.0);
+    const double s = js * (cs ? cd[CD_SCALE + k] : 1.0);
     jc[k] = j0 * s; jc[6 + k] = j1 * s;
   }
 #pragma unroll

@@ -13,7 +13,8 @@ enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 
 // ---------------------------------------------------------------------------------------------
 // Per-camera derived quantities: rotation matrix (ceres::AngleAxisRotatePoint semantics, incl. the
 // first-order branch for theta^2 <= eps) and the SO(3) left Jacobian used for d(R v)/d(aa).
-__global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc) {
+__global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc, const double* __restrict__ cs,
+                             const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_group) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= nc) return;
   const double wx = cam[6 * c + 3], wy = cam[6 * c + 4], wz = cam[6 * c + 5];
@@ -40,18 +41,22 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
       B = (th - s) / (th2 * th);
     }
     // [w]x^2 = w w^T - th2 I
-    o[9]  = 1.0 + B * (wx * wx - th2); o[10] = -A * wz + B * wx * wy;     o[11] = A * wy + B * wx * wz;
-    o[12] = A * wz + B * wx * wy;      o[13] = 1.0 + B * (wy * wy - th2); o[14] = -A * wx + B * wy * wz;
-    o[15] = -A * wy + B * wx * wz;     o[16] = A * wx + B * wy * wz;      o[17] = 1.0 + B * (wz * wz - th2);
-    o[18] = 0.0;
+    o[12] = 1.0 + B * (wx * wx - th2); o[13] = -A * wz + B * wx * wy;     o[14] = A * wy + B * wx * wz;
+    o[15] = A * wz + B * wx * wy;      o[16] = 1.0 + B * (wy * wy - th2); o[17] = -A * wx + B * wy * wz;
+    o[18] = -A * wy + B * wx * wz;     o[19] = A * wx + B * wy * wz;      o[20] = 1.0 + B * (wz * wz - th2);
+    o[21] = 0.0;
   } else {
     o[0] = 1.0; o[1] = -wz; o[2] = wy;
     o[3] = wz;  o[4] = 1.0; o[5] = -wx;
     o[6] = -wy; o[7] = wx;  o[8] = 1.0;
-    o[9] = 1.0; o[10] = 0.0; o[11] = 0.0; o[12] = 0.0; o[13] = 1.0; o[14] = 0.0; o[15] = 0.0; o[16] = 0.0; o[17] = 1.0;
-    o[18] = 1.0;
+    o[12] = 1.0; o[13] = 0.0; o[14] = 0.0; o[15] = 0.0; o[16] = 1.0; o[17] = 0.0; o[18] = 0.0; o[19] = 0.0; o[20] = 1.0;
+    o[21] = 1.0;
   }
-  o[19] = 0.0;
+  o[9] = cam[6 * c]; o[10] = cam[6 * c + 1]; o[11] = cam[6 * c + 2];
+  for (int k = 0; k < 6; ++k) o[CD_SCALE + k] = cs ? cs[6 * c + k] : 1.0;
+  o[CD_CONST] = (double)cam_const[c];
+  o[CD_GROUP] = (double)cam_group[c];
+  o[30] = 0.0; o[31] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -59,12 +64,11 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
 // One thread per observation. HBM-bound: reads 40 B/obs (+ L2-resident parameter gathers), writes
 // (2 + 12 + 2*PD + 2*NK) * 8 B/obs as fully coalesced plane stores.
 template <int MODEL, int PD, int NK>
-__global__ void __launch_bounds__(256) k_jacobian(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
+__global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
                                                   const double* __restrict__ ps, const double* __restrict__ is,
                                                   double* __restrict__ r_pl, double* __restrict__ jc_pl,
                                                   double* __restrict__ jp_pl, double* __restrict__ ji_pl,
                                                   double* __restrict__ scal, int* __restrict__ iflag) {
-  __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double hc = 0.0;
   if (i < K.no) {
@@ -90,8 +94,9 @@ __global__ void __launch_bounds__(256) k_jacobian(BaConst K, BaState S, ObsSoA O
 #pragma unroll
     for (int k = 0; k < 2 * NK; ++k) ji_pl[k * no + i] = ji[k];
   }
-  hc = block_sum(hc, red);
-  if (threadIdx.x == 0) atomicAdd(scal + SC_COST_X, hc);
+  // one atomic per warp, no block barrier: warps retire independently
+  hc = warp_sum(hc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(scal + SC_COST_X, hc);
 }
 
 // Cost only (candidate evaluation): 0.5 * sum rho(|r|^2).
@@ -510,6 +515,16 @@ __global__ void k_make_scale(int n, const double* __restrict__ diag, double* __r
 __global__ void k_fill(int n, double* __restrict__ a, double v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
+}
+
+// L2 flush by reading: fills the cache with clean lines of a scratch buffer
+__global__ void k_flush_read(const double2* __restrict__ buf, size_t n, double* __restrict__ sink) {
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double2 v = __ldcg(buf + i);
+    acc += v.x + v.y;
+  }
+  if (acc == 123.456) *sink = acc;  // never true: keeps the loads alive
 }
 
 // x_norm^2 over the non-constant blocks of a state
