@@ -279,6 +279,41 @@ int thb_ransac_relpose_batch(const ThbPairBatch* batch, const ThbRansacParams* p
                              ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream);
 
 /*
+ * theia::EstimateCalibratedAbsolutePose (sfm/estimators/estimate_calibrated_absolute_pose.cc:176-190) with
+ * PnPType::KNEIP (the estimator's default, :66): sample size 3, PoseFromThreePoints, squared normalised reprojection
+ * error (:158-167). batch->corr is [total * 5] = FeatureCorrespondence2D3D {feature (x, y), world_point (X, Y, Z)}
+ * (feature_correspondence_2d_3d.h:42-49). Results use ThbRelPoseResult with rotation / position =
+ * CalibratedAbsolutePose::{rotation, position}; essential_matrix is zero. DLS / SQPnP are not replayable.
+ */
+int thb_ransac_abspose_batch(const ThbPairBatch* batch, const ThbRansacParams* params,
+                             ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream);
+
+/*
+ * theia::EstimateHomography (sfm/estimators/estimate_homography.cc:122-136): sample size 4, FourPointHomography,
+ * one-way transfer error (:104-111). Results use ThbRelPoseResult with essential_matrix = the homography (row-major);
+ * rotation / position are zero. This is also TwoViewMatchGeometricVerification::CountHomographyInliers
+ * (two_view_match_geometric_verification.cc:331-366): num_inliers.
+ */
+int thb_ransac_homography_batch(const ThbPairBatch* batch, const ThbRansacParams* params,
+                                ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream);
+
+/* theia::PoseFromThreePoints (sfm/pose/perspective_three_point.cc:182-291) for `count` independent samples (host
+ * pointers): features [count*3*2], world_points [count*3*3]; R_out [count*4*9] row-major, t_out [count*4*3],
+ * num_solutions [count] (0 => collinear world points, the reference returns false). */
+int thb_p3p(const double* features, const double* world_points, int32_t count, double* R_out, double* t_out,
+            int32_t* num_solutions, void* cuda_stream);
+
+/* theia::FourPointHomography (sfm/pose/four_point_homography.cc:72-102), minimal case: corr [count*4*4] (x1,y1,x2,y2),
+ * H_out [count*9] row-major, ok [count]. */
+int thb_four_point_homography(const double* corr, int32_t count, double* H_out, int32_t* ok, void* cuda_stream);
+
+/* theia::SevenPointFundamentalMatrix (sfm/pose/seven_point_fundamental_matrix.cc:72-152): corr [count*7*4],
+ * F_out [count*3*9] row-major, num_solutions [count]. Reproduces the reference as written, including its
+ * cubic-coefficient order. */
+int thb_seven_point_fundamental_matrix(const double* corr, int32_t count, double* F_out, int32_t* num_solutions,
+                                       void* cuda_stream);
+
+/*
  * theia::FivePointRelativePose (sfm/pose/five_point_relative_pose.cc:212-293), minimal case, for `count`
  * independent 5-point samples (host pointers): x1, x2 [count*5*2]; E_out [count*10*9] row-major, in the
  * reference's solution order; num_solutions [count] (0 => the reference returns false).

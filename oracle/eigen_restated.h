@@ -144,77 +144,81 @@ inline bool MakeJacobi(double x, double y, double z, JacobiRot* j) {
   j->c = n;
   return true;
 }
-inline void RotLeft3(double* M, int p, int q, JacobiRot j) {  // rows p, q: x' = c x + s y, y' = -s x + c y
-  for (int i = 0; i < 3; ++i) {
-    const double x = M[p * 3 + i], y = M[q * 3 + i];
-    M[p * 3 + i] = j.c * x + j.s * y;
-    M[q * 3 + i] = -j.s * x + j.c * y;
+template <int N>
+inline void RotLeftN(double* M, int p, int q, JacobiRot j) {  // rows p, q: x' = c x + s y, y' = -s x + c y
+  for (int i = 0; i < N; ++i) {
+    const double x = M[p * N + i], y = M[q * N + i];
+    M[p * N + i] = j.c * x + j.s * y;
+    M[q * N + i] = -j.s * x + j.c * y;
   }
 }
-inline void RotRight3(double* M, int p, int q, JacobiRot j) {  // cols p, q with j^T: x' = c x - s y, y' = s x + c y
-  for (int i = 0; i < 3; ++i) {
-    const double x = M[i * 3 + p], y = M[i * 3 + q];
-    M[i * 3 + p] = j.c * x - j.s * y;
-    M[i * 3 + q] = j.s * x + j.c * y;
+template <int N>
+inline void RotRightN(double* M, int p, int q, JacobiRot j) {  // cols p, q with j^T: x' = c x - s y, y' = s x + c y
+  for (int i = 0; i < N; ++i) {
+    const double x = M[i * N + p], y = M[i * N + q];
+    M[i * N + p] = j.c * x - j.s * y;
+    M[i * N + q] = j.s * x + j.c * y;
   }
 }
-inline void JacobiSVD3(const double* A, double* U, double* S, double* V) {
+// Square JacobiSVD (no QR preconditioner is applied by Eigen when rows == cols), row-major N x N.
+template <int N>
+inline void JacobiSVDN(const double* A, double* U, double* S, double* V) {
   const double precision = 2.0 * std::numeric_limits<double>::epsilon();
   const double considerAsZero = std::numeric_limits<double>::min();
   double scale = 0.0;
-  for (int i = 0; i < 9; ++i) scale = std::max(scale, std::fabs(A[i]));
+  for (int i = 0; i < N * N; ++i) scale = std::max(scale, std::fabs(A[i]));
   if (scale == 0.0) scale = 1.0;
-  double W[9];
-  for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
-  double maxDiag = std::max(std::fabs(W[0]), std::max(std::fabs(W[4]), std::fabs(W[8])));
+  double W[N * N];
+  for (int i = 0; i < N * N; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i / N == i % N) ? 1.0 : 0.0; }
+  double maxDiag = 0.0;
+  for (int i = 0; i < N; ++i) maxDiag = std::max(maxDiag, std::fabs(W[i * N + i]));
   bool finished = false;
   int sweeps = 0;
-  while (!finished && sweeps++ < 100) {
+  while (!finished && sweeps++ < 1000) {
     finished = true;
-    for (int p = 1; p < 3; ++p)
+    for (int p = 1; p < N; ++p)
       for (int q = 0; q < p; ++q) {
         const double threshold = std::max(considerAsZero, precision * maxDiag);
-        if (std::fabs(W[p * 3 + q]) > threshold || std::fabs(W[q * 3 + p]) > threshold) {
+        if (std::fabs(W[p * N + q]) > threshold || std::fabs(W[q * N + p]) > threshold) {
           finished = false;
           // real_2x2_jacobi_svd on [[W_pp, W_pq], [W_qp, W_qq]]
-          double m00 = W[p * 3 + p], m01 = W[p * 3 + q], m10 = W[q * 3 + p], m11 = W[q * 3 + q];
+          const double m00 = W[p * N + p], m01 = W[p * N + q], m10 = W[q * N + p], m11 = W[q * N + q];
           JacobiRot rot1;
           const double t = m00 + m11, d = m10 - m01;
           if (std::fabs(d) < std::numeric_limits<double>::min()) { rot1.s = 0.0; rot1.c = 1.0; }
           else { const double u = t / d, tmp = std::sqrt(1.0 + u * u); rot1.s = 1.0 / tmp; rot1.c = u / tmp; }
-          // m.applyOnTheLeft(0, 1, rot1)
           const double n00 = rot1.c * m00 + rot1.s * m10, n01 = rot1.c * m01 + rot1.s * m11;
           const double n11 = -rot1.s * m01 + rot1.c * m11;
           JacobiRot jr;
           MakeJacobi(n00, n01, n11, &jr);
-          // j_left = rot1 * j_right^T
           const JacobiRot jrt{jr.c, -jr.s};
           const JacobiRot jl{rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
-          RotLeft3(W, p, q, jl);
-          RotRight3(U, p, q, JacobiRot{jl.c, -jl.s});
-          RotRight3(W, p, q, jr);
-          RotRight3(V, p, q, jr);
-          maxDiag = std::max(maxDiag, std::max(std::fabs(W[p * 3 + p]), std::fabs(W[q * 3 + q])));
+          RotLeftN<N>(W, p, q, jl);
+          RotRightN<N>(U, p, q, JacobiRot{jl.c, -jl.s});
+          RotRightN<N>(W, p, q, jr);
+          RotRightN<N>(V, p, q, jr);
+          maxDiag = std::max(maxDiag, std::max(std::fabs(W[p * N + p]), std::fabs(W[q * N + q])));
         }
       }
   }
-  for (int i = 0; i < 3; ++i) {
-    const double a = W[i * 3 + i];
+  for (int i = 0; i < N; ++i) {
+    const double a = W[i * N + i];
     S[i] = std::fabs(a);
-    if (a < 0.0) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+    if (a < 0.0) for (int r = 0; r < N; ++r) U[r * N + i] = -U[r * N + i];
   }
-  for (int i = 0; i < 3; ++i) S[i] *= scale;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < N; ++i) S[i] *= scale;
+  for (int i = 0; i < N; ++i) {
     int pos = i;
     double best = S[i];
-    for (int k = i + 1; k < 3; ++k) if (S[k] > best) { best = S[k]; pos = k; }
+    for (int k = i + 1; k < N; ++k) if (S[k] > best) { best = S[k]; pos = k; }
     if (best == 0.0) break;
     if (pos != i) {
       std::swap(S[i], S[pos]);
-      for (int r = 0; r < 3; ++r) { std::swap(U[r * 3 + i], U[r * 3 + pos]); std::swap(V[r * 3 + i], V[r * 3 + pos]); }
+      for (int r = 0; r < N; ++r) { std::swap(U[r * N + i], U[r * N + pos]); std::swap(V[r * N + i], V[r * N + pos]); }
     }
   }
 }
+inline void JacobiSVD3(const double* A, double* U, double* S, double* V) { JacobiSVDN<3>(A, U, S, V); }
 
 // ---------------------------------------------------------------------------------------------
 // EigenSolver for a real N x N matrix (row-major). eig_re/eig_im: eigenvalues in Eigen's order; vec: for
@@ -266,7 +270,7 @@ struct EigenSolverReal {
     }
   }
 
-  void compute(const double* A) {
+  void compute(const double* A, bool want_vectors = true) {
     ok = true;
     double scale = 0.0;
     for (int i = 0; i < N * N; ++i) scale = std::max(scale, std::fabs(A[i]));
@@ -363,7 +367,7 @@ struct EigenSolverReal {
         i += 2;
       }
     }
-    ComputeRealEigenvectors();
+    if (want_vectors) ComputeRealEigenvectors();
   }
 
   void SplitOffTwoRows(int iu, double exshift) {

@@ -32,6 +32,12 @@ def load():
         lib.oracle_ransac_default_params.argtypes = [C.POINTER(capi.ThbRansacParams)]
         lib.oracle_five_point.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.oracle_ransac_relpose_batch.argtypes = [C.POINTER(capi.ThbPairBatch), C.POINTER(capi.ThbRansacParams), C.c_void_p, C.c_void_p, C.c_int32]
+        for name in ("oracle_ransac_abspose_batch", "oracle_ransac_homography_batch"):
+            getattr(lib, name).argtypes = [C.POINTER(capi.ThbPairBatch), C.POINTER(capi.ThbRansacParams), C.c_void_p, C.c_void_p, C.c_int32]
+        lib.oracle_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.oracle_seven_point_fundamental.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        lib.oracle_poly_roots.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.oracle_jacobi_svd3.argtypes = [C.c_void_p] * 4
         lib.oracle_eigen10.argtypes = [C.c_void_p] * 4
         lib.oracle_fullpivlu_kernel_5x9.argtypes = [C.c_void_p] * 2
@@ -95,10 +101,46 @@ def five_point(x1, x2):
     return E, n
 
 
-def ransac_relpose_batch(batch, params, threads=0):
-    """Returns (results structured array [num_pairs], inlier mask [total])."""
+def ransac_batch(kind, batch, params, threads=0):
+    """kind in {relpose, abspose, homography}. Returns (rc, results structured array [num_pairs], inlier mask [total])."""
     res = np.zeros(batch.num_pairs, capi.RELPOSE_DTYPE)
     mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
     b = batch.struct()
-    rc = load().oracle_ransac_relpose_batch(C.byref(b), C.byref(params), _vp(res), _vp(mask), threads)
+    rc = getattr(load(), "oracle_ransac_%s_batch" % kind)(C.byref(b), C.byref(params), _vp(res), _vp(mask), threads)
     return rc, res, mask
+
+
+def ransac_relpose_batch(batch, params, threads=0):
+    return ransac_batch("relpose", batch, params, threads)
+
+
+def p3p(feat, world):
+    """feat [count,3,2], world [count,3,3] -> (R [count,4,3,3], t [count,4,3], n [count])"""
+    feat = np.ascontiguousarray(feat, np.float64); world = np.ascontiguousarray(world, np.float64)
+    count = feat.shape[0]
+    R = np.zeros((count, 4, 3, 3)); t = np.zeros((count, 4, 3)); n = np.zeros(count, np.int32)
+    load().oracle_p3p(_vp(feat), _vp(world), count, _vp(R), _vp(t), _vp(n))
+    return R, t, n
+
+
+def four_point_homography(corr):
+    corr = np.ascontiguousarray(corr, np.float64)
+    count = corr.shape[0]
+    H = np.zeros((count, 3, 3)); ok = np.zeros(count, np.int32)
+    load().oracle_four_point_homography(_vp(corr), count, _vp(H), _vp(ok))
+    return H, ok
+
+
+def seven_point_fundamental(corr):
+    corr = np.ascontiguousarray(corr, np.float64)
+    count = corr.shape[0]
+    F = np.zeros((count, 3, 3, 3)); n = np.zeros(count, np.int32)
+    load().oracle_seven_point_fundamental(_vp(corr), count, _vp(F), _vp(n))
+    return F, n
+
+
+def poly_roots(poly):
+    poly = np.ascontiguousarray(poly, np.float64)
+    re = np.zeros(4); im = np.zeros(4)
+    n = load().oracle_poly_roots(_vp(poly), len(poly), _vp(re), _vp(im))
+    return re[:n] + 1j * im[:n]

@@ -207,7 +207,323 @@ int BestPose(const double* E, const double* corr, int n, double* Rbest, double* 
   return best_count;
 }
 
-struct Model { double E[9], R[9], p[3]; };
+// ---------------------------------------------------------------------------------------------------------
+// math/find_polynomial_roots_companion_matrix.cc:89-233 (balance :89-137, companion :139-151) and
+// math/polynomial.cc:176-231 (degree 1 and 2). coeffs: highest degree first. Returns the number of roots.
+template <int D>
+int CompanionRoots(const double* monic_tail /* p1..pD of the monic polynomial */, double* re, double* im) {
+  double C[D * D], Off[D * D];
+  for (int i = 0; i < D * D; ++i) C[i] = 0.0;
+  for (int i = 1; i < D; ++i) C[i * D + i - 1] = 1.0;
+  for (int i = 0; i < D; ++i) C[i * D + D - 1] = -monic_tail[D - 1 - i];
+  for (int i = 0; i < D * D; ++i) Off[i] = C[i];
+  for (int i = 0; i < D; ++i) Off[i * D + i] = 0.0;
+  const double gamma = 0.9;
+  bool changed;
+  do {
+    changed = false;
+    for (int i = 0; i < D; ++i) {
+      double row_norm = 0.0, col_norm = 0.0;
+      for (int k = 0; k < D; ++k) { row_norm += std::fabs(Off[i * D + k]); col_norm += std::fabs(Off[k * D + i]); }
+      int exponent = 0;
+      std::frexp(row_norm / col_norm, &exponent);
+      exponent /= 2;
+      if (exponent != 0) {
+        const double scaled_col = std::ldexp(col_norm, exponent), scaled_row = std::ldexp(row_norm, -exponent);
+        if (scaled_col + scaled_row < gamma * (col_norm + row_norm)) {
+          changed = true;
+          const double fr = std::ldexp(1.0, -exponent), fc = std::ldexp(1.0, exponent);
+          for (int k = 0; k < D; ++k) Off[i * D + k] *= fr;
+          for (int k = 0; k < D; ++k) Off[k * D + i] *= fc;
+        }
+      }
+    }
+  } while (changed);
+  for (int i = 0; i < D; ++i) Off[i * D + i] = C[i * D + i];
+  EigenSolverReal<D> es;
+  es.compute(Off, false);
+  if (!es.ok) return 0;
+  for (int i = 0; i < D; ++i) { re[i] = es.eig_re[i]; im[i] = es.eig_im[i]; }
+  return D;
+}
+// FindPolynomialRoots for a polynomial of size n+1 (degree <= 4 here). Real parts in re, imaginary in im.
+int PolyRoots(const double* poly_in, int size, double* re, double* im) {
+  int lead = 0;
+  while (lead < size - 1 && poly_in[lead] == 0.0) ++lead;  // RemoveLeadingZeros
+  const double* p = poly_in + lead;
+  const int degree = size - lead - 1;
+  if (degree == 0) return 0;
+  if (degree == 1) { re[0] = -p[1] / p[0]; im[0] = 0.0; return 1; }
+  if (degree == 2) {
+    const double a = p[0], b = p[1], c = p[2];
+    const double D = b * b - 4 * a * c, sqrt_D = std::sqrt(std::fabs(D));
+    im[0] = im[1] = 0.0;
+    if (D >= 0) {
+      if (b >= 0) { re[0] = (-b - sqrt_D) / (2.0 * a); re[1] = (2.0 * c) / (-b - sqrt_D); }
+      else { re[0] = (2.0 * c) / (-b + sqrt_D); re[1] = (-b + sqrt_D) / (2.0 * a); }
+      return 2;
+    }
+    re[0] = -b / (2.0 * a); re[1] = -b / (2.0 * a);
+    im[0] = sqrt_D / (2.0 * a); im[1] = -sqrt_D / (2.0 * a);
+    return 2;
+  }
+  double tail[4];
+  for (int i = 0; i < degree; ++i) tail[i] = p[1 + i] / p[0];
+  if (degree == 3) return CompanionRoots<3>(tail, re, im);
+  return CompanionRoots<4>(tail, re, im);
+}
+
+inline void Cross(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double Dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline void Normalize3(double* a) { const double n = std::sqrt(Dot3(a, a)); a[0] /= n; a[1] /= n; a[2] /= n; }
+
+// sfm/pose/perspective_three_point.cc:182-291 (Kneip), with SolvePlaneRotation :58-130 and Backsubstitute :135-178.
+// feat: 3 x (x, y); world: 3 x (X, Y, Z). Outputs up to 4 (R row-major, t). Returns the number of solutions.
+int P3P(const double* feat, const double* world, double* Rs, double* ts) {
+  double f[3][3], w[3][3];
+  for (int i = 0; i < 3; ++i) {
+    f[i][0] = feat[2 * i]; f[i][1] = feat[2 * i + 1]; f[i][2] = 1.0;
+    Normalize3(f[i]);
+    for (int k = 0; k < 3; ++k) w[i][k] = world[3 * i + k];
+  }
+  double w10[3], w20[3], cr[3];
+  for (int k = 0; k < 3; ++k) { w10[k] = w[1][k] - w[0][k]; w20[k] = w[2][k] - w[0][k]; }
+  Cross(w10, w20, cr);
+  if (Dot3(cr, cr) < 1e-6) return 0;
+  double Tc[3][3];  // intermediate camera frame (rows)
+  auto camera_frame = [&]() {
+    for (int k = 0; k < 3; ++k) Tc[0][k] = f[0][k];
+    Cross(f[0], f[1], Tc[2]); Normalize3(Tc[2]);
+    Cross(Tc[2], Tc[0], Tc[1]);
+  };
+  camera_frame();
+  double ip[3];
+  for (int r = 0; r < 3; ++r) ip[r] = Dot3(Tc[r], f[2]);
+  if (ip[2] > 0) {
+    for (int k = 0; k < 3; ++k) { std::swap(f[0][k], f[1][k]); }
+    camera_frame();
+    for (int r = 0; r < 3; ++r) ip[r] = Dot3(Tc[r], f[2]);
+    for (int k = 0; k < 3; ++k) std::swap(w[0][k], w[1][k]);
+    for (int k = 0; k < 3; ++k) { w10[k] = w[1][k] - w[0][k]; w20[k] = w[2][k] - w[0][k]; }
+  }
+  double Nw[3][3];  // intermediate world frame (rows)
+  for (int k = 0; k < 3; ++k) Nw[0][k] = w10[k];
+  Normalize3(Nw[0]);
+  Cross(Nw[0], w20, Nw[2]); Normalize3(Nw[2]);
+  Cross(Nw[2], Nw[0], Nw[1]);
+  double iw[3];
+  for (int r = 0; r < 3; ++r) iw[r] = Dot3(Nw[r], w20);
+  const double d_12 = std::sqrt(Dot3(w10, w10));
+  // SolvePlaneRotation
+  const double f_1 = ip[0] / ip[2], f_2 = ip[1] / ip[2], p_1 = iw[0], p_2 = iw[1];
+  const double cos_beta = Dot3(f[0], f[1]);
+  double b = 1.0 / (1.0 - cos_beta * cos_beta) - 1.0;
+  b = cos_beta < 0 ? -std::sqrt(b) : std::sqrt(b);
+  const double f_1_pw2 = f_1 * f_1, f_2_pw2 = f_2 * f_2, p_1_pw2 = p_1 * p_1, p_1_pw3 = p_1_pw2 * p_1, p_1_pw4 = p_1_pw3 * p_1;
+  const double p_2_pw2 = p_2 * p_2, p_2_pw3 = p_2_pw2 * p_2, p_2_pw4 = p_2_pw3 * p_2, d_12_pw2 = d_12 * d_12, b_pw2 = b * b;
+  double co[5];
+  co[0] = -f_2_pw2 * p_2_pw4 - p_2_pw4 * f_1_pw2 - p_2_pw4;
+  co[1] = 2.0 * p_2_pw3 * d_12 * b + 2.0 * f_2_pw2 * p_2_pw3 * d_12 * b - 2.0 * f_2 * p_2_pw3 * f_1 * d_12;
+  co[2] = -f_2_pw2 * p_2_pw2 * p_1_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2 + f_2_pw2 * p_2_pw4 +
+          p_2_pw4 * f_1_pw2 + 2.0 * p_1 * p_2_pw2 * d_12 + 2.0 * f_1 * f_2 * p_1 * p_2_pw2 * d_12 * b - p_2_pw2 * p_1_pw2 * f_1_pw2 +
+          2.0 * p_1 * p_2_pw2 * f_2_pw2 * d_12 - p_2_pw2 * d_12_pw2 * b_pw2 - 2.0 * p_1_pw2 * p_2_pw2;
+  co[3] = 2.0 * p_1_pw2 * p_2 * d_12 * b + 2.0 * f_2 * p_2_pw3 * f_1 * d_12 - 2.0 * f_2_pw2 * p_2_pw3 * d_12 * b - 2.0 * p_1 * p_2 * d_12_pw2 * b;
+  co[4] = -2 * f_2 * p_2_pw2 * f_1 * p_1 * d_12 * b + f_2_pw2 * p_2_pw2 * d_12_pw2 + 2.0 * p_1_pw3 * d_12 - p_1_pw2 * d_12_pw2 +
+          f_2_pw2 * p_2_pw2 * p_1_pw2 - p_1_pw4 - 2.0 * f_2_pw2 * p_2_pw2 * p_1 * d_12 + p_2_pw2 * f_1_pw2 * p_1_pw2 +
+          f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2;
+  double re[4], im[4];
+  const int nroots = PolyRoots(co, 5, re, im);
+  for (int s = 0; s < nroots; ++s) {
+    const double cos_theta = re[s];
+    const double cot_alpha = (-f_1 * p_1 / f_2 - cos_theta * p_2 + d_12 * b) / (-f_1 * cos_theta * p_2 / f_2 + p_1 - d_12);
+    // Backsubstitute
+    const double sin_theta = std::sqrt(1.0 - cos_theta * cos_theta);
+    const double sin_alpha = std::sqrt(1.0 / (cot_alpha * cot_alpha + 1.0));
+    double cos_alpha = std::sqrt(1.0 - sin_alpha * sin_alpha);
+    if (cot_alpha < 0) cos_alpha = -cos_alpha;
+    const double k = sin_alpha * b + cos_alpha;
+    const double c_nu[3] = {d_12 * cos_alpha * k, cos_theta * d_12 * sin_alpha * k, sin_theta * d_12 * sin_alpha * k};
+    double trans[3];
+    for (int c = 0; c < 3; ++c) trans[c] = w[0][c] + (Nw[0][c] * c_nu[0] + Nw[1][c] * c_nu[1] + Nw[2][c] * c_nu[2]);  // N^T c_nu
+    const double Q[3][3] = {{-cos_alpha, -sin_alpha * cos_theta, -sin_alpha * sin_theta},
+                            {sin_alpha, -cos_alpha * cos_theta, -cos_alpha * sin_theta},
+                            {0, -sin_theta, cos_theta}};
+    // rotation = (N^T Q^T Tc)^T = Tc^T Q N
+    double QN[3][3], R[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) QN[r][c] = Q[r][0] * Nw[0][c] + Q[r][1] * Nw[1][c] + Q[r][2] * Nw[2][c];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = Tc[0][r] * QN[0][c] + Tc[1][r] * QN[1][c] + Tc[2][r] * QN[2][c];
+    for (int k2 = 0; k2 < 9; ++k2) Rs[9 * s + k2] = R[k2];
+    for (int r = 0; r < 3; ++r) ts[3 * s + r] = -(R[r * 3] * trans[0] + R[r * 3 + 1] * trans[1] + R[r * 3 + 2] * trans[2]);
+  }
+  return nroots;
+}
+
+// pose/util.cc:81-111
+void NormalizeImagePoints(const double* pts, int n, int stride, double* out, double* T) {
+  double cx = 0.0, cy = 0.0;
+  for (int i = 0; i < n; ++i) { cx += pts[i * stride]; cy += pts[i * stride + 1]; }
+  cx /= n; cy /= n;
+  double sq = 0.0;
+  for (int i = 0; i < n; ++i) { const double dx = pts[i * stride] - cx, dy = pts[i * stride + 1] - cy; sq += dx * dx; sq += dy * dy; }
+  const double rms = std::sqrt(sq / n);
+  const double nf = std::sqrt(2.0) / rms;
+  T[0] = nf; T[1] = 0; T[2] = -1.0 * nf * cx; T[3] = 0; T[4] = nf; T[5] = -1.0 * nf * cy; T[6] = 0; T[7] = 0; T[8] = 1;
+  for (int i = 0; i < n; ++i) {
+    const double x = pts[i * stride], y = pts[i * stride + 1];
+    const double hx = T[0] * x + T[1] * y + T[2], hy = T[3] * x + T[4] * y + T[5], hw = T[6] * x + T[7] * y + T[8];
+    out[2 * i] = hx / hw; out[2 * i + 1] = hy / hw;
+  }
+}
+inline void Inverse3(const double* M, double* inv) {
+  const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+  const double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = (M[2] * M[7] - M[1] * M[8]) * id; inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+  inv[3] = c01 * id; inv[4] = (M[0] * M[8] - M[2] * M[6]) * id; inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+  inv[6] = c02 * id; inv[7] = (M[1] * M[6] - M[0] * M[7]) * id; inv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+inline void Mul33(const double* A, const double* B, double* C) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+
+// sfm/pose/four_point_homography.cc:72-102, minimal case (4 correspondences x1,y1,x2,y2). H row-major.
+bool FourPointH(const double* corr, double* H) {
+  double n1[8], n2[8], T1[9], T2[9];
+  NormalizeImagePoints(corr, 4, 4, n1, T1);
+  NormalizeImagePoints(corr + 2, 4, 4, n2, T2);
+  double A[8 * 9];
+  for (int i = 0; i < 4; ++i) {
+    const double x = n1[2 * i], y = n1[2 * i + 1], u = n2[2 * i], v = n2[2 * i + 1];
+    double* r0 = A + 18 * i; double* r1 = r0 + 9;
+    r0[0] = 0; r0[1] = 0; r0[2] = 0; r0[3] = -x; r0[4] = -y; r0[5] = -1.0; r0[6] = x * v; r0[7] = y * v; r0[8] = v;
+    r1[0] = x; r1[1] = y; r1[2] = 1.0; r1[3] = 0; r1[4] = 0; r1[5] = 0; r1[6] = -x * u; r1[7] = -y * u; r1[8] = -u;
+  }
+  double AtA[81];
+  for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0.0; for (int k = 0; k < 8; ++k) s += A[k * 9 + r] * A[k * 9 + c]; AtA[r * 9 + c] = s; }
+  double U[81], S[9], V[81];
+  JacobiSVDN<9>(AtA, U, S, V);
+  double Hn[9];
+  for (int k = 0; k < 9; ++k) Hn[k] = V[k * 9 + 8];  // Map<Matrix3d>(null).transpose(): H(r,c) = null[3r + c]
+  double T2i[9], tmp[9];
+  Inverse3(T2, T2i);
+  Mul33(T2i, Hn, tmp);
+  Mul33(tmp, T1, H);
+  return true;
+}
+
+// sfm/pose/seven_point_fundamental_matrix.cc:72-152 — including its coefficient-order quirk: the
+// det(F2)-only term is stored at index 0 although polynomial(0) is the highest-degree coefficient, and the real
+// parts of ALL roots are used. img: 7 x (x1,y1,x2,y2). F_out: up to 3 row-major matrices.
+int SevenPointF(const double* corr, double* F_out) {
+  double n1[14], n2[14], T1[9], T2[9];
+  NormalizeImagePoints(corr, 7, 4, n1, T1);
+  NormalizeImagePoints(corr + 2, 7, 4, n2, T2);
+  double epi[7 * 9];
+  for (int i = 0; i < 7; ++i) {
+    const double ax = n1[2 * i], ay = n1[2 * i + 1], bx = n2[2 * i], by = n2[2 * i + 1];
+    double* r = epi + 9 * i;
+    r[0] = bx * ax; r[1] = by * ax; r[2] = ax; r[3] = bx * ay; r[4] = by * ay; r[5] = ay; r[6] = bx; r[7] = by; r[8] = 1.0;
+  }
+  FullPivLU<7, 9> lu;
+  lu.compute(epi);
+  if (lu.dimensionOfKernel() != 2) return 0;
+  double ns[18];
+  lu.kernel(ns);
+  double v1[9], v2[9];
+  for (int k = 0; k < 9; ++k) { v1[k] = ns[k * 2] - ns[k * 2 + 1]; v2[k] = ns[k * 2 + 1]; }
+  // Map<const Matrix3d>(vec): column-major, M(r, c) = vec[c*3 + r]
+  auto F1 = [&](int r, int c) { return v1[c * 3 + r]; };
+  auto F2 = [&](int r, int c) { return v2[c * 3 + r]; };
+  double dc[4];
+  dc[0] = -(F2(1, 2) * F2(2, 1) - F2(1, 1) * F2(2, 2)) * F2(0, 0) + (F2(0, 2) * F2(2, 1) - F2(0, 1) * F2(2, 2)) * F2(1, 0) -
+          (F2(0, 2) * F2(1, 1) - F2(0, 1) * F2(1, 2)) * F2(2, 0);
+  dc[1] = -(F2(1, 2) * F2(2, 1) - F2(1, 1) * F2(2, 2)) * F1(0, 0) + (F2(0, 2) * F2(2, 1) - F2(0, 1) * F2(2, 2)) * F1(1, 0) -
+          (F2(0, 2) * F2(1, 1) - F2(0, 1) * F2(1, 2)) * F1(2, 0) +
+          (F1(2, 2) * F2(1, 1) - F1(2, 1) * F2(1, 2) - F1(1, 2) * F2(2, 1) + F1(1, 1) * F2(2, 2)) * F2(0, 0) -
+          (F1(2, 2) * F2(0, 1) - F1(2, 1) * F2(0, 2) - F1(0, 2) * F2(2, 1) + F1(0, 1) * F2(2, 2)) * F2(1, 0) +
+          (F1(1, 2) * F2(0, 1) - F1(1, 1) * F2(0, 2) - F1(0, 2) * F2(1, 1) + F1(0, 1) * F2(1, 2)) * F2(2, 0);
+  dc[2] = (F1(2, 2) * F2(1, 1) - F1(2, 1) * F2(1, 2) - F1(1, 2) * F2(2, 1) + F1(1, 1) * F2(2, 2)) * F1(0, 0) -
+          (F1(2, 2) * F2(0, 1) - F1(2, 1) * F2(0, 2) - F1(0, 2) * F2(2, 1) + F1(0, 1) * F2(2, 2)) * F1(1, 0) +
+          (F1(1, 2) * F2(0, 1) - F1(1, 1) * F2(0, 2) - F1(0, 2) * F2(1, 1) + F1(0, 1) * F2(1, 2)) * F1(2, 0) -
+          (F1(1, 2) * F1(2, 1) - F1(1, 1) * F1(2, 2)) * F2(0, 0) + (F1(0, 2) * F1(2, 1) - F1(0, 1) * F1(2, 2)) * F2(1, 0) -
+          (F1(0, 2) * F1(1, 1) - F1(0, 1) * F1(1, 2)) * F2(2, 0);
+  dc[3] = -(F1(1, 2) * F1(2, 1) - F1(1, 1) * F1(2, 2)) * F1(0, 0) + (F1(0, 2) * F1(2, 1) - F1(0, 1) * F1(2, 2)) * F1(1, 0) -
+          (F1(0, 2) * F1(1, 1) - F1(0, 1) * F1(1, 2)) * F1(2, 0);
+  double re[4], im[4];
+  const int nroots = PolyRoots(dc, 4, re, im);
+  double T2t[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T2t[r * 3 + c] = T2[c * 3 + r];
+  for (int s = 0; s < nroots; ++s) {
+    double M[9], tmp[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r * 3 + c] = re[s] * F1(r, c) + F2(r, c);
+    Mul33(T2t, M, tmp);
+    Mul33(tmp, T1, F_out + 9 * s);
+  }
+  return nroots;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Estimator policies (solvers/estimator.h): sample size, model estimation, per-datum error.
+struct Model { double E[9], R[9], p[3]; };  // 21 doubles: the ThbRelPoseResult payload
+
+struct RelPoseEst {  // RelativePoseEstimator, estimate_relative_pose.cc:65-155
+  static constexpr int S = 5, D = 4, MAXM = 10;
+  static int Solve(const double* sample, Model* out) {
+    double x1[10], x2[10], Es[90];
+    for (int i = 0; i < 5; ++i) { x1[2 * i] = sample[4 * i]; x1[2 * i + 1] = sample[4 * i + 1]; x2[2 * i] = sample[4 * i + 2]; x2[2 * i + 1] = sample[4 * i + 3]; }
+    const int ne = FivePoint(x1, x2, Es);
+    int n = 0;
+    for (int e = 0; e < ne; ++e) {
+      Model m;
+      std::memcpy(m.E, Es + 9 * e, sizeof(m.E));
+      if (BestPose(m.E, sample, 5, m.R, m.p) < 4) continue;
+      out[n++] = m;
+    }
+    return n;
+  }
+  static double Error(const Model& m, const double* c) { return InFront(c, m.R, m.p) ? Sampson(m.E, c) : DBL_MAX; }
+};
+
+struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator with PnPType::KNEIP, estimate_calibrated_absolute_pose.cc:63-172
+  static constexpr int S = 3, D = 5, MAXM = 4;   // datum: feature (x, y), world point (X, Y, Z)
+  static int Solve(const double* sample, Model* out) {
+    double feat[6], world[9], Rs[36], ts[12];
+    for (int i = 0; i < 3; ++i) { feat[2 * i] = sample[5 * i]; feat[2 * i + 1] = sample[5 * i + 1]; for (int k = 0; k < 3; ++k) world[3 * i + k] = sample[5 * i + 2 + k]; }
+    const int n = P3P(feat, world, Rs, ts);
+    for (int s = 0; s < n; ++s) {
+      Model& m = out[s];
+      std::memset(&m, 0, sizeof(m));
+      for (int k = 0; k < 9; ++k) m.R[k] = Rs[9 * s + k];
+      for (int c = 0; c < 3; ++c) m.p[c] = -(m.R[0 * 3 + c] * ts[3 * s] + m.R[1 * 3 + c] * ts[3 * s + 1] + m.R[2 * 3 + c] * ts[3 * s + 2]);  // -R^T t
+    }
+    return n;
+  }
+  static double Error(const Model& m, const double* d) {  // squared reprojection error, :158-167
+    const double v[3] = {d[2] - m.p[0], d[3] - m.p[1], d[4] - m.p[2]};
+    const double px = std::fma(m.R[0], v[0], std::fma(m.R[1], v[1], m.R[2] * v[2]));
+    const double py = std::fma(m.R[3], v[0], std::fma(m.R[4], v[1], m.R[5] * v[2]));
+    const double pz = std::fma(m.R[6], v[0], std::fma(m.R[7], v[1], m.R[8] * v[2]));
+    const double ex = px / pz - d[0], ey = py / pz - d[1];
+    return std::fma(ex, ex, ey * ey);
+  }
+};
+
+struct HomographyEst {  // HomographyEstimator, estimate_homography.cc:62-116; the model lives in Model::E
+  static constexpr int S = 4, D = 4, MAXM = 1;
+  static int Solve(const double* sample, Model* out) {
+    std::memset(out, 0, sizeof(Model));
+    return FourPointH(sample, out->E) ? 1 : 0;
+  }
+  static double Error(const Model& m, const double* c) {  // one-way transfer error
+    const double* H = m.E;
+    const double px = std::fma(H[0], c[0], std::fma(H[1], c[1], H[2]));
+    const double py = std::fma(H[3], c[0], std::fma(H[4], c[1], H[5]));
+    const double pz = std::fma(H[6], c[0], std::fma(H[7], c[1], H[8]));
+    const double ex = c[2] - px / pz, ey = c[3] - py / pz;
+    return std::fma(ex, ex, ey * ey);
+  }
+};
 
 // sample_consensus_estimator.h:251-297
 int ComputeMaxIterations(const ThbRansacParams& P, double min_sample_size, double inlier_ratio, double log_failure_prob, int total) {
@@ -223,11 +539,12 @@ int ComputeMaxIterations(const ThbRansacParams& P, double min_sample_size, doubl
   return std::max(static_cast<double>(P.min_iterations), std::min(num_iterations, static_cast<double>(P.max_iterations)));
 }
 
-double Score(const ThbRansacParams& P, const double* corr, int n, const Model& m, std::vector<int>* inliers) {
+template <class Est>
+double Score(const ThbRansacParams& P, const double* data, int n, const Model& m, std::vector<int>* inliers) {
   inliers->clear();
   double cost = 0.0;
   for (int i = 0; i < n; ++i) {
-    const double r = InFront(corr + 4 * i, m.R, m.p) ? Sampson(m.E, corr + 4 * i) : DBL_MAX;
+    const double r = Est::Error(m, data + Est::D * (size_t)i);
     if (P.use_mle) {
       if (r < P.error_thresh) { cost += r; inliers->push_back(i); } else cost += P.error_thresh;
     } else if (r < P.error_thresh) {
@@ -237,61 +554,72 @@ double Score(const ThbRansacParams& P, const double* corr, int n, const Model& m
   return P.use_mle ? cost : static_cast<double>(n - static_cast<int>(inliers->size()));
 }
 
-void EstimatePair(const ThbRansacParams& P, const double* corr, int n, uint32_t seed, ThbRelPoseResult* out, uint8_t* mask) {
+// SampleConsensusEstimator::Estimate (sample_consensus_estimator.h:299-415) with RandomSampler (random_sampler.cc:53-72)
+template <class Est>
+void EstimatePair(const ThbRansacParams& P, const double* data, int n, uint32_t seed, ThbRelPoseResult* out, uint8_t* mask) {
+  constexpr int S = Est::S;
   std::memset(out, 0, sizeof(*out));
   out->num_input_data_points = n;
   if (mask) std::memset(mask, 0, n);
-  if (n < 5) return;  // RandomSampler::Initialize CHECK_GE -> reported as failure instead of aborting
+  if (n < S) return;  // RandomSampler::Initialize CHECK_GE -> reported as failure instead of aborting
   std::mt19937 gen(seed);
   std::vector<int> sample_indices(n);
   std::iota(sample_indices.begin(), sample_indices.end(), 0);
   const double log_failure_prob = std::log(P.failure_probability);
   double best_cost = DBL_MAX;
   int max_iterations = P.max_iterations;
-  if (P.min_inlier_ratio > 0) max_iterations = std::min(ComputeMaxIterations(P, 5, P.min_inlier_ratio, log_failure_prob, n), P.max_iterations);
+  if (P.min_inlier_ratio > 0) max_iterations = std::min(ComputeMaxIterations(P, S, P.min_inlier_ratio, log_failure_prob, n), P.max_iterations);
   Model best;
   std::memset(&best, 0, sizeof(best));
   std::vector<int> inl;
   int it;
   for (it = 0; it < max_iterations; ++it) {
-    int idx[5];
-    for (int i = 0; i < 5; ++i) {
+    double sample[S * Est::D];
+    for (int i = 0; i < S; ++i) {
       std::uniform_int_distribution<int> dist(i, n - 1);
       std::swap(sample_indices[i], sample_indices[dist(gen)]);
-      idx[i] = sample_indices[i];
+      for (int k = 0; k < Est::D; ++k) sample[Est::D * i + k] = data[Est::D * (size_t)sample_indices[i] + k];
     }
-    double x1[10], x2[10], sc[20];
-    for (int i = 0; i < 5; ++i) {
-      const double* c = corr + 4 * (size_t)idx[i];
-      x1[2 * i] = c[0]; x1[2 * i + 1] = c[1]; x2[2 * i] = c[2]; x2[2 * i + 1] = c[3];
-      for (int k = 0; k < 4; ++k) sc[4 * i + k] = c[k];
-    }
-    double Es[90];
-    const int ne = FivePoint(x1, x2, Es);
-    for (int e = 0; e < ne; ++e) {
-      Model m;
-      std::memcpy(m.E, Es + 9 * e, sizeof(m.E));
-      if (BestPose(m.E, sc, 5, m.R, m.p) < 4) continue;
-      const double cost = Score(P, corr, n, m, &inl);
+    Model models[Est::MAXM];
+    const int nm = Est::Solve(sample, models);
+    for (int e = 0; e < nm; ++e) {
+      const Model& m = models[e];
+      const double cost = Score<Est>(P, data, n, m, &inl);
       const double inlier_ratio = static_cast<double>(inl.size()) / static_cast<double>(n);
       if (cost < best_cost) {
         best = m; best_cost = cost;
-        if (inlier_ratio < 5.0 / static_cast<double>(n)) continue;
-        max_iterations = std::min(ComputeMaxIterations(P, 5, inlier_ratio, log_failure_prob, n), max_iterations);
+        if (inlier_ratio < static_cast<double>(S) / static_cast<double>(n)) continue;
+        max_iterations = std::min(ComputeMaxIterations(P, S, inlier_ratio, log_failure_prob, n), max_iterations);
       }
     }
   }
-  Score(P, corr, n, best, &inl);
+  Score<Est>(P, data, n, best, &inl);
   out->success = 1;
   out->num_iterations = it;
   out->num_inliers = static_cast<int>(inl.size());
   const double ratio = static_cast<double>(inl.size()) / n;
-  out->confidence = 1.0 - std::pow(1.0 - std::pow(ratio, 5.0), out->num_iterations);
+  out->confidence = 1.0 - std::pow(1.0 - std::pow(ratio, static_cast<double>(S)), out->num_iterations);
   out->best_cost = best_cost;
   std::memcpy(out->essential_matrix, best.E, sizeof(best.E));
   std::memcpy(out->rotation, best.R, sizeof(best.R));
   std::memcpy(out->position, best.p, sizeof(best.p));
   if (mask) for (int i : inl) mask[i] = 1;
+}
+
+template <class Est>
+int RunBatch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
+  if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
+  if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
+      p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) return THB_E_INVALID_ARGUMENT;
+  if (p->use_lo || p->ransac_type != 0) return THB_E_UNSUPPORTED;
+  const int nt = threads > 0 ? threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
+  for (int i = 0; i < b->num_pairs; ++i) {
+    const int64_t o = b->pair_offset[i];
+    const int n = static_cast<int>(b->pair_offset[i + 1] - o);
+    EstimatePair<Est>(*p, b->corr + Est::D * o, n, b->seed[i], results + i, mask ? mask + o : nullptr);
+  }
+  return THB_OK;
 }
 
 }  // namespace
@@ -315,19 +643,34 @@ int oracle_five_point(const double* x1, const double* x2, int32_t count, double*
 }
 
 int oracle_ransac_relpose_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
-  if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
-  if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
-      p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) return THB_E_INVALID_ARGUMENT;
-  if (p->use_lo || p->ransac_type != 0) return THB_E_UNSUPPORTED;
-  const int nt = threads > 0 ? threads : omp_get_max_threads();
-#pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
-  for (int i = 0; i < b->num_pairs; ++i) {
-    const int64_t o = b->pair_offset[i];
-    const int n = static_cast<int>(b->pair_offset[i + 1] - o);
-    oracle::EstimatePair(*p, b->corr + 4 * o, n, b->seed[i], results + i, mask ? mask + o : nullptr);
+  return oracle::RunBatch<oracle::RelPoseEst>(b, p, results, mask, threads);
+}
+int oracle_ransac_abspose_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
+  return oracle::RunBatch<oracle::AbsPoseEst>(b, p, results, mask, threads);
+}
+int oracle_ransac_homography_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
+  return oracle::RunBatch<oracle::HomographyEst>(b, p, results, mask, threads);
+}
+int oracle_p3p(const double* feat, const double* world, int32_t count, double* R_out, double* t_out, int32_t* num_solutions) {
+  for (int i = 0; i < count; ++i) {
+    for (int k = 0; k < 36; ++k) R_out[(size_t)i * 36 + k] = 0.0;
+    for (int k = 0; k < 12; ++k) t_out[(size_t)i * 12 + k] = 0.0;
+    num_solutions[i] = oracle::P3P(feat + 6 * (size_t)i, world + 9 * (size_t)i, R_out + 36 * (size_t)i, t_out + 12 * (size_t)i);
   }
   return THB_OK;
 }
+int oracle_four_point_homography(const double* corr, int32_t count, double* H_out, int32_t* ok) {
+  for (int i = 0; i < count; ++i) ok[i] = oracle::FourPointH(corr + 16 * (size_t)i, H_out + 9 * (size_t)i) ? 1 : 0;
+  return THB_OK;
+}
+int oracle_seven_point_fundamental(const double* corr, int32_t count, double* F_out, int32_t* num_solutions) {
+  for (int i = 0; i < count; ++i) {
+    for (int k = 0; k < 27; ++k) F_out[(size_t)i * 27 + k] = 0.0;
+    num_solutions[i] = oracle::SevenPointF(corr + 28 * (size_t)i, F_out + 27 * (size_t)i);
+  }
+  return THB_OK;
+}
+int oracle_poly_roots(const double* poly, int32_t size, double* re, double* im) { return oracle::PolyRoots(poly, size, re, im); }
 
 // helpers exposed for the unit tests of the restated decompositions
 void oracle_jacobi_svd3(const double* A, double* U, double* S, double* V) { oracle::JacobiSVD3(A, U, S, V); }

@@ -128,14 +128,15 @@ assert RELPOSE_DTYPE.itemsize == C.sizeof(ThbRelPoseResult)
 class HostPairBatch:
     """Correspondences of a batch of image pairs in the C-ABI layout (host memory)."""
 
-    def __init__(self, corr_list, seeds):
+    def __init__(self, corr_list, seeds, width=4):
+        self.width = width  # 4: FeatureCorrespondence (x1,y1,x2,y2); 5: FeatureCorrespondence2D3D (x,y,X,Y,Z)
         self.num_pairs = len(corr_list)
         sizes = [len(c) for c in corr_list]
         self.pair_offset = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
         self.corr = (np.ascontiguousarray(np.concatenate(corr_list, 0), dtype=np.float64) if self.num_pairs and self.pair_offset[-1] > 0
-                     else np.zeros((0, 4)))
+                     else np.zeros((0, width)))
         self.seed = np.ascontiguousarray(seeds, dtype=np.uint32)
-        assert self.corr.shape == (self.pair_offset[-1], 4) and self.seed.shape == (self.num_pairs,)
+        assert self.corr.shape == (self.pair_offset[-1], width) and self.seed.shape == (self.num_pairs,)
 
     def struct(self):
         b = ThbPairBatch()
@@ -193,6 +194,15 @@ def load_library():
     lib.thb_ransac_default_params.restype = None
     lib.thb_ransac_relpose_batch.argtypes = [C.POINTER(ThbPairBatch), C.POINTER(ThbRansacParams), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_ransac_relpose_batch.restype = C.c_int
+    for name in ("thb_ransac_abspose_batch", "thb_ransac_homography_batch"):
+        getattr(lib, name).argtypes = [C.POINTER(ThbPairBatch), C.POINTER(ThbRansacParams), C.c_void_p, C.c_void_p, C.c_void_p]
+        getattr(lib, name).restype = C.c_int
+    lib.thb_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_p3p.restype = C.c_int
+    lib.thb_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_four_point_homography.restype = C.c_int
+    lib.thb_seven_point_fundamental_matrix.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_seven_point_fundamental_matrix.restype = C.c_int
     lib.thb_five_point_relative_pose.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_five_point_relative_pose.restype = C.c_int
     lib.thb_dense_spd_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]

@@ -61,7 +61,7 @@ __device__ int five_point(const double* x1, const double* x2, double* E_out) {
     lu.lu = epi;
     lu.compute();
     if (9 - lu.rank() != 4) return 0;
-    sl::kernel_5x9(lu, ns);
+    sl::kernel_rx9<5>(lu, ns);
   }
   const double* E[3][3];
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) E[i][j] = ns + 4 * (i + 3 * j);
@@ -193,6 +193,321 @@ __device__ int best_pose(const double* E, const double* corr, int n, double* Rbe
   return best_count;
 }
 
+// ---- polynomial roots: theia::FindPolynomialRootsCompanionMatrix (math/find_polynomial_roots_companion_matrix.cc:
+// 89-233: Parlett-Reinsch balancing :89-137, companion matrix :139-151) and the closed forms of
+// math/polynomial.cc:176-231 for degree 1 and 2 -----------------------------------------------------------------
+template <int D>
+__device__ int companion_roots(const double* monic_tail, double* re, double* im) {
+  double C[D * D], Off[D * D], Uq[D * D], M[D * D];
+  for (int i = 0; i < D * D; ++i) C[i] = 0.0;
+  for (int i = 1; i < D; ++i) C[i * D + i - 1] = 1.0;
+  for (int i = 0; i < D; ++i) C[i * D + D - 1] = -monic_tail[D - 1 - i];
+  for (int i = 0; i < D * D; ++i) Off[i] = C[i];
+  for (int i = 0; i < D; ++i) Off[i * D + i] = 0.0;
+  const double gamma = 0.9;
+  bool changed;
+  do {
+    changed = false;
+    for (int i = 0; i < D; ++i) {
+      double row_norm = 0.0, col_norm = 0.0;
+      for (int k = 0; k < D; ++k) { row_norm += fabs(Off[i * D + k]); col_norm += fabs(Off[k * D + i]); }
+      int exponent = 0;
+      frexp(row_norm / col_norm, &exponent);
+      exponent /= 2;
+      if (exponent != 0) {
+        const double scaled_col = ldexp(col_norm, exponent), scaled_row = ldexp(row_norm, -exponent);
+        if (scaled_col + scaled_row < gamma * (col_norm + row_norm)) {
+          changed = true;
+          const double fr = ldexp(1.0, -exponent), fc = ldexp(1.0, exponent);
+          for (int k = 0; k < D; ++k) Off[i * D + k] *= fr;
+          for (int k = 0; k < D; ++k) Off[k * D + i] *= fc;
+        }
+      }
+    }
+  } while (changed);
+  for (int i = 0; i < D; ++i) Off[i * D + i] = C[i * D + i];
+  sl::EigenReal<D> es;
+  es.T = Off; es.Uq = Uq; es.M = M;
+  es.compute(nullptr, false);
+  if (!es.ok) return 0;
+  for (int i = 0; i < D; ++i) { re[i] = es.eig_re[i]; im[i] = es.eig_im[i]; }
+  return D;
+}
+__device__ int poly_roots(const double* poly_in, int size, double* re, double* im) {
+  int lead = 0;
+  while (lead < size - 1 && poly_in[lead] == 0.0) ++lead;
+  const double* p = poly_in + lead;
+  const int degree = size - lead - 1;
+  if (degree == 0) return 0;
+  if (degree == 1) { re[0] = -p[1] / p[0]; im[0] = 0.0; return 1; }
+  if (degree == 2) {
+    const double a = p[0], b = p[1], c = p[2];
+    const double Dd = b * b - 4 * a * c, sqrt_D = sqrt(fabs(Dd));
+    im[0] = im[1] = 0.0;
+    if (Dd >= 0) {
+      if (b >= 0) { re[0] = (-b - sqrt_D) / (2.0 * a); re[1] = (2.0 * c) / (-b - sqrt_D); }
+      else { re[0] = (2.0 * c) / (-b + sqrt_D); re[1] = (-b + sqrt_D) / (2.0 * a); }
+      return 2;
+    }
+    re[0] = -b / (2.0 * a); re[1] = -b / (2.0 * a);
+    im[0] = sqrt_D / (2.0 * a); im[1] = -sqrt_D / (2.0 * a);
+    return 2;
+  }
+  double tail[4];
+  for (int i = 0; i < degree; ++i) tail[i] = p[1 + i] / p[0];
+  if (degree == 3) return companion_roots<3>(tail, re, im);
+  return companion_roots<4>(tail, re, im);
+}
+
+__device__ __forceinline__ void cross3(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ double dot3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+__device__ __forceinline__ void normalize3(double* a) { const double n = sqrt(dot3(a, a)); a[0] /= n; a[1] /= n; a[2] /= n; }
+
+// theia::PoseFromThreePoints (Kneip P3P, sfm/pose/perspective_three_point.cc:182-291; quartic :58-130, back-substitution
+// :135-178). The real parts of all roots are kept, as the reference does.
+__device__ int p3p(const double* feat, const double* world, double* Rs, double* ts) {
+  double f[3][3], w[3][3];
+  for (int i = 0; i < 3; ++i) {
+    f[i][0] = feat[2 * i]; f[i][1] = feat[2 * i + 1]; f[i][2] = 1.0;
+    normalize3(f[i]);
+    for (int k = 0; k < 3; ++k) w[i][k] = world[3 * i + k];
+  }
+  double w10[3], w20[3], cr[3];
+  for (int k = 0; k < 3; ++k) { w10[k] = w[1][k] - w[0][k]; w20[k] = w[2][k] - w[0][k]; }
+  cross3(w10, w20, cr);
+  if (dot3(cr, cr) < 1e-6) return 0;
+  double Tc[3][3];
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = 0; k < 3; ++k) Tc[0][k] = f[0][k];
+    cross3(f[0], f[1], Tc[2]); normalize3(Tc[2]);
+    cross3(Tc[2], Tc[0], Tc[1]);
+    if (pass == 1) break;
+    if (dot3(Tc[2], f[2]) > 0) {
+      for (int k = 0; k < 3; ++k) { const double t = f[0][k]; f[0][k] = f[1][k]; f[1][k] = t; }
+      for (int k = 0; k < 3; ++k) { const double t = w[0][k]; w[0][k] = w[1][k]; w[1][k] = t; }
+      for (int k = 0; k < 3; ++k) { w10[k] = w[1][k] - w[0][k]; w20[k] = w[2][k] - w[0][k]; }
+    } else {
+      break;
+    }
+  }
+  double ip[3];
+  for (int r = 0; r < 3; ++r) ip[r] = dot3(Tc[r], f[2]);
+  double Nw[3][3];
+  for (int k = 0; k < 3; ++k) Nw[0][k] = w10[k];
+  normalize3(Nw[0]);
+  cross3(Nw[0], w20, Nw[2]); normalize3(Nw[2]);
+  cross3(Nw[2], Nw[0], Nw[1]);
+  double iw[3];
+  for (int r = 0; r < 3; ++r) iw[r] = dot3(Nw[r], w20);
+  const double d_12 = sqrt(dot3(w10, w10));
+  const double f_1 = ip[0] / ip[2], f_2 = ip[1] / ip[2], p_1 = iw[0], p_2 = iw[1];
+  const double cos_beta = dot3(f[0], f[1]);
+  double b = 1.0 / (1.0 - cos_beta * cos_beta) - 1.0;
+  b = cos_beta < 0 ? -sqrt(b) : sqrt(b);
+  const double f_1_pw2 = f_1 * f_1, f_2_pw2 = f_2 * f_2, p_1_pw2 = p_1 * p_1, p_1_pw3 = p_1_pw2 * p_1, p_1_pw4 = p_1_pw3 * p_1;
+  const double p_2_pw2 = p_2 * p_2, p_2_pw3 = p_2_pw2 * p_2, p_2_pw4 = p_2_pw3 * p_2, d_12_pw2 = d_12 * d_12, b_pw2 = b * b;
+  double co[5];
+  co[0] = -f_2_pw2 * p_2_pw4 - p_2_pw4 * f_1_pw2 - p_2_pw4;
+  co[1] = 2.0 * p_2_pw3 * d_12 * b + 2.0 * f_2_pw2 * p_2_pw3 * d_12 * b - 2.0 * f_2 * p_2_pw3 * f_1 * d_12;
+  co[2] = -f_2_pw2 * p_2_pw2 * p_1_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2 - f_2_pw2 * p_2_pw2 * d_12_pw2 + f_2_pw2 * p_2_pw4 +
+          p_2_pw4 * f_1_pw2 + 2.0 * p_1 * p_2_pw2 * d_12 + 2.0 * f_1 * f_2 * p_1 * p_2_pw2 * d_12 * b - p_2_pw2 * p_1_pw2 * f_1_pw2 +
+          2.0 * p_1 * p_2_pw2 * f_2_pw2 * d_12 - p_2_pw2 * d_12_pw2 * b_pw2 - 2.0 * p_1_pw2 * p_2_pw2;
+  co[3] = 2.0 * p_1_pw2 * p_2 * d_12 * b + 2.0 * f_2 * p_2_pw3 * f_1 * d_12 - 2.0 * f_2_pw2 * p_2_pw3 * d_12 * b - 2.0 * p_1 * p_2 * d_12_pw2 * b;
+  co[4] = -2 * f_2 * p_2_pw2 * f_1 * p_1 * d_12 * b + f_2_pw2 * p_2_pw2 * d_12_pw2 + 2.0 * p_1_pw3 * d_12 - p_1_pw2 * d_12_pw2 +
+          f_2_pw2 * p_2_pw2 * p_1_pw2 - p_1_pw4 - 2.0 * f_2_pw2 * p_2_pw2 * p_1 * d_12 + p_2_pw2 * f_1_pw2 * p_1_pw2 +
+          f_2_pw2 * p_2_pw2 * d_12_pw2 * b_pw2;
+  double re[4], im[4];
+  const int nroots = poly_roots(co, 5, re, im);
+  for (int s = 0; s < nroots; ++s) {
+    const double cos_theta = re[s];
+    const double cot_alpha = (-f_1 * p_1 / f_2 - cos_theta * p_2 + d_12 * b) / (-f_1 * cos_theta * p_2 / f_2 + p_1 - d_12);
+    const double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+    const double sin_alpha = sqrt(1.0 / (cot_alpha * cot_alpha + 1.0));
+    double cos_alpha = sqrt(1.0 - sin_alpha * sin_alpha);
+    if (cot_alpha < 0) cos_alpha = -cos_alpha;
+    const double k = sin_alpha * b + cos_alpha;
+    const double c_nu[3] = {d_12 * cos_alpha * k, cos_theta * d_12 * sin_alpha * k, sin_theta * d_12 * sin_alpha * k};
+    double trans[3];
+    for (int c = 0; c < 3; ++c) trans[c] = w[0][c] + (Nw[0][c] * c_nu[0] + Nw[1][c] * c_nu[1] + Nw[2][c] * c_nu[2]);
+    const double Q[3][3] = {{-cos_alpha, -sin_alpha * cos_theta, -sin_alpha * sin_theta},
+                            {sin_alpha, -cos_alpha * cos_theta, -cos_alpha * sin_theta},
+                            {0, -sin_theta, cos_theta}};
+    double QN[3][3], R[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) QN[r][c] = Q[r][0] * Nw[0][c] + Q[r][1] * Nw[1][c] + Q[r][2] * Nw[2][c];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = Tc[0][r] * QN[0][c] + Tc[1][r] * QN[1][c] + Tc[2][r] * QN[2][c];
+    for (int k2 = 0; k2 < 9; ++k2) Rs[9 * s + k2] = R[k2];
+    for (int r = 0; r < 3; ++r) ts[3 * s + r] = -(R[r * 3] * trans[0] + R[r * 3 + 1] * trans[1] + R[r * 3 + 2] * trans[2]);
+  }
+  return nroots;
+}
+
+// theia::NormalizeImagePoints (sfm/pose/util.cc:81-111)
+__device__ void normalize_image_points(const double* pts, int n, int stride, double* out, double* T) {
+  double cx = 0.0, cy = 0.0;
+  for (int i = 0; i < n; ++i) { cx += pts[i * stride]; cy += pts[i * stride + 1]; }
+  cx /= n; cy /= n;
+  double sq = 0.0;
+  for (int i = 0; i < n; ++i) { const double dx = pts[i * stride] - cx, dy = pts[i * stride + 1] - cy; sq += dx * dx; sq += dy * dy; }
+  const double rms = sqrt(sq / n);
+  const double nf = sqrt(2.0) / rms;
+  T[0] = nf; T[1] = 0; T[2] = -1.0 * nf * cx; T[3] = 0; T[4] = nf; T[5] = -1.0 * nf * cy; T[6] = 0; T[7] = 0; T[8] = 1;
+  for (int i = 0; i < n; ++i) {
+    const double x = pts[i * stride], y = pts[i * stride + 1];
+    const double hx = T[0] * x + T[1] * y + T[2], hy = T[3] * x + T[4] * y + T[5], hw = T[6] * x + T[7] * y + T[8];
+    out[2 * i] = hx / hw; out[2 * i + 1] = hy / hw;
+  }
+}
+__device__ __forceinline__ void inverse3(const double* M, double* inv) {
+  const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+  const double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
+  inv[0] = c00 * id; inv[1] = (M[2] * M[7] - M[1] * M[8]) * id; inv[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+  inv[3] = c01 * id; inv[4] = (M[0] * M[8] - M[2] * M[6]) * id; inv[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+  inv[6] = c02 * id; inv[7] = (M[1] * M[6] - M[0] * M[7]) * id; inv[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+__device__ __forceinline__ void mul33(const double* A, const double* B, double* C) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+}
+
+// theia::FourPointHomography, minimal case (sfm/pose/four_point_homography.cc:72-102)
+__device__ bool four_point_h(const double* corr, double* H) {
+  double n1[8], n2[8], T1[9], T2[9];
+  normalize_image_points(corr, 4, 4, n1, T1);
+  normalize_image_points(corr + 2, 4, 4, n2, T2);
+  double AtA[81], W[81], U[81], V[81], S[9];
+  {
+    double A[8 * 9];
+    for (int i = 0; i < 4; ++i) {
+      const double x = n1[2 * i], y = n1[2 * i + 1], u = n2[2 * i], v = n2[2 * i + 1];
+      double* r0 = A + 18 * i; double* r1 = r0 + 9;
+      r0[0] = 0; r0[1] = 0; r0[2] = 0; r0[3] = -x; r0[4] = -y; r0[5] = -1.0; r0[6] = x * v; r0[7] = y * v; r0[8] = v;
+      r1[0] = x; r1[1] = y; r1[2] = 1.0; r1[3] = 0; r1[4] = 0; r1[5] = 0; r1[6] = -x * u; r1[7] = -y * u; r1[8] = -u;
+    }
+    for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0.0; for (int k = 0; k < 8; ++k) s += A[k * 9 + r] * A[k * 9 + c]; AtA[r * 9 + c] = s; }
+  }
+  sl::jacobi_svd<9>(AtA, W, U, S, V);
+  double Hn[9], T2i[9], tmp[9];
+  for (int k = 0; k < 9; ++k) Hn[k] = V[k * 9 + 8];
+  inverse3(T2, T2i);
+  mul33(T2i, Hn, tmp);
+  mul33(tmp, T1, H);
+  return true;
+}
+
+// theia::SevenPointFundamentalMatrix (sfm/pose/seven_point_fundamental_matrix.cc:72-152), including the reference's
+// coefficient-order quirk: the det(F2)-only term sits at index 0 although polynomial(0) is the highest-degree
+// coefficient, and the real parts of all roots are used.
+__device__ int seven_point_f(const double* corr, double* F_out) {
+  double n1[14], n2[14], T1[9], T2[9];
+  normalize_image_points(corr, 7, 4, n1, T1);
+  normalize_image_points(corr + 2, 7, 4, n2, T2);
+  double ns[18];
+  {
+    double epi[7 * 9];
+    for (int i = 0; i < 7; ++i) {
+      const double ax = n1[2 * i], ay = n1[2 * i + 1], bx = n2[2 * i], by = n2[2 * i + 1];
+      double* r = epi + 9 * i;
+      r[0] = bx * ax; r[1] = by * ax; r[2] = ax; r[3] = bx * ay; r[4] = by * ay; r[5] = ay; r[6] = bx; r[7] = by; r[8] = 1.0;
+    }
+    sl::FullPivLU<7, 9> lu;
+    lu.lu = epi;
+    lu.compute();
+    if (9 - lu.rank() != 2) return 0;
+    sl::kernel_rx9<7>(lu, ns);
+  }
+  double v1[9], v2[9];
+  for (int k = 0; k < 9; ++k) { v1[k] = ns[k * 2] - ns[k * 2 + 1]; v2[k] = ns[k * 2 + 1]; }
+#define F1(r, c) v1[(c) * 3 + (r)]
+#define F2(r, c) v2[(c) * 3 + (r)]
+  double dc[4];
+  dc[0] = -(F2(1, 2) * F2(2, 1) - F2(1, 1) * F2(2, 2)) * F2(0, 0) + (F2(0, 2) * F2(2, 1) - F2(0, 1) * F2(2, 2)) * F2(1, 0) -
+          (F2(0, 2) * F2(1, 1) - F2(0, 1) * F2(1, 2)) * F2(2, 0);
+  dc[1] = -(F2(1, 2) * F2(2, 1) - F2(1, 1) * F2(2, 2)) * F1(0, 0) + (F2(0, 2) * F2(2, 1) - F2(0, 1) * F2(2, 2)) * F1(1, 0) -
+          (F2(0, 2) * F2(1, 1) - F2(0, 1) * F2(1, 2)) * F1(2, 0) +
+          (F1(2, 2) * F2(1, 1) - F1(2, 1) * F2(1, 2) - F1(1, 2) * F2(2, 1) + F1(1, 1) * F2(2, 2)) * F2(0, 0) -
+          (F1(2, 2) * F2(0, 1) - F1(2, 1) * F2(0, 2) - F1(0, 2) * F2(2, 1) + F1(0, 1) * F2(2, 2)) * F2(1, 0) +
+          (F1(1, 2) * F2(0, 1) - F1(1, 1) * F2(0, 2) - F1(0, 2) * F2(1, 1) + F1(0, 1) * F2(1, 2)) * F2(2, 0);
+  dc[2] = (F1(2, 2) * F2(1, 1) - F1(2, 1) * F2(1, 2) - F1(1, 2) * F2(2, 1) + F1(1, 1) * F2(2, 2)) * F1(0, 0) -
+          (F1(2, 2) * F2(0, 1) - F1(2, 1) * F2(0, 2) - F1(0, 2) * F2(2, 1) + F1(0, 1) * F2(2, 2)) * F1(1, 0) +
+          (F1(1, 2) * F2(0, 1) - F1(1, 1) * F2(0, 2) - F1(0, 2) * F2(1, 1) + F1(0, 1) * F2(1, 2)) * F1(2, 0) -
+          (F1(1, 2) * F1(2, 1) - F1(1, 1) * F1(2, 2)) * F2(0, 0) + (F1(0, 2) * F1(2, 1) - F1(0, 1) * F1(2, 2)) * F2(1, 0) -
+          (F1(0, 2) * F1(1, 1) - F1(0, 1) * F1(1, 2)) * F2(2, 0);
+  dc[3] = -(F1(1, 2) * F1(2, 1) - F1(1, 1) * F1(2, 2)) * F1(0, 0) + (F1(0, 2) * F1(2, 1) - F1(0, 1) * F1(2, 2)) * F1(1, 0) -
+          (F1(0, 2) * F1(1, 1) - F1(0, 1) * F1(1, 2)) * F1(2, 0);
+  double re[4], im[4];
+  const int nroots = poly_roots(dc, 4, re, im);
+  double T2t[9];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) T2t[r * 3 + c] = T2[c * 3 + r];
+  for (int s = 0; s < nroots; ++s) {
+    double M[9], tmp[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) M[r * 3 + c] = re[s] * F1(r, c) + F2(r, c);
+    mul33(T2t, M, tmp);
+    mul33(tmp, T1, F_out + 9 * s);
+  }
+#undef F1
+#undef F2
+  return nroots;
+}
+
+// ---- estimator policies (solvers/estimator.h): sample size, datum width, model estimation, per-datum error ----
+struct RelPoseEst {  // RelativePoseEstimator (sfm/estimators/estimate_relative_pose.cc:65-155)
+  static constexpr int S = 5, D = 4, MAXM = 10;
+  __device__ static int solve(const double* sample, Model* out) {
+    double x1[10], x2[10], Es[90];
+    for (int i = 0; i < 5; ++i) { x1[2 * i] = sample[4 * i]; x1[2 * i + 1] = sample[4 * i + 1]; x2[2 * i] = sample[4 * i + 2]; x2[2 * i + 1] = sample[4 * i + 3]; }
+    const int ne = five_point(x1, x2, Es);
+    int n = 0;
+    for (int e = 0; e < ne; ++e) {
+      Model m;
+      for (int k = 0; k < 9; ++k) m.E[k] = Es[9 * e + k];
+      if (best_pose(m.E, sample, 5, m.R, m.p) < 4) continue;
+      out[n++] = m;
+    }
+    return n;
+  }
+  __device__ __forceinline__ static double error(const double* E, const double* R, const double* p, const double* c) {
+    return in_front(c[0], c[1], c[2], c[3], R, p) ? sampson(E, c[0], c[1], c[2], c[3]) : DBL_MAX;
+  }
+};
+struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator, PnPType::KNEIP (sfm/estimators/estimate_calibrated_absolute_pose.cc:63-172)
+  static constexpr int S = 3, D = 5, MAXM = 4;  // datum: feature (x, y), world point (X, Y, Z)
+  __device__ static int solve(const double* sample, Model* out) {
+    double feat[6], world[9], Rs[36], ts[12];
+    for (int i = 0; i < 3; ++i) { feat[2 * i] = sample[5 * i]; feat[2 * i + 1] = sample[5 * i + 1]; for (int k = 0; k < 3; ++k) world[3 * i + k] = sample[5 * i + 2 + k]; }
+    const int n = p3p(feat, world, Rs, ts);
+    for (int s = 0; s < n; ++s) {
+      Model& m = out[s];
+      for (int k = 0; k < 9; ++k) { m.E[k] = 0.0; m.R[k] = Rs[9 * s + k]; }
+      for (int c = 0; c < 3; ++c) m.p[c] = -(m.R[0 * 3 + c] * ts[3 * s] + m.R[1 * 3 + c] * ts[3 * s + 1] + m.R[2 * 3 + c] * ts[3 * s + 2]);
+    }
+    return n;
+  }
+  __device__ __forceinline__ static double error(const double*, const double* R, const double* p, const double* d) {
+    const double v0 = d[2] - p[0], v1 = d[3] - p[1], v2 = d[4] - p[2];
+    const double px = fma(R[0], v0, fma(R[1], v1, R[2] * v2));
+    const double py = fma(R[3], v0, fma(R[4], v1, R[5] * v2));
+    const double pz = fma(R[6], v0, fma(R[7], v1, R[8] * v2));
+    const double ex = px / pz - d[0], ey = py / pz - d[1];
+    return fma(ex, ex, ey * ey);
+  }
+};
+struct HomographyEst {  // HomographyEstimator (sfm/estimators/estimate_homography.cc:62-116); H lives in Model::E
+  static constexpr int S = 4, D = 4, MAXM = 1;
+  __device__ static int solve(const double* sample, Model* out) {
+    for (int k = 0; k < 9; ++k) out->R[k] = 0.0;
+    for (int k = 0; k < 3; ++k) out->p[k] = 0.0;
+    return four_point_h(sample, out->E) ? 1 : 0;
+  }
+  __device__ __forceinline__ static double error(const double* H, const double*, const double*, const double* c) {
+    const double px = fma(H[0], c[0], fma(H[1], c[1], H[2]));
+    const double py = fma(H[3], c[0], fma(H[4], c[1], H[5]));
+    const double pz = fma(H[6], c[0], fma(H[7], c[1], H[8]));
+    const double ex = c[2] - px / pz, ey = c[3] - py / pz;
+    return fma(ex, ex, ey * ey);
+  }
+};
+
 // ---- std::mt19937 + libstdc++ std::uniform_int_distribution<int> (util/random.cc:46-84) -----------------
 struct Mt19937 {
   uint32_t mt[624];
@@ -247,9 +562,10 @@ __device__ int compute_max_iterations(const ThbRansacParams& P, double min_sampl
   return (int)fmax((double)P.min_iterations, fmin(num_iterations, (double)P.max_iterations));
 }
 
-// Warp-wide score of one model over all correspondences. Returns (cost, #inliers) in every lane; cost = +inf if
-// the model was abandoned because its partial cost reached `bail`. If mask != nullptr the inlier flags are written.
-__device__ void score_model(const ThbRansacParams& P, const double4* __restrict__ corr, int n, const Model& m, double bail,
+// Warp-wide score of one model over all data. Returns (cost, #inliers) in every lane; cost = +inf if the model was
+// abandoned because its partial cost reached `bail`. If mask != nullptr the inlier flags are written.
+template <class Est>
+__device__ void score_model(const ThbRansacParams& P, const double* __restrict__ data, int n, const Model& m, double bail,
                             uint8_t* __restrict__ mask, double* cost_out, int* ninl_out) {
   const int lane = threadIdx.x & 31;
   double cost = 0.0;
@@ -264,8 +580,10 @@ __device__ void score_model(const ThbRansacParams& P, const double4* __restrict_
   for (int s = 0; s < steps; ++s) {
     const int i = s * 32 + lane;
     if (i < n) {
-      const double4 c = corr[i];
-      const double r = in_front(c.x, c.y, c.z, c.w, R, p) ? sampson(E, c.x, c.y, c.z, c.w) : DBL_MAX;
+      double d[Est::D];
+#pragma unroll
+      for (int k = 0; k < Est::D; ++k) d[k] = data[(size_t)i * Est::D + k];
+      const double r = Est::error(E, R, p, d);
       const bool inl = r < thresh;
       if (P.use_mle) cost += inl ? r : thresh; else cost += inl ? 0.0 : 1.0;
       ninl += inl ? 1 : 0;
@@ -290,19 +608,21 @@ struct RansacShared {
   int ninl[BI * MAXM];
   int nmodels[BI];
   int model_start[BI + 1];
-  int samples[BI][5];
+  int samples[BI][5];  // up to 5 indices per sample
   Mt19937 rng;
   double best_cost;
   int max_iterations, it0, finished, num_iterations, have_best;
 };
 
-__global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
-                                                       const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
-                                                       ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
-                                                       int* __restrict__ idx_ws, int smem_corr_cap) {
+template <class Est>
+__global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
+                                               const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
+                                               ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
+                                               int* __restrict__ idx_ws, int smem_corr_cap) {
+  constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
-  double4* s_corr = reinterpret_cast<double4*>(smem_raw + ((sizeof(RansacShared) + 31) / 32) * 32);
+  double* s_corr = reinterpret_cast<double*>(smem_raw + ((sizeof(RansacShared) + 31) / 32) * 32);
   const int pair = blockIdx.x;
   if (pair >= num_pairs) return;
   const long long off = pair_offset[pair];
@@ -310,16 +630,16 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   ThbRelPoseResult* out = results + pair;
   uint8_t* mask = mask_all ? mask_all + off : nullptr;
-  if (n < 5) {  // RandomSampler::Initialize would CHECK-abort; reported as failure
+  if (n < SS) {  // RandomSampler::Initialize would CHECK-abort; reported as failure
     if (t == 0) { memset(out, 0, sizeof(*out)); out->num_input_data_points = n; }
     if (mask) for (int i = t; i < n; i += RT) mask[i] = 0;
     return;
   }
-  const double4* g_corr = reinterpret_cast<const double4*>(corr_all) + off;
+  const double* g_corr = corr_all + (size_t)off * DD;
   const bool in_smem = n <= smem_corr_cap;
-  const double4* corr = g_corr;
+  const double* corr = g_corr;
   if (in_smem) {
-    for (int i = t; i < n; i += RT) s_corr[i] = g_corr[i];
+    for (int i = t; i < n * DD; i += RT) s_corr[i] = g_corr[i];
     corr = s_corr;
   }
   int* sidx = idx_ws + off;  // RandomSampler::sample_indices_ (persistent permutation)
@@ -330,7 +650,7 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
     S.best_cost = DBL_MAX;
     S.max_iterations = P.max_iterations;
     if (P.min_inlier_ratio > 0) {
-      const int mi = compute_max_iterations(P, 5, P.min_inlier_ratio, log_failure_prob, n);
+      const int mi = compute_max_iterations(P, SS, P.min_inlier_ratio, log_failure_prob, n);
       S.max_iterations = mi < P.max_iterations ? mi : P.max_iterations;
     }
     S.it0 = 0; S.finished = 0; S.num_iterations = 0; S.have_best = 0;
@@ -346,7 +666,7 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
     // ---- draw
     if (t == 0) {
       for (int b = 0; b < nit; ++b)
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < SS; ++i) {
           const int j = mt_uniform_int(&S.rng, i, n - 1);
           const int a = sidx[i], c = sidx[j];
           sidx[i] = c; sidx[j] = a;
@@ -358,20 +678,12 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
     if (w == 0) {
       int nm = 0;
       if (lane < nit) {
-        double x1[10], x2[10], sc[20], Es[90];
-        for (int i = 0; i < 5; ++i) {
-          const double4 c = corr[S.samples[lane][i]];
-          x1[2 * i] = c.x; x1[2 * i + 1] = c.y; x2[2 * i] = c.z; x2[2 * i + 1] = c.w;
-          sc[4 * i] = c.x; sc[4 * i + 1] = c.y; sc[4 * i + 2] = c.z; sc[4 * i + 3] = c.w;
-        }
-        const int ne = five_point(x1, x2, Es);
-        for (int e = 0; e < ne; ++e) {
-          Model m;
-          for (int k = 0; k < 9; ++k) m.E[k] = Es[9 * e + k];
-          if (best_pose(m.E, sc, 5, m.R, m.p) < 4) continue;
-          S.models[lane * MAXM + nm] = m;
-          ++nm;
-        }
+        double sample[SS * DD];
+        for (int i = 0; i < SS; ++i)
+          for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[lane][i] * DD + k];
+        Model found[Est::MAXM];
+        nm = Est::solve(sample, found);
+        for (int e = 0; e < nm; ++e) S.models[lane * MAXM + e] = found[e];
       }
       if (lane < BI) S.nmodels[lane] = nm;
       __syncwarp();
@@ -390,7 +702,7 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
       while (S.model_start[b + 1] <= j) ++b;
       const int k = j - S.model_start[b];
       double cost; int ninl;
-      score_model(P, corr, n, S.models[b * MAXM + k], bail, nullptr, &cost, &ninl);
+      score_model<Est>(P, corr, n, S.models[b * MAXM + k], bail, nullptr, &cost, &ninl);
       if (lane == 0) { S.cost[b * MAXM + k] = cost; S.ninl[b * MAXM + k] = ninl; }
     }
     __syncthreads();
@@ -406,8 +718,8 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
             S.best = S.models[b * MAXM + k];
             S.best_cost = sample_cost;
             S.have_best = 1;
-            if (inlier_ratio < 5.0 / (double)n) continue;
-            const int mi = compute_max_iterations(P, 5, inlier_ratio, log_failure_prob, n);
+            if (inlier_ratio < (double)SS / (double)n) continue;
+            const int mi = compute_max_iterations(P, SS, inlier_ratio, log_failure_prob, n);
             if (mi < S.max_iterations) S.max_iterations = mi;
           }
         }
@@ -419,14 +731,14 @@ __global__ void __launch_bounds__(RT) k_ransac_relpose(ThbRansacParams P, int nu
   // ---- final inliers of the best model (sample_consensus_estimator.h:396-414)
   if (w == 0) {
     double cost; int ninl;
-    score_model(P, corr, n, S.best, DBL_MAX, mask, &cost, &ninl);
+    score_model<Est>(P, corr, n, S.best, DBL_MAX, mask, &cost, &ninl);
     if (lane == 0) {
       out->success = 1;
       out->num_inliers = ninl;
       out->num_iterations = S.num_iterations;
       out->num_input_data_points = n;
       const double ratio = (double)ninl / (double)n;
-      out->confidence = 1.0 - pow(1.0 - pow(ratio, 5.0), (double)S.num_iterations);
+      out->confidence = 1.0 - pow(1.0 - pow(ratio, (double)SS), (double)S.num_iterations);
       out->best_cost = S.best_cost;
       for (int k = 0; k < 9; ++k) { out->essential_matrix[k] = S.best.E[k]; out->rotation[k] = S.best.R[k]; }
       for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
@@ -468,6 +780,110 @@ int check_device() {
   return THB_OK;
 }
 
+template <class Est>
+int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream) {
+  if (!b || !p || !results) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
+  // the reference CHECK-aborts on these (sample_consensus_estimator.h:217-223)
+  if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
+      p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) THB_FAIL(THB_E_INVALID_ARGUMENT, "invalid RansacParameters");
+  if (p->use_lo) THB_FAIL(THB_E_UNSUPPORTED, "use_lo (LO-RANSAC refinement by bundle adjustment) is not implemented");
+  if (p->ransac_type != 0) THB_FAIL(THB_E_UNSUPPORTED, "only RansacType::RANSAC is implemented");
+  if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
+  if (b->num_pairs == 0) return THB_OK;
+  if (!b->pair_offset || !b->seed) THB_FAIL(THB_E_INVALID_ARGUMENT, "null batch array");
+  int rc = check_device();
+  if (rc != THB_OK) return rc;
+  constexpr int DD = Est::D;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int np = b->num_pairs;
+  const bool host = b->memory_space == THB_MEM_HOST;
+  std::vector<long long> h_off(np + 1);
+  if (host) std::memcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1));
+  else THB_CUDA_CHECK(cudaMemcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyDeviceToHost));
+  int max_n = 0;
+  for (int i = 0; i < np; ++i) {
+    const long long n = h_off[i + 1] - h_off[i];
+    if (n < 0 || n > 2147483647LL || h_off[0] != 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "pair_offset must start at 0 and be non-decreasing");
+    if ((int)n > max_n) max_n = (int)n;
+  }
+  const long long total = h_off[np];
+  if (total > 0 && !b->corr) THB_FAIL(THB_E_INVALID_ARGUMENT, "null corr");
+  Bufs B;
+  const long long* d_off; const double* d_corr; const uint32_t* d_seed; ThbRelPoseResult* d_res; uint8_t* d_mask = nullptr;
+  if (host) {
+    long long* o = B.get<long long>(np + 1); double* c = B.get<double>((size_t)total * DD); uint32_t* s = B.get<uint32_t>(np);
+    d_res = B.get<ThbRelPoseResult>(np);
+    if (inlier_mask) d_mask = B.get<uint8_t>((size_t)total);
+    if (!o || !c || !s || !d_res || (inlier_mask && !d_mask)) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+    THB_CUDA_CHECK(cudaMemcpyAsync(o, b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(c, b->corr, sizeof(double) * DD * total, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(s, b->seed, sizeof(uint32_t) * np, cudaMemcpyHostToDevice, st));
+    d_off = o; d_corr = c; d_seed = s;
+  } else {
+    d_off = (const long long*)b->pair_offset; d_corr = b->corr; d_seed = b->seed; d_res = results; d_mask = inlier_mask;
+  }
+  int* d_idx = B.get<int>((size_t)total);
+  if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  // shared memory: control block + as many data as fit
+  const size_t ctrl = ((sizeof(RansacShared) + 31) / 32) * 32;
+  const size_t per = sizeof(double) * DD;
+  size_t want = ctrl + (size_t)max_n * per;
+  const size_t limit = 227 * 1024;
+  int cap = max_n;
+  if (want > limit) { cap = (int)((limit - ctrl) / per); want = ctrl + (size_t)cap * per; }
+  THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac<Est>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+  k_ransac<Est><<<np, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap);
+  THB_CUDA_CHECK(cudaGetLastError());
+  if (host) {
+    THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
+    if (inlier_mask) THB_CUDA_CHECK(cudaMemcpyAsync(inlier_mask, d_mask, (size_t)total, cudaMemcpyDeviceToHost, st));
+  }
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return THB_OK;
+}
+
+// one thread per independent minimal problem: which = 0 P3P, 1 four-point homography, 2 seven-point F
+template <int IN_A, int IN_B, int OUT_A, int OUT_B>
+__global__ void k_minimal_solver(const double* __restrict__ a, const double* __restrict__ b, int count, double* __restrict__ oa,
+                                 double* __restrict__ ob, int* __restrict__ nsol, int which) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double ia[IN_A], ib[IN_B > 0 ? IN_B : 1], ra[OUT_A], rb[OUT_B > 0 ? OUT_B : 1];
+  for (int k = 0; k < IN_A; ++k) ia[k] = a[(size_t)i * IN_A + k];
+  for (int k = 0; k < IN_B; ++k) ib[k] = b[(size_t)i * IN_B + k];
+  for (int k = 0; k < OUT_A; ++k) ra[k] = 0.0;
+  for (int k = 0; k < OUT_B; ++k) rb[k] = 0.0;
+  int n = 0;
+  if (which == 0) n = p3p(ia, ib, ra, rb);
+  else if (which == 1) n = four_point_h(ia, ra) ? 1 : 0;
+  else n = seven_point_f(ia, ra);
+  nsol[i] = n;
+  for (int k = 0; k < OUT_A; ++k) oa[(size_t)i * OUT_A + k] = ra[k];
+  for (int k = 0; k < OUT_B; ++k) ob[(size_t)i * OUT_B + k] = rb[k];
+}
+
+template <int IN_A, int IN_B, int OUT_A, int OUT_B>
+int run_solver(const double* a, const double* b, int count, double* oa, double* ob, int* nsol, void* cuda_stream, int which) {
+  if (count == 0) return THB_OK;
+  int rc = check_device();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  Bufs B;
+  double* da = B.get<double>((size_t)count * IN_A); double* db = B.get<double>((size_t)count * (IN_B > 0 ? IN_B : 1));
+  double* doa = B.get<double>((size_t)count * OUT_A); double* dob = B.get<double>((size_t)count * (OUT_B > 0 ? OUT_B : 1));
+  int* dn = B.get<int>(count);
+  if (!da || !db || !doa || !dob || !dn) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemcpyAsync(da, a, sizeof(double) * IN_A * count, cudaMemcpyHostToDevice, st));
+  if (IN_B > 0) THB_CUDA_CHECK(cudaMemcpyAsync(db, b, sizeof(double) * IN_B * count, cudaMemcpyHostToDevice, st));
+  k_minimal_solver<IN_A, IN_B, OUT_A, OUT_B><<<(count + 31) / 32, 32, 0, st>>>(da, db, count, doa, dob, dn, which);
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(oa, doa, sizeof(double) * OUT_A * count, cudaMemcpyDeviceToHost, st));
+  if (OUT_B > 0) THB_CUDA_CHECK(cudaMemcpyAsync(ob, dob, sizeof(double) * OUT_B * count, cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(nsol, dn, sizeof(int) * count, cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return THB_OK;
+}
+
 }  // namespace
 }  // namespace thb
 
@@ -486,62 +902,29 @@ void thb_ransac_default_params(ThbRansacParams* p) {
 
 int thb_ransac_relpose_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask,
                              void* cuda_stream) {
-  if (!b || !p || !results) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
-  // the reference CHECK-aborts on these (sample_consensus_estimator.h:217-223)
-  if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
-      p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) THB_FAIL(THB_E_INVALID_ARGUMENT, "invalid RansacParameters");
-  if (p->use_lo) THB_FAIL(THB_E_UNSUPPORTED, "use_lo (LO-RANSAC refinement by two-view BA) is not implemented");
-  if (p->ransac_type != 0) THB_FAIL(THB_E_UNSUPPORTED, "only RansacType::RANSAC is implemented");
-  if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
-  if (b->num_pairs == 0) return THB_OK;
-  if (!b->pair_offset || !b->seed) THB_FAIL(THB_E_INVALID_ARGUMENT, "null batch array");
-  int rc = check_device();
-  if (rc != THB_OK) return rc;
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int np = b->num_pairs;
-  const bool host = b->memory_space == THB_MEM_HOST;
-  std::vector<long long> h_off(np + 1);
-  if (host) std::memcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1));
-  else THB_CUDA_CHECK(cudaMemcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyDeviceToHost));
-  int max_n = 0;
-  for (int i = 0; i < np; ++i) {
-    const long long n = h_off[i + 1] - h_off[i];
-    if (n < 0 || n > 2147483647LL || h_off[0] != 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "pair_offset must start at 0 and be non-decreasing");
-    if ((int)n > max_n) max_n = (int)n;
-  }
-  const long long total = h_off[np];
-  if (total > 0 && !b->corr) THB_FAIL(THB_E_INVALID_ARGUMENT, "null corr");
-  Bufs B;
-  const long long* d_off; const double* d_corr; const uint32_t* d_seed; ThbRelPoseResult* d_res; uint8_t* d_mask = nullptr;
-  if (host) {
-    long long* o = B.get<long long>(np + 1); double* c = B.get<double>((size_t)total * 4); uint32_t* s = B.get<uint32_t>(np);
-    d_res = B.get<ThbRelPoseResult>(np);
-    if (inlier_mask) d_mask = B.get<uint8_t>((size_t)total);
-    if (!o || !c || !s || !d_res || (inlier_mask && !d_mask)) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-    THB_CUDA_CHECK(cudaMemcpyAsync(o, b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
-    THB_CUDA_CHECK(cudaMemcpyAsync(c, b->corr, sizeof(double) * 4 * total, cudaMemcpyHostToDevice, st));
-    THB_CUDA_CHECK(cudaMemcpyAsync(s, b->seed, sizeof(uint32_t) * np, cudaMemcpyHostToDevice, st));
-    d_off = o; d_corr = c; d_seed = s;
-  } else {
-    d_off = (const long long*)b->pair_offset; d_corr = b->corr; d_seed = b->seed; d_res = results; d_mask = inlier_mask;
-  }
-  int* d_idx = B.get<int>((size_t)total);
-  if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-  // shared memory: control block + as many correspondences as fit (two CTAs per SM when the pair is small enough)
-  const size_t ctrl = ((sizeof(RansacShared) + 31) / 32) * 32;
-  size_t want = ctrl + (size_t)max_n * sizeof(double4);
-  const size_t limit = 227 * 1024;
-  int cap = max_n;
-  if (want > limit) { cap = (int)((limit - ctrl) / sizeof(double4)); want = ctrl + (size_t)cap * sizeof(double4); }
-  THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac_relpose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-  k_ransac_relpose<<<np, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap);
-  THB_CUDA_CHECK(cudaGetLastError());
-  if (host) {
-    THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
-    if (inlier_mask) THB_CUDA_CHECK(cudaMemcpyAsync(inlier_mask, d_mask, (size_t)total, cudaMemcpyDeviceToHost, st));
-  }
-  THB_CUDA_CHECK(cudaStreamSynchronize(st));
-  return THB_OK;
+  return run_batch<RelPoseEst>(b, p, results, inlier_mask, cuda_stream);
+}
+int thb_ransac_abspose_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask,
+                             void* cuda_stream) {
+  return run_batch<AbsPoseEst>(b, p, results, inlier_mask, cuda_stream);
+}
+int thb_ransac_homography_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask,
+                                void* cuda_stream) {
+  return run_batch<HomographyEst>(b, p, results, inlier_mask, cuda_stream);
+}
+
+int thb_p3p(const double* features, const double* world_points, int32_t count, double* R_out, double* t_out, int32_t* num_solutions,
+            void* cuda_stream) {
+  if (!features || !world_points || !R_out || !t_out || !num_solutions || count < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  return run_solver<6, 9, 36, 12>(features, world_points, count, R_out, t_out, num_solutions, cuda_stream, 0);
+}
+int thb_four_point_homography(const double* corr, int32_t count, double* H_out, int32_t* ok, void* cuda_stream) {
+  if (!corr || !H_out || !ok || count < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  return run_solver<16, 0, 9, 0>(corr, nullptr, count, H_out, nullptr, ok, cuda_stream, 1);
+}
+int thb_seven_point_fundamental_matrix(const double* corr, int32_t count, double* F_out, int32_t* num_solutions, void* cuda_stream) {
+  if (!corr || !F_out || !num_solutions || count < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  return run_solver<28, 0, 27, 0>(corr, nullptr, count, F_out, nullptr, num_solutions, cuda_stream, 2);
 }
 
 int thb_five_point_relative_pose(const double* x1, const double* x2, int32_t count, double* E_out, int32_t* num_solutions,

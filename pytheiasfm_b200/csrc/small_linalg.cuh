@@ -66,9 +66,10 @@ struct FullPivLU {
   }
 };
 
-// kernel of a full-row-rank 5x9 matrix: ker[9][4] (row-major). lu5 holds the computed decomposition.
-__device__ inline void kernel_5x9(const FullPivLU<5, 9>& d, double* ker) {
-  constexpr int C = 9, rk = 5, dimker = 4;
+// kernel of a full-row-rank R x 9 matrix: ker[9][9-R] (row-major). d holds the computed decomposition.
+template <int R>
+__device__ inline void kernel_rx9(const FullPivLU<R, 9>& d, double* ker) {
+  constexpr int C = 9, rk = R, dimker = 9 - R;
   double m[rk * C];
   for (int i = 0; i < rk; ++i) {
     for (int c = 0; c < i; ++c) m[i * C + c] = 0.0;
@@ -123,38 +124,42 @@ __device__ __forceinline__ void make_jacobi(double x, double y, double z, Rot* j
   j->s = -sign_t * (y / fabs(y)) * fabs(t) * n;
   j->c = n;
 }
-__device__ __forceinline__ void rot_left3(double* M, int p, int q, Rot j) {
-  for (int i = 0; i < 3; ++i) {
-    const double x = M[p * 3 + i], y = M[q * 3 + i];
-    M[p * 3 + i] = j.c * x + j.s * y;
-    M[q * 3 + i] = -j.s * x + j.c * y;
+template <int N>
+__device__ __forceinline__ void rot_left(double* M, int p, int q, Rot j) {
+  for (int i = 0; i < N; ++i) {
+    const double x = M[p * N + i], y = M[q * N + i];
+    M[p * N + i] = j.c * x + j.s * y;
+    M[q * N + i] = -j.s * x + j.c * y;
   }
 }
-__device__ __forceinline__ void rot_right3(double* M, int p, int q, Rot j) {
-  for (int i = 0; i < 3; ++i) {
-    const double x = M[i * 3 + p], y = M[i * 3 + q];
-    M[i * 3 + p] = j.c * x - j.s * y;
-    M[i * 3 + q] = j.s * x + j.c * y;
+template <int N>
+__device__ __forceinline__ void rot_right(double* M, int p, int q, Rot j) {
+  for (int i = 0; i < N; ++i) {
+    const double x = M[i * N + p], y = M[i * N + q];
+    M[i * N + p] = j.c * x - j.s * y;
+    M[i * N + q] = j.s * x + j.c * y;
   }
 }
-__device__ inline void jacobi_svd3(const double* A, double* U, double* S, double* V) {
+// Square two-sided Jacobi SVD, row-major N x N; W is caller-provided N*N scratch (may alias nothing else).
+template <int N>
+__device__ inline void jacobi_svd(const double* A, double* W, double* U, double* S, double* V) {
   const double precision = 2.0 * kEps;
   double scale = 0.0;
-  for (int i = 0; i < 9; ++i) scale = fmax(scale, fabs(A[i]));
+  for (int i = 0; i < N * N; ++i) scale = fmax(scale, fabs(A[i]));
   if (scale == 0.0) scale = 1.0;
-  double W[9];
-  for (int i = 0; i < 9; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i % 4 == 0) ? 1.0 : 0.0; }
-  double maxDiag = fmax(fabs(W[0]), fmax(fabs(W[4]), fabs(W[8])));
+  for (int i = 0; i < N * N; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i / N == i % N) ? 1.0 : 0.0; }
+  double maxDiag = 0.0;
+  for (int i = 0; i < N; ++i) maxDiag = fmax(maxDiag, fabs(W[i * N + i]));
   bool finished = false;
   int sweeps = 0;
-  while (!finished && sweeps++ < 100) {
+  while (!finished && sweeps++ < 1000) {
     finished = true;
-    for (int p = 1; p < 3; ++p)
+    for (int p = 1; p < N; ++p)
       for (int q = 0; q < p; ++q) {
         const double threshold = fmax(kMin, precision * maxDiag);
-        if (fabs(W[p * 3 + q]) > threshold || fabs(W[q * 3 + p]) > threshold) {
+        if (fabs(W[p * N + q]) > threshold || fabs(W[q * N + p]) > threshold) {
           finished = false;
-          const double m00 = W[p * 3 + p], m01 = W[p * 3 + q], m10 = W[q * 3 + p], m11 = W[q * 3 + q];
+          const double m00 = W[p * N + p], m01 = W[p * N + q], m10 = W[q * N + p], m11 = W[q * N + q];
           Rot rot1;
           const double t = m00 + m11, d = m10 - m01;
           if (fabs(d) < kMin) { rot1.s = 0.0; rot1.c = 1.0; }
@@ -165,30 +170,34 @@ __device__ inline void jacobi_svd3(const double* A, double* U, double* S, double
           make_jacobi(n00, n01, n11, &jr);
           const Rot jrt{jr.c, -jr.s};
           const Rot jl{rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
-          rot_left3(W, p, q, jl);
-          rot_right3(U, p, q, Rot{jl.c, -jl.s});
-          rot_right3(W, p, q, jr);
-          rot_right3(V, p, q, jr);
-          maxDiag = fmax(maxDiag, fmax(fabs(W[p * 3 + p]), fabs(W[q * 3 + q])));
+          rot_left<N>(W, p, q, jl);
+          rot_right<N>(U, p, q, Rot{jl.c, -jl.s});
+          rot_right<N>(W, p, q, jr);
+          rot_right<N>(V, p, q, jr);
+          maxDiag = fmax(maxDiag, fmax(fabs(W[p * N + p]), fabs(W[q * N + q])));
         }
       }
   }
-  for (int i = 0; i < 3; ++i) {
-    const double a = W[i * 3 + i];
+  for (int i = 0; i < N; ++i) {
+    const double a = W[i * N + i];
     S[i] = fabs(a);
-    if (a < 0.0) for (int r = 0; r < 3; ++r) U[r * 3 + i] = -U[r * 3 + i];
+    if (a < 0.0) for (int r = 0; r < N; ++r) U[r * N + i] = -U[r * N + i];
   }
-  for (int i = 0; i < 3; ++i) S[i] *= scale;
-  for (int i = 0; i < 3; ++i) {
+  for (int i = 0; i < N; ++i) S[i] *= scale;
+  for (int i = 0; i < N; ++i) {
     int pos = i;
     double best = S[i];
-    for (int k = i + 1; k < 3; ++k) if (S[k] > best) { best = S[k]; pos = k; }
+    for (int k = i + 1; k < N; ++k) if (S[k] > best) { best = S[k]; pos = k; }
     if (best == 0.0) break;
     if (pos != i) {
       dswap(S[i], S[pos]);
-      for (int r = 0; r < 3; ++r) { dswap(U[r * 3 + i], U[r * 3 + pos]); dswap(V[r * 3 + i], V[r * 3 + pos]); }
+      for (int r = 0; r < N; ++r) { dswap(U[r * N + i], U[r * N + pos]); dswap(V[r * N + i], V[r * N + pos]); }
     }
   }
+}
+__device__ inline void jacobi_svd3(const double* A, double* U, double* S, double* V) {
+  double W[9];
+  jacobi_svd<3>(A, W, U, S, V);
 }
 
 // ---- real nonsymmetric eigen-decomposition, N x N row-major ---------------------------------------
@@ -251,12 +260,12 @@ struct EigenReal {
   }
 
   // A is read from T (caller fills T with the matrix).
-  __device__ void compute(double (*vec_tail4)[4]) {
+  __device__ void compute(double (*vec_tail4)[4], bool want_vectors = true) {
     ok = true;
     double scale = 0.0;
     for (int i = 0; i < N * N; ++i) scale = fmax(scale, fabs(T[i]));
     for (int i = 0; i < N * N; ++i) Uq[i] = (i / N == i % N) ? 1.0 : 0.0;
-    for (int j = 0; j < N; ++j) for (int k = 0; k < 4; ++k) vec_tail4[j][k] = 0.0;
+    if (want_vectors) for (int j = 0; j < N; ++j) for (int k = 0; k < 4; ++k) vec_tail4[j][k] = 0.0;
     if (scale < kMin) {
       for (int i = 0; i < N; ++i) { eig_re[i] = 0.0; eig_im[i] = 0.0; }
       return;
@@ -341,7 +350,7 @@ struct EigenReal {
         i += 2;
       }
     }
-    real_eigenvectors(vec_tail4);
+    if (want_vectors) real_eigenvectors(vec_tail4);
   }
 
   __device__ void split_off_two_rows(int iu, double exshift) {
@@ -463,7 +472,7 @@ struct EigenReal {
         col[r] = s; nrm += s * s;
       }
       nrm = sqrt(nrm);
-      for (int k = 0; k < 4; ++k) vec_tail4[n][k] = col[N - 4 + k] / nrm;
+      for (int k = 0; k < 4; ++k) vec_tail4[n][k] = col[(N >= 4 ? N - 4 : 0) + (N >= 4 ? k : 0)] / nrm;
     }
   }
 };

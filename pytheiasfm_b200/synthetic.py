@@ -258,3 +258,37 @@ def c4_params(lib_or_oracle_params):
     p.error_thresh = (2e-3) ** 2; p.failure_probability = 1e-4; p.min_iterations = 10; p.max_iterations = 1000
     p.use_mle = 1; p.use_lo = 0; p.min_inlier_ratio = 0.0; p.ransac_type = 0
     return p
+
+
+def make_abspose_batch(num, n=500, inlier_ratio=0.7, noise=1e-3, seed=0, base_seed=2000):
+    """2D-3D batches for EstimateCalibratedAbsolutePose: datum = (x, y, X, Y, Z) in normalised image coordinates."""
+    rng = np.random.default_rng(seed)
+    data, gts = [], []
+    for _ in range(num):
+        R = random_rotation(rng, 40.0)
+        c = rng.normal(size=3)
+        ni = int(round(inlier_ratio * n))
+        Xc = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(3, 9, n)], -1)   # in the camera frame
+        X = Xc @ R + c                                                                            # world = R^T Xc + c
+        x = Xc[:, :2] / Xc[:, 2:3] + rng.normal(0, noise, (n, 2))
+        x[ni:] = rng.uniform(-1, 1, (n - ni, 2))
+        flags = np.arange(n) < ni
+        perm = rng.permutation(n)
+        data.append(np.concatenate([x, X], 1)[perm]); gts.append((R, c, flags[perm]))
+    return capi.HostPairBatch(data, base_seed + np.arange(num), width=5), gts
+
+
+def make_homography_batch(num, n=500, inlier_ratio=0.6, noise=1e-3, seed=0, base_seed=3000):
+    rng = np.random.default_rng(seed)
+    data, gts = [], []
+    for _ in range(num):
+        H = np.eye(3) + rng.normal(0, 0.2, (3, 3)); H /= H[2, 2]
+        ni = int(round(inlier_ratio * n))
+        x1 = rng.uniform(-1, 1, (n, 2))
+        y = np.c_[x1, np.ones(n)] @ H.T
+        x2 = y[:, :2] / y[:, 2:] + rng.normal(0, noise, (n, 2))
+        x2[ni:] = rng.uniform(-1, 1, (n - ni, 2))
+        flags = np.arange(n) < ni
+        perm = rng.permutation(n)
+        data.append(np.c_[x1, x2][perm]); gts.append((H, flags[perm]))
+    return capi.HostPairBatch(data, base_seed + np.arange(num)), gts

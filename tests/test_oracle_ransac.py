@@ -196,3 +196,110 @@ def test_default_ransac_parameters(oracle):
     p = oracle.ransac_default_params()  # sample_consensus_estimator.h:59-68
     assert p.error_thresh == -1 and p.failure_probability == 0.01 and p.min_inlier_ratio == 0
     assert p.min_iterations == 100 and p.max_iterations == 2**31 - 1 and not p.use_mle and not p.use_lo and p.lo_start_iterations == 50
+
+
+def test_polynomial_roots_match_numpy(oracle):
+    """math/find_polynomial_roots_companion_matrix.cc via the restated balance + EigenSolver; degree 1-4, leading zeros."""
+    rng = np.random.default_rng(20)
+    for _ in range(200):
+        deg = int(rng.integers(1, 5))
+        poly = rng.normal(size=deg + 1) * 10 ** rng.uniform(-2, 2, deg + 1)
+        if rng.random() < 0.2:
+            poly = np.concatenate([[0.0], poly])[: 5]
+        got = oracle.poly_roots(poly)
+        ref = np.roots(poly)
+        assert len(got) == len(ref)
+        assert np.abs(np.sort_complex(got) - np.sort_complex(ref)).max() <= 1e-8 * max(1.0, np.abs(ref).max())
+
+
+def _rot(axis, deg):
+    a = np.deg2rad(deg); axis = np.array(axis, float)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(a) * K + (1 - np.cos(a)) * K @ K
+
+
+P3P_KAT_POINTS = np.array([[-0.3001, -0.5840, 1.2271], [-1.4487, 0.6965, 0.3889], [-0.7815, 0.7642, 0.1257]])
+
+
+def p3p_kat(noise, seed=55):
+    """perspective_three_point_test.cc:56-112"""
+    Rg = _rot([1, 0, 0], 15.0) @ _rot([0, 1, 0], -10.0)
+    tg = np.array([0.3, -1.7, 1.15])
+    pc = P3P_KAT_POINTS @ Rg.T + tg
+    x = pc[:, :2] / pc[:, 2:]
+    if noise:
+        x = x + np.random.default_rng(seed).normal(0, noise, x.shape)
+    return x, Rg, tg
+
+
+def check_p3p_solutions(R, t, n, x, Rg, tg):
+    matched = False
+    for k in range(n):
+        ang = np.rad2deg(np.arccos(np.clip((np.trace(R[k] @ Rg.T) - 1) / 2, -1, 1)))
+        if ang < 1.0 and np.linalg.norm((-Rg @ tg) - (-R[k] @ t[k])) < 0.1:
+            matched = True
+            pc = P3P_KAT_POINTS @ R[k].T + t[k]
+            assert (np.linalg.norm(x - pc[:, :2] / pc[:, 2:], axis=1) * 800.0 < 2.0).all()
+    assert matched
+
+
+@pytest.mark.parametrize("noise", [0.0, 1.0 / 800.0])
+def test_p3p_reference_kat(oracle, noise):
+    x, Rg, tg = p3p_kat(noise)
+    R, t, n = oracle.p3p(x[None], P3P_KAT_POINTS[None])
+    assert n[0] == 4                     # the reference keeps the real part of all four roots
+    check_p3p_solutions(R[0], t[0], n[0], x, Rg, tg)
+    Rc, tc, nc = oracle.p3p(x[None], np.array([[[0, 0, 1.0], [1, 1, 2.0], [2, 2, 3.0]]]))
+    assert nc[0] == 0                    # collinear world points: no solution (:196-204)
+
+
+def test_four_point_homography_properties(oracle):
+    """four_point_homography_test.cc:127-205 style: exact data -> transfer error ~ 0, H up to scale."""
+    rng = np.random.default_rng(21)
+    for _ in range(50):
+        H = np.eye(3) + rng.normal(0, 0.3, (3, 3)); H /= H[2, 2]
+        x1 = rng.uniform(-1, 1, (4, 2)); y = np.c_[x1, np.ones(4)] @ H.T; x2 = y[:, :2] / y[:, 2:]
+        Ho, ok = oracle.four_point_homography(np.c_[x1, x2][None])
+        assert ok[0] == 1
+        yy = np.c_[x1, np.ones(4)] @ Ho[0].T
+        assert np.abs(yy[:, :2] / yy[:, 2:] - x2).max() < 1e-7
+        assert equal_up_to_scale(Ho[0], H, 1e-6)
+
+
+def test_seven_point_reproduces_reference_including_its_quirk(oracle):
+    """seven_point_fundamental_matrix.cc:72-152: every returned F satisfies the 7 epipolar constraints (any member of
+    the 2-dim null space does); because the cubic's coefficients are stored in reversed order the
+    rank-2 constraint det F = 0 is NOT met in general — the oracle reproduces the reference as written."""
+    rng = np.random.default_rng(22)
+    dets = []
+    for _ in range(20):
+        c, _, _, _ = synthetic.make_pair(rng, 7, 1.0, 0.0)
+        F, n = oracle.seven_point_fundamental(c[None])
+        assert 1 <= n[0] <= 3
+        for k in range(n[0]):
+            for i in range(7):
+                assert sampson(F[0, k], c[i, :2], c[i, 2:]) < 1e-12
+            dets.append(abs(np.linalg.det(F[0, k] / np.linalg.norm(F[0, k]))))
+    assert max(dets) > 1e-6
+
+
+def test_absolute_pose_and_homography_ransac(oracle):
+    batch, gts = synthetic.make_abspose_batch(5, n=300, seed=23)
+    p = synthetic.c4_params(oracle.ransac_default_params()); p.error_thresh = (3e-3) ** 2
+    rc, res, mask = oracle.ransac_batch("abspose", batch, p)
+    assert rc == 0
+    for i in range(5):
+        R, c, flags = gts[i]
+        assert res["success"][i] == 1
+        ang = np.rad2deg(np.arccos(np.clip((np.trace(res["rotation"][i] @ R.T) - 1) / 2, -1, 1)))
+        assert ang < 1.0 and np.linalg.norm(res["position"][i] - c) < 0.1
+        m = mask[batch.pair_offset[i]: batch.pair_offset[i + 1]].astype(bool)
+        assert (m & flags).sum() >= 0.85 * flags.sum() and (m & ~flags).sum() <= 0.05 * (~flags).sum()
+    batch, gts = synthetic.make_homography_batch(5, n=300, seed=24)
+    rc, res, mask = oracle.ransac_batch("homography", batch, p)
+    assert rc == 0
+    for i in range(5):
+        H, flags = gts[i]
+        assert res["success"][i] == 1 and equal_up_to_scale(res["essential_matrix"][i], H, 2e-2)
+        m = mask[batch.pair_offset[i]: batch.pair_offset[i + 1]].astype(bool)
+        assert (m & flags).sum() >= 0.75 * flags.sum() and (m & ~flags).sum() <= 0.05 * (~flags).sum()

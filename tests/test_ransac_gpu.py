@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 from pytheiasfm_b200 import capi, synthetic
-from test_oracle_ransac import FIVE_PT_CASES, five_point_case, equal_up_to_scale, sampson
+from test_oracle_ransac import (FIVE_PT_CASES, five_point_case, equal_up_to_scale, sampson, p3p_kat, check_p3p_solutions,
+                                P3P_KAT_POINTS)
 
 pytestmark = pytest.mark.gpu
 
@@ -22,11 +23,12 @@ def gpu_five_point(lib, x1, x2):
     return E, n
 
 
-def gpu_ransac(lib, batch, params, want_mask=True):
+def gpu_ransac(lib, batch, params, want_mask=True, kind="relpose"):
     res = np.zeros(batch.num_pairs, capi.RELPOSE_DTYPE)
     mask = np.zeros(int(batch.pair_offset[-1]), np.uint8) if want_mask else None
     b = batch.struct()
-    capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), _vp(res), None if mask is None else _vp(mask), None))
+    fn = getattr(lib, "thb_ransac_%s_batch" % kind)
+    capi.check(fn(C.byref(b), C.byref(params), _vp(res), None if mask is None else _vp(mask), None))
     return res, mask
 
 
@@ -153,3 +155,60 @@ def test_c4_full_size_properties(lib):
         ref = front & (r < params.error_thresh)
         m = mask[batch.pair_offset[p]: batch.pair_offset[p + 1]].astype(bool)
         assert (ref != m).sum() <= 2
+
+
+@pytest.mark.parametrize("noise", [0.0, 1.0 / 800.0])
+def test_p3p_reference_kat_on_device(lib, oracle, noise):
+    x, Rg, tg = p3p_kat(noise)
+    R = np.zeros((1, 4, 3, 3)); t = np.zeros((1, 4, 3)); n = np.zeros(1, np.int32)
+    capi.check(lib.thb_p3p(_vp(np.ascontiguousarray(x)), _vp(np.ascontiguousarray(P3P_KAT_POINTS)), 1, _vp(R), _vp(t), _vp(n), None))
+    assert n[0] == 4
+    check_p3p_solutions(R[0], t[0], n[0], x, Rg, tg)
+
+
+def test_minimal_solvers_match_oracle_bit_for_bit(lib, oracle):
+    """P3P, four-point homography and seven-point F: same solution count, order and values as the oracle."""
+    batch, _ = synthetic.make_abspose_batch(64, n=3, inlier_ratio=1.0, noise=1e-3, seed=30)
+    d = batch.corr.reshape(64, 3, 5)
+    feat = np.ascontiguousarray(d[:, :, :2]); world = np.ascontiguousarray(d[:, :, 2:])
+    R = np.zeros((64, 4, 3, 3)); t = np.zeros((64, 4, 3)); n = np.zeros(64, np.int32)
+    capi.check(lib.thb_p3p(_vp(feat), _vp(world), 64, _vp(R), _vp(t), _vp(n), None))
+    Ro, to, no = oracle.p3p(feat, world)
+    np.testing.assert_array_equal(n, no)
+    assert np.array_equal(R, Ro, equal_nan=True) and np.array_equal(t, to, equal_nan=True)
+
+    hb, _ = synthetic.make_homography_batch(64, n=4, inlier_ratio=1.0, noise=1e-3, seed=31)
+    corr = np.ascontiguousarray(hb.corr.reshape(64, 4, 4))
+    H = np.zeros((64, 3, 3)); ok = np.zeros(64, np.int32)
+    capi.check(lib.thb_four_point_homography(_vp(corr), 64, _vp(H), _vp(ok), None))
+    Ho, oko = oracle.four_point_homography(corr)
+    np.testing.assert_array_equal(ok, oko)
+    assert np.array_equal(H, Ho)
+
+    rng = np.random.default_rng(32)
+    c7 = np.ascontiguousarray(np.stack([synthetic.make_pair(rng, 7, 1.0, 1e-3)[0] for _ in range(64)]))
+    F = np.zeros((64, 3, 3, 3)); n7 = np.zeros(64, np.int32)
+    capi.check(lib.thb_seven_point_fundamental_matrix(_vp(c7), 64, _vp(F), _vp(n7), None))
+    Fo, n7o = oracle.seven_point_fundamental(c7)
+    np.testing.assert_array_equal(n7, n7o)
+    assert np.array_equal(F, Fo)
+
+
+@pytest.mark.parametrize("kind", ["abspose", "homography"])
+def test_abspose_and_homography_ransac_identical_inlier_sets(lib, oracle, kind):
+    if kind == "abspose":
+        batch, _ = synthetic.make_abspose_batch(24, n=400, seed=33)
+    else:
+        batch, _ = synthetic.make_homography_batch(24, n=400, seed=34)
+    def mk(p):
+        p = synthetic.c4_params(p); p.error_thresh = (3e-3) ** 2
+        return p
+    res, mask = gpu_ransac(lib, batch, mk(capi.ThbRansacParams()), kind=kind)
+    rc, ores, omask = oracle.ransac_batch(kind, batch, mk(oracle.ransac_default_params()))
+    assert rc == 0
+    for f in ("success", "num_iterations", "num_inliers", "num_input_data_points"):
+        np.testing.assert_array_equal(res[f], ores[f], err_msg=f)
+    np.testing.assert_array_equal(mask, omask)
+    for f in ("essential_matrix", "rotation", "position"):
+        assert np.array_equal(res[f], ores[f], equal_nan=True), f
+    assert (res["num_inliers"] > 100).all()
