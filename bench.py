@@ -186,10 +186,11 @@ def run_ransac(args, rank, local_rank, world):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_library()
-    # static block partition of the pair table (every pair has the same size here, so blocks are balanced)
-    lo, hi = total_pairs * rank // world, total_pairs * (rank + 1) // world
+    # static block partition of the pair table by cumulative correspondence count (pytheiasfm_b200/sharding.py)
+    from pytheiasfm_b200 import sharding
     full, _ = synthetic.make_pair_batch(total_pairs, n=2000, seed=21)
-    mine = capi.HostPairBatch([full.corr[full.pair_offset[i]: full.pair_offset[i + 1]] for i in range(lo, hi)], full.seed[lo:hi])
+    ranges = sharding.partition_by_work(full.pair_offset, world)
+    mine, lo, hi = sharding.shard_batch(full, rank, world)
     params = synthetic.c4_params(capi.ThbRansacParams())
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
@@ -198,14 +199,17 @@ def run_ransac(args, rank, local_rank, world):
     rec = capi.RELPOSE_DTYPE.itemsize
     d_res = torch.zeros(mine.num_pairs * rec, dtype=torch.uint8, device="cuda")
     d_mask = torch.zeros(int(mine.pair_offset[-1]), dtype=torch.uint8, device="cuda")
-    gathered = [torch.zeros(((total_pairs * (r + 1) // world) - (total_pairs * r // world)) * rec, dtype=torch.uint8, device="cuda") for r in range(world)]
+    pad = max(h - l for l, h in ranges) * rec
+    gathered = [torch.zeros(pad, dtype=torch.uint8, device="cuda") for _ in range(world)]
+    sendbuf = torch.zeros(pad, dtype=torch.uint8, device="cuda")
     b = capi.ThbPairBatch(); b.num_pairs = mine.num_pairs; b.memory_space = capi.THB_MEM_DEVICE
     b.pair_offset = d_off.data_ptr(); b.corr = d_corr.data_ptr(); b.seed = d_seed.data_ptr()
 
     def step():
         capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), C.c_void_p(d_res.data_ptr()), C.c_void_p(d_mask.data_ptr()), sptr))
-        if world > 1:
-            dist.all_gather(gathered, d_res)
+        if world > 1:  # one collective per batch: fixed-size result records, padded to the largest block
+            sendbuf[: d_res.numel()] = d_res
+            dist.all_gather(gathered, sendbuf)
 
     W, K = max(args.warmup, 3), args.steps
     for _ in range(W):

@@ -1,0 +1,64 @@
+"""Pair-queue sharding for multi-GPU RANSAC verification.
+
+Image pairs are independent units (the reference fans them out over a thread pool,
+matching/feature_matcher.cc:117-126). One process per GPU; the pair table is split into contiguous blocks balanced by
+cumulative correspondence count (the cost of a pair is proportional to its number of correspondences times its
+iteration count); every rank verifies its block with thb_ransac_*_batch; one all_gather of the fixed-size result
+records assembles the full table on every rank. No collective sits on the data path of the kernels.
+"""
+import numpy as np
+
+from . import capi
+
+
+def partition_by_work(pair_offset, world):
+    """Contiguous [lo, hi) pair ranges, one per rank, with near-equal correspondence counts. Every pair is covered
+    exactly once; ranks may be empty when there are fewer pairs than ranks."""
+    pair_offset = np.asarray(pair_offset, dtype=np.int64)
+    num_pairs = len(pair_offset) - 1
+    total = int(pair_offset[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        # first pair whose END offset reaches the target; keep the sequence non-decreasing
+        idx = int(np.searchsorted(pair_offset[1:], target, side="left")) + 1 if total > 0 else num_pairs * r // world
+        bounds.append(min(max(idx, bounds[-1]), num_pairs))
+    bounds.append(num_pairs)
+    return [(bounds[r], bounds[r + 1]) for r in range(world)]
+
+
+def shard_batch(batch, rank, world):
+    """The rank's block of a HostPairBatch (a new HostPairBatch with re-based offsets) and its [lo, hi) range."""
+    lo, hi = partition_by_work(batch.pair_offset, world)[rank]
+    o0, o1 = int(batch.pair_offset[lo]), int(batch.pair_offset[hi])
+    sub = capi.HostPairBatch.__new__(capi.HostPairBatch)
+    sub.width = batch.width
+    sub.num_pairs = hi - lo
+    sub.pair_offset = (batch.pair_offset[lo: hi + 1] - o0).astype(np.int64)
+    sub.corr = np.ascontiguousarray(batch.corr[o0:o1])
+    sub.seed = np.ascontiguousarray(batch.seed[lo:hi])
+    return sub, lo, hi
+
+
+def all_gather_results(local_records, ranges, group=None, device=None):
+    """all_gather of per-pair result records (structured array of capi.RELPOSE_DTYPE, or a uint8 torch tensor on the
+    rank's device) into the full table, ordered by global pair index. Works on NCCL (GPU) and gloo (CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    rec = capi.RELPOSE_DTYPE.itemsize
+    world = dist.get_world_size(group)
+    counts = [hi - lo for lo, hi in ranges]
+    if isinstance(local_records, np.ndarray):
+        local = torch.from_numpy(local_records.view(np.uint8).reshape(-1).copy())
+        if device is not None:
+            local = local.to(device)
+    else:
+        local = local_records.reshape(-1)
+    assert local.numel() == counts[dist.get_rank(group)] * rec
+    pad = max(counts) * rec
+    buf = torch.zeros(pad, dtype=torch.uint8, device=local.device)
+    buf[: local.numel()] = local
+    out = [torch.zeros(pad, dtype=torch.uint8, device=local.device) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    full = torch.cat([out[r][: counts[r] * rec] for r in range(world)])
+    return np.frombuffer(full.cpu().numpy().tobytes(), capi.RELPOSE_DTYPE)

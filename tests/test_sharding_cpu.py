@@ -1,0 +1,65 @@
+"""Multi-process (gloo, world_size 2 and 3, CPU) tests of the pair-queue sharding used for multi-GPU verification."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from pytheiasfm_b200 import capi, sharding, synthetic
+
+
+def test_partition_covers_every_pair_once_and_balances_work():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 4, 8):
+        for _ in range(20):
+            sizes = rng.integers(0, 3000, size=int(rng.integers(0, 40)))
+            off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+            parts = sharding.partition_by_work(off, world)
+            assert len(parts) == world and parts[0][0] == 0 and parts[-1][1] == len(sizes)
+            assert all(parts[r][1] == parts[r + 1][0] for r in range(world - 1))
+            assert all(lo <= hi for lo, hi in parts)
+            if len(sizes) >= 4 * world and sizes.sum() > 0:
+                work = [int(off[hi] - off[lo]) for lo, hi in parts]
+                assert max(work) - min(work) <= 2 * sizes.max()
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        corrs = [rng.uniform(-1, 1, (int(n), 4)) for n in rng.integers(5, 400, size=23)]
+        batch = capi.HostPairBatch(corrs, 100 + np.arange(23))
+        ranges = sharding.partition_by_work(batch.pair_offset, world)
+        sub, lo, hi = sharding.shard_batch(batch, rank, world)
+        assert (lo, hi) == ranges[rank] and sub.num_pairs == hi - lo
+        np.testing.assert_array_equal(sub.seed, batch.seed[lo:hi])
+        np.testing.assert_array_equal(sub.corr, batch.corr[batch.pair_offset[lo]: batch.pair_offset[hi]])
+        # stand-in for the device results of this rank's block: records tagged with the global pair index
+        local = np.zeros(hi - lo, capi.RELPOSE_DTYPE)
+        local["success"] = 1
+        local["num_iterations"] = np.arange(lo, hi)
+        local["num_input_data_points"] = np.diff(sub.pair_offset)
+        full = sharding.all_gather_results(local, ranges)
+        assert len(full) == 23
+        np.testing.assert_array_equal(full["num_iterations"], np.arange(23))
+        np.testing.assert_array_equal(full["num_input_data_points"], np.diff(batch.pair_offset))
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shard_and_gather_over_gloo(world):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))
