@@ -1,0 +1,702 @@
+// Host-side mirror of the reference interface for the two hot paths, in C++ behind pybind11 (the reference's host
+// language): the same free functions, argument orders and return types that src/pytheia/sfm/sfm.cc binds —
+//   pt.sfm.BundleAdjustReconstruction(opts, recon)                sfm.cc:1605-1621, bundle_adjustment_wrapper.cc:98-103
+//   pt.sfm.BundleAdjustPartialReconstruction(opts, views, tracks, recon)
+//   pt.sfm.BundleAdjustView(recon, opts, view_id) / BundleAdjustViews      bundle_adjustment_wrapper.cc:14-40
+//   pt.sfm.BundleAdjustTrack(recon, opts, track_id) / BundleAdjustTracks
+//   pt.sfm.EstimateRelativePose / EstimateCalibratedAbsolutePose / EstimateHomography   sfm.cc:825-850, estimators_wrapper.cc
+//   pt.sfm.FivePointRelativePose / FourPointHomography / SevenPointFundamentalMatrix / PoseFromThreePoints  sfm.cc:577-597
+// implemented as gather -> C-ABI (include/theia_b200.h) -> scatter over a minimal mirror of
+// Reconstruction / View / Track / Camera / Feature (sfm/reconstruction.h, view.h, track.h, camera/camera.h, feature.h)
+// with the reference's method names. No Eigen: vectors and matrices cross the binding as numpy arrays.
+// There is no CPU implementation here: every compute call goes to libtheia_b200.so and fails loudly without a B200.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "../../../include/theia_b200.h"
+#include "../camera_models.cuh"  // plain C++ under g++ (THB_HD = inline): Camera::ProjectPoint uses the same camera math
+
+namespace py = pybind11;
+
+namespace {
+
+using Vec = py::array_t<double, py::array::c_style | py::array::forcecast>;
+typedef uint32_t ViewId;
+typedef uint32_t TrackId;
+typedef uint32_t GroupId;
+constexpr uint32_t kInvalid = std::numeric_limits<uint32_t>::max();  // types.h:48-56
+
+Vec MakeVec(const double* d, int n) {
+  Vec v(n);
+  std::memcpy(v.mutable_data(), d, sizeof(double) * n);
+  return v;
+}
+Vec MakeMat(const double* d, int r, int c) {
+  Vec v({r, c});
+  std::memcpy(v.mutable_data(), d, sizeof(double) * r * c);
+  return v;
+}
+void CopyVec(const Vec& v, double* out, int n, const char* what) {
+  if (v.size() != n) throw std::invalid_argument(std::string(what) + ": expected " + std::to_string(n) + " values");
+  std::memcpy(out, v.data(), sizeof(double) * n);
+}
+void Check(int rc) {
+  if (rc != THB_OK) throw std::runtime_error(std::string("theia_b200: ") + thb_last_error() + " (code " + std::to_string(rc) + ")");
+}
+
+// ceres::AngleAxisRotatePoint / AngleAxisToRotationMatrix semantics (external)
+void AngleAxisToRotation(const double* aa, double* R) {
+  const double th2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (th2 > std::numeric_limits<double>::epsilon()) {
+    const double th = std::sqrt(th2), c = std::cos(th), s = std::sin(th), oc = 1.0 - c;
+    const double x = aa[0] / th, y = aa[1] / th, z = aa[2] / th;
+    R[0] = c + oc * x * x; R[1] = oc * x * y - s * z; R[2] = oc * x * z + s * y;
+    R[3] = oc * x * y + s * z; R[4] = c + oc * y * y; R[5] = oc * y * z - s * x;
+    R[6] = oc * x * z - s * y; R[7] = oc * y * z + s * x; R[8] = c + oc * z * z;
+  } else {
+    R[0] = 1; R[1] = -aa[2]; R[2] = aa[1]; R[3] = aa[2]; R[4] = 1; R[5] = -aa[0]; R[6] = -aa[1]; R[7] = aa[0]; R[8] = 1;
+  }
+}
+void RotationToAngleAxis(const double* R, double* aa) {  // via the quaternion, like ceres::RotationMatrixToAngleAxis
+  double q[4];
+  const double tr = R[0] + R[4] + R[8];
+  if (tr >= 0.0) {
+    double t = std::sqrt(tr + 1.0);
+    q[0] = 0.5 * t; t = 0.5 / t;
+    q[1] = (R[7] - R[5]) * t; q[2] = (R[2] - R[6]) * t; q[3] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 4]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    double t = std::sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+    q[i + 1] = 0.5 * t; t = 0.5 / t;
+    q[0] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    q[j + 1] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    q[k + 1] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+  }
+  const double s2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (s2 > 0.0) {
+    const double s = std::sqrt(s2);
+    const double two_theta = 2.0 * (q[0] < 0.0 ? std::atan2(-s, -q[0]) : std::atan2(s, q[0]));
+    const double k = two_theta / s;
+    aa[0] = q[1] * k; aa[1] = q[2] * k; aa[2] = q[3] * k;
+  } else {
+    aa[0] = q[1] * 2.0; aa[1] = q[2] * 2.0; aa[2] = q[3] * 2.0;
+  }
+}
+
+// feature.h:47-112 (point_, covariance_; depth prior unused on this path)
+struct Feature {
+  double point[2] = {0, 0};
+  double cov[4] = {1, 0, 0, 1};
+};
+
+// camera_intrinsics_model.h + the per-model parameter layouts; shared between views of one group
+struct Intrinsics {
+  int model = THB_MODEL_PINHOLE;
+  double params[THB_INTR_STRIDE] = {1, 1, 0, 0, 0, 0, 0, 0, 0, 0};
+  void SetType(int m) {
+    if (thb::num_intrinsics(m) < 0) throw std::invalid_argument("camera model not on the hot path");
+    model = m;
+    std::fill(params, params + THB_INTR_STRIDE, 0.0);
+    params[0] = 1.0; params[1] = 1.0;                        // f = 1, aspect = 1 (all models)
+    if (m == THB_MODEL_FOV) params[4] = 0.75;                 // fov_camera_model.cc:61
+    if (m == THB_MODEL_DOUBLE_SPHERE) params[6] = 0.75;       // alpha, double_sphere_camera_model.cc:57-64
+    if (m == THB_MODEL_EXTENDED_UNIFIED) { params[5] = 0.5; params[6] = 1.0; }
+  }
+  bool has_skew() const { return model != THB_MODEL_FOV && model != THB_MODEL_DIVISION_UNDISTORTION; }
+  int cx_index() const { return has_skew() ? 3 : 2; }
+};
+
+// camera/camera.h: extrinsics [C(3), angle-axis(3)] (camera.h:202-204), shared_ptr intrinsics
+struct Camera {
+  double ext[6] = {0, 0, 0, 0, 0, 0};
+  std::shared_ptr<Intrinsics> intr = std::make_shared<Intrinsics>();
+  int width = 0, height = 0;
+
+  void SetPosition(const Vec& p) { CopyVec(p, ext, 3, "position"); }
+  Vec GetPosition() const { return MakeVec(ext, 3); }
+  void SetOrientationFromAngleAxis(const Vec& a) { CopyVec(a, ext + 3, 3, "angle_axis"); }
+  Vec GetOrientationAsAngleAxis() const { return MakeVec(ext + 3, 3); }
+  Vec GetOrientationAsRotationMatrix() const { double R[9]; AngleAxisToRotation(ext + 3, R); return MakeMat(R, 3, 3); }
+  void SetOrientationFromRotationMatrix(const Vec& Rm) { double R[9]; CopyVec(Rm, R, 9, "rotation"); RotationToAngleAxis(R, ext + 3); }
+  void SetFocalLength(double f) { intr->params[0] = f; }
+  double FocalLength() const { return intr->params[0]; }
+  void SetPrincipalPoint(double cx, double cy) { intr->params[intr->cx_index()] = cx; intr->params[intr->cx_index() + 1] = cy; }
+  double PrincipalPointX() const { return intr->params[intr->cx_index()]; }
+  double PrincipalPointY() const { return intr->params[intr->cx_index() + 1]; }
+  void SetImageSize(int w, int h) { width = w; height = h; }
+  void SetCameraIntrinsicsModelType(int m) { intr->SetType(m); }
+  int GetCameraIntrinsicsModelType() const { return intr->model; }
+  Vec Parameters() const { return MakeVec(intr->params, thb::num_intrinsics(intr->model)); }
+  void SetParameters(const Vec& v) { CopyVec(v, intr->params, thb::num_intrinsics(intr->model), "intrinsics"); }
+  void DeepCopy(const Camera& o) {  // camera.cc: copies extrinsics and a private copy of the intrinsics
+    std::copy(o.ext, o.ext + 6, ext);
+    intr = std::make_shared<Intrinsics>(*o.intr);
+    width = o.width; height = o.height;
+  }
+  // Camera::ProjectPoint (camera.cc:206-216): returns (depth, pixel)
+  double ProjectRaw(const double* X4, double* pixel) const {
+    double R[9];
+    AngleAxisToRotation(ext + 3, R);
+    const double a[3] = {X4[0] - X4[3] * ext[0], X4[1] - X4[3] * ext[1], X4[2] - X4[3] * ext[2]};
+    double p[3];
+    for (int r = 0; r < 3; ++r) p[r] = R[3 * r] * a[0] + R[3 * r + 1] * a[1] + R[3 * r + 2] * a[2];
+    if (pixel) thb::project<-1, double, double>(intr->model, intr->params, p, pixel);
+    return p[2] / X4[3];
+  }
+  py::tuple ProjectPoint(const Vec& X) const {
+    double x[4], pix[2] = {0, 0};
+    CopyVec(X, x, 4, "point");
+    const double depth = ProjectRaw(x, pix);
+    return py::make_tuple(depth, MakeVec(pix, 2));
+  }
+};
+
+// track.h
+struct Track {
+  double point[4] = {0, 0, 0, 1};
+  bool estimated = false;
+  double inverse_depth = 0.0;
+  ViewId reference_view = kInvalid;
+  std::vector<ViewId> views;  // insertion order; the first view added is the reference view (track.cc:78-83)
+  void SetPoint(const Vec& p) { CopyVec(p, point, 4, "point"); }
+  Vec Point() const { return MakeVec(point, 4); }
+};
+
+// view.h
+struct View {
+  std::string name;
+  bool estimated = false;
+  Camera camera;
+  std::unordered_map<TrackId, Feature> features;
+  std::vector<TrackId> track_order;
+  std::vector<TrackId> TrackIds() const { return track_order; }
+  const Feature* GetFeature(TrackId t) const { auto it = features.find(t); return it == features.end() ? nullptr : &it->second; }
+};
+
+// reconstruction.h:196-206 (hash maps of views and tracks, intrinsics groups)
+struct Reconstruction {
+  std::unordered_map<ViewId, View> views;
+  std::unordered_map<TrackId, Track> tracks;
+  std::unordered_map<ViewId, GroupId> view_group;
+  std::unordered_map<GroupId, std::vector<ViewId>> group_views;
+  std::unordered_map<std::string, ViewId> name_to_view;
+  std::vector<ViewId> view_order;
+  std::vector<TrackId> track_order;
+  ViewId next_view = 0; TrackId next_track = 0; GroupId next_group = 0;
+
+  ViewId AddView(const std::string& name, GroupId group, double /*timestamp*/) {  // reconstruction.cc:104-146
+    if (name_to_view.count(name)) return kInvalid;
+    const ViewId id = next_view++;
+    View& v = views[id];
+    v.name = name;
+    name_to_view[name] = id;
+    view_order.push_back(id);
+    auto& members = group_views[group];
+    if (!members.empty()) v.camera.intr = views[members.front()].camera.intr;  // shared intrinsics (reconstruction.cc:129-140)
+    members.push_back(id);
+    view_group[id] = group;
+    next_group = std::max(next_group, group + 1);
+    return id;
+  }
+  ViewId AddViewAutoGroup(const std::string& name, double ts) { return AddView(name, next_group, ts); }
+  TrackId AddTrack() { const TrackId id = next_track++; tracks[id]; track_order.push_back(id); return id; }
+  bool AddObservation(ViewId v, TrackId t, const Feature& f) {  // reconstruction.cc:221-251
+    auto vi = views.find(v); auto ti = tracks.find(t);
+    if (vi == views.end() || ti == tracks.end() || vi->second.features.count(t)) return false;
+    vi->second.features[t] = f;
+    vi->second.track_order.push_back(t);
+    ti->second.views.push_back(v);
+    if (ti->second.reference_view == kInvalid) ti->second.reference_view = v;
+    return true;
+  }
+  View* MutableView(ViewId v) { auto it = views.find(v); return it == views.end() ? nullptr : &it->second; }
+  Track* MutableTrack(TrackId t) { auto it = tracks.find(t); return it == tracks.end() ? nullptr : &it->second; }
+  GroupId CameraIntrinsicsGroupIdFromViewId(ViewId v) const { auto it = view_group.find(v); return it == view_group.end() ? kInvalid : it->second; }
+};
+
+// bundle_adjustment.h:71-85
+enum OptimizeIntrinsicsType { NONE = 0x00, FOCAL_LENGTH = 0x01, ASPECT_RATIO = 0x02, SKEW = 0x04, PRINCIPAL_POINTS = 0x08,
+                              RADIAL_DISTORTION = 0x10, TANGENTIAL_DISTORTION = 0x20, ALL = 0x3f };
+enum LinearSolverType { DENSE_NORMAL_CHOLESKY = 0, DENSE_QR = 1, SPARSE_NORMAL_CHOLESKY = 2, DENSE_SCHUR = 3, SPARSE_SCHUR = 4,
+                        ITERATIVE_SCHUR = 5, CGNR = 6 };  // ceres::LinearSolverType values
+
+// GetSubsetFromOptimizeIntrinsicsType (e.g. pinhole_camera_model.cc:132-162): bit k set => parameter k CONSTANT
+uint16_t ConstantIntrinsicsMask(const Intrinsics& in, int to_optimize) {
+  const int K = thb::num_intrinsics(in.model);
+  if (to_optimize == ALL) return 0;
+  uint16_t m = 0;
+  if (!(to_optimize & FOCAL_LENGTH)) m |= 1u << 0;
+  if (!(to_optimize & ASPECT_RATIO)) m |= 1u << 1;
+  int k = 2;
+  if (in.has_skew()) { if (!(to_optimize & SKEW)) m |= 1u << 2; k = 3; }
+  if (!(to_optimize & PRINCIPAL_POINTS)) m |= (1u << k) | (1u << (k + 1));
+  if (!(to_optimize & RADIAL_DISTORTION)) for (int i = k + 2; i < K; ++i) m |= 1u << i;
+  return m;
+}
+
+// bundle_adjustment.h:87-167
+struct BundleAdjustmentOptions {
+  int loss_function_type = THB_LOSS_TRIVIAL;
+  double robust_loss_width = 2.0;
+  int linear_solver_type = SPARSE_SCHUR;
+  bool verbose = false, constant_camera_orientation = false, constant_camera_position = false;
+  bool use_homogeneous_point_parametrization = true, use_inverse_depth_parametrization = false;
+  int intrinsics_to_optimize = NONE;
+  int num_threads = 1, max_num_iterations = 100;
+  double max_solver_time_in_seconds = 3600.0;
+  bool use_inner_iterations = true;
+  double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8, max_trust_region_radius = 1e12;
+  bool use_position_priors = false, use_orientation_priors = false, use_depth_priors = false, orthographic_camera = false,
+       use_gravity_priors = false;
+};
+struct BundleAdjustmentSummary {  // bundle_adjustment.h:170-178
+  bool success = false;
+  double initial_cost = 0, final_cost = 0, setup_time_in_seconds = 0, solve_time_in_seconds = 0;
+};
+
+struct Flat {
+  std::vector<ViewId> view_ids; std::unordered_map<ViewId, int> view_index;
+  std::vector<TrackId> track_ids; std::unordered_map<TrackId, int> track_index;
+  std::vector<Intrinsics*> groups; std::unordered_map<Intrinsics*, int> group_index;
+  std::vector<double> cam_ext, intr, pts, obs_xy, obs_si;
+  std::vector<uint8_t> cam_const, pt_const; std::vector<uint16_t> intr_const;
+  std::vector<int32_t> cam_group, intr_model, obs_cam, obs_pt;
+};
+
+// What BundleAdjuster::AddView / AddTrack register (bundle_adjuster.cc:116-221), flattened.
+BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vector<ViewId>& views, const std::vector<TrackId>& tracks,
+                              Reconstruction* r, bool force_no_inner) {
+  if (o.use_inverse_depth_parametrization) throw std::runtime_error("use_inverse_depth_parametrization is not implemented");
+  if (o.use_position_priors || o.use_orientation_priors || o.use_depth_priors || o.use_gravity_priors || o.orthographic_camera)
+    throw std::runtime_error("prior residuals / orthographic cameras are not implemented");
+  Flat f;
+  const std::unordered_set<ViewId> vset(views.begin(), views.end());
+  const std::unordered_set<TrackId> tset(tracks.begin(), tracks.end());
+  auto add_view = [&](ViewId v, bool free_cam) {
+    auto it = f.view_index.find(v);
+    if (it != f.view_index.end()) return it->second;
+    View& view = r->views.at(v);
+    const int idx = (int)f.view_ids.size();
+    f.view_index[v] = idx; f.view_ids.push_back(v);
+    f.cam_ext.insert(f.cam_ext.end(), view.camera.ext, view.camera.ext + 6);
+    uint8_t c = free_cam ? 0 : THB_CAM_CONST_ALL;
+    if (o.constant_camera_position) c |= THB_CAM_CONST_POSITION;          // bundle_adjuster.cc:357-380
+    if (o.constant_camera_orientation) c |= THB_CAM_CONST_ORIENTATION;
+    f.cam_const.push_back(c);
+    Intrinsics* in = view.camera.intr.get();
+    if (!f.group_index.count(in)) {
+      f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
+      f.intr_model.push_back(in->model);
+      f.intr.insert(f.intr.end(), in->params, in->params + THB_INTR_STRIDE);
+      f.intr_const.push_back(0xffff);                                      // constant until an optimised view claims it
+    }
+    const int g = f.group_index[in];
+    if (free_cam) f.intr_const[g] = ConstantIntrinsicsMask(*in, o.intrinsics_to_optimize);   // bundle_adjuster.cc:382-460
+    f.cam_group.push_back(g);
+    return idx;
+  };
+  auto add_track = [&](TrackId t, bool free_pt) {
+    auto it = f.track_index.find(t);
+    if (it != f.track_index.end()) { if (free_pt) f.pt_const[it->second] = 0; return it->second; }
+    const int idx = (int)f.track_ids.size();
+    f.track_index[t] = idx; f.track_ids.push_back(t);
+    const Track& tr = r->tracks.at(t);
+    f.pts.insert(f.pts.end(), tr.point, tr.point + 4);
+    f.pt_const.push_back(free_pt ? 0 : 1);
+    return idx;
+  };
+  auto add_obs = [&](int ci, int pi, const Feature& feat) {
+    f.obs_cam.push_back(ci); f.obs_pt.push_back(pi);
+    f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
+    f.obs_si.push_back(1.0 / std::sqrt(feat.cov[0])); f.obs_si.push_back(1.0 / std::sqrt(feat.cov[3]));   // reprojection_error.h:96-103
+  };
+  for (ViewId v : views) {                                                 // AddView
+    auto vi = r->views.find(v);
+    if (vi == r->views.end()) throw std::invalid_argument("unknown view id");   // the reference CHECK-aborts (bundle_adjuster.cc:117)
+    if (!vi->second.estimated) continue;
+    const int ci = add_view(v, true);
+    for (TrackId t : vi->second.track_order) {
+      const Track& tr = r->tracks.at(t);
+      if (!tr.estimated) continue;
+      add_obs(ci, add_track(t, false), vi->second.features.at(t));
+    }
+  }
+  for (TrackId t : tracks) {                                               // AddTrack
+    auto ti = r->tracks.find(t);
+    if (ti == r->tracks.end()) throw std::invalid_argument("unknown track id");
+    if (!ti->second.estimated) continue;
+    const int pi = add_track(t, true);
+    for (ViewId v : ti->second.views) {
+      View& view = r->views.at(v);
+      if (vset.count(v) || !view.estimated) continue;
+      add_obs(add_view(v, false), pi, view.features.at(t));
+    }
+  }
+  BundleAdjustmentSummary out;
+  if (f.obs_cam.empty()) { out.success = true; return out; }
+  ThbBaProblem p;
+  std::memset(&p, 0, sizeof(p));
+  p.num_cameras = (int)f.view_ids.size(); p.num_groups = (int)f.groups.size();
+  p.num_points = (int)f.track_ids.size(); p.num_observations = (int)f.obs_cam.size();
+  p.memory_space = THB_MEM_HOST;
+  p.cam_ext = f.cam_ext.data(); p.cam_const = f.cam_const.data(); p.cam_group = f.cam_group.data();
+  p.intr = f.intr.data(); p.intr_model = f.intr_model.data(); p.intr_const = f.intr_const.data();
+  p.pts = f.pts.data(); p.pt_const = f.pt_const.data();
+  p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data(); p.obs_sqrt_info = f.obs_si.data();
+  ThbBaOptions opt;
+  thb_ba_default_options(&opt);                                            // SetSolverOptions, bundle_adjuster.cc:63-89
+  opt.loss_function_type = o.loss_function_type; opt.robust_loss_width = o.robust_loss_width;
+  opt.use_homogeneous_point_parametrization = o.use_homogeneous_point_parametrization ? 1 : 0;
+  opt.use_inner_iterations = (!force_no_inner && o.use_inner_iterations) ? 1 : 0;
+  opt.max_num_iterations = o.max_num_iterations;
+  opt.function_tolerance = o.function_tolerance; opt.gradient_tolerance = o.gradient_tolerance;
+  opt.parameter_tolerance = o.parameter_tolerance; opt.max_trust_region_radius = o.max_trust_region_radius;
+  opt.max_solver_time_in_seconds = o.max_solver_time_in_seconds; opt.verbose = o.verbose;
+  opt.linear_solver = THB_SOLVER_SCHUR_CHOLESKY;                           // every exact ceres solver type maps here
+  if (o.linear_solver_type == ITERATIVE_SCHUR || o.linear_solver_type == CGNR)
+    throw std::runtime_error("iterative linear solvers are not implemented; use SPARSE_SCHUR / DENSE_SCHUR / DENSE_QR");
+  ThbBaSummary s;
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = thb_ba_solve(&p, &opt, &s, nullptr);
+  }
+  if (rc == THB_E_NUMERICAL) return out;                                   // ceres FAILURE -> summary.success = false
+  Check(rc);
+  out.success = s.success != 0;
+  out.initial_cost = s.initial_cost; out.final_cost = s.final_cost;
+  out.setup_time_in_seconds = s.setup_time_in_seconds; out.solve_time_in_seconds = s.solve_time_in_seconds;
+  if (!out.success) return out;
+  for (size_t i = 0; i < f.view_ids.size(); ++i) std::copy_n(&f.cam_ext[6 * i], 6, r->views.at(f.view_ids[i]).camera.ext);
+  for (size_t i = 0; i < f.track_ids.size(); ++i) std::copy_n(&f.pts[4 * i], 4, r->tracks.at(f.track_ids[i]).point);
+  for (size_t g = 0; g < f.groups.size(); ++g) std::copy_n(&f.intr[THB_INTR_STRIDE * g], THB_INTR_STRIDE, f.groups[g]->params);
+  return out;
+}
+
+// UpdateInverseDepth (bundle_adjustment.cc:69-83)
+void UpdateInverseDepth(const std::vector<TrackId>& ids, Reconstruction* r) {
+  for (TrackId t : ids) {
+    auto it = r->tracks.find(t);
+    if (it == r->tracks.end() || !it->second.estimated) continue;
+    auto vi = r->views.find(it->second.reference_view);
+    if (vi == r->views.end()) continue;
+    it->second.inverse_depth = 1.0 / vi->second.camera.ProjectRaw(it->second.point, nullptr);
+  }
+}
+std::vector<TrackId> TracksOfViews(const std::vector<ViewId>& vs, Reconstruction* r) {
+  std::vector<TrackId> out;
+  for (ViewId v : vs) { auto it = r->views.find(v); if (it != r->views.end()) for (TrackId t : it->second.track_order) if (r->tracks.at(t).reference_view == v) out.push_back(t); }
+  return out;
+}
+
+// solvers/sample_consensus_estimator.h:58-144
+struct RansacParameters {
+  double error_thresh = -1, failure_probability = 0.01, min_inlier_ratio = 0;
+  int min_iterations = 100, max_iterations = std::numeric_limits<int>::max();
+  bool use_mle = false, use_Tdd_test = false, use_lo = false;
+  int lo_start_iterations = 50;
+  int64_t seed = -1;  // ADDITIVE: the reference's `rng` member is not bindable (solvers.cc:89-102); < 0 => clock-seeded like the reference
+};
+struct RansacSummary {
+  std::vector<int> inliers;
+  int num_input_data_points = 0, num_iterations = 0, num_lo_iterations = 0;
+  double confidence = 0;
+};
+struct FeatureCorrespondence { Feature feature1, feature2; };                       // matching/feature_correspondence.h:49-72
+struct FeatureCorrespondence2D3D { double feature[2] = {0, 0}; double world_point[3] = {0, 0, 0}; };  // feature_correspondence_2d_3d.h
+struct RelativePose { double E[9] = {0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}; };      // estimate_relative_pose.h:49-53
+struct CalibratedAbsolutePose { double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, p[3] = {0, 0, 0}; };
+
+ThbRansacParams ToC(const RansacParameters& q, int ransac_type) {
+  ThbRansacParams p;
+  thb_ransac_default_params(&p);
+  p.error_thresh = q.error_thresh; p.failure_probability = q.failure_probability; p.min_inlier_ratio = q.min_inlier_ratio;
+  p.min_iterations = q.min_iterations; p.max_iterations = q.max_iterations; p.use_mle = q.use_mle; p.use_lo = q.use_lo;
+  p.lo_start_iterations = q.lo_start_iterations; p.ransac_type = ransac_type;
+  return p;
+}
+uint32_t SeedOf(const RansacParameters& q) { return q.seed >= 0 ? (uint32_t)q.seed : std::random_device{}(); }
+
+typedef int (*BatchFn)(const ThbPairBatch*, const ThbRansacParams*, ThbRelPoseResult*, uint8_t*, void*);
+bool RunOne(BatchFn fn, const RansacParameters& q, int type, const std::vector<double>& data, int width, ThbRelPoseResult* res, RansacSummary* sum) {
+  const int64_t n = (int64_t)(data.size() / width);
+  const int64_t off[2] = {0, n};
+  const uint32_t seed = SeedOf(q);
+  ThbPairBatch b = {1, THB_MEM_HOST, off, data.data(), &seed};
+  const ThbRansacParams p = ToC(q, type);
+  std::vector<uint8_t> mask((size_t)n);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = fn(&b, &p, res, mask.data(), nullptr);
+  }
+  Check(rc);
+  sum->inliers.clear();
+  for (int64_t i = 0; i < n; ++i) if (mask[i]) sum->inliers.push_back((int)i);
+  sum->num_input_data_points = res->num_input_data_points; sum->num_iterations = res->num_iterations; sum->confidence = res->confidence;
+  return res->success != 0;
+}
+std::vector<double> Flatten(const std::vector<FeatureCorrespondence>& c) {
+  std::vector<double> d(c.size() * 4);
+  for (size_t i = 0; i < c.size(); ++i) { d[4 * i] = c[i].feature1.point[0]; d[4 * i + 1] = c[i].feature1.point[1]; d[4 * i + 2] = c[i].feature2.point[0]; d[4 * i + 3] = c[i].feature2.point[1]; }
+  return d;
+}
+std::vector<double> Points2(const std::vector<Vec>& pts, size_t expect_min) {
+  if (pts.size() < expect_min) throw std::invalid_argument("not enough points");
+  std::vector<double> d(pts.size() * 2);
+  for (size_t i = 0; i < pts.size(); ++i) CopyVec(pts[i], &d[2 * i], 2, "image point");
+  return d;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_pt, m) {
+  m.doc() = "theia-b200: pt.sfm / pt.solvers / pt.matching names of pyTheia for the B200 hot paths";
+  py::module_ sfm = m.def_submodule("sfm");
+  py::module_ solvers = m.def_submodule("solvers");
+  py::module_ matching = m.def_submodule("matching");
+
+  py::enum_<OptimizeIntrinsicsType>(sfm, "OptimizeIntrinsicsType", py::arithmetic())
+      .value("NONE", NONE).value("FOCAL_LENGTH", FOCAL_LENGTH).value("ASPECT_RATIO", ASPECT_RATIO).value("SKEW", SKEW)
+      .value("PRINCIPAL_POINTS", PRINCIPAL_POINTS).value("RADIAL_DISTORTION", RADIAL_DISTORTION)
+      .value("TANGENTIAL_DISTORTION", TANGENTIAL_DISTORTION).value("ALL", ALL);
+  py::enum_<LinearSolverType>(sfm, "LinearSolverType")
+      .value("DENSE_NORMAL_CHOLESKY", DENSE_NORMAL_CHOLESKY).value("DENSE_QR", DENSE_QR).value("SPARSE_NORMAL_CHOLESKY", SPARSE_NORMAL_CHOLESKY)
+      .value("DENSE_SCHUR", DENSE_SCHUR).value("SPARSE_SCHUR", SPARSE_SCHUR).value("ITERATIVE_SCHUR", ITERATIVE_SCHUR).value("CGNR", CGNR);
+  struct LossNs {}; struct ModelNs {}; struct RansacNs {}; struct PnPNs {};
+  py::class_<LossNs>(sfm, "LossFunctionType")
+      .def_property_readonly_static("TRIVIAL", [](py::object) { return THB_LOSS_TRIVIAL; }).def_property_readonly_static("HUBER", [](py::object) { return THB_LOSS_HUBER; })
+      .def_property_readonly_static("SOFTLONE", [](py::object) { return THB_LOSS_SOFTLONE; }).def_property_readonly_static("CAUCHY", [](py::object) { return THB_LOSS_CAUCHY; })
+      .def_property_readonly_static("ARCTAN", [](py::object) { return THB_LOSS_ARCTAN; }).def_property_readonly_static("TUKEY", [](py::object) { return THB_LOSS_TUKEY; })
+      .def_property_readonly_static("TRUNCATED", [](py::object) { return THB_LOSS_TRUNCATED; });
+  py::class_<ModelNs>(sfm, "CameraIntrinsicsModelType")
+      .def_property_readonly_static("PINHOLE", [](py::object) { return THB_MODEL_PINHOLE; }).def_property_readonly_static("FISHEYE", [](py::object) { return THB_MODEL_FISHEYE; })
+      .def_property_readonly_static("FOV", [](py::object) { return THB_MODEL_FOV; })
+      .def_property_readonly_static("DIVISION_UNDISTORTION", [](py::object) { return THB_MODEL_DIVISION_UNDISTORTION; })
+      .def_property_readonly_static("DOUBLE_SPHERE", [](py::object) { return THB_MODEL_DOUBLE_SPHERE; })
+      .def_property_readonly_static("EXTENDED_UNIFIED", [](py::object) { return THB_MODEL_EXTENDED_UNIFIED; });
+  py::class_<RansacNs>(sfm, "RansacType")
+      .def_property_readonly_static("RANSAC", [](py::object) { return 0; }).def_property_readonly_static("PROSAC", [](py::object) { return 1; })
+      .def_property_readonly_static("LMED", [](py::object) { return 2; }).def_property_readonly_static("EXHAUSTIVE", [](py::object) { return 3; });
+  py::class_<PnPNs>(sfm, "PnPType")
+      .def_property_readonly_static("KNEIP", [](py::object) { return 0; }).def_property_readonly_static("DLS", [](py::object) { return 1; })
+      .def_property_readonly_static("SQPnP", [](py::object) { return 2; });
+
+  py::class_<Feature>(sfm, "Feature")
+      .def(py::init<>())
+      .def(py::init([](const Vec& p) { Feature f; CopyVec(p, f.point, 2, "point"); return f; }))
+      .def(py::init([](const Vec& p, const Vec& c) { Feature f; CopyVec(p, f.point, 2, "point"); CopyVec(c, f.cov, 4, "covariance"); return f; }))
+      .def_property("point", [](const Feature& f) { return MakeVec(f.point, 2); }, [](Feature& f, const Vec& p) { CopyVec(p, f.point, 2, "point"); })
+      .def_property("covariance", [](const Feature& f) { return MakeMat(f.cov, 2, 2); }, [](Feature& f, const Vec& c) { CopyVec(c, f.cov, 4, "covariance"); });
+
+  py::class_<Camera>(sfm, "Camera")
+      .def(py::init<>())
+      .def("DeepCopy", &Camera::DeepCopy)
+      .def("SetPosition", &Camera::SetPosition).def("GetPosition", &Camera::GetPosition)
+      .def("SetOrientationFromAngleAxis", &Camera::SetOrientationFromAngleAxis).def("GetOrientationAsAngleAxis", &Camera::GetOrientationAsAngleAxis)
+      .def("SetOrientationFromRotationMatrix", &Camera::SetOrientationFromRotationMatrix)
+      .def("GetOrientationAsRotationMatrix", &Camera::GetOrientationAsRotationMatrix)
+      .def("SetFocalLength", &Camera::SetFocalLength).def("FocalLength", &Camera::FocalLength)
+      .def("SetPrincipalPoint", &Camera::SetPrincipalPoint).def("PrincipalPointX", &Camera::PrincipalPointX).def("PrincipalPointY", &Camera::PrincipalPointY)
+      .def("SetImageSize", &Camera::SetImageSize).def("ImageWidth", [](const Camera& c) { return c.width; }).def("ImageHeight", [](const Camera& c) { return c.height; })
+      .def("SetCameraIntrinsicsModelType", &Camera::SetCameraIntrinsicsModelType).def("GetCameraIntrinsicsModelType", &Camera::GetCameraIntrinsicsModelType)
+      .def("Parameters", &Camera::Parameters).def("SetParameters", &Camera::SetParameters)
+      .def("ProjectPoint", &Camera::ProjectPoint);
+
+  py::class_<Track>(sfm, "Track")
+      .def("SetPoint", &Track::SetPoint).def("Point", &Track::Point)
+      .def("SetIsEstimated", [](Track& t, bool e) { t.estimated = e; }).def("IsEstimated", [](const Track& t) { return t.estimated; })
+      .def("NumViews", [](const Track& t) { return (int)t.views.size(); }).def("ViewIds", [](const Track& t) { return t.views; })
+      .def("InverseDepth", [](const Track& t) { return t.inverse_depth; }).def("ReferenceViewId", [](const Track& t) { return t.reference_view; });
+
+  py::class_<View>(sfm, "View")
+      .def("Name", [](const View& v) { return v.name; })
+      .def("SetIsEstimated", [](View& v, bool e) { v.estimated = e; }).def("IsEstimated", [](const View& v) { return v.estimated; })
+      .def("Camera", [](View& v) -> Camera& { return v.camera; }, py::return_value_policy::reference_internal)
+      .def("MutableCamera", [](View& v) -> Camera& { return v.camera; }, py::return_value_policy::reference_internal)
+      .def("NumFeatures", [](const View& v) { return (int)v.features.size(); }).def("TrackIds", &View::TrackIds)
+      .def("GetFeature", [](const View& v, TrackId t) { const Feature* f = v.GetFeature(t); if (!f) throw std::invalid_argument("no such feature"); return *f; });
+
+  py::class_<Reconstruction>(sfm, "Reconstruction")
+      .def(py::init<>())
+      .def("AddView", &Reconstruction::AddView, py::arg("name"), py::arg("group_id"), py::arg("timestamp"))
+      .def("AddView", &Reconstruction::AddViewAutoGroup, py::arg("name"), py::arg("timestamp"))
+      .def("AddTrack", &Reconstruction::AddTrack)
+      .def("AddObservation", &Reconstruction::AddObservation)
+      .def("View", [](Reconstruction& r, ViewId v) -> View* { return r.MutableView(v); }, py::return_value_policy::reference_internal)
+      .def("MutableView", &Reconstruction::MutableView, py::return_value_policy::reference_internal)
+      .def("Track", [](Reconstruction& r, TrackId t) -> Track* { return r.MutableTrack(t); }, py::return_value_policy::reference_internal)
+      .def("MutableTrack", &Reconstruction::MutableTrack, py::return_value_policy::reference_internal)
+      .def("ViewIds", [](const Reconstruction& r) { return r.view_order; }).def("TrackIds", [](const Reconstruction& r) { return r.track_order; })
+      .def("NumViews", [](const Reconstruction& r) { return (int)r.views.size(); }).def("NumTracks", [](const Reconstruction& r) { return (int)r.tracks.size(); })
+      .def("CameraIntrinsicsGroupIdFromViewId", &Reconstruction::CameraIntrinsicsGroupIdFromViewId);
+
+  py::class_<BundleAdjustmentOptions>(sfm, "BundleAdjustmentOptions")
+      .def(py::init<>())
+      .def_readwrite("loss_function_type", &BundleAdjustmentOptions::loss_function_type)
+      .def_readwrite("robust_loss_width", &BundleAdjustmentOptions::robust_loss_width)
+      .def_readwrite("linear_solver_type", &BundleAdjustmentOptions::linear_solver_type)
+      .def_readwrite("verbose", &BundleAdjustmentOptions::verbose)
+      .def_readwrite("constant_camera_orientation", &BundleAdjustmentOptions::constant_camera_orientation)
+      .def_readwrite("constant_camera_position", &BundleAdjustmentOptions::constant_camera_position)
+      .def_readwrite("use_homogeneous_point_parametrization", &BundleAdjustmentOptions::use_homogeneous_point_parametrization)
+      .def_readwrite("use_inverse_depth_parametrization", &BundleAdjustmentOptions::use_inverse_depth_parametrization)
+      .def_readwrite("intrinsics_to_optimize", &BundleAdjustmentOptions::intrinsics_to_optimize)
+      .def_readwrite("num_threads", &BundleAdjustmentOptions::num_threads)
+      .def_readwrite("max_num_iterations", &BundleAdjustmentOptions::max_num_iterations)
+      .def_readwrite("max_solver_time_in_seconds", &BundleAdjustmentOptions::max_solver_time_in_seconds)
+      .def_readwrite("use_inner_iterations", &BundleAdjustmentOptions::use_inner_iterations)
+      .def_readwrite("function_tolerance", &BundleAdjustmentOptions::function_tolerance)
+      .def_readwrite("gradient_tolerance", &BundleAdjustmentOptions::gradient_tolerance)
+      .def_readwrite("parameter_tolerance", &BundleAdjustmentOptions::parameter_tolerance)
+      .def_readwrite("max_trust_region_radius", &BundleAdjustmentOptions::max_trust_region_radius)
+      .def_readwrite("use_position_priors", &BundleAdjustmentOptions::use_position_priors)
+      .def_readwrite("use_orientation_priors", &BundleAdjustmentOptions::use_orientation_priors)
+      .def_readwrite("use_depth_priors", &BundleAdjustmentOptions::use_depth_priors)
+      .def_readwrite("orthographic_camera", &BundleAdjustmentOptions::orthographic_camera)
+      .def_readwrite("use_gravity_priors", &BundleAdjustmentOptions::use_gravity_priors);
+  py::class_<BundleAdjustmentSummary>(sfm, "BundleAdjustmentSummary")
+      .def_readonly("success", &BundleAdjustmentSummary::success).def_readonly("initial_cost", &BundleAdjustmentSummary::initial_cost)
+      .def_readonly("final_cost", &BundleAdjustmentSummary::final_cost)
+      .def_readonly("setup_time_in_seconds", &BundleAdjustmentSummary::setup_time_in_seconds)
+      .def_readonly("solve_time_in_seconds", &BundleAdjustmentSummary::solve_time_in_seconds);
+
+  // bundle_adjustment.cc:188-217 / :111-143 / :220-258 / :261-285,389-418 and their wrappers' argument orders
+  sfm.def("BundleAdjustReconstruction", [](const BundleAdjustmentOptions& o, Reconstruction& r) {
+    BundleAdjustmentSummary s = RunBa(o, r.view_order, r.track_order, &r, false);
+    UpdateInverseDepth(r.track_order, &r);
+    return s;
+  });
+  sfm.def("BundleAdjustPartialReconstruction", [](const BundleAdjustmentOptions& o, const std::vector<ViewId>& v, const std::vector<TrackId>& t, Reconstruction& r) {
+    BundleAdjustmentSummary s = RunBa(o, v, t, &r, false);
+    UpdateInverseDepth(t, &r);
+    return s;
+  });
+  sfm.def("BundleAdjustView", [](Reconstruction& r, const BundleAdjustmentOptions& o, ViewId v) {
+    BundleAdjustmentSummary s = RunBa(o, {v}, {}, &r, true);   // forces DENSE_QR, no inner iterations (:225)
+    UpdateInverseDepth(TracksOfViews({v}, &r), &r);
+    return s;
+  });
+  sfm.def("BundleAdjustViews", [](Reconstruction& r, const BundleAdjustmentOptions& o, const std::vector<ViewId>& v) {
+    BundleAdjustmentSummary s = RunBa(o, v, {}, &r, true);
+    UpdateInverseDepth(TracksOfViews(v, &r), &r);
+    return s;
+  });
+  sfm.def("BundleAdjustTrack", [](Reconstruction& r, const BundleAdjustmentOptions& o, TrackId t) {
+    BundleAdjustmentSummary s = RunBa(o, {}, {t}, &r, true);   // no inner iterations (:267)
+    UpdateInverseDepth({t}, &r);
+    return s;
+  });
+  sfm.def("BundleAdjustTracks", [](Reconstruction& r, const BundleAdjustmentOptions& o, const std::vector<TrackId>& t) {
+    BundleAdjustmentSummary s = RunBa(o, {}, t, &r, true);
+    UpdateInverseDepth(t, &r);
+    return s;
+  });
+
+  py::class_<RansacParameters>(solvers, "RansacParameters")
+      .def(py::init<>())
+      .def_readwrite("error_thresh", &RansacParameters::error_thresh).def_readwrite("failure_probability", &RansacParameters::failure_probability)
+      .def_readwrite("min_inlier_ratio", &RansacParameters::min_inlier_ratio).def_readwrite("min_iterations", &RansacParameters::min_iterations)
+      .def_readwrite("max_iterations", &RansacParameters::max_iterations).def_readwrite("use_mle", &RansacParameters::use_mle)
+      .def_readwrite("use_Tdd_test", &RansacParameters::use_Tdd_test).def_readwrite("use_lo", &RansacParameters::use_lo)
+      .def_readwrite("lo_start_iterations", &RansacParameters::lo_start_iterations).def_readwrite("seed", &RansacParameters::seed);
+  py::class_<RansacSummary>(solvers, "RansacSummary")
+      .def_readonly("inliers", &RansacSummary::inliers).def_readonly("num_input_data_points", &RansacSummary::num_input_data_points)
+      .def_readonly("num_iterations", &RansacSummary::num_iterations).def_readonly("confidence", &RansacSummary::confidence)
+      .def_readonly("num_lo_iterations", &RansacSummary::num_lo_iterations);
+  py::class_<FeatureCorrespondence>(matching, "FeatureCorrespondence")
+      .def(py::init<>())
+      .def(py::init([](const Feature& a, const Feature& b) { FeatureCorrespondence c; c.feature1 = a; c.feature2 = b; return c; }))
+      .def_readwrite("feature1", &FeatureCorrespondence::feature1).def_readwrite("feature2", &FeatureCorrespondence::feature2);
+  py::class_<FeatureCorrespondence2D3D>(sfm, "FeatureCorrespondence2D3D")
+      .def(py::init<>())
+      .def(py::init([](const Vec& f, const Vec& w) { FeatureCorrespondence2D3D c; CopyVec(f, c.feature, 2, "feature"); CopyVec(w, c.world_point, 3, "world_point"); return c; }))
+      .def_property("feature", [](const FeatureCorrespondence2D3D& c) { return MakeVec(c.feature, 2); }, [](FeatureCorrespondence2D3D& c, const Vec& v) { CopyVec(v, c.feature, 2, "feature"); })
+      .def_property("world_point", [](const FeatureCorrespondence2D3D& c) { return MakeVec(c.world_point, 3); }, [](FeatureCorrespondence2D3D& c, const Vec& v) { CopyVec(v, c.world_point, 3, "world_point"); });
+  py::class_<RelativePose>(sfm, "RelativePose")
+      .def_property_readonly("essential_matrix", [](const RelativePose& p) { return MakeMat(p.E, 3, 3); })
+      .def_property_readonly("rotation", [](const RelativePose& p) { return MakeMat(p.R, 3, 3); })
+      .def_property_readonly("position", [](const RelativePose& p) { return MakeVec(p.p, 3); });
+  py::class_<CalibratedAbsolutePose>(sfm, "CalibratedAbsolutePose")
+      .def_property_readonly("rotation", [](const CalibratedAbsolutePose& p) { return MakeMat(p.R, 3, 3); })
+      .def_property_readonly("position", [](const CalibratedAbsolutePose& p) { return MakeVec(p.p, 3); });
+
+  // estimators_wrapper.cc:42-60, 99-115, 130-146: tuple(bool, Model, RansacSummary)
+  sfm.def("EstimateRelativePose", [](const RansacParameters& q, int type, const std::vector<FeatureCorrespondence>& c) {
+    ThbRelPoseResult res; RansacSummary sum; RelativePose pose;
+    const bool ok = RunOne(thb_ransac_relpose_batch, q, type, Flatten(c), 4, &res, &sum);
+    std::copy_n(res.essential_matrix, 9, pose.E); std::copy_n(res.rotation, 9, pose.R); std::copy_n(res.position, 3, pose.p);
+    return py::make_tuple(ok, pose, sum);
+  });
+  sfm.def("EstimateHomography", [](const RansacParameters& q, int type, const std::vector<FeatureCorrespondence>& c) {
+    ThbRelPoseResult res; RansacSummary sum;
+    const bool ok = RunOne(thb_ransac_homography_batch, q, type, Flatten(c), 4, &res, &sum);
+    return py::make_tuple(ok, MakeMat(res.essential_matrix, 3, 3), sum);
+  });
+  sfm.def("EstimateCalibratedAbsolutePose", [](const RansacParameters& q, int type, int pnp_type, const std::vector<FeatureCorrespondence2D3D>& c) {
+    if (pnp_type != 0) throw std::runtime_error("only PnPType.KNEIP is implemented (DLS / SQPnP are not replayable, DESIGN.md)");
+    std::vector<double> d(c.size() * 5);
+    for (size_t i = 0; i < c.size(); ++i) { d[5 * i] = c[i].feature[0]; d[5 * i + 1] = c[i].feature[1]; std::copy_n(c[i].world_point, 3, &d[5 * i + 2]); }
+    ThbRelPoseResult res; RansacSummary sum; CalibratedAbsolutePose pose;
+    const bool ok = RunOne(thb_ransac_abspose_batch, q, type, d, 5, &res, &sum);
+    std::copy_n(res.rotation, 9, pose.R); std::copy_n(res.position, 3, pose.p);
+    return py::make_tuple(ok, pose, sum);
+  });
+
+  // pose_wrapper.cc:166-173, 210-217, 369-377 and PoseFromThreePoints
+  sfm.def("FivePointRelativePose", [](const std::vector<Vec>& a, const std::vector<Vec>& b) {
+    if (a.size() != 5 || b.size() != 5) throw std::runtime_error("only the minimal 5-point case is implemented");
+    const std::vector<double> x1 = Points2(a, 5), x2 = Points2(b, 5);
+    double E[90]; int32_t n = 0;
+    Check(thb_five_point_relative_pose(x1.data(), x2.data(), 1, E, &n, nullptr));
+    std::vector<Vec> out;
+    for (int k = 0; k < n; ++k) out.push_back(MakeMat(E + 9 * k, 3, 3));
+    return py::make_tuple(n > 0, out);
+  });
+  sfm.def("FourPointHomography", [](const std::vector<Vec>& a, const std::vector<Vec>& b) {
+    if (a.size() != 4 || b.size() != 4) throw std::runtime_error("only the minimal 4-point case is implemented");
+    const std::vector<double> x1 = Points2(a, 4), x2 = Points2(b, 4);
+    double c[16], H[9]; int32_t ok = 0;
+    for (int i = 0; i < 4; ++i) { c[4 * i] = x1[2 * i]; c[4 * i + 1] = x1[2 * i + 1]; c[4 * i + 2] = x2[2 * i]; c[4 * i + 3] = x2[2 * i + 1]; }
+    Check(thb_four_point_homography(c, 1, H, &ok, nullptr));
+    return py::make_tuple(ok != 0, MakeMat(H, 3, 3));
+  });
+  sfm.def("SevenPointFundamentalMatrix", [](const std::vector<Vec>& a, const std::vector<Vec>& b) {
+    if (a.size() != 7 || b.size() != 7) throw std::invalid_argument("exactly 7 correspondences are required");   // CHECK_EQ in the reference
+    const std::vector<double> x1 = Points2(a, 7), x2 = Points2(b, 7);
+    double c[28], F[27]; int32_t n = 0;
+    for (int i = 0; i < 7; ++i) { c[4 * i] = x1[2 * i]; c[4 * i + 1] = x1[2 * i + 1]; c[4 * i + 2] = x2[2 * i]; c[4 * i + 3] = x2[2 * i + 1]; }
+    Check(thb_seven_point_fundamental_matrix(c, 1, F, &n, nullptr));
+    std::vector<Vec> out;
+    for (int k = 0; k < n; ++k) out.push_back(MakeMat(F + 9 * k, 3, 3));
+    return py::make_tuple(n > 0, out);
+  });
+  sfm.def("PoseFromThreePoints", [](const std::vector<Vec>& feats, const std::vector<Vec>& world) {
+    if (feats.size() != 3 || world.size() != 3) throw std::invalid_argument("exactly 3 correspondences are required");
+    const std::vector<double> f = Points2(feats, 3);
+    double w[9], R[36], t[12]; int32_t n = 0;
+    for (int i = 0; i < 3; ++i) CopyVec(world[i], w + 3 * i, 3, "world point");
+    Check(thb_p3p(f.data(), w, 1, R, t, &n, nullptr));
+    std::vector<Vec> Rs, ts;
+    for (int k = 0; k < n; ++k) { Rs.push_back(MakeMat(R + 9 * k, 3, 3)); ts.push_back(MakeVec(t + 3 * k, 3)); }
+    return py::make_tuple(n > 0, Rs, ts);
+  });
+}

@@ -15,7 +15,7 @@
 
 namespace thb {
 
-__host__ __device__ __forceinline__ int num_intrinsics(int model) {
+THB_HD int num_intrinsics(int model) {
   switch (model) {
     case THB_MODEL_PINHOLE: return 7;
     case THB_MODEL_FISHEYE: return 9;
@@ -29,13 +29,13 @@ __host__ __device__ __forceinline__ int num_intrinsics(int model) {
 
 // [f, a, s, cx, cy] tail shared by the models with skew.
 template <typename TK, typename T>
-__device__ __forceinline__ void apply_fasc(const TK* K, const T& dx, const T& dy, T pix[2]) {
+THB_HD void apply_fasc(const TK* K, const T& dx, const T& dy, T pix[2]) {
   pix[0] = K[0] * dx + K[2] * dy + K[3];
   pix[1] = (K[0] * K[1]) * dy + K[4];
 }
 
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_pinhole(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_pinhole(const TK* K, const T p[3], T pix[2]) {
   const T iz = 1.0 / p[2];
   const T nx = p[0] * iz, ny = p[1] * iz;
   const T r2 = nx * nx + ny * ny;
@@ -45,7 +45,7 @@ __device__ __forceinline__ bool project_pinhole(const TK* K, const T p[3], T pix
 }
 
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_double_sphere(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_double_sphere(const TK* K, const T p[3], T pix[2]) {
   const TK xi = K[5], alpha = K[6];
   const T r2 = p[0] * p[0] + p[1] * p[1];
   const T d1 = d_sqrt(T(r2 + p[2] * p[2]));
@@ -61,7 +61,7 @@ __device__ __forceinline__ bool project_double_sphere(const TK* K, const T p[3],
 }
 
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_extended_unified(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_extended_unified(const TK* K, const T p[3], T pix[2]) {
   const TK alpha = K[5], beta = K[6];
   const T r2 = p[0] * p[0] + p[1] * p[1];
   const T rho = d_sqrt(T(beta * r2 + p[2] * p[2]));
@@ -83,7 +83,7 @@ __device__ __forceinline__ bool project_extended_unified(const TK* K, const T p[
 }
 
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_fisheye(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_fisheye(const TK* K, const T p[3], T pix[2]) {
   const T r2 = p[0] * p[0] + p[1] * p[1];
   if (val(r2) < 1e-8) {
     apply_fasc(K, p[0], p[1], pix);
@@ -102,7 +102,7 @@ __device__ __forceinline__ bool project_fisheye(const TK* K, const T p[3], T pix
 
 // K = [f, a, cx, cy, omega]
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_fov(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_fov(const TK* K, const T p[3], T pix[2]) {
   const T iz = 1.0 / p[2];
   const T nx = p[0] * iz, ny = p[1] * iz;
   const TK omega = K[4];
@@ -124,7 +124,7 @@ __device__ __forceinline__ bool project_fov(const TK* K, const T p[3], T pix[2])
 
 // K = [f, a, cx, cy, k]; focal length applied before the distortion.
 template <typename TK, typename T>
-__device__ __forceinline__ bool project_division(const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project_division(const TK* K, const T p[3], T pix[2]) {
   const T iz = 1.0 / p[2];
   const T ux = K[0] * (p[0] * iz), uy = (K[0] * K[1]) * (p[1] * iz);
   const T r2 = ux * ux + uy * uy;
@@ -145,7 +145,7 @@ __device__ __forceinline__ bool project_division(const TK* K, const T p[3], T pi
 // MODEL >= 0: compile-time model (single-model reconstructions, no switch in the kernel).
 // MODEL == -1: run-time dispatch on `model` (mixed intrinsics groups).
 template <int MODEL, typename TK, typename T>
-__device__ __forceinline__ bool project(int model, const TK* K, const T p[3], T pix[2]) {
+THB_HD bool project(int model, const TK* K, const T p[3], T pix[2]) {
   if (MODEL >= 0) model = MODEL;
   switch (model) {
     case THB_MODEL_PINHOLE: return project_pinhole(K, p, pix);

@@ -2,16 +2,26 @@
 #ifndef THB_COMMON_CUH_
 #define THB_COMMON_CUH_
 
-#include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
 #include <cstdio>
 #include <string>
 
 #include "../../include/theia_b200.h"
 
+// The per-element camera math (Dual numbers, project_*) is plain C++: under nvcc it is __host__ __device__, and the
+// host adapter (csrc/adapter/pt_module.cc, compiled by g++) includes the same headers for Camera::ProjectPoint.
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define THB_HD __host__ __device__ __forceinline__
+#else
+#define THB_HD inline
+#endif
+
 namespace thb {
 
+#if defined(__CUDACC__)
 // thread-local error text behind thb_last_error()
 void SetLastError(const std::string& s);
 const char* GetLastError();
@@ -33,6 +43,8 @@ const char* GetLastError();
     return (code);                   \
   } while (0)
 
+#endif  // __CUDACC__
+
 constexpr int KS = THB_INTR_STRIDE;
 
 // Forward-mode dual number with N tangent directions, fully unrolled into registers.
@@ -40,81 +52,82 @@ template <int N>
 struct Dual {
   double a;
   double v[N];
-  __device__ __forceinline__ Dual() {}
-  __device__ __forceinline__ Dual(double s) : a(s) {  // NOLINT
+  THB_HD Dual() {}
+  THB_HD Dual(double s) : a(s) {  // NOLINT
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = 0.0;
   }
 };
 
-template <int N> __device__ __forceinline__ Dual<N> seed(double s, int k) {
+template <int N> THB_HD Dual<N> seed(double s, int k) {
   Dual<N> d(s);
 #pragma unroll
   for (int i = 0; i < N; ++i) d.v[i] = (i == k) ? 1.0 : 0.0;
   return d;
 }
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N>& f, const Dual<N>& g) {
+template <int N> THB_HD Dual<N> operator+(const Dual<N>& f, const Dual<N>& g) {
   Dual<N> h; h.a = f.a + g.a;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = f.v[i] + g.v[i];
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N>& f, const Dual<N>& g) {
+template <int N> THB_HD Dual<N> operator-(const Dual<N>& f, const Dual<N>& g) {
   Dual<N> h; h.a = f.a - g.a;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = f.v[i] - g.v[i];
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N>& f) {
+template <int N> THB_HD Dual<N> operator-(const Dual<N>& f) {
   Dual<N> h; h.a = -f.a;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = -f.v[i];
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N>& f, const Dual<N>& g) {
+template <int N> THB_HD Dual<N> operator*(const Dual<N>& f, const Dual<N>& g) {
   Dual<N> h; h.a = f.a * g.a;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = f.a * g.v[i] + f.v[i] * g.a;
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& f, const Dual<N>& g) {
+template <int N> THB_HD Dual<N> operator/(const Dual<N>& f, const Dual<N>& g) {
   Dual<N> h; const double gi = 1.0 / g.a; h.a = f.a * gi;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - h.a * g.v[i]) * gi;
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(const Dual<N>& f, double s) { Dual<N> h = f; h.a += s; return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator+(double s, const Dual<N>& f) { Dual<N> h = f; h.a += s; return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(const Dual<N>& f, double s) { Dual<N> h = f; h.a -= s; return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator-(double s, const Dual<N>& f) { Dual<N> h = -f; h.a += s; return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(const Dual<N>& f, double s) {
+template <int N> THB_HD Dual<N> operator+(const Dual<N>& f, double s) { Dual<N> h = f; h.a += s; return h; }
+template <int N> THB_HD Dual<N> operator+(double s, const Dual<N>& f) { Dual<N> h = f; h.a += s; return h; }
+template <int N> THB_HD Dual<N> operator-(const Dual<N>& f, double s) { Dual<N> h = f; h.a -= s; return h; }
+template <int N> THB_HD Dual<N> operator-(double s, const Dual<N>& f) { Dual<N> h = -f; h.a += s; return h; }
+template <int N> THB_HD Dual<N> operator*(const Dual<N>& f, double s) {
   Dual<N> h; h.a = f.a * s;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * s;
   return h; }
-template <int N> __device__ __forceinline__ Dual<N> operator*(double s, const Dual<N>& f) { return f * s; }
-template <int N> __device__ __forceinline__ Dual<N> operator/(const Dual<N>& f, double s) { return f * (1.0 / s); }
-template <int N> __device__ __forceinline__ Dual<N> operator/(double s, const Dual<N>& g) { return Dual<N>(s) / g; }
+template <int N> THB_HD Dual<N> operator*(double s, const Dual<N>& f) { return f * s; }
+template <int N> THB_HD Dual<N> operator/(const Dual<N>& f, double s) { return f * (1.0 / s); }
+template <int N> THB_HD Dual<N> operator/(double s, const Dual<N>& g) { return Dual<N>(s) / g; }
 
-template <int N> __device__ __forceinline__ Dual<N> chain(const Dual<N>& f, double val, double dval) {
+template <int N> THB_HD Dual<N> chain(const Dual<N>& f, double val, double dval) {
   Dual<N> h; h.a = val;
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = dval * f.v[i];
   return h; }
 
-__device__ __forceinline__ double val(double x) { return x; }
-template <int N> __device__ __forceinline__ double val(const Dual<N>& f) { return f.a; }
+THB_HD double val(double x) { return x; }
+template <int N> THB_HD double val(const Dual<N>& f) { return f.a; }
 
-__device__ __forceinline__ double d_sqrt(double x) { return sqrt(x); }
-__device__ __forceinline__ double d_tan(double x) { return tan(x); }
-__device__ __forceinline__ double d_atan(double x) { return atan(x); }
-__device__ __forceinline__ double d_abs(double x) { return fabs(x); }
-__device__ __forceinline__ double d_atan2(double y, double x) { return atan2(y, x); }
-template <int N> __device__ __forceinline__ Dual<N> d_sqrt(const Dual<N>& f) { const double s = sqrt(f.a); return chain(f, s, 0.5 / s); }
-template <int N> __device__ __forceinline__ Dual<N> d_tan(const Dual<N>& f) { const double t = tan(f.a); return chain(f, t, 1.0 + t * t); }
-template <int N> __device__ __forceinline__ Dual<N> d_atan(const Dual<N>& f) { return chain(f, atan(f.a), 1.0 / (1.0 + f.a * f.a)); }
-template <int N> __device__ __forceinline__ Dual<N> d_abs(const Dual<N>& f) { return chain(f, fabs(f.a), copysign(1.0, f.a)); }
-template <int N> __device__ __forceinline__ Dual<N> d_atan2(const Dual<N>& y, const Dual<N>& x) {
+THB_HD double d_sqrt(double x) { return sqrt(x); }
+THB_HD double d_tan(double x) { return tan(x); }
+THB_HD double d_atan(double x) { return atan(x); }
+THB_HD double d_abs(double x) { return fabs(x); }
+THB_HD double d_atan2(double y, double x) { return atan2(y, x); }
+template <int N> THB_HD Dual<N> d_sqrt(const Dual<N>& f) { const double s = sqrt(f.a); return chain(f, s, 0.5 / s); }
+template <int N> THB_HD Dual<N> d_tan(const Dual<N>& f) { const double t = tan(f.a); return chain(f, t, 1.0 + t * t); }
+template <int N> THB_HD Dual<N> d_atan(const Dual<N>& f) { return chain(f, atan(f.a), 1.0 / (1.0 + f.a * f.a)); }
+template <int N> THB_HD Dual<N> d_abs(const Dual<N>& f) { return chain(f, fabs(f.a), copysign(1.0, f.a)); }
+template <int N> THB_HD Dual<N> d_atan2(const Dual<N>& y, const Dual<N>& x) {
   Dual<N> h; const double t = 1.0 / (x.a * x.a + y.a * y.a); h.a = atan2(y.a, x.a);
 #pragma unroll
   for (int i = 0; i < N; ++i) h.v[i] = t * (x.a * y.v[i] - y.a * x.v[i]);
   return h; }
 
+#if defined(__CUDACC__)
 // Block-wide sum of one double; result valid in thread 0. blockDim.x multiple of 32, <= 1024.
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -138,6 +151,8 @@ __device__ __forceinline__ double block_sum(double v, double* smem32) {
   }
   return v;
 }
+
+#endif  // __CUDACC__
 
 }  // namespace thb
 #endif  // THB_COMMON_CUH_

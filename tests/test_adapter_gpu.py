@@ -1,0 +1,189 @@
+"""The reference's own Python tests, re-run through the drop-in adapter (`import pytheiasfm_b200 as pt`):
+pytests/sfm/bundle_adjuster_test.py:6-26, pytests/sfm/random_recon_gen.py (scene generator),
+pytests/sfm/two_view_pose_test.py:96-111 and pytests/sfm/absolute_pose_estimator_test.py:11-24 — same calls,
+same argument orders, same assertions. GPU only (the adapter has no CPU path)."""
+import numpy as np
+import pytest
+
+import pytheiasfm_b200 as pt
+
+pytestmark = pytest.mark.gpu
+
+
+class RandomReconGenerator:
+    """random_recon_gen.py:27-176 with the Camera set up directly (CameraIntrinsicsPrior is not on the hot path)."""
+
+    def __init__(self, seed=42):
+        np.random.seed(seed)
+        self.recon = pt.sfm.Reconstruction()
+        self.camera = pt.sfm.Camera()
+        self.camera.SetFocalLength(900.0)
+        self.camera.SetPrincipalPoint(720, 540)
+        self.camera.SetImageSize(1440, 1080)
+
+    def generate_random_recon(self, nr_views=10, nr_tracks=100, pt3_xyz_min=(-4, -4, 0), pt3_xyz_max=(4, 4, 6),
+                              cam_xyz_min=(-6, -6, -1), cam_xyz_max=(6, 6, -10), pixel_noise=0.0):
+        P = np.random.uniform(pt3_xyz_min, pt3_xyz_max, size=(nr_tracks, 3))
+        for i in range(nr_tracks):
+            tid = self.recon.AddTrack()
+            track = self.recon.MutableTrack(tid)
+            track.SetPoint(np.append(P[i], 1.0))
+            track.SetIsEstimated(True)
+        Cw = np.random.uniform(cam_xyz_min, cam_xyz_max, size=(nr_views, 3))
+        ax = np.random.uniform(-0.2, 0.1, size=(nr_views, 3))
+        ang = np.random.uniform(-np.pi / 4, np.pi / 4, size=nr_views)
+        for i in range(nr_views):
+            vid = self.recon.AddView(str(i), 0, i)
+            view = self.recon.View(vid)
+            cam = view.MutableCamera()
+            cam.DeepCopy(self.camera)
+            cam.SetPosition(Cw[i])
+            cam.SetOrientationFromAngleAxis(ang[i] * ax[i] / np.linalg.norm(ax[i]))
+            view.SetIsEstimated(True)
+        for tid in self.recon.TrackIds():
+            pt3d = self.recon.Track(tid).Point()
+            for vid in self.recon.ViewIds():
+                cam = self.recon.View(vid).Camera()
+                depth, pix = cam.ProjectPoint(pt3d)
+                if depth <= 0 or pix[0] < 0 or pix[0] > 1440 or pix[1] < 0 or pix[1] > 1080:
+                    continue
+                self.recon.AddObservation(vid, tid, pt.sfm.Feature(pix + np.random.randn(2) * pixel_noise))
+        return self.recon
+
+    def add_noise_to_views(self, noise_pos=1e-5, noise_angle=1e-2):
+        for vid in self.recon.ViewIds():
+            cam = self.recon.View(vid).MutableCamera()
+            cam.SetPosition(cam.GetPosition() + noise_pos * np.random.randn(3))
+            cam.SetOrientationFromAngleAxis(cam.GetOrientationAsAngleAxis() + noise_angle * np.pi / 180.0 * np.random.randn(3))
+
+    def add_noise_to_tracks(self, noise_track=1e-5):
+        for tid in self.recon.TrackIds():
+            p = self.recon.Track(tid).Point()
+            self.recon.MutableTrack(tid).SetPoint(np.append(p[:3] / p[3] + noise_track * np.random.randn(3), 1.0))
+
+
+@pytest.fixture
+def gen():
+    g = RandomReconGenerator(seed=42)
+    g.generate_random_recon(nr_views=10, nr_tracks=100)
+    return g
+
+
+@pytest.fixture
+def ba_options():
+    return pt.sfm.BundleAdjustmentOptions()
+
+
+def test_BundleAdjustView(gen, ba_options):
+    """bundle_adjuster_test.py:6-15"""
+    for vid in gen.recon.ViewIds():
+        orig_pos = gen.recon.View(vid).Camera().GetPosition()
+        gen.add_noise_to_views(noise_pos=1e-3, noise_angle=1e-1)
+        result = pt.sfm.BundleAdjustView(gen.recon, ba_options, vid)
+        dist_pos = np.linalg.norm(orig_pos - gen.recon.View(vid).Camera().GetPosition())
+        assert dist_pos < 1e-4
+        assert result.success
+
+
+def test_BundleAdjustTrack(gen, ba_options):
+    """bundle_adjuster_test.py:17-22"""
+    gen.add_noise_to_tracks(noise_track=1e-3)
+    for t_id in gen.recon.TrackIds():
+        if gen.recon.Track(t_id).NumViews() < 2:
+            continue
+        truth = gen.recon.Track(t_id).Point()
+        result = pt.sfm.BundleAdjustTrack(gen.recon, ba_options, t_id)
+        assert result.success
+        assert result.final_cost <= result.initial_cost + 1e-12
+        assert gen.recon.Track(t_id).InverseDepth() != 0.0   # UpdateInverseDepth side effect (bundle_adjustment.cc:69-83)
+
+
+def test_BundleAdjustReconstruction_full_and_partial(gen, ba_options):
+    """pyexamples/sfm_pipeline_*.py usage: pt.sfm.BundleAdjustReconstruction(opts, recon) with HUBER loss."""
+    gen.add_noise_to_views(noise_pos=1e-2, noise_angle=0.5)
+    gen.add_noise_to_tracks(noise_track=1e-2)
+    ba_options.use_inner_iterations = False       # the only supported setting; True is rejected loudly (below)
+    ba_options.loss_function_type = pt.sfm.LossFunctionType.HUBER
+    ba_options.robust_loss_width = 2.0
+    result = pt.sfm.BundleAdjustReconstruction(ba_options, gen.recon)
+    assert result.success and result.final_cost < 1e-6 * result.initial_cost + 1e-9
+    # partial: half of the views, all tracks
+    views = gen.recon.ViewIds()[:5]
+    before = {v: gen.recon.View(v).Camera().GetPosition() for v in gen.recon.ViewIds()}
+    gen.add_noise_to_tracks(noise_track=1e-2)
+    result = pt.sfm.BundleAdjustPartialReconstruction(ba_options, views, gen.recon.TrackIds(), gen.recon)
+    assert result.success
+    for v in gen.recon.ViewIds()[5:]:                # views outside the set keep their extrinsics (bundle_adjuster.cc:199-204)
+        np.testing.assert_array_equal(gen.recon.View(v).Camera().GetPosition(), before[v])
+    ba_options.use_inner_iterations = True
+    with pytest.raises(RuntimeError, match="inner"):
+        pt.sfm.BundleAdjustReconstruction(ba_options, gen.recon)
+
+
+def _two_view_corrs(n=300, outliers=0.3, noise=1e-3, seed=65):
+    rng = np.random.default_rng(seed)
+    ang = np.deg2rad(10.0)
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    c = np.array([1.0, 0.2, 0.1]); c /= np.linalg.norm(c)
+    X = np.stack([rng.uniform(-3, 3, n), rng.uniform(-3, 3, n), rng.uniform(4, 10, n)], -1)
+    x1 = X[:, :2] / X[:, 2:]; Xc = (X - c) @ R.T; x2 = Xc[:, :2] / Xc[:, 2:]
+    x1 += rng.normal(0, noise, x1.shape); x2 += rng.normal(0, noise, x2.shape)
+    k = int(outliers * n)
+    x2[:k] = rng.uniform(-1, 1, (k, 2))
+    corrs = [pt.matching.FeatureCorrespondence(pt.sfm.Feature(a), pt.sfm.Feature(b)) for a, b in zip(x1, x2)]
+    return corrs, R, c
+
+
+def test_EstimateRelativePose():
+    """two_view_pose_test.py:96-111: (success, pose, summary) and the translation direction within tolerance."""
+    corrs, R, c = _two_view_corrs()
+    params = pt.solvers.RansacParameters()
+    params.error_thresh = (2e-3) ** 2; params.failure_probability = 1e-4; params.min_iterations = 10; params.max_iterations = 1000
+    params.use_mle = True; params.seed = 7
+    success, pose, summary = pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)
+    assert success
+    assert np.rad2deg(np.arccos(np.clip(pose.position @ c, -1, 1))) < 5.0
+    assert np.rad2deg(np.arccos(np.clip((np.trace(pose.rotation @ R.T) - 1) / 2, -1, 1))) < 1.0
+    assert len(summary.inliers) > 150 and summary.num_input_data_points == 300 and summary.confidence > 0.99
+    again = pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)   # the seed field makes it reproducible
+    assert again[2].inliers == summary.inliers and again[2].num_iterations == summary.num_iterations
+    params.use_lo = True
+    with pytest.raises(RuntimeError, match="use_lo"):
+        pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)
+
+
+def test_PoseFromThreePoints_and_EstimateCalibratedAbsolutePose():
+    """absolute_pose_estimator_test.py:11-24 (P3P on 3 points) and the RANSAC estimator with PnPType.KNEIP."""
+    rng = np.random.default_rng(3)
+    ang = np.deg2rad(15.0)
+    R = np.array([[1, 0, 0], [0, np.cos(ang), -np.sin(ang)], [0, np.sin(ang), np.cos(ang)]])
+    c = np.array([0.3, -0.4, 0.2])
+    Xc = np.stack([rng.uniform(-2, 2, 200), rng.uniform(-2, 2, 200), rng.uniform(3, 8, 200)], -1)
+    X = Xc @ R + c
+    x = Xc[:, :2] / Xc[:, 2:]
+    ok, Rs, ts = pt.sfm.PoseFromThreePoints([x[0], x[1], x[2]], [X[0], X[1], X[2]])
+    assert ok and len(Rs) == 4
+    assert min(np.abs(Rk - R).max() + np.abs(tk + R @ c).max() for Rk, tk in zip(Rs, ts)) < 1e-8
+    x[:40] = rng.uniform(-1, 1, (40, 2))
+    corrs = [pt.sfm.FeatureCorrespondence2D3D(a, b) for a, b in zip(x, X)]
+    params = pt.solvers.RansacParameters(); params.error_thresh = 1e-6; params.seed = 11
+    success, pose, summary = pt.sfm.EstimateCalibratedAbsolutePose(params, pt.sfm.RansacType.RANSAC, pt.sfm.PnPType.KNEIP, corrs)
+    assert success and np.abs(pose.rotation - R).max() < 1e-6 and np.abs(pose.position - c).max() < 1e-6
+    assert len(summary.inliers) >= 160
+    with pytest.raises(RuntimeError, match="KNEIP"):
+        pt.sfm.EstimateCalibratedAbsolutePose(params, pt.sfm.RansacType.RANSAC, pt.sfm.PnPType.DLS, corrs)
+
+
+def test_minimal_solver_bindings():
+    """pose_wrapper.cc return conventions: (success, [E...]), (success, H), (success, [F...])."""
+    corrs, R, c = _two_view_corrs(n=7, outliers=0.0, noise=0.0)
+    x1 = [cc.feature1.point for cc in corrs]; x2 = [cc.feature2.point for cc in corrs]
+    ok, Es = pt.sfm.FivePointRelativePose(x1[:5], x2[:5])
+    assert ok and 1 <= len(Es) <= 10 and Es[0].shape == (3, 3)
+    t = -R @ c
+    E_gt = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+    assert min(min(np.abs(E / np.linalg.norm(E) - s * E_gt / np.linalg.norm(E_gt)).max() for s in (1, -1)) for E in Es) < 1e-6
+    ok, H = pt.sfm.FourPointHomography(x1[:4], x2[:4])
+    assert ok and H.shape == (3, 3)
+    ok, Fs = pt.sfm.SevenPointFundamentalMatrix(x1, x2)
+    assert ok and 1 <= len(Fs) <= 3
