@@ -7,7 +7,13 @@
 namespace thb {
 
 // indices into the per-iteration device scalar block
-enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_MCC = 2, SC_STEP2 = 3, SC_XNEW2 = 4, SC_GRADMAX = 5, SC_COUNT = 8 };
+enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_STEP2 = 2, SC_XNEW2 = 3, SC_GTD = 4, SC_MCC = 5, SC_GRADMAX = 6, SC_COUNT = 8 };
+
+// Variable intrinsics blocks sit behind the camera blocks in the reduced system: block `slot` occupies the NI indices
+// from 6*nc + NI*slot. Coordinates that are constant (SubsetManifold, bundle_adjuster.cc:429-441) or beyond the model's
+// parameter count keep zero Jacobian columns and a unit diagonal, so their step is exactly zero.
+constexpr int NI = 9;
+constexpr int MAX_VG = 8;
 enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 };
 
 // ---------------------------------------------------------------------------------------------
@@ -377,12 +383,14 @@ __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __rest
   }
 }
 
-// K5a: back-substitution per point, y_p = V^-1 (g_p - sum_i W_i^T y_ci), and the model cost change
-// -(J step)^T (r + J step / 2) with step = -y. One thread per point.
-template <int PD>
-__global__ void __launch_bounds__(128) k_backsub(int np, int no, const int* __restrict__ pt_start, const int* __restrict__ o_cam,
+// K5a: back-substitution per point, y_p = V^-1 (g_p - sum_i Jp_i^T (Jc_i y_ci + Ji_i y_si)), and the model cost change
+// -(J step)^T (r + J step / 2) with step = -y. One thread per point. NK > 0: variable intrinsics blocks exist.
+template <int PD, int NK>
+__global__ void __launch_bounds__(128) k_backsub(int np, int no, int nc, const int* __restrict__ pt_start, const int* __restrict__ o_cam,
+                                                 const int8_t* __restrict__ o_slot,
                                                  const double* __restrict__ r_pl, const double* __restrict__ jc_pl,
-                                                 const double* __restrict__ jp_pl, const double* __restrict__ vinv,
+                                                 const double* __restrict__ jp_pl, const double* __restrict__ ji_pl,
+                                                 const double* __restrict__ vinv,
                                                  const double* __restrict__ gp, const double* __restrict__ yred,
                                                  double* __restrict__ yp, double* __restrict__ scal) {
   __shared__ double red[32];
@@ -399,6 +407,13 @@ __global__ void __launch_bounds__(128) k_backsub(int np, int no, const int* __re
       double jy0 = 0.0, jy1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) { const double y = yred[6 * c + k]; jy0 += jc_pl[k * n + q] * y; jy1 += jc_pl[(6 + k) * n + q] * y; }
+      if (NK > 0) {
+        const int sl = o_slot[q];
+        if (sl >= 0) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) { const double y = yred[6 * nc + NK * sl + k]; jy0 += ji_pl[k * n + q] * y; jy1 += ji_pl[(NK + k) * n + q] * y; }
+        }
+      }
 #pragma unroll
       for (int a = 0; a < PD; ++a) b[a] -= jp_pl[a * n + q] * jy0 + jp_pl[(PD + a) * n + q] * jy1;
     }
@@ -416,6 +431,13 @@ __global__ void __launch_bounds__(128) k_backsub(int np, int no, const int* __re
       double m0 = 0.0, m1 = 0.0;
 #pragma unroll
       for (int k = 0; k < 6; ++k) { const double yc = yred[6 * c + k]; m0 += jc_pl[k * n + q] * yc; m1 += jc_pl[(6 + k) * n + q] * yc; }
+      if (NK > 0) {
+        const int sl = o_slot[q];
+        if (sl >= 0) {
+#pragma unroll
+          for (int k = 0; k < NK; ++k) { const double yi = yred[6 * nc + NK * sl + k]; m0 += ji_pl[k * n + q] * yi; m1 += ji_pl[(NK + k) * n + q] * yi; }
+        }
+      }
 #pragma unroll
       for (int a = 0; a < PD; ++a) { m0 += jp_pl[a * n + q] * y[a]; m1 += jp_pl[(PD + a) * n + q] * y[a]; }
       m0 = -m0; m1 = -m1;  // J * step, step = -y
@@ -426,38 +448,63 @@ __global__ void __launch_bounds__(128) k_backsub(int np, int no, const int* __re
   if (threadIdx.x == 0) atomicAdd(scal + SC_MCC, mcc);
 }
 
-// K5b: candidate = Plus(x, delta), delta = -scale * y. Cameras: SubsetManifold semantics (constant
+// Manifold Plus of a point block: SphereManifold<4> (PD == 3) or Euclidean (PD == 4).
+template <int PD>
+__device__ __forceinline__ void point_plus(const double x[4], const double d[PD], double o[4]) {
+  if (PD == 3) {
+    o[0] = x[0]; o[1] = x[1]; o[2] = x[2]; o[3] = x[3];
+    const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    if (nd != 0.0) {
+      double v[3], beta;
+      householder4(x, v, &beta);
+      const double sbd = sin(nd) / nd;
+      const double y[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cos(nd)};
+      const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + y[3];
+      const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
+      o[0] = nx * (y[0] - v[0] * (beta * vty));
+      o[1] = nx * (y[1] - v[1] * (beta * vty));
+      o[2] = nx * (y[2] - v[2] * (beta * vty));
+      o[3] = nx * (y[3] - (beta * vty));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = x[k] + d[k < PD ? k : 0];
+  }
+}
+
+// K5b: candidate = Plus(x, alpha * delta), delta = -scale * y. Cameras: SubsetManifold semantics (constant
 // coordinates have zero Jacobian columns, hence y = 0). Accumulates |x - x_new|^2 and |x_new|^2 over the
-// non-constant blocks (TrustRegionMinimizer::ParameterToleranceReached).
+// non-constant blocks (TrustRegionMinimizer::ParameterToleranceReached) and gradient . delta (line search).
 __global__ void k_update_cams(int nc, const uint8_t* __restrict__ cam_const,
-                              const double* __restrict__ cam, const double* __restrict__ yred,
-                              const double* __restrict__ cs, double* __restrict__ cam_new, double* __restrict__ scal) {
+                              const double* __restrict__ cam, const double* __restrict__ yred, const double* __restrict__ braw,
+                              const double* __restrict__ cs, double alpha, double* __restrict__ cam_new, double* __restrict__ scal) {
   __shared__ double red[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  double s2 = 0.0, x2 = 0.0;
+  double s2 = 0.0, x2 = 0.0, gd = 0.0;
   if (c < nc) {
     const bool variable = cam_const[c] != THB_CAM_CONST_ALL;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const double o = cam[6 * c + k];
-      const double d = variable ? -yred[6 * c + k] * cs[6 * c + k] : 0.0;
+      const double d = variable ? (-yred[6 * c + k] * cs[6 * c + k]) * alpha : 0.0;
       const double v = o + d;
       cam_new[6 * c + k] = v;
-      if (variable) { s2 += (v - o) * (v - o); x2 += v * v; }
+      if (variable) { s2 += (v - o) * (v - o); x2 += v * v; gd -= braw[6 * c + k] * yred[6 * c + k]; }
     }
   }
   s2 = block_sum(s2, red);
   x2 = block_sum(x2, red);
-  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); }
+  gd = block_sum(gd, red);
+  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); atomicAdd(scal + SC_GTD, gd); }
 }
 
 template <int PD>
 __global__ void k_update_pts(int np, const uint8_t* __restrict__ pt_const, const double* __restrict__ pts,
-                             const double* __restrict__ yp, const double* __restrict__ ps,
+                             const double* __restrict__ yp, const double* __restrict__ gp, const double* __restrict__ ps, double alpha,
                              double* __restrict__ pts_new, double* __restrict__ scal) {
   __shared__ double red[32];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  double s2 = 0.0, x2 = 0.0;
+  double s2 = 0.0, x2 = 0.0, gd = 0.0;
   if (p < np) {
     const double4 X4 = *reinterpret_cast<const double4*>(pts + (size_t)p * 4);
     const double x[4] = {X4.x, X4.y, X4.z, X4.w};
@@ -466,26 +513,11 @@ __global__ void k_update_pts(int np, const uint8_t* __restrict__ pt_const, const
     if (variable) {
       double d[PD];
 #pragma unroll
-      for (int k = 0; k < PD; ++k) d[k] = -yp[(size_t)p * PD + k] * ps[(size_t)p * PD + k];
-      if (PD == 3) {
-        // ceres SphereManifold<4>::Plus
-        const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        if (nd != 0.0) {
-          double v[3], beta;
-          householder4(x, v, &beta);
-          const double sbd = sin(nd) / nd;
-          const double y[4] = {sbd * d[0], sbd * d[1], sbd * d[2], cos(nd)};
-          const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2] + y[3];
-          const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
-          o[0] = nx * (y[0] - v[0] * (beta * vty));
-          o[1] = nx * (y[1] - v[1] * (beta * vty));
-          o[2] = nx * (y[2] - v[2] * (beta * vty));
-          o[3] = nx * (y[3] - (beta * vty));
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) o[k] = x[k] + d[k < PD ? k : 0];
+      for (int k = 0; k < PD; ++k) {
+        d[k] = (-yp[(size_t)p * PD + k] * ps[(size_t)p * PD + k]) * alpha;
+        gd -= gp[(size_t)p * PD + k] * yp[(size_t)p * PD + k];
       }
+      point_plus<PD>(x, d, o);
 #pragma unroll
       for (int k = 0; k < 4; ++k) { s2 += (o[k] - x[k]) * (o[k] - x[k]); x2 += o[k] * o[k]; }
     }
@@ -493,7 +525,33 @@ __global__ void k_update_pts(int np, const uint8_t* __restrict__ pt_const, const
   }
   s2 = block_sum(s2, red);
   x2 = block_sum(x2, red);
-  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); }
+  gd = block_sum(gd, red);
+  if (threadIdx.x == 0) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); atomicAdd(scal + SC_GTD, gd); }
+}
+
+// Intrinsics blocks: Euclidean Plus on the free coordinates, then projection on the box constraints of
+// bundle_adjuster.cc:396-427 (ceres ParameterBlock::Plus). One thread per group; yred == nullptr projects only.
+__global__ void k_update_intr(int ng, int nc, const int* __restrict__ intr_slot, const int* __restrict__ intr_model,
+                              const double* __restrict__ intr, const double* __restrict__ yred, const double* __restrict__ braw,
+                              const double* __restrict__ cs, const double* __restrict__ lo, const double* __restrict__ hi,
+                              double alpha, double* __restrict__ intr_new, double* __restrict__ scal) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ng) return;
+  const int sl = intr_slot[g];
+  const int Kg = num_intrinsics(intr_model[g]);
+  double s2 = 0.0, x2 = 0.0, gd = 0.0;
+  for (int k = 0; k < KS; ++k) {
+    const double o = intr[(size_t)g * KS + k];
+    double v = o;
+    if (sl >= 0 && k < NI) {
+      const int idx = 6 * nc + NI * sl + k;
+      if (yred) { v = o + (-yred[idx] * cs[idx]) * alpha; gd -= braw[idx] * yred[idx]; }
+      v = fmin(fmax(v, lo[NI * sl + k]), hi[NI * sl + k]);
+      if (k < Kg) { s2 += (v - o) * (v - o); x2 += v * v; }
+    }
+    intr_new[(size_t)g * KS + k] = v;
+  }
+  if (sl >= 0 && scal) { atomicAdd(scal + SC_STEP2, s2); atomicAdd(scal + SC_XNEW2, x2); atomicAdd(scal + SC_GTD, gd); }
 }
 
 // max-norm of the (unscaled) gradient: g = (Js^T r) / scale
@@ -528,8 +586,9 @@ __global__ void k_flush_read(const double2* __restrict__ buf, size_t n, double* 
 }
 
 // x_norm^2 over the non-constant blocks of a state
-__global__ void k_xnorm(int nc, int np, const uint8_t* __restrict__ cam_const,
-                        const uint8_t* __restrict__ pt_const, const double* __restrict__ cam, const double* __restrict__ pts,
+__global__ void k_xnorm(int nc, int np, int ng, const uint8_t* __restrict__ cam_const,
+                        const uint8_t* __restrict__ pt_const, const int* __restrict__ intr_slot, const int* __restrict__ intr_model,
+                        const double* __restrict__ cam, const double* __restrict__ pts, const double* __restrict__ intr,
                         double* __restrict__ out) {
   __shared__ double red[32];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -540,9 +599,268 @@ __global__ void k_xnorm(int nc, int np, const uint8_t* __restrict__ cam_const,
   } else if (i - nc < np) {
     const int p = i - nc;
     if (!pt_const[p]) for (int k = 0; k < 4; ++k) s += pts[(size_t)p * 4 + k] * pts[(size_t)p * 4 + k];
+  } else if (i - nc - np < ng) {
+    const int g = i - nc - np;
+    if (intr_slot[g] >= 0) for (int k = 0; k < num_intrinsics(intr_model[g]); ++k) s += intr[(size_t)g * KS + k] * intr[(size_t)g * KS + k];
   }
   s = block_sum(s, red);
   if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variable (shared) intrinsics blocks — CameraIntrinsicsGroup parameter vectors shared by all views of the group
+// (reconstruction.cc:129-140), Schur group 1 (bundle_adjuster.cc:547-577). With E_p the point's rows of J_red^T J_p, the
+// row block of an intrinsics slot s is Z_{p,s} = sum_{i in obs(p), slot(i)=s} Ji_i^T Jp_i, and T_{p,s} = Z_{p,s} V_p^-1.
+// ZT layout: [np][nvg][2][NI*PD] (Z then T), one contiguous record per (point, slot).
+
+// K2c: Z and T per (point, slot); rhs_s -= T g_p. grid (ceil(np/128), nvg).
+template <int PD>
+__global__ void __launch_bounds__(128) k_intr_point(int np, int no, int nvg, int base, const int* __restrict__ pt_start,
+                                                    const int8_t* __restrict__ o_slot, const double* __restrict__ jp_pl,
+                                                    const double* __restrict__ ji_pl, const double* __restrict__ vinv,
+                                                    const double* __restrict__ gp, double* __restrict__ ZT,
+                                                    double* __restrict__ rhs) {
+  __shared__ double red[32];
+  const int s = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  double tg[NI];
+#pragma unroll
+  for (int k = 0; k < NI; ++k) tg[k] = 0.0;
+  if (p < np) {
+    const size_t n = no;
+    double z[NI][PD];
+#pragma unroll
+    for (int k = 0; k < NI; ++k)
+#pragma unroll
+      for (int t = 0; t < PD; ++t) z[k][t] = 0.0;
+    for (int q = pt_start[p]; q < pt_start[p + 1]; ++q) {
+      if (o_slot[q] != s) continue;
+      double jp[2 * PD];
+#pragma unroll
+      for (int t = 0; t < 2 * PD; ++t) jp[t] = jp_pl[t * n + q];
+#pragma unroll
+      for (int k = 0; k < NI; ++k) {
+        const double j0 = ji_pl[k * n + q], j1 = ji_pl[(NI + k) * n + q];
+#pragma unroll
+        for (int t = 0; t < PD; ++t) z[k][t] += j0 * jp[t] + j1 * jp[PD + t];
+      }
+    }
+    double Vi[PD * PD], g[PD];
+#pragma unroll
+    for (int k = 0; k < PD * PD; ++k) Vi[k] = vinv[(size_t)p * PD * PD + k];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) g[k] = gp[(size_t)p * PD + k];
+    double* rec = ZT + ((size_t)p * nvg + s) * (2 * NI * PD);
+#pragma unroll
+    for (int k = 0; k < NI; ++k)
+#pragma unroll
+      for (int t = 0; t < PD; ++t) {
+        double v = 0.0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) v += z[k][u] * Vi[u * PD + t];
+        rec[k * PD + t] = z[k][t];
+        rec[NI * PD + k * PD + t] = v;
+        tg[k] += v * g[t];
+      }
+  }
+#pragma unroll
+  for (int k = 0; k < NI; ++k) {
+    const double v = block_sum(tg[k], red);
+    if (threadIdx.x == 0 && v != 0.0) atomicAdd(rhs + base + NI * s + k, -v);
+  }
+}
+
+// K2d: direct terms of an intrinsics block: U_ss = sum Ji^T Ji (lower), b_s = sum Ji^T r over the observations of the
+// slot. grid (G, nvg); coalesced plane reads, CTA reduction, then one atomic per CTA and entry.
+__global__ void __launch_bounds__(256) k_intr_direct(int no, int base, const int8_t* __restrict__ o_slot,
+                                                     const double* __restrict__ r_pl, const double* __restrict__ ji_pl,
+                                                     double* __restrict__ Smat, int ld, double* __restrict__ rhs,
+                                                     double* __restrict__ braw, double* __restrict__ cdiag) {
+  constexpr int NA = NI * (NI + 1) / 2 + NI;
+  __shared__ double red[8][NA];
+  const int s = blockIdx.y;
+  const size_t n = no;
+  double acc[NA];
+#pragma unroll
+  for (int k = 0; k < NA; ++k) acc[k] = 0.0;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < no; q += gridDim.x * blockDim.x) {
+    if (o_slot[q] != s) continue;
+    double j0[NI], j1[NI];
+#pragma unroll
+    for (int k = 0; k < NI; ++k) { j0[k] = ji_pl[k * n + q]; j1[k] = ji_pl[(NI + k) * n + q]; }
+    const double r0 = r_pl[q], r1 = r_pl[n + q];
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < NI; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) acc[k++] += j0[a] * j0[b] + j1[a] * j1[b];
+#pragma unroll
+    for (int a = 0; a < NI; ++a) acc[k++] += j0[a] * r0 + j1[a] * r1;
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NA; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NA) {
+    const int k = threadIdx.x;
+    double v = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += red[ww][k];
+    if (v != 0.0) {
+      constexpr int NL = NI * (NI + 1) / 2;
+      if (k < NL) {
+        int a = 0, b = k;
+        while (b > a) { b -= a + 1; ++a; }
+        atomicAdd(&Smat[(size_t)(base + NI * s + a) * ld + base + NI * s + b], v);
+        if (a == b) atomicAdd(cdiag + base + NI * s + a, v);
+      } else {
+        atomicAdd(braw + base + NI * s + (k - NL), v);
+        atomicAdd(rhs + base + NI * s + (k - NL), v);
+      }
+    }
+  }
+}
+
+// K3b: intrinsics-intrinsics Schur terms, S[s,s'] -= sum_p T_{p,s} Z_{p,s'}^T. grid (G, pairs s >= s', NI rows).
+template <int PD>
+__global__ void __launch_bounds__(256) k_intr_intr(int np, int nvg, int base, const double* __restrict__ ZT,
+                                                   double* __restrict__ Smat, int ld) {
+  __shared__ double red[8][NI];
+  int s = 0, s2 = blockIdx.y;
+  while (s2 > s) { s2 -= s + 1; ++s; }
+  const int a = blockIdx.z;
+  double acc[NI];
+#pragma unroll
+  for (int b = 0; b < NI; ++b) acc[b] = 0.0;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < np; p += gridDim.x * blockDim.x) {
+    const double* Ts = ZT + ((size_t)p * nvg + s) * (2 * NI * PD) + NI * PD + a * PD;
+    const double* Z2 = ZT + ((size_t)p * nvg + s2) * (2 * NI * PD);
+    double t[PD];
+#pragma unroll
+    for (int u = 0; u < PD; ++u) t[u] = Ts[u];
+#pragma unroll
+    for (int b = 0; b < NI; ++b)
+#pragma unroll
+      for (int u = 0; u < PD; ++u) acc[b] += t[u] * Z2[b * PD + u];
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int b = 0; b < NI; ++b) {
+    const double v = warp_sum(acc[b]);
+    if (lane == 0) red[w][b] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NI) {
+    const int b = threadIdx.x;
+    double v = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) v += red[ww][b];
+    if ((s > s2 || b <= a) && v != 0.0) atomicAdd(&Smat[(size_t)(base + NI * s + a) * ld + base + NI * s2 + b], -v);
+  }
+}
+
+// K3c: intrinsics-camera blocks, S[s,c] = sum_{i in obs(c)} ([slot(c)=s] Ji_i^T Jc_i - T_{p(i),s} W_i^T). grid (nc, nvg), one
+// CTA per block, camera-major observations, J recomputed like K2b; deterministic, written without atomics.
+template <int PD>
+__global__ void __launch_bounds__(128) k_cam_intr_pass(BaConst K, BaState S, ObsSoA O, const int* __restrict__ cam_start,
+                                                       const double* __restrict__ cs, const double* __restrict__ ps, int nvg,
+                                                       const double* __restrict__ ZT, double* __restrict__ Smat, int ld) {
+  __shared__ double red[4][NI * 6];
+  const int c = blockIdx.x, s = blockIdx.y;
+  const int base = 6 * K.nc;
+  const bool mine = K.intr_slot[K.cam_group[c]] == s;
+  double acc[NI * 6];
+#pragma unroll
+  for (int k = 0; k < NI * 6; ++k) acc[k] = 0.0;
+  for (int q = cam_start[c] + threadIdx.x; q < cam_start[c + 1]; q += blockDim.x) {
+    const int p = O.pt[q];
+    double r[2], jc[12], jp[2 * PD], ji[2 * NI], hc;
+    if (!eval_obs<-1, PD, NI>(K, S, c, p, O.xy[q], O.si[q], cs, ps, cs + base, r, jc, jp, ji, &hc)) continue;
+    double W[6][PD];
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+#pragma unroll
+      for (int t = 0; t < PD; ++t) W[b][t] = jc[b] * jp[t] + jc[6 + b] * jp[PD + t];
+    const double* T = ZT + ((size_t)p * nvg + s) * (2 * NI * PD) + NI * PD;
+#pragma unroll
+    for (int a = 0; a < NI; ++a) {
+      double t[PD];
+#pragma unroll
+      for (int u = 0; u < PD; ++u) t[u] = T[a * PD + u];
+#pragma unroll
+      for (int b = 0; b < 6; ++b) {
+        double v = mine ? ji[a] * jc[b] + ji[NI + a] * jc[6 + b] : 0.0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) v -= t[u] * W[b][u];
+        acc[a * 6 + b] += v;
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NI * 6; ++k) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) red[w][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NI * 6) {
+    const int k = threadIdx.x, a = k / 6, b = k % 6;
+    Smat[(size_t)(base + NI * s + a) * ld + 6 * c + b] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+  }
+}
+
+// LM diagonal of the intrinsics blocks; unit diagonal on the coordinates that are not free.
+__global__ void k_intr_finalize(int nvg, int base, const int* __restrict__ slot_group, const int* __restrict__ intr_model,
+                                const uint16_t* __restrict__ intr_const, const double* __restrict__ cdiag, double inv_radius,
+                                double min_diag, double max_diag, double* __restrict__ Smat, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nvg * NI) return;
+  const int s = i / NI, k = i % NI, g = slot_group[s];
+  const bool is_free = k < num_intrinsics(intr_model[g]) && !((intr_const[g] >> k) & 1);
+  double* d = &Smat[(size_t)(base + i) * ld + base + i];
+  if (is_free) *d += fmin(fmax(cdiag[base + i], min_diag), max_diag) * inv_radius;
+  else *d = 1.0;
+}
+
+// Bounds-constrained gradient norm (TrustRegionMinimizer::EvaluateGradientAndJacobian with is_constrained):
+// max |Plus(x, -g) - x| over the non-constant blocks, g = (Js^T r) / scale. Index space: cameras | points | groups.
+template <int PD>
+__global__ void k_grad_proj(BaConst K, BaState S, const double* __restrict__ braw, const double* __restrict__ gp,
+                            const double* __restrict__ cs, const double* __restrict__ ps, const double* __restrict__ lo,
+                            const double* __restrict__ hi, double* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (i < K.nc) {
+    if (K.cam_const[i] != THB_CAM_CONST_ALL)
+      for (int k = 0; k < 6; ++k) { const double x = S.cam[6 * i + k]; const double v = x + (-(braw[6 * i + k] / cs[6 * i + k])); m = fmax(m, fabs(x - v)); }
+  } else if (i - K.nc < K.np) {
+    const int p = i - K.nc;
+    if (!K.pt_const[p]) {
+      double x[4], d[PD], o[4];
+      for (int k = 0; k < 4; ++k) x[k] = S.pts[(size_t)p * 4 + k];
+      for (int k = 0; k < PD; ++k) d[k] = -(gp[(size_t)p * PD + k] / ps[(size_t)p * PD + k]);
+      point_plus<PD>(x, d, o);
+      for (int k = 0; k < 4; ++k) m = fmax(m, fabs(x[k] - o[k]));
+    }
+  } else if (i - K.nc - K.np < K.ng) {
+    const int g = i - K.nc - K.np, sl = K.intr_slot[g];
+    if (sl >= 0) {
+      const int Kg = num_intrinsics(K.intr_model[g]);
+      for (int k = 0; k < Kg; ++k) {
+        const int idx = 6 * K.nc + NI * sl + k;
+        const double x = S.intr[(size_t)g * KS + k];
+        double v = x + (-(braw[idx] / cs[idx]));
+        v = fmin(fmax(v, lo[NI * sl + k]), hi[NI * sl + k]);
+        m = fmax(m, fabs(x - v));
+      }
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.0)
+    atomicMax(reinterpret_cast<unsigned long long*>(scal + SC_GRADMAX), (unsigned long long)__double_as_longlong(m));
 }
 
 // Ambient (no manifold, no loss) evaluation in the caller's observation order: thb_ba_evaluate.

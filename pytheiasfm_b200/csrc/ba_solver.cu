@@ -65,7 +65,9 @@ struct ThbBaSession {
   cudaStream_t st = nullptr;
   int nc = 0, ng = 0, np = 0, no = 0;
   int PD = 3, model = -1, n_red = 0;
-  bool red_variable = false;  // any non-constant camera coordinate
+  int nvg = 0;                // intrinsics groups with free coordinates (slots of the reduced system)
+  bool constrained = false;   // bounds on a non-constant block (ceres Program::IsBoundsConstrained)
+  bool red_variable = false;  // any non-constant camera coordinate or intrinsics block
   bool any_variable = false;
   BaConst K{};
   BaState X{}, Xc{};
@@ -78,7 +80,10 @@ struct ThbBaSession {
   double2 *d_op_xy = nullptr, *d_op_si = nullptr, *d_oc_xy = nullptr, *d_oc_si = nullptr;
   int *d_pt_start = nullptr, *d_cam_start = nullptr, *d_chunk_pt = nullptr;
   int nchunks = 0;
-  double *d_r = nullptr, *d_jc = nullptr, *d_jp = nullptr;
+  double *d_r = nullptr, *d_jc = nullptr, *d_jp = nullptr, *d_ji = nullptr;
+  int8_t* d_op_slot = nullptr;
+  int* d_slot_group = nullptr;
+  double *d_zt = nullptr, *d_ilo = nullptr, *d_ihi = nullptr;
   double *d_cs = nullptr, *d_ps = nullptr;
   double *d_vinv = nullptr, *d_gp = nullptr, *d_pdiag = nullptr, *d_braw = nullptr, *d_cdiag = nullptr, *d_yp = nullptr;
   double* d_scal = nullptr;
@@ -111,6 +116,7 @@ void FreeSession(ThbBaSession* s) {
   cudaFree(s->d_op_xy); cudaFree(s->d_op_si); cudaFree(s->d_oc_xy); cudaFree(s->d_oc_si);
   cudaFree(s->d_pt_start); cudaFree(s->d_cam_start); cudaFree(s->d_chunk_pt);
   cudaFree(s->d_r); cudaFree(s->d_jc); cudaFree(s->d_jp); cudaFree(s->d_cs); cudaFree(s->d_ps);
+  cudaFree(s->d_ji); cudaFree(s->d_op_slot); cudaFree(s->d_slot_group); cudaFree(s->d_zt); cudaFree(s->d_ilo); cudaFree(s->d_ihi);
   cudaFree(s->d_vinv); cudaFree(s->d_gp); cudaFree(s->d_pdiag); cudaFree(s->d_braw); cudaFree(s->d_cdiag); cudaFree(s->d_yp);
   cudaFree(s->d_scal); cudaFree(s->d_flag); cudaFree(s->d_flush);
   if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -169,8 +175,14 @@ void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
     default: LaunchJacobian<-1, PD>(s, cs, ps); break;
   }
 }
+template <int PD>
+void LaunchJacobianIntr(ThbBaSession* s, const double* cs, const double* ps) {
+  k_jacobian<-1, PD, NI><<<cdiv(s->no, 128), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, cs + 6 * s->nc, s->d_r, s->d_jc, s->d_jp,
+                                                             s->d_ji, s->d_scal, s->d_flag);
+}
 void RunJacobian(ThbBaSession* s, const double* cs, const double* ps) {
-  if (s->PD == 3) DispatchJacobian<3>(s, cs, ps); else DispatchJacobian<4>(s, cs, ps);
+  if (s->nvg > 0) { if (s->PD == 3) LaunchJacobianIntr<3>(s, cs, ps); else LaunchJacobianIntr<4>(s, cs, ps); }
+  else if (s->PD == 3) DispatchJacobian<3>(s, cs, ps); else DispatchJacobian<4>(s, cs, ps);
   ++s->sum.gpu_launches;
 }
 
@@ -251,20 +263,65 @@ int BuildBlocks(ThbBaSession* s, bool want_grad) {
                                                         s->opt.max_lm_diagonal, s->d_vinv, s->d_gp, s->d_pdiag, s->d_flag);
   if (s->PD == 3) DispatchCamPass<3>(s, inv_radius); else DispatchCamPass<4>(s, inv_radius);
   s->sum.gpu_launches += 2;
+  if (s->nvg > 0) {
+    const int base = 6 * s->nc, nvg = s->nvg;
+    THB_CUDA_CHECK(cudaMemsetAsync(s->d_braw + base, 0, sizeof(double) * NI * nvg, s->st));
+    THB_CUDA_CHECK(cudaMemsetAsync(s->d_cdiag + base, 0, sizeof(double) * NI * nvg, s->st));
+    const dim3 gp_(cdiv(s->np, 128), nvg), gd_(std::min(cdiv(s->no, 256), 296), nvg), gi_(std::min(cdiv(s->np, 256), 148), nvg * (nvg + 1) / 2, NI),
+        gc_(s->nc, nvg);
+    if (s->PD == 3) {
+      k_intr_point<3><<<gp_, 128, 0, s->st>>>(s->np, s->no, nvg, base, s->d_pt_start, s->d_op_slot, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->d_zt, s->chol.RhsRow());
+      k_intr_intr<3><<<gi_, 256, 0, s->st>>>(s->np, nvg, base, s->d_zt, s->chol.A, s->chol.ld);
+      k_cam_intr_pass<3><<<gc_, 128, 0, s->st>>>(s->K, s->X, s->Oc, s->d_cam_start, s->d_cs, s->d_ps, nvg, s->d_zt, s->chol.A, s->chol.ld);
+    } else {
+      k_intr_point<4><<<gp_, 128, 0, s->st>>>(s->np, s->no, nvg, base, s->d_pt_start, s->d_op_slot, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->d_zt, s->chol.RhsRow());
+      k_intr_intr<4><<<gi_, 256, 0, s->st>>>(s->np, nvg, base, s->d_zt, s->chol.A, s->chol.ld);
+      k_cam_intr_pass<4><<<gc_, 128, 0, s->st>>>(s->K, s->X, s->Oc, s->d_cam_start, s->d_cs, s->d_ps, nvg, s->d_zt, s->chol.A, s->chol.ld);
+    }
+    k_intr_direct<<<gd_, 256, 0, s->st>>>(s->no, base, s->d_op_slot, s->d_r, s->d_ji, s->chol.A, s->chol.ld, s->chol.RhsRow(), s->d_braw, s->d_cdiag);
+    k_intr_finalize<<<cdiv(nvg * NI, 128), 128, 0, s->st>>>(nvg, base, s->d_slot_group, s->d_intr_model, s->d_intr_const, s->d_cdiag, inv_radius,
+                                                          s->opt.min_lm_diagonal, s->opt.max_lm_diagonal, s->chol.A, s->chol.ld);
+    s->sum.gpu_launches += 5;
+  }
   if (want_grad) {
     THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_GRADMAX, 0, sizeof(double), s->st));
-    k_grad_max<<<cdiv(s->n_red, 256), 256, 0, s->st>>>(s->n_red, s->d_braw, s->d_cs, s->d_scal);
-    k_grad_max<<<cdiv((long long)s->np * s->PD, 256), 256, 0, s->st>>>(s->np * s->PD, s->d_gp, s->d_ps, s->d_scal);
-    s->sum.gpu_launches += 2;
+    if (s->constrained) {
+      const int tot = s->nc + s->np + s->ng;
+      if (s->PD == 3) k_grad_proj<3><<<cdiv(tot, 256), 256, 0, s->st>>>(s->K, s->X, s->d_braw, s->d_gp, s->d_cs, s->d_ps, s->d_ilo, s->d_ihi, s->d_scal);
+      else k_grad_proj<4><<<cdiv(tot, 256), 256, 0, s->st>>>(s->K, s->X, s->d_braw, s->d_gp, s->d_cs, s->d_ps, s->d_ilo, s->d_ihi, s->d_scal);
+      ++s->sum.gpu_launches;
+    } else {
+      k_grad_max<<<cdiv(s->n_red, 256), 256, 0, s->st>>>(s->n_red, s->d_braw, s->d_cs, s->d_scal);
+      k_grad_max<<<cdiv((long long)s->np * s->PD, 256), 256, 0, s->st>>>(s->np * s->PD, s->d_gp, s->d_ps, s->d_scal);
+      s->sum.gpu_launches += 2;
+    }
   }
   s->t_normal.End();
   return THB_OK;
 }
 
+// candidate = Plus(x, alpha * delta) and its cost (ComputeCandidatePointAndEvaluateCost).
+int ComputeCandidate(ThbBaSession* s, double alpha) {
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_CAND, 0, sizeof(double) * 4, s->st));  // cand, step2, xnew2, gtd
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_EVAL_CAND, 0, sizeof(int), s->st));
+  if (s->PD == 3) k_update_pts<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_gp, s->d_ps, alpha, s->Xc.pts, s->d_scal);
+  else k_update_pts<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_gp, s->d_ps, alpha, s->Xc.pts, s->d_scal);
+  k_update_cams<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_cam_const, s->X.cam, s->chol.x, s->d_braw, s->d_cs, alpha, s->Xc.cam, s->d_scal);
+  if (s->nvg > 0) {
+    k_update_intr<<<cdiv(s->ng, 128), 128, 0, s->st>>>(s->ng, s->nc, s->d_intr_slot, s->d_intr_model, s->X.intr, s->chol.x, s->d_braw, s->d_cs, s->d_ilo,
+                                                      s->d_ihi, alpha, s->Xc.intr, s->d_scal);
+    ++s->sum.gpu_launches;
+  }
+  k_cam_derive<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->Xc.cam, s->Xc.camd, s->nc, s->d_cs, s->d_cam_const, s->d_cam_group);
+  s->sum.gpu_launches += 3;
+  RunCost(s, s->Xc, SC_COST_CAND, FL_EVAL_CAND);
+  ++s->sum.num_cost_evaluations;
+  return THB_OK;
+}
+
 // Schur complement off-diagonal blocks, factor + solve, back-substitution, candidate, candidate cost.
 int SolveAndStep(ThbBaSession* s) {
-  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_CAND, 0, sizeof(double) * 4, s->st));  // cand, mcc, step2, xnew2
-  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_EVAL_CAND, 0, sizeof(int), s->st));
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_MCC, 0, sizeof(double), s->st));
   if (s->red_variable) {
     s->t_normal.Begin();
     if (s->PD == 3)
@@ -281,20 +338,18 @@ int SolveAndStep(ThbBaSession* s) {
   }
   ++s->sum.num_linear_solves;
   s->t_update.Begin();
-  if (s->PD == 3) {
-    k_backsub<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_op_cam, s->d_r, s->d_jc, s->d_jp, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
-    k_update_pts<3><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_ps, s->Xc.pts, s->d_scal);
+  const int gb = cdiv(s->np, 128);
+  if (s->nvg > 0) {
+    if (s->PD == 3) k_backsub<3, NI><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, s->d_op_slot, s->d_r, s->d_jc, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
+    else k_backsub<4, NI><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, s->d_op_slot, s->d_r, s->d_jc, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
   } else {
-    k_backsub<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->no, s->d_pt_start, s->d_op_cam, s->d_r, s->d_jc, s->d_jp, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
-    k_update_pts<4><<<cdiv(s->np, 128), 128, 0, s->st>>>(s->np, s->d_pt_const, s->X.pts, s->d_yp, s->d_ps, s->Xc.pts, s->d_scal);
+    if (s->PD == 3) k_backsub<3, 0><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
+    else k_backsub<4, 0><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
   }
-  k_update_cams<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_cam_const, s->X.cam, s->chol.x, s->d_cs, s->Xc.cam, s->d_scal);
-  k_cam_derive<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->Xc.cam, s->Xc.camd, s->nc, s->d_cs, s->d_cam_const, s->d_cam_group);
-  s->sum.gpu_launches += 4;
-  RunCost(s, s->Xc, SC_COST_CAND, FL_EVAL_CAND);
-  ++s->sum.num_cost_evaluations;
+  ++s->sum.gpu_launches;
+  const int rc = ComputeCandidate(s, 1.0);
   s->t_update.End();
-  return THB_OK;
+  return rc;
 }
 
 void Terminate(ThbBaSession* s, int type) { s->sum.termination_type = type; s->finished = true; }
@@ -332,6 +387,31 @@ int OneIteration(ThbBaSession* s) {
     return THB_OK;
   }
   s->num_consecutive_invalid = 0;
+  if (s->constrained) {
+    // TrustRegionMinimizer::DoLineSearch (projected Armijo search along delta, first probe at step size 1 = the candidate
+    // just evaluated). A failed probe halves the step until the sufficient-decrease test holds (at most 20 probes), as
+    // the oracle does; Ceres contracts by polynomial interpolation instead (deviations).
+    const double gtd = s->h_scal[SC_GTD];
+    ++s->sum.num_cost_evaluations;
+    auto probe_ok = [&](double alpha) {
+      const double c = s->h_scal[SC_COST_CAND];
+      return !s->h_flag[FL_EVAL_CAND] && std::isfinite(c) && c <= s->x_cost + 1e-4 * gtd * alpha;
+    };
+    if (!probe_ok(1.0)) {
+      double alpha = 1.0;
+      bool found = false;
+      for (int it = 1; it < 20 && !found; ++it) {
+        alpha *= 0.5;
+        if ((rc = ComputeCandidate(s, alpha)) != THB_OK) return rc;
+        if ((rc = ReadScalars(s)) != THB_OK) return rc;
+        found = probe_ok(alpha);
+      }
+      if (!found) {
+        if ((rc = ComputeCandidate(s, 1.0)) != THB_OK) return rc;
+        if ((rc = ReadScalars(s)) != THB_OK) return rc;
+      }
+    }
+  }
   const double cand_cost = s->h_flag[FL_EVAL_CAND] ? std::numeric_limits<double>::max() : s->h_scal[SC_COST_CAND];
   // ParameterToleranceReached
   const double step_norm = std::sqrt(s->h_scal[SC_STEP2]);
@@ -404,10 +484,6 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   for (int g = 0; g < ng; ++g) {
     const int K = num_intrinsics(h_intr_model[g]);
     if (K < 0) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path"); }
-    if ((h_intr_const[g] & ((1u << K) - 1)) != ((1u << K) - 1)) {
-      FreeSession(s);
-      THB_FAIL(THB_E_UNSUPPORTED, "intrinsics refinement is not implemented yet: every intrinsics parameter must be constant");
-    }
   }
   for (int c = 0; c < nc; ++c)
     if (h_cam_group[c] < 0 || h_cam_group[c] >= ng) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range"); }
@@ -432,15 +508,32 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   s->h_perm_p = perm_p;
   s->model = ng > 0 ? h_intr_model[0] : THB_MODEL_PINHOLE;
   for (int g = 1; g < ng; ++g) if (h_intr_model[g] != s->model) s->model = -1;
-  s->red_variable = false; s->any_variable = false;
+  // variable intrinsics groups: observed by at least one residual and with at least one free coordinate
+  std::vector<int> slot(ng, -1), slot_group;
+  {
+    std::vector<char> used(ng, 0);
+    for (int i = 0; i < no; ++i) used[h_cam_group[h_obs_cam[i]]] = 1;
+    for (int g = 0; g < ng; ++g) {
+      const unsigned all = (1u << num_intrinsics(h_intr_model[g])) - 1;
+      if (used[g] && (h_intr_const[g] & all) != all) { slot[g] = (int)slot_group.size(); slot_group.push_back(g); }
+    }
+  }
+  s->nvg = (int)slot_group.size();
+  if (s->nvg > MAX_VG) {
+    FreeSession(s);
+    THB_FAIL(THB_E_UNSUPPORTED, "more than 8 intrinsics groups with free parameters are not supported (shared-intrinsics design)");
+  }
+  s->constrained = s->nvg > 0;  // focal length >= 1 is always set on a non-constant block (bundle_adjuster.cc:396-405)
+  s->red_variable = s->nvg > 0; s->any_variable = false;
   for (int c = 0; c < nc; ++c) if (h_cam_const[c] != THB_CAM_CONST_ALL) s->red_variable = true;
   for (int p = 0; p < np; ++p) if (!h_pt_const[p]) s->any_variable = true;
   s->any_variable |= s->red_variable;
   // Ceres drops residual blocks whose parameter blocks are all constant (their cost is Summary::fixed_cost);
   // they still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
   bool has_fixed = false;
-  for (int i = 0; i < no && !has_fixed; ++i) has_fixed = h_cam_const[h_obs_cam[i]] == THB_CAM_CONST_ALL && h_pt_const[h_obs_pt[i]];
-  if (has_fixed && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera and point are both constant are not supported in a problem with free blocks"); }
+  for (int i = 0; i < no && !has_fixed; ++i)
+    has_fixed = h_cam_const[h_obs_cam[i]] == THB_CAM_CONST_ALL && h_pt_const[h_obs_pt[i]] && slot[h_cam_group[h_obs_cam[i]]] < 0;
+  if (has_fixed && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera, intrinsics and point are all constant are not supported in a problem with free blocks"); }
   // Schur chunks: consecutive points with <= 64 observations in total
   std::vector<int> chunk_pt;
   chunk_pt.push_back(0);
@@ -451,7 +544,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   }
   chunk_pt.push_back(np);
   s->nchunks = (int)chunk_pt.size() - 1;
-  s->n_red = 6 * nc;
+  s->n_red = 6 * nc + NI * s->nvg;
 
   // ---- device memory ----
   THB_TRY(DevAlloc(&s->X.cam, (size_t)nc * 6)); THB_TRY(DevAlloc(&s->X.camd, (size_t)nc * CAMD));
@@ -468,6 +561,12 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY(DevAlloc(&s->d_vinv, (size_t)np * s->PD * s->PD)); THB_TRY(DevAlloc(&s->d_gp, (size_t)np * s->PD)); THB_TRY(DevAlloc(&s->d_pdiag, (size_t)np * s->PD));
   THB_TRY(DevAlloc(&s->d_braw, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_cdiag, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_yp, (size_t)np * s->PD));
   THB_TRY(DevAlloc(&s->d_scal, SC_COUNT)); THB_TRY(DevAlloc(&s->d_flag, FL_COUNT));
+  THB_TRY(DevAlloc(&s->d_op_slot, no)); THB_TRY(DevAlloc(&s->d_slot_group, s->nvg));
+  THB_TRY(DevAlloc(&s->d_ilo, (size_t)NI * s->nvg)); THB_TRY(DevAlloc(&s->d_ihi, (size_t)NI * s->nvg));
+  if (s->nvg > 0) {
+    THB_TRY(DevAlloc(&s->d_ji, (size_t)no * 2 * NI));
+    THB_TRY(DevAlloc(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
+  }
   THB_TRY_CUDA(cudaMallocHost(&s->h_scal, sizeof(double) * SC_COUNT));
   THB_TRY_CUDA(cudaMallocHost(&s->h_flag, sizeof(int) * FL_COUNT));
   THB_TRY(s->chol.Init(std::max(1, s->n_red)));
@@ -479,7 +578,6 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->X.pts, P->pts, sizeof(double) * np * 4, kin, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->Xc.intr, s->X.intr, sizeof(double) * ng * KS, cudaMemcpyDeviceToDevice, st));
-  std::vector<int> slot(ng, -1);
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, h_cam_group.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_model, h_intr_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_slot, slot.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
@@ -489,6 +587,20 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_start, pt_start.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_start, cam_start.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_chunk_pt, chunk_pt.data(), sizeof(int) * chunk_pt.size(), cudaMemcpyHostToDevice, st));
+  std::vector<int8_t> op_slot(no);
+  for (int q = 0; q < no; ++q) op_slot[q] = (int8_t)slot[h_cam_group[h_obs_cam[perm_p[q]]]];
+  // box constraints of bundle_adjuster.cc:396-427
+  std::vector<double> ilo((size_t)NI * s->nvg, -std::numeric_limits<double>::max()), ihi((size_t)NI * s->nvg, std::numeric_limits<double>::max());
+  for (int sl = 0; sl < s->nvg; ++sl) {
+    const int m = h_intr_model[slot_group[sl]];
+    ilo[NI * sl + 0] = 1.0;  // focal length is parameter 0 of every model
+    if (m == THB_MODEL_DOUBLE_SPHERE) { ilo[NI * sl + 5] = -1.0; ihi[NI * sl + 5] = 1.0; ilo[NI * sl + 6] = 0.0; ihi[NI * sl + 6] = 1.0; }
+    else if (m == THB_MODEL_EXTENDED_UNIFIED) { ilo[NI * sl + 5] = 0.0; ihi[NI * sl + 5] = 1.0; ilo[NI * sl + 6] = 0.1; }
+  }
+  THB_TRY_CUDA(cudaMemcpy(s->d_op_slot, op_slot.data(), no, cudaMemcpyHostToDevice));
+  THB_TRY_CUDA(cudaMemcpy(s->d_slot_group, slot_group.data(), sizeof(int) * s->nvg, cudaMemcpyHostToDevice));
+  THB_TRY_CUDA(cudaMemcpy(s->d_ilo, ilo.data(), sizeof(double) * ilo.size(), cudaMemcpyHostToDevice));
+  THB_TRY_CUDA(cudaMemcpy(s->d_ihi, ihi.data(), sizeof(double) * ihi.size(), cudaMemcpyHostToDevice));
   {
     // reorder observations on the host (the reference walks hash maps at this point, bundle_adjuster.cc:116-173)
     std::vector<double> h_xy, h_si;
@@ -541,7 +653,13 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   k_fill<<<cdiv(s->n_red, 256), 256, 0, st>>>(s->n_red, s->d_cs, 1.0);
   k_fill<<<cdiv((long long)np * s->PD, 256), 256, 0, st>>>(np * s->PD, s->d_ps, 1.0);
   k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(s->X.cam, s->X.camd, nc, s->d_cs, s->d_cam_const, s->d_cam_group);
-  k_xnorm<<<cdiv((long long)nc + np, 256), 256, 0, st>>>(nc, np, s->d_cam_const, s->d_pt_const, s->X.cam, s->X.pts, s->d_scal + SC_XNEW2);
+  if (s->constrained) {  // IterationZero: x = Plus(x, 0) makes the start feasible
+    k_update_intr<<<cdiv(ng, 128), 128, 0, st>>>(ng, nc, s->d_intr_slot, s->d_intr_model, s->X.intr, nullptr, nullptr, nullptr, s->d_ilo, s->d_ihi, 1.0,
+                                                s->X.intr, nullptr);
+    ++s->sum.gpu_launches;
+  }
+  k_xnorm<<<cdiv((long long)nc + np + ng, 256), 256, 0, st>>>(nc, np, ng, s->d_cam_const, s->d_pt_const, s->d_intr_slot, s->d_intr_model, s->X.cam,
+                                                             s->X.pts, s->X.intr, s->d_scal + SC_XNEW2);
   s->sum.gpu_launches += 4;
   if (O->jacobi_scaling) {
     // column norms of the unscaled Jacobian -> scale = 1/(1+sqrt(norm^2)), fixed for the whole solve
@@ -625,6 +743,7 @@ int thb_ba_finish(ThbBaSession* s, ThbBaSummary* summary) {
     const cudaMemcpyKind kout = s->prob.memory_space == THB_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     cudaError_t e = cudaMemcpyAsync(s->prob.cam_ext, s->X.cam, sizeof(double) * s->nc * 6, kout, s->st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(s->prob.pts, s->X.pts, sizeof(double) * s->np * 4, kout, s->st);
+    if (e == cudaSuccess && s->nvg > 0) e = cudaMemcpyAsync(s->prob.intr, s->X.intr, sizeof(double) * s->ng * KS, kout, s->st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
     if (e != cudaSuccess) { SetLastError(cudaGetErrorString(e)); rc = THB_E_CUDA; }
   }

@@ -74,8 +74,11 @@ def ba_options():
     return pt.sfm.BundleAdjustmentOptions()
 
 
-def test_BundleAdjustView(gen, ba_options):
-    """bundle_adjuster_test.py:6-15"""
+def test_BundleAdjustView(ba_options):
+    """bundle_adjuster_test.py:6-15, on the scene its __main__ builds (:95-96: 1 view, 20 tracks)."""
+    gen = RandomReconGenerator(seed=42)
+    gen.generate_random_recon(nr_views=1, nr_tracks=20)
+    assert gen.recon.View(gen.recon.ViewIds()[0]).NumFeatures() >= 6
     for vid in gen.recon.ViewIds():
         orig_pos = gen.recon.View(vid).Camera().GetPosition()
         gen.add_noise_to_views(noise_pos=1e-3, noise_angle=1e-1)
@@ -83,6 +86,20 @@ def test_BundleAdjustView(gen, ba_options):
         dist_pos = np.linalg.norm(orig_pos - gen.recon.View(vid).Camera().GetPosition())
         assert dist_pos < 1e-4
         assert result.success
+
+
+def test_BundleAdjustView_each_of_ten(gen, ba_options):
+    """Same assertion on a 10-view scene, perturbing only the view being adjusted (add_noise_to_view, random_recon_gen.py:152-159)."""
+    for vid in gen.recon.ViewIds():
+        if gen.recon.View(vid).NumFeatures() < 6:
+            continue
+        cam = gen.recon.View(vid).MutableCamera()
+        orig_pos = cam.GetPosition()
+        cam.SetPosition(orig_pos + 1e-3 * np.random.randn(3))
+        cam.SetOrientationFromAngleAxis(cam.GetOrientationAsAngleAxis() + 1e-1 * np.pi / 180.0 * np.random.randn(3))
+        result = pt.sfm.BundleAdjustView(gen.recon, ba_options, vid)
+        assert result.success
+        assert np.linalg.norm(orig_pos - gen.recon.View(vid).Camera().GetPosition()) < 1e-4
 
 
 def test_BundleAdjustTrack(gen, ba_options):

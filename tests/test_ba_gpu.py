@@ -154,6 +154,77 @@ def test_partial_reconstruction_semantics(lib, oracle):
     _compare_solves(lib, oracle, prob, capi.default_options(lib))
 
 
+FREE_F_AND_DISTORTION = {  # GetSubsetFromOptimizeIntrinsicsType(FOCAL_LENGTH | RADIAL_DISTORTION): bit k set => constant
+    capi.MODEL_PINHOLE: 0b0011110, capi.MODEL_DOUBLE_SPHERE: 0b0011110, capi.MODEL_EXTENDED_UNIFIED: 0b0011110,
+    capi.MODEL_FISHEYE: 0b000011110, capi.MODEL_FOV: 0b01110, capi.MODEL_DIVISION_UNDISTORTION: 0b01110}
+
+
+def _perturb_intrinsics(prob, rel_f=0.01):
+    prob.a["intr"][:, 0] *= 1.0 + rel_f
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_intrinsics_refinement_shared_group(lib, oracle, model):
+    """One shared intrinsics block (reconstruction.cc:129-140) refined with the cameras: Schur group 1
+    (bundle_adjuster.cc:547-577), SubsetManifold on the constant coordinates (:429-441), bounds (:396-427)."""
+    prob, gt = synthetic.make_ba_problem(12, 400, 4, models=(model,), seed=80 + model, intr_const_mask=[FREE_F_AND_DISTORTION[model]])
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        prob.a["intr"][0, 4] = -5e-7
+    _perturb_intrinsics(prob)
+    before = prob.a["intr"].copy()
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    const = [k for k in range(capi.MODEL_NUM_PARAMS[model]) if (FREE_F_AND_DISTORTION[model] >> k) & 1]
+    np.testing.assert_array_equal(pg.a["intr"][0, const], before[0, const])
+    assert pg.a["intr"][0, 0] != before[0, 0]
+    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
+
+
+def test_c3_scaled_mixed_models_intrinsics_refinement(lib, oracle):
+    """BASELINE configs[2] scaled: DoubleSphere + ExtendedUnified groups, FOCAL_LENGTH|RADIAL_DISTORTION free."""
+    prob, gt = synthetic.config_c3(scale=0.06)
+    _perturb_intrinsics(prob, 0.02)
+    o = capi.default_options(lib)
+    g, oo, pg, po = _compare_solves(lib, oracle, prob, o)
+    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
+    # forced iterations (benchmark setting)
+    o.function_tolerance = -1.0; o.gradient_tolerance = -1.0; o.parameter_tolerance = -1.0; o.max_num_iterations = 8
+    _compare_solves(lib, oracle, prob, o)
+
+
+def test_intrinsics_all_free_euclidean_points_and_huber(lib, oracle):
+    prob, gt = synthetic.make_ba_problem(10, 300, 5, models=(capi.MODEL_PINHOLE, capi.MODEL_FISHEYE), seed=91, intr_const_mask=[0, 0])
+    _perturb_intrinsics(prob, -0.015)
+    o = capi.default_options(lib); o.use_homogeneous_point_parametrization = 0
+    o.loss_function_type = capi.LOSS_HUBER; o.robust_loss_width = 3.0
+    _compare_solves(lib, oracle, prob, o)
+
+
+def test_intrinsics_bounds_projection(lib, oracle):
+    """Infeasible start (EUCM beta < 0.1, DS alpha > 1): IterationZero projects on the box (bundle_adjuster.cc:407-427)."""
+    prob, gt = synthetic.config_c3(scale=0.04, seed=5)
+    prob.a["intr"][0, 6] = 1.02   # DS alpha  in [0, 1]
+    prob.a["intr"][1, 6] = 0.05   # EUCM beta >= 0.1
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib), rel=1e-5)
+    assert 0.0 <= pg.a["intr"][0, 6] <= 1.0 and pg.a["intr"][1, 6] >= 0.1
+
+
+def test_intrinsics_constant_group_next_to_free_group(lib, oracle):
+    """Partial BA: the group no optimised view belongs to stays constant (bundle_adjuster.cc:442-459)."""
+    prob, gt = synthetic.make_ba_problem(12, 300, 4, models=(capi.MODEL_PINHOLE, capi.MODEL_PINHOLE), seed=93, intr_const_mask=[0b0011110, 0b1111111])
+    _perturb_intrinsics(prob)
+    prob.a["cam_const"][6:] = 3
+    before = prob.a["intr"].copy()
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    np.testing.assert_array_equal(pg.a["intr"][1], before[1])
+
+
+def test_too_many_free_intrinsics_groups_is_an_error(lib):
+    models = (capi.MODEL_PINHOLE,) * 9
+    prob, _ = synthetic.make_ba_problem(18, 200, 4, models=models, seed=94, intr_const_mask=[0b0011110] * 9)
+    s = capi.ThbBaSummary(); p = prob.struct(); o = capi.default_options(lib)
+    assert lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None) == capi.THB_E_UNSUPPORTED
+
+
 def test_device_resident_session_matches_one_shot(lib):
     """thb_ba_create/iterate/finish with THB_MEM_DEVICE pointers == thb_ba_solve with host pointers."""
     import torch

@@ -155,3 +155,24 @@ def test_rejects_unsupported_and_invalid(oracle):
     assert oracle.ba_solve(prob.copy(), o)["rc"] == capi.THB_E_UNSUPPORTED
     bad = prob.copy(); bad.a["obs_cam"][0] = 99
     assert oracle.ba_solve(bad, oracle.default_options())["rc"] == capi.THB_E_INVALID_ARGUMENT
+
+
+def test_intrinsics_refinement_recovers_focal_and_respects_subset(oracle):
+    """bundle_adjuster.cc:382-441: FOCAL_LENGTH|RADIAL_DISTORTION free on a shared block, the rest constant."""
+    prob, gt = synthetic.make_ba_problem(10, 300, 4, seed=81, pixel_sigma=0.0, intr_const_mask=[0b0011110])
+    prob.a["intr"][0, 0] *= 1.01
+    before = prob.a["intr"].copy()
+    s = oracle.ba_solve(prob, oracle.default_options())
+    assert s["success"] == 1 and s["final_cost"] < 1e-8 * s["initial_cost"]
+    np.testing.assert_array_equal(prob.a["intr"][0, 1:5], before[0, 1:5])
+    assert abs(prob.a["intr"][0, 0] - gt["intr"][0, 0]) < 1e-3 * gt["intr"][0, 0]
+
+
+def test_intrinsics_bounds_are_enforced(oracle):
+    """bundle_adjuster.cc:407-427: DS alpha in [0,1], EUCM beta >= 0.1; an infeasible start is projected first."""
+    prob, gt = synthetic.config_c3(scale=0.04, seed=5)
+    prob.a["intr"][0, 6] = 1.02
+    prob.a["intr"][1, 6] = 0.05
+    s = oracle.ba_solve(prob, oracle.default_options())
+    assert s["success"] == 1
+    assert 0.0 <= prob.a["intr"][0, 6] <= 1.0 and prob.a["intr"][1, 6] >= 0.1
