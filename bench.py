@@ -45,6 +45,9 @@ def make_options(lib_or_oracle_default, iters):
     o.gradient_tolerance = -1.0
     o.parameter_tolerance = -1.0
     o.max_num_iterations = iters
+    # past convergence the model cost change is round-off and steps turn "invalid"; Ceres would stop with FAILURE after 5
+    # in a row, a forced-K run keeps going (each such iteration still builds, factors and back-substitutes the system)
+    o.max_num_consecutive_invalid_steps = 1 << 30
     return o
 
 
@@ -377,7 +380,8 @@ def main():
                          "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},
             "phase_ms_per_step": {"jacobian": summ.ms_jacobian / (W + K), "normal_equations": summ.ms_normal / (W + K),
                                   "reduced_solve": summ.ms_solve / (W + K), "update_and_cost": summ.ms_update / (W + K)},
-            "final_cost": summ.final_cost, "clocks": sampler.summary(),
+            "final_cost": summ.final_cost, "initial_cost": summ.initial_cost, "num_successful_steps": summ.num_successful_steps,
+            "termination_type": summ.termination_type, "clocks": sampler.summary(),
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(prob, iters=2)

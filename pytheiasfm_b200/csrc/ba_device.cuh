@@ -15,11 +15,29 @@
 
 namespace thb {
 
-// Per-camera record gathered by every observation: one 192-byte, 32-byte-aligned block read with six 256-bit
-// loads (uncoalesced 8-byte gathers are bound by L1 wavefronts, measured):
-//   R[9] | C[3] | M[9] | small-angle flag | column scale[6] | constness | intrinsics group | pad[2]   = 256 bytes
-constexpr int CAMD = 32;
-constexpr int CD_SCALE = 22, CD_CONST = 28, CD_GROUP = 29;
+// Per-camera record gathered by every observation: one 160-byte, 32-byte-aligned block read with FIVE 256-bit loads
+// (LDG.E.ENL2.256). Every lane of a point-major warp reads a different camera, so each load instruction costs 32 L1 tag
+// lookups whatever its width: the r01 ncu capture showed K1 bound by exactly that (17 128-bit gathers of a 256-byte
+// record, l1tex 77 % busy). The rotation matrix and the SO(3) left Jacobian are therefore NOT stored (18 doubles) but
+// applied from the angle-axis vector and four scalar coefficients:
+//   R   = I + a [w]x + b [w]x^2        (ceres::AngleAxisRotatePoint; first-order branch: a = 1, b = 0)
+//   J_l = I + A [w]x + B [w]x^2        (A = b, B = (th - sin th)/th^3; first-order branch: A = B = 0)
+//   w[3] | a b A B | th2 | C[3] | group | column scale[6] | constness | first-order flag            = 20 doubles
+constexpr int CAMD = 20;
+constexpr int CD_W = 0, CD_A = 3, CD_B = 4, CD_JA = 5, CD_JB = 6, CD_TH2 = 7, CD_C = 8, CD_GROUP = 11, CD_SCALE = 12, CD_CONST = 18, CD_SMALL = 19;
+
+__device__ __forceinline__ void ld256(const double* p, double* o) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+
+// y = (I + s*a [w]x + b [w]x^2) v with [w]x^2 = w w^T - th2 I; s = +1: the matrix, s = -1: its transpose.
+__device__ __forceinline__ void rot_apply(const double w[3], double a, double b, double th2, const double v[3], double y[3]) {
+  const double wv = w[0] * v[0] + w[1] * v[1] + w[2] * v[2];
+  const double c0 = w[1] * v[2] - w[2] * v[1], c1 = w[2] * v[0] - w[0] * v[2], c2 = w[0] * v[1] - w[1] * v[0];
+  y[0] = v[0] + a * c0 + b * (w[0] * wv - th2 * v[0]);
+  y[1] = v[1] + a * c1 + b * (w[1] * wv - th2 * v[1]);
+  y[2] = v[2] + a * c2 + b * (w[2] * wv - th2 * v[2]);
+}
 
 struct BaState {  // one set of parameter values (current x, or the candidate)
   double* cam;
@@ -105,16 +123,17 @@ __device__ __forceinline__ void householder4(const double x[4], double v[3], dou
 template <int MODEL>
 __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S, int c, int p, double2 xy,
                                               double2 si, double r[2]) {
-  const double4* cd4 = reinterpret_cast<const double4*>(S.camd + (size_t)c * CAMD);
-  const double4 q0 = cd4[0], q1 = cd4[1], q2 = cd4[2];  // R[0..8], C[0..2]
+  double cd[12];
+  {
+    const double* rec = S.camd + (size_t)c * CAMD;
+    ld256(rec, cd); ld256(rec + 4, cd + 4); ld256(rec + 8, cd + 8);
+  }
   const double4 X = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
-  const double ax = X.x - X.w * q2.y, ay = X.y - X.w * q2.z, az = X.z - X.w * q2.w;
-  if (ax * ax + ay * ay + az * az < 1e-8) return false;
+  const double adj[3] = {X.x - X.w * cd[CD_C], X.y - X.w * cd[CD_C + 1], X.z - X.w * cd[CD_C + 2]};
+  if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
   double pc[3];
-  pc[0] = q0.x * ax + q0.y * ay + q0.z * az;
-  pc[1] = q0.w * ax + q1.x * ay + q1.y * az;
-  pc[2] = q1.z * ax + q1.w * ay + q2.x * az;
-  const int g = (int)S.camd[(size_t)c * CAMD + CD_GROUP];
+  rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[CD_TH2], adj, pc);
+  const int g = (int)cd[CD_GROUP];
   double pix[2];
   if (!project<MODEL, double, double>(K.intr_model[g], S.intr + (size_t)g * KS, pc, pix)) return false;
   r[0] = si.x * (pix[0] - xy.x);
@@ -135,21 +154,19 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   typedef Dual<ND> D;
   double cd[CAMD];
   {
-    const double4* cd4 = reinterpret_cast<const double4*>(S.camd + (size_t)c * CAMD);
+    const double* rec = S.camd + (size_t)c * CAMD;
 #pragma unroll
-    for (int k = 0; k < CAMD / 4; ++k) { const double4 v = cd4[k]; cd[4 * k] = v.x; cd[4 * k + 1] = v.y; cd[4 * k + 2] = v.z; cd[4 * k + 3] = v.w; }
+    for (int k = 0; k < CAMD / 4; ++k) ld256(rec + 4 * k, cd + 4 * k);
   }
   const double4 X4 = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
   const double X[4] = {X4.x, X4.y, X4.z, X4.w};
-  const double C[3] = {cd[9], cd[10], cd[11]};
+  const double C[3] = {cd[CD_C], cd[CD_C + 1], cd[CD_C + 2]};
   const double adj[3] = {X[0] - X[3] * C[0], X[1] - X[3] * C[1], X[2] - X[3] * C[2]};
   if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
-  double R[9];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = cd[k];
+  const double* w = cd + CD_W;
+  const double th2 = cd[CD_TH2];
   double pc[3];
-#pragma unroll
-  for (int a = 0; a < 3; ++a) pc[a] = R[3 * a] * adj[0] + R[3 * a + 1] * adj[1] + R[3 * a + 2] * adj[2];
+  rot_apply(w, cd[CD_A], cd[CD_B], th2, adj, pc);
 
   const int g = (int)cd[CD_GROUP];
   const int model = MODEL >= 0 ? MODEL : K.intr_model[g];
@@ -173,12 +190,10 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   double A[6];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { A[k] = si.x * pix[0].v[k]; A[3 + k] = si.y * pix[1].v[k]; }
-  // AR = A * R (2x3): d r / d adj
+  // AR = A * R (2x3): d r / d adj; row a = R^T A_a
   double AR[6];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) AR[3 * a + k] = A[3 * a] * R[k] + A[3 * a + 1] * R[3 + k] + A[3 * a + 2] * R[6 + k];
+  rot_apply(w, -cd[CD_A], cd[CD_B], th2, A, AR);
+  rot_apply(w, -cd[CD_A], cd[CD_B], th2, A + 3, AR + 3);
   const int cconst = (int)cd[CD_CONST];
   // d r / d C = -w * AR
 #pragma unroll
@@ -188,25 +203,23 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   // d r / d aa = A * (-[q]x M): q = R adj and M = left Jacobian of SO(3); in Ceres' small-angle
   // branch (R = I + [aa]x) q = adj and M = I.
   {
-    const bool small = cd[21] != 0.0;
+    const bool small = cd[CD_SMALL] != 0.0;
     const double q0 = small ? adj[0] : pc[0], q1 = small ? adj[1] : pc[1], q2 = small ? adj[2] : pc[2];
-    // G = A * (-[q]x): row a: -(A_a x q)^T ... (A_a^T [q]x)_k = (q x A_a)_k ; so -A_a [q]x = (A_a x q)... computed explicitly
-    double G[6];
+    // G = A * (-[q]x), with [q]x = [[0,-q2,q1],[q2,0,-q0],[-q1,q0,0]]; then row a of G * J_l = J_l^T G_a
+    double G[6], GM[6];
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
       const double a0 = A[3 * a], a1 = A[3 * a + 1], a2 = A[3 * a + 2];
-      // row vector a^T * (-[q]x), with [q]x = [[0,-q2,q1],[q2,0,-q0],[-q1,q0,0]]
       G[3 * a + 0] = -(a1 * q2 - a2 * q1);
       G[3 * a + 1] = -(a2 * q0 - a0 * q2);
       G[3 * a + 2] = -(a0 * q1 - a1 * q0);
     }
+    rot_apply(w, -cd[CD_JA], cd[CD_JB], th2, G, GM);
+    rot_apply(w, -cd[CD_JA], cd[CD_JB], th2, G + 3, GM + 3);
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int k = 0; k < 3; ++k)
-        jc[6 * a + 3 + k] = (cconst & THB_CAM_CONST_ORIENTATION)
-                                ? 0.0
-                                : G[3 * a] * cd[12 + k] + G[3 * a + 1] * cd[15 + k] + G[3 * a + 2] * cd[18 + k];
+      for (int k = 0; k < 3; ++k) jc[6 * a + 3 + k] = (cconst & THB_CAM_CONST_ORIENTATION) ? 0.0 : GM[3 * a + k];
   }
   // d r / d X (2x4) = [AR | -AR*C], then the tangent block
   const bool pconst = K.pt_const[p] != 0;

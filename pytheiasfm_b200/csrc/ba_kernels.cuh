@@ -17,8 +17,9 @@ constexpr int MAX_VG = 8;
 enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 };
 
 // ---------------------------------------------------------------------------------------------
-// Per-camera derived quantities: rotation matrix (ceres::AngleAxisRotatePoint semantics, incl. the
-// first-order branch for theta^2 <= eps) and the SO(3) left Jacobian used for d(R v)/d(aa).
+// Per-camera record (ba_device.cuh): angle-axis vector plus the scalar coefficients of the rotation
+// (ceres::AngleAxisRotatePoint semantics, incl. the first-order branch for theta^2 <= eps) and of the SO(3) left
+// Jacobian used for d(R v)/d(aa).
 __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc, const double* __restrict__ cs,
                              const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_group) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -26,17 +27,14 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
   const double wx = cam[6 * c + 3], wy = cam[6 * c + 4], wz = cam[6 * c + 5];
   double* o = camd + (size_t)c * CAMD;
   const double th2 = wx * wx + wy * wy + wz * wz;
+  o[CD_W] = wx; o[CD_W + 1] = wy; o[CD_W + 2] = wz;
+  o[CD_TH2] = th2;
   if (th2 > 2.220446049250313e-16) {
     const double th = sqrt(th2);
     double s, co;
     sincos(th, &s, &co);
-    const double it = 1.0 / th;
-    const double ux = wx * it, uy = wy * it, uz = wz * it;
-    const double oc = 1.0 - co;
-    o[0] = co + oc * ux * ux;      o[1] = oc * ux * uy - s * uz;  o[2] = oc * ux * uz + s * uy;
-    o[3] = oc * ux * uy + s * uz;  o[4] = co + oc * uy * uy;      o[5] = oc * uy * uz - s * ux;
-    o[6] = oc * ux * uz - s * uy;  o[7] = oc * uy * uz + s * ux;  o[8] = co + oc * uz * uz;
-    // left Jacobian J_l = I + A [w]x + B [w]x^2, A = (1-cos)/th^2, B = (th - sin)/th^3
+    // R = I + (sin th / th) [w]x + ((1 - cos th) / th^2) [w]x^2; J_l = I + A [w]x + B [w]x^2,
+    // A = (1 - cos th)/th^2, B = (th - sin th)/th^3 (series below 1e-2: the closed forms cancel)
     double A, B;
     if (th < 1e-2) {
       A = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
@@ -46,23 +44,16 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
       A = 2.0 * sh * sh / th2;
       B = (th - s) / (th2 * th);
     }
-    // [w]x^2 = w w^T - th2 I
-    o[12] = 1.0 + B * (wx * wx - th2); o[13] = -A * wz + B * wx * wy;     o[14] = A * wy + B * wx * wz;
-    o[15] = A * wz + B * wx * wy;      o[16] = 1.0 + B * (wy * wy - th2); o[17] = -A * wx + B * wy * wz;
-    o[18] = -A * wy + B * wx * wz;     o[19] = A * wx + B * wy * wz;      o[20] = 1.0 + B * (wz * wz - th2);
-    o[21] = 0.0;
+    o[CD_A] = s / th; o[CD_B] = A; o[CD_JA] = A; o[CD_JB] = B;
+    o[CD_SMALL] = 0.0;
   } else {
-    o[0] = 1.0; o[1] = -wz; o[2] = wy;
-    o[3] = wz;  o[4] = 1.0; o[5] = -wx;
-    o[6] = -wy; o[7] = wx;  o[8] = 1.0;
-    o[12] = 1.0; o[13] = 0.0; o[14] = 0.0; o[15] = 0.0; o[16] = 1.0; o[17] = 0.0; o[18] = 0.0; o[19] = 0.0; o[20] = 1.0;
-    o[21] = 1.0;
+    o[CD_A] = 1.0; o[CD_B] = 0.0; o[CD_JA] = 0.0; o[CD_JB] = 0.0;
+    o[CD_SMALL] = 1.0;
   }
-  o[9] = cam[6 * c]; o[10] = cam[6 * c + 1]; o[11] = cam[6 * c + 2];
+  o[CD_C] = cam[6 * c]; o[CD_C + 1] = cam[6 * c + 1]; o[CD_C + 2] = cam[6 * c + 2];
   for (int k = 0; k < 6; ++k) o[CD_SCALE + k] = cs ? cs[6 * c + k] : 1.0;
   o[CD_CONST] = (double)cam_const[c];
   o[CD_GROUP] = (double)cam_group[c];
-  o[30] = 0.0; o[31] = 0.0;
 }
 
 // ---------------------------------------------------------------------------------------------
