@@ -17,6 +17,70 @@ constexpr int MAX_VG = 8;
 enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 };
 
 // ---------------------------------------------------------------------------------------------
+// Problem setup on the device (ValidateAndCreate): what BundleAdjuster::AddView/AddTrack decide while walking the
+// reconstruction (bundle_adjuster.cc:116-221) - which blocks exist, which are constant - plus the index validation.
+enum { SF_BAD_INDEX = 0, SF_BAD_GROUP = 1, SF_RED_VARIABLE = 2, SF_PT_VARIABLE = 3, SF_HAS_FIXED = 4, SF_COUNT = 8 };
+
+__global__ void k_setup_check_groups(int nc, int ng, const int* __restrict__ cam_group, int* __restrict__ flags) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc && (cam_group[c] < 0 || cam_group[c] >= ng)) flags[SF_BAD_GROUP] = 1;
+}
+
+// observation histogram per point and per camera; marks the intrinsics groups that own a residual
+__global__ void k_setup_count(int no, int nc, int np, int ng, const int* __restrict__ obs_cam, const int* __restrict__ obs_pt,
+                              const int* __restrict__ cam_group, int* __restrict__ pt_cnt, int* __restrict__ cam_cnt,
+                              int* __restrict__ used, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= no) return;
+  const int c = obs_cam[i], p = obs_pt[i];
+  if (c < 0 || c >= nc || p < 0 || p >= np) { flags[SF_BAD_INDEX] = 1; return; }
+  atomicAdd(pt_cnt + p, 1);
+  atomicAdd(cam_cnt + c, 1);
+  const int g = cam_group[c];
+  if (g >= 0 && g < ng && used[g] == 0) used[g] = 1;
+}
+
+// blocks without observations are not part of the problem (constant); which kinds of free blocks exist
+__global__ void k_setup_const(int nc, int np, const int* __restrict__ cam_start, const int* __restrict__ pt_start,
+                              uint8_t* __restrict__ cam_const, uint8_t* __restrict__ pt_const, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nc) {
+    const uint8_t v = (cam_start[i + 1] == cam_start[i]) ? (uint8_t)THB_CAM_CONST_ALL : (uint8_t)(cam_const[i] & THB_CAM_CONST_ALL);
+    cam_const[i] = v;
+    if (v != THB_CAM_CONST_ALL) flags[SF_RED_VARIABLE] = 1;
+  } else if (i - nc < np) {
+    const int p = i - nc;
+    const uint8_t v = (pt_start[p + 1] == pt_start[p] || pt_const[p]) ? 1 : 0;
+    pt_const[p] = v;
+    if (!v) flags[SF_PT_VARIABLE] = 1;
+  }
+}
+
+// observations of one ordering, gathered from the caller's arrays
+__global__ void k_setup_gather(int no, const int* __restrict__ perm, const int* __restrict__ raw_cam, const int* __restrict__ raw_pt,
+                               const double2* __restrict__ raw_xy, const double2* __restrict__ raw_si, int* __restrict__ o_cam,
+                               int* __restrict__ o_pt, double2* __restrict__ o_xy, double2* __restrict__ o_si) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= no) return;
+  const int i = perm[q];
+  o_cam[q] = raw_cam[i]; o_pt[q] = raw_pt[i];
+  o_xy[q] = raw_xy[i];
+  o_si[q] = raw_si ? raw_si[i] : make_double2(1.0, 1.0);
+}
+
+// intrinsics slot of every point-major observation; detects residual blocks whose parameter blocks are all constant
+__global__ void k_setup_slots(int no, const int* __restrict__ op_cam, const int* __restrict__ op_pt, const int* __restrict__ cam_group,
+                              const int* __restrict__ intr_slot, const uint8_t* __restrict__ cam_const,
+                              const uint8_t* __restrict__ pt_const, int8_t* __restrict__ op_slot, int* __restrict__ flags) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= no) return;
+  const int c = op_cam[q];
+  const int sl = intr_slot[cam_group[c]];
+  op_slot[q] = (int8_t)sl;
+  if (sl < 0 && cam_const[c] == THB_CAM_CONST_ALL && pt_const[op_pt[q]]) flags[SF_HAS_FIXED] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Per-camera record (ba_device.cuh): angle-axis vector plus the scalar coefficients of the rotation
 // (ceres::AngleAxisRotatePoint semantics, incl. the first-order branch for theta^2 <= eps) and of the SO(3) left
 // Jacobian used for d(R v)/d(aa).

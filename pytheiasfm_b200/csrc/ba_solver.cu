@@ -10,9 +10,11 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "ba_setup.cuh"
 #include "dense_chol.cuh"
 
 namespace thb {
@@ -20,13 +22,61 @@ namespace {
 
 thread_local std::string g_last_error;
 
-template <typename T>
-int DevAlloc(T** p, size_t n) {
-  *p = nullptr;
-  if (n == 0) n = 1;
-  THB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
-  return THB_OK;
+// Stream-ordered allocation from the device's default memory pool. The pool keeps freed blocks (release threshold =
+// max), so a solve after the first one pays no cudaMalloc/cudaFree: BundleAdjustTrack-style callers create thousands of
+// short sessions.
+void ConfigurePoolOnce() {
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [dev] {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  });
 }
+
+struct Arena {  // every device buffer of a session; released in one go on the session's stream
+  std::vector<void*> blocks;
+  cudaStream_t st = nullptr;
+  template <typename T>
+  int Get(T** p, size_t n) {
+    *p = nullptr;
+    void* q = nullptr;
+    THB_CUDA_CHECK(cudaMallocAsync(&q, std::max<size_t>(1, n) * sizeof(T), st));
+    blocks.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return THB_OK;
+  }
+  void Release() {
+    for (void* q : blocks) cudaFreeAsync(q, st);
+    blocks.clear();
+  }
+};
+
+// Pinned host blocks for the per-iteration scalar read-back, recycled across sessions (cudaMallocHost is slow).
+struct PinnedCache {
+  std::mutex mu;
+  std::vector<void*> free_blocks;
+  static constexpr size_t kBytes = 1024;
+  void* Get() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!free_blocks.empty()) { void* q = free_blocks.back(); free_blocks.pop_back(); return q; }
+    }
+    void* q = nullptr;
+    if (cudaMallocHost(&q, kBytes) != cudaSuccess) return nullptr;
+    return q;
+  }
+  void Put(void* q) {
+    if (!q) return;
+    std::lock_guard<std::mutex> lk(mu);
+    free_blocks.push_back(q);
+  }
+};
+PinnedCache g_pinned;
 
 inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
 
@@ -101,27 +151,17 @@ struct ThbBaSession {
   ThbBaSummary sum{};
   PhaseTimer t_jac, t_normal, t_solve, t_update;
   std::chrono::steady_clock::time_point t_create, t_solve_start;
-  std::vector<int> h_perm_p;  // point-major position -> caller's observation index
+  Arena arena;
+  void* h_block = nullptr;  // pinned block behind h_scal / h_flag
 };
 
 namespace {
 
 void FreeSession(ThbBaSession* s) {
   if (!s) return;
-  cudaFree(s->X.cam); cudaFree(s->X.camd); cudaFree(s->X.intr); cudaFree(s->X.pts);
-  cudaFree(s->Xc.cam); cudaFree(s->Xc.camd); cudaFree(s->Xc.intr); cudaFree(s->Xc.pts);
-  cudaFree(s->d_cam_group); cudaFree(s->d_intr_model); cudaFree(s->d_intr_slot); cudaFree(s->d_cam_const);
-  cudaFree(s->d_pt_const); cudaFree(s->d_intr_const);
-  cudaFree(s->d_op_cam); cudaFree(s->d_op_pt); cudaFree(s->d_oc_cam); cudaFree(s->d_oc_pt);
-  cudaFree(s->d_op_xy); cudaFree(s->d_op_si); cudaFree(s->d_oc_xy); cudaFree(s->d_oc_si);
-  cudaFree(s->d_pt_start); cudaFree(s->d_cam_start); cudaFree(s->d_chunk_pt);
-  cudaFree(s->d_r); cudaFree(s->d_jc); cudaFree(s->d_jp); cudaFree(s->d_cs); cudaFree(s->d_ps);
-  cudaFree(s->d_ji); cudaFree(s->d_op_slot); cudaFree(s->d_slot_group); cudaFree(s->d_zt); cudaFree(s->d_ilo); cudaFree(s->d_ihi);
-  cudaFree(s->d_vinv); cudaFree(s->d_gp); cudaFree(s->d_pdiag); cudaFree(s->d_braw); cudaFree(s->d_cdiag); cudaFree(s->d_yp);
-  cudaFree(s->d_scal); cudaFree(s->d_flag); cudaFree(s->d_flush);
-  if (s->h_scal) cudaFreeHost(s->h_scal);
-  if (s->h_flag) cudaFreeHost(s->h_flag);
-  s->chol.Free();
+  s->chol.Free(s->st);
+  s->arena.Release();
+  g_pinned.Put(s->h_block);
   s->t_jac.Free(); s->t_normal.Free(); s->t_solve.Free(); s->t_update.Free();
   delete s;
 }
@@ -152,9 +192,9 @@ int CheckDevice() {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) THB_FAIL(THB_E_NO_DEVICE, "no CUDA device visible; libtheia_b200 has no CPU path");
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceProp pr;
-  THB_CUDA_CHECK(cudaGetDeviceProperties(&pr, dev));
-  if (pr.major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
+  int major = 0;
+  THB_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
   return THB_OK;
 }
 
@@ -470,53 +510,96 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
 #define THB_TRY(expr) do { rc = (expr); if (rc != THB_OK) { FreeSession(s); return rc; } } while (0)
 #define THB_TRY_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { SetLastError(std::string(#expr) + ": " + cudaGetErrorString(_e)); FreeSession(s); return THB_E_CUDA; } } while (0)
 
-  // ---- structure on the host: validation, constness, the two observation orders ----
-  std::vector<int> h_cam_group, h_intr_model, h_obs_cam, h_obs_pt;
-  std::vector<uint8_t> h_cam_const(nc, 0), h_pt_const(np, 0);
+  // ---- device memory (stream-ordered, pooled) ----
+  ConfigurePoolOnce();
+  s->arena.st = s->st;
+  Arena& M = s->arena;
+  cudaStream_t st = s->st;
+  s->h_block = g_pinned.Get();
+  if (!s->h_block) { FreeSession(s); THB_FAIL(THB_E_CUDA, "cudaMallocHost failed"); }
+  s->h_scal = reinterpret_cast<double*>(s->h_block);
+  s->h_flag = reinterpret_cast<int*>(reinterpret_cast<char*>(s->h_block) + 128);
+  int* h_setup = reinterpret_cast<int*>(reinterpret_cast<char*>(s->h_block) + 256);  // SF_COUNT ints
+  THB_TRY(M.Get(&s->X.cam, (size_t)nc * 6)); THB_TRY(M.Get(&s->X.camd, (size_t)nc * CAMD));
+  THB_TRY(M.Get(&s->X.intr, (size_t)ng * KS)); THB_TRY(M.Get(&s->X.pts, (size_t)np * 4));
+  THB_TRY(M.Get(&s->Xc.cam, (size_t)nc * 6)); THB_TRY(M.Get(&s->Xc.camd, (size_t)nc * CAMD));
+  THB_TRY(M.Get(&s->Xc.intr, (size_t)ng * KS)); THB_TRY(M.Get(&s->Xc.pts, (size_t)np * 4));
+  THB_TRY(M.Get(&s->d_cam_group, nc)); THB_TRY(M.Get(&s->d_intr_model, ng)); THB_TRY(M.Get(&s->d_intr_slot, ng));
+  THB_TRY(M.Get(&s->d_cam_const, nc)); THB_TRY(M.Get(&s->d_pt_const, np)); THB_TRY(M.Get(&s->d_intr_const, ng));
+  THB_TRY(M.Get(&s->d_op_cam, no)); THB_TRY(M.Get(&s->d_op_pt, no)); THB_TRY(M.Get(&s->d_oc_cam, no)); THB_TRY(M.Get(&s->d_oc_pt, no));
+  THB_TRY(M.Get(&s->d_op_xy, no)); THB_TRY(M.Get(&s->d_op_si, no)); THB_TRY(M.Get(&s->d_oc_xy, no)); THB_TRY(M.Get(&s->d_oc_si, no));
+  THB_TRY(M.Get(&s->d_pt_start, np + 1)); THB_TRY(M.Get(&s->d_cam_start, nc + 1));
+  THB_TRY(M.Get(&s->d_r, (size_t)no * 2)); THB_TRY(M.Get(&s->d_jc, (size_t)no * 12)); THB_TRY(M.Get(&s->d_jp, (size_t)no * 2 * s->PD));
+  THB_TRY(M.Get(&s->d_ps, (size_t)np * s->PD));
+  THB_TRY(M.Get(&s->d_vinv, (size_t)np * s->PD * s->PD)); THB_TRY(M.Get(&s->d_gp, (size_t)np * s->PD)); THB_TRY(M.Get(&s->d_pdiag, (size_t)np * s->PD));
+  THB_TRY(M.Get(&s->d_yp, (size_t)np * s->PD));
+  THB_TRY(M.Get(&s->d_scal, SC_COUNT)); THB_TRY(M.Get(&s->d_flag, FL_COUNT));
+  THB_TRY(M.Get(&s->d_op_slot, no));
+  int *d_used = nullptr, *d_setup = nullptr, *d_perm = nullptr;
+  THB_TRY(M.Get(&d_used, ng)); THB_TRY(M.Get(&d_setup, SF_COUNT)); THB_TRY(M.Get(&d_perm, no));
+
+  // ---- the caller's arrays on the device (memory_space == DEVICE: used in place) ----
+  const cudaMemcpyKind kin = sp == THB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  const int *raw_cam = P->obs_cam, *raw_pt = P->obs_pt;
+  const double2* raw_xy = reinterpret_cast<const double2*>(P->obs_xy);
+  const double2* raw_si = reinterpret_cast<const double2*>(P->obs_sqrt_info);
+  if (sp == THB_MEM_HOST && no > 0) {
+    int *dc = nullptr, *dp = nullptr; double2 *dxy = nullptr, *dsi = nullptr;
+    THB_TRY(M.Get(&dc, no)); THB_TRY(M.Get(&dp, no)); THB_TRY(M.Get(&dxy, no));
+    THB_TRY_CUDA(cudaMemcpyAsync(dc, P->obs_cam, sizeof(int) * no, cudaMemcpyHostToDevice, st));
+    THB_TRY_CUDA(cudaMemcpyAsync(dp, P->obs_pt, sizeof(int) * no, cudaMemcpyHostToDevice, st));
+    THB_TRY_CUDA(cudaMemcpyAsync(dxy, P->obs_xy, sizeof(double2) * no, cudaMemcpyHostToDevice, st));
+    if (P->obs_sqrt_info) {
+      THB_TRY(M.Get(&dsi, no));
+      THB_TRY_CUDA(cudaMemcpyAsync(dsi, P->obs_sqrt_info, sizeof(double2) * no, cudaMemcpyHostToDevice, st));
+    }
+    raw_cam = dc; raw_pt = dp; raw_xy = dxy; raw_si = dsi;
+  }
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.cam, P->cam_ext, sizeof(double) * nc * 6, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->X.pts, P->pts, sizeof(double) * np * 4, kin, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->Xc.intr, s->X.intr, sizeof(double) * ng * KS, cudaMemcpyDeviceToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, P->cam_group, sizeof(int) * nc, kin, st));
+  if (P->cam_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, P->cam_const, nc, kin, st));
+  else THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_const, 0, std::max(nc, 1), st));
+  if (P->pt_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, P->pt_const, np, kin, st));
+  else THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_const, 0, std::max(np, 1), st));
+
+  // ---- structure: validation, constness, the two observation orders (histogram + scan + stable radix sort) ----
+  THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_start, 0, sizeof(int) * (np + 1), st));
+  THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_start, 0, sizeof(int) * (nc + 1), st));
+  THB_TRY_CUDA(cudaMemsetAsync(d_used, 0, sizeof(int) * std::max(ng, 1), st));
+  THB_TRY_CUDA(cudaMemsetAsync(d_setup, 0, sizeof(int) * SF_COUNT, st));
+  if (nc > 0) k_setup_check_groups<<<cdiv(nc, 256), 256, 0, st>>>(nc, ng, s->d_cam_group, d_setup);
+  if (no > 0) k_setup_count<<<cdiv(no, 256), 256, 0, st>>>(no, nc, np, ng, raw_cam, raw_pt, s->d_cam_group, s->d_pt_start, s->d_cam_start, d_used, d_setup);
+  // indices must be known good before they key a sort
+  THB_TRY_CUDA(cudaMemcpyAsync(h_setup, d_setup, sizeof(int) * SF_COUNT, cudaMemcpyDeviceToHost, st));
+  std::vector<int> h_intr_model;
   std::vector<uint16_t> h_intr_const(ng, 0xffff);
-  THB_TRY(FetchToHost(P->cam_group, nc, sp, &h_cam_group));
   THB_TRY(FetchToHost(P->intr_model, ng, sp, &h_intr_model));
-  THB_TRY(FetchToHost(P->obs_cam, no, sp, &h_obs_cam));
-  THB_TRY(FetchToHost(P->obs_pt, no, sp, &h_obs_pt));
-  if (P->cam_const) THB_TRY(FetchToHost(P->cam_const, nc, sp, &h_cam_const));
-  if (P->pt_const) THB_TRY(FetchToHost(P->pt_const, np, sp, &h_pt_const));
   if (P->intr_const) THB_TRY(FetchToHost(P->intr_const, ng, sp, &h_intr_const));
-  for (int g = 0; g < ng; ++g) {
-    const int K = num_intrinsics(h_intr_model[g]);
-    if (K < 0) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path"); }
-  }
-  for (int c = 0; c < nc; ++c)
-    if (h_cam_group[c] < 0 || h_cam_group[c] >= ng) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range"); }
-  std::vector<int> pt_start(np + 1, 0), cam_start(nc + 1, 0);
-  for (int i = 0; i < no; ++i) {
-    const int c = h_obs_cam[i], p = h_obs_pt[i];
-    if (c < 0 || c >= nc || p < 0 || p >= np) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range"); }
-    ++pt_start[p + 1]; ++cam_start[c + 1];
-  }
-  // blocks without observations are not part of the problem
-  for (int c = 0; c < nc; ++c) if (cam_start[c + 1] == 0) h_cam_const[c] = THB_CAM_CONST_ALL; else h_cam_const[c] &= THB_CAM_CONST_ALL;
-  for (int p = 0; p < np; ++p) if (pt_start[p + 1] == 0) h_pt_const[p] = 1;
-  for (int p = 0; p < np; ++p) pt_start[p + 1] += pt_start[p];
-  for (int c = 0; c < nc; ++c) cam_start[c + 1] += cam_start[c];
-  std::vector<int> perm_p(no), perm_c(no);
-  {
-    std::vector<int> cur(pt_start.begin(), pt_start.end() - 1);
-    for (int i = 0; i < no; ++i) perm_p[cur[h_obs_pt[i]]++] = i;
-    std::vector<int> cur2(cam_start.begin(), cam_start.end() - 1);
-    for (int i = 0; i < no; ++i) perm_c[cur2[h_obs_cam[i]]++] = i;
-  }
-  s->h_perm_p = perm_p;
+  for (int g = 0; g < ng; ++g)
+    if (num_intrinsics(h_intr_model[g]) < 0) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path"); }
+  THB_TRY_CUDA(cudaStreamSynchronize(st));
+  if (h_setup[SF_BAD_GROUP]) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range"); }
+  if (h_setup[SF_BAD_INDEX]) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range"); }
+  THB_TRY(GroupByKey(raw_pt, no, np, s->d_pt_start, d_perm, st));
+  if (no > 0) k_setup_gather<<<cdiv(no, 256), 256, 0, st>>>(no, d_perm, raw_cam, raw_pt, raw_xy, raw_si, s->d_op_cam, s->d_op_pt, s->d_op_xy, s->d_op_si);
+  THB_TRY(GroupByKey(raw_cam, no, nc, s->d_cam_start, d_perm, st));
+  if (no > 0) k_setup_gather<<<cdiv(no, 256), 256, 0, st>>>(no, d_perm, raw_cam, raw_pt, raw_xy, raw_si, s->d_oc_cam, s->d_oc_pt, s->d_oc_xy, s->d_oc_si);
+  if (nc + np > 0) k_setup_const<<<cdiv((long long)nc + np, 256), 256, 0, st>>>(nc, np, s->d_cam_start, s->d_pt_start, s->d_cam_const, s->d_pt_const, d_setup);
+  std::vector<int> pt_start(np + 1, 0), used(ng, 0);
+  THB_TRY_CUDA(cudaMemcpyAsync(pt_start.data(), s->d_pt_start, sizeof(int) * (np + 1), cudaMemcpyDeviceToHost, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(used.data(), d_used, sizeof(int) * ng, cudaMemcpyDeviceToHost, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(h_setup, d_setup, sizeof(int) * SF_COUNT, cudaMemcpyDeviceToHost, st));
+  THB_TRY_CUDA(cudaStreamSynchronize(st));
   s->model = ng > 0 ? h_intr_model[0] : THB_MODEL_PINHOLE;
   for (int g = 1; g < ng; ++g) if (h_intr_model[g] != s->model) s->model = -1;
   // variable intrinsics groups: observed by at least one residual and with at least one free coordinate
   std::vector<int> slot(ng, -1), slot_group;
-  {
-    std::vector<char> used(ng, 0);
-    for (int i = 0; i < no; ++i) used[h_cam_group[h_obs_cam[i]]] = 1;
-    for (int g = 0; g < ng; ++g) {
-      const unsigned all = (1u << num_intrinsics(h_intr_model[g])) - 1;
-      if (used[g] && (h_intr_const[g] & all) != all) { slot[g] = (int)slot_group.size(); slot_group.push_back(g); }
-    }
+  for (int g = 0; g < ng; ++g) {
+    const unsigned all = (1u << num_intrinsics(h_intr_model[g])) - 1;
+    if (used[g] && (h_intr_const[g] & all) != all) { slot[g] = (int)slot_group.size(); slot_group.push_back(g); }
   }
   s->nvg = (int)slot_group.size();
   if (s->nvg > MAX_VG) {
@@ -524,16 +607,8 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
     THB_FAIL(THB_E_UNSUPPORTED, "more than 8 intrinsics groups with free parameters are not supported (shared-intrinsics design)");
   }
   s->constrained = s->nvg > 0;  // focal length >= 1 is always set on a non-constant block (bundle_adjuster.cc:396-405)
-  s->red_variable = s->nvg > 0; s->any_variable = false;
-  for (int c = 0; c < nc; ++c) if (h_cam_const[c] != THB_CAM_CONST_ALL) s->red_variable = true;
-  for (int p = 0; p < np; ++p) if (!h_pt_const[p]) s->any_variable = true;
-  s->any_variable |= s->red_variable;
-  // Ceres drops residual blocks whose parameter blocks are all constant (their cost is Summary::fixed_cost);
-  // they still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
-  bool has_fixed = false;
-  for (int i = 0; i < no && !has_fixed; ++i)
-    has_fixed = h_cam_const[h_obs_cam[i]] == THB_CAM_CONST_ALL && h_pt_const[h_obs_pt[i]] && slot[h_cam_group[h_obs_cam[i]]] < 0;
-  if (has_fixed && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera, intrinsics and point are all constant are not supported in a problem with free blocks"); }
+  s->red_variable = s->nvg > 0 || h_setup[SF_RED_VARIABLE] != 0;
+  s->any_variable = s->red_variable || h_setup[SF_PT_VARIABLE] != 0;
   // Schur chunks: consecutive points with <= 64 observations in total
   std::vector<int> chunk_pt;
   chunk_pt.push_back(0);
@@ -545,50 +620,15 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   chunk_pt.push_back(np);
   s->nchunks = (int)chunk_pt.size() - 1;
   s->n_red = 6 * nc + NI * s->nvg;
-
-  // ---- device memory ----
-  THB_TRY(DevAlloc(&s->X.cam, (size_t)nc * 6)); THB_TRY(DevAlloc(&s->X.camd, (size_t)nc * CAMD));
-  THB_TRY(DevAlloc(&s->X.intr, (size_t)ng * KS)); THB_TRY(DevAlloc(&s->X.pts, (size_t)np * 4));
-  THB_TRY(DevAlloc(&s->Xc.cam, (size_t)nc * 6)); THB_TRY(DevAlloc(&s->Xc.camd, (size_t)nc * CAMD));
-  THB_TRY(DevAlloc(&s->Xc.intr, (size_t)ng * KS)); THB_TRY(DevAlloc(&s->Xc.pts, (size_t)np * 4));
-  THB_TRY(DevAlloc(&s->d_cam_group, nc)); THB_TRY(DevAlloc(&s->d_intr_model, ng)); THB_TRY(DevAlloc(&s->d_intr_slot, ng));
-  THB_TRY(DevAlloc(&s->d_cam_const, nc)); THB_TRY(DevAlloc(&s->d_pt_const, np)); THB_TRY(DevAlloc(&s->d_intr_const, ng));
-  THB_TRY(DevAlloc(&s->d_op_cam, no)); THB_TRY(DevAlloc(&s->d_op_pt, no)); THB_TRY(DevAlloc(&s->d_oc_cam, no)); THB_TRY(DevAlloc(&s->d_oc_pt, no));
-  THB_TRY(DevAlloc(&s->d_op_xy, no)); THB_TRY(DevAlloc(&s->d_op_si, no)); THB_TRY(DevAlloc(&s->d_oc_xy, no)); THB_TRY(DevAlloc(&s->d_oc_si, no));
-  THB_TRY(DevAlloc(&s->d_pt_start, np + 1)); THB_TRY(DevAlloc(&s->d_cam_start, nc + 1)); THB_TRY(DevAlloc(&s->d_chunk_pt, chunk_pt.size()));
-  THB_TRY(DevAlloc(&s->d_r, (size_t)no * 2)); THB_TRY(DevAlloc(&s->d_jc, (size_t)no * 12)); THB_TRY(DevAlloc(&s->d_jp, (size_t)no * 2 * s->PD));
-  THB_TRY(DevAlloc(&s->d_cs, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_ps, (size_t)np * s->PD));
-  THB_TRY(DevAlloc(&s->d_vinv, (size_t)np * s->PD * s->PD)); THB_TRY(DevAlloc(&s->d_gp, (size_t)np * s->PD)); THB_TRY(DevAlloc(&s->d_pdiag, (size_t)np * s->PD));
-  THB_TRY(DevAlloc(&s->d_braw, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_cdiag, (size_t)s->n_red)); THB_TRY(DevAlloc(&s->d_yp, (size_t)np * s->PD));
-  THB_TRY(DevAlloc(&s->d_scal, SC_COUNT)); THB_TRY(DevAlloc(&s->d_flag, FL_COUNT));
-  THB_TRY(DevAlloc(&s->d_op_slot, no)); THB_TRY(DevAlloc(&s->d_slot_group, s->nvg));
-  THB_TRY(DevAlloc(&s->d_ilo, (size_t)NI * s->nvg)); THB_TRY(DevAlloc(&s->d_ihi, (size_t)NI * s->nvg));
+  THB_TRY(M.Get(&s->d_chunk_pt, chunk_pt.size()));
+  THB_TRY(M.Get(&s->d_cs, (size_t)s->n_red)); THB_TRY(M.Get(&s->d_braw, (size_t)s->n_red)); THB_TRY(M.Get(&s->d_cdiag, (size_t)s->n_red));
+  THB_TRY(M.Get(&s->d_slot_group, s->nvg));
+  THB_TRY(M.Get(&s->d_ilo, (size_t)NI * s->nvg)); THB_TRY(M.Get(&s->d_ihi, (size_t)NI * s->nvg));
   if (s->nvg > 0) {
-    THB_TRY(DevAlloc(&s->d_ji, (size_t)no * 2 * NI));
-    THB_TRY(DevAlloc(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
+    THB_TRY(M.Get(&s->d_ji, (size_t)no * 2 * NI));
+    THB_TRY(M.Get(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
   }
-  THB_TRY_CUDA(cudaMallocHost(&s->h_scal, sizeof(double) * SC_COUNT));
-  THB_TRY_CUDA(cudaMallocHost(&s->h_flag, sizeof(int) * FL_COUNT));
-  THB_TRY(s->chol.Init(std::max(1, s->n_red)));
-
-  // ---- upload ----
-  const cudaMemcpyKind kin = sp == THB_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
-  cudaStream_t st = s->st;
-  THB_TRY_CUDA(cudaMemcpyAsync(s->X.cam, P->cam_ext, sizeof(double) * nc * 6, kin, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->X.pts, P->pts, sizeof(double) * np * 4, kin, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->Xc.intr, s->X.intr, sizeof(double) * ng * KS, cudaMemcpyDeviceToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, h_cam_group.data(), sizeof(int) * nc, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_model, h_intr_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_slot, slot.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, h_cam_const.data(), nc, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, h_pt_const.data(), np, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_const, h_intr_const.data(), sizeof(uint16_t) * ng, cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_start, pt_start.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_start, cam_start.data(), sizeof(int) * (nc + 1), cudaMemcpyHostToDevice, st));
-  THB_TRY_CUDA(cudaMemcpyAsync(s->d_chunk_pt, chunk_pt.data(), sizeof(int) * chunk_pt.size(), cudaMemcpyHostToDevice, st));
-  std::vector<int8_t> op_slot(no);
-  for (int q = 0; q < no; ++q) op_slot[q] = (int8_t)slot[h_cam_group[h_obs_cam[perm_p[q]]]];
+  THB_TRY(s->chol.Init(std::max(1, s->n_red), st));
   // box constraints of bundle_adjuster.cc:396-427
   std::vector<double> ilo((size_t)NI * s->nvg, -std::numeric_limits<double>::max()), ihi((size_t)NI * s->nvg, std::numeric_limits<double>::max());
   for (int sl = 0; sl < s->nvg; ++sl) {
@@ -597,32 +637,20 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
     if (m == THB_MODEL_DOUBLE_SPHERE) { ilo[NI * sl + 5] = -1.0; ihi[NI * sl + 5] = 1.0; ilo[NI * sl + 6] = 0.0; ihi[NI * sl + 6] = 1.0; }
     else if (m == THB_MODEL_EXTENDED_UNIFIED) { ilo[NI * sl + 5] = 0.0; ihi[NI * sl + 5] = 1.0; ilo[NI * sl + 6] = 0.1; }
   }
-  THB_TRY_CUDA(cudaMemcpy(s->d_op_slot, op_slot.data(), no, cudaMemcpyHostToDevice));
-  THB_TRY_CUDA(cudaMemcpy(s->d_slot_group, slot_group.data(), sizeof(int) * s->nvg, cudaMemcpyHostToDevice));
-  THB_TRY_CUDA(cudaMemcpy(s->d_ilo, ilo.data(), sizeof(double) * ilo.size(), cudaMemcpyHostToDevice));
-  THB_TRY_CUDA(cudaMemcpy(s->d_ihi, ihi.data(), sizeof(double) * ihi.size(), cudaMemcpyHostToDevice));
-  {
-    // reorder observations on the host (the reference walks hash maps at this point, bundle_adjuster.cc:116-173)
-    std::vector<double> h_xy, h_si;
-    THB_TRY(FetchToHost(P->obs_xy, (size_t)no * 2, sp, &h_xy));
-    if (P->obs_sqrt_info) THB_TRY(FetchToHost(P->obs_sqrt_info, (size_t)no * 2, sp, &h_si));
-    else h_si.assign((size_t)no * 2, 1.0);
-    std::vector<int> oc(no), op(no);
-    std::vector<double> xy((size_t)no * 2), si((size_t)no * 2);
-    for (int pass = 0; pass < 2; ++pass) {
-      const std::vector<int>& perm = pass == 0 ? perm_p : perm_c;
-      for (int q = 0; q < no; ++q) {
-        const int i = perm[q];
-        oc[q] = h_obs_cam[i]; op[q] = h_obs_pt[i];
-        xy[2 * (size_t)q] = h_xy[2 * (size_t)i]; xy[2 * (size_t)q + 1] = h_xy[2 * (size_t)i + 1];
-        si[2 * (size_t)q] = h_si[2 * (size_t)i]; si[2 * (size_t)q + 1] = h_si[2 * (size_t)i + 1];
-      }
-      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_cam : s->d_oc_cam, oc.data(), sizeof(int) * no, cudaMemcpyHostToDevice));
-      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_pt : s->d_oc_pt, op.data(), sizeof(int) * no, cudaMemcpyHostToDevice));
-      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_xy : s->d_oc_xy, xy.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice));
-      THB_TRY_CUDA(cudaMemcpy(pass == 0 ? s->d_op_si : s->d_oc_si, si.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice));
-    }
-  }
+  // pageable sources: these copies complete before the call returns
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_model, h_intr_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_const, h_intr_const.data(), sizeof(uint16_t) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_intr_slot, slot.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_chunk_pt, chunk_pt.data(), sizeof(int) * chunk_pt.size(), cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_slot_group, slot_group.data(), sizeof(int) * s->nvg, cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_ilo, ilo.data(), sizeof(double) * ilo.size(), cudaMemcpyHostToDevice, st));
+  THB_TRY_CUDA(cudaMemcpyAsync(s->d_ihi, ihi.data(), sizeof(double) * ihi.size(), cudaMemcpyHostToDevice, st));
+  if (no > 0) k_setup_slots<<<cdiv(no, 256), 256, 0, st>>>(no, s->d_op_cam, s->d_op_pt, s->d_cam_group, s->d_intr_slot, s->d_cam_const, s->d_pt_const, s->d_op_slot, d_setup);
+  // Ceres drops residual blocks whose parameter blocks are all constant (their cost is Summary::fixed_cost);
+  // they would still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
+  THB_TRY_CUDA(cudaMemcpyAsync(h_setup, d_setup, sizeof(int) * SF_COUNT, cudaMemcpyDeviceToHost, st));
+  THB_TRY_CUDA(cudaStreamSynchronize(st));  // also: the host vectors above may now go out of scope
+  if (h_setup[SF_HAS_FIXED] && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera, intrinsics and point are all constant are not supported in a problem with free blocks"); }
   s->Op = ObsSoA{s->d_op_cam, s->d_op_pt, s->d_op_xy, s->d_op_si};
   s->Oc = ObsSoA{s->d_oc_cam, s->d_oc_pt, s->d_oc_xy, s->d_oc_si};
   s->K = BaConst{nc, ng, np, no, s->d_cam_group, s->d_intr_model, s->d_cam_const, s->d_intr_const, s->d_pt_const, s->d_intr_slot,
@@ -771,7 +799,8 @@ int thb_ba_time_jacobian(ThbBaSession* s, int32_t repeats, int32_t flush_l2, dou
   // nobody: a write-flush (memset) would leave dirty lines whose write-back gets billed to the timed kernel.
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2 && !s->d_flush) {
-    THB_CUDA_CHECK(cudaMalloc(&s->d_flush, flush_bytes));
+    THB_CUDA_CHECK(cudaMallocAsync(&s->d_flush, flush_bytes, s->st));
+    s->arena.blocks.push_back(s->d_flush);
     THB_CUDA_CHECK(cudaMemsetAsync(s->d_flush, 0, flush_bytes, s->st));
     THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
   }
@@ -801,7 +830,8 @@ int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, 
   if (rc != THB_OK) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   DenseChol ch;
-  if ((rc = ch.Init(n)) != THB_OK) { ch.Free(); return rc; }
+  ConfigurePoolOnce();
+  if ((rc = ch.Init(n, st)) != THB_OK) { ch.Free(st); return rc; }
   DevBufs B;
   int* d_fail = B.get<int>(1);
   int launches = 0, h_fail = 0;
@@ -813,7 +843,7 @@ int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, 
   if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpyAsync(x, ch.x, sizeof(double) * n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && rc == THB_OK) e = cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess && rc == THB_OK) e = cudaStreamSynchronize(st);
-  ch.Free();
+  ch.Free(st);
   if (e != cudaSuccess) THB_FAIL(THB_E_CUDA, cudaGetErrorString(e));
   if (rc != THB_OK) return rc;
   if (h_fail) THB_FAIL(THB_E_NUMERICAL, "matrix is not positive definite");

@@ -20,6 +20,7 @@
 #include "dense_chol.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace thb {
 
@@ -366,27 +367,34 @@ __global__ void chol_copy_row_kernel(const double* __restrict__ src, double* __r
 
 }  // namespace
 
-int DenseChol::Init(int n_) {
+int DenseChol::Init(int n_, cudaStream_t st) {
   n = n_;
   n_pad = (n + OB - 1) / OB * OB;
   ld = n_pad;
   nblk = n_pad / NB;
   rows_total = n_pad + 1;  // + the rhs row
-  THB_CUDA_CHECK(cudaMalloc(&A, sizeof(double) * (size_t)rows_total * ld));
-  THB_CUDA_CHECK(cudaMalloc(&dinv, sizeof(double) * (size_t)nblk * NB * NB));
-  THB_CUDA_CHECK(cudaMalloc(&x, sizeof(double) * n_pad));
-  THB_CUDA_CHECK(cudaMalloc(&ready, sizeof(int) * nblk));
-  THB_CUDA_CHECK(cudaMalloc(&rdiag, sizeof(double) * n_pad));
-  THB_CUDA_CHECK(cudaFuncSetAttribute(chol_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
-  THB_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kInvSmem));
-  THB_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<OB, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(STAGES * (OB + OB) * LDK * sizeof(double))));
-  THB_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<OB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(STAGES * (NB + OB) * LDK * sizeof(double))));
-  THB_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<NB, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(STAGES * (NB + NB) * LDK * sizeof(double))));
+  // stream-ordered allocations out of the device's default pool (kept warm by ConfigurePoolOnce in ba_solver.cu)
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&A), sizeof(double) * (size_t)rows_total * ld, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&dinv), sizeof(double) * (size_t)nblk * NB * NB, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&x), sizeof(double) * n_pad, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ready), sizeof(int) * nblk, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rdiag), sizeof(double) * n_pad, st));
+  static std::once_flag attr_once[64];
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once[dev & 63], [&attr_err] {
+    auto set = [&attr_err](const void* f, int bytes) {
+      const cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+      if (e != cudaSuccess) attr_err = e;
+    };
+    set((const void*)chol_inverse_kernel, kInvSmem);
+    set((const void*)chol_panel_kernel, kInvSmem);
+    set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
+    set((const void*)chol_update_kernel<OB, NB>, (int)(STAGES * (NB + OB) * LDK * sizeof(double)));
+    set((const void*)chol_update_kernel<NB, NB>, (int)(STAGES * (NB + NB) * LDK * sizeof(double)));
+  });
+  THB_CUDA_CHECK(attr_err);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   num_sms = sms > 0 ? sms : 148;
   THB_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
@@ -398,8 +406,12 @@ int DenseChol::Init(int n_) {
   return THB_OK;
 }
 
-void DenseChol::Free() {
-  cudaFree(A); cudaFree(dinv); cudaFree(x); cudaFree(ready); cudaFree(rdiag);
+void DenseChol::Free(cudaStream_t st) {
+  if (A) cudaFreeAsync(A, st);
+  if (dinv) cudaFreeAsync(dinv, st);
+  if (x) cudaFreeAsync(x, st);
+  if (ready) cudaFreeAsync(ready, st);
+  if (rdiag) cudaFreeAsync(rdiag, st);
   A = dinv = x = rdiag = nullptr; ready = nullptr;
   if (s2) { cudaStreamDestroy(s2); s2 = nullptr; }
   if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }

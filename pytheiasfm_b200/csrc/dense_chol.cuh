@@ -14,8 +14,8 @@ struct DenseChol {
   double* x = nullptr;     // n_pad solution
   int* ready = nullptr;    // per-64-block flags of the backward substitution
 
-  int Init(int n);
-  void Free();
+  int Init(int n, cudaStream_t st);  // stream-ordered allocations
+  void Free(cudaStream_t st);
   int Clear(cudaStream_t st);  // zero A, identity on the padding
   double* RhsRow() { return A + (size_t)n_pad * ld; }
   int FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches);
