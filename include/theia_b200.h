@@ -223,6 +223,14 @@ int thb_ba_time_jacobian(ThbBaSession* session, int32_t repeats, int32_t flush_l
  */
 int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, void* cuda_stream);
 
+/*
+ * Measurement entry for K4: factor + solve a synthetic diagonally dominant SPD system of order n that is built
+ * on the device, `repeats` times; returns the average milliseconds of FactorAndSolve (CUDA events on the
+ * stream; the matrix is rebuilt outside the timed region) and the max-norm residual |A x - b| of the last
+ * solve relative to |b|. Used only for roofline reporting and the ncu launch lists.
+ */
+int thb_dense_spd_time(int32_t n, int32_t repeats, double* avg_ms, double* rel_residual, void* cuda_stream);
+
 /* ------------------------------------------------------------------------------------------------
  * RANSAC two-view geometric verification (hot path 2).
  * ---------------------------------------------------------------------------------------------- */

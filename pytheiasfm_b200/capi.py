@@ -207,6 +207,8 @@ def load_library():
     lib.thb_five_point_relative_pose.restype = C.c_int
     lib.thb_dense_spd_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
     lib.thb_dense_spd_solve.restype = C.c_int
+    lib.thb_dense_spd_time.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
+    lib.thb_dense_spd_time.restype = C.c_int
     _lib = lib
     return lib
 

@@ -630,6 +630,35 @@ __global__ void k_fill(int n, double* __restrict__ a, double v) {
   if (i < n) a[i] = v;
 }
 
+// Synthetic SPD system of thb_dense_spd_time: A_ij = h(i,j) in [-1,1) for j < i, A_ii = n, b_i = h(i, n+1).
+__device__ __forceinline__ double synth_entry(int i, int j) {
+  unsigned x = (unsigned)i * 2654435761u ^ ((unsigned)j * 40503u + 0x9e3779b9u);
+  x ^= x >> 15; x *= 2246822519u; x ^= x >> 13; x *= 3266489917u; x ^= x >> 16;
+  return (double)x * (2.0 / 4294967296.0) - 1.0;
+}
+__global__ void k_synth_spd(double* __restrict__ A, int ld, int n, int n_pad) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;  // row n = the rhs row (stored at row n_pad)
+  if (j >= n) return;
+  if (i == n) A[(size_t)n_pad * ld + j] = synth_entry(j, n + 1);
+  else if (j < i) A[(size_t)i * ld + j] = synth_entry(i, j);
+  else if (j == i) A[(size_t)i * ld + j] = (double)n;
+}
+__global__ void k_synth_spd_residual(const double* __restrict__ x, int n, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double r = 0.0, bn = 0.0;
+  if (i < n) {
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc += (j == i ? (double)n : (j < i ? synth_entry(i, j) : synth_entry(j, i))) * x[j];
+    bn = fabs(synth_entry(i, n + 1));
+    r = fabs(acc - synth_entry(i, n + 1));
+  }
+  r = warp_max(r); bn = warp_max(bn);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(r));
+    atomicMax(reinterpret_cast<unsigned long long*>(out + 1), (unsigned long long)__double_as_longlong(bn));
+  }
+}
+
 // L2 flush by reading: fills the cache with clean lines of a scratch buffer
 __global__ void k_flush_read(const double2* __restrict__ buf, size_t n, double* __restrict__ sink) {
   double acc = 0.0;

@@ -850,6 +850,50 @@ int thb_dense_spd_solve(const double* A, const double* b, int32_t n, double* x, 
   return THB_OK;
 }
 
+int thb_dense_spd_time(int32_t n, int32_t repeats, double* avg_ms, double* rel_residual, void* cuda_stream) {
+  if (n <= 0 || repeats <= 0 || !avg_ms) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  ConfigurePoolOnce();
+  DenseChol ch;
+  if ((rc = ch.Init(n, st)) != THB_OK) { ch.Free(st); return rc; }
+  DevBufs B;
+  int* d_fail = B.get<int>(1);
+  double* d_res = B.get<double>(2);
+  cudaEvent_t a = nullptr, b = nullptr;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  double total = 0.0, h_res[2] = {0.0, 1.0};
+  int launches = 0, h_fail = 0;
+  cudaError_t e = cudaMemsetAsync(d_fail, 0, sizeof(int), st);
+  for (int it = 0; it < repeats && e == cudaSuccess && rc == THB_OK; ++it) {
+    rc = ch.Clear(st);
+    k_synth_spd<<<dim3((ch.n_pad + 255) / 256, n + 1), 256, 0, st>>>(ch.A, ch.ld, n, ch.n_pad);
+    cudaEventRecord(a, st);
+    if (rc == THB_OK) rc = ch.FactorAndSolve(st, d_fail, &launches);
+    cudaEventRecord(b, st);
+    e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    total += ms;
+  }
+  if (e == cudaSuccess && rc == THB_OK) {
+    cudaMemsetAsync(d_res, 0, 2 * sizeof(double), st);
+    k_synth_spd_residual<<<(n + 127) / 128, 128, 0, st>>>(ch.x, n, d_res);
+    cudaMemcpyAsync(h_res, d_res, 2 * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&h_fail, d_fail, sizeof(int), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  ch.Free(st);
+  if (e != cudaSuccess) THB_FAIL(THB_E_CUDA, cudaGetErrorString(e));
+  if (rc != THB_OK) return rc;
+  if (h_fail) THB_FAIL(THB_E_NUMERICAL, "synthetic matrix not positive definite");
+  *avg_ms = total / repeats;
+  if (rel_residual) *rel_residual = h_res[1] > 0.0 ? h_res[0] / h_res[1] : 0.0;
+  return THB_OK;
+}
+
 int thb_ba_evaluate(const ThbBaProblem* P, double* residuals, double* jac_cam, double* jac_intr, double* jac_pt,
                     uint8_t* ok, void* cuda_stream) {
   if (!P) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem");

@@ -26,6 +26,13 @@ namespace thb {
 
 namespace {
 
+#ifdef THB_K4_PROBE  // scratch/k4_micro.cu: phase time stamps of CTA 0
+__device__ long long g_probe[16];
+#define THB_PROBE(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_probe[slot] = clock64(); } while (0)
+#else
+#define THB_PROBE(slot) do { } while (0)
+#endif
+
 constexpr int NB = 64;    // inner panel width
 constexpr int OB = 128;   // outer block / update tile
 constexpr int SB = 16;    // sub-block of the diagonal kernel
@@ -46,6 +53,19 @@ __device__ __forceinline__ double fast_rsqrt(double d) {
   y = y * fma(-h, y * y, 1.5);
   return y;
 }
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // ---- diag: factor A[k0:k0+64, k0:k0+64] in place (lower); rd[k] = 1 / L_kk ------------------------
 // Thread (i = t % 64, g = t / 64) owns row i and the 16 columns j = 4*jj + g in registers. One pivot = one
@@ -75,17 +95,20 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
       if (t == 0) atomicExch(fail, 1);
       return;
     }
-    const double rs = fast_rsqrt(d);
-    const double ci = colbuf[k & 1][i];
-    if (g == gk) {
-      a[jk] = ci * rs;  // i == k: d * rsqrt(d) = sqrt(d)
-      if (i == k) rd[k] = rs;
-    }
-    const double cid = ci * (rs * rs);  // c_i / d
+    // rows 0..31 are finished once k >= 32: their two warps only keep the barrier count (FP64 issue is the limit)
+    if (k < 32 || i >= 32) {
+      const double rs = fast_rsqrt(d);
+      const double ci = colbuf[k & 1][i];
+      if (g == gk) {
+        a[jk] = ci * rs;  // i == k: d * rsqrt(d) = sqrt(d)
+        if (i == k) rd[k] = rs;
+      }
+      const double cid = ci * (rs * rs);  // c_i / d
 #pragma unroll
-    for (int jj = jk; jj < 16; ++jj) {
-      const int j = 4 * jj + g;
-      if (j > k && j <= i) a[jj] -= cid * colbuf[k & 1][j];
+      for (int jj = jk; jj < 16; ++jj) {
+        const int j = 4 * jj + g;
+        if (j > k && j <= i) a[jj] -= cid * colbuf[k & 1][j];
+      }
     }
   }
   __syncthreads();
@@ -98,41 +121,379 @@ __global__ void __launch_bounds__(256) chol_diag_kernel(double* __restrict__ A, 
   }
 }
 
-// ---- panel: for each 64-row tile below the diagonal block, X L11^T = A21 -------------------------------
-// 128 threads: all four warps move the tiles (coalesced), warps 0-1 solve with one row per lane in registers.
+// ---- panel: for each 32-row tile below the diagonal block, X L11^T = A21 -------------------------------
+// FP64 SIMT issue bounds this kernel (16 lanes/clk/SM), so a row is split over FOUR lanes (columns j = 4*jj + q) and a
+// tile is only 32 rows: up to 188 CTAs spread the substitution over all SMs. x_k is produced by the lane that owns
+// column k and broadcast inside the quad with one shuffle; everything else is thread-local registers.
+constexpr int PR = 32;
+constexpr int kPanelSmem = (NB * (NB + 1) + PR * (NB + 1)) * sizeof(double);
 __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A, int ld, int k0,
                                                          const double* __restrict__ rd, int nrows_total) {
   extern __shared__ double psm[];
   double (*Lt)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);                   // Lt[k][j] = L11[j][k]
   double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm + NB * (NB + 1));
   __shared__ double rdg[NB];
-  const int r0 = k0 + NB + blockIdx.x * NB;
+  const int r0 = k0 + NB + blockIdx.x * PR;
   const int t = threadIdx.x;
   for (int e = t; e < NB * NB; e += 128) {
     const int i = e >> 6, j = e & 63;
     Lt[j][i] = (j <= i) ? A[(size_t)(k0 + i) * ld + k0 + j] : 0.0;
+  }
+  for (int e = t; e < PR * NB; e += 128) {
+    const int i = e >> 6, j = e & 63;
     Bs[i][j] = (r0 + i < nrows_total) ? A[(size_t)(r0 + i) * ld + k0 + j] : 0.0;
   }
   if (t < NB) rdg[t] = rd[t];
   __syncthreads();
-  if (t < NB) {
-    double b[NB];
+  const int row = t >> 2, q = t & 3, lane = t & 31;
+  double b[16];
 #pragma unroll
-    for (int j = 0; j < NB; ++j) b[j] = Bs[t][j];
+  for (int jj = 0; jj < 16; ++jj) b[jj] = Bs[row][4 * jj + q];
 #pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const double xv = b[k] * rdg[k];
-      b[k] = xv;
+  for (int k = 0; k < NB; ++k) {
+    const int qk = k & 3, jk = k >> 2;
+    double xv = b[jk] * rdg[k];  // meaningful in the owner lane (q == qk) only
+    xv = __shfl_sync(0xffffffffu, xv, (lane & ~3) | qk);
+    if (q == qk) b[jk] = xv;
+    if (q > qk) b[jk] -= xv * Lt[k][4 * jk + q];
 #pragma unroll
-      for (int j = k + 1; j < NB; ++j) b[j] -= xv * Lt[k][j];
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) Bs[t][j] = b[j];
+    for (int jj = jk + 1; jj < 16; ++jj) b[jj] -= xv * Lt[k][4 * jj + q];
   }
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) Bs[row][4 * jj + q] = b[jj];
   __syncthreads();
-  for (int e = t; e < NB * NB; e += 128) {
+  for (int e = t; e < PR * NB; e += 128) {
     const int i = e >> 6, j = e & 63;
     if (r0 + i < nrows_total) A[(size_t)(r0 + i) * ld + k0 + j] = Bs[i][j];
+  }
+}
+
+// ---- compact variants of diag / panel -------------------------------------------------------------------------------
+// The fully unrolled kernels above are 64 KB / 27 KB of straight-line code that every launch executes exactly once:
+// measured at warm clocks they run at ~10 cycles per instruction, i.e. they are instruction-fetch bound, not FP64 bound
+// (B200 issues a warp-wide DFMA every 2.1 cycles per SM sub-partition, latency 8.8 cycles; scratch/k4_micro.cu). The
+// variants below keep the register-resident row slices but ROTATE them (local index 0 is always the active column
+// group), so four pivots form a loop body of a few KB that stays in the instruction cache.
+__global__ void __launch_bounds__(256) chol_diag2_kernel(double* __restrict__ A, int ld, int k0,
+                                                         double* __restrict__ rd, int* __restrict__ fail) {
+  __shared__ double S[NB][NB + 1];
+  __shared__ double colbuf[2][NB];
+  const int t = threadIdx.x, i = t & 63, g = t >> 6;
+  {
+    double v[16];  // all 16 loads of a thread in flight at once
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 256 * m, r = e >> 6, c = e & 63;
+      v[m] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 256 * m;
+      S[e >> 6][e & 63] = v[m];
+    }
+  }
+  __syncthreads();
+  double a[16];
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) a[jj] = S[i][4 * jj + g];
+  __syncthreads();  // S becomes the output buffer
+#pragma unroll 1
+  for (int m = 0; m < 16; ++m) {
+    const int live = 16 - m;  // local column groups 0 .. live-1 are still in play
+#pragma unroll
+    for (int gk = 0; gk < 4; ++gk) {
+      const int k = 4 * m + gk;
+      double* cb = colbuf[gk & 1];
+      if (g == gk) cb[i] = a[0];
+      __syncthreads();
+      const double d = cb[k];
+      if (!(d > 0.0)) {  // not positive definite (or NaN): uniform across the CTA
+        if (t == 0) atomicExch(fail, 1);
+        return;
+      }
+      if (i >= k) {
+        const double rs = fast_rsqrt(d);
+        const double ci = cb[i];
+        if (g == gk) {
+          a[0] = ci * rs;  // i == k: d * rsqrt(d) = sqrt(d)
+          if (i == k) rd[k] = rs;
+        }
+        const double cid = ci * (rs * rs);  // c_i / d
+        const double* cj = cb + 4 * m + g;  // cj[4 l] = c_j of local column group l
+        if (g > gk && 4 * m + g <= i) a[0] -= cid * cj[0];
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          if (4 * qd < live) {  // uniform: skip finished column groups four at a time
+#pragma unroll
+            for (int l = 4 * qd; l < 4 * qd + 4; ++l) {
+              if (l == 0) continue;
+              if (l < live && 4 * (m + l) + g <= i) a[l] -= cid * cj[4 * l];
+            }
+          }
+        }
+      }
+    }
+    S[i][4 * m + g] = a[0];  // column group m is final
+#pragma unroll
+    for (int l = 0; l < 15; ++l) a[l] = a[l + 1];
+  }
+  __syncthreads();
+  for (int e = t; e < NB * NB; e += 256) {  // coalesced store of the lower triangle
+    const int r = e >> 6, c = e & 63;
+    if (c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = S[r][c];
+  }
+}
+
+__global__ void __launch_bounds__(128) chol_panel2_kernel(double* __restrict__ A, int ld, int k0,
+                                                          const double* __restrict__ rd, int nrows_total) {
+  extern __shared__ double psm[];
+  double (*Lt)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);                   // Lt[k][j] = L11[j][k]
+  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm + NB * (NB + 1));
+  __shared__ double rdg[NB];
+  const int r0 = k0 + NB + blockIdx.x * PR;
+  const int t = threadIdx.x;
+  THB_PROBE(0);
+  {
+    double v[16], u[16];  // two batches of loads in flight
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 128 * m, ii = e >> 6, j = e & 63;
+      v[m] = (j <= ii) ? A[(size_t)(k0 + ii) * ld + k0 + j] : 0.0;
+      u[m] = (r0 + ii < nrows_total) ? A[(size_t)(r0 + ii) * ld + k0 + j] : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 128 * m;
+      Lt[e & 63][e >> 6] = v[m];
+      Bs[e >> 6][e & 63] = u[m];
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 128 * (m + 16), ii = e >> 6, j = e & 63;
+      v[m] = (j <= ii) ? A[(size_t)(k0 + ii) * ld + k0 + j] : 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 128 * (m + 16);
+      Lt[e & 63][e >> 6] = v[m];
+    }
+  }
+  if (t < NB) rdg[t] = rd[t];
+  __syncthreads();
+  THB_PROBE(1);
+  const int row = t >> 2, q = t & 3, lane = t & 31;
+  double b[16];
+#pragma unroll
+  for (int jj = 0; jj < 16; ++jj) b[jj] = Bs[row][4 * jj + q];
+#pragma unroll 1
+  for (int m = 0; m < 16; ++m) {
+    const int live = 16 - m;
+#pragma unroll
+    for (int qk = 0; qk < 4; ++qk) {
+      const int k = 4 * m + qk;
+      double xv = b[0] * rdg[k];  // meaningful in the owner lane (q == qk) only
+      xv = __shfl_sync(0xffffffffu, xv, (lane & ~3) | qk);
+      if (q == qk) b[0] = xv;
+      const double* Lk = &Lt[k][4 * m + q];  // Lk[4 l] = L11[4 (m + l) + q][k]
+      if (q > qk) b[0] -= xv * Lk[0];
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+        if (4 * qd < live) {
+#pragma unroll
+          for (int l = 4 * qd; l < 4 * qd + 4; ++l) {
+            if (l == 0) continue;
+            if (l < live) b[l] -= xv * Lk[4 * l];
+          }
+        }
+      }
+    }
+    Bs[row][4 * m + q] = b[0];
+#pragma unroll
+    for (int l = 0; l < 15; ++l) b[l] = b[l + 1];
+  }
+  __syncthreads();
+  THB_PROBE(2);
+  for (int e = t; e < PR * NB; e += 128) {
+    const int ii = e >> 6, j = e & 63;
+    if (r0 + ii < nrows_total) A[(size_t)(r0 + ii) * ld + k0 + j] = Bs[ii][j];
+  }
+  THB_PROBE(3);
+}
+
+// ---- thread-per-row variants (the ones FactorAndSolve launches) ------------------------------------------------------
+// Measured on B200 (scratch/k4_micro.cu, scratch/lat_micro.cu): a warp-wide DFMA issues every 2.1 cycles per SM
+// sub-partition with 8.8 cycles latency, i.e. FP64 SIMT runs at the full 64 FMA/clk/SM; a publish + __syncthreads + read
+// round trip costs 75-95 cycles, a quad shuffle 30, a branch ~25, and straight-line code that is executed once is
+// instruction-fetch bound when the I-cache is cold. The kernels above spend 350-950 cycles per pivot on exactly those
+// latencies. Here one THREAD owns one matrix row in registers, columns are handled in blocks of 8 (2 barriers per block
+// instead of 1 per pivot, no shuffles), the register row is rotated by 8 per block so the loop body has static register
+// indices and stays a few KB, and everything inside a block is independent FMAs that pipeline at full rate.
+
+// MUFU.RSQ64H seed + one third-order step: 2.2e-16 relative error over the whole exponent range, ~65 cycles of latency
+// (the fp32-seed version above: cvt + MUFU + cvt + two Newton steps = ~120).
+__device__ __forceinline__ double rsqrt_f64(double d) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+  const double e = fma(-d * y, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  return fma(y * e, p, y);
+}
+__device__ __forceinline__ void ldg256(const double* p, double* o) {
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(double* p, const double* o) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(o[0]), "d"(o[1]), "d"(o[2]), "d"(o[3]) : "memory");
+}
+
+// diag: factor A[k0:k0+64, k0:k0+64] in place (lower); rd[k] = 1 / L_kk. 64 threads, thread i owns row i.
+__global__ void __launch_bounds__(64) chol_diag3_kernel(double* __restrict__ A, int ld, int k0,
+                                                        double* __restrict__ rd, int* __restrict__ fail) {
+  __shared__ __align__(32) double Dblk[8][8];   // raw diagonal block of the current block column
+  __shared__ __align__(32) double Lb[NB][8];    // the 8 finished L values of every row for the current block column
+  const int i = threadIdx.x;
+  THB_PROBE(0);
+  double* grow = A + (size_t)(k0 + i) * ld + k0;
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 4) ldg256(grow + c, a + c);  // entries right of the diagonal are never used
+  THB_PROBE(1);
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int k = 8 * kb;
+    if ((i >> 3) == kb) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Dblk[i & 7][u] = a[u];
+    }
+    __syncthreads();
+    if (i >= k) {
+      // every live thread factors the 8x8 block itself: no communication inside the block
+      double D[8][8], rs[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double4 lo = *reinterpret_cast<const double4*>(&Dblk[v][0]);
+        const double4 hi = *reinterpret_cast<const double4*>(&Dblk[v][4]);
+        D[v][0] = lo.x; D[v][1] = lo.y; D[v][2] = lo.z; D[v][3] = lo.w; D[v][4] = hi.x; D[v][5] = hi.y; D[v][6] = hi.z; D[v][7] = hi.w;
+      }
+      bool bad = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double d = D[u][u];
+        bad |= !(d > 0.0);
+        rs[u] = rsqrt_f64(d);
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) D[v][u] *= rs[u];
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v)
+#pragma unroll
+          for (int w = u + 1; w <= v; ++w) D[v][w] -= D[v][u] * D[w][u];
+      }
+      if (bad) {  // not positive definite (or NaN); identical in every thread, the factor is garbage from here on
+        if (i == k) atomicExch(fail, 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rs[u] = 0.0;
+      }
+      // own row of the block column: x L_kk^T = a[0..7]
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double x = a[u] * rs[u];
+        a[u] = x;
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) a[v] -= x * D[v][u];
+      }
+      *reinterpret_cast<double4*>(&Lb[i][0]) = make_double4(a[0], a[1], a[2], a[3]);
+      *reinterpret_cast<double4*>(&Lb[i][4]) = make_double4(a[4], a[5], a[6], a[7]);
+      if (i == k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rd[k + u] = rs[u];
+      }
+      // finished block column of this row -> global (only the lower triangle is ever written)
+      if (i >= k + 8) {
+        stg256(grow + k, a); stg256(grow + k + 4, a + 4);
+      } else {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (k + u <= i) grow[k + u] = a[u];
+      }
+    }
+    __syncthreads();
+    // trailing columns of this row: a[c] -= sum_u L_i,u * L_j,u for k + 8 <= j = k + c <= i
+#pragma unroll
+    for (int cg = 1; cg < 8; ++cg) {
+      if (cg < 8 - kb && k + 8 * cg <= (i | 31)) {  // uniform per warp
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int j = k + 8 * cg + v;
+          const double4 lo = *reinterpret_cast<const double4*>(&Lb[j][0]);
+          const double4 hi = *reinterpret_cast<const double4*>(&Lb[j][4]);
+          double acc = a[8 * cg + v];
+          acc = fma(-a[0], lo.x, acc); acc = fma(-a[1], lo.y, acc); acc = fma(-a[2], lo.z, acc); acc = fma(-a[3], lo.w, acc);
+          acc = fma(-a[4], hi.x, acc); acc = fma(-a[5], hi.y, acc); acc = fma(-a[6], hi.z, acc); acc = fma(-a[7], hi.w, acc);
+          if (j <= i) a[8 * cg + v] = acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB - 8; ++c) a[c] = a[c + 8];
+    THB_PROBE(2 + kb);
+  }
+}
+
+// panel: for each 64-row tile below the diagonal block, X L11^T = A21; thread-per-row, rows straight from / to global.
+constexpr int PR3 = 64;
+constexpr int LP = NB + 2;  // L11 row pitch in shared memory (16-byte aligned rows)
+constexpr int kPanel3Smem = NB * LP * sizeof(double);
+__global__ void __launch_bounds__(64) chol_panel3_kernel(double* __restrict__ A, int ld, int k0,
+                                                         const double* __restrict__ rd, int nrows_total) {
+  extern __shared__ __align__(16) double psm[];
+  double (*L)[LP] = reinterpret_cast<double (*)[LP]>(psm);  // L[j][k] = L11[j][k]
+  __shared__ double rdg[NB];
+  const int t = threadIdx.x;
+  THB_PROBE(0);
+  const int r = k0 + NB + blockIdx.x * PR3 + t;
+  const bool valid = r < nrows_total;
+  // L11 -> shared memory: 2048 16-byte pieces, all in flight at once
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const int e = t + 64 * m, row = e >> 5, piece = e & 31;
+    cp_async16(&L[row][2 * piece], A + (size_t)(k0 + row) * ld + k0 + 2 * piece);
+  }
+  cp_async_commit();
+  rdg[t] = rd[t];
+  double* grow = A + (size_t)(valid ? r : k0 + NB) * ld + k0;
+  double b[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 4) ldg256(grow + c, b + c);
+  cp_async_wait<0>();
+  __syncthreads();
+  THB_PROBE(1);
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int k = 8 * kb;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double x = b[u] * rdg[k + u];
+      b[u] = x;
+#pragma unroll
+      for (int v = u + 1; v < 8; ++v) b[v] -= x * L[k + v][k + u];
+    }
+    if (valid) { stg256(grow + k, b); stg256(grow + k + 4, b + 4); }
+#pragma unroll
+    for (int cg = 1; cg < 8; ++cg) {
+      if (cg < 8 - kb) {  // uniform
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const double* Lj = &L[k + 8 * cg + v][k];
+          const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+          const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+          double acc = b[8 * cg + v];
+          acc = fma(-b[0], l0.x, acc); acc = fma(-b[1], l0.y, acc); acc = fma(-b[2], l1.x, acc); acc = fma(-b[3], l1.y, acc);
+          acc = fma(-b[4], l2.x, acc); acc = fma(-b[5], l2.y, acc); acc = fma(-b[6], l3.x, acc); acc = fma(-b[7], l3.y, acc);
+          b[8 * cg + v] = acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB - 8; ++c) b[c] = b[c + 8];
+    THB_PROBE(2 + kb);
   }
 }
 
@@ -196,19 +557,6 @@ __global__ void __launch_bounds__(256) chol_inverse_kernel(const double* __restr
   }
 }
 
-__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
 // ---- update: C[r0:r0+128, c0:c0+BN] -= P[r0.., kc0:kc0+KT] * P[c0.., kc0:kc0+KT]^T ------------------
 // BN = 128: square tiles over the lower-triangular tile set (linear block index -> (bi, bj <= bi)).
 // BN = 64 : the one 64-column strip after the first inner panel (blockIdx.x = bi, bj = 0).
@@ -230,7 +578,7 @@ __global__ void __launch_bounds__(256, 1) chol_update_kernel(double* __restrict_
     while (bi * (bi + 1) / 2 > lin) --bi;
     bj = lin - bi * (bi + 1) / 2;
   } else {
-    bi = blockIdx.x; bj = 0;
+    bi = blockIdx.x; bj = blockIdx.y;
   }
   const int r0 = row_base + bi * BM, c0 = col_base + bj * BN;
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
@@ -304,6 +652,103 @@ __global__ void __launch_bounds__(256, 1) chol_update_kernel(double* __restrict_
     for (int v = 0; v < NV; ++v) {
       const int c = c0 + wc + v * 8 + 2 * fk;
       *reinterpret_cast<double2*>(&A[(size_t)r * ld + c]) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
+  }
+}
+
+// ---- trailing update, main variant: 128 x 64 tile, 128 threads (2 x 2 warps of 64 x 32), TWO CTAs per SM ---------
+// A lone 128x128 CTA per SM (above) spends a third of its life loading and storing its C tile with the tensor pipe idle
+// (measured r01: 26.6 us per tile against 16.7 us of DMMA time). Two smaller co-resident CTAs overlap one's C traffic
+// with the other's K loop: same per-warp register tile, K chunk 16, 3-stage cp.async ring = 90 KB of shared memory.
+// Tiles cover the lower triangle in 128-row x 64-column units: row block bi owns column tiles bj = 0 .. 2*bi+1, the
+// rhs tile-row (bi == row_tiles) the tiles 0 .. 2*row_tiles-1.
+constexpr int KC2 = 16, LDK2 = KC2 + 4, U_BM = 128, U_BN = 64;
+constexpr int kUpd2Smem = STAGES * (U_BM + U_BN) * LDK2 * sizeof(double);
+template <bool LOAD_C = true, bool STORE_C = true>
+__global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict__ A, int ld, int kc0, int KT,
+                                                             int base, int nrows_total) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int A_ELEMS = U_BM * LDK2, B_ELEMS = U_BN * LDK2, STAGE = A_ELEMS + B_ELEMS;
+  constexpr int NV = 4;
+  const int lin = blockIdx.x;
+  int bi = (int)((sqrt(4.0 * lin + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) <= lin) ++bi;
+  while (bi * (bi + 1) > lin) --bi;
+  const int bj = lin - bi * (bi + 1);
+  const int r0 = base + bi * U_BM, c0 = base + bj * U_BN;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int wr = (w >> 1) * 64, wc = (w & 1) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int nchunks = KT / KC2;
+
+  auto load_stage = [&](int chunk, int stage) {
+    double* sa = smem + stage * STAGE;
+    double* sb = sa + A_ELEMS;
+    const int kc = kc0 + chunk * KC2;
+#pragma unroll
+    for (int e = t; e < (U_BM + U_BN) * (KC2 / 2); e += 128) {
+      const int row = e / (KC2 / 2), piece = e % (KC2 / 2);
+      if (row < U_BM) {
+        int gr = r0 + row; if (gr >= nrows_total) gr = nrows_total - 1;
+        cp_async16(sa + row * LDK2 + piece * 2, A + (size_t)gr * ld + kc + piece * 2);
+      } else {
+        const int rb = row - U_BM;
+        cp_async16(sb + rb * LDK2 + piece * 2, A + (size_t)(c0 + rb) * ld + kc + piece * 2);
+      }
+    }
+  };
+
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  // accumulators start from C (the loads overlap the first operand chunks), D = C + (-A) B^T
+  double acc[8][NV][2];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    int r = r0 + wr + u * 8 + fr; if (r >= nrows_total) r = nrows_total - 1;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = c0 + wc + v * 8 + 2 * fk;
+      if (LOAD_C) {
+        const double2 cv = *reinterpret_cast<const double2*>(&A[(size_t)r * ld + c]);
+        acc[u][v][0] = cv.x; acc[u][v][1] = cv.y;
+      } else {
+        acc[u][v][0] = 0.0; acc[u][v][1] = 0.0;
+      }
+    }
+  }
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    const int nxt = ch + STAGES - 1;
+    if (nxt < nchunks) load_stage(nxt, nxt % STAGES);
+    cp_async_commit();
+    const double* sa = smem + (ch % STAGES) * STAGE;
+    const double* sb = sa + A_ELEMS;
+#pragma unroll
+    for (int k = 0; k < KC2; k += 4) {
+      double a[8], b[NV];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] = -sa[(wr + u * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) b[v] = sb[(wc + v * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) dmma_m8n8k4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int r = r0 + wr + u * 8 + fr;
+    if (r >= nrows_total) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = c0 + wc + v * 8 + 2 * fk;
+      if (STORE_C || acc[u][v][0] == 1.2345e300) *reinterpret_cast<double2*>(&A[(size_t)r * ld + c]) = make_double2(acc[u][v][0], acc[u][v][1]);
     }
   }
 }
@@ -389,19 +834,25 @@ int DenseChol::Init(int n_, cudaStream_t st) {
       if (e != cudaSuccess) attr_err = e;
     };
     set((const void*)chol_inverse_kernel, kInvSmem);
-    set((const void*)chol_panel_kernel, kInvSmem);
+    set((const void*)chol_panel_kernel, kPanelSmem);
+    set((const void*)chol_panel2_kernel, kPanelSmem);
+    set((const void*)chol_panel3_kernel, kPanel3Smem);
     set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
+    set((const void*)chol_update2_kernel<true, true>, kUpd2Smem);
     set((const void*)chol_update_kernel<OB, NB>, (int)(STAGES * (NB + OB) * LDK * sizeof(double)));
     set((const void*)chol_update_kernel<NB, NB>, (int)(STAGES * (NB + NB) * LDK * sizeof(double)));
   });
   THB_CUDA_CHECK(attr_err);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   num_sms = sms > 0 ? sms : 148;
-  THB_CUDA_CHECK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+  // the latency-bound diag/panel chain is the critical path: its CTAs must win free SM slots against the trailing update
+  int prio_lo = 0, prio_hi = 0;
+  THB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  THB_CUDA_CHECK(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_hi));
   THB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) {
-    THB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_ready[i], cudaEventDisableTiming));
-    THB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_col[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) {
+    THB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_pp[i], cudaEventDisableTiming));
+    THB_CUDA_CHECK(cudaEventCreateWithFlags(&ev_c2[i], cudaEventDisableTiming));
   }
   return THB_OK;
 }
@@ -415,9 +866,9 @@ void DenseChol::Free(cudaStream_t st) {
   A = dinv = x = rdiag = nullptr; ready = nullptr;
   if (s2) { cudaStreamDestroy(s2); s2 = nullptr; }
   if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
-  for (int i = 0; i < 2; ++i) {
-    if (ev_ready[i]) { cudaEventDestroy(ev_ready[i]); ev_ready[i] = nullptr; }
-    if (ev_col[i]) { cudaEventDestroy(ev_col[i]); ev_col[i] = nullptr; }
+  for (int i = 0; i < 4; ++i) {
+    if (ev_pp[i]) { cudaEventDestroy(ev_pp[i]); ev_pp[i] = nullptr; }
+    if (ev_c2[i]) { cudaEventDestroy(ev_c2[i]); ev_c2[i] = nullptr; }
   }
 }
 
@@ -430,51 +881,54 @@ int DenseChol::Clear(cudaStream_t st) {
 // One outer block (two inner panels) of panel work on stream `q`.
 void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches) {
   const int k0 = ob * OB;
-  chol_diag_kernel<<<1, 256, 0, q>>>(A, ld, k0, rdiag + k0, fail_flag);
+  chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0, rdiag + k0, fail_flag);
   // 64-row tiles below the diagonal block; the last tile holds only the rhs row (guarded)
-  chol_panel_kernel<<<(n_pad - k0 - NB) / NB + 1, 128, kInvSmem, q>>>(A, ld, k0, rdiag + k0, rows_total);
+  chol_panel3_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0, rdiag + k0, rows_total);
   {  // strip: columns k0+64 .. k0+127, rows k0+64 .. end, K = 64
     const int rows = rows_total - (k0 + NB);
     const int tr = (rows + NB - 1) / NB;
     chol_update_kernel<NB, NB><<<tr, 256, STAGES * (NB + NB) * LDK * sizeof(double), q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, 1);
   }
-  chol_diag_kernel<<<1, 256, 0, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag);
-  chol_panel_kernel<<<(n_pad - k0 - OB) / NB + 1, 128, kInvSmem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, rows_total);
+  chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag);
+  chol_panel3_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, rows_total);
   *launches += 5;
 }
 
 // Factor the lower triangle of A (n_pad x n_pad, row n_pad = rhs) and leave the solution in x.
-// Lookahead: the trailing update of outer block ob first updates only the next block's 128 columns; the
-// next block's (latency-bound) diag/panel chain then runs on a second stream while the rest of the
-// trailing matrix is updated on the caller's stream.
+//
+// Schedule (outer blocks of 128 columns, b = 0 .. nob-1), two streams:
+//   critical stream s2 (high priority):  L(b)  block column b  -=  panels b-2, b-1   (left-looking, K = 256)
+//                                        PP(b) diag / panel / strip / diag / panel of block b
+//   bulk stream st:                      C2(b) columns >= b+3  -=  panel b            (right-looking, K = 128)
+// L(b) needs C2(b-3) and every earlier C2 (stream order), C2(b) needs PP(b). The serial chain L, PP, L, PP ... therefore
+// runs two blocks ahead of the bulk updates instead of waiting for each of them (the r01 schedule had the next
+// block-column update queued behind the whole trailing update). Event rings of four: a dependency spans <= 3 blocks.
 int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
   const int nob = n_pad / OB;
-  const size_t upd_smem = STAGES * (OB + OB) * LDK * sizeof(double);
   THB_CUDA_CHECK(cudaEventRecord(ev_start, st));
   THB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_start, 0));
-  PanelPair(s2, 0, fail_flag, launches);
-  THB_CUDA_CHECK(cudaEventRecord(ev_ready[0], s2));
-  for (int ob = 0; ob < nob; ++ob) {
-    const int k0 = ob * OB;
-    THB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_ready[ob & 1], 0));
-    const int nt = nob - ob - 1;
-    if (nt <= 0) break;
-    // (A) next block's columns only: tiles (bi, 0), bi = 0..nt (bi = nt is the rhs row)
-    chol_update_kernel<OB, NB><<<2 * nt + 1, 256, STAGES * (NB + OB) * LDK * sizeof(double), st>>>(A, ld, k0, OB, k0 + OB, k0 + OB, rows_total, 1);
-    THB_CUDA_CHECK(cudaEventRecord(ev_col[ob & 1], st));
-    // (B) next block's panel chain on the second stream
-    THB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_col[ob & 1], 0));
-    PanelPair(s2, ob + 1, fail_flag, launches);
-    THB_CUDA_CHECK(cudaEventRecord(ev_ready[(ob + 1) & 1], s2));
-    // (C) the rest of the trailing matrix: tiles (bi, bj) with bj >= 1
-    const int ntr = nt - 1;
-    if (ntr > 0) {
-      const int tiles = ntr * (ntr + 1) / 2 + ntr;  // + the rhs tile-row
-      chol_update_kernel<OB, OB><<<tiles, 256, upd_smem, st>>>(A, ld, k0, OB, k0 + 2 * OB, k0 + 2 * OB, rows_total, 0);
+  for (int b = 0; b < nob; ++b) {
+    const int k0 = b * OB;
+    if (b >= 1) {
+      if (b >= 3) THB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_c2[(b - 3) & 3], 0));
+      const int pb = b >= 2 ? b - 2 : 0;  // first pending panel
+      const int rows = rows_total - k0;
+      const dim3 grid((rows + NB - 1) / NB, OB / NB);  // 64 x 64 tiles, two CTAs per SM
+      chol_update_kernel<NB, NB><<<grid, 256, STAGES * (NB + NB) * LDK * sizeof(double), s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total, 1);
       *launches += 1;
     }
-    *launches += 1;
+    PanelPair(s2, b, fail_flag, launches);
+    THB_CUDA_CHECK(cudaEventRecord(ev_pp[b & 3], s2));
+    const int ntr = nob - b - 3;  // 128-row tile rows of the region right of block column b+2
+    if (ntr >= 1) {
+      THB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_pp[b & 3], 0));
+      const int tiles = ntr * (ntr + 1) + 2 * ntr;  // 128 x 64 tiles of the lower triangle + the rhs tile-row
+      chol_update2_kernel<true, true><<<tiles, 128, kUpd2Smem, st>>>(A, ld, k0, OB, k0 + 3 * OB, rows_total);
+      THB_CUDA_CHECK(cudaEventRecord(ev_c2[b & 3], st));
+      *launches += 1;
+    }
   }
+  THB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_pp[(nob - 1) & 3], 0));
   chol_inverse_kernel<<<nblk, 256, kInvSmem, st>>>(A, ld, dinv);
   chol_copy_row_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(A + (size_t)n_pad * ld, x, n_pad);
   THB_CUDA_CHECK(cudaMemsetAsync(ready, 0, sizeof(int) * nblk, st));

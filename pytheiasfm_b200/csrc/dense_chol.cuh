@@ -23,7 +23,7 @@ struct DenseChol {
  private:
   void PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches);
   cudaStream_t s2 = nullptr;  // lookahead stream for the diag/panel chain
-  cudaEvent_t ev_start = nullptr, ev_ready[2] = {nullptr, nullptr}, ev_col[2] = {nullptr, nullptr};
+  cudaEvent_t ev_start = nullptr, ev_pp[4] = {nullptr, nullptr, nullptr, nullptr}, ev_c2[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace thb

@@ -303,6 +303,14 @@ def test_k4_dense_cholesky_solve_vs_numpy(lib, n):
     np.testing.assert_allclose(x, ref, rtol=1e-6, atol=1e-9 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("n", [300, 2500, 6000])
+def test_k4_full_size_residual(lib, n):
+    """K4 at the reduced-camera-system size of C2 (6000): device-built SPD system, max-norm residual of the solve."""
+    ms, res = C.c_double(0.0), C.c_double(1.0)
+    capi.check(lib.thb_dense_spd_time(n, 1, C.byref(ms), C.byref(res), None))
+    assert res.value <= 1e-11, res.value
+
+
 def test_k4_reports_indefinite_matrix(lib):
     n = 150
     A = np.eye(n); A[100, 100] = -1.0
