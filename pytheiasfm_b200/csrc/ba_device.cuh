@@ -146,7 +146,8 @@ __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S
 //   r[2]; jc[2][6] (position | angle-axis); jp[2][PD]; ji[2][NK] (only NK > 0)
 //   *half_rho = 0.5*rho(|r|^2) (cost contribution)
 // cs/ps/is: column scales of the camera, point and intrinsics blocks (may be null => 1).
-template <int MODEL, int PD, int NK>
+// ROBUST = false compiles the loss / Corrector code out (TRIVIAL loss, the reference default).
+template <int MODEL, int PD, int NK, bool ROBUST = true>
 __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int c, int p, double2 xy, double2 si,
                                          const double* cs, const double* ps, const double* is, double r[2],
                                          double jc[12], double jp[2 * PD], double* ji, double* half_rho) {
@@ -254,7 +255,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   // loss: cost and Corrector (ceres/corrector.cc, external)
   const double sq = r[0] * r[0] + r[1] * r[1];
   double rs = 1.0, js = 1.0, asn = 0.0;
-  if (K.loss_type != THB_LOSS_TRIVIAL) {
+  if (ROBUST && K.loss_type != THB_LOSS_TRIVIAL) {
     double rho[3];
     eval_loss(K.loss_type, K.loss_width, sq, rho);
     *half_rho = 0.5 * rho[0];

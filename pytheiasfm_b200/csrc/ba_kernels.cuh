@@ -124,18 +124,33 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
 // K1: residual + tangent-space Jacobian of every observation, point-major, into the plane layout.
 // One thread per observation. HBM-bound: reads 40 B/obs (+ L2-resident parameter gathers), writes
 // (2 + 12 + 2*PD + 2*NK) * 8 B/obs as fully coalesced plane stores.
-template <int MODEL, int PD, int NK>
+constexpr int K1_OBS_PER_THREAD = 4;
+template <int MODEL, int PD, int NK, bool ROBUST>
 __global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
                                                   const double* __restrict__ ps, const double* __restrict__ is,
                                                   double* __restrict__ r_pl, double* __restrict__ jc_pl,
                                                   double* __restrict__ jp_pl, double* __restrict__ ji_pl,
                                                   double* __restrict__ scal, int* __restrict__ iflag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double hc = 0.0;
-  if (i < K.no) {
-    const int c = O.cam[i], p = O.pt[i];
+  // A thread walks K1_OBS_PER_THREAD observations (stride 128, so every access stays coalesced) and fetches the next
+  // observation's indices / measurement while it works on the current one: the DRAM latency of the observation stream
+  // is then off the dependent chain index -> camera gather -> FP64 -> stores (r01 ncu: long-scoreboard stalls dominate).
+  // The observation stream is read once: evict-first, so it does not push the gathered camera / point records out.
+  const int base = blockIdx.x * (128 * K1_OBS_PER_THREAD) + threadIdx.x;
+  double hc_sum = 0.0;
+  int c_n = 0, p_n = 0;
+  double2 xy_n = make_double2(0.0, 0.0), si_n = make_double2(0.0, 0.0);
+  if (base < K.no) { c_n = __ldcs(O.cam + base); p_n = __ldcs(O.pt + base); xy_n = __ldcs(O.xy + base); si_n = __ldcs(O.si + base); }
+#pragma unroll 1
+  for (int u = 0; u < K1_OBS_PER_THREAD; ++u) {
+    const int i = base + 128 * u;
+    if (i >= K.no) break;
+    const int c = c_n, p = p_n;
+    const double2 xy = xy_n, si = si_n;
+    const int in = i + 128;
+    if (u + 1 < K1_OBS_PER_THREAD && in < K.no) { c_n = __ldcs(O.cam + in); p_n = __ldcs(O.pt + in); xy_n = __ldcs(O.xy + in); si_n = __ldcs(O.si + in); }
+    double hc = 0.0;
     double r[2], jc[12], jp[2 * PD], ji[NK > 0 ? 2 * NK : 1];
-    const bool ok = eval_obs<MODEL, PD, NK>(K, S, c, p, O.xy[i], O.si[i], cs, ps, is, r, jc, jp, ji, &hc);
+    const bool ok = eval_obs<MODEL, PD, NK, ROBUST>(K, S, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc);
     if (!ok) {
       atomicOr(iflag + FL_EVAL_X, 1);
       hc = 0.0; r[0] = r[1] = 0.0;
@@ -146,18 +161,19 @@ __global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSo
 #pragma unroll
       for (int k = 0; k < 2 * NK; ++k) ji[k] = 0.0;
     }
+    hc_sum += hc;
     const size_t no = K.no;
-    r_pl[i] = r[0]; r_pl[no + i] = r[1];
+    __stcs(r_pl + i, r[0]); __stcs(r_pl + no + i, r[1]);
 #pragma unroll
-    for (int k = 0; k < 12; ++k) jc_pl[k * no + i] = jc[k];
+    for (int k = 0; k < 12; ++k) __stcs(jc_pl + k * no + i, jc[k]);
 #pragma unroll
-    for (int k = 0; k < 2 * PD; ++k) jp_pl[k * no + i] = jp[k];
+    for (int k = 0; k < 2 * PD; ++k) __stcs(jp_pl + k * no + i, jp[k]);
 #pragma unroll
-    for (int k = 0; k < 2 * NK; ++k) ji_pl[k * no + i] = ji[k];
+    for (int k = 0; k < 2 * NK; ++k) __stcs(ji_pl + k * no + i, ji[k]);
   }
   // one atomic per warp, no block barrier: warps retire independently
-  hc = warp_sum(hc);
-  if ((threadIdx.x & 31) == 0) atomicAdd(scal + SC_COST_X, hc);
+  hc_sum = warp_sum(hc_sum);
+  if ((threadIdx.x & 31) == 0) atomicAdd(scal + SC_COST_X, hc_sum);
 }
 
 // Cost only (candidate evaluation): 0.5 * sum rho(|r|^2).

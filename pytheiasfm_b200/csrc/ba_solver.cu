@@ -200,8 +200,12 @@ int CheckDevice() {
 
 template <int MODEL, int PD>
 void LaunchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
-  k_jacobian<MODEL, PD, 0><<<cdiv(s->no, 128), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
-                                                               nullptr, s->d_scal, s->d_flag);
+  if (s->opt.loss_function_type == THB_LOSS_TRIVIAL)
+    k_jacobian<MODEL, PD, 0, false><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
+                                                                        nullptr, s->d_scal, s->d_flag);
+  else
+    k_jacobian<MODEL, PD, 0, true><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
+                                                                       nullptr, s->d_scal, s->d_flag);
 }
 template <int PD>
 void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
@@ -217,7 +221,7 @@ void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
 }
 template <int PD>
 void LaunchJacobianIntr(ThbBaSession* s, const double* cs, const double* ps) {
-  k_jacobian<-1, PD, NI><<<cdiv(s->no, 128), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, cs + 6 * s->nc, s->d_r, s->d_jc, s->d_jp,
+  k_jacobian<-1, PD, NI, true><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, cs + 6 * s->nc, s->d_r, s->d_jc, s->d_jp,
                                                              s->d_ji, s->d_scal, s->d_flag);
 }
 void RunJacobian(ThbBaSession* s, const double* cs, const double* ps) {

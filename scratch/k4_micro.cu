@@ -50,6 +50,25 @@ __global__ void k_dmma_chain_t(double* out, int iters) {
   double s = 0; for (int i = 0; i < NCH; ++i) s += d[i][0] + d[i][1];
   if (threadIdx.x == 0) { out[blockIdx.x * 2] = (double)(t1 - t0); out[blockIdx.x * 2 + 1] = s; }
 }
+// the update kernel's register pattern: 8 A fragments x 4 B fragments -> 32 accumulators, no memory traffic
+__global__ void __launch_bounds__(128) k_dmma_tile(double* out, int iters) {
+  double acc[8][4][2], a[8], b[4];
+  for (int u = 0; u < 8; ++u) { a[u] = 1e-3 * (threadIdx.x + u); for (int v = 0; v < 4; ++v) { acc[u][v][0] = u; acc[u][v][1] = v; } }
+  for (int v = 0; v < 4; ++v) b[v] = 1e-3 * v;
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) dmma_m8n8k4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += 1e-9;
+  }
+  long long t1 = clock64();
+  double s = 0;
+  for (int u = 0; u < 8; ++u) for (int v = 0; v < 4; ++v) s += acc[u][v][0] + acc[u][v][1];
+  if (threadIdx.x == 0) { out[blockIdx.x * 2] = (double)(t1 - t0); out[blockIdx.x * 2 + 1] = s; }
+}
 __global__ void k_shfl_chain(double* out, int iters) {
   double a = threadIdx.x;
   long long t0 = clock64();
@@ -134,6 +153,8 @@ int main(int argc, char** argv) {
   RUN("DMMA 8 warps, 16 chains", k_dmma_chain_t<16>, 1, 256, 16);
   RUN("DMMA 16 warps, 8 chains", k_dmma_chain_t<8>, 1, 512, 8);
   RUN("SHFL f64 chain 1 warp", k_shfl_chain, 1, 32, 1);
+  RUN("DMMA 8x4 register tile, 4 warps (1/SMSP)", k_dmma_tile, 1, 128, 32);
+  RUN("DMMA 8x4 register tile, 8 warps (2/SMSP, 2 CTAs)", k_dmma_tile, 2 * 148, 128, 32);
 
   {
     const int it2 = 20000;
@@ -221,6 +242,13 @@ int main(int argc, char** argv) {
     const int tiles1 = ntr * (ntr + 1) / 2 + ntr;
     const float ms1 = time_ms([&] { chol_update_kernel<OB, OB><<<tiles1, 256, STAGES * (OB + OB) * LDK * sizeof(double)>>>(A, ld, k0, OB, k0 + 2 * OB, k0 + 2 * OB, rows_total, 0); }, blocks_only ? 1 : 20);
     printf("update1 ob=%2d     %.2f us (%d tiles) %.2f TFLOP/s\n", ob, 1e3 * ms1, tiles1, tiles1 * 128.0 * 128 * 128 * 2 / ms1 / 1e9);
+  }
+  for (int KT : {128, 256, 512, 1024}) {
+    const int ntr = 30, tiles = ntr * (ntr + 1) + 2 * ntr, base = 2048;
+    cudaFuncSetAttribute(chol_update2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
+    const float msn = time_ms([&] { chol_update2_kernel<false, false><<<tiles, 128, kUpd2Smem>>>(A, ld, 0, KT, base, rows_total); }, blocks_only ? 1 : 10);
+    const float msc = time_ms([&] { chol_update2_kernel<true, true><<<tiles, 128, kUpd2Smem>>>(A, ld, 0, KT, base, rows_total); }, blocks_only ? 1 : 10);
+    printf("update2 K=%4d (%d tiles): no C %.2f TFLOP/s, with C %.2f TFLOP/s\n", KT, tiles, tiles * 128.0 * 64 * KT * 2 / msn / 1e9, tiles * 128.0 * 64 * KT * 2 / msc / 1e9);
   }
   printf("SM clock right after the update loops: %.0f MHz\n", probe_mhz(d_out));
   return 0;
