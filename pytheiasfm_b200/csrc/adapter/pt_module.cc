@@ -466,6 +466,63 @@ std::vector<double> Points2(const std::vector<Vec>& pts, size_t expect_min) {
   return d;
 }
 
+// ---- EstimateTwoViewInfo (sfm/estimate_twoview_info.cc:133-305), calibrated branch -------------------------------------
+template <int N> struct Prior { bool is_set = false; double value[N] = {0.0}; };   // camera_intrinsics_prior.h:50-79
+struct CameraIntrinsicsPrior {                                                      // camera_intrinsics_prior.h:83-118
+  int image_width = 0, image_height = 0;
+  std::string camera_intrinsics_model_type = "PINHOLE";
+  Prior<1> focal_length; Prior<2> principal_point; Prior<1> aspect_ratio; Prior<1> skew;
+  Prior<4> radial_distortion; Prior<2> tangential_distortion;
+  Prior<3> position; Prior<3> orientation; Prior<1> latitude; Prior<1> longitude; Prior<1> altitude;
+};
+struct TwoViewInfo {                                                                // twoview_info.h:54-90
+  double focal_length_1 = 0, focal_length_2 = 0, position_2[3] = {0, 0, 0}, rotation_2[3] = {0, 0, 0};
+  int num_verified_matches = 0, num_homography_inliers = 0, visibility_score = 0;
+  double scale_estimate = -1.0;
+};
+struct EstimateTwoViewInfoOptions {                                                 // estimate_twoview_info.h:52-80
+  int ransac_type = 0;
+  double max_sampson_error_pixels = 6.0, expected_ransac_confidence = 0.9999;
+  int min_ransac_iterations = 10, max_ransac_iterations = 1000;
+  bool use_mle = true, use_lo = false;
+  int lo_start_iterations = 10;
+  double min_focal_length = 1.0, max_focal_length = std::numeric_limits<double>::max();
+  int64_t seed = -1;  // ADDITIVE, like RansacParameters::seed: the reference's `rng` member is not bound (sfm.cc:864-885)
+};
+
+// PinholeCameraModel::SetFromCameraIntrinsicsPriors (pinhole_camera_model.cc:74-107) on a default-constructed model
+void PinholeFromPrior(const CameraIntrinsicsPrior& p, double K[7]) {
+  const double def[7] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // f, aspect, skew, cx, cy, k1, k2
+  std::copy(def, def + 7, K);
+  if (p.focal_length.is_set) K[0] = p.focal_length.value[0];
+  else if (p.image_width != 0 && p.image_height != 0) K[0] = 1.2 * (double)std::max(p.image_width, p.image_height);
+  if (p.principal_point.is_set) { K[3] = p.principal_point.value[0]; K[4] = p.principal_point.value[1]; }
+  else if (p.image_width != 0 && p.image_height != 0) { K[3] = p.image_width / 2.0; K[4] = p.image_height / 2.0; }
+  if (p.aspect_ratio.is_set) K[1] = p.aspect_ratio.value[0];
+  if (p.skew.is_set) K[2] = p.skew.value[0];
+  if (p.radial_distortion.is_set) { K[5] = p.radial_distortion.value[0]; K[6] = p.radial_distortion.value[1]; }
+}
+// PinholeCameraModel::PixelToCameraCoordinates + UndistortPoint (pinhole_camera_model.h:214-241, 262-300), then hnormalized()
+void PinholePixelToNormalized(const double K[7], const double px[2], double out[2]) {
+  const double fy = K[0] * K[1];
+  const double dy = (px[1] - K[4]) / fy;
+  const double dx = (px[0] - K[3] - dy * K[2]) / K[0];
+  double ux = dx, uy = dy;
+  for (int it = 0; it < 100; ++it) {
+    const double pxv = ux, pyv = uy;
+    const double r2 = ux * ux + uy * uy;
+    const double d = 1.0 + r2 * (K[5] + K[6] * r2);
+    ux = dx / d; uy = dy / d;
+    if (std::fabs(ux - pxv) < 1e-10 && std::fabs(uy - pyv) < 1e-10) break;
+  }
+  out[0] = ux / 1.0; out[1] = uy / 1.0;
+}
+// reconstruction_estimator_utils.cc:98-110
+double ComputeResolutionScaledThreshold(double threshold_pixels, int w, int h) {
+  if (w == 0 && h == 0) return threshold_pixels;
+  return threshold_pixels * (double)std::max(w, h) / 1024.0;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_pt, m) {
@@ -659,6 +716,80 @@ PYBIND11_MODULE(_pt, m) {
     const bool ok = RunOne(thb_ransac_abspose_batch, q, type, d, 5, &res, &sum);
     std::copy_n(res.rotation, 9, pose.R); std::copy_n(res.position, 3, pose.p);
     return py::make_tuple(ok, pose, sum);
+  });
+
+  // sfm.cc:156-163, 545-568, 864-885, 1456-1467
+  auto add_prior = [&](auto tag, const char* name) {
+    using P = decltype(tag);
+    constexpr int N = (int)(sizeof(P::value) / sizeof(double));
+    py::class_<P>(sfm, name).def(py::init<>()).def_readwrite("is_set", &P::is_set)
+        .def_property("value", [](const P& p) { return MakeVec(p.value, N); },
+                      [](P& p, const Vec& v) { CopyVec(v, p.value, N, "prior value"); p.is_set = true; });
+  };
+  add_prior(Prior<1>{}, "Prior1d"); add_prior(Prior<2>{}, "Prior2d"); add_prior(Prior<3>{}, "Prior3d"); add_prior(Prior<4>{}, "Prior4d");
+  py::class_<CameraIntrinsicsPrior>(sfm, "CameraIntrinsicsPrior")
+      .def(py::init<>())
+      .def_readwrite("image_width", &CameraIntrinsicsPrior::image_width).def_readwrite("image_height", &CameraIntrinsicsPrior::image_height)
+      .def_readwrite("camera_intrinsics_model_type", &CameraIntrinsicsPrior::camera_intrinsics_model_type)
+      .def_readwrite("focal_length", &CameraIntrinsicsPrior::focal_length).def_readwrite("principal_point", &CameraIntrinsicsPrior::principal_point)
+      .def_readwrite("aspect_ratio", &CameraIntrinsicsPrior::aspect_ratio).def_readwrite("skew", &CameraIntrinsicsPrior::skew)
+      .def_readwrite("radial_distortion", &CameraIntrinsicsPrior::radial_distortion)
+      .def_readwrite("tangential_distortion", &CameraIntrinsicsPrior::tangential_distortion)
+      .def_readwrite("position", &CameraIntrinsicsPrior::position).def_readwrite("orientation", &CameraIntrinsicsPrior::orientation)
+      .def_readwrite("latitude", &CameraIntrinsicsPrior::latitude).def_readwrite("longitude", &CameraIntrinsicsPrior::longitude)
+      .def_readwrite("altitude", &CameraIntrinsicsPrior::altitude);
+  py::class_<TwoViewInfo>(sfm, "TwoViewInfo")
+      .def(py::init<>())
+      .def_readwrite("focal_length_1", &TwoViewInfo::focal_length_1).def_readwrite("focal_length_2", &TwoViewInfo::focal_length_2)
+      .def_property("position_2", [](const TwoViewInfo& t) { return MakeVec(t.position_2, 3); }, [](TwoViewInfo& t, const Vec& v) { CopyVec(v, t.position_2, 3, "position_2"); })
+      .def_property("rotation_2", [](const TwoViewInfo& t) { return MakeVec(t.rotation_2, 3); }, [](TwoViewInfo& t, const Vec& v) { CopyVec(v, t.rotation_2, 3, "rotation_2"); })
+      .def_readwrite("num_verified_matches", &TwoViewInfo::num_verified_matches)
+      .def_readwrite("num_homography_inliers", &TwoViewInfo::num_homography_inliers)
+      .def_readwrite("visibility_score", &TwoViewInfo::visibility_score).def_readwrite("scale_estimate", &TwoViewInfo::scale_estimate);
+  py::class_<EstimateTwoViewInfoOptions>(sfm, "EstimateTwoViewInfoOptions")
+      .def(py::init<>())
+      .def_readwrite("ransac_type", &EstimateTwoViewInfoOptions::ransac_type)
+      .def_readwrite("max_sampson_error_pixels", &EstimateTwoViewInfoOptions::max_sampson_error_pixels)
+      .def_readwrite("expected_ransac_confidence", &EstimateTwoViewInfoOptions::expected_ransac_confidence)
+      .def_readwrite("min_ransac_iterations", &EstimateTwoViewInfoOptions::min_ransac_iterations)
+      .def_readwrite("max_ransac_iterations", &EstimateTwoViewInfoOptions::max_ransac_iterations)
+      .def_readwrite("use_mle", &EstimateTwoViewInfoOptions::use_mle).def_readwrite("use_lo", &EstimateTwoViewInfoOptions::use_lo)
+      .def_readwrite("lo_start_iterations", &EstimateTwoViewInfoOptions::lo_start_iterations)
+      .def_readwrite("min_focal_length", &EstimateTwoViewInfoOptions::min_focal_length)
+      .def_readwrite("max_focal_length", &EstimateTwoViewInfoOptions::max_focal_length)
+      .def_readwrite("seed", &EstimateTwoViewInfoOptions::seed);
+  // sfm_wrapper.cc:12-26: tuple(bool, TwoViewInfo, inlier indices). Calibrated branch (estimate_twoview_info.cc:133-191):
+  // normalise by the intrinsics, resolution-scaled Sampson threshold, EstimateRelativePose on the device, fill TwoViewInfo.
+  sfm.def("EstimateTwoViewInfo", [](const EstimateTwoViewInfoOptions& o, const CameraIntrinsicsPrior& i1, const CameraIntrinsicsPrior& i2,
+                                    const std::vector<FeatureCorrespondence>& c) -> py::tuple {
+    if (!(i1.focal_length.is_set && i2.focal_length.is_set))
+      throw std::runtime_error("EstimateTwoViewInfo: the uncalibrated branch (EstimateUncalibratedRelativePose, 8-point) is not on the B200 hot path");
+    if (i1.camera_intrinsics_model_type != "PINHOLE" || i2.camera_intrinsics_model_type != "PINHOLE")
+      throw std::runtime_error("EstimateTwoViewInfo: only PINHOLE priors are implemented for the feature normalisation");
+    double K1[7], K2[7];
+    PinholeFromPrior(i1, K1); PinholeFromPrior(i2, K2);
+    std::vector<double> d(c.size() * 4);
+    for (size_t k = 0; k < c.size(); ++k) {
+      PinholePixelToNormalized(K1, c[k].feature1.point, &d[4 * k]);
+      PinholePixelToNormalized(K2, c[k].feature2.point, &d[4 * k + 2]);
+    }
+    RansacParameters q;
+    q.failure_probability = 1.0 - o.expected_ransac_confidence;
+    q.min_iterations = o.min_ransac_iterations; q.max_iterations = o.max_ransac_iterations;
+    q.use_lo = o.use_lo; q.lo_start_iterations = o.lo_start_iterations; q.use_mle = o.use_mle; q.seed = o.seed;
+    const double t1 = ComputeResolutionScaledThreshold(o.max_sampson_error_pixels, i1.image_width, i1.image_height);
+    const double t2 = ComputeResolutionScaledThreshold(o.max_sampson_error_pixels, i2.image_width, i2.image_height);
+    q.error_thresh = t1 * t2 / (i1.focal_length.value[0] * i2.focal_length.value[0]);
+    ThbRelPoseResult res; RansacSummary sum; TwoViewInfo info;
+    if (!RunOne(thb_ransac_relpose_batch, q, o.ransac_type, d, 4, &res, &sum)) return py::make_tuple(false, info, std::vector<int>());
+    RotationToAngleAxis(res.rotation, info.rotation_2);
+    std::copy_n(res.position, 3, info.position_2);
+    info.focal_length_1 = i1.focal_length.value[0]; info.focal_length_2 = i2.focal_length.value[0];
+    info.num_verified_matches = (int)sum.inliers.size();
+    // The reference scores the visibility pyramid over *inlier_indices BEFORE assigning it (estimate_twoview_info.cc:186-189),
+    // i.e. over an empty list: the score is 0 whatever the inliers are. Reproduced, not fixed.
+    info.visibility_score = 0;
+    return py::make_tuple(true, info, sum.inliers);
   });
 
   // pose_wrapper.cc:166-173, 210-217, 369-377 and PoseFromThreePoints

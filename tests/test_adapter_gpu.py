@@ -204,3 +204,57 @@ def test_minimal_solver_bindings():
     assert ok and H.shape == (3, 3)
     ok, Fs = pt.sfm.SevenPointFundamentalMatrix(x1, x2)
     assert ok and 1 <= len(Fs) <= 3
+
+
+def test_EstimateTwoViewInfo_against_the_oracle():
+    """pt.sfm.EstimateTwoViewInfo (sfm.cc:922, estimate_twoview_info.cc:133-191, calibrated branch): pixel correspondences
+    + two CameraIntrinsicsPriors -> (success, TwoViewInfo, inlier indices). Checked against the same composition done in
+    numpy over the oracle's EstimateRelativePose: identical inlier list, pose within 1e-9."""
+    from oracle import oracle_py
+    from pytheiasfm_b200 import capi
+    corrs_n, R, c = _two_view_corrs(n=400, outliers=0.3, noise=5e-4)
+    xn = np.array([[cc.feature1.point[0], cc.feature1.point[1], cc.feature2.point[0], cc.feature2.point[1]] for cc in corrs_n])
+    f1, f2, a2, s1 = 1100.0, 950.0, 1.02, 0.7
+    pp1, pp2 = np.array([960.0, 540.0]), np.array([640.0, 480.0])
+    px = np.empty_like(xn)   # pixels of two pinhole cameras (skew on the first, aspect ratio on the second)
+    px[:, 0] = f1 * xn[:, 0] + s1 * xn[:, 1] + pp1[0]; px[:, 1] = f1 * xn[:, 1] + pp1[1]
+    px[:, 2] = f2 * xn[:, 2] + pp2[0]; px[:, 3] = f2 * a2 * xn[:, 3] + pp2[1]
+    corrs = [pt.matching.FeatureCorrespondence(pt.sfm.Feature(p[:2]), pt.sfm.Feature(p[2:])) for p in px]
+    pr1, pr2 = pt.sfm.CameraIntrinsicsPrior(), pt.sfm.CameraIntrinsicsPrior()
+    pr1.image_width, pr1.image_height, pr2.image_width, pr2.image_height = 1920, 1080, 1280, 960
+    pr1.focal_length.value = [f1]; pr2.focal_length.value = [f2]
+    pr1.principal_point.value = pp1; pr2.principal_point.value = pp2
+    pr1.skew.value = [s1]; pr2.aspect_ratio.value = [a2]
+    assert pr1.focal_length.is_set and not pr1.aspect_ratio.is_set
+    opts = pt.sfm.EstimateTwoViewInfoOptions()
+    assert (opts.max_sampson_error_pixels, opts.expected_ransac_confidence, opts.min_ransac_iterations, opts.max_ransac_iterations,
+            opts.use_mle, opts.use_lo) == (6.0, 0.9999, 10, 1000, True, False)   # estimate_twoview_info.h:52-73
+    opts.max_sampson_error_pixels = 2.0
+    opts.seed = 5
+    success, info, inliers = pt.sfm.EstimateTwoViewInfo(opts, pr1, pr2, corrs)
+    assert success and info.focal_length_1 == f1 and info.focal_length_2 == f2
+    assert info.num_verified_matches == len(inliers) > 200 and info.visibility_score == 0 and info.scale_estimate == -1.0
+
+    # the same composition over the oracle: normalise (same operation order), scaled threshold, EstimateRelativePose
+    y1 = (px[:, 1] - pp1[1]) / (f1 * 1.0); x1 = (px[:, 0] - pp1[0] - y1 * s1) / f1
+    y2 = (px[:, 3] - pp2[1]) / (f2 * a2); x2 = (px[:, 2] - pp2[0] - y2 * 0.0) / f2
+    norm = np.stack([x1 / 1.0 / 1.0, y1 / 1.0 / 1.0, x2 / 1.0 / 1.0, y2 / 1.0 / 1.0], -1)
+    batch = capi.HostPairBatch([norm], [5])
+    p = oracle_py.ransac_default_params()
+    p.failure_probability = 1.0 - 0.9999; p.min_iterations = 10; p.max_iterations = 1000; p.use_mle = 1; p.use_lo = 0
+    p.min_inlier_ratio = 0.0; p.ransac_type = 0
+    p.error_thresh = (2.0 * 1920 / 1024.0) * (2.0 * 1280 / 1024.0) / (f1 * f2)
+    rc, res, mask = oracle_py.ransac_relpose_batch(batch, p)
+    assert rc == 0 and res["success"][0] == 1
+    assert inliers == list(np.nonzero(mask)[0])
+    Ro = res["rotation"][0].reshape(3, 3)
+    ang = np.arccos(np.clip((np.trace(Ro) - 1) / 2, -1, 1))
+    axis = np.array([Ro[2, 1] - Ro[1, 2], Ro[0, 2] - Ro[2, 0], Ro[1, 0] - Ro[0, 1]]) / (2 * np.sin(ang))
+    np.testing.assert_allclose(info.rotation_2, ang * axis, rtol=0, atol=1e-9)
+    np.testing.assert_allclose(info.position_2, res["position"][0], rtol=0, atol=1e-12)
+    # and against the ground truth of the scene
+    assert np.rad2deg(np.arccos(np.clip(info.position_2 @ c, -1, 1))) < 5.0
+
+    pr2.focal_length.is_set = False
+    with pytest.raises(RuntimeError, match="uncalibrated"):
+        pt.sfm.EstimateTwoViewInfo(opts, pr1, pr2, corrs)
