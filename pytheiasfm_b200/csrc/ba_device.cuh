@@ -15,16 +15,19 @@
 
 namespace thb {
 
-// Per-camera record gathered by every observation: one 160-byte, 32-byte-aligned block read with FIVE 256-bit loads
+// Per-camera record gathered by every observation: ONE 128-byte, 128-byte-aligned L1 line read with four 256-bit loads
 // (LDG.E.ENL2.256). Every lane of a point-major warp reads a different camera, so each load instruction costs 32 L1 tag
 // lookups whatever its width: the r01 ncu capture showed K1 bound by exactly that (17 128-bit gathers of a 256-byte
-// record, l1tex 77 % busy). The rotation matrix and the SO(3) left Jacobian are therefore NOT stored (18 doubles) but
-// applied from the angle-axis vector and four scalar coefficients:
+// record, l1tex 77 % busy), and a 160-byte record straddles two lines (37 % L1 hit rate on the camera table). The
+// rotation matrix and the SO(3) left Jacobian are therefore NOT stored (18 doubles) but applied from the angle-axis
+// vector and four scalar coefficients:
 //   R   = I + a [w]x + b [w]x^2        (ceres::AngleAxisRotatePoint; first-order branch: a = 1, b = 0)
-//   J_l = I + A [w]x + B [w]x^2        (A = b, B = (th - sin th)/th^3; first-order branch: A = B = 0)
-//   w[3] | a b A B | th2 | C[3] | group | column scale[6] | constness | first-order flag            = 20 doubles
-constexpr int CAMD = 20;
-constexpr int CD_W = 0, CD_A = 3, CD_B = 4, CD_JA = 5, CD_JB = 6, CD_TH2 = 7, CD_C = 8, CD_GROUP = 11, CD_SCALE = 12, CD_CONST = 18, CD_SMALL = 19;
+//   J_l = I + A [w]x + B [w]x^2        (A = b, B = (th - sin th)/th^3; first-order branch: A = B = 0, the flag is A == 0)
+//   w[3] | a b A B | C[3] | column scale[6]                                                      = 16 doubles
+// Constant coordinates (SubsetManifold) carry column scale 0, which zeroes their Jacobian columns; th^2 = w.w is
+// recomputed; the intrinsics group comes from BaConst::cam_group when there is more than one group.
+constexpr int CAMD = 16;
+constexpr int CD_W = 0, CD_A = 3, CD_B = 4, CD_JA = 5, CD_JB = 6, CD_C = 7, CD_SCALE = 10;
 
 __device__ __forceinline__ void ld256(const double* p, double* o) {
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
@@ -132,8 +135,8 @@ __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S
   const double adj[3] = {X.x - X.w * cd[CD_C], X.y - X.w * cd[CD_C + 1], X.z - X.w * cd[CD_C + 2]};
   if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
   double pc[3];
-  rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[CD_TH2], adj, pc);
-  const int g = (int)cd[CD_GROUP];
+  rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2], adj, pc);
+  const int g = K.ng > 1 ? K.cam_group[c] : 0;
   double pix[2];
   if (!project<MODEL, double, double>(K.intr_model[g], S.intr + (size_t)g * KS, pc, pix)) return false;
   r[0] = si.x * (pix[0] - xy.x);
@@ -165,11 +168,11 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   const double adj[3] = {X[0] - X[3] * C[0], X[1] - X[3] * C[1], X[2] - X[3] * C[2]};
   if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
   const double* w = cd + CD_W;
-  const double th2 = cd[CD_TH2];
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   double pc[3];
   rot_apply(w, cd[CD_A], cd[CD_B], th2, adj, pc);
 
-  const int g = (int)cd[CD_GROUP];
+  const int g = K.ng > 1 ? K.cam_group[c] : 0;
   const int model = MODEL >= 0 ? MODEL : K.intr_model[g];
   const double* Kp = S.intr + (size_t)g * KS;
   D pd[3], pix[2];
@@ -195,16 +198,15 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   double AR[6];
   rot_apply(w, -cd[CD_A], cd[CD_B], th2, A, AR);
   rot_apply(w, -cd[CD_A], cd[CD_B], th2, A + 3, AR + 3);
-  const int cconst = (int)cd[CD_CONST];
-  // d r / d C = -w * AR
+  // d r / d C = -w * AR (the columns of constant coordinates are zeroed by their column scale below)
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
-    for (int k = 0; k < 3; ++k) jc[6 * a + k] = (cconst & THB_CAM_CONST_POSITION) ? 0.0 : -X[3] * AR[3 * a + k];
+    for (int k = 0; k < 3; ++k) jc[6 * a + k] = -X[3] * AR[3 * a + k];
   // d r / d aa = A * (-[q]x M): q = R adj and M = left Jacobian of SO(3); in Ceres' small-angle
   // branch (R = I + [aa]x) q = adj and M = I.
   {
-    const bool small = cd[CD_SMALL] != 0.0;
+    const bool small = cd[CD_JA] == 0.0;  // first-order branch of k_cam_derive (A > 0 otherwise)
     const double q0 = small ? adj[0] : pc[0], q1 = small ? adj[1] : pc[1], q2 = small ? adj[2] : pc[2];
     // G = A * (-[q]x), with [q]x = [[0,-q2,q1],[q2,0,-q0],[-q1,q0,0]]; then row a of G * J_l = J_l^T G_a
     double G[6], GM[6];
@@ -220,7 +222,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int k = 0; k < 3; ++k) jc[6 * a + 3 + k] = (cconst & THB_CAM_CONST_ORIENTATION) ? 0.0 : GM[3 * a + k];
+      for (int k = 0; k < 3; ++k) jc[6 * a + 3 + k] = GM[3 * a + k];
   }
   // d r / d X (2x4) = [AR | -AR*C], then the tangent block
   const bool pconst = K.pt_const[p] != 0;

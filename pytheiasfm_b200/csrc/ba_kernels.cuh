@@ -92,7 +92,6 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
   double* o = camd + (size_t)c * CAMD;
   const double th2 = wx * wx + wy * wy + wz * wz;
   o[CD_W] = wx; o[CD_W + 1] = wy; o[CD_W + 2] = wz;
-  o[CD_TH2] = th2;
   if (th2 > 2.220446049250313e-16) {
     const double th = sqrt(th2);
     double s, co;
@@ -109,15 +108,15 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
       B = (th - s) / (th2 * th);
     }
     o[CD_A] = s / th; o[CD_B] = A; o[CD_JA] = A; o[CD_JB] = B;
-    o[CD_SMALL] = 0.0;
   } else {
     o[CD_A] = 1.0; o[CD_B] = 0.0; o[CD_JA] = 0.0; o[CD_JB] = 0.0;
-    o[CD_SMALL] = 1.0;
   }
   o[CD_C] = cam[6 * c]; o[CD_C + 1] = cam[6 * c + 1]; o[CD_C + 2] = cam[6 * c + 2];
-  for (int k = 0; k < 6; ++k) o[CD_SCALE + k] = cs ? cs[6 * c + k] : 1.0;
-  o[CD_CONST] = (double)cam_const[c];
-  o[CD_GROUP] = (double)cam_group[c];
+  const int cc = cam_const[c];
+  for (int k = 0; k < 6; ++k) {
+    const bool is_const = (cc & (k < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) != 0;
+    o[CD_SCALE + k] = is_const ? 0.0 : (cs ? cs[6 * c + k] : 1.0);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -198,14 +198,22 @@ int CheckDevice() {
   return THB_OK;
 }
 
+// K1 uses no shared memory: ask for the largest L1 so the 128-byte camera records stay resident.
+template <typename Kern>
+void PreferL1Once(Kern kern) {
+  static bool done = false;
+  if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); done = true; }
+}
 template <int MODEL, int PD>
 void LaunchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
-  if (s->opt.loss_function_type == THB_LOSS_TRIVIAL)
-    k_jacobian<MODEL, PD, 0, false><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
-                                                                        nullptr, s->d_scal, s->d_flag);
-  else
-    k_jacobian<MODEL, PD, 0, true><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp,
-                                                                       nullptr, s->d_scal, s->d_flag);
+  const int grid = cdiv(s->no, 128 * K1_OBS_PER_THREAD);
+  if (s->opt.loss_function_type == THB_LOSS_TRIVIAL) {
+    PreferL1Once(k_jacobian<MODEL, PD, 0, false>);
+    k_jacobian<MODEL, PD, 0, false><<<grid, 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_scal, s->d_flag);
+  } else {
+    PreferL1Once(k_jacobian<MODEL, PD, 0, true>);
+    k_jacobian<MODEL, PD, 0, true><<<grid, 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_scal, s->d_flag);
+  }
 }
 template <int PD>
 void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
