@@ -371,23 +371,27 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
 
 // K3: off-diagonal camera-camera blocks of the Schur complement, S[ci,cj] -= T_i W_j^T for every pair of
 // observations (i,j) of a point. Points are grouped on the host into chunks of <= CH observations; W and
-// T of a chunk are staged in shared memory, then the (pair, a, b) work items are spread over the CTA and
-// each issues one FP64 atomic (RED) into the lower triangle of S.
+// T of a chunk are staged in shared memory together with a table of its observation pairs, then the (pair, a, b) work
+// items are spread over the CTA and each issues one FP64 atomic (RED) into the lower triangle of S. The pair table
+// matters: r01 ncu showed this kernel ISSUE-bound (73 % issue active, 148 instructions per warp work item) on decoding
+// a linear pair index with a square root and two correction loops per item.
 template <int PD>
 __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __restrict__ chunk_pt, const int* __restrict__ pt_start,
                                                        const int* __restrict__ o_cam, const double* __restrict__ jc_pl,
                                                        const double* __restrict__ jp_pl, const double* __restrict__ vinv,
                                                        double* __restrict__ Smat, int ld) {
   constexpr int CH = 64;
+  constexpr int MAXPAIRS = CH * (CH - 1) / 2;
   __shared__ double sW[CH][6 * PD];
   __shared__ double sT[CH][6 * PD];
   __shared__ int sC[CH];
+  __shared__ unsigned short sPair[MAXPAIRS];  // li | lj << 8, local observation indices of the chunk
+  __shared__ int sNumPairs;
   const int p0 = chunk_pt[blockIdx.x], p1 = chunk_pt[blockIdx.x + 1];
   const int q0 = pt_start[p0], q1 = pt_start[p1];
   const int nq = q1 - q0;
   const size_t n = no;
-  const bool staged = nq <= CH;
-  if (staged) {
+  if (nq <= CH) {
     for (int e = threadIdx.x; e < nq * 6; e += blockDim.x) {
       const int ql = e / 6, a = e % 6, q = q0 + ql;
       // point of q: chunk holds few points; find by scan
@@ -407,8 +411,33 @@ __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __rest
       }
       if (a == 0) sC[ql] = o_cam[q];
     }
+    // pair table: for every point of the chunk, all (i, j), i < j, of its observations
+    int pair_base = 0;
+    for (int p = p0; p < p1; ++p) {
+      const int b0 = pt_start[p] - q0, np_obs = pt_start[p + 1] - pt_start[p];
+      for (int i = threadIdx.x; i < np_obs - 1; i += blockDim.x) {
+        int o = pair_base + i * (2 * np_obs - i - 1) / 2;
+        for (int j = i + 1; j < np_obs; ++j) sPair[o++] = (unsigned short)((b0 + i) | ((b0 + j) << 8));
+      }
+      pair_base += np_obs * (np_obs - 1) / 2;
+    }
+    if (threadIdx.x == 0) sNumPairs = pair_base;
     __syncthreads();
+    const int items = sNumPairs * 36;
+    for (int e = threadIdx.x; e < items; e += blockDim.x) {
+      const int pair = e / 36, ab = e - 36 * pair, a = ab / 6, b = ab - 6 * a;
+      const int lp = sPair[pair], li = lp & 255, lj = lp >> 8;
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < PD; ++t) v += sT[li][a * PD + t] * sW[lj][b * PD + t];
+      const int ci = sC[li], cj = sC[lj];
+      if (ci > cj) atomicAdd(&Smat[(size_t)(6 * ci + a) * ld + 6 * cj + b], -v);
+      else if (ci < cj) atomicAdd(&Smat[(size_t)(6 * cj + b) * ld + 6 * ci + a], -v);
+      else atomicAdd(&Smat[(size_t)(6 * ci + max(a, b)) * ld + 6 * ci + min(a, b)], a == b ? -2.0 * v : -v);
+    }
+    return;
   }
+  // a single point with more than CH observations: no staging, operands straight from the planes
   for (int p = p0; p < p1; ++p) {
     const int b0 = pt_start[p], np_obs = pt_start[p + 1] - b0;
     const long long items = (long long)np_obs * (np_obs - 1) / 2 * 36;
@@ -420,32 +449,24 @@ __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __rest
       while ((long long)(i + 1) * (2 * np_obs - i - 2) / 2 <= pair) ++i;
       while ((long long)i * (2 * np_obs - i - 1) / 2 > pair) --i;
       const int j = i + 1 + (pair - (int)((long long)i * (2 * np_obs - i - 1) / 2));
-      double v = 0.0;
-      int ci, cj;
-      if (staged) {
-        const int li = b0 - q0 + i, lj = b0 - q0 + j;
+      const int qi = b0 + i, qj = b0 + j;
+      const double i0 = jc_pl[a * n + qi], i1 = jc_pl[(6 + a) * n + qi];
+      const double k0 = jc_pl[b * n + qj], k1 = jc_pl[(6 + b) * n + qj];
+      double Wi[PD], Wj[PD];
 #pragma unroll
-        for (int t = 0; t < PD; ++t) v += sT[li][a * PD + t] * sW[lj][b * PD + t];
-        ci = sC[li]; cj = sC[lj];
-      } else {
-        const int qi = b0 + i, qj = b0 + j;
-        const double i0 = jc_pl[a * n + qi], i1 = jc_pl[(6 + a) * n + qi];
-        const double k0 = jc_pl[b * n + qj], k1 = jc_pl[(6 + b) * n + qj];
-        double Wi[PD], Wj[PD];
-#pragma unroll
-        for (int t = 0; t < PD; ++t) {
-          Wi[t] = i0 * jp_pl[t * n + qi] + i1 * jp_pl[(PD + t) * n + qi];
-          Wj[t] = k0 * jp_pl[t * n + qj] + k1 * jp_pl[(PD + t) * n + qj];
-        }
-#pragma unroll
-        for (int t = 0; t < PD; ++t) {
-          double ti = 0.0;
-#pragma unroll
-          for (int u = 0; u < PD; ++u) ti += Wi[u] * vinv[(size_t)p * PD * PD + u * PD + t];
-          v += ti * Wj[t];
-        }
-        ci = o_cam[qi]; cj = o_cam[qj];
+      for (int t = 0; t < PD; ++t) {
+        Wi[t] = i0 * jp_pl[t * n + qi] + i1 * jp_pl[(PD + t) * n + qi];
+        Wj[t] = k0 * jp_pl[t * n + qj] + k1 * jp_pl[(PD + t) * n + qj];
       }
+      double v = 0.0;
+#pragma unroll
+      for (int t = 0; t < PD; ++t) {
+        double ti = 0.0;
+#pragma unroll
+        for (int u = 0; u < PD; ++u) ti += Wi[u] * vinv[(size_t)p * PD * PD + u * PD + t];
+        v += ti * Wj[t];
+      }
+      const int ci = o_cam[qi], cj = o_cam[qj];
       if (ci > cj) atomicAdd(&Smat[(size_t)(6 * ci + a) * ld + 6 * cj + b], -v);
       else if (ci < cj) atomicAdd(&Smat[(size_t)(6 * cj + b) * ld + 6 * ci + a], -v);
       else atomicAdd(&Smat[(size_t)(6 * ci + max(a, b)) * ld + 6 * ci + min(a, b)], a == b ? -2.0 * v : -v);
@@ -453,66 +474,98 @@ __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __rest
   }
 }
 
-// K5a: back-substitution per point, y_p = V^-1 (g_p - sum_i Jp_i^T (Jc_i y_ci + Ji_i y_si)), and the model cost change
-// -(J step)^T (r + J step / 2) with step = -y. One thread per point. NK > 0: variable intrinsics blocks exist.
-template <int PD, int NK>
-__global__ void __launch_bounds__(128) k_backsub(int np, int no, int nc, const int* __restrict__ pt_start, const int* __restrict__ o_cam,
-                                                 const int8_t* __restrict__ o_slot,
-                                                 const double* __restrict__ r_pl, const double* __restrict__ jc_pl,
-                                                 const double* __restrict__ jp_pl, const double* __restrict__ ji_pl,
-                                                 const double* __restrict__ vinv,
-                                                 const double* __restrict__ gp, const double* __restrict__ yred,
-                                                 double* __restrict__ yp, double* __restrict__ scal) {
-  __shared__ double red[32];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  double mcc = 0.0;
-  if (p < np) {
-    const size_t n = no;
-    const int q0 = pt_start[p], q1 = pt_start[p + 1];
-    double b[PD];
+// K5a: back-substitution, y_p = V^-1 (g_p - sum_i Jp_i^T (Jc_i y_ci + Ji_i y_si)), and the model cost change
+// -(J step)^T (r + J step / 2) with step = -y. Three passes, all with ONE THREAD PER OBSERVATION or per point so that every
+// plane access is coalesced: the r01 version (one thread per point walking its observations) pulled 2.9 GB from DRAM for
+// 160 MB of planes (32-byte sectors for 8-byte strided reads) and took 0.42 ms.
+//   k_backsub_obs1   jy = Jc y_c (+ Ji y_s) per observation -> jy planes; Jp^T jy summed per point (segmented warp sum)
+//   k_backsub_pt     y_p = V^-1 (g_p - that sum)
+//   k_backsub_obs2   m = -(jy + Jp y_p); model cost change
+template <int PD>
+__device__ __forceinline__ void warp_segmented_add(int key, double v[PD], double* __restrict__ out) {
+  // keys are non-decreasing over the lanes (point-major order); key < 0 marks an idle lane
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int a = 0; a < PD; ++a) b[a] = gp[(size_t)p * PD + a];
-    for (int q = q0; q < q1; ++q) {
-      const int c = o_cam[q];
-      double jy0 = 0.0, jy1 = 0.0;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) { const double y = yred[6 * c + k]; jy0 += jc_pl[k * n + q] * y; jy1 += jc_pl[(6 + k) * n + q] * y; }
-      if (NK > 0) {
-        const int sl = o_slot[q];
-        if (sl >= 0) {
-#pragma unroll
-          for (int k = 0; k < NK; ++k) { const double y = yred[6 * nc + NK * sl + k]; jy0 += ji_pl[k * n + q] * y; jy1 += ji_pl[(NK + k) * n + q] * y; }
-        }
-      }
-#pragma unroll
-      for (int a = 0; a < PD; ++a) b[a] -= jp_pl[a * n + q] * jy0 + jp_pl[(PD + a) * n + q] * jy1;
-    }
-    double y[PD];
+  for (int d = 1; d < 32; d <<= 1) {
+    const int k2 = __shfl_up_sync(full, key, d);
 #pragma unroll
     for (int a = 0; a < PD; ++a) {
-      double v = 0.0;
-#pragma unroll
-      for (int u = 0; u < PD; ++u) v += vinv[(size_t)p * PD * PD + a * PD + u] * b[u];
-      y[a] = v;
-      yp[(size_t)p * PD + a] = v;
+      const double o = __shfl_up_sync(full, v[a], d);
+      if (lane >= d && k2 == key) v[a] += o;
     }
-    for (int q = q0; q < q1; ++q) {
-      const int c = o_cam[q];
-      double m0 = 0.0, m1 = 0.0;
+  }
+  const int knext = __shfl_down_sync(full, key, 1);
+  if (key >= 0 && (lane == 31 || knext != key)) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { const double yc = yred[6 * c + k]; m0 += jc_pl[k * n + q] * yc; m1 += jc_pl[(6 + k) * n + q] * yc; }
-      if (NK > 0) {
-        const int sl = o_slot[q];
-        if (sl >= 0) {
+    for (int a = 0; a < PD; ++a) atomicAdd(out + (size_t)key * PD + a, v[a]);
+  }
+}
+
+template <int PD, int NK>
+__global__ void __launch_bounds__(256) k_backsub_obs1(int no, int nc, const int* __restrict__ o_cam, const int* __restrict__ o_pt,
+                                                      const int8_t* __restrict__ o_slot, const double* __restrict__ jc_pl,
+                                                      const double* __restrict__ jp_pl, const double* __restrict__ ji_pl,
+                                                      const double* __restrict__ yred, double* __restrict__ jy_pl,
+                                                      double* __restrict__ bsum) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = no;
+  int key = -1;
+  double t[PD];
 #pragma unroll
-          for (int k = 0; k < NK; ++k) { const double yi = yred[6 * nc + NK * sl + k]; m0 += ji_pl[k * n + q] * yi; m1 += ji_pl[(NK + k) * n + q] * yi; }
-        }
+  for (int a = 0; a < PD; ++a) t[a] = 0.0;
+  if (q < no) {
+    const int c = o_cam[q];
+    key = o_pt[q];
+    double jy0 = 0.0, jy1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { const double y = yred[6 * c + k]; jy0 += jc_pl[k * n + q] * y; jy1 += jc_pl[(6 + k) * n + q] * y; }
+    if (NK > 0) {
+      const int sl = o_slot[q];
+      if (sl >= 0) {
+#pragma unroll
+        for (int k = 0; k < NK; ++k) { const double y = yred[6 * nc + NK * sl + k]; jy0 += ji_pl[k * n + q] * y; jy1 += ji_pl[(NK + k) * n + q] * y; }
       }
-#pragma unroll
-      for (int a = 0; a < PD; ++a) { m0 += jp_pl[a * n + q] * y[a]; m1 += jp_pl[(PD + a) * n + q] * y[a]; }
-      m0 = -m0; m1 = -m1;  // J * step, step = -y
-      mcc -= m0 * (r_pl[q] + 0.5 * m0) + m1 * (r_pl[n + q] + 0.5 * m1);
     }
+    jy_pl[q] = jy0; jy_pl[n + q] = jy1;
+#pragma unroll
+    for (int a = 0; a < PD; ++a) t[a] = jp_pl[a * n + q] * jy0 + jp_pl[(PD + a) * n + q] * jy1;
+  }
+  warp_segmented_add<PD>(key, t, bsum);
+}
+
+template <int PD>
+__global__ void __launch_bounds__(128) k_backsub_pt(int np, const double* __restrict__ vinv, const double* __restrict__ gp,
+                                                    const double* __restrict__ bsum, double* __restrict__ yp) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  double b[PD];
+#pragma unroll
+  for (int a = 0; a < PD; ++a) b[a] = gp[(size_t)p * PD + a] - bsum[(size_t)p * PD + a];
+#pragma unroll
+  for (int a = 0; a < PD; ++a) {
+    double v = 0.0;
+#pragma unroll
+    for (int u = 0; u < PD; ++u) v += vinv[(size_t)p * PD * PD + a * PD + u] * b[u];
+    yp[(size_t)p * PD + a] = v;
+  }
+}
+
+template <int PD>
+__global__ void __launch_bounds__(256) k_backsub_obs2(int no, const int* __restrict__ o_pt, const double* __restrict__ r_pl,
+                                                      const double* __restrict__ jp_pl, const double* __restrict__ jy_pl,
+                                                      const double* __restrict__ yp, double* __restrict__ scal) {
+  __shared__ double red[32];
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = no;
+  double mcc = 0.0;
+  if (q < no) {
+    const int p = o_pt[q];
+    double m0 = jy_pl[q], m1 = jy_pl[n + q];
+#pragma unroll
+    for (int a = 0; a < PD; ++a) { const double y = yp[(size_t)p * PD + a]; m0 += jp_pl[a * n + q] * y; m1 += jp_pl[(PD + a) * n + q] * y; }
+    m0 = -m0; m1 = -m1;  // J * step, step = -y
+    mcc = -(m0 * (r_pl[q] + 0.5 * m0) + m1 * (r_pl[n + q] + 0.5 * m1));
   }
   mcc = block_sum(mcc, red);
   if (threadIdx.x == 0) atomicAdd(scal + SC_MCC, mcc);

@@ -136,6 +136,7 @@ struct ThbBaSession {
   double *d_zt = nullptr, *d_ilo = nullptr, *d_ihi = nullptr;
   double *d_cs = nullptr, *d_ps = nullptr;
   double *d_vinv = nullptr, *d_gp = nullptr, *d_pdiag = nullptr, *d_braw = nullptr, *d_cdiag = nullptr, *d_yp = nullptr;
+  double *d_jy = nullptr, *d_bsum = nullptr;  // back-substitution: Jc y_c per observation, Jp^T (Jc y_c) per point
   double* d_scal = nullptr;
   int* d_flag = nullptr;
   double* h_scal = nullptr;  // pinned
@@ -390,15 +391,25 @@ int SolveAndStep(ThbBaSession* s) {
   }
   ++s->sum.num_linear_solves;
   s->t_update.Begin();
-  const int gb = cdiv(s->np, 128);
-  if (s->nvg > 0) {
-    if (s->PD == 3) k_backsub<3, NI><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, s->d_op_slot, s->d_r, s->d_jc, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
-    else k_backsub<4, NI><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, s->d_op_slot, s->d_r, s->d_jc, s->d_jp, s->d_ji, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
-  } else {
-    if (s->PD == 3) k_backsub<3, 0><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
-    else k_backsub<4, 0><<<gb, 128, 0, s->st>>>(s->np, s->no, s->nc, s->d_pt_start, s->d_op_cam, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_vinv, s->d_gp, s->chol.x, s->d_yp, s->d_scal);
+  {
+    const int gq = cdiv(s->no, 256), gp_ = cdiv(s->np, 128);
+    THB_CUDA_CHECK(cudaMemsetAsync(s->d_bsum, 0, sizeof(double) * (size_t)s->np * s->PD, s->st));
+    if (s->nvg > 0) {
+      if (s->PD == 3) k_backsub_obs1<3, NI><<<gq, 256, 0, s->st>>>(s->no, s->nc, s->d_op_cam, s->d_op_pt, s->d_op_slot, s->d_jc, s->d_jp, s->d_ji, s->chol.x, s->d_jy, s->d_bsum);
+      else k_backsub_obs1<4, NI><<<gq, 256, 0, s->st>>>(s->no, s->nc, s->d_op_cam, s->d_op_pt, s->d_op_slot, s->d_jc, s->d_jp, s->d_ji, s->chol.x, s->d_jy, s->d_bsum);
+    } else {
+      if (s->PD == 3) k_backsub_obs1<3, 0><<<gq, 256, 0, s->st>>>(s->no, s->nc, s->d_op_cam, s->d_op_pt, nullptr, s->d_jc, s->d_jp, nullptr, s->chol.x, s->d_jy, s->d_bsum);
+      else k_backsub_obs1<4, 0><<<gq, 256, 0, s->st>>>(s->no, s->nc, s->d_op_cam, s->d_op_pt, nullptr, s->d_jc, s->d_jp, nullptr, s->chol.x, s->d_jy, s->d_bsum);
+    }
+    if (s->PD == 3) {
+      k_backsub_pt<3><<<gp_, 128, 0, s->st>>>(s->np, s->d_vinv, s->d_gp, s->d_bsum, s->d_yp);
+      k_backsub_obs2<3><<<gq, 256, 0, s->st>>>(s->no, s->d_op_pt, s->d_r, s->d_jp, s->d_jy, s->d_yp, s->d_scal);
+    } else {
+      k_backsub_pt<4><<<gp_, 128, 0, s->st>>>(s->np, s->d_vinv, s->d_gp, s->d_bsum, s->d_yp);
+      k_backsub_obs2<4><<<gq, 256, 0, s->st>>>(s->no, s->d_op_pt, s->d_r, s->d_jp, s->d_jy, s->d_yp, s->d_scal);
+    }
+    s->sum.gpu_launches += 3;
   }
-  ++s->sum.gpu_launches;
   const int rc = ComputeCandidate(s, 1.0);
   s->t_update.End();
   return rc;
@@ -545,6 +556,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY(M.Get(&s->d_ps, (size_t)np * s->PD));
   THB_TRY(M.Get(&s->d_vinv, (size_t)np * s->PD * s->PD)); THB_TRY(M.Get(&s->d_gp, (size_t)np * s->PD)); THB_TRY(M.Get(&s->d_pdiag, (size_t)np * s->PD));
   THB_TRY(M.Get(&s->d_yp, (size_t)np * s->PD));
+  THB_TRY(M.Get(&s->d_jy, (size_t)no * 2)); THB_TRY(M.Get(&s->d_bsum, (size_t)np * s->PD));
   THB_TRY(M.Get(&s->d_scal, SC_COUNT)); THB_TRY(M.Get(&s->d_flag, FL_COUNT));
   THB_TRY(M.Get(&s->d_op_slot, no));
   int *d_used = nullptr, *d_setup = nullptr, *d_perm = nullptr;
