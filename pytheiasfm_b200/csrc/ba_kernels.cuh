@@ -373,8 +373,10 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
 // observations (i,j) of a point. Points are grouped on the host into chunks of <= CH observations; W and
 // T of a chunk are staged in shared memory together with a table of its observation pairs, then the (pair, a, b) work
 // items are spread over the CTA and each issues one FP64 atomic (RED) into the lower triangle of S. The pair table
-// matters: r01 ncu showed this kernel ISSUE-bound (73 % issue active, 148 instructions per warp work item) on decoding
-// a linear pair index with a square root and two correction loops per item.
+// removes the square-root decode of a linear pair index (r01 ncu: 148 instructions per warp work item, 73 % issue
+// active); what remains is the RED rate of the SM's load/store path: 162 M atomics in 0.9 ms = 1.3 per clock per SM,
+// whether their sectors hit L2 or not (row-banded passes that keep S in L2 take a third of the time each - measured).
+// There is no vector form of red.add.f64 (ptxas rejects .v2.f64), so the count itself has to go down to go faster.
 template <int PD>
 __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __restrict__ chunk_pt, const int* __restrict__ pt_start,
                                                        const int* __restrict__ o_cam, const double* __restrict__ jc_pl,
