@@ -659,14 +659,18 @@ __global__ void __launch_bounds__(256, 1) chol_update_kernel(double* __restrict_
 // ---- trailing update, main variant: 128 x 64 tile, 128 threads (2 x 2 warps of 64 x 32), TWO CTAs per SM ---------
 // A lone 128x128 CTA per SM (above) spends a third of its life loading and storing its C tile with the tensor pipe idle
 // (measured r01: 26.6 us per tile against 16.7 us of DMMA time). Two smaller co-resident CTAs overlap one's C traffic
-// with the other's K loop: same per-warp register tile, K chunk 16, 3-stage cp.async ring = 90 KB of shared memory.
+// with the other's K loop: K chunk 16, 3-stage cp.async ring = 90 KB of shared memory. (NT = 256, four warps per SM
+// sub-partition with 32 x 32 warp tiles, is 8 % faster in isolation - 23.9 vs 22.1 TFLOP/s - but fills the register file,
+// so the critical-path kernels cannot slip in next to it: the whole factorisation gets 0.3 ms SLOWER. Measured.)
 // Tiles cover the lower triangle in 128-row x 64-column units: row block bi owns column tiles bj = 0 .. 2*bi+1, the
 // rhs tile-row (bi == row_tiles) the tiles 0 .. 2*row_tiles-1.
 constexpr int KC2 = 16, LDK2 = KC2 + 4, U_BM = 128, U_BN = 64;
 constexpr int kUpd2Smem = STAGES * (U_BM + U_BN) * LDK2 * sizeof(double);
-template <bool LOAD_C = true, bool STORE_C = true>
-__global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict__ A, int ld, int kc0, int KT,
-                                                             int base, int nrows_total) {
+template <bool LOAD_C = true, bool STORE_C = true, int NT = 128>
+__global__ void __launch_bounds__(NT, 2) chol_update2_kernel(double* __restrict__ A, int ld, int kc0, int KT,
+                                                            int base, int nrows_total) {
+  // NT = 128: 2 x 2 warps of 64 x 32; NT = 256: 4 x 2 warps of 32 x 32 (half the accumulators per warp, twice the warps)
+  constexpr int MU = NT == 128 ? 8 : 4;  // m8 fragments per warp
   extern __shared__ __align__(16) double smem[];
   constexpr int A_ELEMS = U_BM * LDK2, B_ELEMS = U_BN * LDK2, STAGE = A_ELEMS + B_ELEMS;
   constexpr int NV = 4;
@@ -677,7 +681,7 @@ __global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict
   const int bj = lin - bi * (bi + 1);
   const int r0 = base + bi * U_BM, c0 = base + bj * U_BN;
   const int t = threadIdx.x, w = t >> 5, lane = t & 31;
-  const int wr = (w >> 1) * 64, wc = (w & 1) * 32;
+  const int wr = (w >> 1) * (8 * MU), wc = (w & 1) * 32;
   const int fr = lane >> 2, fk = lane & 3;
   const int nchunks = KT / KC2;
 
@@ -686,7 +690,7 @@ __global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict
     double* sb = sa + A_ELEMS;
     const int kc = kc0 + chunk * KC2;
 #pragma unroll
-    for (int e = t; e < (U_BM + U_BN) * (KC2 / 2); e += 128) {
+    for (int e = t; e < (U_BM + U_BN) * (KC2 / 2); e += NT) {
       const int row = e / (KC2 / 2), piece = e % (KC2 / 2);
       if (row < U_BM) {
         int gr = r0 + row; if (gr >= nrows_total) gr = nrows_total - 1;
@@ -704,9 +708,9 @@ __global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict
     cp_async_commit();
   }
   // accumulators start from C (the loads overlap the first operand chunks), D = C + (-A) B^T
-  double acc[8][NV][2];
+  double acc[MU][NV][2];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < MU; ++u) {
     int r = r0 + wr + u * 8 + fr; if (r >= nrows_total) r = nrows_total - 1;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
@@ -729,20 +733,20 @@ __global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict
     const double* sb = sa + A_ELEMS;
 #pragma unroll
     for (int k = 0; k < KC2; k += 4) {
-      double a[8], b[NV];
+      double a[MU], b[NV];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) a[u] = -sa[(wr + u * 8 + fr) * LDK2 + k + fk];
+      for (int u = 0; u < MU; ++u) a[u] = -sa[(wr + u * 8 + fr) * LDK2 + k + fk];
 #pragma unroll
       for (int v = 0; v < NV; ++v) b[v] = sb[(wc + v * 8 + fr) * LDK2 + k + fk];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < MU; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) dmma_m8n8k4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
     }
   }
   cp_async_wait<0>();
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
+  for (int u = 0; u < MU; ++u) {
     const int r = r0 + wr + u * 8 + fr;
     if (r >= nrows_total) continue;
 #pragma unroll
@@ -750,6 +754,87 @@ __global__ void __launch_bounds__(128, 2) chol_update2_kernel(double* __restrict
       const int c = c0 + wc + v * 8 + 2 * fk;
       if (STORE_C || acc[u][v][0] == 1.2345e300) *reinterpret_cast<double2*>(&A[(size_t)r * ld + c]) = make_double2(acc[u][v][0], acc[u][v][1]);
     }
+  }
+}
+
+// ---- block-column updates on the critical path (L(b) and the strip): 64 x 64 tiles, 8 warps of 32 x 16 ------------
+// The generic kernel above gives a 64 x 64 tile to 8 warps of 64 x 8: nine shared-memory fragment loads per eight DMMAs.
+// Here a warp owns 32 x 16 (six loads per eight DMMAs), the K chunk is 16 and three CTAs fit an SM.
+// TM = 32 halves the tile (and its latency) for the second half of the factorisation, where a block column has fewer
+// 64-row tiles than the GPU has SMs.
+constexpr int S64 = 3;  // cp.async stages (5 stages measured no faster per launch and 0.2 ms slower overall: less co-residency)
+constexpr int kUpd64Smem = S64 * (NB + NB) * LDK2 * sizeof(double);
+template <int TM>
+__global__ void __launch_bounds__(256, 3) chol_update64_kernel(double* __restrict__ A, int ld, int kc0, int KT,
+                                                              int row_base, int col_base, int nrows_total) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int A_ELEMS = TM * LDK2, STAGE = A_ELEMS + NB * LDK2;
+  constexpr int MU = TM / 16, NV = 2;
+  const int r0 = row_base + blockIdx.x * TM, c0 = col_base + blockIdx.y * NB;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int wr = (w >> 2) * (TM / 2), wc = (w & 3) * 16;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int nchunks = KT / KC2;
+  auto load_stage = [&](int chunk, int stage) {
+    double* sa = smem + stage * STAGE;
+    double* sb = sa + A_ELEMS;
+    const int kc = kc0 + chunk * KC2;
+#pragma unroll
+    for (int e = t; e < (TM + NB) * (KC2 / 2); e += 256) {
+      const int row = e / (KC2 / 2), piece = e % (KC2 / 2);
+      if (row < TM) {
+        int gr = r0 + row; if (gr >= nrows_total) gr = nrows_total - 1;
+        cp_async16(sa + row * LDK2 + piece * 2, A + (size_t)gr * ld + kc + piece * 2);
+      } else {
+        const int rb = row - TM;
+        cp_async16(sb + rb * LDK2 + piece * 2, A + (size_t)(c0 + rb) * ld + kc + piece * 2);
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < S64 - 1; ++s) {
+    if (s < nchunks) load_stage(s, s);
+    cp_async_commit();
+  }
+  double acc[MU][NV][2];
+#pragma unroll
+  for (int u = 0; u < MU; ++u) {
+    int r = r0 + wr + u * 8 + fr; if (r >= nrows_total) r = nrows_total - 1;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const double2 cv = *reinterpret_cast<const double2*>(&A[(size_t)r * ld + c0 + wc + v * 8 + 2 * fk]);
+      acc[u][v][0] = cv.x; acc[u][v][1] = cv.y;
+    }
+  }
+  for (int ch = 0; ch < nchunks; ++ch) {
+    cp_async_wait<S64 - 2>();
+    __syncthreads();
+    const int nxt = ch + S64 - 1;
+    if (nxt < nchunks) load_stage(nxt, nxt % S64);
+    cp_async_commit();
+    const double* sa = smem + (ch % S64) * STAGE;
+    const double* sb = sa + A_ELEMS;
+#pragma unroll
+    for (int k = 0; k < KC2; k += 4) {
+      double a[MU], b[NV];
+#pragma unroll
+      for (int u = 0; u < MU; ++u) a[u] = -sa[(wr + u * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+      for (int v = 0; v < NV; ++v) b[v] = sb[(wc + v * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+      for (int u = 0; u < MU; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) dmma_m8n8k4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int u = 0; u < MU; ++u) {
+    const int r = r0 + wr + u * 8 + fr;
+    if (r >= nrows_total) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      *reinterpret_cast<double2*>(&A[(size_t)r * ld + c0 + wc + v * 8 + 2 * fk]) = make_double2(acc[u][v][0], acc[u][v][1]);
   }
 }
 
@@ -838,7 +923,9 @@ int DenseChol::Init(int n_, cudaStream_t st) {
     set((const void*)chol_panel2_kernel, kPanelSmem);
     set((const void*)chol_panel3_kernel, kPanel3Smem);
     set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
-    set((const void*)chol_update2_kernel<true, true>, kUpd2Smem);
+    set((const void*)chol_update2_kernel<true, true, 128>, kUpd2Smem);
+    set((const void*)chol_update64_kernel<64>, kUpd64Smem);
+    set((const void*)chol_update64_kernel<32>, kUpd64Smem);
     set((const void*)chol_update_kernel<OB, NB>, (int)(STAGES * (NB + OB) * LDK * sizeof(double)));
     set((const void*)chol_update_kernel<NB, NB>, (int)(STAGES * (NB + NB) * LDK * sizeof(double)));
   });
@@ -887,7 +974,8 @@ void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches)
   {  // strip: columns k0+64 .. k0+127, rows k0+64 .. end, K = 64
     const int rows = rows_total - (k0 + NB);
     const int tr = (rows + NB - 1) / NB;
-    chol_update_kernel<NB, NB><<<tr, 256, STAGES * (NB + NB) * LDK * sizeof(double), q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, 1);
+    if (tr * 2 <= num_sms) chol_update64_kernel<32><<<(rows + 31) / 32, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total);
+    else chol_update64_kernel<64><<<tr, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total);
   }
   chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag);
   chol_panel3_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, rows_total);
@@ -913,8 +1001,11 @@ int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
       if (b >= 3) THB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_c2[(b - 3) & 3], 0));
       const int pb = b >= 2 ? b - 2 : 0;  // first pending panel
       const int rows = rows_total - k0;
-      const dim3 grid((rows + NB - 1) / NB, OB / NB);  // 64 x 64 tiles, two CTAs per SM
-      chol_update_kernel<NB, NB><<<grid, 256, STAGES * (NB + NB) * LDK * sizeof(double), s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total, 1);
+      const dim3 grid((rows + NB - 1) / NB, OB / NB);
+      if ((int)(grid.x * grid.y) * 2 <= num_sms)  // second half of the factorisation: halve the tiles, use more SMs
+        chol_update64_kernel<32><<<dim3((rows + 31) / 32, OB / NB), 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total);
+      else
+        chol_update64_kernel<64><<<grid, 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total);
       *launches += 1;
     }
     PanelPair(s2, b, fail_flag, launches);
@@ -923,7 +1014,7 @@ int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
     if (ntr >= 1) {
       THB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_pp[b & 3], 0));
       const int tiles = ntr * (ntr + 1) + 2 * ntr;  // 128 x 64 tiles of the lower triangle + the rhs tile-row
-      chol_update2_kernel<true, true><<<tiles, 128, kUpd2Smem, st>>>(A, ld, k0, OB, k0 + 3 * OB, rows_total);
+      chol_update2_kernel<true, true, 128><<<tiles, 128, kUpd2Smem, st>>>(A, ld, k0, OB, k0 + 3 * OB, rows_total);
       THB_CUDA_CHECK(cudaEventRecord(ev_c2[b & 3], st));
       *launches += 1;
     }

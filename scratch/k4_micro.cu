@@ -223,6 +223,18 @@ int main(int argc, char** argv) {
     const int rows = rows_total - (k0 + NB), tr = (rows + NB - 1) / NB;
     printf("strip k0=%4d     %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_update_kernel<NB, NB><<<tr, 256, STAGES * (NB + NB) * LDK * sizeof(double)>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, 1); }, reps), tr);
   }
+  for (int k0 : {0, 3008, 5760}) {
+    const int rows = rows_total - (k0 + NB), tr = (rows + NB - 1) / NB;
+    printf("strip64 k0=%4d   %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_update64_kernel<64><<<tr, 256, kUpd64Smem>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total); }, reps), tr);
+  }
+  for (int b : {2, 24, 45}) {
+    const int k0 = b * OB, rows = rows_total - k0;
+    const dim3 grid((rows + NB - 1) / NB, OB / NB);
+    printf("L(b) old b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update_kernel<NB, NB><<<grid, 256, STAGES * (NB + NB) * LDK * sizeof(double)>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total, 1); }, reps), grid.x * grid.y);
+    printf("L(b) new b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<64><<<grid, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total); }, reps), grid.x * grid.y);
+    const dim3 g32((rows + 31) / 32, OB / NB);
+    printf("L(b) 32r b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<32><<<g32, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total); }, reps), g32.x * g32.y);
+  }
   for (int ob : {0, 23, 44}) {
     const int k0 = ob * OB, nt = n_pad / OB - ob - 1;
     printf("colupd ob=%2d      %.2f us (%d CTAs)\n", ob, 1e3 * time_ms([&] { chol_update_kernel<OB, NB><<<2 * nt + 1, 256, STAGES * (NB + OB) * LDK * sizeof(double)>>>(A, ld, k0, OB, k0 + OB, k0 + OB, rows_total, 1); }, reps), 2 * nt + 1);
@@ -231,12 +243,16 @@ int main(int argc, char** argv) {
   for (int ob : {0, 10, 23, 36, 43}) {
     const int k0 = ob * OB, ntr = n_pad / OB - ob - 2;
     const int tiles = ntr * (ntr + 1) + 2 * ntr;
-    const float ms = time_ms([&] { chol_update2_kernel<true, true><<<tiles, 128, kUpd2Smem>>>(A, ld, k0, OB, k0 + 2 * OB, rows_total); }, blocks_only ? 1 : 20);
+    cudaFuncSetAttribute(chol_update2_kernel<true, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
+    const float ms = time_ms([&] { chol_update2_kernel<true, true, 128><<<tiles, 128, kUpd2Smem>>>(A, ld, k0, OB, k0 + 2 * OB, rows_total); }, blocks_only ? 1 : 20);
     printf("update2 ob=%2d     %.2f us (%d tiles) %.2f TFLOP/s\n", ob, 1e3 * ms, tiles, tiles * 128.0 * 64 * 128 * 2 / ms / 1e9);
     cudaFuncSetAttribute(chol_update2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
     cudaFuncSetAttribute(chol_update2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
     const float msn = time_ms([&] { chol_update2_kernel<false, false><<<tiles, 128, kUpd2Smem>>>(A, ld, k0, OB, k0 + 2 * OB, rows_total); }, blocks_only ? 1 : 20);
     printf("update2 noC ob=%2d %.2f us (%d tiles) %.2f TFLOP/s\n", ob, 1e3 * msn, tiles, tiles * 128.0 * 64 * 128 * 2 / msn / 1e9);
+    cudaFuncSetAttribute(chol_update2_kernel<true, true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
+    const float ms8 = time_ms([&] { chol_update2_kernel<true, true, 256><<<tiles, 256, kUpd2Smem>>>(A, ld, k0, OB, k0 + 2 * OB, rows_total); }, blocks_only ? 1 : 20);
+    printf("update2 8w  ob=%2d %.2f us (%d tiles) %.2f TFLOP/s\n", ob, 1e3 * ms8, tiles, tiles * 128.0 * 64 * 128 * 2 / ms8 / 1e9);
     const float msl = time_ms([&] { chol_update2_kernel<true, false><<<tiles, 128, kUpd2Smem>>>(A, ld, k0, OB, k0 + 2 * OB, rows_total); }, blocks_only ? 1 : 20);
     printf("update2 ldC ob=%2d %.2f us (%d tiles) %.2f TFLOP/s\n", ob, 1e3 * msl, tiles, tiles * 128.0 * 64 * 128 * 2 / msl / 1e9);
     const int tiles1 = ntr * (ntr + 1) / 2 + ntr;
@@ -247,7 +263,7 @@ int main(int argc, char** argv) {
     const int ntr = 30, tiles = ntr * (ntr + 1) + 2 * ntr, base = 2048;
     cudaFuncSetAttribute(chol_update2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kUpd2Smem);
     const float msn = time_ms([&] { chol_update2_kernel<false, false><<<tiles, 128, kUpd2Smem>>>(A, ld, 0, KT, base, rows_total); }, blocks_only ? 1 : 10);
-    const float msc = time_ms([&] { chol_update2_kernel<true, true><<<tiles, 128, kUpd2Smem>>>(A, ld, 0, KT, base, rows_total); }, blocks_only ? 1 : 10);
+    const float msc = time_ms([&] { chol_update2_kernel<true, true, 128><<<tiles, 128, kUpd2Smem>>>(A, ld, 0, KT, base, rows_total); }, blocks_only ? 1 : 10);
     printf("update2 K=%4d (%d tiles): no C %.2f TFLOP/s, with C %.2f TFLOP/s\n", KT, tiles, tiles * 128.0 * 64 * KT * 2 / msn / 1e9, tiles * 128.0 * 64 * KT * 2 / msc / 1e9);
   }
   printf("SM clock right after the update loops: %.0f MHz\n", probe_mhz(d_out));
