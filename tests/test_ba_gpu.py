@@ -191,6 +191,30 @@ def test_c3_scaled_mixed_models_intrinsics_refinement(lib, oracle):
     _compare_solves(lib, oracle, prob, o)
 
 
+def test_c3_full_size_properties(lib):
+    """BASELINE configs[2] at full size (500 cams / 50k pts / 400k obs, DoubleSphere + ExtendedUnified groups, focal length
+    and distortion refined with bounds): size-independent properties - success, monotone cost, chi^2 noise floor, focal
+    lengths back near the generating values, idempotence at the optimum."""
+    prob, gt = synthetic.config_c3()
+    assert prob.num_cameras == 500 and prob.num_points == 50000 and prob.num_observations == 400000
+    truth = prob.a["intr"].copy()
+    _perturb_intrinsics(prob, 0.02)
+    o = capi.default_options(lib)
+    o.max_num_iterations = 50
+    g = gpu_solve(lib, prob, o)
+    assert g["success"] == 1 and g["num_iterations"] >= 3
+    costs = np.array(g["iter_cost"])
+    assert np.all(np.diff(costs) <= 1e-9 * costs[:-1])
+    dof = 2 * prob.num_observations - (6 * prob.num_cameras + 3 * prob.num_points + 2 * 3 - 7)
+    assert abs(g["final_cost"] / (0.5 * 0.25 * dof) - 1.0) < 0.03      # sigma = 0.5 px
+    # the pinhole-like EUCM focal length is pulled back; the DoubleSphere one stays within the perturbation (f trades
+    # against xi / alpha at the noise floor, and Ceres' function tolerance stops the solve there)
+    np.testing.assert_allclose(prob.a["intr"][1, 0], truth[1, 0], rtol=2e-3)
+    np.testing.assert_allclose(prob.a["intr"][:, 0], truth[:, 0], rtol=2.5e-2)
+    g2 = gpu_solve(lib, prob, capi.default_options(lib))
+    assert g2["num_iterations"] <= 2 and abs(g2["final_cost"] - g["final_cost"]) <= 1e-6 * g["final_cost"]
+
+
 def test_intrinsics_all_free_euclidean_points_and_huber(lib, oracle):
     prob, gt = synthetic.make_ba_problem(10, 300, 5, models=(capi.MODEL_PINHOLE, capi.MODEL_FISHEYE), seed=91, intr_const_mask=[0, 0])
     _perturb_intrinsics(prob, -0.015)
