@@ -27,9 +27,9 @@
 namespace thb {
 namespace {
 
-constexpr int RT = 256;   // threads per CTA
+constexpr int RT = 128;   // threads per CTA (three CTAs per SM: the relative-pose solver wants ~170 registers)
 constexpr int NW = RT / 32;
-constexpr int BI = 32;    // iterations per batch
+constexpr int BI = 64;    // iterations per batch = hypotheses solved in parallel (warps 0 and 1)
 constexpr int MAXM = 10;  // five-point solutions per sample
 
 struct Model { double E[9], R[9], p[3]; };
@@ -602,7 +602,6 @@ __device__ void score_model(const ThbRansacParams& P, const double* __restrict__
 }
 
 struct RansacShared {
-  Model models[BI * MAXM];
   Model best;
   double cost[BI * MAXM];
   int ninl[BI * MAXM];
@@ -611,29 +610,41 @@ struct RansacShared {
   int samples[BI][5];  // up to 5 indices per sample
   Mt19937 rng;
   double best_cost;
-  int max_iterations, it0, finished, num_iterations, have_best;
+  int max_iterations, it0, finished, num_iterations, have_best, pair;
 };
 
+// Persistent grid (three CTAs per SM) pulling pairs from an atomic counter: RANSAC iteration counts differ by 100x
+// between pairs, and a CTA is latency-bound while its two solver warps run, so several CTAs per SM in different phases
+// are what keeps the FP64 pipes busy. (r01: one 256-thread CTA of 255 registers per SM, the candidate models in 54 KB of
+// shared memory, one solver warp: ~15 % of the FP64 issue rate.) The candidate models of a batch live in a per-CTA
+// global scratch area (L2-resident) so that shared memory only holds the pair's correspondences and the control block.
 template <class Est>
-__global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
-                                               const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
-                                               ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
-                                               int* __restrict__ idx_ws, int smem_corr_cap) {
+__global__ void __launch_bounds__(RT, 3) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
+                                                  const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
+                                                  ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
+                                                  int* __restrict__ idx_ws, int smem_corr_cap, Model* model_ws,
+                                                  int* __restrict__ pair_counter) {
   constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
   double* s_corr = reinterpret_cast<double*>(smem_raw + ((sizeof(RansacShared) + 31) / 32) * 32);
-  const int pair = blockIdx.x;
-  if (pair >= num_pairs) return;
+  Model* M = model_ws + (size_t)blockIdx.x * BI * MAXM;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const double log_failure_prob = log(P.failure_probability);
+  while (true) {
+  __syncthreads();  // the previous pair is completely done (shared state, final scoring)
+  if (t == 0) S.pair = atomicAdd(pair_counter, 1);
+  __syncthreads();
+  const int pair = S.pair;
+  if (pair >= num_pairs) break;
   const long long off = pair_offset[pair];
   const int n = (int)(pair_offset[pair + 1] - off);
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   ThbRelPoseResult* out = results + pair;
   uint8_t* mask = mask_all ? mask_all + off : nullptr;
   if (n < SS) {  // RandomSampler::Initialize would CHECK-abort; reported as failure
     if (t == 0) { memset(out, 0, sizeof(*out)); out->num_input_data_points = n; }
     if (mask) for (int i = t; i < n; i += RT) mask[i] = 0;
-    return;
+    continue;
   }
   const double* g_corr = corr_all + (size_t)off * DD;
   const bool in_smem = n <= smem_corr_cap;
@@ -644,7 +655,6 @@ __global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs,
   }
   int* sidx = idx_ws + off;  // RandomSampler::sample_indices_ (persistent permutation)
   for (int i = t; i < n; i += RT) sidx[i] = i;
-  const double log_failure_prob = log(P.failure_probability);
   if (t == 0) {
     mt_seed(&S.rng, seed[pair]);
     S.best_cost = DBL_MAX;
@@ -674,24 +684,24 @@ __global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs,
         }
     }
     __syncthreads();
-    // ---- solve: thread b of warp 0 = iteration it0 + b
-    if (w == 0) {
+    // ---- solve: thread b = iteration it0 + b
+    if (t < BI) {
       int nm = 0;
-      if (lane < nit) {
+      if (t < nit) {
         double sample[SS * DD];
         for (int i = 0; i < SS; ++i)
-          for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[lane][i] * DD + k];
+          for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[t][i] * DD + k];
         Model found[Est::MAXM];
         nm = Est::solve(sample, found);
-        for (int e = 0; e < nm; ++e) S.models[lane * MAXM + e] = found[e];
+        for (int e = 0; e < nm; ++e) M[t * MAXM + e] = found[e];
       }
-      if (lane < BI) S.nmodels[lane] = nm;
-      __syncwarp();
-      if (lane == 0) {
-        int acc = 0;
-        for (int b = 0; b < BI; ++b) { S.model_start[b] = acc; acc += (b < nit) ? S.nmodels[b] : 0; }
-        S.model_start[BI] = acc;
-      }
+      S.nmodels[t] = nm;
+    }
+    __syncthreads();
+    if (t == 0) {
+      int acc = 0;
+      for (int b = 0; b < BI; ++b) { S.model_start[b] = acc; acc += (b < nit) ? S.nmodels[b] : 0; }
+      S.model_start[BI] = acc;
     }
     __syncthreads();
     // ---- score: warp w takes flat models w, w + NW, ...
@@ -702,7 +712,7 @@ __global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs,
       while (S.model_start[b + 1] <= j) ++b;
       const int k = j - S.model_start[b];
       double cost; int ninl;
-      score_model<Est>(P, corr, n, S.models[b * MAXM + k], bail, nullptr, &cost, &ninl);
+      score_model<Est>(P, corr, n, M[b * MAXM + k], bail, nullptr, &cost, &ninl);
       if (lane == 0) { S.cost[b * MAXM + k] = cost; S.ninl[b * MAXM + k] = ninl; }
     }
     __syncthreads();
@@ -715,7 +725,7 @@ __global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs,
           const double sample_cost = S.cost[b * MAXM + k];
           if (sample_cost < S.best_cost) {
             const double inlier_ratio = (double)S.ninl[b * MAXM + k] / (double)n;
-            S.best = S.models[b * MAXM + k];
+            S.best = M[b * MAXM + k];
             S.best_cost = sample_cost;
             S.have_best = 1;
             if (inlier_ratio < (double)SS / (double)n) continue;
@@ -744,6 +754,7 @@ __global__ void __launch_bounds__(RT) k_ransac(ThbRansacParams P, int num_pairs,
       for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
     }
   }
+  }  // next pair
 }
 
 __global__ void k_five_point(const double* __restrict__ x1, const double* __restrict__ x2, int count, double* __restrict__ E_out,
@@ -758,12 +769,13 @@ __global__ void k_five_point(const double* __restrict__ x1, const double* __rest
   for (int k = 0; k < 90; ++k) E_out[90 * (size_t)i + k] = Es[k];
 }
 
-struct Bufs {
+struct Bufs {  // scoped, stream-ordered device allocations (no cudaMalloc / cudaFree per batch after the first)
   std::vector<void*> p;
-  ~Bufs() { for (void* q : p) cudaFree(q); }
+  cudaStream_t st = nullptr;
+  ~Bufs() { for (void* q : p) cudaFreeAsync(q, st); }
   template <typename T> T* get(size_t n) {
     void* q = nullptr;
-    if (cudaMalloc(&q, (n ? n : 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    if (cudaMallocAsync(&q, (n ? n : 1) * sizeof(T), st) != cudaSuccess) return nullptr;
     p.push_back(q);
     return (T*)q;
   }
@@ -774,9 +786,15 @@ int check_device() {
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) THB_FAIL(THB_E_NO_DEVICE, "no CUDA device visible; libtheia_b200 has no CPU path");
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceProp pr;
-  THB_CUDA_CHECK(cudaGetDeviceProperties(&pr, dev));
-  if (pr.major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
+  int major = 0;
+  THB_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
+  static bool pool_once = false;
+  if (!pool_once) {  // keep freed blocks in the default pool (same policy as the BA path)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+    pool_once = true;
+  }
   return THB_OK;
 }
 
@@ -809,6 +827,7 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   const long long total = h_off[np];
   if (total > 0 && !b->corr) THB_FAIL(THB_E_INVALID_ARGUMENT, "null corr");
   Bufs B;
+  B.st = st;
   const long long* d_off; const double* d_corr; const uint32_t* d_seed; ThbRelPoseResult* d_res; uint8_t* d_mask = nullptr;
   if (host) {
     long long* o = B.get<long long>(np + 1); double* c = B.get<double>((size_t)total * DD); uint32_t* s = B.get<uint32_t>(np);
@@ -832,7 +851,16 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   int cap = max_n;
   if (want > limit) { cap = (int)((limit - ctrl) / per); want = ctrl + (size_t)cap * per; }
   THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac<Est>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-  k_ransac<Est><<<np, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap);
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = std::min(np, 3 * sms);
+  Model* d_models = B.get<Model>((size_t)grid * BI * MAXM);
+  int* d_counter = B.get<int>(1);
+  if (!d_models || !d_counter) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap, d_models, d_counter);
   THB_CUDA_CHECK(cudaGetLastError());
   if (host) {
     THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
@@ -869,6 +897,7 @@ int run_solver(const double* a, const double* b, int count, double* oa, double* 
   if (rc != THB_OK) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Bufs B;
+  B.st = st;
   double* da = B.get<double>((size_t)count * IN_A); double* db = B.get<double>((size_t)count * (IN_B > 0 ? IN_B : 1));
   double* doa = B.get<double>((size_t)count * OUT_A); double* dob = B.get<double>((size_t)count * (OUT_B > 0 ? OUT_B : 1));
   int* dn = B.get<int>(count);
@@ -935,6 +964,7 @@ int thb_five_point_relative_pose(const double* x1, const double* x2, int32_t cou
   if (rc != THB_OK) return rc;
   cudaStream_t st = (cudaStream_t)cuda_stream;
   Bufs B;
+  B.st = st;
   double* a = B.get<double>((size_t)count * 10); double* b = B.get<double>((size_t)count * 10);
   double* e = B.get<double>((size_t)count * 90); int* n = B.get<int>(count);
   if (!a || !b || !e || !n) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
