@@ -251,11 +251,26 @@ def run_ransac(args, rank, local_rank, world):
     ms = e0.elapsed_time(e1)
     sampler.stop_flag.set(); sampler.join()
     # end to end: host buffers in, results + inlier masks out
-    res = np.zeros(mine.num_pairs, capi.RELPOSE_DTYPE); mask = np.zeros(int(mine.pair_offset[-1]), np.uint8)
-    hb = mine.struct()
-    torch.cuda.synchronize(); t0 = time.perf_counter()
-    capi.check(lib.thb_ransac_relpose_batch(C.byref(hb), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), sptr))
-    e2e_s = time.perf_counter() - t0
+    # pinned host buffers (the contract's e2e: H2D from pinned memory, D2H of the results inside the timed region)
+    pin_corr = torch.from_numpy(mine.corr).pin_memory(); pin_off = torch.from_numpy(mine.pair_offset).pin_memory()
+    pin_seed = torch.from_numpy(mine.seed.astype(np.int64)).to(torch.int32).pin_memory()
+    pin_res = torch.zeros(mine.num_pairs * rec, dtype=torch.uint8).pin_memory()
+    pin_mask = torch.zeros(int(mine.pair_offset[-1]), dtype=torch.uint8).pin_memory()
+    hb = capi.ThbPairBatch(); hb.num_pairs = mine.num_pairs; hb.memory_space = capi.THB_MEM_HOST
+    hb.pair_offset = pin_off.data_ptr(); hb.corr = pin_corr.data_ptr(); hb.seed = pin_seed.data_ptr()
+
+    def e2e_call():
+        capi.check(lib.thb_ransac_relpose_batch(C.byref(hb), C.byref(params), C.c_void_p(pin_res.data_ptr()), C.c_void_p(pin_mask.data_ptr()), sptr))
+    e2e_call()  # warm-up (pool growth)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_call()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / K
+    res = np.frombuffer(pin_res.numpy().tobytes(), dtype=capi.RELPOSE_DTYPE); mask = pin_mask.numpy()
     t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

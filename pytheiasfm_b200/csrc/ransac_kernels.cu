@@ -29,7 +29,7 @@ namespace {
 
 constexpr int RT = 128;   // threads per CTA (three CTAs per SM: the relative-pose solver wants ~170 registers)
 constexpr int NW = RT / 32;
-constexpr int BI = 64;    // iterations per batch = hypotheses solved in parallel (warps 0 and 1)
+constexpr int BI = 128;   // iterations per batch = hypotheses solved in parallel (one per thread)
 constexpr int MAXM = 10;  // five-point solutions per sample
 
 struct Model { double E[9], R[9], p[3]; };
@@ -603,8 +603,6 @@ __device__ void score_model(const ThbRansacParams& P, const double* __restrict__
 
 struct RansacShared {
   Model best;
-  double cost[BI * MAXM];
-  int ninl[BI * MAXM];
   int nmodels[BI];
   int model_start[BI + 1];
   int samples[BI][5];  // up to 5 indices per sample
@@ -622,13 +620,15 @@ template <class Est>
 __global__ void __launch_bounds__(RT, 3) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
                                                   const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
                                                   ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
-                                                  int* __restrict__ idx_ws, int smem_corr_cap, Model* model_ws,
-                                                  int* __restrict__ pair_counter) {
+                                                  int* __restrict__ idx_ws, int smem_corr_cap, Model* model_ws, double* cost_ws,
+                                                  int* ninl_ws, int* __restrict__ pair_counter) {
   constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
   double* s_corr = reinterpret_cast<double*>(smem_raw + ((sizeof(RansacShared) + 31) / 32) * 32);
   Model* M = model_ws + (size_t)blockIdx.x * BI * MAXM;
+  double* g_cost = cost_ws + (size_t)blockIdx.x * BI * MAXM;  // per-model cost / inlier count of the current batch
+  int* g_ninl = ninl_ws + (size_t)blockIdx.x * BI * MAXM;
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const double log_failure_prob = log(P.failure_probability);
   while (true) {
@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(RT, 3) k_ransac(ThbRansacParams P, int num_pai
       const int k = j - S.model_start[b];
       double cost; int ninl;
       score_model<Est>(P, corr, n, M[b * MAXM + k], bail, nullptr, &cost, &ninl);
-      if (lane == 0) { S.cost[b * MAXM + k] = cost; S.ninl[b * MAXM + k] = ninl; }
+      if (lane == 0) { g_cost[b * MAXM + k] = cost; g_ninl[b * MAXM + k] = ninl; }
     }
     __syncthreads();
     // ---- scan in (iteration, model) order
@@ -722,9 +722,9 @@ __global__ void __launch_bounds__(RT, 3) k_ransac(ThbRansacParams P, int num_pai
       for (int b = 0; b < nit; ++b, ++it) {
         if (it >= S.max_iterations) break;
         for (int k = 0; k < S.nmodels[b]; ++k) {
-          const double sample_cost = S.cost[b * MAXM + k];
+          const double sample_cost = g_cost[b * MAXM + k];
           if (sample_cost < S.best_cost) {
-            const double inlier_ratio = (double)S.ninl[b * MAXM + k] / (double)n;
+            const double inlier_ratio = (double)g_ninl[b * MAXM + k] / (double)n;
             S.best = M[b * MAXM + k];
             S.best_cost = sample_cost;
             S.have_best = 1;
@@ -857,10 +857,12 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   if (sms <= 0) sms = 148;
   const int grid = std::min(np, 3 * sms);
   Model* d_models = B.get<Model>((size_t)grid * BI * MAXM);
+  double* d_cost = B.get<double>((size_t)grid * BI * MAXM);
+  int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
   int* d_counter = B.get<int>(1);
-  if (!d_models || !d_counter) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  if (!d_models || !d_cost || !d_ninl || !d_counter) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap, d_models, d_counter);
+  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap, d_models, d_cost, d_ninl, d_counter);
   THB_CUDA_CHECK(cudaGetLastError());
   if (host) {
     THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
