@@ -32,6 +32,12 @@ METRIC = "BA iterations/s (1k cams, 100k pts, 1M obs)"
 UNIT = "iterations/s"
 
 
+def quiet_nccl():
+    """NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must be the one JSON line."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def workload_config(args):
     return {"workload": "C2 synthetic Pinhole BundleAdjustReconstruction: %d cams / %d pts / %d obs" % (
                 int(round(1000 * args.scale)), int(round(100000 * args.scale)), int(round(1000000 * args.scale))),
@@ -204,6 +210,7 @@ def run_ransac(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_library()
     # static block partition of the pair table by cumulative correspondence count (pytheiasfm_b200/sharding.py)
@@ -329,6 +336,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = capi.load_library()  # raises if the CUDA library is missing: no fallback
 
