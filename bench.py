@@ -77,6 +77,24 @@ class ClockSampler(threading.Thread):
         self.samples = []
 
     def run(self):
+        # NVML in-process when available: an nvidia-smi subprocess per sample stalls the driver for tens of ms, which is
+        # visible in a 150 ms timed region
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            reasons_fn = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = [(0x8, 2), (0x40, 3), (0x20, 4), (0x4, 5)]  # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            while not self.stop_flag.is_set():
+                r = int(reasons_fn(h))
+                row = [str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)), "", "", "", ""]
+                for mask, pos in bits:
+                    row[pos] = "Active" if r & mask else "Not Active"
+                self.samples.append(row)
+                self.stop_flag.wait(0.02)
+            return
+        except Exception:  # noqa: BLE001
+            pass
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():

@@ -168,164 +168,12 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A,
   }
 }
 
-// ---- compact variants of diag / panel -------------------------------------------------------------------------------
-// The fully unrolled kernels above are 64 KB / 27 KB of straight-line code that every launch executes exactly once:
-// measured at warm clocks they run at ~10 cycles per instruction, i.e. they are instruction-fetch bound, not FP64 bound
-// (B200 issues a warp-wide DFMA every 2.1 cycles per SM sub-partition, latency 8.8 cycles; scratch/k4_micro.cu). The
-// variants below keep the register-resident row slices but ROTATE them (local index 0 is always the active column
-// group), so four pivots form a loop body of a few KB that stays in the instruction cache.
-__global__ void __launch_bounds__(256) chol_diag2_kernel(double* __restrict__ A, int ld, int k0,
-                                                         double* __restrict__ rd, int* __restrict__ fail) {
-  __shared__ double S[NB][NB + 1];
-  __shared__ double colbuf[2][NB];
-  const int t = threadIdx.x, i = t & 63, g = t >> 6;
-  {
-    double v[16];  // all 16 loads of a thread in flight at once
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 256 * m, r = e >> 6, c = e & 63;
-      v[m] = (c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-    }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 256 * m;
-      S[e >> 6][e & 63] = v[m];
-    }
-  }
-  __syncthreads();
-  double a[16];
-#pragma unroll
-  for (int jj = 0; jj < 16; ++jj) a[jj] = S[i][4 * jj + g];
-  __syncthreads();  // S becomes the output buffer
-#pragma unroll 1
-  for (int m = 0; m < 16; ++m) {
-    const int live = 16 - m;  // local column groups 0 .. live-1 are still in play
-#pragma unroll
-    for (int gk = 0; gk < 4; ++gk) {
-      const int k = 4 * m + gk;
-      double* cb = colbuf[gk & 1];
-      if (g == gk) cb[i] = a[0];
-      __syncthreads();
-      const double d = cb[k];
-      if (!(d > 0.0)) {  // not positive definite (or NaN): uniform across the CTA
-        if (t == 0) atomicExch(fail, 1);
-        return;
-      }
-      if (i >= k) {
-        const double rs = fast_rsqrt(d);
-        const double ci = cb[i];
-        if (g == gk) {
-          a[0] = ci * rs;  // i == k: d * rsqrt(d) = sqrt(d)
-          if (i == k) rd[k] = rs;
-        }
-        const double cid = ci * (rs * rs);  // c_i / d
-        const double* cj = cb + 4 * m + g;  // cj[4 l] = c_j of local column group l
-        if (g > gk && 4 * m + g <= i) a[0] -= cid * cj[0];
-#pragma unroll
-        for (int qd = 0; qd < 4; ++qd) {
-          if (4 * qd < live) {  // uniform: skip finished column groups four at a time
-#pragma unroll
-            for (int l = 4 * qd; l < 4 * qd + 4; ++l) {
-              if (l == 0) continue;
-              if (l < live && 4 * (m + l) + g <= i) a[l] -= cid * cj[4 * l];
-            }
-          }
-        }
-      }
-    }
-    S[i][4 * m + g] = a[0];  // column group m is final
-#pragma unroll
-    for (int l = 0; l < 15; ++l) a[l] = a[l + 1];
-  }
-  __syncthreads();
-  for (int e = t; e < NB * NB; e += 256) {  // coalesced store of the lower triangle
-    const int r = e >> 6, c = e & 63;
-    if (c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = S[r][c];
-  }
-}
-
-__global__ void __launch_bounds__(128) chol_panel2_kernel(double* __restrict__ A, int ld, int k0,
-                                                          const double* __restrict__ rd, int nrows_total) {
-  extern __shared__ double psm[];
-  double (*Lt)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm);                   // Lt[k][j] = L11[j][k]
-  double (*Bs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(psm + NB * (NB + 1));
-  __shared__ double rdg[NB];
-  const int r0 = k0 + NB + blockIdx.x * PR;
-  const int t = threadIdx.x;
-  THB_PROBE(0);
-  {
-    double v[16], u[16];  // two batches of loads in flight
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 128 * m, ii = e >> 6, j = e & 63;
-      v[m] = (j <= ii) ? A[(size_t)(k0 + ii) * ld + k0 + j] : 0.0;
-      u[m] = (r0 + ii < nrows_total) ? A[(size_t)(r0 + ii) * ld + k0 + j] : 0.0;
-    }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 128 * m;
-      Lt[e & 63][e >> 6] = v[m];
-      Bs[e >> 6][e & 63] = u[m];
-    }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 128 * (m + 16), ii = e >> 6, j = e & 63;
-      v[m] = (j <= ii) ? A[(size_t)(k0 + ii) * ld + k0 + j] : 0.0;
-    }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const int e = t + 128 * (m + 16);
-      Lt[e & 63][e >> 6] = v[m];
-    }
-  }
-  if (t < NB) rdg[t] = rd[t];
-  __syncthreads();
-  THB_PROBE(1);
-  const int row = t >> 2, q = t & 3, lane = t & 31;
-  double b[16];
-#pragma unroll
-  for (int jj = 0; jj < 16; ++jj) b[jj] = Bs[row][4 * jj + q];
-#pragma unroll 1
-  for (int m = 0; m < 16; ++m) {
-    const int live = 16 - m;
-#pragma unroll
-    for (int qk = 0; qk < 4; ++qk) {
-      const int k = 4 * m + qk;
-      double xv = b[0] * rdg[k];  // meaningful in the owner lane (q == qk) only
-      xv = __shfl_sync(0xffffffffu, xv, (lane & ~3) | qk);
-      if (q == qk) b[0] = xv;
-      const double* Lk = &Lt[k][4 * m + q];  // Lk[4 l] = L11[4 (m + l) + q][k]
-      if (q > qk) b[0] -= xv * Lk[0];
-#pragma unroll
-      for (int qd = 0; qd < 4; ++qd) {
-        if (4 * qd < live) {
-#pragma unroll
-          for (int l = 4 * qd; l < 4 * qd + 4; ++l) {
-            if (l == 0) continue;
-            if (l < live) b[l] -= xv * Lk[4 * l];
-          }
-        }
-      }
-    }
-    Bs[row][4 * m + q] = b[0];
-#pragma unroll
-    for (int l = 0; l < 15; ++l) b[l] = b[l + 1];
-  }
-  __syncthreads();
-  THB_PROBE(2);
-  for (int e = t; e < PR * NB; e += 128) {
-    const int ii = e >> 6, j = e & 63;
-    if (r0 + ii < nrows_total) A[(size_t)(r0 + ii) * ld + k0 + j] = Bs[ii][j];
-  }
-  THB_PROBE(3);
-}
-
 // ---- thread-per-row variants (the ones FactorAndSolve launches) ------------------------------------------------------
 // Measured on B200 (scratch/k4_micro.cu, scratch/lat_micro.cu): a warp-wide DFMA issues every 2.1 cycles per SM
 // sub-partition with 8.8 cycles latency, i.e. FP64 SIMT runs at the full 64 FMA/clk/SM; a publish + __syncthreads + read
 // round trip costs 75-95 cycles, a quad shuffle 30, a branch ~25, and straight-line code that is executed once is
-// instruction-fetch bound when the I-cache is cold. The kernels above spend 350-950 cycles per pivot on exactly those
-// latencies. Here one THREAD owns one matrix row in registers, columns are handled in blocks of 8 (2 barriers per block
+// instruction-fetch bound when the I-cache is cold. The r01-start kernels above spend 350-650 cycles per pivot on exactly
+// those latencies (a loop-compacted variant of them, 950; removed). Here one THREAD owns one matrix row in registers, columns are handled in blocks of 8 (2 barriers per block
 // instead of 1 per pivot, no shuffles), the register row is rotated by 8 per block so the loop body has static register
 // indices and stays a few KB, and everything inside a block is independent FMAs that pipeline at full rate.
 
@@ -920,7 +768,6 @@ int DenseChol::Init(int n_, cudaStream_t st) {
     };
     set((const void*)chol_inverse_kernel, kInvSmem);
     set((const void*)chol_panel_kernel, kPanelSmem);
-    set((const void*)chol_panel2_kernel, kPanelSmem);
     set((const void*)chol_panel3_kernel, kPanel3Smem);
     set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
     set((const void*)chol_update2_kernel<true, true, 128>, kUpd2Smem);

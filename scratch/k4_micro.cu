@@ -198,12 +198,9 @@ int main(int argc, char** argv) {
   }
   printf("diag64            %.2f us\n", 1e3 * time_ms([&] { chol_diag_kernel<<<1, 256>>>(A, ld, 4096, rd, d_fail); }, reps));
   printf("SM clock right after the diag loop: %.0f MHz\n", probe_mhz(d_out));
-  printf("diag64 compact    %.2f us\n", 1e3 * time_ms([&] { chol_diag2_kernel<<<1, 256>>>(A, ld, 4096, rd, d_fail); }, reps));
   printf("diag64 row/thread %.2f us\n", 1e3 * time_ms([&] { chol_diag3_kernel<<<1, 64>>>(A, ld, 4096, rd, d_fail); }, reps));
   for (int k0 : {0, 3008, 5760})
     printf("panel3 k0=%4d    %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_panel3_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kPanel3Smem>>>(A, ld, k0, rd, rows_total); }, reps), (n_pad - k0 - NB) / PR3 + 1);
-  for (int k0 : {0, 3008, 5760})
-    printf("panel2 k0=%4d    %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_panel2_kernel<<<(n_pad - k0 - NB) / PR + 1, 128, kPanelSmem>>>(A, ld, k0, rd, rows_total); }, reps), (n_pad - k0 - NB) / PR + 1);
   for (int k0 : {0, 3008, 5760})
     printf("panel k0=%4d     %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_panel_kernel<<<(n_pad - k0 - NB) / PR + 1, 128, kPanelSmem>>>(A, ld, k0, rd, rows_total); }, reps), (n_pad - k0 - NB) / PR + 1);
   {
