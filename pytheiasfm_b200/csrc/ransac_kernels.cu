@@ -98,7 +98,10 @@ __device__ int five_point(const double* x1, const double* x2, double* E_out) {
       for (int k = 0; k < 20; ++k) row[k] += t20[k];
     }
   }
-  double L[100], Rm[100], X[100];
+  // per-thread work matrices live in local memory and their footprint decides the L1 hit rate of the solve phase:
+  // X reuses C, which is dead between its split into L | Rm and its reuse as eigen-solver scratch
+  double L[100], Rm[100];
+  double* X = C;
   for (int r = 0; r < 10; ++r) for (int c = 0; c < 10; ++c) { L[r * 10 + c] = C[r * 20 + c]; Rm[r * 10 + c] = C[r * 20 + 10 + c]; }
   {
     sl::FullPivLU<10, 10> clu;
@@ -698,9 +701,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
         double sample[SS * DD];
         for (int i = 0; i < SS; ++i)
           for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[t][i] * csi + (size_t)k * csk];
-        Model found[Est::MAXM];
-        nm = Est::solve(sample, found);
-        for (int e = 0; e < nm; ++e) M[t * MAXM + e] = found[e];
+        nm = Est::solve(sample, M + t * MAXM);  // straight into the CTA's scratch area: no 1.7 KB local copy
       }
       S.nmodels[t] = nm;
     }
