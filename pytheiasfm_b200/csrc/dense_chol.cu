@@ -345,6 +345,155 @@ __global__ void __launch_bounds__(64) chol_panel3_kernel(double* __restrict__ A,
   }
 }
 
+// ---- diag + panel in ONE launch (what FactorAndSolve uses) ---------------------------------------------------------
+// Every CTA factors the 64 x 64 diagonal block itself (the same latency-bound 8-column-block loop as chol_diag3_kernel;
+// redundant FP64 work is free here) while cp.async brings its own 64 panel rows into shared memory, then runs the
+// chol_panel3_kernel substitution against the factor it holds in shared memory. CTA 0 alone stores the factored block
+// and 1 / L_kk. Saves a dependent launch and an L11 round trip through global memory per inner panel.
+constexpr int kDpSmem = 2 * NB * LP * sizeof(double);
+__global__ void __launch_bounds__(64) chol_dp_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ rd,
+                                                     int* __restrict__ fail, int nrows_total,
+                                                     const double* __restrict__ diag_src) {
+  extern __shared__ __align__(16) double psm[];
+  double (*L)[LP] = reinterpret_cast<double (*)[LP]>(psm);             // L11, filled block column by block column
+  double (*Bt)[LP] = reinterpret_cast<double (*)[LP]>(psm + NB * LP);  // this CTA's panel rows (prefetched)
+  __shared__ __align__(32) double Dblk[8][8];
+  __shared__ double rdg[NB];
+  const int i = threadIdx.x;
+  const bool writer = blockIdx.x == 0;
+  const int r = k0 + NB + blockIdx.x * PR3 + i;
+  const bool valid = r < nrows_total;
+  {  // panel rows -> shared memory, in flight during the whole factorisation
+    const int r0 = k0 + NB + blockIdx.x * PR3;
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const int e = i + 64 * m, row = e >> 5, piece = e & 31;
+      const int gr = min(r0 + row, nrows_total - 1);
+      cp_async16(&Bt[row][2 * piece], A + (size_t)gr * ld + k0 + 2 * piece);
+    }
+    cp_async_commit();
+  }
+  double* grow = A + (size_t)(k0 + i) * ld + k0;
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 4) ldg256(diag_src + i * NB + c, a + c);  // the copy, not A (see chol_update64_kernel)
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int k = 8 * kb;
+    if ((i >> 3) == kb) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Dblk[i & 7][u] = a[u];
+    }
+    __syncthreads();
+    if (i >= k) {
+      double D[8][8], rs[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double4 lo = *reinterpret_cast<const double4*>(&Dblk[v][0]);
+        const double4 hi = *reinterpret_cast<const double4*>(&Dblk[v][4]);
+        D[v][0] = lo.x; D[v][1] = lo.y; D[v][2] = lo.z; D[v][3] = lo.w; D[v][4] = hi.x; D[v][5] = hi.y; D[v][6] = hi.z; D[v][7] = hi.w;
+      }
+      bool bad = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double d = D[u][u];
+        bad |= !(d > 0.0);
+        rs[u] = rsqrt_f64(d);
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) D[v][u] *= rs[u];
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v)
+#pragma unroll
+          for (int w = u + 1; w <= v; ++w) D[v][w] -= D[v][u] * D[w][u];
+      }
+      if (bad) {  // not positive definite (or NaN); identical in every thread and CTA, the factor is garbage from here on
+        if (writer && i == k) atomicExch(fail, 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rs[u] = 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double x = a[u] * rs[u];
+        a[u] = x;
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) a[v] -= x * D[v][u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(&L[i][k + u]) = make_double2(a[u], a[u + 1]);
+      if (i == k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { rdg[k + u] = rs[u]; if (writer) rd[k + u] = rs[u]; }
+      }
+      if (writer) {  // finished block column of this row -> global (only the lower triangle is ever written)
+        if (i >= k + 8) {
+          stg256(grow + k, a); stg256(grow + k + 4, a + 4);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) if (k + u <= i) grow[k + u] = a[u];
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int cg = 1; cg < 8; ++cg) {
+      if (cg < 8 - kb && k + 8 * cg <= (i | 31)) {  // uniform per warp
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const int j = k + 8 * cg + v;
+          const double* Lj = &L[j][k];
+          const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+          const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+          double acc = a[8 * cg + v];
+          acc = fma(-a[0], l0.x, acc); acc = fma(-a[1], l0.y, acc); acc = fma(-a[2], l1.x, acc); acc = fma(-a[3], l1.y, acc);
+          acc = fma(-a[4], l2.x, acc); acc = fma(-a[5], l2.y, acc); acc = fma(-a[6], l3.x, acc); acc = fma(-a[7], l3.y, acc);
+          if (j <= i) a[8 * cg + v] = acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB - 8; ++c) a[c] = a[c + 8];
+  }
+  // ---- panel: this CTA's 64 rows against the factor in shared memory ----
+  cp_async_wait<0>();
+  __syncthreads();
+  double* prow = A + (size_t)(valid ? r : k0 + NB) * ld + k0;
+  double b[NB];
+#pragma unroll
+  for (int c = 0; c < NB; c += 2) {
+    const double2 v = *reinterpret_cast<const double2*>(&Bt[i][c]);
+    b[c] = v.x; b[c + 1] = v.y;
+  }
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int k = 8 * kb;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const double x = b[u] * rdg[k + u];
+      b[u] = x;
+#pragma unroll
+      for (int v = u + 1; v < 8; ++v) b[v] -= x * L[k + v][k + u];
+    }
+    if (valid) { stg256(prow + k, b); stg256(prow + k + 4, b + 4); }
+#pragma unroll
+    for (int cg = 1; cg < 8; ++cg) {
+      if (cg < 8 - kb) {  // uniform
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const double* Lj = &L[k + 8 * cg + v][k];
+          const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+          const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+          double acc = b[8 * cg + v];
+          acc = fma(-b[0], l0.x, acc); acc = fma(-b[1], l0.y, acc); acc = fma(-b[2], l1.x, acc); acc = fma(-b[3], l1.y, acc);
+          acc = fma(-b[4], l2.x, acc); acc = fma(-b[5], l2.y, acc); acc = fma(-b[6], l3.x, acc); acc = fma(-b[7], l3.y, acc);
+          b[8 * cg + v] = acc;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NB - 8; ++c) b[c] = b[c + 8];
+  }
+}
+
 // ---- batched inverse of the 64x64 diagonal factors (off the critical path; used by the backward solve) --
 __global__ void __launch_bounds__(256) chol_inverse_kernel(const double* __restrict__ A, int ld, double* __restrict__ dinv) {
   extern __shared__ double dsm[];
@@ -614,7 +763,11 @@ constexpr int S64 = 3;  // cp.async stages (5 stages measured no faster per laun
 constexpr int kUpd64Smem = S64 * (NB + NB) * LDK2 * sizeof(double);
 template <int TM>
 __global__ void __launch_bounds__(256, 3) chol_update64_kernel(double* __restrict__ A, int ld, int kc0, int KT,
-                                                              int row_base, int col_base, int nrows_total) {
+                                                              int row_base, int col_base, int nrows_total,
+                                                              double* __restrict__ diag_copy) {
+  // diag_copy (64 x 64, row-major): second copy of the updated diagonal block A[row_base.., col_base..]. The fused
+  // diag + panel kernel that follows reads the block from there, because its CTA 0 overwrites the block in A with the
+  // factor while later-scheduled CTAs may not have read it yet.
   extern __shared__ __align__(16) double smem[];
   constexpr int A_ELEMS = TM * LDK2, STAGE = A_ELEMS + NB * LDK2;
   constexpr int MU = TM / 16, NV = 2;
@@ -681,8 +834,12 @@ __global__ void __launch_bounds__(256, 3) chol_update64_kernel(double* __restric
     const int r = r0 + wr + u * 8 + fr;
     if (r >= nrows_total) continue;
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-      *reinterpret_cast<double2*>(&A[(size_t)r * ld + c0 + wc + v * 8 + 2 * fk]) = make_double2(acc[u][v][0], acc[u][v][1]);
+    for (int v = 0; v < NV; ++v) {
+      const int c = c0 + wc + v * 8 + 2 * fk;
+      *reinterpret_cast<double2*>(&A[(size_t)r * ld + c]) = make_double2(acc[u][v][0], acc[u][v][1]);
+      if (diag_copy && r < row_base + NB && c < col_base + NB)
+        *reinterpret_cast<double2*>(&diag_copy[(r - row_base) * NB + (c - col_base)]) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
   }
 }
 
@@ -757,6 +914,7 @@ int DenseChol::Init(int n_, cudaStream_t st) {
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&x), sizeof(double) * n_pad, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ready), sizeof(int) * nblk, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rdiag), sizeof(double) * n_pad, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&dscr), sizeof(double) * 2 * NB * NB, st));
   static std::once_flag attr_once[64];
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -769,6 +927,7 @@ int DenseChol::Init(int n_, cudaStream_t st) {
     set((const void*)chol_inverse_kernel, kInvSmem);
     set((const void*)chol_panel_kernel, kPanelSmem);
     set((const void*)chol_panel3_kernel, kPanel3Smem);
+    set((const void*)chol_dp_kernel, kDpSmem);
     set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
     set((const void*)chol_update2_kernel<true, true, 128>, kUpd2Smem);
     set((const void*)chol_update64_kernel<64>, kUpd64Smem);
@@ -797,7 +956,8 @@ void DenseChol::Free(cudaStream_t st) {
   if (x) cudaFreeAsync(x, st);
   if (ready) cudaFreeAsync(ready, st);
   if (rdiag) cudaFreeAsync(rdiag, st);
-  A = dinv = x = rdiag = nullptr; ready = nullptr;
+  if (dscr) cudaFreeAsync(dscr, st);
+  A = dinv = x = rdiag = dscr = nullptr; ready = nullptr;
   if (s2) { cudaStreamDestroy(s2); s2 = nullptr; }
   if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
   for (int i = 0; i < 4; ++i) {
@@ -815,18 +975,22 @@ int DenseChol::Clear(cudaStream_t st) {
 // One outer block (two inner panels) of panel work on stream `q`.
 void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches) {
   const int k0 = ob * OB;
-  chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0, rdiag + k0, fail_flag);
-  // 64-row tiles below the diagonal block; the last tile holds only the rhs row (guarded)
-  chol_panel3_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0, rdiag + k0, rows_total);
+  // diag + panel fused: 64-row tiles below the diagonal block; the last tile holds only the rhs row (guarded)
+  if (ob == 0) {  // the first diagonal block has no producer kernel that could leave a copy: unfused pair
+    chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0, rdiag + k0, fail_flag);
+    chol_panel3_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0, rdiag + k0, rows_total);
+    *launches += 1;
+  } else {
+    chol_dp_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kDpSmem, q>>>(A, ld, k0, rdiag + k0, fail_flag, rows_total, dscr);
+  }
   {  // strip: columns k0+64 .. k0+127, rows k0+64 .. end, K = 64
     const int rows = rows_total - (k0 + NB);
     const int tr = (rows + NB - 1) / NB;
-    if (tr * 2 <= num_sms) chol_update64_kernel<32><<<(rows + 31) / 32, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total);
-    else chol_update64_kernel<64><<<tr, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total);
+    if (tr * 2 <= num_sms) chol_update64_kernel<32><<<(rows + 31) / 32, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, dscr + NB * NB);
+    else chol_update64_kernel<64><<<tr, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, dscr + NB * NB);
   }
-  chol_diag3_kernel<<<1, 64, 0, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag);
-  chol_panel3_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, rows_total);
-  *launches += 5;
+  chol_dp_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 64, kDpSmem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag, rows_total, dscr + NB * NB);
+  *launches += 3;
 }
 
 // Factor the lower triangle of A (n_pad x n_pad, row n_pad = rhs) and leave the solution in x.
@@ -850,9 +1014,9 @@ int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
       const int rows = rows_total - k0;
       const dim3 grid((rows + NB - 1) / NB, OB / NB);
       if ((int)(grid.x * grid.y) * 2 <= num_sms)  // second half of the factorisation: halve the tiles, use more SMs
-        chol_update64_kernel<32><<<dim3((rows + 31) / 32, OB / NB), 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total);
+        chol_update64_kernel<32><<<dim3((rows + 31) / 32, OB / NB), 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total, dscr);
       else
-        chol_update64_kernel<64><<<grid, 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total);
+        chol_update64_kernel<64><<<grid, 256, kUpd64Smem, s2>>>(A, ld, pb * OB, (b - pb) * OB, k0, k0, rows_total, dscr);
       *launches += 1;
     }
     PanelPair(s2, b, fail_flag, launches);

@@ -11,6 +11,7 @@ struct DenseChol {
   double* A = nullptr;     // (n_pad + 1) x ld, row-major; lower triangle = S, row n_pad = rhs
   double* dinv = nullptr;  // nblk inverted 64x64 diagonal factors
   double* rdiag = nullptr; // 1 / L_kk
+  double* dscr = nullptr;  // two 64 x 64 copies of the next diagonal blocks (input of the fused diag + panel kernel)
   double* x = nullptr;     // n_pad solution
   int* ready = nullptr;    // per-64-block flags of the backward substitution
 

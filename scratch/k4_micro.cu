@@ -222,15 +222,15 @@ int main(int argc, char** argv) {
   }
   for (int k0 : {0, 3008, 5760}) {
     const int rows = rows_total - (k0 + NB), tr = (rows + NB - 1) / NB;
-    printf("strip64 k0=%4d   %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_update64_kernel<64><<<tr, 256, kUpd64Smem>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total); }, reps), tr);
+    printf("strip64 k0=%4d   %.2f us (%d CTAs)\n", k0, 1e3 * time_ms([&] { chol_update64_kernel<64><<<tr, 256, kUpd64Smem>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, nullptr); }, reps), tr);
   }
   for (int b : {2, 24, 45}) {
     const int k0 = b * OB, rows = rows_total - k0;
     const dim3 grid((rows + NB - 1) / NB, OB / NB);
     printf("L(b) old b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update_kernel<NB, NB><<<grid, 256, STAGES * (NB + NB) * LDK * sizeof(double)>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total, 1); }, reps), grid.x * grid.y);
-    printf("L(b) new b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<64><<<grid, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total); }, reps), grid.x * grid.y);
+    printf("L(b) new b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<64><<<grid, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total, nullptr); }, reps), grid.x * grid.y);
     const dim3 g32((rows + 31) / 32, OB / NB);
-    printf("L(b) 32r b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<32><<<g32, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total); }, reps), g32.x * g32.y);
+    printf("L(b) 32r b=%2d     %.2f us (%d CTAs)\n", b, 1e3 * time_ms([&] { chol_update64_kernel<32><<<g32, 256, kUpd64Smem>>>(A, ld, (b - 2) * OB, 2 * OB, k0, k0, rows_total, nullptr); }, reps), g32.x * g32.y);
   }
   for (int ob : {0, 23, 44}) {
     const int k0 = ob * OB, nt = n_pad / OB - ob - 1;
