@@ -351,41 +351,90 @@ __global__ void __launch_bounds__(64) chol_panel3_kernel(double* __restrict__ A,
 // chol_panel3_kernel substitution against the factor it holds in shared memory. CTA 0 alone stores the factored block
 // and 1 / L_kk. Saves a dependent launch and an L11 round trip through global memory per inner panel.
 constexpr int kDpSmem = 2 * NB * LP * sizeof(double);
-__global__ void __launch_bounds__(64) chol_dp_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ rd,
-                                                     int* __restrict__ fail, int nrows_total,
-                                                     const double* __restrict__ diag_src) {
+// panel block step kb for one row held in b[] (rotated by 8 per step): in-block substitution, store, trailing update
+__device__ __forceinline__ void dp_panel_step(int kb, double (&b)[NB], const double (*L)[LP], const double* rdg, double* prow,
+                                              bool valid) {
+  const int k = 8 * kb;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const double x = b[u] * rdg[k + u];
+    b[u] = x;
+#pragma unroll
+    for (int v = u + 1; v < 8; ++v) b[v] -= x * L[k + v][k + u];
+  }
+  if (valid) { stg256(prow + k, b); stg256(prow + k + 4, b + 4); }
+#pragma unroll
+  for (int cg = 1; cg < 8; ++cg) {
+    if (cg < 8 - kb) {  // uniform
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double* Lj = &L[k + 8 * cg + v][k];
+        const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+        const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+        double acc = b[8 * cg + v];
+        acc = fma(-b[0], l0.x, acc); acc = fma(-b[1], l0.y, acc); acc = fma(-b[2], l1.x, acc); acc = fma(-b[3], l1.y, acc);
+        acc = fma(-b[4], l2.x, acc); acc = fma(-b[5], l2.y, acc); acc = fma(-b[6], l3.x, acc); acc = fma(-b[7], l3.y, acc);
+        b[8 * cg + v] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB - 8; ++c) b[c] = b[c + 8];
+}
+
+// 128 threads, two roles on separate warps (one warp per SM sub-partition): threads 0-63 factor the diagonal block (one
+// row each), threads 64-127 own one panel row each and run ONE BLOCK STEP BEHIND the factorisation - block column kb-1 of
+// L11 is complete in shared memory after the second barrier of step kb-1 - so the panel costs one extra block step of
+// latency instead of a second pass.
+__global__ void __launch_bounds__(128) chol_dp_kernel(double* __restrict__ A, int ld, int k0, double* __restrict__ rd,
+                                                      int* __restrict__ fail, int nrows_total,
+                                                      const double* __restrict__ diag_src) {
   extern __shared__ __align__(16) double psm[];
   double (*L)[LP] = reinterpret_cast<double (*)[LP]>(psm);             // L11, filled block column by block column
   double (*Bt)[LP] = reinterpret_cast<double (*)[LP]>(psm + NB * LP);  // this CTA's panel rows (prefetched)
   __shared__ __align__(32) double Dblk[8][8];
   __shared__ double rdg[NB];
-  const int i = threadIdx.x;
+  const int t = threadIdx.x;
+  const bool diag_role = t < NB;
+  const int i = t & (NB - 1);  // diagonal-block row (diag role) or panel row within the tile (panel role)
   const bool writer = blockIdx.x == 0;
   const int r = k0 + NB + blockIdx.x * PR3 + i;
   const bool valid = r < nrows_total;
-  {  // panel rows -> shared memory, in flight during the whole factorisation
+  {  // panel rows -> shared memory, in flight during the first block step
     const int r0 = k0 + NB + blockIdx.x * PR3;
 #pragma unroll
-    for (int m = 0; m < 32; ++m) {
-      const int e = i + 64 * m, row = e >> 5, piece = e & 31;
+    for (int m = 0; m < 16; ++m) {
+      const int e = t + 128 * m, row = e >> 5, piece = e & 31;
       const int gr = min(r0 + row, nrows_total - 1);
       cp_async16(&Bt[row][2 * piece], A + (size_t)gr * ld + k0 + 2 * piece);
     }
     cp_async_commit();
   }
   double* grow = A + (size_t)(k0 + i) * ld + k0;
-  double a[NB];
+  double* prow = A + (size_t)(valid ? r : k0 + NB) * ld + k0;
+  double a[NB];  // diag role: row i of the diagonal block; panel role: panel row i. Rotated by 8 per block step.
+  if (diag_role) {
 #pragma unroll
-  for (int c = 0; c < NB; c += 4) ldg256(diag_src + i * NB + c, a + c);  // the copy, not A (see chol_update64_kernel)
+    for (int c = 0; c < NB; c += 4) ldg256(diag_src + i * NB + c, a + c);  // the copy, not A (see chol_update64_kernel)
+  }
 #pragma unroll 1
   for (int kb = 0; kb < 8; ++kb) {
     const int k = 8 * kb;
-    if ((i >> 3) == kb) {
+    if (diag_role && (i >> 3) == kb) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) Dblk[i & 7][u] = a[u];
     }
     __syncthreads();
-    if (i >= k) {
+    if (!diag_role) {
+      if (kb == 1) {  // the panel rows landed before the second barrier of step 0
+#pragma unroll
+        for (int c = 0; c < NB; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(&Bt[i][c]);
+          a[c] = v.x; a[c + 1] = v.y;
+        }
+      }
+      if (kb >= 1) dp_panel_step(kb - 1, a, L, rdg, prow, valid);
+    } else if (i >= k) {
       double D[8][8], rs[8];
 #pragma unroll
       for (int v = 0; v < 8; ++v) {
@@ -433,65 +482,30 @@ __global__ void __launch_bounds__(64) chol_dp_kernel(double* __restrict__ A, int
         }
       }
     }
+    if (kb == 0) cp_async_wait<0>();
     __syncthreads();
+    if (diag_role) {
 #pragma unroll
-    for (int cg = 1; cg < 8; ++cg) {
-      if (cg < 8 - kb && k + 8 * cg <= (i | 31)) {  // uniform per warp
+      for (int cg = 1; cg < 8; ++cg) {
+        if (cg < 8 - kb && k + 8 * cg <= (i | 31)) {  // uniform per warp
 #pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const int j = k + 8 * cg + v;
-          const double* Lj = &L[j][k];
-          const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
-          const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
-          double acc = a[8 * cg + v];
-          acc = fma(-a[0], l0.x, acc); acc = fma(-a[1], l0.y, acc); acc = fma(-a[2], l1.x, acc); acc = fma(-a[3], l1.y, acc);
-          acc = fma(-a[4], l2.x, acc); acc = fma(-a[5], l2.y, acc); acc = fma(-a[6], l3.x, acc); acc = fma(-a[7], l3.y, acc);
-          if (j <= i) a[8 * cg + v] = acc;
+          for (int v = 0; v < 8; ++v) {
+            const int j = k + 8 * cg + v;
+            const double* Lj = &L[j][k];
+            const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+            const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+            double acc = a[8 * cg + v];
+            acc = fma(-a[0], l0.x, acc); acc = fma(-a[1], l0.y, acc); acc = fma(-a[2], l1.x, acc); acc = fma(-a[3], l1.y, acc);
+            acc = fma(-a[4], l2.x, acc); acc = fma(-a[5], l2.y, acc); acc = fma(-a[6], l3.x, acc); acc = fma(-a[7], l3.y, acc);
+            if (j <= i) a[8 * cg + v] = acc;
+          }
         }
       }
+#pragma unroll
+      for (int c = 0; c < NB - 8; ++c) a[c] = a[c + 8];
     }
-#pragma unroll
-    for (int c = 0; c < NB - 8; ++c) a[c] = a[c + 8];
   }
-  // ---- panel: this CTA's 64 rows against the factor in shared memory ----
-  cp_async_wait<0>();
-  __syncthreads();
-  double* prow = A + (size_t)(valid ? r : k0 + NB) * ld + k0;
-  double b[NB];
-#pragma unroll
-  for (int c = 0; c < NB; c += 2) {
-    const double2 v = *reinterpret_cast<const double2*>(&Bt[i][c]);
-    b[c] = v.x; b[c + 1] = v.y;
-  }
-#pragma unroll 1
-  for (int kb = 0; kb < 8; ++kb) {
-    const int k = 8 * kb;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const double x = b[u] * rdg[k + u];
-      b[u] = x;
-#pragma unroll
-      for (int v = u + 1; v < 8; ++v) b[v] -= x * L[k + v][k + u];
-    }
-    if (valid) { stg256(prow + k, b); stg256(prow + k + 4, b + 4); }
-#pragma unroll
-    for (int cg = 1; cg < 8; ++cg) {
-      if (cg < 8 - kb) {  // uniform
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const double* Lj = &L[k + 8 * cg + v][k];
-          const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
-          const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
-          double acc = b[8 * cg + v];
-          acc = fma(-b[0], l0.x, acc); acc = fma(-b[1], l0.y, acc); acc = fma(-b[2], l1.x, acc); acc = fma(-b[3], l1.y, acc);
-          acc = fma(-b[4], l2.x, acc); acc = fma(-b[5], l2.y, acc); acc = fma(-b[6], l3.x, acc); acc = fma(-b[7], l3.y, acc);
-          b[8 * cg + v] = acc;
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < NB - 8; ++c) b[c] = b[c + 8];
-  }
+  if (!diag_role) dp_panel_step(7, a, L, rdg, prow, valid);  // last block column: no further barrier needed, L is complete
 }
 
 // ---- batched inverse of the 64x64 diagonal factors (off the critical path; used by the backward solve) --
@@ -981,7 +995,7 @@ void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches)
     chol_panel3_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kPanel3Smem, q>>>(A, ld, k0, rdiag + k0, rows_total);
     *launches += 1;
   } else {
-    chol_dp_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 64, kDpSmem, q>>>(A, ld, k0, rdiag + k0, fail_flag, rows_total, dscr);
+    chol_dp_kernel<<<(n_pad - k0 - NB) / PR3 + 1, 128, kDpSmem, q>>>(A, ld, k0, rdiag + k0, fail_flag, rows_total, dscr);
   }
   {  // strip: columns k0+64 .. k0+127, rows k0+64 .. end, K = 64
     const int rows = rows_total - (k0 + NB);
@@ -989,7 +1003,7 @@ void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches)
     if (tr * 2 <= num_sms) chol_update64_kernel<32><<<(rows + 31) / 32, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, dscr + NB * NB);
     else chol_update64_kernel<64><<<tr, 256, kUpd64Smem, q>>>(A, ld, k0, NB, k0 + NB, k0 + NB, rows_total, dscr + NB * NB);
   }
-  chol_dp_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 64, kDpSmem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag, rows_total, dscr + NB * NB);
+  chol_dp_kernel<<<(n_pad - k0 - OB) / PR3 + 1, 128, kDpSmem, q>>>(A, ld, k0 + NB, rdiag + k0 + NB, fail_flag, rows_total, dscr + NB * NB);
   *launches += 3;
 }
 
