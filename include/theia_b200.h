@@ -322,6 +322,18 @@ int thb_seven_point_fundamental_matrix(const double* corr, int32_t count, double
                                        void* cuda_stream);
 
 /*
+ * theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157) for a batch of tracks: track t owns the rays
+ * ray_offset[t] .. ray_offset[t+1]-1 (origin and direction, 3 doubles each; directions as the caller passes them, the
+ * reference does not normalise). A = sum (I4 - d d^T) with d = (direction, 0), b = sum (I4 - d d^T) (origin, 1), 4x4
+ * Cholesky solve; ok[t] = 0 when the factorisation fails (Eigen::LLT info != Success) or the track has fewer than two
+ * rays (the reference CHECK-aborts there). points_out [num_tracks*4]. This is the per-track kernel of
+ * TrackEstimator::EstimateAllTracks (estimate_track.cc:124-321), one launch for all tracks. memory_space as in ThbBaProblem.
+ */
+int thb_triangulate_midpoint_batch(const double* ray_origins, const double* ray_directions, const int64_t* ray_offset,
+                                   int32_t num_tracks, int32_t memory_space, double* points_out, uint8_t* ok,
+                                   void* cuda_stream);
+
+/*
  * theia::FivePointRelativePose (sfm/pose/five_point_relative_pose.cc:212-293), minimal case, for `count`
  * independent 5-point samples (host pointers): x1, x2 [count*5*2]; E_out [count*10*9] row-major, in the
  * reference's solution order; num_solutions [count] (0 => the reference returns false).

@@ -35,6 +35,7 @@ def load():
         for name in ("oracle_ransac_abspose_batch", "oracle_ransac_homography_batch"):
             getattr(lib, name).argtypes = [C.POINTER(capi.ThbPairBatch), C.POINTER(capi.ThbRansacParams), C.c_void_p, C.c_void_p, C.c_int32]
         lib.oracle_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_triangulate_midpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.oracle_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.oracle_seven_point_fundamental.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         lib.oracle_poly_roots.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
@@ -121,6 +122,16 @@ def p3p(feat, world):
     R = np.zeros((count, 4, 3, 3)); t = np.zeros((count, 4, 3)); n = np.zeros(count, np.int32)
     load().oracle_p3p(_vp(feat), _vp(world), count, _vp(R), _vp(t), _vp(n))
     return R, t, n
+
+
+def triangulate_midpoint_batch(origins, directions, ray_offset):
+    """origins, directions [total,3]; ray_offset [num_tracks+1] int64 -> (points [num_tracks,4], ok [num_tracks])"""
+    origins = np.ascontiguousarray(origins, np.float64); directions = np.ascontiguousarray(directions, np.float64)
+    ray_offset = np.ascontiguousarray(ray_offset, np.int64)
+    nt = len(ray_offset) - 1
+    out = np.zeros((nt, 4)); ok = np.zeros(nt, np.uint8)
+    load().oracle_triangulate_midpoint_batch(_vp(origins), _vp(directions), _vp(ray_offset), nt, _vp(out), _vp(ok))
+    return out, ok
 
 
 def four_point_homography(corr):

@@ -659,6 +659,43 @@ int oracle_p3p(const double* feat, const double* world, int32_t count, double* R
   }
   return THB_OK;
 }
+// theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157): A = sum (I4 - d d^T), b = sum (I4 - d d^T) (o, 1),
+// Eigen::LLT<Matrix4d> solve (unblocked lower Cholesky, forward / backward substitution).
+int oracle_triangulate_midpoint_batch(const double* org, const double* dir, const int64_t* off, int32_t num_tracks, double* out,
+                                      uint8_t* ok) {
+  for (int t = 0; t < num_tracks; ++t) {
+    double A[4][4] = {}, b[4] = {};
+    for (int64_t q = off[t]; q < off[t + 1]; ++q) {
+      const double d[4] = {dir[3 * q], dir[3 * q + 1], dir[3 * q + 2], 0.0};
+      const double o[4] = {org[3 * q], org[3 * q + 1], org[3 * q + 2], 1.0};
+      for (int r = 0; r < 4; ++r) {
+        double s = 0.0;
+        for (int c = 0; c < 4; ++c) { const double T = (r == c ? 1.0 : 0.0) - d[r] * d[c]; A[r][c] += T; s += T * o[c]; }
+        b[r] += s;
+      }
+    }
+    bool good = off[t + 1] - off[t] >= 2;
+    double L[4][4] = {};
+    for (int k = 0; k < 4; ++k) {
+      double x = A[k][k];
+      for (int j = 0; j < k; ++j) x -= L[k][j] * L[k][j];
+      if (!(x > 0.0)) good = false;
+      x = std::sqrt(x);
+      L[k][k] = x;
+      for (int r = k + 1; r < 4; ++r) {
+        double v = A[r][k];
+        for (int j = 0; j < k; ++j) v -= L[r][j] * L[k][j];
+        L[r][k] = v / x;
+      }
+    }
+    double y[4], z[4];
+    for (int r = 0; r < 4; ++r) { double v = b[r]; for (int j = 0; j < r; ++j) v -= L[r][j] * y[j]; y[r] = v / L[r][r]; }
+    for (int r = 3; r >= 0; --r) { double v = y[r]; for (int j = r + 1; j < 4; ++j) v -= L[j][r] * z[j]; z[r] = v / L[r][r]; }
+    for (int r = 0; r < 4; ++r) out[4 * (size_t)t + r] = good ? z[r] : 0.0;
+    if (ok) ok[t] = good ? 1 : 0;
+  }
+  return THB_OK;
+}
 int oracle_four_point_homography(const double* corr, int32_t count, double* H_out, int32_t* ok) {
   for (int i = 0; i < count; ++i) ok[i] = oracle::FourPointH(corr + 16 * (size_t)i, H_out + 9 * (size_t)i) ? 1 : 0;
   return THB_OK;

@@ -199,6 +199,8 @@ def load_library():
         getattr(lib, name).restype = C.c_int
     lib.thb_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_p3p.restype = C.c_int
+    lib.thb_triangulate_midpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_triangulate_midpoint_batch.restype = C.c_int
     lib.thb_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_four_point_homography.restype = C.c_int
     lib.thb_seven_point_fundamental_matrix.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -792,6 +792,19 @@ PYBIND11_MODULE(_pt, m) {
     return py::make_tuple(true, info, sum.inliers);
   });
 
+  // triangulation_wrapper.h:15-17, sfm.cc:854: (success, homogeneous point). One track per call here; the batched C-ABI entry
+  // (all tracks of a reconstruction in one launch) is what a TrackEstimator replacement calls.
+  sfm.def("TriangulateMidpoint", [](const std::vector<Vec>& origins, const std::vector<Vec>& directions) {
+    if (origins.size() < 2 || origins.size() != directions.size()) throw std::invalid_argument("TriangulateMidpoint: need >= 2 rays, as many origins as directions");
+    std::vector<double> o(origins.size() * 3), d(origins.size() * 3);
+    for (size_t i = 0; i < origins.size(); ++i) { CopyVec(origins[i], &o[3 * i], 3, "ray origin"); CopyVec(directions[i], &d[3 * i], 3, "ray direction"); }
+    const int64_t off[2] = {0, (int64_t)origins.size()};
+    double X[4] = {0, 0, 0, 0};
+    uint8_t ok = 0;
+    Check(thb_triangulate_midpoint_batch(o.data(), d.data(), off, 1, THB_MEM_HOST, X, &ok, nullptr));
+    return py::make_tuple(ok != 0, MakeVec(X, 4));
+  });
+
   // pose_wrapper.cc:166-173, 210-217, 369-377 and PoseFromThreePoints
   sfm.def("FivePointRelativePose", [](const std::vector<Vec>& a, const std::vector<Vec>& b) {
     if (a.size() != 5 || b.size() != 5) throw std::runtime_error("only the minimal 5-point case is implemented");

@@ -258,3 +258,18 @@ def test_EstimateTwoViewInfo_against_the_oracle():
     pr2.focal_length.is_set = False
     with pytest.raises(RuntimeError, match="uncalibrated"):
         pt.sfm.EstimateTwoViewInfo(opts, pr1, pr2, corrs)
+
+
+def test_TriangulateMidpoint():
+    """pytests-style call of pt.sfm.TriangulateMidpoint (sfm.cc:854, triangulation_test.cc:312-335): (success, point)."""
+    X = np.array([5.0, 20.0, 23.0])
+    a = 0.15
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    t = np.array([-3.0, 1.5, 11.0])
+    origins = [np.zeros(3), -R.T @ t]
+    dirs = [X / np.linalg.norm(X), R.T @ ((R @ X + t) / np.linalg.norm(R @ X + t))]
+    ok, p = pt.sfm.TriangulateMidpoint(origins, dirs)
+    assert ok
+    np.testing.assert_allclose(p[:3] / p[3], X, rtol=1e-12)
+    with pytest.raises(ValueError):
+        pt.sfm.TriangulateMidpoint(origins[:1], dirs[:1])
