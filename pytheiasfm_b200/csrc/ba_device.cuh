@@ -33,6 +33,31 @@ __device__ __forceinline__ void ld256(const double* p, double* o) {
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
 }
 
+// Shared-memory copy of the camera table: record c keeps its 128 bytes, with its eight 16-byte pieces rotated by c.
+// The lanes of a quarter-warp read the same piece k of eight different cameras in one LDS.128 phase: unrotated they would
+// all sit on banks 4k..4k+3 (8-way conflict), rotated they collide only when two cameras agree mod 8.
+__device__ __forceinline__ unsigned cam_smem_piece(unsigned base, int c, int k) { return base + c * (CAMD * 8) + (((k + c) & 7) << 4); }
+__device__ __forceinline__ void lds128(unsigned addr, double* o) {
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+}
+__device__ __forceinline__ double lds64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// All threads of the CTA: record pieces go straight to their rotated place with cp.async (no registers, every copy in flight
+// at once - a load / store loop here waited out one L2 latency per 8 KB: 14 % of the kernel's samples in the r01 capture).
+// The caller commits, waits (cp_async_wait_all) and places a __syncthreads() before the first eval_obs.
+__device__ __forceinline__ void stage_cam_table(const double* __restrict__ camd, int nc, unsigned base) {
+  static_assert(CAMD == 16, "eight 16-byte pieces per record");
+  const double2* src = reinterpret_cast<const double2*>(camd);
+  for (int q = threadIdx.x; q < nc * 8; q += blockDim.x) cp_async16(cam_smem_piece(base, q >> 3, q & 7), src + q);
+}
+
 // y = (I + s*a [w]x + b [w]x^2) v with [w]x^2 = w w^T - th2 I; s = +1: the matrix, s = -1: its transpose.
 __device__ __forceinline__ void rot_apply(const double w[3], double a, double b, double th2, const double v[3], double y[3]) {
   const double wv = w[0] * v[0] + w[1] * v[1] + w[2] * v[2];
@@ -150,20 +175,34 @@ __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S
 //   *half_rho = 0.5*rho(|r|^2) (cost contribution)
 // cs/ps/is: column scales of the camera, point and intrinsics blocks (may be null => 1).
 // ROBUST = false compiles the loss / Corrector code out (TRIVIAL loss, the reference default).
-template <int MODEL, int PD, int NK, bool ROBUST = true>
+// CAM_SMEM (k_jacobian_sc): the camera record comes from the CTA's shared-memory copy of the table (cam_smem = its shared-space
+// address, written by stage_cam_table), and the point, its column scales and its constness flag were fetched one round ahead:
+// the point as two 16-byte pieces at pt_x and pt_x + 16 * pt_stride, scale k at pt_ps + 8 * k * pt_stride (cp.async slots of
+// this thread), the flag in pt_const_flag.
+template <int MODEL, int PD, int NK, bool ROBUST = true, bool CAM_SMEM = false>
 __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int c, int p, double2 xy, double2 si,
                                          const double* cs, const double* ps, const double* is, double r[2],
-                                         double jc[12], double jp[2 * PD], double* ji, double* half_rho) {
+                                         double jc[12], double jp[2 * PD], double* ji, double* half_rho,
+                                         unsigned cam_smem = 0, unsigned pt_x = 0, unsigned pt_ps = 0, int pt_stride = 0,
+                                         int pt_const_flag = 0) {
   constexpr int ND = 3 + NK;
   typedef Dual<ND> D;
   double cd[CAMD];
-  {
+  if (CAM_SMEM) {
+#pragma unroll
+    for (int k = 0; k < CD_SCALE / 2; ++k) lds128(cam_smem_piece(cam_smem, c, k), cd + 2 * k);  // column scales: read where used
+  } else {
     const double* rec = S.camd + (size_t)c * CAMD;
 #pragma unroll
     for (int k = 0; k < CAMD / 4; ++k) ld256(rec + 4 * k, cd + 4 * k);
   }
-  const double4 X4 = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
-  const double X[4] = {X4.x, X4.y, X4.z, X4.w};
+  double X[4];
+  if (CAM_SMEM) {
+    lds128(pt_x, X); lds128(pt_x + 16 * pt_stride, X + 2);
+  } else {
+    const double4 X4 = *reinterpret_cast<const double4*>(S.pts + (size_t)p * 4);
+    X[0] = X4.x; X[1] = X4.y; X[2] = X4.z; X[3] = X4.w;
+  }
   const double C[3] = {cd[CD_C], cd[CD_C + 1], cd[CD_C + 2]};
   const double adj[3] = {X[0] - X[3] * C[0], X[1] - X[3] * C[1], X[2] - X[3] * C[2]};
   if (adj[0] * adj[0] + adj[1] * adj[1] + adj[2] * adj[2] < 1e-8) return false;
@@ -225,7 +264,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
       for (int k = 0; k < 3; ++k) jc[6 * a + 3 + k] = GM[3 * a + k];
   }
   // d r / d X (2x4) = [AR | -AR*C], then the tangent block
-  const bool pconst = K.pt_const[p] != 0;
+  const bool pconst = CAM_SMEM ? pt_const_flag != 0 : K.pt_const[p] != 0;
   if (PD == 3) {
     double v[3], beta;
     householder4(X, v, &beta);
@@ -274,6 +313,10 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
     *half_rho = 0.5 * sq;
   }
   // correct + scale columns
+  if (CAM_SMEM && cs) {
+#pragma unroll
+    for (int k = CD_SCALE / 2; k < CAMD / 2; ++k) lds128(cam_smem_piece(cam_smem, c, k), cd + 2 * k);
+  }
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
     double j0 = jc[k], j1 = jc[6 + k];
@@ -285,7 +328,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   for (int k = 0; k < PD; ++k) {
     double j0 = jp[k], j1 = jp[PD + k];
     if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
-    const double s = js * (ps ? ps[(size_t)p * PD + k] : 1.0);
+    const double s = js * (ps ? (CAM_SMEM ? lds64(pt_ps + 8 * k * pt_stride) : ps[(size_t)p * PD + k]) : 1.0);
     jp[k] = j0 * s; jp[PD + k] = j1 * s;
   }
   if (NK > 0) {

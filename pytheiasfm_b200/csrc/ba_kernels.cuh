@@ -175,6 +175,98 @@ __global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSo
   if ((threadIdx.x & 31) == 0) atomicAdd(scal + SC_COST_X, hc_sum);
 }
 
+// K1, shared-camera form (north_star: "shared-memory staging of camera blocks"): one persistent 512-thread CTA per SM copies
+// the whole camera table (nc * 128 B, at most K1S_MAX_CAMS records) into shared memory once, then walks its observations
+// with a grid stride. The r01 ncu capture of k_jacobian shows why: a point-major warp gathers 32 different camera records
+// = 128 of the 190 L1 sectors it touches per observation, half of them L1 misses, and the warps wait on that gather
+// (long scoreboard 5.6 of 8.6 stalled warps per issue). From shared memory the gather is eight LDS.128 with no tag work.
+// Every round of an observation thread also fetches, one round ahead and with no registers (cp.async into the thread's own
+// shared-memory slots, two buffers), the point, its column scales and (one register) its constness flag; the observation
+// indices are read two rounds ahead, xy / sqrt_info one round ahead. The r01 ncu source page of k_jacobian shows two serial
+// DRAM-latency waits per observation - the point gather (613 + 212 of 3407 samples) and then the column scales ps[p] (487),
+// which the compiler sinks below the projection for lack of registers - and at 13 rounds per thread those waits, not
+// bandwidth, set the kernel's duration.
+constexpr int K1S_THREADS = 512;
+constexpr int K1S_PT_BYTES = 2 * K1S_THREADS * (32 + 8 * 4);  // two buffers of [X01 | X23 | ps0..ps3][THREADS]
+constexpr int K1S_MAX_CAMS = (227 * 1024 - K1S_PT_BYTES) / (CAMD * 8);
+template <int MODEL, int PD, int NK, bool ROBUST>
+__global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
+                                                                const double* __restrict__ ps, const double* __restrict__ is,
+                                                                double* __restrict__ r_pl, double* __restrict__ jc_pl,
+                                                                double* __restrict__ jp_pl, double* __restrict__ ji_pl,
+                                                                double* __restrict__ scal, int* __restrict__ iflag) {
+  constexpr int T = K1S_THREADS;
+  extern __shared__ __align__(128) unsigned char k1s_smem[];
+  const unsigned pt_smem = (unsigned)__cvta_generic_to_shared(k1s_smem);
+  const unsigned cam_smem = pt_smem + K1S_PT_BYTES;
+  // this thread's slots in buffer b: X01 at xs(b), X23 at xs(b) + 16 T, scale k at pss(b) + 8 k T
+  auto xs = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + threadIdx.x * 16; };
+  auto pss = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + 32 * T + threadIdx.x * 8; };
+  auto fetch_point = [&](int b, int p) {
+    const double* X = S.pts + (size_t)p * 4;
+    cp_async16(xs(b), X); cp_async16(xs(b) + 16 * T, X + 2);
+    if (ps) {
+#pragma unroll
+      for (int k = 0; k < PD; ++k) cp_async8(pss(b) + 8 * k * T, ps + (size_t)p * PD + k);
+    }
+  };
+  // CTA b walks the contiguous range [b * per, (b + 1) * per) in rounds of T observations: the last, partial round is then
+  // spread over all SMs (a few warps each) instead of being a full extra round on some of them.
+  constexpr int stride = T;
+  const int per = ((K.no + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
+  const int end = min(K.no, ((int)blockIdx.x + 1) * per);
+  int i = blockIdx.x * per + threadIdx.x;
+  int c_n = 0, p_n = 0, c_nn = 0, p_nn = 0, pc_n = 0;
+  double2 xy_n = make_double2(0.0, 0.0), si_n = make_double2(0.0, 0.0);
+  if (i < end) { c_n = __ldcs(O.cam + i); p_n = __ldcs(O.pt + i); xy_n = __ldcs(O.xy + i); si_n = __ldcs(O.si + i); }
+  if (i + stride < end) { c_nn = __ldcs(O.cam + i + stride); p_nn = __ldcs(O.pt + i + stride); }
+  stage_cam_table(S.camd, K.nc, cam_smem);
+  if (i < end) { fetch_point(0, p_n); pc_n = K.pt_const[p_n]; }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncthreads();
+  double hc_sum = 0.0;
+  int buf = 0;
+#pragma unroll 1
+  for (; i < end; i += stride, buf ^= 1) {
+    const int c = c_n, p = p_n, pc = pc_n;
+    const double2 xy = xy_n, si = si_n;
+    const int in = i + stride;
+    cp_async_wait_all();  // this round's point, fetched one round ago
+    if (in < end) {
+      c_n = c_nn; p_n = p_nn;
+      fetch_point(buf ^ 1, p_n); pc_n = K.pt_const[p_n];
+      xy_n = __ldcs(O.xy + in); si_n = __ldcs(O.si + in);
+      if (in + stride < end) { c_nn = __ldcs(O.cam + in + stride); p_nn = __ldcs(O.pt + in + stride); }
+    }
+    cp_async_commit();
+    double hc = 0.0;
+    double r[2], jc[12], jp[2 * PD], ji[NK > 0 ? 2 * NK : 1];
+    const bool ok = eval_obs<MODEL, PD, NK, ROBUST, true>(K, S, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc, cam_smem, xs(buf), pss(buf), T, pc);
+    if (!ok) {
+      atomicOr(iflag + FL_EVAL_X, 1);
+      hc = 0.0; r[0] = r[1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) jc[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2 * PD; ++k) jp[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 2 * NK; ++k) ji[k] = 0.0;
+    }
+    hc_sum += hc;
+    const size_t no = K.no;
+    __stcs(r_pl + i, r[0]); __stcs(r_pl + no + i, r[1]);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) __stcs(jc_pl + k * no + i, jc[k]);
+#pragma unroll
+    for (int k = 0; k < 2 * PD; ++k) __stcs(jp_pl + k * no + i, jp[k]);
+#pragma unroll
+    for (int k = 0; k < 2 * NK; ++k) __stcs(ji_pl + k * no + i, ji[k]);
+  }
+  hc_sum = warp_sum(hc_sum);
+  if ((threadIdx.x & 31) == 0) atomicAdd(scal + SC_COST_X, hc_sum);
+}
+
 // Cost only (candidate evaluation): 0.5 * sum rho(|r|^2).
 template <int MODEL>
 __global__ void __launch_bounds__(256) k_cost(BaConst K, BaState S, ObsSoA O, double* __restrict__ scal, int slot,

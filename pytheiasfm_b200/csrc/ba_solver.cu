@@ -205,16 +205,38 @@ void PreferL1Once(Kern kern) {
   static bool done = false;
   if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); done = true; }
 }
+int SmCount() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+// The shared-camera K1 (k_jacobian_sc) pays one copy of the camera table per SM: used when the table fits in shared memory and
+// every SM gets at least eight rounds of observations. THB_K1_MODE=gather forces the L1-gather kernel (A/B timing),
+// THB_K1_MODE=shared the shared-camera kernel whenever the table fits (parity tests at small sizes).
+bool UseSharedCameraK1(const ThbBaSession* s) {
+  if (s->nc > K1S_MAX_CAMS) return false;
+  const char* e = getenv("THB_K1_MODE");
+  if (e && !strcmp(e, "gather")) return false;
+  if (e && !strcmp(e, "shared")) return true;
+  return (long long)s->no >= 8LL * 512 * SmCount();
+}
+template <int MODEL, int PD, int NK, bool ROBUST>
+void LaunchJacobianKernel(ThbBaSession* s, const double* cs, const double* ps, const double* is, double* ji) {
+  if (UseSharedCameraK1(s)) {
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(k_jacobian_sc<MODEL, PD, NK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+    k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
+        s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
+  } else {
+    PreferL1Once(k_jacobian<MODEL, PD, NK, ROBUST>);
+    k_jacobian<MODEL, PD, NK, ROBUST><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal,
+                                                                                             s->d_flag);
+  }
+}
 template <int MODEL, int PD>
 void LaunchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
-  const int grid = cdiv(s->no, 128 * K1_OBS_PER_THREAD);
-  if (s->opt.loss_function_type == THB_LOSS_TRIVIAL) {
-    PreferL1Once(k_jacobian<MODEL, PD, 0, false>);
-    k_jacobian<MODEL, PD, 0, false><<<grid, 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_scal, s->d_flag);
-  } else {
-    PreferL1Once(k_jacobian<MODEL, PD, 0, true>);
-    k_jacobian<MODEL, PD, 0, true><<<grid, 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, nullptr, s->d_r, s->d_jc, s->d_jp, nullptr, s->d_scal, s->d_flag);
-  }
+  if (s->opt.loss_function_type == THB_LOSS_TRIVIAL) LaunchJacobianKernel<MODEL, PD, 0, false>(s, cs, ps, nullptr, nullptr);
+  else LaunchJacobianKernel<MODEL, PD, 0, true>(s, cs, ps, nullptr, nullptr);
 }
 template <int PD>
 void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
@@ -230,8 +252,7 @@ void DispatchJacobian(ThbBaSession* s, const double* cs, const double* ps) {
 }
 template <int PD>
 void LaunchJacobianIntr(ThbBaSession* s, const double* cs, const double* ps) {
-  k_jacobian<-1, PD, NI, true><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, cs + 6 * s->nc, s->d_r, s->d_jc, s->d_jp,
-                                                             s->d_ji, s->d_scal, s->d_flag);
+  LaunchJacobianKernel<-1, PD, NI, true>(s, cs, ps, cs + 6 * s->nc, s->d_ji);
 }
 void RunJacobian(ThbBaSession* s, const double* cs, const double* ps) {
   if (s->nvg > 0) { if (s->PD == 3) LaunchJacobianIntr<3>(s, cs, ps); else LaunchJacobianIntr<4>(s, cs, ps); }

@@ -1,0 +1,30 @@
+"""A/B timing of the two K1 kernels on C2 (thb_ba_time_jacobian: CUDA events on the launch stream, L2 read-flush between
+launches). Usage: python scratch/k1_ab.py [mode ...]  (spec = gather | shared[:threads[:prefetch]])"""
+import ctypes as C
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from pytheiasfm_b200 import capi, synthetic
+
+lib = capi.load_library()
+prob, _ = synthetic.config_c2(scale=1.0)
+dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
+pd = prob.struct()
+pd.memory_space = capi.THB_MEM_DEVICE
+for k, v in dev.items():
+    setattr(pd, k, None if v is None else v.data_ptr())
+sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+for spec in (sys.argv[1:] or ["gather", "shared", "gather", "shared"]):
+    mode, threads, pf = (spec.split(":") + ["512", "1"])[:3]
+    os.environ["THB_K1_MODE"] = mode; os.environ["THB_K1_THREADS"] = threads; os.environ["THB_K1_PF"] = pf
+    sess = C.c_void_p()
+    o = capi.default_options(lib)
+    o.use_inner_iterations = 0
+    capi.check(lib.thb_ba_create(C.byref(pd), C.byref(o), sptr, C.byref(sess)))
+    ms = C.c_double(0.0)
+    for rep in range(2):
+        capi.check(lib.thb_ba_time_jacobian(sess, 20, 1, C.byref(ms)))
+    capi.check(lib.thb_ba_finish(sess, None))
+    print("K1 %-14s %.2f us  %.0f GB/s (203.3 MB algorithmic)" % (spec, ms.value * 1e3, 203.304e6 / (ms.value * 1e-3) / 1e9), flush=True)

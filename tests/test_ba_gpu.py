@@ -78,6 +78,40 @@ def _compare_solves(lib, oracle, prob, opts, rel=1e-6, check_log=True):
     return g, o, pg, po
 
 
+@pytest.mark.parametrize("model", ALL_MODELS)
+@pytest.mark.parametrize("homogeneous", [True, False])
+def test_k1_shared_camera_kernel_matches_gather_kernel(lib, oracle, monkeypatch, model, homogeneous):
+    """The two K1 kernels (camera records gathered through L1 / read from the CTA's shared-memory copy of the table) run
+    the same arithmetic: the same iteration logs and refined parameters, and parity with the oracle."""
+    prob, _ = synthetic.make_ba_problem(12, 600, 5, models=(model,), seed=70 + model)
+    opts = capi.default_options(lib)
+    opts.use_homogeneous_point_parametrization = int(homogeneous)
+    opts.loss_function_type = capi.LOSS_HUBER if model % 2 else capi.LOSS_TRIVIAL
+    opts.robust_loss_width = 2.0
+    runs = {}
+    for mode in ("gather", "shared"):
+        monkeypatch.setenv("THB_K1_MODE", mode)
+        pg = prob.copy()
+        runs[mode] = (gpu_solve(lib, pg, opts), pg)
+    a, b = runs["gather"], runs["shared"]
+    # per-observation values are identical; the cost is summed by one atomic per warp, in arrival order
+    np.testing.assert_allclose(a[0]["iter_cost"], b[0]["iter_cost"], rtol=1e-13)
+    assert a[0]["num_iterations"] == b[0]["num_iterations"]
+    # (the two instantiations need not contract the same multiply-adds, and the Euclidean 4-vector points have a gauge
+    # direction along which last-bit differences drift)
+    for k in ("cam_ext", "pts", "intr"):
+        np.testing.assert_allclose(a[1].a[k], b[1].a[k], rtol=1e-6, atol=1e-9)
+    _compare_solves(lib, oracle, prob, opts)     # still under THB_K1_MODE=shared
+
+
+def test_k1_shared_camera_kernel_with_refined_intrinsics(lib, oracle, monkeypatch):
+    monkeypatch.setenv("THB_K1_MODE", "shared")
+    prob, gt = synthetic.config_c3(scale=0.06)
+    _perturb_intrinsics(prob, 0.02)
+    g, oo, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
+
+
 def test_c1_full_ba_matches_oracle(lib, oracle):
     """BASELINE configs[0]: 10 cams / 500 pts / 2k obs, defaults (inner iterations off)."""
     prob, _ = synthetic.config_c1()
