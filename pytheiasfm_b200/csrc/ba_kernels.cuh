@@ -188,7 +188,9 @@ __global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSo
 // bandwidth, set the kernel's duration.
 constexpr int K1S_THREADS = 512;
 constexpr int K1S_PT_BYTES = 2 * K1S_THREADS * (32 + 8 * 4);  // two buffers of [X01 | X23 | ps0..ps3][THREADS]
-constexpr int K1S_MAX_CAMS = (227 * 1024 - K1S_PT_BYTES) / (CAMD * 8);
+constexpr int K1S_INTR_GROUPS = 16;                            // intrinsics blocks copied to shared memory when ng <= this
+constexpr int K1S_INTR_BYTES = K1S_INTR_GROUPS * KS * 8;
+constexpr int K1S_MAX_CAMS = (227 * 1024 - K1S_PT_BYTES - K1S_INTR_BYTES) / (CAMD * 8);
 template <int MODEL, int PD, int NK, bool ROBUST>
 __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaState S, ObsSoA O, const double* __restrict__ cs,
                                                                 const double* __restrict__ ps, const double* __restrict__ is,
@@ -198,7 +200,14 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaSta
   constexpr int T = K1S_THREADS;
   extern __shared__ __align__(128) unsigned char k1s_smem[];
   const unsigned pt_smem = (unsigned)__cvta_generic_to_shared(k1s_smem);
-  const unsigned cam_smem = pt_smem + K1S_PT_BYTES;
+  const unsigned cam_smem = pt_smem + K1S_PT_BYTES + K1S_INTR_BYTES;
+  // the intrinsics blocks every observation reads (same address for the whole warp, but still an L1 round trip each)
+  double* intr_sm = reinterpret_cast<double*>(k1s_smem + K1S_PT_BYTES);
+  BaState Ss = S;
+  if (K.ng <= K1S_INTR_GROUPS) {
+    for (int q = threadIdx.x; q < K.ng * KS; q += T) intr_sm[q] = S.intr[q];
+    Ss.intr = intr_sm;
+  }
   // this thread's slots in buffer b: X01 at xs(b), X23 at xs(b) + 16 T, scale k at pss(b) + 8 k T
   auto xs = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + threadIdx.x * 16; };
   auto pss = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + 32 * T + threadIdx.x * 8; };
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaSta
     cp_async_commit();
     double hc = 0.0;
     double r[2], jc[12], jp[2 * PD], ji[NK > 0 ? 2 * NK : 1];
-    const bool ok = eval_obs<MODEL, PD, NK, ROBUST, true>(K, S, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc, cam_smem, xs(buf), pss(buf), T, pc);
+    const bool ok = eval_obs<MODEL, PD, NK, ROBUST, true>(K, Ss, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc, cam_smem, xs(buf), pss(buf), T, pc);
     if (!ok) {
       atomicOr(iflag + FL_EVAL_X, 1);
       hc = 0.0; r[0] = r[1] = 0.0;

@@ -225,7 +225,7 @@ void LaunchJacobianKernel(ThbBaSession* s, const double* cs, const double* ps, c
   if (UseSharedCameraK1(s)) {
     static bool done = false;
     if (!done) { cudaFuncSetAttribute(k_jacobian_sc<MODEL, PD, NK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-    k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
+    k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + K1S_INTR_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
         s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
   } else {
     PreferL1Once(k_jacobian<MODEL, PD, NK, ROBUST>);
