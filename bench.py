@@ -453,7 +453,7 @@ def main():
                     "note": "thb_ba_solve calls on pinned host buffers: H2D + device-side setup + iterations + D2H of the refined "
                             "parameters; the per-iteration scalar read-back (96 B) is in d2h"},
             "gpu_launches": launches_timed,
-            "roofline": {"bound": "hbm", "kernel": "k_jacobian (K1, materialised tangent-space Jacobian planes)",
+            "roofline": {"bound": "hbm", "kernel": "k_jacobian_sc (K1, shared-memory camera table, materialised tangent-space Jacobian planes)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_from_profiles(), "peak_source": peak_src + ", burst",
                          "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},

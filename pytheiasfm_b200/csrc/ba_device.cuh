@@ -40,13 +40,7 @@ __device__ __forceinline__ unsigned cam_smem_piece(unsigned base, int c, int k) 
 __device__ __forceinline__ void lds128(unsigned addr, double* o) {
   asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
 }
-__device__ __forceinline__ double lds64(unsigned addr) {
-  double v;
-  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-  return v;
-}
 __device__ __forceinline__ void cp_async16(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
-__device__ __forceinline__ void cp_async8(unsigned dst, const void* src) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // All threads of the CTA: record pieces go straight to their rotated place with cp.async (no registers, every copy in flight
@@ -177,14 +171,14 @@ __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S
 // ROBUST = false compiles the loss / Corrector code out (TRIVIAL loss, the reference default).
 // CAM_SMEM (k_jacobian_sc): the camera record comes from the CTA's shared-memory copy of the table (cam_smem = its shared-space
 // address, written by stage_cam_table), and the point, its column scales and its constness flag were fetched one round ahead:
-// the point as two 16-byte pieces at pt_x and pt_x + 16 * pt_stride, scale k at pt_ps + 8 * k * pt_stride (cp.async slots of
-// this thread), the flag in pt_const_flag.
+// the point as two 16-byte pieces at pt_x and pt_x + 16 * pt_stride (cp.async slots of this thread), the scales in
+// pt_scale[PD] (registers), the flag in pt_const_flag.
 template <int MODEL, int PD, int NK, bool ROBUST = true, bool CAM_SMEM = false>
 __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int c, int p, double2 xy, double2 si,
                                          const double* cs, const double* ps, const double* is, double r[2],
                                          double jc[12], double jp[2 * PD], double* ji, double* half_rho,
-                                         unsigned cam_smem = 0, unsigned pt_x = 0, unsigned pt_ps = 0, int pt_stride = 0,
-                                         int pt_const_flag = 0) {
+                                         unsigned cam_smem = 0, unsigned pt_x = 0, int pt_stride = 0, int pt_const_flag = 0,
+                                         const double* pt_scale = nullptr) {
   constexpr int ND = 3 + NK;
   typedef Dual<ND> D;
   double cd[CAMD];
@@ -328,7 +322,7 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
   for (int k = 0; k < PD; ++k) {
     double j0 = jp[k], j1 = jp[PD + k];
     if (asn != 0.0) { const double rtj = j0 * r[0] + j1 * r[1]; j0 -= asn * r[0] * rtj; j1 -= asn * r[1] * rtj; }
-    const double s = js * (ps ? (CAM_SMEM ? lds64(pt_ps + 8 * k * pt_stride) : ps[(size_t)p * PD + k]) : 1.0);
+    const double s = js * (ps ? (CAM_SMEM ? pt_scale[k] : ps[(size_t)p * PD + k]) : 1.0);
     jp[k] = j0 * s; jp[PD + k] = j1 * s;
   }
   if (NK > 0) {

@@ -180,14 +180,15 @@ __global__ void __launch_bounds__(128, 4) k_jacobian(BaConst K, BaState S, ObsSo
 // with a grid stride. The r01 ncu capture of k_jacobian shows why: a point-major warp gathers 32 different camera records
 // = 128 of the 190 L1 sectors it touches per observation, half of them L1 misses, and the warps wait on that gather
 // (long scoreboard 5.6 of 8.6 stalled warps per issue). From shared memory the gather is eight LDS.128 with no tag work.
-// Every round of an observation thread also fetches, one round ahead and with no registers (cp.async into the thread's own
-// shared-memory slots, two buffers), the point, its column scales and (one register) its constness flag; the observation
-// indices are read two rounds ahead, xy / sqrt_info one round ahead. The r01 ncu source page of k_jacobian shows two serial
-// DRAM-latency waits per observation - the point gather (613 + 212 of 3407 samples) and then the column scales ps[p] (487),
-// which the compiler sinks below the projection for lack of registers - and at 13 rounds per thread those waits, not
-// bandwidth, set the kernel's duration.
+// Every round of an observation thread also fetches, one round ahead, the point (cp.async into the thread's own shared-memory
+// slots, two buffers: no registers), its column scales (PD registers: measured - as cp.async pieces the 8-byte gathers cost
+// 22 LSU wavefronts per instruction and 5 us, with the point in registers as well the kernel spills) and its constness flag;
+// the observation indices are read two rounds ahead, xy / sqrt_info one round ahead. The r01 ncu source page of k_jacobian
+// shows two serial DRAM-latency waits per observation - the point gather (613 + 212 of 3407 samples) and then the column
+// scales ps[p] (487), which the compiler sinks below the projection for lack of registers - and at 13 rounds per thread
+// those waits, not bandwidth, set the kernel's duration.
 constexpr int K1S_THREADS = 512;
-constexpr int K1S_PT_BYTES = 2 * K1S_THREADS * (32 + 8 * 4);  // two buffers of [X01 | X23 | ps0..ps3][THREADS]
+constexpr int K1S_PT_BYTES = 2 * K1S_THREADS * 32;             // two buffers of [X01 | X23][THREADS]
 constexpr int K1S_INTR_GROUPS = 16;                            // intrinsics blocks copied to shared memory when ng <= this
 constexpr int K1S_INTR_BYTES = K1S_INTR_GROUPS * KS * 8;
 constexpr int K1S_MAX_CAMS = (227 * 1024 - K1S_PT_BYTES - K1S_INTR_BYTES) / (CAMD * 8);
@@ -208,16 +209,16 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaSta
     for (int q = threadIdx.x; q < K.ng * KS; q += T) intr_sm[q] = S.intr[q];
     Ss.intr = intr_sm;
   }
-  // this thread's slots in buffer b: X01 at xs(b), X23 at xs(b) + 16 T, scale k at pss(b) + 8 k T
+  // this thread's point slots in buffer b: X01 at xs(b), X23 at xs(b) + 16 T
   auto xs = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + threadIdx.x * 16; };
-  auto pss = [&](int b) { return pt_smem + b * (K1S_PT_BYTES / 2) + 32 * T + threadIdx.x * 8; };
+  double sc_n[PD];
+  int c_n = 0, p_n = 0, c_nn = 0, p_nn = 0, pc_n = 0;
   auto fetch_point = [&](int b, int p) {
     const double* X = S.pts + (size_t)p * 4;
     cp_async16(xs(b), X); cp_async16(xs(b) + 16 * T, X + 2);
-    if (ps) {
 #pragma unroll
-      for (int k = 0; k < PD; ++k) cp_async8(pss(b) + 8 * k * T, ps + (size_t)p * PD + k);
-    }
+    for (int k = 0; k < PD; ++k) sc_n[k] = ps ? ps[(size_t)p * PD + k] : 1.0;
+    pc_n = K.pt_const[p];
   };
   // CTA b walks the contiguous range [b * per, (b + 1) * per) in rounds of T observations: the last, partial round is then
   // spread over all SMs (a few warps each) instead of being a full extra round on some of them.
@@ -225,12 +226,13 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaSta
   const int per = ((K.no + (int)gridDim.x - 1) / (int)gridDim.x + 31) & ~31;
   const int end = min(K.no, ((int)blockIdx.x + 1) * per);
   int i = blockIdx.x * per + threadIdx.x;
-  int c_n = 0, p_n = 0, c_nn = 0, p_nn = 0, pc_n = 0;
   double2 xy_n = make_double2(0.0, 0.0), si_n = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int k = 0; k < PD; ++k) sc_n[k] = 1.0;
   if (i < end) { c_n = __ldcs(O.cam + i); p_n = __ldcs(O.pt + i); xy_n = __ldcs(O.xy + i); si_n = __ldcs(O.si + i); }
   if (i + stride < end) { c_nn = __ldcs(O.cam + i + stride); p_nn = __ldcs(O.pt + i + stride); }
   stage_cam_table(S.camd, K.nc, cam_smem);
-  if (i < end) { fetch_point(0, p_n); pc_n = K.pt_const[p_n]; }
+  if (i < end) fetch_point(0, p_n);
   cp_async_commit();
   cp_async_wait_all();
   __syncthreads();
@@ -241,17 +243,20 @@ __global__ void __launch_bounds__(K1S_THREADS, 1) k_jacobian_sc(BaConst K, BaSta
     const int c = c_n, p = p_n, pc = pc_n;
     const double2 xy = xy_n, si = si_n;
     const int in = i + stride;
+    double sc[PD];
+#pragma unroll
+    for (int k = 0; k < PD; ++k) sc[k] = sc_n[k];
     cp_async_wait_all();  // this round's point, fetched one round ago
     if (in < end) {
       c_n = c_nn; p_n = p_nn;
-      fetch_point(buf ^ 1, p_n); pc_n = K.pt_const[p_n];
+      fetch_point(buf ^ 1, p_n);
       xy_n = __ldcs(O.xy + in); si_n = __ldcs(O.si + in);
       if (in + stride < end) { c_nn = __ldcs(O.cam + in + stride); p_nn = __ldcs(O.pt + in + stride); }
     }
     cp_async_commit();
     double hc = 0.0;
     double r[2], jc[12], jp[2 * PD], ji[NK > 0 ? 2 * NK : 1];
-    const bool ok = eval_obs<MODEL, PD, NK, ROBUST, true>(K, Ss, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc, cam_smem, xs(buf), pss(buf), T, pc);
+    const bool ok = eval_obs<MODEL, PD, NK, ROBUST, true>(K, Ss, c, p, xy, si, cs, ps, is, r, jc, jp, ji, &hc, cam_smem, xs(buf), T, pc, sc);
     if (!ok) {
       atomicOr(iflag + FL_EVAL_X, 1);
       hc = 0.0; r[0] = r[1] = 0.0;

@@ -222,16 +222,18 @@ bool UseSharedCameraK1(const ThbBaSession* s) {
 }
 template <int MODEL, int PD, int NK, bool ROBUST>
 void LaunchJacobianKernel(ThbBaSession* s, const double* cs, const double* ps, const double* is, double* ji) {
-  if (UseSharedCameraK1(s)) {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(k_jacobian_sc<MODEL, PD, NK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
-    k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + K1S_INTR_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
-        s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
-  } else {
-    PreferL1Once(k_jacobian<MODEL, PD, NK, ROBUST>);
-    k_jacobian<MODEL, PD, NK, ROBUST><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal,
-                                                                                             s->d_flag);
+  // refined intrinsics (NK > 0) stay on the gather kernel: the shared-camera instantiation spills ~400 bytes there
+  if constexpr (NK == 0) {
+    if (UseSharedCameraK1(s)) {
+      static bool done = false;
+      if (!done) { cudaFuncSetAttribute(k_jacobian_sc<MODEL, PD, NK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+      k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + K1S_INTR_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
+          s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
+      return;
+    }
   }
+  PreferL1Once(k_jacobian<MODEL, PD, NK, ROBUST>);
+  k_jacobian<MODEL, PD, NK, ROBUST><<<cdiv(s->no, 128 * K1_OBS_PER_THREAD), 128, 0, s->st>>>(s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
 }
 template <int MODEL, int PD>
 void LaunchJacobian(ThbBaSession* s, const double* cs, const double* ps) {

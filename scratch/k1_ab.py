@@ -1,5 +1,5 @@
 """A/B timing of the two K1 kernels on C2 (thb_ba_time_jacobian: CUDA events on the launch stream, L2 read-flush between
-launches). Usage: python scratch/k1_ab.py [mode ...]  (spec = gather | shared[:threads[:prefetch]])"""
+launches). Usage: python scratch/k1_ab.py [mode ...]  (spec = gather | shared)"""
 import ctypes as C
 import os
 import sys
@@ -17,8 +17,8 @@ for k, v in dev.items():
     setattr(pd, k, None if v is None else v.data_ptr())
 sptr = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 for spec in (sys.argv[1:] or ["gather", "shared", "gather", "shared"]):
-    mode, threads, pf = (spec.split(":") + ["512", "1"])[:3]
-    os.environ["THB_K1_MODE"] = mode; os.environ["THB_K1_THREADS"] = threads; os.environ["THB_K1_PF"] = pf
+    mode = spec
+    os.environ["THB_K1_MODE"] = mode
     sess = C.c_void_p()
     o = capi.default_options(lib)
     o.use_inner_iterations = 0

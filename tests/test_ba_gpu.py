@@ -104,14 +104,6 @@ def test_k1_shared_camera_kernel_matches_gather_kernel(lib, oracle, monkeypatch,
     _compare_solves(lib, oracle, prob, opts)     # still under THB_K1_MODE=shared
 
 
-def test_k1_shared_camera_kernel_with_refined_intrinsics(lib, oracle, monkeypatch):
-    monkeypatch.setenv("THB_K1_MODE", "shared")
-    prob, gt = synthetic.config_c3(scale=0.06)
-    _perturb_intrinsics(prob, 0.02)
-    g, oo, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
-    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
-
-
 def test_c1_full_ba_matches_oracle(lib, oracle):
     """BASELINE configs[0]: 10 cams / 500 pts / 2k obs, defaults (inner iterations off)."""
     prob, _ = synthetic.config_c1()
