@@ -321,6 +321,25 @@ int thb_four_point_homography(const double* corr, int32_t count, double* H_out, 
 int thb_seven_point_fundamental_matrix(const double* corr, int32_t count, double* F_out, int32_t* num_solutions,
                                        void* cuda_stream);
 
+/* Per-track record of thb_ba_tracks_batch: what BundleAdjustTrack's BundleAdjustmentSummary carries for one track. */
+typedef struct ThbTrackBaResult {
+  double initial_cost;
+  double final_cost;
+  int32_t num_iterations;   /* -1: track not optimised (constant or without observations) */
+  int32_t termination_type; /* THB_TERM_*; THB_TERM_FAILURE leaves the point untouched (summary.success == false) */
+} ThbTrackBaResult;
+
+/*
+ * theia::BundleAdjustTrack (sfm/bundle_adjustment/bundle_adjustment.cc:261-285) for EVERY non-constant point of the problem
+ * in one launch: each track is its own trust-region problem over its 3 (homogeneous parametrisation) or 4 coordinates with
+ * all cameras and intrinsics constant (bundle_adjuster.cc:176-221) - what TrackEstimator::EstimateTrack does once per track
+ * from a thread pool (sfm/estimate_track.cc:286-290). problem->cam_const / intr_const are ignored (everything but the
+ * points is constant), problem->pt_const selects the tracks, options as for thb_ba_solve (use_inner_iterations must be 0,
+ * as BundleAdjustTrack forces, bundle_adjustment.cc:267). Refines problem->pts in place; results [num_points] may be NULL.
+ * Host memory only for now (THB_E_UNSUPPORTED for THB_MEM_DEVICE).
+ */
+int thb_ba_tracks_batch(const ThbBaProblem* problem, const ThbBaOptions* options, ThbTrackBaResult* results, void* cuda_stream);
+
 /*
  * theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157) for a batch of tracks: track t owns the rays
  * ray_offset[t] .. ray_offset[t+1]-1 (origin and direction, 3 doubles each; directions as the caller passes them, the

@@ -118,6 +118,8 @@ class ThbRelPoseResult(C.Structure):
     ]
 
 
+TRACK_BA_DTYPE = np.dtype([("initial_cost", np.float64), ("final_cost", np.float64), ("num_iterations", np.int32),
+                           ("termination_type", np.int32)])
 RELPOSE_DTYPE = np.dtype([("success", np.int32), ("num_inliers", np.int32), ("num_iterations", np.int32),
                           ("num_input_data_points", np.int32), ("confidence", np.float64), ("best_cost", np.float64),
                           ("essential_matrix", np.float64, (3, 3)), ("rotation", np.float64, (3, 3)),
@@ -199,6 +201,8 @@ def load_library():
         getattr(lib, name).restype = C.c_int
     lib.thb_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_p3p.restype = C.c_int
+    lib.thb_ba_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.POINTER(ThbBaOptions), C.c_void_p, C.c_void_p]
+    lib.thb_ba_tracks_batch.restype = C.c_int
     lib.thb_triangulate_midpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_triangulate_midpoint_batch.restype = C.c_int
     lib.thb_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

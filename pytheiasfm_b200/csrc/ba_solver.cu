@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "track_ba.cuh"
 #include "ba_setup.cuh"
 #include "dense_chol.cuh"
 
@@ -938,6 +939,89 @@ int thb_dense_spd_time(int32_t n, int32_t repeats, double* avg_ms, double* rel_r
   if (h_fail) THB_FAIL(THB_E_NUMERICAL, "synthetic matrix not positive definite");
   *avg_ms = total / repeats;
   if (rel_residual) *rel_residual = h_res[1] > 0.0 ? h_res[0] / h_res[1] : 0.0;
+  return THB_OK;
+}
+
+int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBaResult* results, void* cuda_stream) {
+  if (!P || !O) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem or options");
+  if (O->use_inner_iterations) THB_FAIL(THB_E_UNSUPPORTED, "BundleAdjustTrack runs without inner iterations (bundle_adjustment.cc:267)");
+  if (P->memory_space != THB_MEM_HOST) THB_FAIL(THB_E_UNSUPPORTED, "thb_ba_tracks_batch takes host buffers");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  const int nc = P->num_cameras, ng = P->num_groups, np = P->num_points, no = P->num_observations;
+  if (nc < 0 || ng < 0 || np < 0 || no < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "negative size");
+  if (np == 0) return THB_OK;
+  if (!P->pts || (no > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->obs_cam || !P->obs_pt || !P->obs_xy)))
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
+  for (int g = 0; g < ng; ++g) if (num_intrinsics(P->intr_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
+  for (int c = 0; c < nc; ++c) if (P->cam_group[c] < 0 || P->cam_group[c] >= ng) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
+  // observations grouped by track (stable counting sort), as AddTrack walks track->ViewIds()
+  std::vector<int> start(np + 1, 0), h_cam(no);
+  std::vector<double> h_xy((size_t)no * 2), h_si((size_t)no * 2);
+  for (int i = 0; i < no; ++i) {
+    if (P->obs_cam[i] < 0 || P->obs_cam[i] >= nc || P->obs_pt[i] < 0 || P->obs_pt[i] >= np) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
+    ++start[P->obs_pt[i] + 1];
+  }
+  for (int p = 0; p < np; ++p) start[p + 1] += start[p];
+  {
+    std::vector<int> cursor(start.begin(), start.end() - 1);
+    for (int i = 0; i < no; ++i) {
+      const int q = cursor[P->obs_pt[i]]++;
+      h_cam[q] = P->obs_cam[i];
+      h_xy[2 * (size_t)q] = P->obs_xy[2 * (size_t)i]; h_xy[2 * (size_t)q + 1] = P->obs_xy[2 * (size_t)i + 1];
+      h_si[2 * (size_t)q] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i] : 1.0;
+      h_si[2 * (size_t)q + 1] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i + 1] : 1.0;
+    }
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int PD = O->use_homogeneous_point_parametrization ? 3 : 4;
+  DevBufs B;
+  BaState X{B.get<double>((size_t)nc * 6), B.get<double>((size_t)nc * CAMD), B.get<double>((size_t)ng * KS), B.get<double>((size_t)np * 4)};
+  BaState Xc = X;
+  Xc.pts = B.get<double>((size_t)np * 4);
+  int* d_group = B.get<int>(nc); int* d_model = B.get<int>(ng); int* d_start = B.get<int>(np + 1); int* d_oc = B.get<int>(no);
+  uint8_t* d_cc = B.get<uint8_t>(nc); uint8_t* d_pc = B.get<uint8_t>(np);
+  double2* d_xy = B.get<double2>(no); double2* d_si = B.get<double2>(no);
+  double* d_ps = B.get<double>((size_t)np * PD);
+  ThbTrackBaResult* d_res = B.get<ThbTrackBaResult>(np);
+  if (!X.cam || !X.camd || !X.intr || !X.pts || !Xc.pts || !d_group || !d_model || !d_start || !d_oc || !d_cc || !d_pc || !d_xy || !d_si || !d_ps || !d_res)
+    THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * np * 4, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, P->cam_group, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, P->intr_model, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_oc, h_cam.data(), sizeof(int) * no, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_xy, h_xy.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_si, h_si.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, THB_CAM_CONST_ALL, nc, st));
+  if (P->pt_const) THB_CUDA_CHECK(cudaMemcpyAsync(d_pc, P->pt_const, np, cudaMemcpyHostToDevice, st));
+  else THB_CUDA_CHECK(cudaMemsetAsync(d_pc, 0, np, st));
+  k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc, nullptr, d_cc, d_group);
+  BaConst K{};
+  K.nc = nc; K.ng = ng; K.np = np; K.no = no;
+  K.cam_group = d_group; K.intr_model = d_model; K.cam_const = d_cc; K.intr_const = nullptr; K.pt_const = d_pc; K.intr_slot = nullptr;
+  K.loss_type = O->loss_function_type; K.loss_width = O->robust_loss_width;
+  ObsSoA Ob{d_oc, nullptr, d_xy, d_si};
+  TrackBaParams tp;
+  tp.max_num_iterations = O->max_num_iterations; tp.max_invalid = O->max_num_consecutive_invalid_steps; tp.jacobi_scaling = O->jacobi_scaling;
+  tp.ftol = O->function_tolerance; tp.gtol = O->gradient_tolerance; tp.ptol = O->parameter_tolerance;
+  tp.radius0 = O->initial_trust_region_radius; tp.min_radius = O->min_trust_region_radius; tp.max_radius = O->max_trust_region_radius;
+  tp.min_relative_decrease = O->min_relative_decrease; tp.min_diag = O->min_lm_diagonal; tp.max_diag = O->max_lm_diagonal;
+  if (PD == 3) k_track_ba<3><<<cdiv(np, 128), 128, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
+  else k_track_ba<4><<<cdiv(np, 128), 128, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
+  THB_CUDA_CHECK(cudaGetLastError());
+  std::vector<ThbTrackBaResult> h_res(np);
+  std::vector<double> h_pts((size_t)np * 4);
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_res.data(), d_res, sizeof(ThbTrackBaResult) * np, cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_pts.data(), X.pts, sizeof(double) * np * 4, cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int p = 0; p < np; ++p) {  // IsSolutionUsable() == false leaves the track as it was
+    if (h_res[p].num_iterations >= 0 && h_res[p].termination_type != THB_TERM_FAILURE)
+      for (int k = 0; k < 4; ++k) P->pts[4 * (size_t)p + k] = h_pts[4 * (size_t)p + k];
+    if (results) results[p] = h_res[p];
+  }
   return THB_OK;
 }
 

@@ -50,6 +50,7 @@ def test_no_cpu_fallback(lib):
     o = capi.default_options(lib)
     rc = lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None)
     assert rc == capi.THB_E_NO_DEVICE
+    assert lib.thb_ba_tracks_batch(C.byref(p), C.byref(o), None, None) == capi.THB_E_NO_DEVICE
     assert b"no CPU path" in lib.thb_last_error() or b"sm_100" in lib.thb_last_error()
 
 

@@ -1,0 +1,118 @@
+"""Batched theia::BundleAdjustTrack (bundle_adjustment.cc:261-285): every track its own trust-region solve with the cameras
+constant, one launch for all tracks. Checked track by track against the oracle run on the single-track problem the
+reference would build (bundle_adjuster.cc:176-221), and through properties at C5 size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from pytheiasfm_b200 import capi, synthetic
+
+pytestmark = pytest.mark.gpu
+
+ALL_MODELS = [capi.MODEL_PINHOLE, capi.MODEL_FISHEYE, capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION,
+              capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED]
+
+
+def gpu_tracks(lib, prob, opts):
+    res = np.zeros(prob.num_points, capi.TRACK_BA_DTYPE)
+    p = prob.struct()
+    capi.check(lib.thb_ba_tracks_batch(C.byref(p), C.byref(opts), res.ctypes.data_as(C.c_void_p), None))
+    return res
+
+
+def single_track_problem(prob, t):
+    """What BundleAdjustTrack(options, t, reconstruction) hands to Ceres: the track's observations, every camera constant."""
+    a = dict(prob.a)
+    keep = prob.a["obs_pt"] == t
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        a[k] = None if prob.a[k] is None else prob.a[k][keep]
+    a["cam_const"] = np.full(prob.num_cameras, 3, np.uint8)
+    a["intr_const"] = None
+    return capi.HostBaProblem(a)
+
+
+def perturbed(ncam, npts, obs_per_pt, seed, sigma=0.05, **kw):
+    prob, _ = synthetic.make_ba_problem(ncam, npts, obs_per_pt, seed=seed, **kw)
+    rng = np.random.default_rng(seed + 1000)
+    prob.a["pts"][:, :3] += rng.normal(0, sigma, (npts, 3))
+    return prob
+
+
+def check_against_oracle(lib, oracle, prob, opts, tracks):
+    pg = prob.copy()
+    res = gpu_tracks(lib, pg, opts)
+    for t in tracks:
+        sub = single_track_problem(prob, t)
+        o = oracle.ba_solve(sub, opts)
+        assert o["rc"] == 0
+        r = res[t]
+        assert r["termination_type"] == o["termination_type"], (t, r, o["termination_type"])
+        assert abs(r["initial_cost"] - o["initial_cost"]) <= 1e-10 * max(o["initial_cost"], 1e-30)
+        assert abs(r["final_cost"] - o["final_cost"]) <= 1e-6 * max(o["final_cost"], 1e-12), (t, r, o["final_cost"])
+        assert r["num_iterations"] == o["num_iterations"], (t, r["num_iterations"], o["num_iterations"])
+        np.testing.assert_allclose(pg.a["pts"][t], sub.a["pts"][t], rtol=1e-6, atol=1e-9)
+    return res, pg
+
+
+@pytest.mark.parametrize("homogeneous", [True, False])
+def test_tracks_match_the_oracle_track_by_track(lib, oracle, homogeneous):
+    prob = perturbed(12, 150, 5, seed=301)
+    opts = capi.default_options(lib)
+    opts.use_inner_iterations = 0
+    opts.use_homogeneous_point_parametrization = int(homogeneous)
+    res, pg = check_against_oracle(lib, oracle, prob, opts, range(0, 150, 3))
+    assert (res["num_iterations"] > 0).all()
+    assert (res["final_cost"] < res["initial_cost"]).all()
+    # cameras and intrinsics are inputs only
+    np.testing.assert_array_equal(pg.a["cam_ext"], prob.a["cam_ext"])
+
+
+@pytest.mark.parametrize("model", ALL_MODELS)
+def test_every_camera_model_and_a_robust_loss(lib, oracle, model):
+    prob = perturbed(10, 60, 4, seed=310 + model, sigma=0.02, models=(model,))
+    if model == capi.MODEL_DIVISION_UNDISTORTION:
+        prob.a["intr"][0, 4] = -5e-7
+    opts = capi.default_options(lib)
+    opts.use_inner_iterations = 0
+    opts.loss_function_type = capi.LOSS_HUBER if model % 2 else capi.LOSS_TRIVIAL
+    opts.robust_loss_width = 2.0
+    check_against_oracle(lib, oracle, prob, opts, range(0, 60, 4))
+
+
+def test_constant_and_unobserved_tracks_are_left_alone(lib):
+    prob = perturbed(8, 40, 4, seed=320)
+    prob.a["pt_const"][::4] = 1
+    keep = prob.a["obs_pt"] != 5
+    a = dict(prob.a)
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        a[k] = prob.a[k][keep]
+    prob = capi.HostBaProblem(a)
+    before = prob.a["pts"].copy()
+    opts = capi.default_options(lib)
+    opts.use_inner_iterations = 0
+    res = gpu_tracks(lib, prob, opts)
+    skipped = np.zeros(40, bool); skipped[::4] = True; skipped[5] = True
+    assert (res["num_iterations"][skipped] == -1).all() and (res["num_iterations"][~skipped] > 0).all()
+    np.testing.assert_array_equal(prob.a["pts"][skipped], before[skipped])
+    assert (prob.a["pts"][~skipped] != before[~skipped]).any(axis=1).all()
+    opts.use_inner_iterations = 1
+    p = prob.struct()
+    assert lib.thb_ba_tracks_batch(C.byref(p), C.byref(opts), None, None) == capi.THB_E_UNSUPPORTED
+
+
+def test_c5_sized_batch_properties(lib):
+    """128 cameras / 60k tracks / 360k observations (BASELINE configs[4] shape): every track converges, no track's cost goes up,
+    the summed cost lands on the chi^2 floor of the pixel noise, a second call is a fixed point."""
+    prob, gt = synthetic.make_ba_problem(128, 60000, 6, seed=330, pos_sigma=0.0, rot_sigma=0.0)
+    rng = np.random.default_rng(331)
+    prob.a["pts"][:, :3] += rng.normal(0, 0.05, (60000, 3))
+    opts = capi.default_options(lib)
+    opts.use_inner_iterations = 0
+    res = gpu_tracks(lib, prob, opts)
+    assert (res["termination_type"] == 0).all()
+    assert (res["final_cost"] <= res["initial_cost"]).all()
+    assert res["final_cost"].sum() < 0.05 * res["initial_cost"].sum()
+    again = gpu_tracks(lib, prob, opts)
+    np.testing.assert_allclose(again["final_cost"], res["final_cost"], rtol=1e-6, atol=1e-12)
+    assert again["num_iterations"].max() <= 2
