@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -975,17 +976,23 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int PD = O->use_homogeneous_point_parametrization ? 3 : 4;
-  DevBufs B;
-  BaState X{B.get<double>((size_t)nc * 6), B.get<double>((size_t)nc * CAMD), B.get<double>((size_t)ng * KS), B.get<double>((size_t)np * 4)};
-  BaState Xc = X;
-  Xc.pts = B.get<double>((size_t)np * 4);
-  int* d_group = B.get<int>(nc); int* d_model = B.get<int>(ng); int* d_start = B.get<int>(np + 1); int* d_oc = B.get<int>(no);
-  uint8_t* d_cc = B.get<uint8_t>(nc); uint8_t* d_pc = B.get<uint8_t>(np);
-  double2* d_xy = B.get<double2>(no); double2* d_si = B.get<double2>(no);
-  double* d_ps = B.get<double>((size_t)np * PD);
-  ThbTrackBaResult* d_res = B.get<ThbTrackBaResult>(np);
-  if (!X.cam || !X.camd || !X.intr || !X.pts || !Xc.pts || !d_group || !d_model || !d_start || !d_oc || !d_cc || !d_pc || !d_xy || !d_si || !d_ps || !d_res)
-    THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  // stream-ordered blocks from the device pool (kept across calls: TrackEstimator calls this once per batch of new tracks)
+  ConfigurePoolOnce();
+  struct ScopedArena : Arena { ~ScopedArena() { Release(); } } M;
+  M.st = st;
+  BaState X{}, Xc{};
+  int *d_group = nullptr, *d_model = nullptr, *d_start = nullptr, *d_oc = nullptr;
+  uint8_t *d_cc = nullptr, *d_pc = nullptr;
+  double2 *d_xy = nullptr, *d_si = nullptr;
+  double* d_ps = nullptr;
+  ThbTrackBaResult* d_res = nullptr;
+  if ((rc = M.Get(&X.cam, (size_t)nc * 6)) != THB_OK || (rc = M.Get(&X.camd, (size_t)nc * CAMD)) != THB_OK || (rc = M.Get(&X.intr, (size_t)ng * KS)) != THB_OK ||
+      (rc = M.Get(&X.pts, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_group, nc)) != THB_OK || (rc = M.Get(&d_model, ng)) != THB_OK ||
+      (rc = M.Get(&d_start, np + 1)) != THB_OK || (rc = M.Get(&d_oc, no)) != THB_OK || (rc = M.Get(&d_cc, nc)) != THB_OK || (rc = M.Get(&d_pc, np)) != THB_OK ||
+      (rc = M.Get(&d_xy, no)) != THB_OK || (rc = M.Get(&d_si, no)) != THB_OK || (rc = M.Get(&d_ps, (size_t)np * PD)) != THB_OK || (rc = M.Get(&d_res, np)) != THB_OK)
+    return rc;
+  Xc = X;
+  if ((rc = M.Get(&Xc.pts, (size_t)np * 4)) != THB_OK) return rc;
   THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, cudaMemcpyHostToDevice, st));
   THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, cudaMemcpyHostToDevice, st));
   THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * np * 4, cudaMemcpyHostToDevice, st));
@@ -1009,9 +1016,21 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
   tp.ftol = O->function_tolerance; tp.gtol = O->gradient_tolerance; tp.ptol = O->parameter_tolerance;
   tp.radius0 = O->initial_trust_region_radius; tp.min_radius = O->min_trust_region_radius; tp.max_radius = O->max_trust_region_radius;
   tp.min_relative_decrease = O->min_relative_decrease; tp.min_diag = O->min_lm_diagonal; tp.max_diag = O->max_lm_diagonal;
-  if (PD == 3) k_track_ba<3><<<cdiv(np, 128), 128, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
-  else k_track_ba<4><<<cdiv(np, 128), 128, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
+  // 64-thread CTAs: a C5-sized batch (60k tracks) is only 0.4 threads per resident-thread slot of the GPU, small CTAs spread it
+  // over all SMs (168 registers per thread). THB_TRACK_TIMING=1 prints the kernel's duration (scratch/track_time.py).
+  const bool timing = getenv("THB_TRACK_TIMING") != nullptr;
+  const int cta = 64;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timing) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
+  if (PD == 3) k_track_ba<3><<<cdiv(np, cta), cta, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
+  else k_track_ba<4><<<cdiv(np, cta), cta, 0, st>>>(K, X, Xc, Ob, d_start, d_ps, tp, d_res);
   THB_CUDA_CHECK(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(e1, st); cudaEventSynchronize(e1);
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "k_track_ba<%d>: %d tracks, %d-thread CTAs, %.3f ms\n", PD, np, cta, ms);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   std::vector<ThbTrackBaResult> h_res(np);
   std::vector<double> h_pts((size_t)np * 4);
   THB_CUDA_CHECK(cudaMemcpyAsync(h_res.data(), d_res, sizeof(ThbTrackBaResult) * np, cudaMemcpyDeviceToHost, st));
