@@ -5,6 +5,7 @@ matching/feature_matcher.cc:117-126). One process per GPU; the pair table is spl
 cumulative correspondence count (the cost of a pair is proportional to its number of correspondences times its
 iteration count); every rank verifies its block with thb_ransac_*_batch; one all_gather of the fixed-size result
 records assembles the full table on every rank. No collective sits on the data path of the kernels.
+Tracks (per-track BA, triangulation) shard the same way: shard_tracks.
 """
 import numpy as np
 
@@ -40,12 +41,34 @@ def shard_batch(batch, rank, world):
     return sub, lo, hi
 
 
-def all_gather_results(local_records, ranges, group=None, device=None):
-    """all_gather of per-pair result records (structured array of capi.RELPOSE_DTYPE, or a uint8 torch tensor on the
-    rank's device) into the full table, ordered by global pair index. Works on NCCL (GPU) and gloo (CPU tests)."""
+def shard_tracks(prob, rank, world):
+    """The rank's block of tracks of a HostBaProblem for thb_ba_tracks_batch / thb_triangulate_midpoint_batch (SURVEY 8e,
+    "per-track BA / triangulation: tracks independent given fixed cameras - same scheme as pairs"): contiguous point range
+    [lo, hi) balanced by cumulative observation count, the observations of those points with obs_pt re-based, and ALL
+    cameras / intrinsics (read-only, replicated on every rank). Returns (HostBaProblem, lo, hi)."""
+    obs_pt = prob.a["obs_pt"]
+    counts = np.bincount(obs_pt, minlength=prob.num_points)
+    offset = np.zeros(prob.num_points + 1, np.int64)
+    offset[1:] = np.cumsum(counts)
+    lo, hi = partition_by_work(offset, world)[rank]
+    keep = (obs_pt >= lo) & (obs_pt < hi)
+    a = dict(prob.a)
+    a["pts"] = prob.a["pts"][lo:hi]
+    a["pt_const"] = None if prob.a["pt_const"] is None else prob.a["pt_const"][lo:hi]
+    for k in ("obs_cam", "obs_xy", "obs_sqrt_info"):
+        a[k] = None if prob.a[k] is None else prob.a[k][keep]
+    a["obs_pt"] = obs_pt[keep] - lo
+    return capi.HostBaProblem(a), lo, hi
+
+
+def all_gather_results(local_records, ranges, group=None, device=None, dtype=None):
+    """all_gather of per-unit result records (structured array of `dtype`, default capi.RELPOSE_DTYPE, or a uint8 torch
+    tensor on the rank's device) into the full table, ordered by global pair / track index. Works on NCCL (GPU) and gloo
+    (CPU tests)."""
     import torch
     import torch.distributed as dist
-    rec = capi.RELPOSE_DTYPE.itemsize
+    dtype = capi.RELPOSE_DTYPE if dtype is None else np.dtype(dtype)
+    rec = dtype.itemsize
     world = dist.get_world_size(group)
     counts = [hi - lo for lo, hi in ranges]
     if isinstance(local_records, np.ndarray):
@@ -61,4 +84,4 @@ def all_gather_results(local_records, ranges, group=None, device=None):
     out = [torch.zeros(pad, dtype=torch.uint8, device=local.device) for _ in range(world)]
     dist.all_gather(out, buf, group=group)
     full = torch.cat([out[r][: counts[r] * rec] for r in range(world)])
-    return np.frombuffer(full.cpu().numpy().tobytes(), capi.RELPOSE_DTYPE)
+    return np.frombuffer(full.cpu().numpy().tobytes(), dtype)

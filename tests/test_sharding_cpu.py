@@ -63,3 +63,57 @@ def test_shard_and_gather_over_gloo(world):
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world))
+
+
+def test_track_shards_cover_every_track_and_observation_once():
+    from pytheiasfm_b200 import synthetic
+    prob, _ = synthetic.make_ba_problem(9, 301, 4, seed=3)
+    prob.a["pt_const"][::7] = 1
+    for world in (1, 2, 3, 8):
+        seen_pts = np.zeros(prob.num_points, int); n_obs = 0; work = []
+        for rank in range(world):
+            sub, lo, hi = sharding.shard_tracks(prob, rank, world)
+            seen_pts[lo:hi] += 1
+            n_obs += sub.num_observations
+            work.append(sub.num_observations)
+            assert sub.num_points == hi - lo and sub.num_cameras == prob.num_cameras
+            np.testing.assert_array_equal(sub.a["pts"], prob.a["pts"][lo:hi])
+            np.testing.assert_array_equal(sub.a["pt_const"], prob.a["pt_const"][lo:hi])
+            keep = (prob.a["obs_pt"] >= lo) & (prob.a["obs_pt"] < hi)
+            np.testing.assert_array_equal(sub.a["obs_pt"] + lo, prob.a["obs_pt"][keep])
+            np.testing.assert_array_equal(sub.a["obs_xy"], prob.a["obs_xy"][keep])
+        assert (seen_pts == 1).all() and n_obs == prob.num_observations
+        assert max(work) - min(work) <= 8          # balanced to within a couple of tracks
+
+
+def _track_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    from pytheiasfm_b200 import synthetic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        prob, _ = synthetic.make_ba_problem(6, 57, 3, seed=4)
+        counts = np.bincount(prob.a["obs_pt"], minlength=57)
+        offset = np.concatenate([[0], np.cumsum(counts)])
+        ranges = sharding.partition_by_work(offset, world)
+        sub, lo, hi = sharding.shard_tracks(prob, rank, world)
+        assert (lo, hi) == ranges[rank]
+        # stand-in for this rank's thb_ba_tracks_batch results: records tagged with the global track index
+        local = np.zeros(hi - lo, capi.TRACK_BA_DTYPE)
+        local["num_iterations"] = np.arange(lo, hi)
+        local["final_cost"] = sub.a["pts"][:, 0]
+        full = sharding.all_gather_results(local, ranges, dtype=capi.TRACK_BA_DTYPE)
+        np.testing.assert_array_equal(full["num_iterations"], np.arange(57))
+        np.testing.assert_array_equal(full["final_cost"], prob.a["pts"][:, 0])
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_track_shard_and_gather_over_gloo():
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_track_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert all(ret.get(r) for r in range(2))
