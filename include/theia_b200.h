@@ -340,6 +340,33 @@ typedef struct ThbTrackBaResult {
  */
 int thb_ba_tracks_batch(const ThbBaProblem* problem, const ThbBaOptions* options, ThbTrackBaResult* results, void* cuda_stream);
 
+/* TrackEstimator::Options (sfm/estimate_track.h:59-84), MIDPOINT triangulation (the default). */
+typedef struct ThbTrackEstimatorOptions {
+  double max_acceptable_reprojection_error_pixels; /* 5.0 */
+  double min_triangulation_angle_degrees;          /* 3.0 */
+  int32_t bundle_adjustment;                       /* 1   */
+  int32_t reserved0;
+} ThbTrackEstimatorOptions;
+
+#define THB_TRACK_SKIPPED (-1)             /* constant (already estimated) track: TrackEstimator::EstimateTrack returns early */
+#define THB_TRACK_ESTIMATED 0
+#define THB_TRACK_BAD_ANGLE 1              /* < 2 observations or no pair of rays wider than the minimum angle (:230-236) */
+#define THB_TRACK_FAILED_TRIANGULATION 2   /* TriangulateMidpoint returned false (:256-261)                               */
+#define THB_TRACK_BA_FAILED 3              /* BundleAdjustTrack summary.success == false (:295-297)                       */
+#define THB_TRACK_BAD_REPROJECTION 4       /* a view sees the point behind it, or mean squared error too large (:300-311) */
+
+/*
+ * TrackEstimator::EstimateTrack (sfm/estimate_track.cc:209-321) for every non-constant point of the problem in one launch:
+ * angle test (SufficientTriangulationAngle, triangulation.cc:236-250), TriangulateMidpoint from the camera positions and
+ * the caller's unit ray directions (ray_directions [num_observations*3], one per observation, what
+ * Camera::PixelToUnitDepthRay(feature).normalized() gives, estimate_track.cc:80-87), BundleAdjustTrack, and the
+ * reprojection test (AcceptableReprojectionError, :93-119). status [num_points] receives THB_TRACK_*; problem->pts is
+ * written for THB_TRACK_ESTIMATED tracks only (the caller sets those estimated); ba_results may be NULL. The starting
+ * values in problem->pts are ignored. Host memory only for now.
+ */
+int thb_estimate_tracks_batch(const ThbBaProblem* problem, const double* ray_directions, const ThbTrackEstimatorOptions* options,
+                              const ThbBaOptions* ba_options, int32_t* status, ThbTrackBaResult* ba_results, void* cuda_stream);
+
 /*
  * theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157) for a batch of tracks: track t owns the rays
  * ray_offset[t] .. ray_offset[t+1]-1 (origin and direction, 3 doubles each; directions as the caller passes them, the

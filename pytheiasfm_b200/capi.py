@@ -118,6 +118,18 @@ class ThbRelPoseResult(C.Structure):
     ]
 
 
+TRACK_SKIPPED, TRACK_ESTIMATED, TRACK_BAD_ANGLE, TRACK_FAILED_TRIANGULATION, TRACK_BA_FAILED, TRACK_BAD_REPROJECTION = -1, 0, 1, 2, 3, 4
+
+
+class ThbTrackEstimatorOptions(C.Structure):
+    """TrackEstimator::Options (estimate_track.h:59-84) with its defaults."""
+    _fields_ = [("max_acceptable_reprojection_error_pixels", C.c_double), ("min_triangulation_angle_degrees", C.c_double),
+                ("bundle_adjustment", C.c_int32), ("reserved0", C.c_int32)]
+
+    def __init__(self):
+        super().__init__(5.0, 3.0, 1, 0)
+
+
 TRACK_BA_DTYPE = np.dtype([("initial_cost", np.float64), ("final_cost", np.float64), ("num_iterations", np.int32),
                            ("termination_type", np.int32)])
 RELPOSE_DTYPE = np.dtype([("success", np.int32), ("num_inliers", np.int32), ("num_iterations", np.int32),
@@ -203,6 +215,9 @@ def load_library():
     lib.thb_p3p.restype = C.c_int
     lib.thb_ba_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.POINTER(ThbBaOptions), C.c_void_p, C.c_void_p]
     lib.thb_ba_tracks_batch.restype = C.c_int
+    lib.thb_estimate_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.c_void_p, C.POINTER(ThbTrackEstimatorOptions), C.POINTER(ThbBaOptions),
+                                              C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_estimate_tracks_batch.restype = C.c_int
     lib.thb_triangulate_midpoint_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_triangulate_midpoint_batch.restype = C.c_int
     lib.thb_four_point_homography.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -943,7 +943,11 @@ int thb_dense_spd_time(int32_t n, int32_t repeats, double* avg_ms, double* rel_r
   return THB_OK;
 }
 
-int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBaResult* results, void* cuda_stream) {
+}  // extern "C"
+namespace {
+// shared by thb_ba_tracks_batch (rays == nullptr) and thb_estimate_tracks_batch
+int RunTrackBatch(const ThbBaProblem* P, const ThbBaOptions* O, const double* rays, const ThbTrackEstimatorOptions* E, int32_t* status,
+                  ThbTrackBaResult* results, void* cuda_stream) {
   if (!P || !O) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem or options");
   if (O->use_inner_iterations) THB_FAIL(THB_E_UNSUPPORTED, "BundleAdjustTrack runs without inner iterations (bundle_adjustment.cc:267)");
   if (P->memory_space != THB_MEM_HOST) THB_FAIL(THB_E_UNSUPPORTED, "thb_ba_tracks_batch takes host buffers");
@@ -958,7 +962,7 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
   for (int c = 0; c < nc; ++c) if (P->cam_group[c] < 0 || P->cam_group[c] >= ng) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
   // observations grouped by track (stable counting sort), as AddTrack walks track->ViewIds()
   std::vector<int> start(np + 1, 0), h_cam(no);
-  std::vector<double> h_xy((size_t)no * 2), h_si((size_t)no * 2);
+  std::vector<double> h_xy((size_t)no * 2), h_si((size_t)no * 2), h_ray(rays ? (size_t)no * 3 : 0);
   for (int i = 0; i < no; ++i) {
     if (P->obs_cam[i] < 0 || P->obs_cam[i] >= nc || P->obs_pt[i] < 0 || P->obs_pt[i] >= np) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
     ++start[P->obs_pt[i] + 1];
@@ -972,6 +976,7 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
       h_xy[2 * (size_t)q] = P->obs_xy[2 * (size_t)i]; h_xy[2 * (size_t)q + 1] = P->obs_xy[2 * (size_t)i + 1];
       h_si[2 * (size_t)q] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i] : 1.0;
       h_si[2 * (size_t)q + 1] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i + 1] : 1.0;
+      if (rays) for (int k = 0; k < 3; ++k) h_ray[3 * (size_t)q + k] = rays[3 * (size_t)i + k];
     }
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -993,6 +998,12 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
     return rc;
   Xc = X;
   if ((rc = M.Get(&Xc.pts, (size_t)np * 4)) != THB_OK) return rc;
+  double* d_ray = nullptr;
+  int* d_status = nullptr;
+  if (rays) {
+    if ((rc = M.Get(&d_ray, (size_t)no * 3)) != THB_OK || (rc = M.Get(&d_status, np)) != THB_OK) return rc;
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_ray, h_ray.data(), sizeof(double) * 3 * no, cudaMemcpyHostToDevice, st));
+  }
   THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, cudaMemcpyHostToDevice, st));
   THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, cudaMemcpyHostToDevice, st));
   THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * np * 4, cudaMemcpyHostToDevice, st));
@@ -1016,6 +1027,12 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
   tp.ftol = O->function_tolerance; tp.gtol = O->gradient_tolerance; tp.ptol = O->parameter_tolerance;
   tp.radius0 = O->initial_trust_region_radius; tp.min_radius = O->min_trust_region_radius; tp.max_radius = O->max_trust_region_radius;
   tp.min_relative_decrease = O->min_relative_decrease; tp.min_diag = O->min_lm_diagonal; tp.max_diag = O->max_lm_diagonal;
+  tp.rays = d_ray; tp.status = d_status; tp.bundle_adjustment = 1; tp.cos_min_angle = -2.0; tp.sq_max_reprojection_error = 0.0;
+  if (rays) {
+    tp.bundle_adjustment = E->bundle_adjustment;
+    tp.cos_min_angle = std::cos(E->min_triangulation_angle_degrees * 3.14159265358979323846 / 180.0);  // DegToRad, triangulation.cc:240-241
+    tp.sq_max_reprojection_error = E->max_acceptable_reprojection_error_pixels * E->max_acceptable_reprojection_error_pixels;
+  }
   // 64-thread CTAs: a C5-sized batch (60k tracks) is only 0.4 threads per resident-thread slot of the GPU, small CTAs spread it
   // over all SMs (168 registers per thread). THB_TRACK_TIMING=1 prints the kernel's duration (scratch/track_time.py).
   const bool timing = getenv("THB_TRACK_TIMING") != nullptr;
@@ -1035,13 +1052,26 @@ int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBa
   std::vector<double> h_pts((size_t)np * 4);
   THB_CUDA_CHECK(cudaMemcpyAsync(h_res.data(), d_res, sizeof(ThbTrackBaResult) * np, cudaMemcpyDeviceToHost, st));
   THB_CUDA_CHECK(cudaMemcpyAsync(h_pts.data(), X.pts, sizeof(double) * np * 4, cudaMemcpyDeviceToHost, st));
+  if (rays) THB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
-  for (int p = 0; p < np; ++p) {  // IsSolutionUsable() == false leaves the track as it was
-    if (h_res[p].num_iterations >= 0 && h_res[p].termination_type != THB_TERM_FAILURE)
-      for (int k = 0; k < 4; ++k) P->pts[4 * (size_t)p + k] = h_pts[4 * (size_t)p + k];
+  for (int p = 0; p < np; ++p) {  // IsSolutionUsable() == false leaves the track as it was; EstimateTrack keeps only estimated tracks
+    const bool keep = rays ? status[p] == THB_TRACK_ESTIMATED : (h_res[p].num_iterations >= 0 && h_res[p].termination_type != THB_TERM_FAILURE);
+    if (keep) for (int k = 0; k < 4; ++k) P->pts[4 * (size_t)p + k] = h_pts[4 * (size_t)p + k];
     if (results) results[p] = h_res[p];
   }
   return THB_OK;
+}
+}  // namespace
+extern "C" {
+
+int thb_ba_tracks_batch(const ThbBaProblem* P, const ThbBaOptions* O, ThbTrackBaResult* results, void* cuda_stream) {
+  return RunTrackBatch(P, O, nullptr, nullptr, nullptr, results, cuda_stream);
+}
+
+int thb_estimate_tracks_batch(const ThbBaProblem* P, const double* ray_directions, const ThbTrackEstimatorOptions* E, const ThbBaOptions* O,
+                              int32_t* status, ThbTrackBaResult* results, void* cuda_stream) {
+  if (!ray_directions || !E || !status) THB_FAIL(THB_E_INVALID_ARGUMENT, "null ray_directions, options or status");
+  return RunTrackBatch(P, O, ray_directions, E, status, results, cuda_stream);
 }
 
 int thb_ba_evaluate(const ThbBaProblem* P, double* residuals, double* jac_cam, double* jac_intr, double* jac_pt,

@@ -16,7 +16,73 @@ namespace thb {
 struct TrackBaParams {
   int max_num_iterations, max_invalid, jacobi_scaling;
   double ftol, gtol, ptol, radius0, min_radius, max_radius, min_relative_decrease, min_diag, max_diag;
+  // TrackEstimator::EstimateTrack stages around the solve (estimate_track.cc:209-321); rays == nullptr: plain BundleAdjustTrack
+  const double* rays;       // [no * 3] unit ray direction of every observation, grouped like the observations
+  int* status;              // [np] THB_TRACK_*
+  int bundle_adjustment;
+  double cos_min_angle, sq_max_reprojection_error;
 };
+
+// TriangulateMidpoint (triangulation.cc:130-157) over the track's rays, origins = camera positions. As triangulation.cu.
+__device__ __forceinline__ bool track_midpoint(const BaState& X, const ObsSoA& O, const double* rays, int q0, int q1, double z[4]) {
+  double A[4][4] = {}, b[4] = {};
+  for (int q = q0; q < q1; ++q) {
+    const double* C = X.cam + (size_t)O.cam[q] * 6;
+    const double d[4] = {rays[3 * (size_t)q], rays[3 * (size_t)q + 1], rays[3 * (size_t)q + 2], 0.0};
+    const double o[4] = {C[0], C[1], C[2], 1.0};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { const double T = (r == c ? 1.0 : 0.0) - d[r] * d[c]; A[r][c] += T; s += T * o[c]; }
+      b[r] += s;
+    }
+  }
+  bool good = true;
+  double L[4][4] = {};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double x = A[k][k];
+#pragma unroll
+    for (int j = 0; j < k; ++j) x -= L[k][j] * L[k][j];
+    if (!(x > 0.0)) good = false;
+    x = sqrt(x);
+    L[k][k] = x;
+#pragma unroll
+    for (int r = k + 1; r < 4; ++r) {
+      double v = A[r][k];
+#pragma unroll
+      for (int j = 0; j < k; ++j) v -= L[r][j] * L[k][j];
+      L[r][k] = v / x;
+    }
+  }
+  double y[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { double v = b[r]; for (int j = 0; j < r; ++j) v -= L[r][j] * y[j]; y[r] = v / L[r][r]; }
+#pragma unroll
+  for (int r = 3; r >= 0; --r) { double v = y[r]; for (int j = r + 1; j < 4; ++j) v -= L[j][r] * z[j]; z[r] = v / L[r][r]; }
+  return good;
+}
+
+// AcceptableReprojectionError (estimate_track.cc:93-119): every view sees the point in front (Camera::ProjectPoint depth
+// >= 0, camera.cc:206-216) and the MEAN squared pixel error stays below the threshold.
+__device__ __noinline__ bool track_reprojection_ok(const BaConst& K, const BaState& St, const ObsSoA& O, int p, int q0, int q1, double sq_max) {
+  const double* Xp = St.pts + (size_t)p * 4;
+  const double X[4] = {Xp[0], Xp[1], Xp[2], Xp[3]};
+  double sum = 0.0;
+  for (int q = q0; q < q1; ++q) {
+    const int c = O.cam[q];
+    const double* cd = St.camd + (size_t)c * CAMD;
+    const double adj[3] = {X[0] - X[3] * cd[CD_C], X[1] - X[3] * cd[CD_C + 1], X[2] - X[3] * cd[CD_C + 2]};
+    double pc[3];
+    rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2], adj, pc);
+    if (pc[2] / X[3] < 0.0) return false;
+    double r[2];
+    if (!eval_residual<-1>(K, St, c, p, O.xy[q], make_double2(1.0, 1.0), r)) return false;
+    sum += r[0] * r[0] + r[1] * r[1];
+  }
+  return sum / (double)(q1 - q0) < sq_max;
+}
 
 // One pass over the track's observations at state St: cost, and (WANT_J) V = sum Jp^T Jp (lower, row-major PD x PD) and
 // g = sum Jp^T r with the column scales ps[p * PD + k] applied. Returns false when an evaluation fails (ReprojectionError returned false).
@@ -64,10 +130,28 @@ __global__ void __launch_bounds__(128) k_track_ba(BaConst K, BaState X, BaState 
   const int q0 = pt_start[p], q1 = pt_start[p + 1];
   ThbTrackBaResult out;
   out.initial_cost = 0.0; out.final_cost = 0.0; out.num_iterations = -1; out.termination_type = THB_TERM_CONVERGENCE;
-  if (K.pt_const[p] || q1 == q0) { res[p] = out; return; }
+  if (K.pt_const[p] || (q1 == q0 && !P.rays)) { res[p] = out; if (P.status) P.status[p] = THB_TRACK_SKIPPED; return; }
   double* xp = X.pts + (size_t)p * 4;
   double* xc = Xc.pts + (size_t)p * 4;
   double* ps = ps_all + (size_t)p * PD;
+  if (P.rays) {  // EstimateTrack: angle test, then the midpoint as the starting point
+    bool wide = false;
+    for (int a = q0; a < q1 && !wide; ++a)
+      for (int b = a + 1; b < q1; ++b) {
+        const double* u = P.rays + 3 * (size_t)a; const double* v = P.rays + 3 * (size_t)b;
+        if (u[0] * v[0] + u[1] * v[1] + u[2] * v[2] < P.cos_min_angle) { wide = true; break; }
+      }
+    if (q1 - q0 < 2 || !wide) { res[p] = out; P.status[p] = THB_TRACK_BAD_ANGLE; return; }
+    double z[4];
+    if (!track_midpoint(X, O, P.rays, q0, q1, z)) { res[p] = out; P.status[p] = THB_TRACK_FAILED_TRIANGULATION; return; }
+    xp[0] = z[0]; xp[1] = z[1]; xp[2] = z[2]; xp[3] = z[3];
+    if (!P.bundle_adjustment) {
+      out.num_iterations = 0;
+      res[p] = out;
+      P.status[p] = track_reprojection_ok(K, X, O, p, q0, q1, P.sq_max_reprojection_error) ? THB_TRACK_ESTIMATED : THB_TRACK_BAD_REPROJECTION;
+      return;
+    }
+  }
   double x[4] = {xp[0], xp[1], xp[2], xp[3]};
   double V[PD * PD], g[PD], x_cost = 0.0;
   for (int k = 0; k < PD; ++k) ps[k] = 1.0;
@@ -77,7 +161,7 @@ __global__ void __launch_bounds__(128) k_track_ba(BaConst K, BaState X, BaState 
     for (int k = 0; k < PD; ++k) ps[k] = 1.0 / (1.0 + sqrt(V[k * PD + k]));
   }
   ok = track_pass<PD, true>(K, X, O, p, q0, q1, ps_all, &x_cost, V, g) && ok;
-  if (!ok) { out.num_iterations = 0; out.termination_type = THB_TERM_FAILURE; res[p] = out; return; }
+  if (!ok) { out.num_iterations = 0; out.termination_type = THB_TERM_FAILURE; res[p] = out; if (P.status) P.status[p] = THB_TRACK_BA_FAILED; return; }
   out.initial_cost = x_cost;
   double x_norm = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3]);
   double radius = P.radius0, decrease_factor = 2.0;
@@ -156,6 +240,11 @@ __global__ void __launch_bounds__(128) k_track_ba(BaConst K, BaState X, BaState 
   }
   out.final_cost = x_cost; out.num_iterations = iteration; out.termination_type = term;
   res[p] = out;
+  if (P.status) {
+    if (term == THB_TERM_FAILURE) P.status[p] = THB_TRACK_BA_FAILED;
+    else if (!P.rays) P.status[p] = THB_TRACK_ESTIMATED;
+    else P.status[p] = track_reprojection_ok(K, X, O, p, q0, q1, P.sq_max_reprojection_error) ? THB_TRACK_ESTIMATED : THB_TRACK_BAD_REPROJECTION;
+  }
 }
 
 }  // namespace thb

@@ -51,6 +51,11 @@ def test_no_cpu_fallback(lib):
     rc = lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None)
     assert rc == capi.THB_E_NO_DEVICE
     assert lib.thb_ba_tracks_batch(C.byref(p), C.byref(o), None, None) == capi.THB_E_NO_DEVICE
+    import numpy as np
+    rays = np.zeros((prob.num_observations, 3)); status = np.zeros(prob.num_points, np.int32)
+    e = capi.ThbTrackEstimatorOptions()
+    assert lib.thb_estimate_tracks_batch(C.byref(p), rays.ctypes.data_as(C.c_void_p), C.byref(e), C.byref(o),
+                                         status.ctypes.data_as(C.c_void_p), None, None) == capi.THB_E_NO_DEVICE
     assert b"no CPU path" in lib.thb_last_error() or b"sm_100" in lib.thb_last_error()
 
 

@@ -116,3 +116,114 @@ def test_c5_sized_batch_properties(lib):
     again = gpu_tracks(lib, prob, opts)
     np.testing.assert_allclose(again["final_cost"], res["final_cost"], rtol=1e-6, atol=1e-12)
     assert again["num_iterations"].max() <= 2
+
+
+# ---- TrackEstimator::EstimateTrack (estimate_track.cc:209-321) in one launch --------------------------------------------
+
+def rodrigues(aa):
+    th = np.linalg.norm(aa)
+    if th < 1e-12:
+        return np.eye(3)
+    k = aa / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+
+
+def pinhole_rays(prob):
+    """Camera::PixelToUnitDepthRay(feature).normalized() (camera.cc:218-226) for undistorted pinhole cameras."""
+    a = prob.a
+    rays = np.zeros((prob.num_observations, 3))
+    for i in range(prob.num_observations):
+        c = a["obs_cam"][i]
+        f, ar, s, cx, cy = a["intr"][a["cam_group"][c], :5]
+        y = (a["obs_xy"][i, 1] - cy) / (f * ar)
+        x = (a["obs_xy"][i, 0] - cx - s * y) / f
+        d = rodrigues(a["cam_ext"][c, 3:6]).T @ np.array([x, y, 1.0])
+        rays[i] = d / np.linalg.norm(d)
+    return rays
+
+
+def gpu_estimate(lib, prob, rays, eopts, opts):
+    status = np.full(prob.num_points, 99, np.int32)
+    res = np.zeros(prob.num_points, capi.TRACK_BA_DTYPE)
+    p = prob.struct()
+    capi.check(lib.thb_estimate_tracks_batch(C.byref(p), rays.ctypes.data_as(C.c_void_p), C.byref(eopts), C.byref(opts),
+                                             status.ctypes.data_as(C.c_void_p), res.ctypes.data_as(C.c_void_p), None))
+    return status, res
+
+
+def oracle_estimate_track(oracle, prob, rays, t, eopts, opts):
+    """The stages of EstimateTrack composed from the oracle's pieces; returns (status, point or None)."""
+    a = prob.a
+    idx = np.nonzero(a["obs_pt"] == t)[0]
+    if a["pt_const"] is not None and a["pt_const"][t]:
+        return capi.TRACK_SKIPPED, None
+    d = rays[idx]
+    cos_min = np.cos(np.deg2rad(eopts.min_triangulation_angle_degrees))
+    if len(idx) < 2 or not any(d[i] @ d[j] < cos_min for i in range(len(idx)) for j in range(i + 1, len(idx))):
+        return capi.TRACK_BAD_ANGLE, None
+    org = a["cam_ext"][a["obs_cam"][idx], :3]
+    X, ok = oracle.triangulate_midpoint_batch(org, d, np.array([0, len(idx)], np.int64))
+    if not ok[0]:
+        return capi.TRACK_FAILED_TRIANGULATION, None
+    X = X[0]
+    if eopts.bundle_adjustment:
+        start = prob.copy()
+        start.a["pts"][t] = X
+        sub = single_track_problem(start, t)
+        o = oracle.ba_solve(sub, opts)
+        if not o["success"]:
+            return capi.TRACK_BA_FAILED, None
+        X = sub.a["pts"][t]
+    err = 0.0
+    for i in idx:
+        c = a["obs_cam"][i]
+        pc = rodrigues(a["cam_ext"][c, 3:6]) @ (X[:3] - X[3] * a["cam_ext"][c, :3])
+        if pc[2] / X[3] < 0:
+            return capi.TRACK_BAD_REPROJECTION, None
+        f, ar, s, cx, cy = a["intr"][a["cam_group"][c], :5]
+        n = pc[:2] / pc[2]
+        pix = np.array([f * n[0] + s * n[1] + cx, f * ar * n[1] + cy])
+        err += np.sum((pix - a["obs_xy"][i]) ** 2)
+    if not err / len(idx) < eopts.max_acceptable_reprojection_error_pixels ** 2:
+        return capi.TRACK_BAD_REPROJECTION, None
+    return capi.TRACK_ESTIMATED, X
+
+
+@pytest.mark.parametrize("min_angle,with_ba", [(3.0, True), (120.0, True), (3.0, False)])
+def test_estimate_tracks_matches_the_composed_oracle(lib, oracle, min_angle, with_ba):
+    prob, _ = synthetic.make_ba_problem(12, 160, 4, seed=340, pos_sigma=0.0, rot_sigma=0.0)
+    a = prob.a
+    a["obs_xy"][np.nonzero(a["obs_pt"] == 7)[0][0]] += 300.0       # an outlier observation: bad reprojection
+    a["obs_xy"][np.nonzero(a["obs_pt"] == 11)[0][1]] += 40.0
+    a["pt_const"][[3, 50]] = 1                                     # already estimated tracks are skipped
+    keep = np.ones(prob.num_observations, bool)
+    keep[np.nonzero(a["obs_pt"] == 20)[0][1:]] = False             # a single observation: no angle
+    keep[np.nonzero(a["obs_pt"] == 21)[0]] = False                 # no observation at all
+    arr = dict(a)
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        arr[k] = a[k][keep]
+    prob = capi.HostBaProblem(arr)
+    rays = pinhole_rays(prob)
+    rng = np.random.default_rng(341)
+    prob.a["pts"][:] = rng.normal(0, 50, prob.a["pts"].shape)      # starting values are ignored
+    before = prob.a["pts"].copy()
+    eopts = capi.ThbTrackEstimatorOptions()
+    eopts.min_triangulation_angle_degrees = min_angle
+    eopts.bundle_adjustment = int(with_ba)
+    opts = capi.default_options(lib)
+    opts.use_inner_iterations = 0
+    pg = prob.copy()
+    status, res = gpu_estimate(lib, pg, rays, eopts, opts)
+    want = [oracle_estimate_track(oracle, prob, rays, t, eopts, opts) for t in range(prob.num_points)]
+    np.testing.assert_array_equal(status, [w[0] for w in want])
+    for t, (st, X) in enumerate(want):
+        if st == capi.TRACK_ESTIMATED:
+            np.testing.assert_allclose(pg.a["pts"][t], X, rtol=1e-6, atol=1e-9)
+        else:
+            np.testing.assert_array_equal(pg.a["pts"][t], before[t])
+    assert status[3] == status[50] == capi.TRACK_SKIPPED and status[20] == status[21] == capi.TRACK_BAD_ANGLE
+    assert status[7] == capi.TRACK_BAD_REPROJECTION
+    assert (status == capi.TRACK_ESTIMATED).sum() > (5 if min_angle > 10 else 140)
+    if min_angle > 10:
+        assert (status == capi.TRACK_BAD_ANGLE).sum() > 5
