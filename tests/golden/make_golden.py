@@ -64,9 +64,58 @@ def ransac_golden():
     np.savez_compressed(os.path.join(HERE, "five_point_32samples.npz"), x1=x[:, :, :2].copy(), x2=x[:, :, 2:].copy(), E=E, num_solutions=n)
 
 
+def single_track_problem(prob, t):
+    """What BundleAdjustTrack(options, t, reconstruction) hands to Ceres (bundle_adjuster.cc:176-221)."""
+    a = dict(prob.a)
+    keep = prob.a["obs_pt"] == t
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        a[k] = None if prob.a[k] is None else prob.a[k][keep]
+    a["cam_const"] = np.full(prob.num_cameras, 3, np.uint8)
+    a["intr_const"] = None
+    return capi.HostBaProblem(a)
+
+
+def track_golden():
+    """Track stage: TriangulateMidpoint on 80 ragged tracks, BundleAdjustTrack on each of the 80 tracks of a 10-camera scene."""
+    rng = np.random.default_rng(21)
+    counts = rng.integers(2, 9, 80)
+    off = np.zeros(81, np.int64); off[1:] = np.cumsum(counts)
+    X = rng.uniform(-2, 2, (80, 3))
+    ang = rng.uniform(0, 2 * np.pi, off[-1])
+    org = np.stack([6 * np.cos(ang), 6 * np.sin(ang), rng.uniform(-1, 1, off[-1])], 1)
+    d = np.repeat(X, counts, axis=0) - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d += rng.normal(0, 1e-3, d.shape)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[off[5]:off[6]] *= 3.0                                  # an indefinite system: LLT fails
+    pts, ok = oracle_py.triangulate_midpoint_batch(org, d, off)
+    out = dict(tri_origins=org, tri_directions=d, tri_ray_offset=off, tri_points=pts, tri_ok=ok)
+
+    prob, _ = synthetic.make_ba_problem(10, 80, 4, seed=23, pos_sigma=0.0, rot_sigma=0.0)
+    prob.a["pts"][:, :3] += rng.normal(0, 0.05, (80, 3))
+    prob.a["pt_const"][[4, 40]] = 1
+    out.update(problem_arrays(prob, "in_"))
+    o = oracle_py.default_options()
+    o.use_inner_iterations = 0
+    res = np.zeros(80, capi.TRACK_BA_DTYPE)
+    refined = prob.a["pts"].copy()
+    for t in range(80):
+        if prob.a["pt_const"][t]:
+            res[t] = (0.0, 0.0, -1, 0)
+            continue
+        sub = single_track_problem(prob, t)
+        s = oracle_py.ba_solve(sub, o)
+        assert s["rc"] == 0 and s["success"] == 1
+        res[t] = (s["initial_cost"], s["final_cost"], s["num_iterations"], s["termination_type"])
+        refined[t] = sub.a["pts"][t]
+    out.update(track_results=res.view(np.uint8).reshape(80, -1), out_pts=refined)
+    np.savez_compressed(os.path.join(HERE, "track_stage_80tracks.npz"), **out)
+
+
 if __name__ == "__main__":
     ba_golden()
     ransac_golden()
+    track_golden()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")

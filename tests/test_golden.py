@@ -113,3 +113,51 @@ def test_cuda_ransac_matches_goldens_bit_for_bit(lib):
                                                 ns.ctypes.data_as(C.c_void_p), None))
     np.testing.assert_array_equal(ns, g["num_solutions"])
     assert np.array_equal(E, g["E"])
+
+
+# ---------------------------------------------------------------- track stage (triangulation + per-track BA)
+def _track_results(g):
+    return np.frombuffer(np.ascontiguousarray(g["track_results"]).tobytes(), dtype=capi.TRACK_BA_DTYPE)
+
+
+def test_oracle_reproduces_track_goldens(oracle):
+    import sys
+    sys.path.insert(0, GOLD)
+    from make_golden import single_track_problem
+    g = _load("track_stage_80tracks.npz")
+    pts, ok = oracle.triangulate_midpoint_batch(g["tri_origins"], g["tri_directions"], g["tri_ray_offset"])
+    np.testing.assert_array_equal(ok, g["tri_ok"])
+    np.testing.assert_array_equal(pts, g["tri_points"])
+    assert ok[5] == 0 and ok.sum() == 79
+    prob = _problem(g)
+    o = oracle.default_options()
+    o.use_inner_iterations = 0
+    want = _track_results(g)
+    for t in (0, 17, 63):
+        sub = single_track_problem(prob, t)
+        s = oracle.ba_solve(sub, o)
+        assert s["num_iterations"] == want[t]["num_iterations"]
+        assert abs(s["final_cost"] - want[t]["final_cost"]) <= 1e-12 * want[t]["final_cost"]
+        np.testing.assert_allclose(sub.a["pts"][t], g["out_pts"][t], rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_cuda_track_stage_matches_goldens(lib):
+    g = _load("track_stage_80tracks.npz")
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    org = np.ascontiguousarray(g["tri_origins"]); d = np.ascontiguousarray(g["tri_directions"]); off = np.ascontiguousarray(g["tri_ray_offset"])
+    pts = np.zeros((80, 4)); ok = np.zeros(80, np.uint8)
+    capi.check(lib.thb_triangulate_midpoint_batch(vp(org), vp(d), vp(off), 80, capi.THB_MEM_HOST, vp(pts), vp(ok), None))
+    np.testing.assert_array_equal(ok, g["tri_ok"])
+    np.testing.assert_allclose(pts, g["tri_points"], rtol=1e-12, atol=1e-13)
+    prob = _problem(g)
+    o = capi.default_options(lib)
+    o.use_inner_iterations = 0
+    res = np.zeros(80, capi.TRACK_BA_DTYPE)
+    p = prob.struct()
+    capi.check(lib.thb_ba_tracks_batch(C.byref(p), C.byref(o), vp(res), None))
+    want = _track_results(g)
+    np.testing.assert_array_equal(res["num_iterations"], want["num_iterations"])
+    np.testing.assert_array_equal(res["termination_type"], want["termination_type"])
+    np.testing.assert_allclose(res["final_cost"], want["final_cost"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(prob.a["pts"], g["out_pts"], rtol=1e-6, atol=1e-9)
