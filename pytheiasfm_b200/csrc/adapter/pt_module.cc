@@ -281,6 +281,23 @@ struct Flat {
   std::vector<int32_t> cam_group, intr_model, obs_cam, obs_pt;
 };
 
+// SetSolverOptions, bundle_adjuster.cc:63-89
+ThbBaOptions MapOptions(const BundleAdjustmentOptions& o, bool force_no_inner) {
+  ThbBaOptions opt;
+  thb_ba_default_options(&opt);
+  opt.loss_function_type = o.loss_function_type; opt.robust_loss_width = o.robust_loss_width;
+  opt.use_homogeneous_point_parametrization = o.use_homogeneous_point_parametrization ? 1 : 0;
+  opt.use_inner_iterations = (!force_no_inner && o.use_inner_iterations) ? 1 : 0;
+  opt.max_num_iterations = o.max_num_iterations;
+  opt.function_tolerance = o.function_tolerance; opt.gradient_tolerance = o.gradient_tolerance;
+  opt.parameter_tolerance = o.parameter_tolerance; opt.max_trust_region_radius = o.max_trust_region_radius;
+  opt.max_solver_time_in_seconds = o.max_solver_time_in_seconds; opt.verbose = o.verbose;
+  opt.linear_solver = THB_SOLVER_SCHUR_CHOLESKY;                           // every exact ceres solver type maps here
+  if (o.linear_solver_type == ITERATIVE_SCHUR || o.linear_solver_type == CGNR)
+    throw std::runtime_error("iterative linear solvers are not implemented; use SPARSE_SCHUR / DENSE_SCHUR / DENSE_QR");
+  return opt;
+}
+
 // What BundleAdjuster::AddView / AddTrack register (bundle_adjuster.cc:116-221), flattened.
 BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vector<ViewId>& views, const std::vector<TrackId>& tracks,
                               Reconstruction* r, bool force_no_inner) {
@@ -361,18 +378,7 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   p.intr = f.intr.data(); p.intr_model = f.intr_model.data(); p.intr_const = f.intr_const.data();
   p.pts = f.pts.data(); p.pt_const = f.pt_const.data();
   p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data(); p.obs_sqrt_info = f.obs_si.data();
-  ThbBaOptions opt;
-  thb_ba_default_options(&opt);                                            // SetSolverOptions, bundle_adjuster.cc:63-89
-  opt.loss_function_type = o.loss_function_type; opt.robust_loss_width = o.robust_loss_width;
-  opt.use_homogeneous_point_parametrization = o.use_homogeneous_point_parametrization ? 1 : 0;
-  opt.use_inner_iterations = (!force_no_inner && o.use_inner_iterations) ? 1 : 0;
-  opt.max_num_iterations = o.max_num_iterations;
-  opt.function_tolerance = o.function_tolerance; opt.gradient_tolerance = o.gradient_tolerance;
-  opt.parameter_tolerance = o.parameter_tolerance; opt.max_trust_region_radius = o.max_trust_region_radius;
-  opt.max_solver_time_in_seconds = o.max_solver_time_in_seconds; opt.verbose = o.verbose;
-  opt.linear_solver = THB_SOLVER_SCHUR_CHOLESKY;                           // every exact ceres solver type maps here
-  if (o.linear_solver_type == ITERATIVE_SCHUR || o.linear_solver_type == CGNR)
-    throw std::runtime_error("iterative linear solvers are not implemented; use SPARSE_SCHUR / DENSE_SCHUR / DENSE_QR");
+  const ThbBaOptions opt = MapOptions(o, force_no_inner);
   ThbBaSummary s;
   int rc;
   {
@@ -517,6 +523,122 @@ void PinholePixelToNormalized(const double K[7], const double px[2], double out[
   }
   out[0] = ux / 1.0; out[1] = uy / 1.0;
 }
+// ---- TrackEstimator (sfm/estimate_track.{h,cc}) over thb_estimate_tracks_batch: every unestimated track in ONE launch ------
+struct TrackEstimatorOptions {                                                      // estimate_track.h:59-84
+  int num_threads = 1;
+  double max_acceptable_reprojection_error_pixels = 5.0, min_triangulation_angle_degrees = 3.0;
+  bool bundle_adjustment = true;
+  BundleAdjustmentOptions ba_options;
+  int multithreaded_step_size = 100;
+  int triangulation_method = 0;                                                     // TriangulationMethodType::MIDPOINT
+};
+struct TrackEstimatorSummary {                                                      // estimate_track.h:86-96
+  int input_num_estimated_tracks = 0, num_triangulation_attempts = 0;
+  std::unordered_set<TrackId> estimated_tracks;
+  int num_bad_angles = 0, num_failed_triangulations = 0, num_bad_reprojections = 0; // ADDITIVE: the counters the reference only logs
+};
+struct TrackEstimator {
+  TrackEstimatorOptions options;
+  Reconstruction* recon;
+  TrackEstimator(const TrackEstimatorOptions& o, Reconstruction* r) : options(o), recon(r) {}
+
+  TrackEstimatorSummary EstimateAllTracks() {                                       // estimate_track.cc:124-139
+    std::vector<TrackId> ids; std::unordered_set<TrackId> seen;
+    for (ViewId v : recon->view_order) {
+      const View& view = recon->views.at(v);
+      if (!view.estimated) continue;
+      for (TrackId t : view.track_order) if (seen.insert(t).second) ids.push_back(t);
+    }
+    return EstimateTracks(ids);
+  }
+
+  TrackEstimatorSummary EstimateTracks(const std::vector<TrackId>& track_ids) {    // estimate_track.cc:141-203 + :209-321
+    const BundleAdjustmentOptions& bo = options.ba_options;
+    if (options.triangulation_method != 0) throw std::runtime_error("only TriangulationMethodType.MIDPOINT is implemented");
+    if (bo.use_inverse_depth_parametrization) throw std::runtime_error("use_inverse_depth_parametrization is not implemented");
+    TrackEstimatorSummary sum;
+    Flat f;
+    std::vector<double> rays;
+    for (TrackId t : track_ids) {
+      auto ti = recon->tracks.find(t);
+      if (ti == recon->tracks.end()) throw std::invalid_argument("unknown track id");
+      if (ti->second.estimated) { ++sum.input_num_estimated_tracks; continue; }
+      if (f.track_index.count(t)) continue;
+      const int pi = (int)f.track_ids.size();
+      f.track_index[t] = pi; f.track_ids.push_back(t);
+      f.pts.insert(f.pts.end(), ti->second.point, ti->second.point + 4);
+      for (ViewId v : ti->second.views) {                                           // GetObservationsFromTrackViews, :57-90
+        auto vi = recon->views.find(v);
+        if (vi == recon->views.end() || !vi->second.estimated) continue;
+        View& view = vi->second;
+        int ci;
+        auto it = f.view_index.find(v);
+        if (it != f.view_index.end()) ci = it->second;
+        else {
+          ci = (int)f.view_ids.size();
+          f.view_index[v] = ci; f.view_ids.push_back(v);
+          f.cam_ext.insert(f.cam_ext.end(), view.camera.ext, view.camera.ext + 6);
+          Intrinsics* in = view.camera.intr.get();
+          if (in->model != THB_MODEL_PINHOLE) throw std::runtime_error("TrackEstimator: PixelToUnitDepthRay is implemented for PINHOLE cameras only");
+          if (!f.group_index.count(in)) {
+            f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
+            f.intr_model.push_back(in->model);
+            f.intr.insert(f.intr.end(), in->params, in->params + THB_INTR_STRIDE);
+          }
+          f.cam_group.push_back(f.group_index[in]);
+        }
+        const Feature& feat = view.features.at(t);
+        f.obs_cam.push_back(ci); f.obs_pt.push_back(pi);
+        f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
+        f.obs_si.push_back(1.0 / std::sqrt(feat.cov[0])); f.obs_si.push_back(1.0 / std::sqrt(feat.cov[3]));
+        // Camera::PixelToUnitDepthRay(feature).normalized() (camera.cc:218-226)
+        double n[2], R[9];
+        PinholePixelToNormalized(view.camera.intr->params, feat.point, n);
+        AngleAxisToRotation(view.camera.ext + 3, R);
+        const double u[3] = {n[0], n[1], 1.0};
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = R[0 * 3 + k] * u[0] + R[1 * 3 + k] * u[1] + R[2 * 3 + k] * u[2];   // R^T u
+        const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+        for (int k = 0; k < 3; ++k) rays.push_back(d[k] / nd);
+      }
+    }
+    sum.num_triangulation_attempts = (int)f.track_ids.size();
+    if (f.track_ids.empty()) return sum;
+    ThbBaProblem p;
+    std::memset(&p, 0, sizeof(p));
+    p.num_cameras = (int)f.view_ids.size(); p.num_groups = (int)f.groups.size();
+    p.num_points = (int)f.track_ids.size(); p.num_observations = (int)f.obs_cam.size();
+    p.memory_space = THB_MEM_HOST;
+    p.cam_ext = f.cam_ext.data(); p.cam_group = f.cam_group.data(); p.intr = f.intr.data(); p.intr_model = f.intr_model.data();
+    p.pts = f.pts.data(); p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data(); p.obs_sqrt_info = f.obs_si.data();
+    const ThbBaOptions opt = MapOptions(bo, true);                                  // BundleAdjustTrack: no inner iterations
+    ThbTrackEstimatorOptions eo;
+    eo.max_acceptable_reprojection_error_pixels = options.max_acceptable_reprojection_error_pixels;
+    eo.min_triangulation_angle_degrees = options.min_triangulation_angle_degrees;
+    eo.bundle_adjustment = options.bundle_adjustment ? 1 : 0; eo.reserved0 = 0;
+    std::vector<int32_t> status(f.track_ids.size());
+    int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = thb_estimate_tracks_batch(&p, rays.data(), &eo, &opt, status.data(), nullptr, nullptr);
+    }
+    Check(rc);
+    for (size_t i = 0; i < f.track_ids.size(); ++i) {
+      Track& tr = recon->tracks.at(f.track_ids[i]);
+      switch (status[i]) {
+        case THB_TRACK_ESTIMATED: std::copy_n(&f.pts[4 * i], 4, tr.point); tr.estimated = true; sum.estimated_tracks.insert(f.track_ids[i]); break;
+        case THB_TRACK_BAD_ANGLE: ++sum.num_bad_angles; break;
+        case THB_TRACK_FAILED_TRIANGULATION: ++sum.num_failed_triangulations; break;
+        case THB_TRACK_BAD_REPROJECTION: ++sum.num_bad_reprojections; break;
+        default: break;
+      }
+    }
+    std::vector<TrackId> done(sum.estimated_tracks.begin(), sum.estimated_tracks.end());
+    UpdateInverseDepth(done, recon);                                                // bundle_adjustment.cc:69-83, 283
+    return sum;
+  }
+};
+
 // reconstruction_estimator_utils.cc:98-110
 double ComputeResolutionScaledThreshold(double threshold_pixels, int w, int h) {
   if (w == 0 && h == 0) return threshold_pixels;
@@ -791,6 +913,30 @@ PYBIND11_MODULE(_pt, m) {
     info.visibility_score = 0;
     return py::make_tuple(true, info, sum.inliers);
   });
+
+  // sfm.cc:1095-1135
+  py::class_<TrackEstimatorOptions>(sfm, "TrackEstimatorOptions")
+      .def(py::init<>())
+      .def_readwrite("num_threads", &TrackEstimatorOptions::num_threads)
+      .def_readwrite("max_acceptable_reprojection_error_pixels", &TrackEstimatorOptions::max_acceptable_reprojection_error_pixels)
+      .def_readwrite("min_triangulation_angle_degrees", &TrackEstimatorOptions::min_triangulation_angle_degrees)
+      .def_readwrite("bundle_adjustment", &TrackEstimatorOptions::bundle_adjustment)
+      .def_readwrite("ba_options", &TrackEstimatorOptions::ba_options)
+      .def_readwrite("multithreaded_step_size", &TrackEstimatorOptions::multithreaded_step_size)
+      .def_readwrite("triangulation_method", &TrackEstimatorOptions::triangulation_method);
+  py::class_<TrackEstimatorSummary>(sfm, "TrackEstimatorSummary")
+      .def_readonly("input_num_estimated_tracks", &TrackEstimatorSummary::input_num_estimated_tracks)
+      .def_readonly("num_triangulation_attempts", &TrackEstimatorSummary::num_triangulation_attempts)
+      .def_readonly("estimated_tracks", &TrackEstimatorSummary::estimated_tracks)
+      .def_readonly("num_bad_angles", &TrackEstimatorSummary::num_bad_angles)
+      .def_readonly("num_failed_triangulations", &TrackEstimatorSummary::num_failed_triangulations)
+      .def_readonly("num_bad_reprojections", &TrackEstimatorSummary::num_bad_reprojections);
+  py::class_<TrackEstimator>(sfm, "TrackEstimator")
+      .def(py::init<const TrackEstimatorOptions&, Reconstruction*>(), py::keep_alive<1, 3>())
+      .def("EstimateAllTracks", &TrackEstimator::EstimateAllTracks)
+      .def("EstimateTracks", [](TrackEstimator& e, const std::unordered_set<TrackId>& ids) {
+        return e.EstimateTracks(std::vector<TrackId>(ids.begin(), ids.end()));
+      });
 
   // triangulation_wrapper.h:15-17, sfm.cc:854: (success, homogeneous point). One track per call here; the batched C-ABI entry
   // (all tracks of a reconstruction in one launch) is what a TrackEstimator replacement calls.

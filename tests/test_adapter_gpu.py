@@ -273,3 +273,45 @@ def test_TriangulateMidpoint():
     np.testing.assert_allclose(p[:3] / p[3], X, rtol=1e-12)
     with pytest.raises(ValueError):
         pt.sfm.TriangulateMidpoint(origins[:1], dirs[:1])
+
+
+def test_TrackEstimator_EstimateAllTracks():
+    """pt.sfm.TrackEstimator (sfm.cc:1102-1135; estimate_track_test.cc's scenario: known cameras, tracks reset to unestimated):
+    every track with enough views is re-triangulated and bundle adjusted to its ground-truth position in one launch."""
+    gen = RandomReconGenerator(seed=7)
+    gen.generate_random_recon(nr_views=8, nr_tracks=120, pixel_noise=0.2)
+    recon = gen.recon
+    truth = {}
+    for tid in recon.TrackIds():
+        tr = recon.MutableTrack(tid)
+        truth[tid] = tr.Point()[:3] / tr.Point()[3]
+        tr.SetPoint(np.array([0.0, 0.0, 0.0, 1.0]))
+        tr.SetIsEstimated(False)
+    keep_estimated = recon.TrackIds()[:3]
+    for tid in keep_estimated:
+        recon.MutableTrack(tid).SetPoint(np.append(truth[tid], 1.0))
+        recon.MutableTrack(tid).SetIsEstimated(True)
+    opts = pt.sfm.TrackEstimatorOptions()
+    assert (opts.max_acceptable_reprojection_error_pixels, opts.min_triangulation_angle_degrees, opts.bundle_adjustment) == (5.0, 3.0, True)
+    est = pt.sfm.TrackEstimator(opts, recon)
+    summary = est.EstimateAllTracks()
+    seen = {t for v in recon.ViewIds() for t in recon.View(v).TrackIds()}
+    assert summary.input_num_estimated_tracks == len(set(keep_estimated) & seen)
+    assert summary.num_triangulation_attempts == len(seen) - summary.input_num_estimated_tracks
+    multi = [t for t in seen if recon.Track(t).NumViews() >= 2 and t not in keep_estimated]
+    assert len(summary.estimated_tracks) >= 0.9 * len(multi)
+    assert (len(summary.estimated_tracks) + summary.num_bad_angles + summary.num_failed_triangulations + summary.num_bad_reprojections
+            == summary.num_triangulation_attempts)
+    for tid in recon.TrackIds():
+        tr = recon.Track(tid)
+        if tid in summary.estimated_tracks:
+            assert tr.IsEstimated()
+            p = tr.Point()
+            assert np.linalg.norm(p[:3] / p[3] - truth[tid]) < 0.05
+            assert tr.InverseDepth() > 0
+        elif tid not in keep_estimated:
+            assert not tr.IsEstimated()
+            np.testing.assert_array_equal(tr.Point(), [0.0, 0.0, 0.0, 1.0])
+    # a second pass has nothing left to attempt among the estimated ones
+    again = pt.sfm.TrackEstimator(opts, recon).EstimateTracks(set(summary.estimated_tracks))
+    assert again.num_triangulation_attempts == 0 and again.input_num_estimated_tracks == len(summary.estimated_tracks)
