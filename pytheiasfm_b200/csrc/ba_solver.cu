@@ -212,15 +212,16 @@ int SmCount() {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   return sms;
 }
-// The shared-camera K1 (k_jacobian_sc) pays one copy of the camera table per SM: used when the table fits in shared memory and
-// every SM gets at least eight rounds of observations. THB_K1_MODE=gather forces the L1-gather kernel (A/B timing),
+// The shared-camera K1 (k_jacobian_sc) pays one copy of the camera table per SM; measured faster than the gather kernel from
+// 50k observations (12.1 vs 15.9 us) to 1M (44.6 vs 58.9 us), profiles/r01_k1_ab_scale.txt: used whenever the table fits in
+// shared memory and there are at least 32k observations. THB_K1_MODE=gather forces the L1-gather kernel (A/B timing),
 // THB_K1_MODE=shared the shared-camera kernel whenever the table fits (parity tests at small sizes).
 bool UseSharedCameraK1(const ThbBaSession* s) {
   if (s->nc > K1S_MAX_CAMS) return false;
   const char* e = getenv("THB_K1_MODE");
   if (e && !strcmp(e, "gather")) return false;
   if (e && !strcmp(e, "shared")) return true;
-  return (long long)s->no >= 8LL * 512 * SmCount();
+  return s->no >= 32768;
 }
 template <int MODEL, int PD, int NK, bool ROBUST>
 void LaunchJacobianKernel(ThbBaSession* s, const double* cs, const double* ps, const double* is, double* ji) {

@@ -12,7 +12,7 @@ lib = capi.load_library()
 # THB_K1_AB_MODEL=<THB_MODEL_* id>, THB_K1_AB_LOSS=<THB_LOSS_* id>, THB_K1_AB_EUCLID=1: C2-shaped problem on another instantiation
 MODEL = int(os.environ.get("THB_K1_AB_MODEL", capi.MODEL_PINHOLE)); LOSS = int(os.environ.get("THB_K1_AB_LOSS", capi.LOSS_TRIVIAL))
 if MODEL == capi.MODEL_PINHOLE:
-    prob, _ = synthetic.config_c2(scale=1.0)
+    prob, _ = synthetic.config_c2(scale=float(os.environ.get("THB_K1_AB_SCALE", "1.0")))
 else:
     prob, _ = synthetic.make_ba_problem(1000, 100000, 10, models=(MODEL,), seed=2, num_rings=10, ring_radius=24.0, box=(10.0, 10.0, 3.0))
 dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
@@ -34,4 +34,5 @@ for spec in (sys.argv[1:] or ["gather", "shared", "gather", "shared"]):
     for rep in range(2):
         capi.check(lib.thb_ba_time_jacobian(sess, 20, 1, C.byref(ms)))
     capi.check(lib.thb_ba_finish(sess, None))
-    print("K1 model %d loss %d %-8s %.2f us  %.0f GB/s (203.3 MB algorithmic)" % (MODEL, LOSS, spec, ms.value * 1e3, 203.304e6 / (ms.value * 1e-3) / 1e9), flush=True)
+    ab = prob.num_observations * 200 + prob.num_cameras * 104 + prob.num_points * 32
+    print("K1 model %d loss %d obs %d %-8s %.2f us  %.0f GB/s (%.1f MB algorithmic)" % (MODEL, LOSS, prob.num_observations, spec, ms.value * 1e3, ab / (ms.value * 1e-3) / 1e9, ab / 1e6), flush=True)
