@@ -33,9 +33,31 @@ UNIT = "iterations/s"
 
 
 def quiet_nccl():
-    """NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; rank 0's stdout must be the one JSON line."""
+    """NCCL prints its version banner on STDOUT (any NCCL_DEBUG level from VERSION up); rank 0's stdout must be the one JSON line."""
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
+
+
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Everything libraries write to file descriptor 1 during the run (NCCL's banner, OpenMP notices) goes to stderr; the JSON
+    line is written to the real stdout by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
 
 
 def workload_config(args):
@@ -185,7 +207,7 @@ def run_reference(args, rank, world):
                                        "(the reference itself needs Ceres+Eigen, absent here), wall %.1f s" % (args.steps, nsolves, wall)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 RANSAC_METRIC = "RANSAC pair-verifications/s (10k pairs x 2k correspondences, FivePointRelativePose)"
@@ -216,12 +238,12 @@ def run_ransac(args, rank, local_rank, world):
         secs = (time.time() - t0) / args.steps
         value = sample / secs
         cores = os.cpu_count() or 1
-        print(json.dumps({"impl": "reference", "metric": RANSAC_METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        emit(({"impl": "reference", "metric": RANSAC_METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True,
                           "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": ransac_config(total_pairs),
                           "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
                                            "sample": "%d of the %d pairs per step, oracle port (OpenMP over pairs; the reference's own loop is single-threaded)" % (sample, total_pairs)},
-                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         return
     import torch
     import torch.distributed as dist
@@ -320,7 +342,7 @@ def run_ransac(args, rank, local_rank, world):
             t0 = time.time(); oracle_py.ransac_relpose_batch(sample, po); dt = time.time() - t0
             line["cpu_baseline"] = {"value": 64 / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "first 64 pairs of the workload, oracle/ransac_oracle.cc, OpenMP over pairs"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -340,6 +362,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    capture_stdout()
     if args.workload == "ransac":
         run_ransac(args, rank, local_rank, world)
         return
@@ -466,7 +489,7 @@ def main():
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(prob, iters=2)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
