@@ -480,6 +480,14 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic_from_profiles(), "peak_source": peak_src + ", burst",
                          "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},
+            # the kernel that takes most of the step (K4, dense FP64 Cholesky of the reduced camera system: n^3/3 flops per
+            # iteration) against the FP64 rate measured on this GPU class (scratch/k4_micro.cu)
+            "roofline_k4": {"bound": "fp64", "kernel": "DenseChol (K4: chol_dp / chol_update* kernels, two streams)",
+                            "achieved": (6.0 * prob.num_cameras) ** 3 / 3.0 / (phase["ms_solve"] * 1e-3) / 1e12 if phase["ms_solve"] > 0 else None,
+                            "peak": 37.0, "unit": "TFLOP/s",
+                            "frac": (6.0 * prob.num_cameras) ** 3 / 3.0 / (phase["ms_solve"] * 1e-3) / 1e12 / 37.0 if phase["ms_solve"] > 0 else None,
+                            "peak_source": "measured DFMA/DMMA issue rate (scratch/k4_micro.cu); MEASURED_PEAKS.json has no FP64 figure",
+                            "share_of_step": phase["ms_solve"] / (ms / K)},
             "phase_ms_per_step": {"jacobian": phase["ms_jacobian"], "normal_equations": phase["ms_normal"],
                                   "reduced_solve": phase["ms_solve"], "update_and_cost": phase["ms_update"]},
             "solves": len(sums), "iterations_per_solve": [x["num_iterations"] for x in sums], "setup_ms_per_solve": setup_ms,
