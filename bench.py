@@ -2,7 +2,9 @@
 """Headline benchmark: BA iterations/s on BASELINE.json configs[1]
 (synthetic Pinhole reconstruction, 1k cameras / 100k points / 1M observations).
 
-  python bench.py --gpus N --steps K --warmup W          our arm (CUDA path through the C-ABI)
+  python bench.py --gpus N --steps K --warmup W          our arm (CUDA path through the C-ABI): the line is the BA half of
+                                                          the metric, its `ransac` object the RANSAC half (C4, pairs/s,
+                                                          strong-scaled over the N ranks)
   python bench.py --impl reference --gpus N ...          the reference's CPU algorithm (oracle restatement,
                                                           all host cores) on the same workload/metric
 
@@ -164,8 +166,14 @@ def traffic_from_profiles():
     return None
 
 
+def oracle_threads():
+    """torchrun exports OMP_NUM_THREADS=1: the CPU arm sets its team size explicitly and reports what it got."""
+    from oracle import oracle_py
+    return oracle_py.set_num_threads(os.cpu_count() or 1)
+
+
 def oracle_solves(prob, iters):
-    """The oracle under the same protocol; returns (iterations/s over wall time, wall seconds, #solves)."""
+    """The oracle under the same protocol; returns (iterations/s over wall time, wall seconds, summaries)."""
     from oracle import oracle_py
     cur = {}
 
@@ -175,17 +183,55 @@ def oracle_solves(prob, iters):
     t0 = time.time()
     sums = run_solves(lambda rem: oracle_py.ba_solve(cur["p"], make_options(oracle_py.default_options(), rem)), restore, iters)
     wall = time.time() - t0
-    return iters / wall, wall, len(sums)
+    return iters / wall, wall, sums
 
 
 def cpu_baseline(prob, iters=2):
-    """The oracle (CPU restatement of the reference algorithm, OpenMP over all host cores) on the same
+    """The oracle (CPU restatement of the reference algorithm, OpenMP over the host cores) on the same
     workload for the first `iters` LM iterations of a solve: a reported baseline, not the target."""
-    value, wall, _ = oracle_solves(prob, iters)
-    cores = os.cpu_count() or 1
-    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+    threads = oracle_threads()
+    value, wall, sums = oracle_solves(prob, iters)
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "first %d LM iterations of one solve of the full C2 workload, setup included "
-                      "(oracle/ba_oracle.cc, %d OpenMP threads, %.1f s)" % (iters, cores, wall)}
+                      "(oracle/ba_oracle.cc, %d OpenMP threads used of %d host cores, %.1f s)" % (iters, threads, os.cpu_count() or 1, wall),
+            "iter_cost": sums[0]["iter_cost"]}
+
+
+RANSAC_METRIC = "RANSAC pair-verifications/s (10k pairs x 2k correspondences, FivePointRelativePose)"
+PAIR_BLOCK = 8       # pairs per block of the block-cyclic pair schedule
+C4_SEED = 21
+# FP64 operations per unit of work of k_ransac<RelPoseEst>, measured with ncu's executed-instruction counters
+# (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, fma = 2) - profiles/r02_ransac_flop_calibration.txt
+FLOP_PER_SAMPLE = 50.0e3   # five-point solve of one minimal sample
+FLOP_PER_MODEL = 3.0e3     # essential-matrix decomposition + cheirality vote of one candidate
+FLOP_PER_DATUM = 75.0      # cheirality test + Sampson distance + cost of one correspondence
+
+
+def ransac_flops(stats):
+    return stats["samples_solved"] * FLOP_PER_SAMPLE + stats["models_scored"] * FLOP_PER_MODEL + stats["data_scored"] * FLOP_PER_DATUM
+
+
+def ransac_config(num_pairs, world):
+    return {"workload": "C4 synthetic EstimateRelativePose: %d pairs x 2000 correspondences, 60%% inliers, sigma 1e-3" % num_pairs,
+            "ransac": "RANSAC, error_thresh (2e-3)^2, failure_probability 1e-4, iterations 10..1000, MLE, no LO, per-pair seed",
+            "parallelism": "pair table dealt block-cyclically (blocks of %d pairs) over %d rank(s); per-rank device-side pair counter; "
+                           "one all_gather per step of the result records + bit-packed inlier masks" % (PAIR_BLOCK, world),
+            "l2": "each step re-reads the rank's correspondences (640 MB / ranks, larger than the 126 MB L2 up to 4 ranks)"}
+
+
+def oracle_ransac_sample(num_pairs, steps):
+    """Oracle port on the first `num_pairs` pairs of the C4 table, all host threads; returns (pairs/s, threads, results, masks, batch)."""
+    from oracle import oracle_py
+    from pytheiasfm_b200 import synthetic
+    threads = oracle_threads()
+    batch, _ = synthetic.make_pair_batch_indexed(range(num_pairs), n=2000, seed=C4_SEED)
+    params = synthetic.c4_params(oracle_py.ransac_default_params())
+    t0 = time.time()
+    for _ in range(steps):
+        rc, res, mask = oracle_py.ransac_relpose_batch(batch, params, threads)
+    secs = (time.time() - t0) / steps
+    assert rc == 0
+    return num_pairs / secs, threads, res, mask, batch
 
 
 def run_reference(args, rank, world):
@@ -194,197 +240,193 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from pytheiasfm_b200 import synthetic
-    prob, _ = synthetic.config_c2(scale=args.scale)
-    if args.warmup > 0:
-        oracle_solves(prob, 1)
-    value, wall, nsolves = oracle_solves(prob, args.steps)
-    cores = os.cpu_count() or 1
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d LM iterations (%d solves) of the full workload, oracle port of the reference algorithm "
-                                       "(the reference itself needs Ceres+Eigen, absent here), wall %.1f s" % (args.steps, nsolves, wall)},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    threads = oracle_threads()
+    line = {"impl": "reference"}
+    if args.workload in ("both", "ba"):
+        prob, _ = synthetic.config_c2(scale=args.scale)
+        if args.warmup > 0:
+            oracle_solves(prob, 1)
+        value, wall, sums = oracle_solves(prob, args.steps)
+        line.update({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                     "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+                     "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                                      "sample": "%d LM iterations (%d solves) of the full workload, oracle port of the reference algorithm "
+                                                "(the reference itself needs Ceres+Eigen, absent here), %d OpenMP threads used of %d host cores, wall %.1f s"
+                                                % (args.steps, len(sums), threads, os.cpu_count() or 1, wall)},
+                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0, "final_cost": sums[0]["final_cost"], "initial_cost": sums[0]["initial_cost"],
+                     "iterations_per_solve": [x["num_iterations"] for x in sums]})
+    if args.workload in ("both", "ransac"):
+        sample = min(args.pairs, args.ref_pairs)
+        if args.warmup > 0:
+            oracle_ransac_sample(min(sample, 16), 1)
+        value, threads, res, mask, _ = oracle_ransac_sample(sample, max(1, args.steps if args.workload == "ransac" else min(args.steps, 3)))
+        r = {"metric": RANSAC_METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "scaling": "strong", "higher_is_better": True,
+             "config": ransac_config(args.pairs, 1),
+             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                              "sample": "first %d of the %d pairs per step, oracle port, OpenMP over pairs with %d threads of %d host cores "
+                                        "(the reference's own loop is single-threaded)" % (sample, args.pairs, threads, os.cpu_count() or 1)},
+             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+             "mean_ransac_iterations": float(res["num_iterations"].mean()), "total_inliers_sample": int(mask.sum())}
+        if args.workload == "ransac":
+            line.update(r)
+            line.update({"steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "vs_baseline": None, "dtype": "f64",
+                         "data": "synthetic", "gpu_launches": 0})
+        else:
+            line["ransac"] = r
     emit(line)
 
 
-RANSAC_METRIC = "RANSAC pair-verifications/s (10k pairs x 2k correspondences, FivePointRelativePose)"
-
-
-def ransac_config(num_pairs):
-    return {"workload": "C4 synthetic EstimateRelativePose: %d pairs x 2000 correspondences, 60%% inliers, sigma 1e-3" % num_pairs,
-            "ransac": "RANSAC, error_thresh (2e-3)^2, failure_probability 1e-4, iterations 10..1000, MLE, no LO, per-pair seed",
-            "parallelism": "pairs sharded over ranks (contiguous blocks), results all-gathered"}
-
-
-def run_ransac(args, rank, local_rank, world):
-    """Second headline metric: two-view RANSAC verification throughput. A step = the whole batch of pairs."""
-    import numpy as np
-    from pytheiasfm_b200 import capi, synthetic
-    total_pairs = args.pairs
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        from oracle import oracle_py
-        sample = min(total_pairs, 128)
-        batch, _ = synthetic.make_pair_batch(sample, n=2000, seed=21)
-        params = synthetic.c4_params(oracle_py.ransac_default_params())
-        oracle_py.ransac_relpose_batch(batch, params)  # warm-up
-        t0 = time.time()
-        for _ in range(args.steps):
-            oracle_py.ransac_relpose_batch(batch, params)
-        secs = (time.time() - t0) / args.steps
-        value = sample / secs
-        cores = os.cpu_count() or 1
-        emit(({"impl": "reference", "metric": RANSAC_METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
-                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs, "higher_is_better": True,
-                          "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": ransac_config(total_pairs),
-                          "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                                           "sample": "%d of the %d pairs per step, oracle port (OpenMP over pairs; the reference's own loop is single-threaded)" % (sample, total_pairs)},
-                          "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-        return
+def run_ransac_leg(args, lib, rank, local_rank, world, stream, K, W):
+    """Second half of the metric: two-view RANSAC verification throughput on C4, strong-scaled over the ranks. A step = the
+    whole pair table: every rank verifies the blocks it owns, packs the inlier masks to bits and one all_gather puts the
+    result records and masks of all pairs on every rank. Returns the `ransac` object (rank 0) or None."""
     import torch
     import torch.distributed as dist
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = capi.load_library()
-    # static block partition of the pair table by cumulative correspondence count (pytheiasfm_b200/sharding.py)
-    from pytheiasfm_b200 import sharding
-    full, _ = synthetic.make_pair_batch(total_pairs, n=2000, seed=21)
-    ranges = sharding.partition_by_work(full.pair_offset, world)
-    mine, lo, hi = sharding.shard_batch(full, rank, world)
-    params = synthetic.c4_params(capi.ThbRansacParams())
-    stream = torch.cuda.current_stream()
+    from pytheiasfm_b200 import capi, sharding, synthetic
+    total_pairs = args.pairs
     sptr = C.c_void_p(stream.cuda_stream)
-    d_off = torch.from_numpy(mine.pair_offset).cuda(); d_corr = torch.from_numpy(mine.corr).cuda()
-    d_seed = torch.from_numpy(mine.seed.astype(np.int64)).cuda().to(torch.int32)
+    idx = sharding.block_cyclic_indices(total_pairs, rank, world, PAIR_BLOCK)
+    mine, _ = synthetic.make_pair_batch_indexed(idx, n=2000, seed=C4_SEED)
+    params = synthetic.c4_params(capi.ThbRansacParams())
     rec = capi.RELPOSE_DTYPE.itemsize
-    d_res = torch.zeros(mine.num_pairs * rec, dtype=torch.uint8, device="cuda")
-    d_mask = torch.zeros(int(mine.pair_offset[-1]), dtype=torch.uint8, device="cuda")
-    pad = max(h - l for l, h in ranges) * rec
-    gathered = [torch.zeros(pad, dtype=torch.uint8, device="cuda") for _ in range(world)]
-    sendbuf = torch.zeros(pad, dtype=torch.uint8, device="cuda")
-    b = capi.ThbPairBatch(); b.num_pairs = mine.num_pairs; b.memory_space = capi.THB_MEM_DEVICE
-    b.pair_offset = d_off.data_ptr(); b.corr = d_corr.data_ptr(); b.seed = d_seed.data_ptr()
-
-    def step():
-        capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), C.c_void_p(d_res.data_ptr()), C.c_void_p(d_mask.data_ptr()), sptr))
-        if world > 1:  # one collective per batch: fixed-size result records, padded to the largest block
-            sendbuf[: d_res.numel()] = d_res
-            dist.all_gather(gathered, sendbuf)
-
-    W, K = max(args.warmup, 3), args.steps
-    for _ in range(W):
-        step()
-    sampler = ClockSampler(local_rank); sampler.start()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    sampler.stop_flag.set(); sampler.join()
-    # end to end: host buffers in, results + inlier masks out
-    # pinned host buffers (the contract's e2e: H2D from pinned memory, D2H of the results inside the timed region)
+    npair, ncorr = mine.num_pairs, int(mine.pair_offset[-1])
+    woff = sharding.mask_word_offsets(mine.pair_offset)
+    nwords = int(woff[-1])
     pin_corr = torch.from_numpy(mine.corr).pin_memory(); pin_off = torch.from_numpy(mine.pair_offset).pin_memory()
     pin_seed = torch.from_numpy(mine.seed.astype(np.int64)).to(torch.int32).pin_memory()
-    pin_res = torch.zeros(mine.num_pairs * rec, dtype=torch.uint8).pin_memory()
-    pin_mask = torch.zeros(int(mine.pair_offset[-1]), dtype=torch.uint8).pin_memory()
-    hb = capi.ThbPairBatch(); hb.num_pairs = mine.num_pairs; hb.memory_space = capi.THB_MEM_HOST
-    hb.pair_offset = pin_off.data_ptr(); hb.corr = pin_corr.data_ptr(); hb.seed = pin_seed.data_ptr()
-
-    def e2e_call():
-        capi.check(lib.thb_ransac_relpose_batch(C.byref(hb), C.byref(params), C.c_void_p(pin_res.data_ptr()), C.c_void_p(pin_mask.data_ptr()), sptr))
-    e2e_call()  # warm-up (pool growth)
-    torch.cuda.synchronize()
+    d_corr = torch.empty_like(pin_corr, device="cuda"); d_off = torch.empty_like(pin_off, device="cuda"); d_seed = torch.empty_like(pin_seed, device="cuda")
+    d_woff = torch.from_numpy(woff).cuda()
+    d_mask = torch.zeros(max(ncorr, 1), dtype=torch.uint8, device="cuda")
+    payload_bytes = npair * rec + nwords * 4
+    d_payload = torch.zeros(max(payload_bytes, 8), dtype=torch.uint8, device="cuda")  # [result records | packed mask words]
+    res_ptr = d_payload.data_ptr(); words_ptr = res_ptr + npair * rec
+    assert (npair * rec) % 8 == 0
     if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        e2e_call()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / K
-    res = np.frombuffer(pin_res.numpy().tobytes(), dtype=capi.RELPOSE_DTYPE); mask = pin_mask.numpy()
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        counts_t = torch.tensor([payload_bytes, npair, nwords], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros(3, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(allc, counts_t)
+        counts = [int(c[0]) for c in allc]
+    else:
+        counts = [payload_bytes]
+    pad = max(counts)
+    d_send = torch.zeros(pad, dtype=torch.uint8, device="cuda")
+    d_gather = torch.zeros(world * pad, dtype=torch.uint8, device="cuda")
+    pin_gather = torch.zeros(world * pad, dtype=torch.uint8).pin_memory()
+    b = capi.ThbPairBatch(); b.num_pairs = npair; b.memory_space = capi.THB_MEM_DEVICE
+    b.pair_offset = d_off.data_ptr(); b.corr = d_corr.data_ptr(); b.seed = d_seed.data_ptr()
+
+    def upload():
+        d_corr.copy_(pin_corr, non_blocking=True); d_off.copy_(pin_off, non_blocking=True); d_seed.copy_(pin_seed, non_blocking=True)
+
+    def step(from_host):
+        if from_host:
+            upload()
+        if npair > 0:
+            capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), C.c_void_p(res_ptr), C.c_void_p(d_mask.data_ptr()), sptr))
+            capi.check(lib.thb_pack_inlier_masks(C.c_void_p(d_mask.data_ptr()), C.c_void_p(d_off.data_ptr()), C.c_void_p(d_woff.data_ptr()),
+                                                 npair, capi.THB_MEM_DEVICE, C.c_void_p(words_ptr), sptr))
+        if world > 1:
+            d_send[:payload_bytes] = d_payload[:payload_bytes]
+            dist.all_gather_into_tensor(d_gather, d_send)
+            src = d_gather
+        else:
+            src = d_payload
+        if from_host:  # the verified table (records + masks of ALL pairs) back on the host of every rank
+            pin_gather[: src.numel()].copy_(src[: pin_gather.numel()], non_blocking=True)
+            stream.synchronize()
+
+    def timed(from_host):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            step(from_host)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    upload()
+    for _ in range(W):
+        step(False)
+    sampler = ClockSampler(local_rank); sampler.start()
+    ms = timed(False)
+    sampler.stop_flag.set(); sampler.join()
+    st = capi.ThbRansacStats()
+    capi.check(lib.thb_ransac_last_stats(C.byref(st)))
+    stats = st.as_dict()
+    step(True)  # warm-up of the host path
+    ms_e2e = timed(True)
+    peak = C.c_double(0.0)
+    capi.check(lib.thb_fp64_peak_tflops(5, C.byref(peak), sptr))
+    flops = ransac_flops(stats)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([flops, float(stats["iterations"]), float(stats["samples_solved"]), float(stats["models_scored"]), float(stats["data_scored"]), peak.value],
+                       dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        ms_max, e2e_max = float(t[0]), float(t[1])
-        iters = float(res["num_iterations"].mean())
-        # FP64 work actually done is data dependent (early abandonment); report the full-scoring upper bound
-        line = {"metric": RANSAC_METRIC, "value": total_pairs * K / (ms_max * 1e-3), "unit": "pairs/s", "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": ransac_config(total_pairs),
-                "e2e": {"value": total_pairs / e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": int(mine.corr.nbytes + mine.pair_offset.nbytes + mine.seed.nbytes),
-                        "d2h_bytes_per_step": int(res.nbytes + mask.nbytes)},
-                "gpu_launches": K, "mean_ransac_iterations": iters, "clocks": sampler.summary(),
-                "roofline": {"bound": "hbm", "kernel": "k_ransac_relpose", "achieved": (mine.corr.nbytes + mask.nbytes) / (ms_max / K * 1e-3) / 1e9,
-                             "peak": measured_peak_hbm()[0], "unit": "GB/s", "frac": (mine.corr.nbytes + mask.nbytes) / (ms_max / K * 1e-3) / 1e9 / measured_peak_hbm()[0],
-                             "traffic": None,
-                             "note": "not HBM-bound: each pair's 64 KB of correspondences is staged once in shared memory and re-scored ~10^2-10^3 times; the kernel is FP64-issue-bound (SURVEY 8d), MEASURED_PEAKS.json has no FP64 peak"}}
-        if not args.no_cpu_baseline:
-            from oracle import oracle_py
-            sample, _ = synthetic.make_pair_batch(64, n=2000, seed=21)
-            po = synthetic.c4_params(oracle_py.ransac_default_params())
-            t0 = time.time(); oracle_py.ransac_relpose_batch(sample, po); dt = time.time() - t0
-            line["cpu_baseline"] = {"value": 64 / dt, "unit": "pairs/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": "first 64 pairs of the workload, oracle/ransac_oracle.cc, OpenMP over pairs"}
-        emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank != 0:
+        return None
+    ms_max, e2e_max = float(t[0]), float(t[1])
+    # the gathered table of the last step, in global pair order
+    table = pin_gather.numpy()
+    res_all = np.zeros(total_pairs, capi.RELPOSE_DTYPE)
+    inliers_from_masks = np.zeros(total_pairs, np.int64)
+    wpp = (2000 + 31) // 32
+    for r in range(world):
+        ridx = sharding.block_cyclic_indices(total_pairs, r, world, PAIR_BLOCK)
+        seg = table[r * pad: r * pad + len(ridx) * rec + len(ridx) * wpp * 4]
+        res_all[ridx] = np.frombuffer(seg[: len(ridx) * rec].tobytes(), capi.RELPOSE_DTYPE)
+        words = np.frombuffer(seg[len(ridx) * rec:].tobytes(), np.uint32).reshape(len(ridx), wpp)
+        inliers_from_masks[ridx] = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little").sum(1)
+    assert (res_all["success"] == 1).all(), "a pair of the table was not verified"
+    assert np.array_equal(inliers_from_masks, res_all["num_inliers"].astype(np.int64)), "gathered bit-masks disagree with the result records"
+    flops_all, peak_all = float(tot[0]), float(tot[5])
+    sec = ms_max / K * 1e-3
+    obj = {"metric": RANSAC_METRIC, "value": total_pairs / sec, "unit": "pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "strong", "config": ransac_config(total_pairs, world),
+           "e2e": {"value": total_pairs * K / (e2e_max * 1e-3), "unit": "pairs/s",
+                   "h2d_bytes_per_step": int(mine.corr.nbytes + mine.pair_offset.nbytes + npair * 4), "d2h_bytes_per_step": int(world * pad),
+                   "note": "per rank: H2D of its pairs from pinned memory, k_ransac, mask packing, all_gather, D2H of the whole verified table"},
+           "gpu_launches": 2 * K, "mean_ransac_iterations": float(res_all["num_iterations"].mean()),
+           "total_inliers": int(res_all["num_inliers"].sum()), "pairs_verified": int(res_all["success"].sum()),
+           "gathered_bytes_per_step": int(world * pad), "clocks": sampler.summary(),
+           "work_per_step": {"iterations": float(tot[1]), "samples_solved": float(tot[2]), "models_scored": float(tot[3]), "data_scored": float(tot[4])},
+           "roofline": {"bound": "fp64", "kernel": "k_ransac<RelPoseEst> (persistent CTAs, one pair at a time per CTA)",
+                        "achieved": flops_all / sec / 1e12, "peak": peak_all, "unit": "TFLOP/s", "frac": flops_all / sec / 1e12 / peak_all if peak_all > 0 else None,
+                        "traffic": None, "flops_per_step": flops_all,
+                        "flop_model": {"per_sample_solved": FLOP_PER_SAMPLE, "per_model": FLOP_PER_MODEL, "per_datum_scored": FLOP_PER_DATUM,
+                                       "source": "device work counters (thb_ransac_last_stats) x ncu-calibrated FP64 ops per unit"},
+                        "peak_source": "thb_fp64_peak_tflops: DFMA issue-rate probe run in this process on every rank (summed); MEASURED_PEAKS.json has no FP64 figure"}}
+    if not args.no_cpu_baseline and world == 1:
+        n_chk = min(64, total_pairs)
+        value, threads, ores, omask, ob = oracle_ransac_sample(n_chk, 1)
+        # rank 0 owns every pair at N = 1: the first n_chk records / masks are those pairs
+        same = bool(np.array_equal(ores["num_iterations"], res_all["num_iterations"][:n_chk]) and
+                    np.array_equal(ores["num_inliers"], res_all["num_inliers"][:n_chk]) and
+                    np.array_equal(ores["essential_matrix"], res_all["essential_matrix"][:n_chk]))
+        obj["cpu_baseline"] = {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                               "sample": "first %d pairs of the workload, oracle/ransac_oracle.cc, OpenMP over pairs, %d threads of %d host cores" % (n_chk, threads, os.cpu_count() or 1)}
+        obj["parity"] = {"pairs_checked": n_chk, "identical_iterations_inliers_models": same}
+        assert same, "RANSAC results differ from the oracle on the checked pairs"
+    return obj
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="ba", choices=["ba", "ransac"], help="ba = headline (BASELINE configs[1]); ransac = configs[3]")
-    ap.add_argument("--pairs", type=int, default=10000)
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (debug only; 1.0 = BASELINE config)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    capture_stdout()
-    if args.workload == "ransac":
-        run_ransac(args, rank, local_rank, world)
-        return
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
+def run_ba_leg(args, lib, rank, local_rank, world, stream, K, W):
+    """First half of the metric: BA iterations/s on C2. Returns the line (rank 0) or None."""
     import torch
     import torch.distributed as dist
     from pytheiasfm_b200 import capi, synthetic
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        quiet_nccl()
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = capi.load_library()  # raises if the CUDA library is missing: no fallback
-
-    prob, _ = synthetic.config_c2(scale=args.scale)  # every rank: an identical replica
-    W, K = max(args.warmup, 3), args.steps
-    stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
+    prob, _ = synthetic.config_c2(scale=args.scale)  # every rank: an identical replica
 
     def make_arm(tensors, space):
         """(solve_once, restore) over one set of buffers; the solve refines cam_ext / pts in place, like the reference."""
@@ -443,6 +485,8 @@ def main():
     k1_ms = C.c_double(0.0)
     capi.check(lib.thb_ba_time_jacobian(sess, 20, 1, C.byref(k1_ms)))
     capi.check(lib.thb_ba_finish(sess, None))
+    fp64_peak = C.c_double(0.0)
+    capi.check(lib.thb_fp64_peak_tflops(5, C.byref(fp64_peak), sptr))
 
     # ---- end-to-end arm: the call a user makes, pinned HOST buffers, H2D + setup + iterations + D2H timed ----
     pin = {k: (None if v is None else torch.from_numpy(v.copy()).pin_memory()) for k, v in prob.a.items()}
@@ -463,40 +507,94 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, e2e_max = float(t[0]), float(t[1])
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_hbm()
+    ab = algorithmic_bytes_k1(prob)
+    achieved = ab / (k1_ms.value * 1e-3) / 1e9
+    k4_flops = (6.0 * prob.num_cameras) ** 3 / 3.0
+    line = {
+        "metric": METRIC, "value": world * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args),
+        "e2e": {"value": world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "note": "thb_ba_solve calls on pinned host buffers: H2D + device-side setup + iterations + D2H of the refined "
+                        "parameters; the per-iteration scalar read-back (96 B) is in d2h"},
+        "gpu_launches": launches_timed,
+        "roofline": {"bound": "hbm", "kernel": "k_jacobian_sc (K1, shared-memory camera table, materialised tangent-space Jacobian planes)",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic_from_profiles(), "peak_source": peak_src + ", burst",
+                     "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},
+        # the kernel that takes most of the step (K4, dense FP64 Cholesky of the reduced camera system: n^3/3 flops per
+        # iteration) against the FP64 FMA rate measured in this process (thb_fp64_peak_tflops)
+        "roofline_k4": {"bound": "fp64", "kernel": "DenseChol (K4: dense FP64 Cholesky of the reduced camera system)",
+                        "achieved": k4_flops / (phase["ms_solve"] * 1e-3) / 1e12 if phase["ms_solve"] > 0 else None,
+                        "peak": fp64_peak.value, "unit": "TFLOP/s",
+                        "frac": k4_flops / (phase["ms_solve"] * 1e-3) / 1e12 / fp64_peak.value if phase["ms_solve"] > 0 and fp64_peak.value > 0 else None,
+                        "peak_source": "thb_fp64_peak_tflops: DFMA issue-rate probe run in this process (DMMA m8n8k4 issues at the same rate); MEASURED_PEAKS.json has no FP64 figure",
+                        "share_of_step": phase["ms_solve"] / (ms / K)},
+        "phase_ms_per_step": {"jacobian": phase["ms_jacobian"], "normal_equations": phase["ms_normal"],
+                              "reduced_solve": phase["ms_solve"], "update_and_cost": phase["ms_update"]},
+        "solves": len(sums), "iterations_per_solve": [x["num_iterations"] for x in sums], "setup_ms_per_solve": setup_ms,
+        "successful_steps": sum(x["num_successful_steps"] for x in sums),
+        "final_cost": summ["final_cost"], "initial_cost": summ["initial_cost"],
+        "termination_type": summ["termination_type"], "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cb = cpu_baseline(prob, iters=2)
+        ours, theirs = summ["iter_cost"][:3], cb.pop("iter_cost")[:3]
+        rel = max(abs(a - b) / abs(b) for a, b in zip(ours, theirs))
+        line["cpu_baseline"] = cb
+        line["parity"] = {"iter_cost_gpu": ours, "iter_cost_oracle": theirs, "max_rel_diff": rel, "tolerance": 1e-6}
+        assert len(ours) == len(theirs) and rel <= 1e-6, ("BA cost sequence differs from the oracle", ours, theirs)
+    return line
 
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="both", choices=["both", "ba", "ransac"],
+                    help="both = the two halves of BASELINE.json's metric: BA (configs[1]) as the line, RANSAC (configs[3]) as its `ransac` object")
+    ap.add_argument("--pairs", type=int, default=10000)
+    ap.add_argument("--ref-pairs", type=int, default=512, help="--impl reference: pairs of the C4 table per step (bounded sample)")
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the BA workload (debug only; 1.0 = BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    capture_stdout()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pytheiasfm_b200 import capi
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        quiet_nccl()
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = capi.load_library()  # raises if the CUDA library is missing: no fallback
+    W, K = max(args.warmup, 3), args.steps
+    stream = torch.cuda.current_stream()
+    line = None
+    if args.workload in ("both", "ba"):
+        line = run_ba_leg(args, lib, rank, local_rank, world, stream, K, W)
+    if args.workload in ("both", "ransac"):
+        r = run_ransac_leg(args, lib, rank, local_rank, world, stream, K if args.workload == "ransac" else min(K, 10), W)
+        if rank == 0:
+            if line is None:
+                line = dict(r, vs_baseline=None, dtype="f64", data="synthetic")
+            else:
+                line["ransac"] = r
     if rank == 0:
-        peak, peak_src = measured_peak_hbm()
-        ab = algorithmic_bytes_k1(prob)
-        achieved = ab / (k1_ms.value * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": world * K / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": world * K / e2e_max, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-                    "note": "thb_ba_solve calls on pinned host buffers: H2D + device-side setup + iterations + D2H of the refined "
-                            "parameters; the per-iteration scalar read-back (96 B) is in d2h"},
-            "gpu_launches": launches_timed,
-            "roofline": {"bound": "hbm", "kernel": "k_jacobian_sc (K1, shared-memory camera table, materialised tangent-space Jacobian planes)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic_from_profiles(), "peak_source": peak_src + ", burst",
-                         "algorithmic_bytes": ab, "avg_launch_ms": k1_ms.value},
-            # the kernel that takes most of the step (K4, dense FP64 Cholesky of the reduced camera system: n^3/3 flops per
-            # iteration) against the FP64 rate measured on this GPU class (scratch/k4_micro.cu)
-            "roofline_k4": {"bound": "fp64", "kernel": "DenseChol (K4: chol_dp / chol_update* kernels, two streams)",
-                            "achieved": (6.0 * prob.num_cameras) ** 3 / 3.0 / (phase["ms_solve"] * 1e-3) / 1e12 if phase["ms_solve"] > 0 else None,
-                            "peak": 37.0, "unit": "TFLOP/s",
-                            "frac": (6.0 * prob.num_cameras) ** 3 / 3.0 / (phase["ms_solve"] * 1e-3) / 1e12 / 37.0 if phase["ms_solve"] > 0 else None,
-                            "peak_source": "measured DFMA/DMMA issue rate (scratch/k4_micro.cu); MEASURED_PEAKS.json has no FP64 figure",
-                            "share_of_step": phase["ms_solve"] / (ms / K)},
-            "phase_ms_per_step": {"jacobian": phase["ms_jacobian"], "normal_equations": phase["ms_normal"],
-                                  "reduced_solve": phase["ms_solve"], "update_and_cost": phase["ms_update"]},
-            "solves": len(sums), "iterations_per_solve": [x["num_iterations"] for x in sums], "setup_ms_per_solve": setup_ms,
-            "successful_steps": sum(x["num_successful_steps"] for x in sums),
-            "final_cost": summ["final_cost"], "initial_cost": summ["initial_cost"],
-            "termination_type": summ["termination_type"], "clocks": sampler.summary(),
-        }
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(prob, iters=2)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -248,6 +248,9 @@ typedef struct ThbRansacParams {
   int32_t use_lo;             /* must be 0: LO refinement (two-view BA) is "next", THB_E_UNSUPPORTED */
   int32_t lo_start_iterations;
   int32_t ransac_type;        /* RansacType: only RANSAC (0) (create_and_initialize_ransac_variant.h:52) */
+  int32_t use_tdd_test;       /* RansacParameters::use_Tdd_test: ComputeMaxIterations counts SampleSize + 1 draws */
+                              /* (sample_consensus_estimator.h:272-279); the test itself is unimplemented upstream */
+  int32_t reserved0;
 } ThbRansacParams;
 
 /* A batch of image pairs: pair p owns correspondences [pair_offset[p], pair_offset[p+1]). */
@@ -304,6 +307,35 @@ int thb_ransac_abspose_batch(const ThbPairBatch* batch, const ThbRansacParams* p
  */
 int thb_ransac_homography_batch(const ThbPairBatch* batch, const ThbRansacParams* params,
                                 ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream);
+
+/*
+ * Work counters of the last thb_ransac_*_batch call made by the calling host thread, accumulated on the device
+ * (one atomic add per pair): what the FP64 roofline of the RANSAC kernel is computed from.
+ */
+typedef struct ThbRansacStats {
+  uint64_t pairs;
+  uint64_t iterations;      /* RANSAC iterations consumed (sum of RansacSummary::num_iterations)                  */
+  uint64_t samples_solved;  /* minimal problems solved (a batch solves up to 128 per pair before the replay stops) */
+  uint64_t models_scored;   /* candidate models that entered scoring                                              */
+  uint64_t data_scored;     /* per-datum error evaluations actually executed (early abandonment included)         */
+  uint64_t reserved0;
+} ThbRansacStats;
+int thb_ransac_last_stats(ThbRansacStats* stats);
+
+/*
+ * Bit-packs per-correspondence inlier masks for transport (the pair queue's all-gather): pair p's n_p flags
+ * mask[pair_offset[p] ...] go to words[word_offset[p] ...], bit i of word i/32 = flag i, ceil(n_p / 32) words per pair
+ * (word_offset[p+1] - word_offset[p] must be at least that). All pointers in `memory_space`.
+ */
+int thb_pack_inlier_masks(const uint8_t* mask, const int64_t* pair_offset, const int64_t* word_offset, int32_t num_pairs,
+                          int32_t memory_space, uint32_t* words, void* cuda_stream);
+
+/*
+ * Measurement entry: the FP64 FMA issue rate of the device (independent DFMA chains on every SM, best of `repeats`
+ * launches, CUDA events), in TFLOP/s. The denominator of the FP64 rooflines bench.py reports (MEASURED_PEAKS.json
+ * carries no FP64 figure).
+ */
+int thb_fp64_peak_tflops(int32_t repeats, double* tflops, void* cuda_stream);
 
 /* theia::PoseFromThreePoints (sfm/pose/perspective_three_point.cc:182-291) for `count` independent samples (host
  * pointers): features [count*3*2], world_points [count*3*3]; R_out [count*4*9] row-major, t_out [count*4*3],
@@ -373,7 +405,8 @@ int thb_estimate_tracks_batch(const ThbBaProblem* problem, const double* ray_dir
  * reference does not normalise). A = sum (I4 - d d^T) with d = (direction, 0), b = sum (I4 - d d^T) (origin, 1), 4x4
  * Cholesky solve; ok[t] = 0 when the factorisation fails (Eigen::LLT info != Success) or the track has fewer than two
  * rays (the reference CHECK-aborts there). points_out [num_tracks*4]. This is the per-track kernel of
- * TrackEstimator::EstimateAllTracks (estimate_track.cc:124-321), one launch for all tracks. memory_space as in ThbBaProblem.
+ * TrackEstimator::EstimateAllTracks (estimate_track.cc:124-321), one launch for all tracks. memory_space as in ThbBaProblem;
+ * host offsets are validated (THB_E_INVALID_ARGUMENT), device offsets are trusted.
  */
 int thb_triangulate_midpoint_batch(const double* ray_origins, const double* ray_directions, const int64_t* ray_offset,
                                    int32_t num_tracks, int32_t memory_space, double* points_out, uint8_t* ok,

@@ -807,6 +807,18 @@ int oracle_ba_cost(const ThbBaProblem* p, const ThbBaOptions* o, double* cost) {
   return ok0 && ok1 ? THB_OK : THB_E_NUMERICAL;
 }
 
+// Thread control for the timed baselines: torchrun exports OMP_NUM_THREADS=1, the CPU arm must say how many it used.
+int oracle_set_num_threads(int n) {
+  if (n > 0) omp_set_num_threads(n);
+  int used = 0;
+#pragma omp parallel
+  {
+#pragma omp single
+    used = omp_get_num_threads();
+  }
+  return used;
+}
+
 // SphereManifold<4> helpers exposed for unit tests.
 void oracle_sphere_plus(const double* x, const double* d, double* out) { oracle::SpherePlus(x, d, out); }
 void oracle_sphere_plus_jacobian(const double* x, double* J) { oracle::SpherePlusJacobian(x, J); }

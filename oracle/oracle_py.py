@@ -50,6 +50,14 @@ def load():
     return _lib
 
 
+def set_num_threads(n):
+    """Sets the OpenMP team size of the oracle (0: leave as is); returns the team size a parallel region actually gets."""
+    lib = load()
+    lib.oracle_set_num_threads.argtypes = [C.c_int]
+    lib.oracle_set_num_threads.restype = C.c_int
+    return int(lib.oracle_set_num_threads(int(n)))
+
+
 def default_options():
     o = capi.ThbBaOptions()
     load().oracle_ba_default_options(C.byref(o))

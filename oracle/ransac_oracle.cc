@@ -529,7 +529,7 @@ struct HomographyEst {  // HomographyEstimator, estimate_homography.cc:62-116; t
 int ComputeMaxIterations(const ThbRansacParams& P, double min_sample_size, double inlier_ratio, double log_failure_prob, int total) {
   if (inlier_ratio == 1.0) return P.min_iterations;
   const int ninl = static_cast<int>(inlier_ratio * total);
-  const double num_samples = min_sample_size;
+  const double num_samples = P.use_tdd_test ? min_sample_size + 1 : min_sample_size;  // :272-279
   double a = 1.0, b = 1.0;
   for (int i = 0; i < num_samples; ++i) { a *= ninl - i; b *= total - i; }
   const double prob_all_inliers = a / b;

@@ -101,8 +101,16 @@ class ThbRansacParams(C.Structure):
     _fields_ = [
         ("error_thresh", C.c_double), ("failure_probability", C.c_double), ("min_inlier_ratio", C.c_double),
         ("min_iterations", C.c_int32), ("max_iterations", C.c_int32), ("use_mle", C.c_int32), ("use_lo", C.c_int32),
-        ("lo_start_iterations", C.c_int32), ("ransac_type", C.c_int32),
+        ("lo_start_iterations", C.c_int32), ("ransac_type", C.c_int32), ("use_tdd_test", C.c_int32), ("reserved0", C.c_int32),
     ]
+
+
+class ThbRansacStats(C.Structure):
+    _fields_ = [("pairs", C.c_uint64), ("iterations", C.c_uint64), ("samples_solved", C.c_uint64), ("models_scored", C.c_uint64),
+                ("data_scored", C.c_uint64), ("reserved0", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved0"}
 
 
 class ThbPairBatch(C.Structure):
@@ -211,6 +219,12 @@ def load_library():
     for name in ("thb_ransac_abspose_batch", "thb_ransac_homography_batch"):
         getattr(lib, name).argtypes = [C.POINTER(ThbPairBatch), C.POINTER(ThbRansacParams), C.c_void_p, C.c_void_p, C.c_void_p]
         getattr(lib, name).restype = C.c_int
+    lib.thb_ransac_last_stats.argtypes = [C.POINTER(ThbRansacStats)]
+    lib.thb_ransac_last_stats.restype = C.c_int
+    lib.thb_pack_inlier_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.thb_pack_inlier_masks.restype = C.c_int
+    lib.thb_fp64_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double), C.c_void_p]
+    lib.thb_fp64_peak_tflops.restype = C.c_int
     lib.thb_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_p3p.restype = C.c_int
     lib.thb_ba_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.POINTER(ThbBaOptions), C.c_void_p, C.c_void_p]

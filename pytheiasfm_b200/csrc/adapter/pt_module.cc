@@ -436,7 +436,7 @@ ThbRansacParams ToC(const RansacParameters& q, int ransac_type) {
   thb_ransac_default_params(&p);
   p.error_thresh = q.error_thresh; p.failure_probability = q.failure_probability; p.min_inlier_ratio = q.min_inlier_ratio;
   p.min_iterations = q.min_iterations; p.max_iterations = q.max_iterations; p.use_mle = q.use_mle; p.use_lo = q.use_lo;
-  p.lo_start_iterations = q.lo_start_iterations; p.ransac_type = ransac_type;
+  p.lo_start_iterations = q.lo_start_iterations; p.ransac_type = ransac_type; p.use_tdd_test = q.use_Tdd_test;
   return p;
 }
 uint32_t SeedOf(const RansacParameters& q) { return q.seed >= 0 ? (uint32_t)q.seed : std::random_device{}(); }

@@ -202,14 +202,29 @@ int CheckDevice() {
 }
 
 // K1 uses no shared memory: ask for the largest L1 so the 128-byte camera records stay resident.
+// Function attributes are per device: one once_flag per (kernel instantiation, device), safe under concurrent callers.
 template <typename Kern>
 void PreferL1Once(Kern kern) {
-  static bool done = false;
-  if (!done) { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); done = true; }
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [kern] { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); });
+}
+template <typename Kern>
+void MaxDynamicSmemOnce(Kern kern, int bytes) {
+  static std::once_flag once[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
+  std::call_once(once[dev], [kern, bytes] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
 }
 int SmCount() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = sms;
   return sms;
 }
 // The shared-camera K1 (k_jacobian_sc) pays one copy of the camera table per SM; measured faster than the gather kernel from
@@ -228,8 +243,7 @@ void LaunchJacobianKernel(ThbBaSession* s, const double* cs, const double* ps, c
   // refined intrinsics (NK > 0) stay on the gather kernel: the shared-camera instantiation spills ~400 bytes there
   if constexpr (NK == 0) {
     if (UseSharedCameraK1(s)) {
-      static bool done = false;
-      if (!done) { cudaFuncSetAttribute(k_jacobian_sc<MODEL, PD, NK, ROBUST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); done = true; }
+      MaxDynamicSmemOnce(k_jacobian_sc<MODEL, PD, NK, ROBUST>, 227 * 1024);
       k_jacobian_sc<MODEL, PD, NK, ROBUST><<<std::min(SmCount(), cdiv(s->no, K1S_THREADS)), K1S_THREADS, K1S_PT_BYTES + K1S_INTR_BYTES + (size_t)s->nc * CAMD * 8, s->st>>>(
           s->K, s->X, s->Op, cs, ps, is, s->d_r, s->d_jc, s->d_jp, ji, s->d_scal, s->d_flag);
       return;
@@ -1035,7 +1049,7 @@ int RunTrackBatch(const ThbBaProblem* P, const ThbBaOptions* O, const double* ra
     tp.sq_max_reprojection_error = E->max_acceptable_reprojection_error_pixels * E->max_acceptable_reprojection_error_pixels;
   }
   // 64-thread CTAs: a C5-sized batch (60k tracks) is only 0.4 threads per resident-thread slot of the GPU, small CTAs spread it
-  // over all SMs (168 registers per thread). THB_TRACK_TIMING=1 prints the kernel's duration (scratch/track_time.py).
+  // over all SMs (168 registers per thread). THB_TRACK_TIMING=1 prints the kernel's duration (tools/microbench/track_time.py).
   const bool timing = getenv("THB_TRACK_TIMING") != nullptr;
   const int cta = 64;
   cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -26,7 +26,7 @@ namespace thb {
 
 namespace {
 
-#ifdef THB_K4_PROBE  // scratch/k4_micro.cu: phase time stamps of CTA 0
+#ifdef THB_K4_PROBE  // tools/microbench/k4_micro.cu: phase time stamps of CTA 0
 __device__ long long g_probe[16];
 #define THB_PROBE(slot) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_probe[slot] = clock64(); } while (0)
 #else
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ A,
 }
 
 // ---- thread-per-row variants (the ones FactorAndSolve launches) ------------------------------------------------------
-// Measured on B200 (scratch/k4_micro.cu, scratch/lat_micro.cu): a warp-wide DFMA issues every 2.1 cycles per SM
+// Measured on B200 (tools/microbench/k4_micro.cu, tools/microbench/lat_micro.cu): a warp-wide DFMA issues every 2.1 cycles per SM
 // sub-partition with 8.8 cycles latency, i.e. FP64 SIMT runs at the full 64 FMA/clk/SM; a publish + __syncthreads + read
 // round trip costs 75-95 cycles, a quad shuffle 30, a branch ~25, and straight-line code that is executed once is
 // instruction-fetch bound when the I-cache is cold. The r01-start kernels above spend 350-650 cycles per pivot on exactly

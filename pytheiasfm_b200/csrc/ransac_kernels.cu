@@ -5,20 +5,23 @@
 // with RandomSampler (solvers/random_sampler.cc:53-72) on std::mt19937 (util/random.cc:46-84).
 //
 // The reference loop is sequential (persistent sampler permutation, strict-< best update in model order,
-// adaptive iteration bound). It is replayed exactly: iterations are processed in batches of 32 —
+// adaptive iteration bound). It is replayed exactly: iterations are processed in batches of BI = 128 —
 //   draw   : one thread advances a bit-exact mt19937 + libstdc++ uniform_int_distribution (Lemire) and the
 //            partial Fisher-Yates permutation, 5 indices per iteration
 //   solve  : one THREAD per hypothesis runs the five-point solver (FP64 SIMT is issue-bound, so 32 hypotheses
-//            per warp cost the same as one) and the essential-matrix decomposition + cheirality vote
-//   score  : one WARP per model scores every correspondence (cheirality-gated Sampson) from shared memory,
-//            lane-strided, warp-shuffle reduction; a model whose partial cost already exceeds the best cost
-//            known at batch start is abandoned (it can never win the strict-< test: exactness is preserved)
+//            per warp cost the same as one) and the essential-matrix decomposition + cheirality vote; the
+//            candidate models go to a per-CTA scratch area in global memory (L2)
+//   score  : one WARP per model scores every correspondence (cheirality-gated Sampson), read through L1
+//            (a pair's 64 KB stays cached between models), lane-strided, warp-shuffle reduction; a model
+//            whose partial cost already reaches the best cost known at batch start is abandoned (it can
+//            never win the strict-< test: exactness is preserved)
 //   scan   : one thread walks the (iteration, model) costs in order, updates the best model and the adaptive
 //            bound, and discards everything past the terminating iteration
 // This file is compiled with -fmad=false (see small_linalg.cuh); the scoring formulas use explicit fma() in a
 // fixed order so that they are both fast and bit-reproducible against the CPU oracle.
 #include <cfloat>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -559,8 +562,9 @@ __device__ int compute_max_iterations(const ThbRansacParams& P, double min_sampl
                                       double log_failure_prob, int total) {
   if (inlier_ratio == 1.0) return P.min_iterations;
   const int ninl = (int)(inlier_ratio * total);
+  const double num_samples = P.use_tdd_test ? min_sample_size + 1 : min_sample_size;
   double a = 1.0, b = 1.0;
-  for (int i = 0; i < min_sample_size; ++i) { a *= ninl - i; b *= total - i; }
+  for (int i = 0; i < num_samples; ++i) { a *= ninl - i; b *= total - i; }
   const double prob_all_inliers = a / b;
   if (prob_all_inliers < DBL_EPSILON) return P.max_iterations;
   if (prob_all_inliers >= 1.0 - DBL_EPSILON) return P.min_iterations;
@@ -571,11 +575,9 @@ __device__ int compute_max_iterations(const ThbRansacParams& P, double min_sampl
 // Warp-wide score of one model over all data. Returns (cost, #inliers) in every lane; cost = +inf if the model was
 // abandoned because its partial cost reached `bail`. If mask != nullptr the inlier flags are written.
 template <class Est>
-__device__ void score_model(const ThbRansacParams& P, const double* __restrict__ data, int si, int sk, int n, const Model& m,
-                            double bail, uint8_t* __restrict__ mask, double* cost_out, int* ninl_out) {
-  // datum i, coordinate k at data[i * si + k * sk]: (si, sk) = (D, 1) for the caller's array-of-structs in global memory,
-  // (1, n) for the structure-of-arrays copy in shared memory (lane-consecutive, bank-conflict-free; the AoS copy made every
-  // 8-byte read an 8-way conflict: 1.05 G conflicts in the r01 ncu capture)
+__device__ void score_model(const ThbRansacParams& P, const double* __restrict__ data, int n, const Model& m,
+                            double bail, uint8_t* __restrict__ mask, double* cost_out, int* ninl_out, unsigned* scored) {
+  // datum i at data[i * D .. i * D + D): the caller's array-of-structs, read through L1
   const int lane = threadIdx.x & 31;
   double cost = 0.0;
   int ninl = 0;
@@ -591,7 +593,7 @@ __device__ void score_model(const ThbRansacParams& P, const double* __restrict__
     if (i < n) {
       double d[Est::D];
 #pragma unroll
-      for (int k = 0; k < Est::D; ++k) d[k] = data[(size_t)i * si + (size_t)k * sk];
+      for (int k = 0; k < Est::D; ++k) d[k] = data[(size_t)i * Est::D + k];
       const double r = Est::error(E, R, p, d);
       const bool inl = r < thresh;
       if (P.use_mle) cost += inl ? r : thresh; else cost += inl ? 0.0 : 1.0;
@@ -600,9 +602,10 @@ __device__ void score_model(const ThbRansacParams& P, const double* __restrict__
     }
     if ((s & 15) == 15 && bail < DBL_MAX) {
       const double partial = warp_sum(cost);
-      if (partial >= bail) { *cost_out = INFINITY; *ninl_out = 0; return; }
+      if (partial >= bail) { *cost_out = INFINITY; *ninl_out = 0; *scored += min(n, (s + 1) * 32); return; }
     }
   }
+  *scored += n;
   cost = warp_sum(cost);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ninl += __shfl_xor_sync(0xffffffffu, ninl, o);
@@ -618,6 +621,7 @@ struct RansacShared {
   Mt19937 rng;
   double best_cost;
   int max_iterations, it0, finished, num_iterations, have_best, pair;
+  unsigned long long stat_samples, stat_models, stat_data;
 };
 
 // Persistent grid (three CTAs per SM) pulling pairs from an atomic counter: RANSAC iteration counts differ by 100x
@@ -629,12 +633,11 @@ template <class Est>
 __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
                                                   const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
                                                   ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
-                                                  int* __restrict__ idx_ws, int smem_corr_cap, Model* model_ws, double* cost_ws,
-                                                  int* ninl_ws, int* __restrict__ pair_counter) {
+                                                  int* __restrict__ idx_ws, Model* model_ws, double* cost_ws,
+                                                  int* ninl_ws, int* __restrict__ pair_counter, unsigned long long* __restrict__ stats) {
   constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
-  double* s_corr = reinterpret_cast<double*>(smem_raw + ((sizeof(RansacShared) + 31) / 32) * 32);
   Model* M = model_ws + (size_t)blockIdx.x * BI * MAXM;
   double* g_cost = cost_ws + (size_t)blockIdx.x * BI * MAXM;  // per-model cost / inlier count of the current batch
   int* g_ninl = ninl_ws + (size_t)blockIdx.x * BI * MAXM;
@@ -655,14 +658,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     if (mask) for (int i = t; i < n; i += RT) mask[i] = 0;
     continue;
   }
-  const double* g_corr = corr_all + (size_t)off * DD;
-  const bool in_smem = n <= smem_corr_cap;
-  const double* corr = g_corr;
-  int csi = DD, csk = 1;
-  if (in_smem) {  // transposed into structure-of-arrays
-    for (int e = t; e < n * DD; e += RT) { const int i = e / DD, k = e - i * DD; s_corr[k * n + i] = g_corr[e]; }
-    corr = s_corr; csi = 1; csk = n;
-  }
+  const double* corr = corr_all + (size_t)off * DD;
   int* sidx = idx_ws + off;  // RandomSampler::sample_indices_ (persistent permutation)
   for (int i = t; i < n; i += RT) sidx[i] = i;
   if (t == 0) {
@@ -674,6 +670,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
       S.max_iterations = mi < P.max_iterations ? mi : P.max_iterations;
     }
     S.it0 = 0; S.finished = 0; S.num_iterations = 0; S.have_best = 0;
+    S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
     memset(&S.best, 0, sizeof(Model));
   }
   __syncthreads();
@@ -700,7 +697,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
       if (t < nit) {
         double sample[SS * DD];
         for (int i = 0; i < SS; ++i)
-          for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[t][i] * csi + (size_t)k * csk];
+          for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)S.samples[t][i] * DD + k];
         nm = Est::solve(sample, M + t * MAXM);  // straight into the CTA's scratch area: no 1.7 KB local copy
       }
       S.nmodels[t] = nm;
@@ -710,19 +707,22 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
       int acc = 0;
       for (int b = 0; b < BI; ++b) { S.model_start[b] = acc; acc += (b < nit) ? S.nmodels[b] : 0; }
       S.model_start[BI] = acc;
+      S.stat_samples += nit; S.stat_models += acc;
     }
     __syncthreads();
     // ---- score: warp w takes flat models w, w + NW, ...
     const int total_models = S.model_start[BI];
     const double bail = S.best_cost;
+    unsigned scored = 0;
     for (int j = w; j < total_models; j += NW) {
       int b = 0;
       while (S.model_start[b + 1] <= j) ++b;
       const int k = j - S.model_start[b];
       double cost; int ninl;
-      score_model<Est>(P, corr, csi, csk, n, M[b * MAXM + k], bail, nullptr, &cost, &ninl);
+      score_model<Est>(P, corr, n, M[b * MAXM + k], bail, nullptr, &cost, &ninl, &scored);
       if (lane == 0) { g_cost[b * MAXM + k] = cost; g_ninl[b * MAXM + k] = ninl; }
     }
+    if (lane == 0 && scored) atomicAdd(&S.stat_data, (unsigned long long)scored);
     __syncthreads();
     // ---- scan in (iteration, model) order
     if (t == 0) {
@@ -749,8 +749,13 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
   // ---- final inliers of the best model (sample_consensus_estimator.h:396-414)
   if (w == 0) {
     double cost; int ninl;
-    score_model<Est>(P, corr, csi, csk, n, S.best, DBL_MAX, mask, &cost, &ninl);
+    unsigned scored = 0;
+    score_model<Est>(P, corr, n, S.best, DBL_MAX, mask, &cost, &ninl, &scored);
     if (lane == 0) {
+      if (stats) {
+        atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)S.num_iterations); atomicAdd(stats + 2, S.stat_samples);
+        atomicAdd(stats + 3, S.stat_models + 1); atomicAdd(stats + 4, S.stat_data + scored);
+      }
       out->success = 1;
       out->num_inliers = ninl;
       out->num_iterations = S.num_iterations;
@@ -777,6 +782,34 @@ __global__ void k_five_point(const double* __restrict__ x1, const double* __rest
   for (int k = 0; k < 90; ++k) E_out[90 * (size_t)i + k] = Es[k];
 }
 
+// one CTA per pair: 32 flags -> one word by warp ballot
+__global__ void k_pack_masks(const uint8_t* __restrict__ mask, const long long* __restrict__ pair_offset,
+                             const long long* __restrict__ word_offset, uint32_t* __restrict__ words) {
+  const int p = blockIdx.x;
+  const long long off = pair_offset[p];
+  const int n = (int)(pair_offset[p + 1] - off);
+  uint32_t* out = words + word_offset[p];
+  const int lane = threadIdx.x & 31;
+  for (int base = (threadIdx.x >> 5) * 32; base < n; base += blockDim.x) {
+    const int i = base + lane;
+    const unsigned bits = __ballot_sync(0xffffffffu, i < n && mask[off + i] != 0);
+    if (lane == 0) out[base >> 5] = bits;
+  }
+}
+
+// FP64 issue-rate probe: 8 independent DFMA chains per thread
+__global__ void k_dfma_peak(int iters, double m, double* sink) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double c = 1e-9;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) *sink = s;
+}
+
 struct Bufs {  // scoped, stream-ordered device allocations (no cudaMalloc / cudaFree per batch after the first)
   std::vector<void*> p;
   cudaStream_t st = nullptr;
@@ -789,6 +822,8 @@ struct Bufs {  // scoped, stream-ordered device allocations (no cudaMalloc / cud
   }
 };
 
+thread_local ThbRansacStats g_last_stats = {};
+
 int check_device() {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) THB_FAIL(THB_E_NO_DEVICE, "no CUDA device visible; libtheia_b200 has no CPU path");
@@ -797,12 +832,12 @@ int check_device() {
   int major = 0;
   THB_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) THB_FAIL(THB_E_NO_DEVICE, "device is not sm_100 (B200); kernels are built for sm_100a only");
-  static bool pool_once = false;
-  if (!pool_once) {  // keep freed blocks in the default pool (same policy as the BA path)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
-    pool_once = true;
-  }
+  static std::once_flag pool_once[64];  // keep freed blocks in the default pool (same policy as the BA path), per device
+  if (dev >= 0 && dev < 64)
+    std::call_once(pool_once[dev], [dev] {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) { uint64_t thr = ~0ull; cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr); }
+    });
   return THB_OK;
 }
 
@@ -851,17 +886,10 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   }
   int* d_idx = B.get<int>((size_t)total);
   if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-  // shared memory: control block + as many data as fit
-  const size_t ctrl = ((sizeof(RansacShared) + 31) / 32) * 32;
-  const size_t per = sizeof(double) * DD;
-  size_t want = ctrl + (size_t)max_n * per;
-  const size_t limit = 227 * 1024;
-  int cap = max_n;
-  if (want > limit) { cap = (int)((limit - ctrl) / per); want = ctrl + (size_t)cap * per; }
-  // Measured on C4: NOT staging the correspondences (cap = 0) is 20 % faster (50.5k vs 41.7k pairs/s). Three staged copies
-  // take 207 KB of the SM's 256 KB L1/shared array, and the five-point solver's per-thread work matrices (local memory,
-  // 9.7 KB per thread) then miss L1; read through L1 instead, a pair's 64 KB stays cached between models anyway.
-  cap = 0; want = ctrl;
+  // Shared memory holds the control block only. Staging the pair's correspondences there was measured 20 % slower on C4
+  // (41.7k vs 50.5k pairs/s): three staged copies take 207 KB of the SM's 256 KB L1/shared array and the five-point
+  // solver's per-thread work matrices (local memory) then miss L1; a pair's 64 KB stays L1-resident between models anyway.
+  const size_t want = ((sizeof(RansacShared) + 31) / 32) * 32;
   THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac<Est>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -872,10 +900,13 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   double* d_cost = B.get<double>((size_t)grid * BI * MAXM);
   int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
   int* d_counter = B.get<int>(1);
-  if (!d_models || !d_cost || !d_ninl || !d_counter) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  unsigned long long* d_stats = B.get<unsigned long long>(6);
+  if (!d_models || !d_cost || !d_ninl || !d_counter || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, cap, d_models, d_cost, d_ninl, d_counter);
+  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 6, st));
+  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats);
   THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
   if (host) {
     THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
     if (inlier_mask) THB_CUDA_CHECK(cudaMemcpyAsync(inlier_mask, d_mask, (size_t)total, cudaMemcpyDeviceToHost, st));
@@ -954,6 +985,77 @@ int thb_ransac_abspose_batch(const ThbPairBatch* b, const ThbRansacParams* p, Th
 int thb_ransac_homography_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask,
                                 void* cuda_stream) {
   return run_batch<HomographyEst>(b, p, results, inlier_mask, cuda_stream);
+}
+
+int thb_ransac_last_stats(ThbRansacStats* stats) {
+  if (!stats) THB_FAIL(THB_E_INVALID_ARGUMENT, "null stats");
+  *stats = g_last_stats;
+  return THB_OK;
+}
+
+int thb_pack_inlier_masks(const uint8_t* mask, const int64_t* pair_offset, const int64_t* word_offset, int32_t num_pairs,
+                          int32_t memory_space, uint32_t* words, void* cuda_stream) {
+  if (num_pairs < 0 || (memory_space != THB_MEM_HOST && memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  if (num_pairs == 0) return THB_OK;
+  if (!mask || !pair_offset || !word_offset || !words) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
+  int rc = check_device();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (memory_space == THB_MEM_DEVICE) {
+    k_pack_masks<<<num_pairs, 128, 0, st>>>(mask, (const long long*)pair_offset, (const long long*)word_offset, words);
+    THB_CUDA_CHECK(cudaGetLastError());
+    return THB_OK;
+  }
+  const long long total = pair_offset[num_pairs], nwords = word_offset[num_pairs];
+  for (int i = 0; i < num_pairs; ++i)
+    if (pair_offset[i + 1] < pair_offset[i] || word_offset[i + 1] - word_offset[i] < (pair_offset[i + 1] - pair_offset[i] + 31) / 32)
+      THB_FAIL(THB_E_INVALID_ARGUMENT, "offsets must be non-decreasing with ceil(n/32) words per pair");
+  Bufs B;
+  B.st = st;
+  uint8_t* dm = B.get<uint8_t>((size_t)total); long long* dpo = B.get<long long>(num_pairs + 1); long long* dwo = B.get<long long>(num_pairs + 1);
+  uint32_t* dw = B.get<uint32_t>((size_t)nwords);
+  if (!dm || !dpo || !dwo || !dw) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemcpyAsync(dm, mask, (size_t)total, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(dpo, pair_offset, sizeof(long long) * (num_pairs + 1), cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(dwo, word_offset, sizeof(long long) * (num_pairs + 1), cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(dw, 0, sizeof(uint32_t) * (size_t)nwords, st));
+  k_pack_masks<<<num_pairs, 128, 0, st>>>(dm, dpo, dwo, dw);
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(words, dw, sizeof(uint32_t) * (size_t)nwords, cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return THB_OK;
+}
+
+int thb_fp64_peak_tflops(int32_t repeats, double* tflops, void* cuda_stream) {
+  if (!tflops || repeats <= 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad argument");
+  int rc = check_device();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  Bufs B;
+  B.st = st;
+  double* sink = B.get<double>(1);
+  if (!sink) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  cudaEvent_t a, b;
+  THB_CUDA_CHECK(cudaEventCreate(&a)); THB_CUDA_CHECK(cudaEventCreate(&b));
+  const int iters = 1 << 14, grid = sms * 4, threads = 256;
+  double best = 0.0;
+  for (int r = 0; r < repeats + 1; ++r) {  // first launch is the warm-up
+    cudaEventRecord(a, st);
+    k_dfma_peak<<<grid, threads, 0, st>>>(iters, 1.0000001, sink);
+    cudaEventRecord(b, st);
+    if (cudaEventSynchronize(b) != cudaSuccess) { cudaEventDestroy(a); cudaEventDestroy(b); THB_FAIL(THB_E_CUDA, "fp64 peak kernel failed"); }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    const double flops = 2.0 * 8.0 * (double)iters * threads * grid;
+    if (r > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *tflops = best;
+  return THB_OK;
 }
 
 int thb_p3p(const double* features, const double* world_points, int32_t count, double* R_out, double* t_out, int32_t* num_solutions,

@@ -84,6 +84,8 @@ extern "C" int thb_triangulate_midpoint_batch(const double* ray_origins, const d
   }
   const long long total = ray_offset[num_tracks];
   if (ray_offset[0] != 0 || total < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "ray_offset must start at 0 and be non-decreasing");
+  for (int t = 0; t < num_tracks; ++t)  // a malformed interior offset would send the kernel out of bounds (the device path trusts its caller)
+    if (ray_offset[t + 1] < ray_offset[t] || ray_offset[t + 1] > total) THB_FAIL(THB_E_INVALID_ARGUMENT, "ray_offset must start at 0 and be non-decreasing");
   double *d_org = nullptr, *d_dir = nullptr, *d_out = nullptr; long long* d_off = nullptr; uint8_t* d_ok = nullptr;
   cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&d_org), sizeof(double) * 3 * (total ? total : 1), st);
   if (e == cudaSuccess) e = cudaMallocAsync(reinterpret_cast<void**>(&d_dir), sizeof(double) * 3 * (total ? total : 1), st);

@@ -28,6 +28,30 @@ def partition_by_work(pair_offset, world):
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
+def block_cyclic_indices(num_units, rank, world, block=8):
+    """Over-decomposed static schedule: the table is cut into blocks of `block` consecutive units and block b goes to
+    rank b % world. A pair's cost (its RANSAC iteration count) is unknown before it runs and differs by 100x between
+    pairs; dealing many small blocks round-robin balances the ranks statistically without any communication, and the
+    per-GPU atomic pair counter of k_ransac balances the SMs inside a rank. Returns the rank's global unit indices,
+    ascending."""
+    idx = np.arange(num_units, dtype=np.int64)
+    return idx[(idx // block) % world == rank]
+
+
+def mask_word_offsets(pair_offset):
+    """word_offset [num_pairs + 1] for thb_pack_inlier_masks: ceil(n_p / 32) 32-bit words per pair."""
+    n = np.diff(np.asarray(pair_offset, dtype=np.int64))
+    out = np.zeros(len(n) + 1, np.int64)
+    out[1:] = np.cumsum((n + 31) // 32)
+    return out
+
+
+def unpack_mask_words(words, n):
+    """Inverse of thb_pack_inlier_masks for one pair: `n` flags from ceil(n / 32) little-endian words."""
+    bits = np.unpackbits(np.ascontiguousarray(words, dtype=np.uint32).view(np.uint8), bitorder="little")
+    return bits[:n]
+
+
 def shard_batch(batch, rank, world):
     """The rank's block of a HostPairBatch (a new HostPairBatch with re-based offsets) and its [lo, hi) range."""
     lo, hi = partition_by_work(batch.pair_offset, world)[rank]
@@ -59,6 +83,31 @@ def shard_tracks(prob, rank, world):
         a[k] = None if prob.a[k] is None else prob.a[k][keep]
     a["obs_pt"] = obs_pt[keep] - lo
     return capi.HostBaProblem(a), lo, hi
+
+
+def all_gather_padded(local, counts, group=None):
+    """all_gather of per-rank 1-D tensors of different lengths (counts[r] elements on rank r): one collective on buffers
+    padded to the longest. Returns the list of per-rank tensors, trimmed."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    pad = int(max(counts))
+    buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    buf[: local.numel()] = local.reshape(-1)
+    out = torch.empty(world * pad, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return [out[r * pad: r * pad + int(counts[r])] for r in range(world)]
+
+
+def assemble_block_cyclic(per_rank, num_units, world, block=8, width=1):
+    """Global table (unit-major, `width` elements per unit) from the per-rank pieces of a block_cyclic_indices schedule."""
+    import torch
+    full = torch.empty(num_units * width, dtype=per_rank[0].dtype, device=per_rank[0].device)
+    view = full.view(num_units, width)
+    for r in range(world):
+        idx = torch.from_numpy(block_cyclic_indices(num_units, r, world, block)).to(full.device)
+        view[idx] = per_rank[r].view(-1, width)
+    return full
 
 
 def all_gather_results(local_records, ranges, group=None, device=None, dtype=None):

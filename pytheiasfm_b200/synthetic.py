@@ -252,6 +252,17 @@ def make_pair_batch(num_pairs, n=2000, inlier_ratio=0.6, noise=1e-3, seed=0, bas
     return capi.HostPairBatch(corrs, base_seed + np.arange(num_pairs)), gts
 
 
+def make_pair_batch_indexed(indices, n=2000, inlier_ratio=0.6, noise=1e-3, seed=0, base_seed=1000):
+    """The pairs `indices` of a BASELINE configs[3]-shaped table in which every pair has its OWN generator
+    (default_rng([seed, index])) and seed base_seed + index: a rank builds exactly the pairs it owns, and any
+    partition of the table yields identical pairs."""
+    corrs, gts = [], []
+    for i in indices:
+        c, R, p, f = make_pair(np.random.default_rng([seed, int(i)]), n, inlier_ratio, noise)
+        corrs.append(c); gts.append((R, p, f))
+    return capi.HostPairBatch(corrs, base_seed + np.asarray(indices, dtype=np.int64)), gts
+
+
 def c4_params(lib_or_oracle_params):
     """RansacParameters of BASELINE configs[3]."""
     p = lib_or_oracle_params

@@ -367,3 +367,27 @@ def test_k4_reports_indefinite_matrix(lib):
     b = np.ones(n); x = np.zeros(n)
     rc = lib.thb_dense_spd_solve(A.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), n, x.ctypes.data_as(C.c_void_p), None)
     assert rc == capi.THB_E_NUMERICAL
+
+
+def test_c2_full_size_matches_oracle(lib, oracle):
+    """BASELINE configs[1] at FULL size (1k cams / 100k pts / 1M obs), the benchmark's own solve (reference default
+    tolerances): termination, iteration count, per-iteration costs and final cost against the oracle, <= 1e-6 relative
+    (north_star's tolerance), refined parameters to 1e-6."""
+    prob, _ = synthetic.config_c2()
+    assert prob.num_observations == 1000000 and prob.num_cameras == 1000 and prob.num_points == 100000
+    oracle.set_num_threads(__import__("os").cpu_count() or 1)
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    assert g["num_iterations"] == o["num_iterations"] >= 3
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], rtol=0, atol=1e-6)
+
+
+def test_c3_full_size_matches_oracle(lib, oracle):
+    """BASELINE configs[2] at FULL size (500 cams / 50k pts / 400k obs, DoubleSphere + ExtendedUnified groups, focal length
+    and distortion refined under bounds) against the oracle: same iteration count, costs <= 1e-6 relative, same intrinsics."""
+    prob, _ = synthetic.config_c3()
+    assert prob.num_cameras == 500 and prob.num_points == 50000 and prob.num_observations == 400000
+    _perturb_intrinsics(prob, 0.02)
+    oracle.set_num_threads(__import__("os").cpu_count() or 1)
+    g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
+    assert g["num_iterations"] == o["num_iterations"] >= 3
+    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)

@@ -212,3 +212,63 @@ def test_abspose_and_homography_ransac_identical_inlier_sets(lib, oracle, kind):
     for f in ("essential_matrix", "rotation", "position"):
         assert np.array_equal(res[f], ores[f], equal_nan=True), f
     assert (res["num_inliers"] > 100).all()
+
+
+def test_c4_shaped_pairs_bit_equal_to_oracle(lib, oracle):
+    """320 pairs of the benchmark's own C4 table (2000 correspondences, 60 % inliers, C4 parameters, the table's per-pair
+    seeds): inlier masks, iteration counts and models identical to the oracle bit for bit; the device work counters agree
+    with the iteration counts."""
+    batch, _ = synthetic.make_pair_batch_indexed(range(320), n=2000, seed=21)
+    params = synthetic.c4_params(capi.ThbRansacParams())
+    res, mask = gpu_ransac(lib, batch, params)
+    st = capi.ThbRansacStats()
+    capi.check(lib.thb_ransac_last_stats(C.byref(st)))
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, synthetic.c4_params(oracle.ransac_default_params()))
+    assert rc == 0
+    for f in ("success", "num_iterations", "num_inliers", "num_input_data_points"):
+        np.testing.assert_array_equal(res[f], ores[f], err_msg=f)
+    np.testing.assert_array_equal(mask, omask)
+    for f in ("essential_matrix", "rotation", "position", "best_cost", "confidence"):
+        assert np.array_equal(res[f], ores[f]), f
+    assert st.pairs == 320 and st.iterations == int(res["num_iterations"].sum()) and st.samples_solved >= st.iterations
+    assert st.data_scored >= 2000 * 320 and st.models_scored >= 320
+
+
+def test_use_tdd_test_changes_the_iteration_bound_like_the_oracle(lib, oracle):
+    """RansacParameters::use_Tdd_test: ComputeMaxIterations counts SampleSize + 1 draws (sample_consensus_estimator.h:272-279)."""
+    batch, _ = synthetic.make_pair_batch_indexed(range(12), n=500, seed=3)
+    def mk(p, tdd):
+        p = synthetic.c4_params(p); p.use_tdd_test = tdd
+        return p
+    res0, _ = gpu_ransac(lib, batch, mk(capi.ThbRansacParams(), 0))
+    res1, mask1 = gpu_ransac(lib, batch, mk(capi.ThbRansacParams(), 1))
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, mk(oracle.ransac_default_params(), 1))
+    np.testing.assert_array_equal(res1["num_iterations"], ores["num_iterations"])
+    np.testing.assert_array_equal(mask1, omask)
+    assert (res1["num_iterations"] >= res0["num_iterations"]).all() and (res1["num_iterations"] > res0["num_iterations"]).any()
+
+
+def test_pack_inlier_masks_round_trip(lib):
+    import torch
+    from pytheiasfm_b200 import sharding
+    rng = np.random.default_rng(5)
+    sizes = [0, 1, 31, 32, 33, 2000, 777, 64]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    mask = (rng.random(int(off[-1])) < 0.4).astype(np.uint8)
+    woff = sharding.mask_word_offsets(off)
+    words = np.zeros(int(woff[-1]), np.uint32)
+    capi.check(lib.thb_pack_inlier_masks(_vp(mask), _vp(off), _vp(woff), len(sizes), capi.THB_MEM_HOST, _vp(words), None))
+    for p, n in enumerate(sizes):
+        np.testing.assert_array_equal(sharding.unpack_mask_words(words[woff[p]: woff[p + 1]], n), mask[off[p]: off[p + 1]])
+    d = [torch.from_numpy(a).cuda() for a in (mask, off, woff)]
+    dw = torch.zeros(len(words), dtype=torch.int32, device="cuda")
+    capi.check(lib.thb_pack_inlier_masks(C.c_void_p(d[0].data_ptr()), C.c_void_p(d[1].data_ptr()), C.c_void_p(d[2].data_ptr()), len(sizes),
+                                         capi.THB_MEM_DEVICE, C.c_void_p(dw.data_ptr()), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dw.cpu().numpy().view(np.uint32), words)
+
+
+def test_fp64_peak_probe(lib):
+    t = C.c_double(0.0)
+    capi.check(lib.thb_fp64_peak_tflops(3, C.byref(t), None))
+    assert 20.0 < t.value < 80.0, t.value

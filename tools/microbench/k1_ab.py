@@ -1,5 +1,5 @@
 """A/B timing of the two K1 kernels on C2 (thb_ba_time_jacobian: CUDA events on the launch stream, L2 read-flush between
-launches). Usage: python scratch/k1_ab.py [mode ...]  (spec = gather | shared)"""
+launches). Usage: python tools/microbench/k1_ab.py [mode ...]  (spec = gather | shared)"""
 import ctypes as C
 import os
 import sys

@@ -1,6 +1,6 @@
 // Micro-benchmarks behind the K4 design decisions (FP64 SIMT / DMMA latency and issue rate, per-kernel timings of the
 // Cholesky building blocks at warm clocks). Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17
-//   -I pytheiasfm_b200/csrc scratch/k4_micro.cu build/ba_solver.o ... (see scratch/build_micro.sh). GPU box only.
+//   -I pytheiasfm_b200/csrc tools/microbench/k4_micro.cu build/ba_solver.o ... (see tools/microbench/build_micro.sh). GPU box only.
 #define THB_K4_PROBE
 #include "../pytheiasfm_b200/csrc/dense_chol.cu"
 

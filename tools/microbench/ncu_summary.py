@@ -1,5 +1,5 @@
 """Summarises `ncu -i X.ncu-rep --page raw --csv` (one row per captured launch) into the few metrics DESIGN.md quotes.
-Usage: python scratch/ncu_summary.py raw.csv > profiles/NAME.txt"""
+Usage: python tools/microbench/ncu_summary.py raw.csv > profiles/NAME.txt"""
 import csv
 import sys
 
