@@ -202,9 +202,9 @@ PAIR_BLOCK = 8       # pairs per block of the block-cyclic pair schedule
 C4_SEED = 21
 # FP64 operations per unit of work of k_ransac<RelPoseEst>, measured with ncu's executed-instruction counters
 # (smsp__sass_thread_inst_executed_op_{dadd,dmul,dfma}_pred_on, fma = 2) - profiles/r02_ransac_flop_calibration.txt
-FLOP_PER_SAMPLE = 50.0e3   # five-point solve of one minimal sample
-FLOP_PER_MODEL = 3.0e3     # essential-matrix decomposition + cheirality vote of one candidate
-FLOP_PER_DATUM = 75.0      # cheirality test + Sampson distance + cost of one correspondence
+FLOP_PER_SAMPLE = 53459.0  # five-point solve of one minimal sample
+FLOP_PER_MODEL = 4500.0    # essential-matrix decomposition + cheirality vote of one candidate
+FLOP_PER_DATUM = 79.6      # cheirality test + Sampson distance + cost of one correspondence
 
 
 def ransac_flops(stats):
@@ -368,7 +368,8 @@ def run_ransac_leg(args, lib, rank, local_rank, world, stream, K, W):
     capi.check(lib.thb_fp64_peak_tflops(5, C.byref(peak), sptr))
     flops = ransac_flops(stats)
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([flops, float(stats["iterations"]), float(stats["samples_solved"]), float(stats["models_scored"]), float(stats["data_scored"]), peak.value],
+    tot = torch.tensor([flops, float(stats["iterations"]), float(stats["samples_solved"]), float(stats["models_scored"]), float(stats["data_scored"]), peak.value,
+                        float(stats["cycles_draw"]), float(stats["cycles_solve"]), float(stats["cycles_score"]), float(stats["cycles_scan"])],
                        dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,6 +401,7 @@ def run_ransac_leg(args, lib, rank, local_rank, world, stream, K, W):
            "total_inliers": int(res_all["num_inliers"].sum()), "pairs_verified": int(res_all["success"].sum()),
            "gathered_bytes_per_step": int(world * pad), "clocks": sampler.summary(),
            "work_per_step": {"iterations": float(tot[1]), "samples_solved": float(tot[2]), "models_scored": float(tot[3]), "data_scored": float(tot[4])},
+           "cta_phase_share": {k: float(tot[6 + i]) / max(1.0, float(tot[6:10].sum())) for i, k in enumerate(("draw", "solve", "score", "scan"))},
            "roofline": {"bound": "fp64", "kernel": "k_ransac<RelPoseEst> (persistent CTAs, one pair at a time per CTA)",
                         "achieved": flops_all / sec / 1e12, "peak": peak_all, "unit": "TFLOP/s", "frac": flops_all / sec / 1e12 / peak_all if peak_all > 0 else None,
                         "traffic": None, "flops_per_step": flops_all,

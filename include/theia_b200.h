@@ -319,6 +319,10 @@ typedef struct ThbRansacStats {
   uint64_t models_scored;   /* candidate models that entered scoring                                              */
   uint64_t data_scored;     /* per-datum error evaluations actually executed (early abandonment included)         */
   uint64_t reserved0;
+  uint64_t cycles_draw;     /* SM clock cycles the CTAs spent in each phase of the batches (summed over CTAs): where */
+  uint64_t cycles_solve;    /* a pair's wall time goes                                                            */
+  uint64_t cycles_score;
+  uint64_t cycles_scan;
 } ThbRansacStats;
 int thb_ransac_last_stats(ThbRansacStats* stats);
 

@@ -107,7 +107,8 @@ class ThbRansacParams(C.Structure):
 
 class ThbRansacStats(C.Structure):
     _fields_ = [("pairs", C.c_uint64), ("iterations", C.c_uint64), ("samples_solved", C.c_uint64), ("models_scored", C.c_uint64),
-                ("data_scored", C.c_uint64), ("reserved0", C.c_uint64)]
+                ("data_scored", C.c_uint64), ("reserved0", C.c_uint64), ("cycles_draw", C.c_uint64), ("cycles_solve", C.c_uint64),
+                ("cycles_score", C.c_uint64), ("cycles_scan", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_ if k != "reserved0"}

@@ -20,6 +20,8 @@
 #include "dense_chol.cuh"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 namespace thb {
@@ -857,6 +859,409 @@ __global__ void __launch_bounds__(256, 3) chol_update64_kernel(double* __restric
   }
 }
 
+// ---- left-looking tile Cholesky in ONE persistent kernel (what FactorAndSolve runs) ------------------------------------
+// The r01 schedule (above) is right-looking: ~230 dependent launches on two streams, every 128-column step re-reads and
+// re-writes the whole trailing matrix, and for the last 55 % of the block columns the factorisation waits on the serial
+// diag -> panel -> strip chain (65 us per 128 columns) while the bulk kernels have almost nothing left to do.
+// Here the unit of work is a TILE TASK (J, m): 128 rows x 64 columns of block column J, rows starting at the diagonal
+// (row blocks J + 2m, J + 2m + 1 of 64 rows). A task keeps its tile in DMMA accumulators and runs the whole left-looking
+// update  C -= L[rows, 0:64J] L[J-block rows, 0:64J]^T  (one long K loop: the tile is read once and written once, the
+// operands stream through a 3-stage cp.async ring), then turns it into a tile of L:
+//   m == 0 : the top 64 x 64 is the diagonal block: Cholesky factor + inverse in shared memory (thread-per-row, 8-column
+//            blocks; the inverse rows are produced one block step behind by the second half of the CTA), inv(L_JJ) is
+//            published (dinv, also what the backward substitution uses), then the lower 64 rows are multiplied by inv^T
+//   m  > 0 : wait for inv(L_JJ), X = C inv(L_JJ)^T with DMMA from shared memory (a GEMM instead of a substitution)
+// Tasks are handed out by one atomic counter in column-major order to a grid that is exactly co-resident (2 CTAs per SM),
+// and every dependency of a task is an EARLIER task, so spinning on the progress counters cannot deadlock:
+//   rb_done[rb]  = number of leading block columns in which row block rb is finished (single writer at a time, monotone)
+//   diag_done    = number of diagonal blocks factored and inverted
+// A task polls the three counters of its row blocks (its own two and row block J, the B operand) a few chunks ahead of
+// the loads that need them, so columns J+1, J+2, ... run their K loops while the chain of column J completes: the chain
+// (last update of the diagonal tile, factor + inverse, multiply, publish: ~20 us per 64 columns) only shows where a column
+// has less than that much work, i.e. in the first and last ~12 of the 94 block columns.
+constexpr int TP = NB + 4;                 // shared-memory pitch of the tile / inverse copies: conflict-free DMMA fragments
+constexpr int LL_T = U_BM * TP;            // tile copy (doubles)
+constexpr int LL_LI = NB * TP;             // inverse of the diagonal factor
+constexpr int kLlSmem = (LL_T + LL_LI) * sizeof(double);
+static_assert(kLlSmem >= kUpd2Smem, "the operand ring aliases the tile copy");
+constexpr int LL_TASK = 0, LL_DIAG = 1, LL_TIMEOUT = 2, LL_RB = 8;  // int slots of the sync block
+
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// inverse role, block step kb: row i of X = L^-T (X L^T = I) held in b[] (rotated by 8 per step); writes inv(L)[k+u][i]
+__device__ __forceinline__ void ll_inv_step(int kb, double (&b)[NB], const double* __restrict__ L, const double* rdg,
+                                            double* __restrict__ Li, double* __restrict__ dinv_g, int i) {
+  const int k = 8 * kb;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const double x = b[u] * rdg[k + u];
+    b[u] = x;
+#pragma unroll
+    for (int v = u + 1; v < 8; ++v) b[v] -= x * L[(k + v) * TP + k + u];
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { Li[(k + u) * TP + i] = b[u]; dinv_g[(k + u) * NB + i] = b[u]; }
+#pragma unroll
+  for (int cg = 1; cg < 8; ++cg) {
+    if (cg < 8 - kb) {  // uniform
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double* Lj = &L[(k + 8 * cg + v) * TP + k];
+        const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+        const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+        double acc = b[8 * cg + v];
+        acc = fma(-b[0], l0.x, acc); acc = fma(-b[1], l0.y, acc); acc = fma(-b[2], l1.x, acc); acc = fma(-b[3], l1.y, acc);
+        acc = fma(-b[4], l2.x, acc); acc = fma(-b[5], l2.y, acc); acc = fma(-b[6], l3.x, acc); acc = fma(-b[7], l3.y, acc);
+        b[8 * cg + v] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NB - 8; ++c) b[c] = b[c + 8];
+}
+
+// Factor the 64 x 64 block in rows 0..63 of the tile copy T (pitch TP; only its lower triangle is read) IN PLACE and
+// write inv(L) to Li (pitch TP, full 64 x 64 with explicit zeros) and dinv_g (64 x 64 row-major). 128 threads:
+// t < 64 own one row of the block each (the loop of chol_diag3_kernel), t >= 64 own one row of L^-T each and run one
+// block step behind. Called by all 128 threads of the CTA.
+__device__ void ll_factor_inverse(double* __restrict__ T, double* __restrict__ Li, double* __restrict__ dinv_g, int* fail,
+                                  double (*Dblk)[8], double* rdg) {
+  const int t = threadIdx.x;
+  const bool diag_role = t < NB;
+  const int i = t & (NB - 1);
+  double a[NB];
+  if (diag_role) {
+#pragma unroll
+    for (int c = 0; c < NB; c += 2) { const double2 v = *reinterpret_cast<const double2*>(&T[i * TP + c]); a[c] = v.x; a[c + 1] = v.y; }
+  }
+  __syncthreads();  // every row is in registers: rows 0..63 of T now hold L, block column by block column
+#pragma unroll 1
+  for (int kb = 0; kb < 8; ++kb) {
+    const int k = 8 * kb;
+    if (diag_role && (i >> 3) == kb) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) Dblk[i & 7][u] = a[u];
+    }
+    __syncthreads();
+    if (!diag_role) {
+      if (kb == 1) {
+#pragma unroll
+        for (int c = 0; c < NB; ++c) a[c] = (c == i) ? 1.0 : 0.0;
+      }
+      if (kb >= 1) ll_inv_step(kb - 1, a, T, rdg, Li, dinv_g, i);
+    } else if (i >= k) {
+      double D[8][8], rs[8];
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        const double4 lo = *reinterpret_cast<const double4*>(&Dblk[v][0]);
+        const double4 hi = *reinterpret_cast<const double4*>(&Dblk[v][4]);
+        D[v][0] = lo.x; D[v][1] = lo.y; D[v][2] = lo.z; D[v][3] = lo.w; D[v][4] = hi.x; D[v][5] = hi.y; D[v][6] = hi.z; D[v][7] = hi.w;
+      }
+      bool bad = false;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double d = D[u][u];
+        bad |= !(d > 0.0);
+        rs[u] = rsqrt_f64(d);
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) D[v][u] *= rs[u];
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v)
+#pragma unroll
+          for (int w = u + 1; w <= v; ++w) D[v][w] -= D[v][u] * D[w][u];
+      }
+      if (bad) {  // not positive definite (or NaN); identical in every thread, the factor is garbage from here on
+        if (i == k) atomicExch(fail, 1);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rs[u] = 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const double x = a[u] * rs[u];
+        a[u] = x;
+#pragma unroll
+        for (int v = u + 1; v < 8; ++v) a[v] -= x * D[v][u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) *reinterpret_cast<double2*>(&T[i * TP + k + u]) = make_double2(a[u], a[u + 1]);
+      if (i == k) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rdg[k + u] = rs[u];
+      }
+    }
+    __syncthreads();
+    if (diag_role) {
+#pragma unroll
+      for (int cg = 1; cg < 8; ++cg) {
+        if (cg < 8 - kb && k + 8 * cg <= (i | 31)) {  // uniform per warp
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            const int j = k + 8 * cg + v;
+            const double* Lj = &T[j * TP + k];
+            const double2 l0 = *reinterpret_cast<const double2*>(Lj), l1 = *reinterpret_cast<const double2*>(Lj + 2);
+            const double2 l2 = *reinterpret_cast<const double2*>(Lj + 4), l3 = *reinterpret_cast<const double2*>(Lj + 6);
+            double acc = a[8 * cg + v];
+            acc = fma(-a[0], l0.x, acc); acc = fma(-a[1], l0.y, acc); acc = fma(-a[2], l1.x, acc); acc = fma(-a[3], l1.y, acc);
+            acc = fma(-a[4], l2.x, acc); acc = fma(-a[5], l2.y, acc); acc = fma(-a[6], l3.x, acc); acc = fma(-a[7], l3.y, acc);
+            if (j <= i) a[8 * cg + v] = acc;
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NB - 8; ++c) a[c] = a[c + 8];
+    }
+  }
+  if (!diag_role) ll_inv_step(7, a, T, rdg, Li, dinv_g, i);
+}
+
+// X = T[rows] inv(L)^T for 8 * MF rows per warp (all 64 columns), straight from shared memory; stores the valid rows to A.
+template <int MF>
+__device__ __forceinline__ void ll_multiply_store(const double* __restrict__ T, const double* __restrict__ Li, int tile_row0,
+                                                  double* __restrict__ A, int ld, int grow0, int c0, int rows_total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int rw = tile_row0 + w * (8 * MF);
+  double x[MF][8][2];
+#pragma unroll
+  for (int u = 0; u < MF; ++u)
+#pragma unroll
+    for (int v = 0; v < 8; ++v) { x[u][v][0] = 0.0; x[u][v][1] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NB; k += 4) {
+    double a[MF];
+#pragma unroll
+    for (int u = 0; u < MF; ++u) a[u] = T[(rw + u * 8 + fr) * TP + k + fk];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      if (8 * v + 7 >= k) {  // inv(L) is lower triangular: column block v only sees k <= 8 v + 7
+        const double b = Li[(v * 8 + fr) * TP + k + fk];
+#pragma unroll
+        for (int u = 0; u < MF; ++u) dmma_m8n8k4(x[u][v][0], x[u][v][1], a[u], b);
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < MF; ++u) {
+    const int r = grow0 + rw + u * 8 + fr;
+    if (r >= rows_total) continue;
+#pragma unroll
+    for (int v = 0; v < 8; ++v)
+      *reinterpret_cast<double2*>(&A[(size_t)r * ld + c0 + v * 8 + 2 * fk]) = make_double2(x[u][v][0], x[u][v][1]);
+  }
+}
+
+__global__ void __launch_bounds__(128, 2) chol_ll_kernel(double* __restrict__ A, int ld, int nb64, int rows_total,
+                                                         const int* __restrict__ col_task_start, int* __restrict__ sync,
+                                                         double* __restrict__ dinv, int* __restrict__ fail,
+                                                         long long* __restrict__ prof) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(32) double Dblk[8][8];
+  __shared__ double rdg[NB];
+  __shared__ int s_task;
+  constexpr int A_ELEMS = U_BM * LDK2, B_ELEMS = U_BN * LDK2, STAGE = A_ELEMS + B_ELEMS;
+  constexpr int MU = 8, NV = 4;
+  double* T = smem;
+  double* Li = smem + LL_T;
+  int* rb_done = sync + LL_RB;
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int wr = (w >> 1) * 64, wc = (w & 1) * 32;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int nrb = (rows_total + NB - 1) / NB;
+  const int total_tasks = col_task_start[nb64];
+  constexpr int kSpinLimit = 1 << 22;
+
+  auto stamp = [&](int J_, int m_, int slot) {  // THB_K4_PROF: global-timer stamps of the first two tiles of every column
+    if (prof && t == 0 && m_ < 2) { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); prof[(J_ * 2 + m_) * 8 + slot] = g; }
+  };
+  while (true) {
+    __syncthreads();  // the previous task is done with shared memory
+    if (t == 0) s_task = atomicAdd(&sync[LL_TASK], 1);
+    __syncthreads();
+    const int task = s_task;
+    if (task >= total_tasks) break;
+    int J = 0;
+    {
+      int lo = 0, hi = nb64;  // col_task_start[lo] <= task < col_task_start[hi]
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (col_task_start[mid] <= task) lo = mid; else hi = mid; }
+      J = lo;
+    }
+    const int m = task - col_task_start[J];
+    const int rb0 = J + 2 * m;
+    const int r0 = rb0 * NB, c0 = J * NB;
+    const int nch = 4 * J;  // K chunks of 16 columns
+
+    auto load_stage = [&](int chunk, int stage) {
+      double* sa = smem + stage * STAGE;
+      double* sb = sa + A_ELEMS;
+      const int kc = chunk * KC2;
+#pragma unroll
+      for (int e = t; e < (U_BM + U_BN) * (KC2 / 2); e += 128) {
+        const int row = e / (KC2 / 2), piece = e % (KC2 / 2);
+        if (row < U_BM) {
+          int gr = r0 + row; if (gr >= rows_total) gr = rows_total - 1;
+          cp_async16(sa + row * LDK2 + piece * 2, A + (size_t)gr * ld + kc + piece * 2);
+        } else {
+          const int rb = row - U_BM;
+          cp_async16(sb + rb * LDK2 + piece * 2, A + (size_t)(c0 + rb) * ld + kc + piece * 2);
+        }
+      }
+    };
+    // readiness of block columns [0, known) for the three row blocks this task reads (thread 0 only)
+    int known = 0, fenced = 0, p0 = 0, p1 = 0, p2 = 0, spins = 0;
+    bool pf = false;
+    auto poll = [&]() {
+      const int a = ld_relaxed(&rb_done[J]), b = ld_relaxed(&rb_done[rb0]);
+      const int c = rb0 + 1 < nrb ? ld_relaxed(&rb_done[rb0 + 1]) : J;
+      return min(min(a, b), min(c, J));
+    };
+    auto wait_for = [&](int kb_needed) {  // CTA-uniform: returns when block column kb_needed is ready
+      bool stall = false;
+      if (t == 0) {
+        if (kb_needed >= known) known = max(known, poll());
+        stall = kb_needed >= known;
+        if (!stall && known != fenced) { __threadfence(); fenced = known; }
+      }
+      while (__syncthreads_or(stall)) {
+        if (t == 0) {
+          __nanosleep(m <= 1 ? 40 : 400);
+          known = max(known, poll());
+          stall = kb_needed >= known;
+          if (stall && ++spins > kSpinLimit) { atomicExch(&sync[LL_TIMEOUT], 1); known = J; stall = false; }  // never hang the GPU
+          if (!stall) { __threadfence(); fenced = known; }
+        }
+      }
+    };
+
+    stamp(J, m, 0);
+    if (nch > 0) wait_for(0);
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+      if (s < nch) load_stage(s, s);
+      cp_async_commit();
+    }
+    // accumulators start from the tile itself (the loads overlap the first operand chunks)
+    double acc[MU][NV][2];
+#pragma unroll
+    for (int u = 0; u < MU; ++u) {
+      int r = r0 + wr + u * 8 + fr; if (r >= rows_total) r = rows_total - 1;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const double2 cv = *reinterpret_cast<const double2*>(&A[(size_t)r * ld + c0 + wc + v * 8 + 2 * fk]);
+        acc[u][v][0] = cv.x; acc[u][v][1] = cv.y;
+      }
+    }
+    auto compute_chunk = [&](int ch) {
+      const double* sa = smem + (ch % STAGES) * STAGE;
+      const double* sb = sa + A_ELEMS;
+#pragma unroll
+      for (int k = 0; k < KC2; k += 4) {
+        double a[MU], b[NV];
+#pragma unroll
+        for (int u = 0; u < MU; ++u) a[u] = -sa[(wr + u * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) b[v] = sb[(wc + v * 8 + fr) * LDK2 + k + fk];
+#pragma unroll
+        for (int u = 0; u < MU; ++u)
+#pragma unroll
+          for (int v = 0; v < NV; ++v) dmma_m8n8k4(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+      }
+    };
+    for (int ch = 0; ch < nch; ++ch) {
+      cp_async_wait<STAGES - 2>();
+      const int nxt = ch + STAGES - 1;
+      if (t == 0 && pf && (ch & 3) == 2) { known = max(known, min(min(p0, p1), min(p2, J))); pf = false; }
+      bool late = false;  // CTA-uniform: the block column of chunk nxt is not ready yet
+      if (nxt < nch && (nxt & 3) == 0) {
+        bool stall = false;
+        if (t == 0) {
+          const int kb = nxt >> 2;
+          if (kb >= known) known = max(known, poll());
+          stall = kb >= known;
+          if (!stall && known != fenced) { __threadfence(); fenced = known; }
+        }
+        late = __syncthreads_or(stall);  // also the barrier of this chunk
+      } else {
+        __syncthreads();
+      }
+      if (late) {  // use the wait: the chunks already in the ring do not depend on it
+        compute_chunk(ch);
+        wait_for(nxt >> 2);
+        load_stage(nxt, nxt % STAGES);
+        cp_async_commit();
+        continue;
+      }
+      if (nxt < nch) load_stage(nxt, nxt % STAGES);
+      cp_async_commit();
+      if (t == 0 && (ch & 3) == 0 && known < J) {  // look ahead: consumed two chunks later
+        p0 = ld_relaxed(&rb_done[J]); p1 = ld_relaxed(&rb_done[rb0]); p2 = rb0 + 1 < nrb ? ld_relaxed(&rb_done[rb0 + 1]) : J;
+        pf = true;
+      }
+      compute_chunk(ch);
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // the ring is free: the tile copy aliases it
+    stamp(J, m, 1);
+#pragma unroll
+    for (int u = 0; u < MU; ++u)
+#pragma unroll
+      for (int v = 0; v < NV; ++v)
+        *reinterpret_cast<double2*>(&T[(wr + u * 8 + fr) * TP + wc + v * 8 + 2 * fk]) = make_double2(acc[u][v][0], acc[u][v][1]);
+    __syncthreads();
+    double* dinv_g = dinv + (size_t)J * NB * NB;
+    if (m == 0) {
+      stamp(J, m, 2);
+      ll_factor_inverse(T, Li, dinv_g, fail, Dblk, rdg);
+      stamp(J, m, 3);
+      __threadfence();
+      __syncthreads();
+      if (t == 0) st_release(&sync[LL_DIAG], J + 1);  // inv(L_JJ) is published: the rest of the column can finish
+      stamp(J, m, 4);
+      ll_multiply_store<2>(T, Li, NB, A, ld, r0, c0, rows_total);
+      stamp(J, m, 5);
+    } else {
+      bool stall = false;
+      if (t == 0) { stall = ld_relaxed(&sync[LL_DIAG]) <= J; if (!stall) __threadfence(); }
+      while (__syncthreads_or(stall)) {
+        if (t == 0) {
+          __nanosleep(m <= 1 ? 40 : 400);
+          stall = ld_relaxed(&sync[LL_DIAG]) <= J;
+          if (stall && ++spins > kSpinLimit) { atomicExch(&sync[LL_TIMEOUT], 1); stall = false; }
+          if (!stall) __threadfence();
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < (NB * NB / 2) / 128; ++q) {
+        const int e = t + 128 * q, row = e >> 5, piece = e & 31;
+        cp_async16(&Li[row * TP + 2 * piece], dinv_g + row * NB + 2 * piece);
+      }
+      stamp(J, m, 2);
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncthreads();
+      stamp(J, m, 3);
+      // top row block first: the next column's diagonal tile is waiting for it when this is tile m = 1
+      ll_multiply_store<2>(T, Li, 0, A, ld, r0, c0, rows_total);
+      __threadfence();
+      __syncthreads();
+      if (t == 0) st_release(&rb_done[rb0], J + 1);
+      ll_multiply_store<2>(T, Li, NB, A, ld, r0, c0, rows_total);
+      stamp(J, m, 5);
+    }
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      if (m == 0) st_release(&rb_done[rb0], J + 1);
+      if (rb0 + 1 < nrb) st_release(&rb_done[rb0 + 1], J + 1);
+    }
+    stamp(J, m, 6);
+  }
+}
+
 // ---- backward substitution in one launch ---------------------------------------------------------
 // CTA handles 64-column blocks b = nblk-1-blockIdx.x, then b - gridDim.x, ... (descending, so that a
 // CTA never waits on a block owned by a CTA that is not yet resident).
@@ -904,6 +1309,11 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double* __res
   }
 }
 
+// a spin that ran into its limit means the factor is garbage: report it like a failed factorisation
+__global__ void chol_ll_check_kernel(const int* __restrict__ sync, int* __restrict__ fail) {
+  if (sync[LL_TIMEOUT]) atomicExch(fail, 2);
+}
+
 __global__ void chol_pad_kernel(double* __restrict__ A, int ld, int n, int n_pad) {
   const int i = n + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) A[(size_t)i * ld + i] = 1.0;
@@ -929,6 +1339,17 @@ int DenseChol::Init(int n_, cudaStream_t st) {
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ready), sizeof(int) * nblk, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rdiag), sizeof(double) * n_pad, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&dscr), sizeof(double) * 2 * NB * NB, st));
+  {  // tile tasks of the left-looking kernel: block column J has ceil((row blocks from the diagonal down) / 2) tiles
+    const int nrb = (rows_total + NB - 1) / NB;
+    h_cols.assign(nblk + 1, 0);
+    for (int J = 0; J < nblk; ++J) h_cols[J + 1] = h_cols[J] + (nrb - J + 1) / 2;
+    ll_sync_ints = LL_RB + nrb + 8;
+    THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ll_sync), sizeof(int) * ll_sync_ints, st));
+    THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ll_cols), sizeof(int) * (nblk + 1), st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(ll_cols, h_cols.data(), sizeof(int) * (nblk + 1), cudaMemcpyHostToDevice, st));
+    const char* mode = getenv("THB_K4_MODE");
+    legacy = mode && !strcmp(mode, "legacy");
+  }
   static std::once_flag attr_once[64];
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
@@ -942,6 +1363,7 @@ int DenseChol::Init(int n_, cudaStream_t st) {
     set((const void*)chol_panel_kernel, kPanelSmem);
     set((const void*)chol_panel3_kernel, kPanel3Smem);
     set((const void*)chol_dp_kernel, kDpSmem);
+    set((const void*)chol_ll_kernel, kLlSmem);
     set((const void*)chol_update_kernel<OB, OB>, (int)(STAGES * (OB + OB) * LDK * sizeof(double)));
     set((const void*)chol_update2_kernel<true, true, 128>, kUpd2Smem);
     set((const void*)chol_update64_kernel<64>, kUpd64Smem);
@@ -952,6 +1374,12 @@ int DenseChol::Init(int n_, cudaStream_t st) {
   THB_CUDA_CHECK(attr_err);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   num_sms = sms > 0 ? sms : 148;
+  {  // the persistent grid must be co-resident: its CTAs spin on each other's progress counters
+    int per_sm = 0;
+    THB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_ll_kernel, 128, kLlSmem));
+    if (per_sm < 1) THB_FAIL(THB_E_CUDA, "chol_ll_kernel does not fit an SM");
+    ll_grid = std::min(per_sm * num_sms, h_cols[nblk]);
+  }
   // the latency-bound diag/panel chain is the critical path: its CTAs must win free SM slots against the trailing update
   int prio_lo = 0, prio_hi = 0;
   THB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
@@ -971,7 +1399,9 @@ void DenseChol::Free(cudaStream_t st) {
   if (ready) cudaFreeAsync(ready, st);
   if (rdiag) cudaFreeAsync(rdiag, st);
   if (dscr) cudaFreeAsync(dscr, st);
-  A = dinv = x = rdiag = dscr = nullptr; ready = nullptr;
+  if (ll_sync) cudaFreeAsync(ll_sync, st);
+  if (ll_cols) cudaFreeAsync(ll_cols, st);
+  A = dinv = x = rdiag = dscr = nullptr; ready = nullptr; ll_sync = ll_cols = nullptr;
   if (s2) { cudaStreamDestroy(s2); s2 = nullptr; }
   if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
   for (int i = 0; i < 4; ++i) {
@@ -1017,6 +1447,36 @@ void DenseChol::PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches)
 // runs two blocks ahead of the bulk updates instead of waiting for each of them (the r01 schedule had the next
 // block-column update queued behind the whole trailing update). Event rings of four: a dependency spans <= 3 blocks.
 int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
+  if (legacy) return FactorLegacy(st, fail_flag, launches);
+  // one persistent kernel factors (left-looking tile tasks, see chol_ll_kernel), forward-substitutes the rhs row and leaves
+  // the inverted diagonal factors in dinv; then the one-launch backward substitution
+  THB_CUDA_CHECK(cudaMemsetAsync(ll_sync, 0, sizeof(int) * ll_sync_ints, st));
+  long long* prof = nullptr;
+  const bool want_prof = getenv("THB_K4_PROF") != nullptr;
+  if (want_prof) { cudaMalloc(&prof, sizeof(long long) * nblk * 16); cudaMemset(prof, 0, sizeof(long long) * nblk * 16); }
+  chol_ll_kernel<<<ll_grid, 128, kLlSmem, st>>>(A, ld, nblk, rows_total, ll_cols, ll_sync, dinv, fail_flag, prof);
+  if (want_prof) {  // debugging aid: per-column phase stamps of the chain (ns, relative to the first stamp)
+    std::vector<long long> h(nblk * 16);
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h.data(), prof, sizeof(long long) * nblk * 16, cudaMemcpyDeviceToHost);
+    cudaFree(prof);
+    const long long t0 = h[0];
+    for (int J = 0; J < nblk; ++J) {
+      fprintf(stderr, "K4PROF J=%d", J);
+      for (int m = 0; m < 2; ++m) { fprintf(stderr, " |"); for (int k = 0; k < 7; ++k) fprintf(stderr, " %lld", h[(J * 2 + m) * 8 + k] ? h[(J * 2 + m) * 8 + k] - t0 : -1); }
+      fprintf(stderr, "\n");
+    }
+  }
+  chol_ll_check_kernel<<<1, 1, 0, st>>>(ll_sync, fail_flag);
+  chol_copy_row_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(A + (size_t)n_pad * ld, x, n_pad);
+  THB_CUDA_CHECK(cudaMemsetAsync(ready, 0, sizeof(int) * nblk, st));
+  chol_backsolve_kernel<<<std::min(nblk, num_sms), 256, kBackSmem, st>>>(A, ld, nblk, dinv, x, ready);
+  *launches += 4;
+  THB_CUDA_CHECK(cudaGetLastError());
+  return THB_OK;
+}
+
+int DenseChol::FactorLegacy(cudaStream_t st, int* fail_flag, int* launches) {
   const int nob = n_pad / OB;
   THB_CUDA_CHECK(cudaEventRecord(ev_start, st));
   THB_CUDA_CHECK(cudaStreamWaitEvent(s2, ev_start, 0));

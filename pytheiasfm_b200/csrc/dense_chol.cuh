@@ -2,6 +2,8 @@
 #ifndef THB_DENSE_CHOL_CUH_
 #define THB_DENSE_CHOL_CUH_
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace thb {
@@ -14,6 +16,10 @@ struct DenseChol {
   double* dscr = nullptr;  // two 64 x 64 copies of the next diagonal blocks (input of the fused diag + panel kernel)
   double* x = nullptr;     // n_pad solution
   int* ready = nullptr;    // per-64-block flags of the backward substitution
+  int* ll_sync = nullptr;  // task counter + progress counters of the left-looking tile kernel
+  int* ll_cols = nullptr;  // first task index of every 64-column block (+ total)
+  int ll_grid = 0, ll_sync_ints = 0;
+  bool legacy = false;     // THB_K4_MODE=legacy: the r01 right-looking multi-launch schedule (kept for A/B timing)
 
   int Init(int n, cudaStream_t st);  // stream-ordered allocations
   void Free(cudaStream_t st);
@@ -23,6 +29,8 @@ struct DenseChol {
 
  private:
   void PanelPair(cudaStream_t q, int ob, int* fail_flag, int* launches);
+  int FactorLegacy(cudaStream_t st, int* fail_flag, int* launches);
+  std::vector<int> h_cols;
   cudaStream_t s2 = nullptr;  // lookahead stream for the diag/panel chain
   cudaEvent_t ev_start = nullptr, ev_pp[4] = {nullptr, nullptr, nullptr, nullptr}, ev_c2[4] = {nullptr, nullptr, nullptr, nullptr};
 };

@@ -622,6 +622,7 @@ struct RansacShared {
   double best_cost;
   int max_iterations, it0, finished, num_iterations, have_best, pair;
   unsigned long long stat_samples, stat_models, stat_data;
+  long long cyc[4];  // draw, solve, score, scan
 };
 
 // Persistent grid (three CTAs per SM) pulling pairs from an atomic counter: RANSAC iteration counts differ by 100x
@@ -671,6 +672,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     }
     S.it0 = 0; S.finished = 0; S.num_iterations = 0; S.have_best = 0;
     S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
+    S.cyc[0] = S.cyc[1] = S.cyc[2] = S.cyc[3] = 0;
     memset(&S.best, 0, sizeof(Model));
   }
   __syncthreads();
@@ -681,6 +683,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     const int it0 = S.it0;
     const int nit = min(BI, S.max_iterations - it0);
     // ---- draw
+    long long tick = clock64();
     if (t == 0) {
       for (int b = 0; b < nit; ++b)
         for (int i = 0; i < SS; ++i) {
@@ -691,6 +694,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
         }
     }
     __syncthreads();
+    if (t == 0) { const long long now = clock64(); S.cyc[0] += now - tick; tick = now; }
     // ---- solve: thread b = iteration it0 + b
     if (t < BI) {
       int nm = 0;
@@ -708,6 +712,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
       for (int b = 0; b < BI; ++b) { S.model_start[b] = acc; acc += (b < nit) ? S.nmodels[b] : 0; }
       S.model_start[BI] = acc;
       S.stat_samples += nit; S.stat_models += acc;
+      const long long now = clock64(); S.cyc[1] += now - tick; tick = now;
     }
     __syncthreads();
     // ---- score: warp w takes flat models w, w + NW, ...
@@ -726,6 +731,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     __syncthreads();
     // ---- scan in (iteration, model) order
     if (t == 0) {
+      { const long long now = clock64(); S.cyc[2] += now - tick; tick = now; }
       int it = it0;
       for (int b = 0; b < nit; ++b, ++it) {
         if (it >= S.max_iterations) break;
@@ -743,6 +749,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
         }
       }
       S.it0 = it;
+      S.cyc[3] += clock64() - tick;
     }
     __syncthreads();
   }
@@ -755,6 +762,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
       if (stats) {
         atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)S.num_iterations); atomicAdd(stats + 2, S.stat_samples);
         atomicAdd(stats + 3, S.stat_models + 1); atomicAdd(stats + 4, S.stat_data + scored);
+        for (int k = 0; k < 4; ++k) atomicAdd(stats + 6 + k, (unsigned long long)S.cyc[k]);
       }
       out->success = 1;
       out->num_inliers = ninl;
@@ -900,10 +908,10 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   double* d_cost = B.get<double>((size_t)grid * BI * MAXM);
   int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
   int* d_counter = B.get<int>(1);
-  unsigned long long* d_stats = B.get<unsigned long long>(6);
+  unsigned long long* d_stats = B.get<unsigned long long>(10);
   if (!d_models || !d_cost || !d_ninl || !d_counter || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 6, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
   k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats);
   THB_CUDA_CHECK(cudaGetLastError());
   THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
