@@ -108,7 +108,7 @@ typedef struct ThbBaOptions {
   int32_t loss_function_type; /* THB_LOSS_*                                           */
   int32_t linear_solver;      /* THB_SOLVER_*                                         */
   int32_t use_homogeneous_point_parametrization; /* SphereManifold<4> on points       */
-  int32_t use_inner_iterations; /* must be 0: THB_E_UNSUPPORTED otherwise */
+  int32_t use_inner_iterations; /* ceres inner iterations with Theia's reversed ordering (bundle_adjuster.cc:329-334) */
   int32_t max_num_iterations;
   int32_t jacobi_scaling;     /* Ceres default true                                   */
   int32_t verbose;

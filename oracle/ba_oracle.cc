@@ -146,7 +146,6 @@ class BaOracle {
     if (P.memory_space != THB_MEM_HOST) return THB_E_INVALID_ARGUMENT;
     if (no > 0 && (!P.cam_ext || !P.cam_group || !P.intr || !P.intr_model || !P.pts || !P.obs_cam ||
                    !P.obs_pt || !P.obs_xy)) return THB_E_INVALID_ARGUMENT;
-    if (O.use_inner_iterations) return THB_E_UNSUPPORTED;
     for (int g = 0; g < ng; ++g) if (NumIntrinsics(P.intr_model[g]) < 0) return THB_E_UNSUPPORTED;
     for (int c = 0; c < nc; ++c) if (P.cam_group[c] < 0 || P.cam_group[c] >= ng) return THB_E_INVALID_ARGUMENT;
     for (int i = 0; i < no; ++i)
@@ -606,6 +605,196 @@ class BaOracle {
     return acc;
   }
 
+  // ---- inner iterations: ceres::internal::CoordinateDescentMinimizer (external) ---------------------
+  // Theia reverses the Schur ordering for them (bundle_adjuster.cc:329-334): extrinsics blocks first, then the shared
+  // intrinsics blocks, then the points. Every non-constant parameter block is minimised on its own - all other blocks
+  // constant at their current values - over the residual blocks that depend on it, by a TrustRegionMinimizer with
+  // default Minimizer::Options (50 iterations, tolerances 1e-6 / 1e-10 / 1e-8, Jacobi scaling, no bounds line search),
+  // a LevenbergMarquardtStrategy with default TrustRegionStrategy::Options (radius 1e4, maximum 1e32) and DENSE_QR.
+  // The blocks of one group share no residual, so solving them in parallel equals solving them one after the other.
+  enum { BLK_CAM = 0, BLK_INTR = 1, BLK_PT = 2 };
+
+  void BuildInnerLists() {
+    if (!cam_start.empty()) return;
+    cam_start.assign(nc + 1, 0); grp_start.assign(ng + 1, 0);
+    for (int i = 0; i < no; ++i) { cam_start[P.obs_cam[i] + 1]++; grp_start[P.cam_group[P.obs_cam[i]] + 1]++; }
+    for (int c = 0; c < nc; ++c) cam_start[c + 1] += cam_start[c];
+    for (int g = 0; g < ng; ++g) grp_start[g + 1] += grp_start[g];
+    cam_list.resize(no); grp_list.resize(no);
+    std::vector<int> cc(cam_start.begin(), cam_start.end() - 1), gc(grp_start.begin(), grp_start.end() - 1);
+    for (int i = 0; i < no; ++i) { cam_list[cc[P.obs_cam[i]]++] = i; grp_list[gc[P.cam_group[P.obs_cam[i]]]++] = i; }
+  }
+
+  // Residuals (robustified) and tangent-space Jacobian of the block over its own residual blocks.
+  bool EvalBlock(const State& s, int kind, int idx, const int* list, int n, bool want_jac, double* cost,
+                 std::vector<double>* r_out, std::vector<double>* J_out, int dim) const {
+    double total = 0.0;
+    if (want_jac) { r_out->assign((size_t)2 * n, 0.0); J_out->assign((size_t)2 * n * dim, 0.0); }
+    double PJ[12];
+    if (want_jac && kind == BLK_PT && dim == 3) SpherePlusJacobian(&s.pts[(size_t)idx * 4], PJ);
+    for (int q = 0; q < n; ++q) {
+      const int i = list[q];
+      double r[2], jc[12], ji[2 * KS], jp[8];
+      if (!EvalObsAmbient(s, i, want_jac, r, jc, ji, jp)) return false;
+      const double sq = r[0] * r[0] + r[1] * r[1];
+      double rho[3];
+      EvaluateLoss(O.loss_function_type, O.robust_loss_width, sq, rho);
+      total += 0.5 * rho[0];
+      if (!want_jac) continue;
+      double t[2][KS];
+      const int c = P.obs_cam[i], g = P.cam_group[c];
+      for (int a = 0; a < 2; ++a) {
+        if (kind == BLK_CAM) for (int k = 0; k < dim; ++k) t[a][k] = jc[a * 6 + cam_idx[c][k]];
+        else if (kind == BLK_INTR) for (int k = 0; k < dim; ++k) t[a][k] = ji[a * KS + intr_idx[g][k]];
+        else if (dim == 3) for (int k = 0; k < 3; ++k) { double v = 0.0; for (int u = 0; u < 4; ++u) v += jp[a * 4 + u] * PJ[u * 3 + k]; t[a][k] = v; }
+        else for (int k = 0; k < 4; ++k) t[a][k] = jp[a * 4 + k];
+      }
+      const double sqrt_rho1 = std::sqrt(rho[1]);
+      double residual_scaling = sqrt_rho1, alpha_sq_norm = 0.0;
+      if (!(sq == 0.0 || rho[2] <= 0.0)) {
+        const double D = 1.0 + 2.0 * sq * rho[2] / rho[1];
+        const double alpha = 1.0 - std::sqrt(D);
+        residual_scaling = sqrt_rho1 / (1 - alpha);
+        alpha_sq_norm = alpha / sq;
+      }
+      for (int k = 0; k < dim; ++k) {
+        if (alpha_sq_norm == 0.0) { t[0][k] *= sqrt_rho1; t[1][k] *= sqrt_rho1; }
+        else {
+          const double rtj = t[0][k] * r[0] + t[1][k] * r[1];
+          t[0][k] = sqrt_rho1 * (t[0][k] - alpha_sq_norm * r[0] * rtj);
+          t[1][k] = sqrt_rho1 * (t[1][k] - alpha_sq_norm * r[1] * rtj);
+        }
+      }
+      (*r_out)[2 * q] = r[0] * residual_scaling; (*r_out)[2 * q + 1] = r[1] * residual_scaling;
+      for (int a = 0; a < 2; ++a) for (int k = 0; k < dim; ++k) (*J_out)[((size_t)2 * q + a) * dim + k] = t[a][k];
+    }
+    *cost = total;
+    return true;
+  }
+
+  // ParameterBlock::Plus of one block (manifold Plus, then the box projection), in place on a copy of the block.
+  void BlockPlus(int kind, int idx, const double* xb, const double* d, int dim, double* out) const {
+    if (kind == BLK_CAM) {
+      for (int k = 0; k < 6; ++k) out[k] = xb[k];
+      for (int k = 0; k < dim; ++k) out[cam_idx[idx][k]] += d[k];
+    } else if (kind == BLK_INTR) {
+      for (int k = 0; k < KS; ++k) out[k] = xb[k];
+      for (int k = 0; k < dim; ++k) out[intr_idx[idx][k]] += d[k];
+      out[0] = std::max(out[0], 1.0);
+      if (P.intr_model[idx] == DOUBLE_SPHERE) { out[5] = std::min(std::max(out[5], -1.0), 1.0); out[6] = std::min(std::max(out[6], 0.0), 1.0); }
+      else if (P.intr_model[idx] == EXTENDED_UNIFIED) { out[5] = std::min(std::max(out[5], 0.0), 1.0); out[6] = std::max(out[6], 0.1); }
+    } else if (dim == 3) {
+      SpherePlus(xb, d, out);
+    } else {
+      for (int k = 0; k < 4; ++k) out[k] = xb[k] + d[k];
+    }
+  }
+
+  // TrustRegionMinimizer::Minimize on one parameter block; s is updated in place on success.
+  void InnerSolve(State* s, int kind, int idx) const {
+    const int* list; int n, dim, bs; double* xb;
+    if (kind == BLK_CAM) { list = &cam_list[cam_start[idx]]; n = cam_start[idx + 1] - cam_start[idx]; dim = cam_td[idx]; bs = 6; xb = &s->cam[(size_t)idx * 6]; }
+    else if (kind == BLK_INTR) { list = &grp_list[grp_start[idx]]; n = grp_start[idx + 1] - grp_start[idx]; dim = intr_td[idx]; bs = intr_K[idx]; xb = &s->intr[(size_t)idx * KS]; }
+    else { list = &pt_list[pt_start[idx]]; n = pt_start[idx + 1] - pt_start[idx]; dim = pt_td[idx]; bs = 4; xb = &s->pts[(size_t)idx * 4]; }
+    if (dim == 0 || n == 0) return;
+    const int store = kind == BLK_INTR ? KS : bs;
+    double x0[KS], cand[KS];
+    for (int k = 0; k < store; ++k) x0[k] = xb[k];  // the minimiser's x; xb follows the best point
+    auto norm_of = [&](const double* v) { double q = 0.0; for (int k = 0; k < bs; ++k) q += v[k] * v[k]; return std::sqrt(q); };
+    std::vector<double> r, J;
+    double x_cost = 0.0, scale[KS], g[KS], diag[KS];
+    auto evaluate_gj = [&](bool first) {
+      if (!EvalBlock(*s, kind, idx, list, n, true, &x_cost, &r, &J, dim)) return false;
+      for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * r[q]; g[k] = a; }
+      if (first) for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; scale[k] = 1.0 / (1.0 + std::sqrt(a)); }
+      for (int q = 0; q < 2 * n; ++q) for (int k = 0; k < dim; ++k) J[(size_t)q * dim + k] *= scale[k];
+      return true;
+    };
+    if (!evaluate_gj(true)) return;  // IterationZero fails: FAILURE, parameters untouched
+    double x_norm = norm_of(x0), radius = 1e4, decrease_factor = 2.0, gmax = 0.0;
+    bool reuse_diagonal = false, step_ok = true;
+    int iteration = 0, invalid = 0;
+    for (;;) {
+      if (iteration >= 50) break;
+      if (step_ok) { gmax = 0.0; for (int k = 0; k < dim; ++k) gmax = std::max(gmax, std::fabs(g[k])); if (gmax <= 1e-10) break; }
+      if (radius <= 1e-32) break;
+      ++iteration;
+      step_ok = false;
+      if (!reuse_diagonal)
+        for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; diag[k] = std::min(std::max(a, 1e-6), 1e32); }
+      reuse_diagonal = true;
+      // (J^T J + D^2) y = J^T r with D^2 = diag / radius; step = -y (DENSE_QR on [J; D] in Ceres: the same least squares)
+      double M[KS * KS], b[KS], y[KS];
+      for (int a = 0; a < dim; ++a) {
+        double bb = 0.0; for (int q = 0; q < 2 * n; ++q) bb += J[(size_t)q * dim + a] * r[q]; b[a] = bb;
+        for (int c = 0; c <= a; ++c) { double v = 0.0; for (int q = 0; q < 2 * n; ++q) v += J[(size_t)q * dim + a] * J[(size_t)q * dim + c]; M[a * dim + c] = v; M[c * dim + a] = v; }
+        M[a * dim + a] += diag[a] / radius;
+      }
+      bool valid = DenseCholeskySolve(dim, M, b, y);
+      double step[KS], mcc = 0.0;
+      if (valid) {
+        for (int k = 0; k < dim; ++k) step[k] = -y[k];
+        for (int q = 0; q < 2 * n; ++q) { double m = 0.0; for (int k = 0; k < dim; ++k) m += J[(size_t)q * dim + k] * step[k]; mcc += -(m * (r[q] + m / 2.0)); }
+        valid = std::isfinite(mcc) && mcc > 0.0;
+      }
+      if (!valid) {
+        if (++invalid >= 5) break;
+        radius /= decrease_factor; decrease_factor *= 2.0;
+        continue;
+      }
+      invalid = 0;
+      double delta[KS];
+      for (int k = 0; k < dim; ++k) delta[k] = step[k] * scale[k];
+      BlockPlus(kind, idx, x0, delta, dim, cand);
+      for (int k = 0; k < store; ++k) xb[k] = cand[k];  // evaluate the candidate in place
+      double cand_cost;
+      std::vector<double> dummy_r, dummy_J;
+      if (!EvalBlock(*s, kind, idx, list, n, false, &cand_cost, &dummy_r, &dummy_J, dim)) cand_cost = kMaxDouble;
+      for (int k = 0; k < store; ++k) xb[k] = x0[k];
+      double sn = 0.0; for (int k = 0; k < bs; ++k) sn += (cand[k] - x0[k]) * (cand[k] - x0[k]);
+      if (std::sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) break;
+      const double cost_change = x_cost - cand_cost;
+      if (std::fabs(cost_change) <= 1e-6 * x_cost) break;
+      const double rel = cand_cost >= kMaxDouble ? std::numeric_limits<double>::lowest() : cost_change / mcc;
+      if (rel > 1e-3) {
+        for (int k = 0; k < store; ++k) { x0[k] = cand[k]; xb[k] = cand[k]; }
+        x_norm = norm_of(x0);
+        if (!evaluate_gj(false)) break;
+        step_ok = true;
+        radius = std::min(1e32, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+        decrease_factor = 2.0; reuse_diagonal = false;
+      } else {
+        radius /= decrease_factor; decrease_factor *= 2.0;
+      }
+    }
+    for (int k = 0; k < store; ++k) xb[k] = x0[k];
+  }
+
+  static bool DenseCholeskySolve(int n, const double* A, const double* b, double* x) {
+    double L[KS * KS];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j <= i; ++j) {
+        double v = A[i * n + j];
+        for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k];
+        if (i == j) { if (!(v > 0.0) || !std::isfinite(v)) return false; L[i * n + i] = std::sqrt(v); }
+        else L[i * n + j] = v / L[j * n + j];
+      }
+    double y[KS];
+    for (int i = 0; i < n; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * n + k] * y[k]; y[i] = v / L[i * n + i]; }
+    for (int i = n - 1; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v / L[i * n + i]; }
+    for (int i = 0; i < n; ++i) if (!std::isfinite(x[i])) return false;
+    return true;
+  }
+
+  void CoordinateDescent(State* s) {
+    BuildInnerLists();
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int c = 0; c < nc; ++c) InnerSolve(s, BLK_CAM, c);
+    for (int g = 0; g < ng; ++g) InnerSolve(s, BLK_INTR, g);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int p = 0; p < np; ++p) InnerSolve(s, BLK_PT, p);
+  }
+
   void Log(ThbBaSummary* s, double cost, double radius) {
     if (s->iter_log_count < THB_MAX_ITER_LOG) {
       s->iter_cost[s->iter_log_count] = cost;
@@ -640,6 +829,12 @@ class BaOracle {
     Log(sum, x_cost + fixed_cost, radius);
     bool step_is_successful = true;  // iteration 0 counts as successful for the gradient test
     int iteration = 0;
+    // the preprocessor disables inner iterations on programs with fewer than two parameter blocks
+    int num_blocks = 0;
+    for (int c = 0; c < nc; ++c) num_blocks += cam_td[c] > 0;
+    for (int g = 0; g < ng; ++g) num_blocks += intr_td[g] > 0;
+    for (int p = 0; p < np; ++p) num_blocks += pt_td[p] > 0;
+    bool inner_enabled = O.use_inner_iterations != 0 && num_blocks >= 2;
     const auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     while (true) {
       // FinalizeIterationAndCheckIfMinimizerCanContinue
@@ -697,6 +892,21 @@ class BaOracle {
       double cand_cost;
       ++n_cost_eval;
       if (!Evaluate(cand, false, &cand_cost)) cand_cost = kMaxDouble;
+      // DoInnerIterationsIfNeeded (trust_region_minimizer.cc; external)
+      bool inner_useful = false;
+      if (inner_enabled && cand_cost < kMaxDouble) {
+        State inner = cand;
+        CoordinateDescent(&inner);
+        double inner_cost;
+        ++n_cost_eval;
+        if (Evaluate(inner, false, &inner_cost)) {
+          cand = inner;
+          model_cost_change += cand_cost - inner_cost;
+          inner_useful = inner_cost < x_cost;
+          inner_enabled = 1.0 - inner_cost / cand_cost > 1e-3;  // inner_iteration_tolerance
+          cand_cost = inner_cost;
+        }
+      }
       // ParameterToleranceReached
       const double step_norm = NormDiff(x, &cand);
       if (O.parameter_tolerance >= 0.0 && step_norm <= O.parameter_tolerance * (x_norm + O.parameter_tolerance)) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
@@ -705,7 +915,7 @@ class BaOracle {
       if (O.function_tolerance >= 0.0 && std::fabs(cost_change) <= O.function_tolerance * x_cost) { sum->termination_type = THB_TERM_CONVERGENCE; break; }
       // IsStepSuccessful (monotonic steps)
       const double relative_decrease = cand_cost >= kMaxDouble ? std::numeric_limits<double>::lowest() : cost_change / model_cost_change;
-      if (relative_decrease > O.min_relative_decrease) {
+      if (inner_useful || relative_decrease > O.min_relative_decrease) {
         x = cand; x_norm = NormDiff(x, nullptr);
         if (!EvaluateGradientAndJacobian(iteration)) { sum->termination_type = THB_TERM_FAILURE; break; }
         step_is_successful = true;
@@ -736,6 +946,7 @@ class BaOracle {
   int nc = 0, ng = 0, np = 0, no = 0, n_tan = 0, n_pt_tan = 0, n_red = 0;
   State x;
   std::vector<int> cam_td, intr_td, intr_K, pt_td, pt_off, intr_off, cam_off, pt_start, pt_list;
+  std::vector<int> cam_start, cam_list, grp_start, grp_list;
   std::vector<std::array<int, 6>> cam_idx;
   std::vector<std::array<int, KS>> intr_idx;
   std::vector<char> fixed;

@@ -142,11 +142,16 @@ __device__ __forceinline__ void householder4(const double x[4], double v[3], dou
 }
 
 // Residual only: ReprojectionError<Model>::operator() (reprojection_error.h:49-114).
+// cam_rec != nullptr: the camera record is read from there (shared or global memory, plain loads) instead of S.camd[c] -
+// the inner-iteration kernels evaluate a camera whose record changes inside the kernel.
 template <int MODEL>
 __device__ __forceinline__ bool eval_residual(const BaConst& K, const BaState& S, int c, int p, double2 xy,
-                                              double2 si, double r[2]) {
+                                              double2 si, double r[2], const double* cam_rec = nullptr) {
   double cd[12];
-  {
+  if (cam_rec) {
+#pragma unroll
+    for (int k = 0; k < 12; ++k) cd[k] = cam_rec[k];
+  } else {
     const double* rec = S.camd + (size_t)c * CAMD;
     ld256(rec, cd); ld256(rec + 4, cd + 4); ld256(rec + 8, cd + 8);
   }
@@ -178,13 +183,16 @@ __device__ __forceinline__ bool eval_obs(const BaConst& K, const BaState& S, int
                                          const double* cs, const double* ps, const double* is, double r[2],
                                          double jc[12], double jp[2 * PD], double* ji, double* half_rho,
                                          unsigned cam_smem = 0, unsigned pt_x = 0, int pt_stride = 0, int pt_const_flag = 0,
-                                         const double* pt_scale = nullptr) {
+                                         const double* pt_scale = nullptr, const double* cam_rec = nullptr) {
   constexpr int ND = 3 + NK;
   typedef Dual<ND> D;
   double cd[CAMD];
   if (CAM_SMEM) {
 #pragma unroll
     for (int k = 0; k < CD_SCALE / 2; ++k) lds128(cam_smem_piece(cam_smem, c, k), cd + 2 * k);  // column scales: read where used
+  } else if (cam_rec) {
+#pragma unroll
+    for (int k = 0; k < CAMD; ++k) cd[k] = cam_rec[k];
   } else {
     const double* rec = S.camd + (size_t)c * CAMD;
 #pragma unroll

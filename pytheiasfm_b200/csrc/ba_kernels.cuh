@@ -7,19 +7,21 @@
 namespace thb {
 
 // indices into the per-iteration device scalar block
-enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_STEP2 = 2, SC_XNEW2 = 3, SC_GTD = 4, SC_MCC = 5, SC_GRADMAX = 6, SC_COUNT = 8 };
+enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_STEP2 = 2, SC_XNEW2 = 3, SC_GTD = 4, SC_MCC = 5, SC_GRADMAX = 6, SC_SINK = 7,
+       SC_COST_INNER = 8, SC_STEP2_INNER = 9, SC_XNEW2_INNER = 10, SC_COUNT = 12 };
 
 // Variable intrinsics blocks sit behind the camera blocks in the reduced system: block `slot` occupies the NI indices
 // from 6*nc + NI*slot. Coordinates that are constant (SubsetManifold, bundle_adjuster.cc:429-441) or beyond the model's
 // parameter count keep zero Jacobian columns and a unit diagonal, so their step is exactly zero.
 constexpr int NI = 9;
 constexpr int MAX_VG = 8;
-enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_COUNT = 4 };
+enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_EVAL_INNER = 4, FL_COUNT = 8 };
 
 // ---------------------------------------------------------------------------------------------
 // Problem setup on the device (ValidateAndCreate): what BundleAdjuster::AddView/AddTrack decide while walking the
 // reconstruction (bundle_adjuster.cc:116-221) - which blocks exist, which are constant - plus the index validation.
-enum { SF_BAD_INDEX = 0, SF_BAD_GROUP = 1, SF_RED_VARIABLE = 2, SF_PT_VARIABLE = 3, SF_HAS_FIXED = 4, SF_COUNT = 8 };
+enum { SF_BAD_INDEX = 0, SF_BAD_GROUP = 1, SF_RED_VARIABLE = 2, SF_PT_VARIABLE = 3, SF_HAS_FIXED = 4, SF_NUM_CAM_VAR = 5, SF_NUM_PT_VAR = 6,
+       SF_COUNT = 8 };
 
 __global__ void k_setup_check_groups(int nc, int ng, const int* __restrict__ cam_group, int* __restrict__ flags) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,12 +49,12 @@ __global__ void k_setup_const(int nc, int np, const int* __restrict__ cam_start,
   if (i < nc) {
     const uint8_t v = (cam_start[i + 1] == cam_start[i]) ? (uint8_t)THB_CAM_CONST_ALL : (uint8_t)(cam_const[i] & THB_CAM_CONST_ALL);
     cam_const[i] = v;
-    if (v != THB_CAM_CONST_ALL) flags[SF_RED_VARIABLE] = 1;
+    if (v != THB_CAM_CONST_ALL) { flags[SF_RED_VARIABLE] = 1; atomicAdd(flags + SF_NUM_CAM_VAR, 1); }
   } else if (i - nc < np) {
     const int p = i - nc;
     const uint8_t v = (pt_start[p + 1] == pt_start[p] || pt_const[p]) ? 1 : 0;
     pt_const[p] = v;
-    if (!v) flags[SF_PT_VARIABLE] = 1;
+    if (!v) { flags[SF_PT_VARIABLE] = 1; atomicAdd(flags + SF_NUM_PT_VAR, 1); }
   }
 }
 
@@ -84,12 +86,8 @@ __global__ void k_setup_slots(int no, const int* __restrict__ op_cam, const int*
 // Per-camera record (ba_device.cuh): angle-axis vector plus the scalar coefficients of the rotation
 // (ceres::AngleAxisRotatePoint semantics, incl. the first-order branch for theta^2 <= eps) and of the SO(3) left
 // Jacobian used for d(R v)/d(aa).
-__global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc, const double* __restrict__ cs,
-                             const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_group) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= nc) return;
-  const double wx = cam[6 * c + 3], wy = cam[6 * c + 4], wz = cam[6 * c + 5];
-  double* o = camd + (size_t)c * CAMD;
+__device__ __forceinline__ void cam_derive_record(const double* __restrict__ cam6, double* __restrict__ o) {
+  const double wx = cam6[3], wy = cam6[4], wz = cam6[5];
   const double th2 = wx * wx + wy * wy + wz * wz;
   o[CD_W] = wx; o[CD_W + 1] = wy; o[CD_W + 2] = wz;
   if (th2 > 2.220446049250313e-16) {
@@ -111,7 +109,14 @@ __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict_
   } else {
     o[CD_A] = 1.0; o[CD_B] = 0.0; o[CD_JA] = 0.0; o[CD_JB] = 0.0;
   }
-  o[CD_C] = cam[6 * c]; o[CD_C + 1] = cam[6 * c + 1]; o[CD_C + 2] = cam[6 * c + 2];
+  o[CD_C] = cam6[0]; o[CD_C + 1] = cam6[1]; o[CD_C + 2] = cam6[2];
+}
+__global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc, const double* __restrict__ cs,
+                             const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_group) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  double* o = camd + (size_t)c * CAMD;
+  cam_derive_record(cam + 6 * (size_t)c, o);
   const int cc = cam_const[c];
   for (int k = 0; k < 6; ++k) {
     const bool is_const = (cc & (k < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) != 0;

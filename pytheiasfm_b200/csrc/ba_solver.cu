@@ -16,6 +16,7 @@
 
 #include "ba_kernels.cuh"
 #include "track_ba.cuh"
+#include "inner_iter.cuh"
 #include "ba_setup.cuh"
 #include "dense_chol.cuh"
 
@@ -156,6 +157,15 @@ struct ThbBaSession {
   std::chrono::steady_clock::time_point t_create, t_solve_start;
   Arena arena;
   void* h_block = nullptr;  // pinned block behind h_scal / h_flag
+  // inner iterations (use_inner_iterations): ceres CoordinateDescentMinimizer state
+  bool inner_enabled = false;
+  double *d_bk_cam = nullptr, *d_bk_pts = nullptr, *d_bk_intr = nullptr;  // the candidate before the inner iterations
+  double *d_inner_ps = nullptr, *d_pts_scratch = nullptr, *d_inner_out = nullptr, *d_inner_scale = nullptr;
+  ThbTrackBaResult* d_inner_res = nullptr;
+  std::vector<int> h_slot_group, h_model;
+  std::vector<uint16_t> h_const;
+  std::vector<double> h_ilo, h_ihi;
+  int num_inner_steps = 0;
 };
 
 namespace {
@@ -455,6 +465,164 @@ int SolveAndStep(ThbBaSession* s) {
   return rc;
 }
 
+
+// ---- inner iterations (ceres CoordinateDescentMinimizer, inner_iter.cuh) on the candidate Xc ------------------------------
+template <int PD>
+int InnerIntrEvaluate(ThbBaSession* s, int sl, bool want_j, double* h_out) {
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_inner_out, 0, sizeof(double) * II_VALS, s->st));
+  const int grid = std::min(cdiv(s->no, 256), 4 * SmCount());
+  if (want_j) k_inner_intr<PD, true><<<grid, 256, 0, s->st>>>(s->K, s->Xc, s->Op, s->d_op_slot, sl, s->d_inner_scale, s->d_inner_out);
+  else k_inner_intr<PD, false><<<grid, 256, 0, s->st>>>(s->K, s->Xc, s->Op, s->d_op_slot, sl, s->d_inner_scale, s->d_inner_out);
+  ++s->sum.gpu_launches;
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_out, s->d_inner_out, sizeof(double) * II_VALS, cudaMemcpyDeviceToHost, s->st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  return THB_OK;
+}
+
+// TrustRegionMinimizer on one shared intrinsics block, driven from the host (a block owns up to every observation: each
+// evaluation is a full-grid launch). Mirrors k_inner_cam / the oracle's InnerSolve.
+template <int PD>
+int InnerIntrSolve(ThbBaSession* s, int sl) {
+  const InnerLmParams P;
+  const int g = s->h_slot_group[sl];
+  const int Kg = num_intrinsics(s->h_model[g]);
+  double x[KS], cand[KS], scale[NI], out[II_VALS];
+  double* d_x = s->Xc.intr + (size_t)g * KS;
+  THB_CUDA_CHECK(cudaMemcpyAsync(x, d_x, sizeof(double) * KS, cudaMemcpyDeviceToHost, s->st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  bool free_k[NI];
+  for (int k = 0; k < NI; ++k) { free_k[k] = k < Kg && !((s->h_const[g] >> k) & 1); scale[k] = 1.0; }
+  int rc;
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->d_inner_scale, scale, sizeof(double) * NI, cudaMemcpyHostToDevice, s->st));
+  if ((rc = InnerIntrEvaluate<PD>(s, sl, true, out)) != THB_OK) return rc;
+  if (out[55] > 0.0) return THB_OK;  // IterationZero failed: block untouched
+  { int e = 0; for (int a = 0; a < NI; ++a) { e += a; scale[a] = free_k[a] ? 1.0 / (1.0 + std::sqrt(out[e])) : 0.0; ++e; } }
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->d_inner_scale, scale, sizeof(double) * NI, cudaMemcpyHostToDevice, s->st));
+  if ((rc = InnerIntrEvaluate<PD>(s, sl, true, out)) != THB_OK) return rc;
+  double H[45], gr[NI], diag[NI], x_cost = out[54], x_norm = 0.0, radius = P.radius0, decrease_factor = 2.0;
+  for (int k = 0; k < 45; ++k) H[k] = out[k];
+  for (int k = 0; k < NI; ++k) gr[k] = out[45 + k];
+  for (int k = 0; k < Kg; ++k) x_norm += x[k] * x[k];
+  x_norm = std::sqrt(x_norm);
+  bool step_ok = true, reuse_diag = false, dirty = false;  // dirty: the device holds a rejected candidate
+  int iteration = 0, invalid = 0;
+  for (;;) {
+    if (iteration >= P.max_num_iterations) break;
+    if (step_ok) {
+      double gmax = 0.0;
+      for (int k = 0; k < NI; ++k) if (free_k[k]) gmax = std::max(gmax, std::fabs(gr[k] / scale[k]));
+      if (gmax <= P.gtol) break;
+    }
+    if (radius <= P.min_radius) break;
+    ++iteration;
+    step_ok = false;
+    if (!reuse_diag) { int e = 0; for (int a = 0; a < NI; ++a) { e += a; diag[a] = std::min(std::max(H[e], P.min_diag), P.max_diag); ++e; } }
+    reuse_diag = true;
+    double Mx[NI * NI], y[NI], mcc = 0.0;
+    { int e = 0; for (int a = 0; a < NI; ++a) for (int b = 0; b <= a; ++b) { Mx[a * NI + b] = H[e]; Mx[b * NI + a] = H[e]; ++e; } }
+    for (int a = 0; a < NI; ++a) Mx[a * NI + a] += diag[a] / radius;
+    bool valid = spd_solve<NI>(Mx, gr, y);
+    if (valid) {
+      double yg = 0.0, yHy = 0.0;
+      int e = 0;
+      for (int a = 0; a < NI; ++a) { yg += y[a] * gr[a]; for (int b = 0; b <= a; ++b) { yHy += (a == b ? 1.0 : 2.0) * y[a] * H[e] * y[b]; ++e; } }
+      mcc = yg - 0.5 * yHy;
+      valid = std::isfinite(mcc) && mcc > 0.0;
+    }
+    if (!valid) {
+      if (++invalid >= P.max_invalid) break;
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      continue;
+    }
+    invalid = 0;
+    for (int k = 0; k < KS; ++k) cand[k] = x[k];
+    for (int k = 0; k < NI; ++k)  // Plus, then the box projection of ParameterBlock::Plus (bounds of bundle_adjuster.cc:396-427)
+      if (k < KS) { if (free_k[k]) cand[k] = x[k] + (-y[k] * scale[k]); cand[k] = std::min(std::max(cand[k], s->h_ilo[NI * sl + k]), s->h_ihi[NI * sl + k]); }
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_x, cand, sizeof(double) * KS, cudaMemcpyHostToDevice, s->st));
+    dirty = true;
+    if ((rc = InnerIntrEvaluate<PD>(s, sl, false, out)) != THB_OK) return rc;
+    const double cand_cost = out[55] > 0.0 ? std::numeric_limits<double>::max() : out[54];
+    double sn = 0.0, cn = 0.0;
+    for (int k = 0; k < Kg; ++k) { sn += (cand[k] - x[k]) * (cand[k] - x[k]); cn += cand[k] * cand[k]; }
+    if (std::sqrt(sn) <= P.ptol * (x_norm + P.ptol)) break;
+    const double cost_change = x_cost - cand_cost;
+    if (std::fabs(cost_change) <= P.ftol * x_cost) break;
+    const double rel = cand_cost >= std::numeric_limits<double>::max() ? std::numeric_limits<double>::lowest() : cost_change / mcc;
+    if (rel > P.min_relative_decrease) {
+      for (int k = 0; k < KS; ++k) x[k] = cand[k];
+      dirty = false;
+      x_norm = std::sqrt(cn);
+      if ((rc = InnerIntrEvaluate<PD>(s, sl, true, out)) != THB_OK) return rc;
+      if (out[55] > 0.0) break;
+      for (int k = 0; k < 45; ++k) H[k] = out[k];
+      for (int k = 0; k < NI; ++k) gr[k] = out[45 + k];
+      x_cost = out[54];
+      step_ok = true;
+      const double u = 2.0 * rel - 1.0;
+      radius = std::min(P.max_radius, radius / std::max(1.0 / 3.0, 1.0 - u * u * u));
+      decrease_factor = 2.0; reuse_diag = false;
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0;
+    }
+  }
+  if (dirty) {
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_x, x, sizeof(double) * KS, cudaMemcpyHostToDevice, s->st));
+    THB_CUDA_CHECK(cudaStreamSynchronize(s->st));  // x lives on this stack frame
+  }
+  return THB_OK;
+}
+
+// DoInnerIterationsIfNeeded (ceres trust_region_minimizer.cc; external): refines the candidate Xc in place; the scalars
+// SC_COST_INNER / SC_STEP2_INNER / SC_XNEW2_INNER and FL_EVAL_INNER are on the host when it returns.
+template <int PD>
+int DoInnerIterations(ThbBaSession* s) {
+  cudaStream_t st = s->st;
+  const int nc = s->nc, np = s->np, ng = s->ng;
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->d_bk_cam, s->Xc.cam, sizeof(double) * 6 * nc, cudaMemcpyDeviceToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->d_bk_pts, s->Xc.pts, sizeof(double) * 4 * np, cudaMemcpyDeviceToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->d_bk_intr, s->Xc.intr, sizeof(double) * KS * ng, cudaMemcpyDeviceToDevice, st));
+  const InnerLmParams P;
+  // group 0: camera extrinsics
+  if (nc > 0) {
+    k_inner_cam<PD><<<nc, IC_THREADS, 0, st>>>(s->K, s->Xc, s->Oc, s->d_cam_start, P);
+    k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(s->Xc.cam, s->Xc.camd, nc, s->d_cs, s->d_cam_const, s->d_cam_group);
+    s->sum.gpu_launches += 2;
+  }
+  // group 1: shared intrinsics blocks
+  for (int sl = 0; sl < s->nvg; ++sl) { const int rc = InnerIntrSolve<PD>(s, sl); if (rc != THB_OK) return rc; }
+  // group 2: points
+  if (np > 0) {
+    TrackBaParams tp;
+    tp.max_num_iterations = P.max_num_iterations; tp.max_invalid = P.max_invalid; tp.jacobi_scaling = 1;
+    tp.ftol = P.ftol; tp.gtol = P.gtol; tp.ptol = P.ptol; tp.radius0 = P.radius0; tp.min_radius = P.min_radius; tp.max_radius = P.max_radius;
+    tp.min_relative_decrease = P.min_relative_decrease; tp.min_diag = P.min_diag; tp.max_diag = P.max_diag;
+    tp.rays = nullptr; tp.status = nullptr; tp.bundle_adjustment = 1; tp.cos_min_angle = -2.0; tp.sq_max_reprojection_error = 0.0;
+    BaState scratch = s->Xc;
+    scratch.pts = s->d_pts_scratch;
+    THB_CUDA_CHECK(cudaMemcpyAsync(s->d_pts_scratch, s->Xc.pts, sizeof(double) * 4 * np, cudaMemcpyDeviceToDevice, st));
+    k_track_ba<PD><<<cdiv(np, 64), 64, 0, st>>>(s->K, s->Xc, scratch, s->Op, s->d_pt_start, s->d_inner_ps, tp, s->d_inner_res);
+    ++s->sum.gpu_launches;
+  }
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_COST_INNER, 0, sizeof(double) * 3, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(s->d_flag + FL_EVAL_INNER, 0, sizeof(int), st));
+  RunCost(s, s->Xc, SC_COST_INNER, FL_EVAL_INNER);
+  ++s->sum.num_cost_evaluations;
+  k_step_norms<<<cdiv((long long)nc + np + ng, 256), 256, 0, st>>>(nc, np, ng, s->d_cam_const, s->d_pt_const, s->d_intr_slot, s->d_intr_model, s->X, s->Xc,
+                                                                  s->d_scal + SC_STEP2_INNER, s->d_scal + SC_XNEW2_INNER);
+  ++s->sum.gpu_launches;
+  ++s->num_inner_steps;
+  return ReadScalars(s);
+}
+
+int RestoreCandidate(ThbBaSession* s) {  // "Inner iteration failed": the trust-region candidate stands
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->Xc.cam, s->d_bk_cam, sizeof(double) * 6 * s->nc, cudaMemcpyDeviceToDevice, s->st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->Xc.pts, s->d_bk_pts, sizeof(double) * 4 * s->np, cudaMemcpyDeviceToDevice, s->st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(s->Xc.intr, s->d_bk_intr, sizeof(double) * KS * s->ng, cudaMemcpyDeviceToDevice, s->st));
+  k_cam_derive<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->Xc.cam, s->Xc.camd, s->nc, s->d_cs, s->d_cam_const, s->d_cam_group);
+  ++s->sum.gpu_launches;
+  return THB_OK;
+}
+
 void Terminate(ThbBaSession* s, int type) { s->sum.termination_type = type; s->finished = true; }
 
 // One pass of TrustRegionMinimizer's main loop. Returns THB_OK; sets s->finished on termination.
@@ -480,7 +648,7 @@ int OneIteration(ThbBaSession* s) {
   }
   ++s->iteration;
   s->step_is_successful = false;
-  const double model_cost_change = s->h_scal[SC_MCC];
+  double model_cost_change = s->h_scal[SC_MCC];
   bool step_valid = !(s->h_flag[FL_CHOL] || s->h_flag[FL_POINT]) && std::isfinite(model_cost_change) && model_cost_change > 0.0;
   if (!step_valid) {
     // HandleInvalidStep / LevenbergMarquardtStrategy::StepIsInvalid
@@ -515,9 +683,26 @@ int OneIteration(ThbBaSession* s) {
       }
     }
   }
-  const double cand_cost = s->h_flag[FL_EVAL_CAND] ? std::numeric_limits<double>::max() : s->h_scal[SC_COST_CAND];
+  double cand_cost = s->h_flag[FL_EVAL_CAND] ? std::numeric_limits<double>::max() : s->h_scal[SC_COST_CAND];
+  double step2 = s->h_scal[SC_STEP2], xnew2 = s->h_scal[SC_XNEW2];
+  // DoInnerIterationsIfNeeded
+  bool inner_useful = false;
+  if (s->inner_enabled && cand_cost < std::numeric_limits<double>::max()) {
+    rc = s->PD == 3 ? DoInnerIterations<3>(s) : DoInnerIterations<4>(s);
+    if (rc != THB_OK) return rc;
+    if (s->h_flag[FL_EVAL_INNER]) {
+      if ((rc = RestoreCandidate(s)) != THB_OK) return rc;
+    } else {
+      const double inner_cost = s->h_scal[SC_COST_INNER];
+      model_cost_change += cand_cost - inner_cost;
+      inner_useful = inner_cost < s->x_cost;
+      s->inner_enabled = 1.0 - inner_cost / cand_cost > 1e-3;  // inner_iteration_tolerance
+      cand_cost = inner_cost;
+      step2 = s->h_scal[SC_STEP2_INNER]; xnew2 = s->h_scal[SC_XNEW2_INNER];
+    }
+  }
   // ParameterToleranceReached
-  const double step_norm = std::sqrt(s->h_scal[SC_STEP2]);
+  const double step_norm = std::sqrt(step2);
   if (O.parameter_tolerance >= 0.0 && step_norm <= O.parameter_tolerance * (s->x_norm + O.parameter_tolerance)) { Terminate(s, THB_TERM_CONVERGENCE); return THB_OK; }
   // FunctionToleranceReached
   const double cost_change = s->x_cost - cand_cost;
@@ -525,9 +710,9 @@ int OneIteration(ThbBaSession* s) {
   // IsStepSuccessful (monotonic)
   const double relative_decrease = cand_cost >= std::numeric_limits<double>::max() ? std::numeric_limits<double>::lowest()
                                                                                    : cost_change / model_cost_change;
-  if (relative_decrease > O.min_relative_decrease) {
+  if (inner_useful || relative_decrease > O.min_relative_decrease) {
     std::swap(s->X, s->Xc);
-    s->x_norm = std::sqrt(s->h_scal[SC_XNEW2]);
+    s->x_norm = std::sqrt(xnew2);
     rc = EvaluateJacobian(s);  // EvaluateGradientAndJacobian(new_evaluation_point = false)
     if (rc != THB_OK) return rc;
     THB_CUDA_CHECK(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double), cudaMemcpyDeviceToHost, s->st));
@@ -558,7 +743,6 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   if (P->memory_space != THB_MEM_HOST && P->memory_space != THB_MEM_DEVICE) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad memory_space");
   if (P->num_observations > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->pts || !P->obs_cam || !P->obs_pt || !P->obs_xy))
     THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
-  if (O->use_inner_iterations) THB_FAIL(THB_E_UNSUPPORTED, "use_inner_iterations is not implemented (set it to false, as BundleAdjustView/Track do)");
   if (O->linear_solver != THB_SOLVER_SCHUR_CHOLESKY) THB_FAIL(THB_E_UNSUPPORTED, "only THB_SOLVER_SCHUR_CHOLESKY is implemented");
   if (O->loss_function_type < THB_LOSS_TRIVIAL || O->loss_function_type > THB_LOSS_TRUNCATED) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad loss type");
 
@@ -693,6 +877,14 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
     THB_TRY(M.Get(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
   }
   THB_TRY(s->chol.Init(std::max(1, s->n_red), st));
+  // the preprocessor disables inner iterations on programs with fewer than two parameter blocks (ceres)
+  s->inner_enabled = O->use_inner_iterations != 0 && h_setup[SF_NUM_CAM_VAR] + h_setup[SF_NUM_PT_VAR] + s->nvg >= 2;
+  if (s->inner_enabled) {
+    THB_TRY(M.Get(&s->d_bk_cam, (size_t)nc * 6)); THB_TRY(M.Get(&s->d_bk_pts, (size_t)np * 4)); THB_TRY(M.Get(&s->d_bk_intr, (size_t)ng * KS));
+    THB_TRY(M.Get(&s->d_inner_ps, (size_t)np * s->PD)); THB_TRY(M.Get(&s->d_pts_scratch, (size_t)np * 4));
+    THB_TRY(M.Get(&s->d_inner_out, II_VALS)); THB_TRY(M.Get(&s->d_inner_scale, NI)); THB_TRY(M.Get(&s->d_inner_res, np));
+    s->h_slot_group = slot_group; s->h_model = h_intr_model; s->h_const = h_intr_const;
+  }
   // box constraints of bundle_adjuster.cc:396-427
   std::vector<double> ilo((size_t)NI * s->nvg, -std::numeric_limits<double>::max()), ihi((size_t)NI * s->nvg, std::numeric_limits<double>::max());
   for (int sl = 0; sl < s->nvg; ++sl) {
@@ -709,6 +901,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_slot_group, slot_group.data(), sizeof(int) * s->nvg, cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_ilo, ilo.data(), sizeof(double) * ilo.size(), cudaMemcpyHostToDevice, st));
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_ihi, ihi.data(), sizeof(double) * ihi.size(), cudaMemcpyHostToDevice, st));
+  s->h_ilo = ilo; s->h_ihi = ihi;
   if (no > 0) k_setup_slots<<<cdiv(no, 256), 256, 0, st>>>(no, s->d_op_cam, s->d_op_pt, s->d_cam_group, s->d_intr_slot, s->d_cam_const, s->d_pt_const, s->d_op_slot, d_setup);
   // Ceres drops residual blocks whose parameter blocks are all constant (their cost is Summary::fixed_cost);
   // they would still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
@@ -795,7 +988,8 @@ int thb_device_count(void) {
 void thb_ba_default_options(ThbBaOptions* o) {
   if (!o) return;
   std::memset(o, 0, sizeof(*o));
-  // BundleAdjustmentOptions defaults (bundle_adjustment.h:87-167); use_inner_iterations is forced off
+  // BundleAdjustmentOptions defaults (bundle_adjustment.h:87-167), except use_inner_iterations: off here (the setting of
+  // every benchmark and of BundleAdjustView / Track); the pt.sfm adapter passes the reference default (on) through
   o->loss_function_type = THB_LOSS_TRIVIAL; o->robust_loss_width = 2.0;
   o->linear_solver = THB_SOLVER_SCHUR_CHOLESKY;
   o->use_homogeneous_point_parametrization = 1; o->use_inner_iterations = 0;
@@ -872,7 +1066,7 @@ int thb_ba_time_jacobian(ThbBaSession* s, int32_t repeats, int32_t flush_l2, dou
   THB_CUDA_CHECK(cudaEventCreate(&a)); THB_CUDA_CHECK(cudaEventCreate(&b));
   double total = 0.0;
   for (int i = 0; i < repeats; ++i) {
-    if (flush_l2) k_flush_read<<<148 * 8, 256, 0, s->st>>>(reinterpret_cast<const double2*>(s->d_flush), flush_bytes / sizeof(double2), s->d_scal + SC_COUNT - 1);
+    if (flush_l2) k_flush_read<<<148 * 8, 256, 0, s->st>>>(reinterpret_cast<const double2*>(s->d_flush), flush_bytes / sizeof(double2), s->d_scal + SC_SINK);
     THB_CUDA_CHECK(cudaEventRecord(a, s->st));
     RunJacobian(s, s->d_cs, s->d_ps);
     THB_CUDA_CHECK(cudaEventRecord(b, s->st));

@@ -119,7 +119,7 @@ def test_BundleAdjustReconstruction_full_and_partial(gen, ba_options):
     """pyexamples/sfm_pipeline_*.py usage: pt.sfm.BundleAdjustReconstruction(opts, recon) with HUBER loss."""
     gen.add_noise_to_views(noise_pos=1e-2, noise_angle=0.5)
     gen.add_noise_to_tracks(noise_track=1e-2)
-    ba_options.use_inner_iterations = False       # the only supported setting; True is rejected loudly (below)
+    ba_options.use_inner_iterations = False
     ba_options.loss_function_type = pt.sfm.LossFunctionType.HUBER
     ba_options.robust_loss_width = 2.0
     result = pt.sfm.BundleAdjustReconstruction(ba_options, gen.recon)
@@ -132,9 +132,13 @@ def test_BundleAdjustReconstruction_full_and_partial(gen, ba_options):
     assert result.success
     for v in gen.recon.ViewIds()[5:]:                # views outside the set keep their extrinsics (bundle_adjuster.cc:199-204)
         np.testing.assert_array_equal(gen.recon.View(v).Camera().GetPosition(), before[v])
-    ba_options.use_inner_iterations = True
-    with pytest.raises(RuntimeError, match="inner"):
-        pt.sfm.BundleAdjustReconstruction(ba_options, gen.recon)
+    # the reference's default options (inner iterations ON, bundle_adjustment.h:144): the call every pyexample pipeline makes
+    gen.add_noise_to_views(noise_pos=1e-2, noise_angle=0.5)
+    gen.add_noise_to_tracks(noise_track=1e-2)
+    defaults = pt.sfm.BundleAdjustmentOptions()
+    assert defaults.use_inner_iterations is True
+    result = pt.sfm.BundleAdjustReconstruction(defaults, gen.recon)
+    assert result.success and result.final_cost < 1e-6 * result.initial_cost + 1e-9
 
 
 def _two_view_corrs(n=300, outliers=0.3, noise=1e-3, seed=65):

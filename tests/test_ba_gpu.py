@@ -332,7 +332,7 @@ def test_invalid_arguments_are_error_codes(lib):
     bad = prob.copy(); bad.a["obs_pt"][3] = 10**6
     p = bad.struct()
     assert lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None) == capi.THB_E_INVALID_ARGUMENT
-    o.use_inner_iterations = 1
+    o.linear_solver = capi.SOLVER_SCHUR_PCG
     p = prob.struct()
     assert lib.thb_ba_solve(C.byref(p), C.byref(o), C.byref(s), None) == capi.THB_E_UNSUPPORTED
     assert lib.thb_ba_solve(None, None, None, None) == capi.THB_E_INVALID_ARGUMENT
@@ -391,3 +391,43 @@ def test_c3_full_size_matches_oracle(lib, oracle):
     g, o, pg, po = _compare_solves(lib, oracle, prob, capi.default_options(lib))
     assert g["num_iterations"] == o["num_iterations"] >= 3
     np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["c1", "c1_huber_euclidean", "const_position", "c3_intrinsics", "fisheye_partial"])
+def test_inner_iterations_match_oracle(lib, oracle, case):
+    """use_inner_iterations = true (the reference default): per-camera / per-intrinsics-block / per-point coordinate descent
+    after every candidate (k_inner_cam, k_inner_intr + host loop, k_track_ba) against the oracle's CoordinateDescentMinimizer
+    restatement: same iteration counts and termination, costs <= 1e-6 relative."""
+    o = capi.default_options(lib)
+    o.use_inner_iterations = 1
+    if case == "c1":
+        prob, _ = synthetic.config_c1()
+    elif case == "c1_huber_euclidean":
+        prob, _ = synthetic.config_c1(seed=4)
+        o.loss_function_type = capi.LOSS_HUBER; o.robust_loss_width = 1.5; o.use_homogeneous_point_parametrization = 0
+    elif case == "const_position":
+        prob, _ = synthetic.make_ba_problem(12, 400, 5, seed=17)
+        prob.a["cam_const"][::2] = capi.CAM_CONST_POSITION
+        prob.a["cam_const"][1] = capi.CAM_CONST_ORIENTATION
+        prob.a["pt_const"][::7] = 1
+    elif case == "c3_intrinsics":
+        prob, _ = synthetic.config_c3(scale=0.06)
+        _perturb_intrinsics(prob, 0.02)
+    else:
+        prob, _ = synthetic.make_ba_problem(9, 300, 4, models=(capi.MODEL_FISHEYE,), seed=23)
+        prob.a["cam_const"][5:] = 3
+    g, oo, pg, po = _compare_solves(lib, oracle, prob, o)
+    assert g["num_iterations"] == oo["num_iterations"]
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(pg.a["intr"], po.a["intr"], rtol=1e-6, atol=1e-9)
+    # and it is a different path from the plain trust-region solve: the first step lands lower
+    o.use_inner_iterations = 0
+    plain = gpu_solve(lib, prob.copy(), o)
+    assert g["iter_cost"][1] < plain["iter_cost"][1]
+
+
+def test_inner_iterations_c2_scaled(lib, oracle):
+    prob, _ = synthetic.config_c2(scale=0.1)
+    o = capi.default_options(lib)
+    o.use_inner_iterations = 1
+    _compare_solves(lib, oracle, prob, o)
