@@ -245,7 +245,10 @@ typedef struct ThbRansacParams {
   int32_t min_iterations;
   int32_t max_iterations;
   int32_t use_mle;            /* MLEQualityMeasurement instead of InlierSupport                     */
-  int32_t use_lo;             /* must be 0: LO refinement (two-view BA) is "next", THB_E_UNSUPPORTED */
+  int32_t use_lo;             /* LO-RANSAC: Estimator::RefineModel on every improved model from lo_start_iterations on and */
+                              /* once on the final inliers (sample_consensus_estimator.h:372-380, 400-405). Relative pose  */
+                              /* only (BundleAdjustTwoViewsAngular); THB_E_UNSUPPORTED for absolute pose, a no-op upstream  */
+                              /* for homographies (Estimator::RefineModel default)                                          */
   int32_t lo_start_iterations;
   int32_t ransac_type;        /* RansacType: only RANSAC (0) (create_and_initialize_ransac_variant.h:52) */
   int32_t use_tdd_test;       /* RansacParameters::use_Tdd_test: ComputeMaxIterations counts SampleSize + 1 draws */
@@ -275,6 +278,8 @@ typedef struct ThbRelPoseResult {
   double essential_matrix[9];
   double rotation[9];
   double position[3];
+  int32_t num_lo_iterations;  /* RansacSummary::num_lo_iterations */
+  int32_t reserved0;
 } ThbRelPoseResult;
 
 void thb_ransac_default_params(ThbRansacParams* params);

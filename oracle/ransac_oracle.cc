@@ -26,6 +26,7 @@
 
 #include "../include/theia_b200.h"
 #include "eigen_restated.h"
+#include "jet.h"
 
 namespace oracle {
 namespace {
@@ -467,8 +468,251 @@ int SevenPointF(const double* corr, double* F_out) {
 // Estimator policies (solvers/estimator.h): sample size, model estimation, per-datum error.
 struct Model { double E[9], R[9], p[3]; };  // 21 doubles: the ThbRelPoseResult payload
 
+// ---- LO-RANSAC refinement of a relative pose: RelativePoseEstimator::RefineModel (estimate_relative_pose.cc:111-138) ->
+// BundleAdjustTwoViewsAngular (sfm/bundle_adjustment/bundle_adjust_two_views.cc:195-246) over AngularEpipolarError
+// (angular_epipolar_error.h:50-108): rotation (angle-axis, 3) and position (unit 3-vector, SphereManifold<3>), TRUNCATED loss
+// of width error_thresh, 15 iterations, Ceres' default tolerances and trust-region radii (the local SetSolverOptions of
+// bundle_adjust_two_views.cc:60-72 overrides the linear solver with DENSE_SCHUR and nothing else). Eigen conversions
+// (AngleAxisd <-> Matrix3d via Quaterniond) and the Ceres minimiser are restated: PARITY UNPINNED like the rest.
+inline void EigenRotationMatrixToAngleAxis(const double* R /*row-major*/, double aa[3]) {
+  // Eigen::Quaternion = Matrix3 (QuaternionBase::operator=, quat_product / rotation matrix branch), then AngleAxis = Quaternion
+  double q[4];  // x, y, z, w
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t; t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+  }
+  double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  double angle, axis[3];
+  if (n != 0.0) {
+    angle = 2.0 * std::atan2(n, std::fabs(q[3]));
+    if (q[3] < 0.0) n = -n;
+    for (int k = 0; k < 3; ++k) axis[k] = q[k] / n;
+  } else { angle = 0.0; axis[0] = 1.0; axis[1] = 0.0; axis[2] = 0.0; }
+  for (int k = 0; k < 3; ++k) aa[k] = angle * axis[k];
+}
+inline void EigenAngleAxisToRotationMatrix(const double aa[3], double* R /*row-major*/) {
+  // rot_vec_out.angle() = |aa|; axis = aa / angle; toRotationMatrix() (Eigen/src/Geometry/AngleAxis.h)
+  const double angle = std::sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+  const double ax[3] = {aa[0] / angle, aa[1] / angle, aa[2] / angle};
+  const double s = std::sin(angle), c = std::cos(angle);
+  const double sa[3] = {s * ax[0], s * ax[1], s * ax[2]}, c1[3] = {(1.0 - c) * ax[0], (1.0 - c) * ax[1], (1.0 - c) * ax[2]};
+  double tmp;
+  tmp = c1[0] * ax[1]; R[1] = tmp - sa[2]; R[3] = tmp + sa[2];
+  tmp = c1[0] * ax[2]; R[2] = tmp + sa[1]; R[6] = tmp - sa[1];
+  tmp = c1[1] * ax[2]; R[5] = tmp - sa[0]; R[7] = tmp + sa[0];
+  R[0] = c1[0] * ax[0] + c; R[4] = c1[1] * ax[1] + c; R[8] = c1[2] * ax[2] + c;
+}
+
+template <typename T>
+inline void CeresAngleAxisToRotationMatrix(const T* aa, T R[3][3]) {  // ceres/rotation.h (external)
+  const T theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (theta2 > DBL_EPSILON) {
+    const T theta = sqrt_(theta2);
+    const T wx = aa[0] / theta, wy = aa[1] / theta, wz = aa[2] / theta;
+    const T ct = cos_(theta), st = sin_(theta);
+    R[0][0] = ct + wx * wx * (1.0 - ct);      R[1][0] = wz * st + wx * wy * (1.0 - ct);  R[2][0] = -wy * st + wx * wz * (1.0 - ct);
+    R[0][1] = wx * wy * (1.0 - ct) - wz * st; R[1][1] = ct + wy * wy * (1.0 - ct);       R[2][1] = wx * st + wy * wz * (1.0 - ct);
+    R[0][2] = wy * st + wx * wz * (1.0 - ct); R[1][2] = -wx * st + wy * wz * (1.0 - ct); R[2][2] = ct + wz * wz * (1.0 - ct);
+  } else {
+    R[0][0] = T(1.0); R[1][0] = aa[2]; R[2][0] = -aa[1];
+    R[0][1] = -aa[2]; R[1][1] = T(1.0); R[2][1] = aa[0];
+    R[0][2] = aa[1]; R[1][2] = -aa[0]; R[2][2] = T(1.0);
+  }
+}
+
+// AngularEpipolarError::operator() (angular_epipolar_error.h:61-96), as written (including R f2 . T R^T f2)
+template <typename T>
+inline T AngularEpipolarResidual(const T* rot, const T* tr, const double* c /*x1 y1 x2 y2*/) {
+  const T f1[3] = {T(c[0]), T(c[1]), T(1.0)}, f2[3] = {T(c[2]), T(c[3]), T(1.0)};
+  T R[3][3];
+  CeresAngleAxisToRotationMatrix(rot, R);
+  T Rf2[3], Rtf2[3];
+  for (int i = 0; i < 3; ++i) { Rf2[i] = R[i][0] * f2[0] + R[i][1] * f2[1] + R[i][2] * f2[2]; Rtf2[i] = R[0][i] * f2[0] + R[1][i] * f2[1] + R[2][i] * f2[2]; }
+  auto apply_term = [&](const T* v, T* out) {  // (I - t t^T) v
+    const T tv = tr[0] * v[0] + tr[1] * v[1] + tr[2] * v[2];
+    for (int i = 0; i < 3; ++i) out[i] = v[i] - tr[i] * tv;
+  };
+  T Tf1[3], TRtf2[3];
+  apply_term(f1, Tf1); apply_term(Rtf2, TRtf2);
+  const T a = (f1[0] * Tf1[0] + f1[1] * Tf1[1] + f1[2] * Tf1[2]) + (Rf2[0] * TRtf2[0] + Rf2[1] * TRtf2[1] + Rf2[2] * TRtf2[2]);
+  const T cr[3] = {f1[1] * Rtf2[2] - f1[2] * Rtf2[1], f1[2] * Rtf2[0] - f1[0] * Rtf2[2], f1[0] * Rtf2[1] - f1[1] * Rtf2[0]};
+  const T b_sqrt = tr[0] * cr[0] + tr[1] * cr[1] + tr[2] * cr[2];
+  const T sqrt_term = (a * a) / 4.0 - b_sqrt * b_sqrt;
+  if (sqrt_term < 0.0) return T(1000.0);
+  return a / 2.0 - sqrt_(sqrt_term);
+}
+
+// ceres SphereManifold<3> on the position (Householder as for the 4-vector points of ba_oracle.cc)
+inline void Householder3(const double x[3], double v[3], double* beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  v[0] = x[0]; v[1] = x[1]; v[2] = 1.0;
+  *beta = 0.0;
+  if (sigma <= DBL_EPSILON) { if (x[2] < 0.0) *beta = 2.0; return; }
+  const double mu = std::sqrt(x[2] * x[2] + sigma);
+  const double vp = x[2] <= 0.0 ? x[2] - mu : -sigma / (x[2] + mu);
+  *beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp; v[1] /= vp;
+}
+inline void Sphere3Plus(const double x[3], const double d[2], double out[3]) {
+  const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1]);
+  if (nd == 0.0) { for (int i = 0; i < 3; ++i) out[i] = x[i]; return; }
+  double v[3], beta;
+  Householder3(x, v, &beta);
+  const double sbd = std::sin(nd) / nd;
+  const double y[3] = {sbd * d[0], sbd * d[1], std::cos(nd)};
+  const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2];
+  const double nx = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * (beta * vty));
+}
+inline void Sphere3PlusJacobian(const double x[3], double J[6] /*3x2 row-major*/) {
+  double v[3], beta;
+  Householder3(x, v, &beta);
+  const double nx = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (int i = 0; i < 2; ++i) {
+    for (int r = 0; r < 3; ++r) J[r * 2 + i] = -beta * v[i] * v[r];
+    J[i * 2 + i] += 1.0;
+  }
+  for (int k = 0; k < 6; ++k) J[k] *= nx;
+}
+
+inline bool SmallSpdSolve(int n, const double* A, const double* b, double* x) {  // Cholesky, n <= 8
+  double L[64], y[8];
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double v = A[i * n + j];
+      for (int k = 0; k < j; ++k) v -= L[i * n + k] * L[j * n + k];
+      if (i == j) { if (!(v > 0.0)) return false; L[i * n + i] = std::sqrt(v); }
+      else L[i * n + j] = v / L[j * n + j];
+    }
+  for (int i = 0; i < n; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * n + k] * y[k]; y[i] = v / L[i * n + i]; }
+  for (int i = n - 1; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < n; ++k) v -= L[k * n + i] * x[k]; x[i] = v / L[i * n + i]; }
+  return true;
+}
+
+// TrustRegionMinimizer on (rotation, position). Returns IsSolutionUsable-style success; costs as ceres::Solver::Summary.
+inline bool AngularBundleAdjust(const double* corr, int n, double width, int max_iterations, double rot[3], double pos[3],
+                                double* initial_cost, double* final_cost) {
+  typedef Jet<6> J6;
+  const double b = width * width;  // TruncatedLoss(a): rho(s) = min(s, a^2) (loss_functions.cc:40-44)
+  struct Eval { double cost; double H[15]; double g[5]; };
+  auto evaluate = [&](const double* r3, const double* p3, bool want_j, const double* scale, Eval* e) {
+    e->cost = 0.0;
+    if (want_j) { for (double& v : e->H) v = 0.0; for (double& v : e->g) v = 0.0; }
+    double PJ[6];
+    if (want_j) Sphere3PlusJacobian(p3, PJ);
+    for (int i = 0; i < n; ++i) {
+      if (!want_j) {
+        const double r = AngularEpipolarResidual<double>(r3, p3, corr + 4 * (size_t)i);
+        e->cost += 0.5 * std::min(r * r, b);
+        continue;
+      }
+      J6 jr[3], jt[3];
+      for (int k = 0; k < 3; ++k) { jr[k] = J6(r3[k], k); jt[k] = J6(p3[k], 3 + k); }
+      const J6 res = AngularEpipolarResidual<J6>(jr, jt, corr + 4 * (size_t)i);
+      const double s = res.a * res.a;
+      e->cost += 0.5 * std::min(s, b);
+      const double w = s < b ? 1.0 : 0.0;  // Corrector with rho'' = 0: residual and Jacobian times sqrt(rho')
+      if (w == 0.0) continue;
+      double t[5];
+      for (int k = 0; k < 3; ++k) t[k] = res.v[k];
+      for (int k = 0; k < 2; ++k) t[3 + k] = res.v[3] * PJ[0 * 2 + k] + res.v[4] * PJ[1 * 2 + k] + res.v[5] * PJ[2 * 2 + k];
+      for (int k = 0; k < 5; ++k) t[k] *= scale[k];
+      int q = 0;
+      for (int a = 0; a < 5; ++a) { e->g[a] += t[a] * res.a; for (int c = 0; c <= a; ++c) e->H[q++] += t[a] * t[c]; }
+    }
+  };
+  double scale[5] = {1, 1, 1, 1, 1};
+  Eval E;
+  evaluate(rot, pos, true, scale, &E);
+  { int q = 0; for (int a = 0; a < 5; ++a) { q += a; scale[a] = 1.0 / (1.0 + std::sqrt(E.H[q])); ++q; } }
+  evaluate(rot, pos, true, scale, &E);
+  double x_cost = E.cost, min_cost = E.cost;
+  *initial_cost = E.cost;
+  double x_norm = std::sqrt(rot[0] * rot[0] + rot[1] * rot[1] + rot[2] * rot[2] + pos[0] * pos[0] + pos[1] * pos[1] + pos[2] * pos[2]);
+  double radius = 1e4, decrease_factor = 2.0, diag[5];
+  bool step_ok = true, reuse_diag = false, failure = false;
+  int iteration = 0, invalid = 0;
+  for (;;) {
+    if (iteration >= max_iterations) break;
+    if (step_ok) { double gmax = 0.0; for (int k = 0; k < 5; ++k) gmax = std::max(gmax, std::fabs(E.g[k] / scale[k])); if (gmax <= 1e-10) break; }
+    if (radius <= 1e-32) break;
+    ++iteration;
+    step_ok = false;
+    if (!reuse_diag) { int q = 0; for (int a = 0; a < 5; ++a) { q += a; diag[a] = std::min(std::max(E.H[q], 1e-6), 1e32); ++q; } }
+    reuse_diag = true;
+    double M[25], y[5];
+    { int q = 0; for (int a = 0; a < 5; ++a) for (int c = 0; c <= a; ++c) { M[a * 5 + c] = E.H[q]; M[c * 5 + a] = E.H[q]; ++q; } }
+    for (int a = 0; a < 5; ++a) M[a * 5 + a] += diag[a] / radius;
+    bool valid = SmallSpdSolve(5, M, E.g, y);
+    double mcc = 0.0;
+    if (valid) {
+      double yg = 0.0, yHy = 0.0;
+      int q = 0;
+      for (int a = 0; a < 5; ++a) { yg += y[a] * E.g[a]; for (int c = 0; c <= a; ++c) { yHy += (a == c ? 1.0 : 2.0) * y[a] * E.H[q] * y[c]; ++q; } }
+      mcc = yg - 0.5 * yHy;
+      valid = std::isfinite(mcc) && mcc > 0.0;
+    }
+    if (!valid) {
+      if (++invalid >= 5) { failure = true; break; }
+      radius /= decrease_factor; decrease_factor *= 2.0;
+      continue;
+    }
+    invalid = 0;
+    double cr[3], cp[3], d2[2] = {-y[3] * scale[3], -y[4] * scale[4]};
+    for (int k = 0; k < 3; ++k) cr[k] = rot[k] + (-y[k] * scale[k]);
+    Sphere3Plus(pos, d2, cp);
+    Eval C;
+    evaluate(cr, cp, false, scale, &C);
+    double sn = 0.0, cn = 0.0;
+    for (int k = 0; k < 3; ++k) { sn += (cr[k] - rot[k]) * (cr[k] - rot[k]) + (cp[k] - pos[k]) * (cp[k] - pos[k]); cn += cr[k] * cr[k] + cp[k] * cp[k]; }
+    if (std::sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) break;
+    const double cost_change = x_cost - C.cost;
+    if (std::fabs(cost_change) <= 1e-6 * x_cost) break;
+    const double rel = cost_change / mcc;
+    if (rel > 1e-3) {
+      for (int k = 0; k < 3; ++k) { rot[k] = cr[k]; pos[k] = cp[k]; }
+      x_norm = std::sqrt(cn);
+      evaluate(rot, pos, true, scale, &E);
+      x_cost = E.cost;
+      min_cost = std::min(min_cost, x_cost);
+      step_ok = true;
+      radius = std::min(1e16, radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rel - 1.0, 3)));
+      decrease_factor = 2.0; reuse_diag = false;
+    } else {
+      radius /= decrease_factor; decrease_factor *= 2.0;
+    }
+  }
+  *final_cost = min_cost;
+  return !failure;
+}
+
+// RelativePoseEstimator::RefineModel: E is NOT recomputed from the refined pose (estimate_relative_pose.cc:111-138)
+inline bool RefineRelativePose(const double* corr, int n, double error_thresh, Model* m) {
+  double rot[3], pos[3] = {m->p[0], m->p[1], m->p[2]};
+  EigenRotationMatrixToAngleAxis(m->R, rot);
+  double c0 = 0.0, c1 = 0.0;
+  AngularBundleAdjust(corr, n, error_thresh, 15, rot, pos, &c0, &c1);
+  for (int k = 0; k < 3; ++k) m->p[k] = pos[k];
+  EigenAngleAxisToRotationMatrix(rot, m->R);
+  return c1 < c0;
+}
+
 struct RelPoseEst {  // RelativePoseEstimator, estimate_relative_pose.cc:65-155
   static constexpr int S = 5, D = 4, MAXM = 10;
+  static constexpr bool HAS_LO = true;
+  static bool Refine(const double* inl, int n, double thresh, Model* m) { return RefineRelativePose(inl, n, thresh, m); }
   static int Solve(const double* sample, Model* out) {
     double x1[10], x2[10], Es[90];
     for (int i = 0; i < 5; ++i) { x1[2 * i] = sample[4 * i]; x1[2 * i + 1] = sample[4 * i + 1]; x2[2 * i] = sample[4 * i + 2]; x2[2 * i + 1] = sample[4 * i + 3]; }
@@ -486,7 +730,9 @@ struct RelPoseEst {  // RelativePoseEstimator, estimate_relative_pose.cc:65-155
 };
 
 struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator with PnPType::KNEIP, estimate_calibrated_absolute_pose.cc:63-172
-  static constexpr int S = 3, D = 5, MAXM = 4;   // datum: feature (x, y), world point (X, Y, Z)
+  static constexpr int S = 3, D = 5, MAXM = 4;
+  static constexpr bool HAS_LO = false;  // LO = BundleAdjustView on a one-view reconstruction (:120-153): not restated
+  static bool Refine(const double*, int, double, Model*) { return false; }   // datum: feature (x, y), world point (X, Y, Z)
   static int Solve(const double* sample, Model* out) {
     double feat[6], world[9], Rs[36], ts[12];
     for (int i = 0; i < 3; ++i) { feat[2 * i] = sample[5 * i]; feat[2 * i + 1] = sample[5 * i + 1]; for (int k = 0; k < 3; ++k) world[3 * i + k] = sample[5 * i + 2 + k]; }
@@ -511,6 +757,8 @@ struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator with PnPType::KNEIP, est
 
 struct HomographyEst {  // HomographyEstimator, estimate_homography.cc:62-116; the model lives in Model::E
   static constexpr int S = 4, D = 4, MAXM = 1;
+  static constexpr bool HAS_LO = false;  // Estimator::RefineModel default returns false (solvers/estimator.h)
+  static bool Refine(const double*, int, double, Model*) { return false; }
   static int Solve(const double* sample, Model* out) {
     std::memset(out, 0, sizeof(Model));
     return FourPointH(sample, out->E) ? 1 : 0;
@@ -572,6 +820,12 @@ void EstimatePair(const ThbRansacParams& P, const double* data, int n, uint32_t 
   Model best;
   std::memset(&best, 0, sizeof(best));
   std::vector<int> inl;
+  std::vector<double> inl_data;
+  int num_lo = 0;
+  auto gather = [&](const std::vector<int>& idx) {  // GetInlierDatum
+    inl_data.resize(idx.size() * Est::D);
+    for (size_t q = 0; q < idx.size(); ++q) for (int k = 0; k < Est::D; ++k) inl_data[q * Est::D + k] = data[Est::D * (size_t)idx[q] + k];
+  };
   int it;
   for (it = 0; it < max_iterations; ++it) {
     double sample[S * Est::D];
@@ -589,17 +843,28 @@ void EstimatePair(const ThbRansacParams& P, const double* data, int n, uint32_t 
       if (cost < best_cost) {
         best = m; best_cost = cost;
         if (inlier_ratio < static_cast<double>(S) / static_cast<double>(n)) continue;
+        if (it >= P.lo_start_iterations && P.use_lo) {  // sample_consensus_estimator.h:372-380
+          gather(inl);
+          if (!Est::Refine(inl_data.data(), static_cast<int>(inl.size()), P.error_thresh, &best)) continue;
+          ++num_lo;
+        }
         max_iterations = std::min(ComputeMaxIterations(P, S, inlier_ratio, log_failure_prob, n), max_iterations);
       }
     }
   }
   Score<Est>(P, data, n, best, &inl);
+  if (P.use_lo) {  // :400-405: the summary's inliers are those of the model BEFORE this last refinement
+    gather(inl);
+    Est::Refine(inl_data.data(), static_cast<int>(inl.size()), P.error_thresh, &best);
+    ++num_lo;
+  }
   out->success = 1;
   out->num_iterations = it;
   out->num_inliers = static_cast<int>(inl.size());
   const double ratio = static_cast<double>(inl.size()) / n;
   out->confidence = 1.0 - std::pow(1.0 - std::pow(ratio, static_cast<double>(S)), out->num_iterations);
   out->best_cost = best_cost;
+  out->num_lo_iterations = num_lo;
   std::memcpy(out->essential_matrix, best.E, sizeof(best.E));
   std::memcpy(out->rotation, best.R, sizeof(best.R));
   std::memcpy(out->position, best.p, sizeof(best.p));
@@ -611,7 +876,7 @@ int RunBatch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* 
   if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
   if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
       p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) return THB_E_INVALID_ARGUMENT;
-  if (p->use_lo || p->ransac_type != 0) return THB_E_UNSUPPORTED;
+  if ((p->use_lo && !Est::HAS_LO) || p->ransac_type != 0) return THB_E_UNSUPPORTED;
   const int nt = threads > 0 ? threads : omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
   for (int i = 0; i < b->num_pairs; ++i) {

@@ -124,6 +124,7 @@ class ThbRelPoseResult(C.Structure):
         ("success", C.c_int32), ("num_inliers", C.c_int32), ("num_iterations", C.c_int32),
         ("num_input_data_points", C.c_int32), ("confidence", C.c_double), ("best_cost", C.c_double),
         ("essential_matrix", C.c_double * 9), ("rotation", C.c_double * 9), ("position", C.c_double * 3),
+        ("num_lo_iterations", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -144,7 +145,7 @@ TRACK_BA_DTYPE = np.dtype([("initial_cost", np.float64), ("final_cost", np.float
 RELPOSE_DTYPE = np.dtype([("success", np.int32), ("num_inliers", np.int32), ("num_iterations", np.int32),
                           ("num_input_data_points", np.int32), ("confidence", np.float64), ("best_cost", np.float64),
                           ("essential_matrix", np.float64, (3, 3)), ("rotation", np.float64, (3, 3)),
-                          ("position", np.float64, (3,))])
+                          ("position", np.float64, (3,)), ("num_lo_iterations", np.int32), ("reserved0", np.int32)])
 assert RELPOSE_DTYPE.itemsize == C.sizeof(ThbRelPoseResult)
 
 

@@ -457,7 +457,7 @@ bool RunOne(BatchFn fn, const RansacParameters& q, int type, const std::vector<d
   Check(rc);
   sum->inliers.clear();
   for (int64_t i = 0; i < n; ++i) if (mask[i]) sum->inliers.push_back((int)i);
-  sum->num_input_data_points = res->num_input_data_points; sum->num_iterations = res->num_iterations; sum->confidence = res->confidence;
+  sum->num_input_data_points = res->num_input_data_points; sum->num_iterations = res->num_iterations; sum->confidence = res->confidence; sum->num_lo_iterations = res->num_lo_iterations;
   return res->success != 0;
 }
 std::vector<double> Flatten(const std::vector<FeatureCorrespondence>& c) {

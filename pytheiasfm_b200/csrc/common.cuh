@@ -117,7 +117,11 @@ THB_HD double d_tan(double x) { return tan(x); }
 THB_HD double d_atan(double x) { return atan(x); }
 THB_HD double d_abs(double x) { return fabs(x); }
 THB_HD double d_atan2(double y, double x) { return atan2(y, x); }
+THB_HD double d_sin(double x) { return sin(x); }
+THB_HD double d_cos(double x) { return cos(x); }
 template <int N> THB_HD Dual<N> d_sqrt(const Dual<N>& f) { const double s = sqrt(f.a); return chain(f, s, 0.5 / s); }
+template <int N> THB_HD Dual<N> d_sin(const Dual<N>& f) { return chain(f, sin(f.a), cos(f.a)); }
+template <int N> THB_HD Dual<N> d_cos(const Dual<N>& f) { return chain(f, cos(f.a), -sin(f.a)); }
 template <int N> THB_HD Dual<N> d_tan(const Dual<N>& f) { const double t = tan(f.a); return chain(f, t, 1.0 + t * t); }
 template <int N> THB_HD Dual<N> d_atan(const Dual<N>& f) { return chain(f, atan(f.a), 1.0 / (1.0 + f.a * f.a)); }
 template <int N> THB_HD Dual<N> d_abs(const Dual<N>& f) { return chain(f, fabs(f.a), copysign(1.0, f.a)); }

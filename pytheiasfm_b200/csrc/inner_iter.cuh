@@ -195,8 +195,10 @@ __global__ void __launch_bounds__(IC_THREADS) k_inner_cam(BaConst K, BaState S, 
       s_go = go;
     }
     __syncthreads();
-    if (s_go == 0) break;
-    if (s_go == 2) {
+    const int go2 = s_go;
+    __syncthreads();  // thread 0 rewrites s_go at the top of the next round: everybody has read it by now
+    if (go2 == 0) break;
+    if (go2 == 2) {
       inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot);
       if (tot[28] > 0.0) break;  // EvaluateGradientAndJacobian failed: FAILURE, x keeps the accepted point
       if (t == 0) {

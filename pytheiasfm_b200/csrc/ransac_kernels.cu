@@ -459,9 +459,312 @@ __device__ int seven_point_f(const double* corr, double* F_out) {
   return nroots;
 }
 
+
+// ---- LO-RANSAC refinement of a relative pose -------------------------------------------------------------------------------
+// RelativePoseEstimator::RefineModel (sfm/estimators/estimate_relative_pose.cc:111-138) = BundleAdjustTwoViewsAngular
+// (sfm/bundle_adjustment/bundle_adjust_two_views.cc:195-246): rotation (angle-axis) + position on the unit sphere
+// (SphereManifold<3>), AngularEpipolarError residuals (angular_epipolar_error.h:50-108) under a TRUNCATED loss of width
+// error_thresh, at most 15 trust-region iterations with Ceres' default tolerances. The whole CTA works on one refinement:
+// every evaluation is a pass over the model's inliers (one residual, differentiated with a 6-direction dual number, per thread
+// and step), J^T J (15) / J^T r (5) / cost are block-reduced in a fixed order and thread 0 takes the trust-region decisions.
+__device__ void eigen_matrix_to_angle_axis(const double* R, double aa[3]) {  // Eigen: Quaterniond(R), then AngleAxisd(q)
+  double q[4];
+  double t = R[0] + R[4] + R[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t; t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 3 + i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+    q[i] = 0.5 * t; t = 0.5 / t;
+    q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  double angle, axis[3];
+  if (n != 0.0) {
+    angle = 2.0 * atan2(n, fabs(q[3]));
+    if (q[3] < 0.0) n = -n;
+    for (int k = 0; k < 3; ++k) axis[k] = q[k] / n;
+  } else { angle = 0.0; axis[0] = 1.0; axis[1] = 0.0; axis[2] = 0.0; }
+  for (int k = 0; k < 3; ++k) aa[k] = angle * axis[k];
+}
+__device__ void eigen_angle_axis_to_matrix(const double aa[3], double* R) {  // AngleAxisd(|aa|, aa / |aa|).toRotationMatrix()
+  const double angle = sqrt(aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2]);
+  const double ax[3] = {aa[0] / angle, aa[1] / angle, aa[2] / angle};
+  const double s = sin(angle), c = cos(angle);
+  const double sa[3] = {s * ax[0], s * ax[1], s * ax[2]}, c1[3] = {(1.0 - c) * ax[0], (1.0 - c) * ax[1], (1.0 - c) * ax[2]};
+  double tmp;
+  tmp = c1[0] * ax[1]; R[1] = tmp - sa[2]; R[3] = tmp + sa[2];
+  tmp = c1[0] * ax[2]; R[2] = tmp + sa[1]; R[6] = tmp - sa[1];
+  tmp = c1[1] * ax[2]; R[5] = tmp - sa[0]; R[7] = tmp + sa[0];
+  R[0] = c1[0] * ax[0] + c; R[4] = c1[1] * ax[1] + c; R[8] = c1[2] * ax[2] + c;
+}
+template <typename T>
+__device__ __forceinline__ void ceres_angle_axis_to_matrix(const T* aa, T R[3][3]) {  // ceres/rotation.h AngleAxisToRotationMatrix
+  const T theta2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (val(theta2) > DBL_EPSILON) {
+    const T theta = d_sqrt(theta2);
+    const T wx = aa[0] / theta, wy = aa[1] / theta, wz = aa[2] / theta;
+    const T ct = d_cos(theta), st = d_sin(theta);
+    R[0][0] = ct + wx * wx * (1.0 - ct);      R[1][0] = wz * st + wx * wy * (1.0 - ct);  R[2][0] = -wy * st + wx * wz * (1.0 - ct);
+    R[0][1] = wx * wy * (1.0 - ct) - wz * st; R[1][1] = ct + wy * wy * (1.0 - ct);       R[2][1] = wx * st + wy * wz * (1.0 - ct);
+    R[0][2] = wy * st + wx * wz * (1.0 - ct); R[1][2] = -wx * st + wy * wz * (1.0 - ct); R[2][2] = ct + wz * wz * (1.0 - ct);
+  } else {
+    R[0][0] = T(1.0); R[1][0] = aa[2]; R[2][0] = -aa[1];
+    R[0][1] = -aa[2]; R[1][1] = T(1.0); R[2][1] = aa[0];
+    R[0][2] = aa[1]; R[1][2] = -aa[0]; R[2][2] = T(1.0);
+  }
+}
+template <typename T>
+__device__ __forceinline__ T angular_epipolar_residual(const T* rot, const T* tr, const double* c) {
+  const T f1[3] = {T(c[0]), T(c[1]), T(1.0)}, f2[3] = {T(c[2]), T(c[3]), T(1.0)};
+  T R[3][3];
+  ceres_angle_axis_to_matrix(rot, R);
+  T Rf2[3], Rtf2[3], Tf1[3], TRtf2[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { Rf2[i] = R[i][0] * f2[0] + R[i][1] * f2[1] + R[i][2] * f2[2]; Rtf2[i] = R[0][i] * f2[0] + R[1][i] * f2[1] + R[2][i] * f2[2]; }
+  {
+    const T tv = tr[0] * f1[0] + tr[1] * f1[1] + tr[2] * f1[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Tf1[i] = f1[i] - tr[i] * tv;
+    const T tw = tr[0] * Rtf2[0] + tr[1] * Rtf2[1] + tr[2] * Rtf2[2];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) TRtf2[i] = Rtf2[i] - tr[i] * tw;
+  }
+  const T a = (f1[0] * Tf1[0] + f1[1] * Tf1[1] + f1[2] * Tf1[2]) + (Rf2[0] * TRtf2[0] + Rf2[1] * TRtf2[1] + Rf2[2] * TRtf2[2]);
+  const T cr[3] = {f1[1] * Rtf2[2] - f1[2] * Rtf2[1], f1[2] * Rtf2[0] - f1[0] * Rtf2[2], f1[0] * Rtf2[1] - f1[1] * Rtf2[0]};
+  const T b_sqrt = tr[0] * cr[0] + tr[1] * cr[1] + tr[2] * cr[2];
+  const T sqrt_term = (a * a) / 4.0 - b_sqrt * b_sqrt;
+  if (val(sqrt_term) < 0.0) return T(1000.0);
+  return a / 2.0 - d_sqrt(sqrt_term);
+}
+__device__ void householder3(const double x[3], double v[3], double* beta) {
+  const double sigma = x[0] * x[0] + x[1] * x[1];
+  v[0] = x[0]; v[1] = x[1]; v[2] = 1.0;
+  *beta = 0.0;
+  if (sigma <= DBL_EPSILON) { if (x[2] < 0.0) *beta = 2.0; return; }
+  const double mu = sqrt(x[2] * x[2] + sigma);
+  const double vp = x[2] <= 0.0 ? x[2] - mu : -sigma / (x[2] + mu);
+  *beta = 2.0 * vp * vp / (sigma + vp * vp);
+  v[0] /= vp; v[1] /= vp;
+}
+__device__ void sphere3_plus(const double x[3], const double d[2], double out[3]) {
+  const double nd = sqrt(d[0] * d[0] + d[1] * d[1]);
+  if (nd == 0.0) { for (int i = 0; i < 3; ++i) out[i] = x[i]; return; }
+  double v[3], beta;
+  householder3(x, v, &beta);
+  const double sbd = sin(nd) / nd;
+  const double y[3] = {sbd * d[0], sbd * d[1], cos(nd)};
+  const double vty = v[0] * y[0] + v[1] * y[1] + v[2] * y[2];
+  const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (int i = 0; i < 3; ++i) out[i] = nx * (y[i] - v[i] * (beta * vty));
+}
+__device__ void sphere3_plus_jacobian(const double x[3], double J[6]) {
+  double v[3], beta;
+  householder3(x, v, &beta);
+  const double nx = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  for (int i = 0; i < 2; ++i) {
+    for (int r = 0; r < 3; ++r) J[r * 2 + i] = -beta * v[i] * v[r];
+    J[i * 2 + i] += 1.0;
+  }
+  for (int k = 0; k < 6; ++k) J[k] *= nx;
+}
+__device__ bool spd_solve5(const double* A, const double* b, double* x) {
+  double L[25], y[5];
+  for (int i = 0; i < 5; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double v = A[i * 5 + j];
+      for (int k = 0; k < j; ++k) v -= L[i * 5 + k] * L[j * 5 + k];
+      if (i == j) { if (!(v > 0.0)) return false; L[i * 5 + i] = sqrt(v); }
+      else L[i * 5 + j] = v / L[j * 5 + j];
+    }
+  for (int i = 0; i < 5; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * 5 + k] * y[k]; y[i] = v / L[i * 5 + i]; }
+  for (int i = 4; i >= 0; --i) { double v = y[i]; for (int k = i + 1; k < 5; ++k) v -= L[k * 5 + i] * x[k]; x[i] = v / L[i * 5 + i]; }
+  return true;
+}
+
+struct LoShared {
+  double rot[3], pos[3], crot[3], cpos[3], scale[5], PJ[6];
+  double tot[21], red[RT / 32][21];
+  int go, ok;
+};
+// one pass over the flagged data at (rot, pos): tot = [H(15) | g(5) | cost]
+template <bool WANT_J>
+__device__ void lo_pass(const double* __restrict__ corr, const uint8_t* __restrict__ flag, int n, double b, const double* rot, const double* pos,
+                        LoShared& L) {
+  double v[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) v[k] = 0.0;
+  for (int i = threadIdx.x; i < n; i += RT) {
+    if (!flag[i]) continue;
+    const double c[4] = {corr[4 * (size_t)i], corr[4 * (size_t)i + 1], corr[4 * (size_t)i + 2], corr[4 * (size_t)i + 3]};
+    if (!WANT_J) {
+      const double r = angular_epipolar_residual<double>(rot, pos, c);
+      v[20] += 0.5 * fmin(r * r, b);
+    } else {
+      typedef Dual<6> D6;
+      D6 jr[3], jt[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { jr[k] = seed<6>(rot[k], k); jt[k] = seed<6>(pos[k], 3 + k); }
+      const D6 res = angular_epipolar_residual<D6>(jr, jt, c);
+      const double s = res.a * res.a;
+      v[20] += 0.5 * fmin(s, b);
+      if (!(s < b)) continue;  // TruncatedLoss: rho' = 0 beyond the width - the Corrector zeroes the row
+      double t[5];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] = res.v[k] * L.scale[k];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) t[3 + k] = (res.v[3] * L.PJ[k] + res.v[4] * L.PJ[2 + k] + res.v[5] * L.PJ[4 + k]) * L.scale[3 + k];
+      int q = 0;
+#pragma unroll
+      for (int a = 0; a < 5; ++a) {
+        v[15 + a] += t[a] * res.a;
+#pragma unroll
+        for (int cc = 0; cc <= a; ++cc) v[q++] += t[a] * t[cc];
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = WANT_J ? 0 : 20; k < 21; ++k) {
+    const double s = warp_sum(v[k]);
+    if (lane == 0) L.red[w][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 21) {
+    double s = 0.0;
+    for (int ww = 0; ww < RT / 32; ++ww) s += L.red[ww][threadIdx.x];
+    L.tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+// Refines m->R / m->p over the flagged correspondences (m->E is left as it is, like the reference). Every thread of the CTA
+// calls it; returns final_cost < initial_cost (uniform).
+__device__ bool lo_refine_relpose(const double* __restrict__ corr, const uint8_t* __restrict__ flag, int n, double width, Model* m, LoShared& L) {
+  const int t = threadIdx.x;
+  const double b = width * width;
+  if (t == 0) {
+    eigen_matrix_to_angle_axis(m->R, L.rot);
+    for (int k = 0; k < 3; ++k) L.pos[k] = m->p[k];
+    for (int k = 0; k < 5; ++k) L.scale[k] = 1.0;
+    sphere3_plus_jacobian(L.pos, L.PJ);
+  }
+  __syncthreads();
+  lo_pass<true>(corr, flag, n, b, L.rot, L.pos, L);
+  if (t == 0) { int q = 0; for (int a = 0; a < 5; ++a) { q += a; L.scale[a] = 1.0 / (1.0 + sqrt(L.tot[q])); ++q; } }
+  __syncthreads();
+  lo_pass<true>(corr, flag, n, b, L.rot, L.pos, L);
+  double H[15], g[5], diag[5], x_cost = L.tot[20], min_cost = L.tot[20], initial_cost = L.tot[20], x_norm = 0.0, radius = 1e4, decrease_factor = 2.0, mcc = 0.0;
+  bool step_ok = true, reuse_diag = false;
+  int iteration = 0, invalid = 0;
+  if (t == 0) {
+    for (int k = 0; k < 15; ++k) H[k] = L.tot[k];
+    for (int k = 0; k < 5; ++k) g[k] = L.tot[15 + k];
+    for (int k = 0; k < 3; ++k) x_norm += L.rot[k] * L.rot[k] + L.pos[k] * L.pos[k];
+    x_norm = sqrt(x_norm);
+  }
+  for (;;) {
+    if (t == 0) {
+      int go = 1;
+      for (;;) {
+        if (iteration >= 15) { go = 0; break; }
+        if (step_ok) { double gmax = 0.0; for (int k = 0; k < 5; ++k) gmax = fmax(gmax, fabs(g[k] / L.scale[k])); if (gmax <= 1e-10) { go = 0; break; } }
+        if (radius <= 1e-32) { go = 0; break; }
+        ++iteration;
+        step_ok = false;
+        if (!reuse_diag) { int q = 0; for (int a = 0; a < 5; ++a) { q += a; diag[a] = fmin(fmax(H[q], 1e-6), 1e32); ++q; } }
+        reuse_diag = true;
+        double M[25], y[5];
+        { int q = 0; for (int a = 0; a < 5; ++a) for (int c = 0; c <= a; ++c) { M[a * 5 + c] = H[q]; M[c * 5 + a] = H[q]; ++q; } }
+        for (int a = 0; a < 5; ++a) M[a * 5 + a] += diag[a] / radius;
+        bool valid = spd_solve5(M, g, y);
+        if (valid) {
+          double yg = 0.0, yHy = 0.0;
+          int q = 0;
+          for (int a = 0; a < 5; ++a) { yg += y[a] * g[a]; for (int c = 0; c <= a; ++c) { yHy += (a == c ? 1.0 : 2.0) * y[a] * H[q] * y[c]; ++q; } }
+          mcc = yg - 0.5 * yHy;
+          valid = isfinite(mcc) && mcc > 0.0;
+        }
+        if (!valid) {
+          if (++invalid >= 5) { go = 0; break; }
+          radius /= decrease_factor; decrease_factor *= 2.0;
+          continue;
+        }
+        invalid = 0;
+        const double d2[2] = {-y[3] * L.scale[3], -y[4] * L.scale[4]};
+        for (int k = 0; k < 3; ++k) L.crot[k] = L.rot[k] + (-y[k] * L.scale[k]);
+        sphere3_plus(L.pos, d2, L.cpos);
+        break;
+      }
+      L.go = go;
+    }
+    __syncthreads();
+    if (L.go == 0) break;  // L.go is next written after the barriers inside lo_pass
+    lo_pass<false>(corr, flag, n, b, L.crot, L.cpos, L);
+    if (t == 0) {
+      int go = 1;
+      const double cand_cost = L.tot[20];
+      double sn = 0.0, cn = 0.0;
+      for (int k = 0; k < 3; ++k) {
+        sn += (L.crot[k] - L.rot[k]) * (L.crot[k] - L.rot[k]) + (L.cpos[k] - L.pos[k]) * (L.cpos[k] - L.pos[k]);
+        cn += L.crot[k] * L.crot[k] + L.cpos[k] * L.cpos[k];
+      }
+      const double cost_change = x_cost - cand_cost;
+      if (sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) go = 0;
+      else if (fabs(cost_change) <= 1e-6 * x_cost) go = 0;
+      else {
+        const double rel = cost_change / mcc;
+        if (rel > 1e-3) {
+          for (int k = 0; k < 3; ++k) { L.rot[k] = L.crot[k]; L.pos[k] = L.cpos[k]; }
+          x_norm = sqrt(cn);
+          sphere3_plus_jacobian(L.pos, L.PJ);
+          const double u = 2.0 * rel - 1.0;
+          radius = fmin(1e16, radius / fmax(1.0 / 3.0, 1.0 - u * u * u));
+          decrease_factor = 2.0; reuse_diag = false;
+          go = 2;
+        } else {
+          radius /= decrease_factor; decrease_factor *= 2.0;
+        }
+      }
+      L.go = go;
+    }
+    __syncthreads();
+    const int go2 = L.go;
+    __syncthreads();  // thread 0 rewrites L.go at the top of the next round: everybody has read it by now
+    if (go2 == 0) break;
+    if (go2 == 2) {
+      lo_pass<true>(corr, flag, n, b, L.rot, L.pos, L);
+      if (t == 0) {
+        for (int k = 0; k < 15; ++k) H[k] = L.tot[k];
+        for (int k = 0; k < 5; ++k) g[k] = L.tot[15 + k];
+        x_cost = L.tot[20];
+        min_cost = fmin(min_cost, x_cost);
+        step_ok = true;
+      }
+    }
+  }
+  if (t == 0) {
+    for (int k = 0; k < 3; ++k) m->p[k] = L.pos[k];
+    eigen_angle_axis_to_matrix(L.rot, m->R);
+    L.ok = min_cost < initial_cost ? 1 : 0;
+  }
+  __syncthreads();
+  return L.ok != 0;
+}
+
 // ---- estimator policies (solvers/estimator.h): sample size, datum width, model estimation, per-datum error ----
 struct RelPoseEst {  // RelativePoseEstimator (sfm/estimators/estimate_relative_pose.cc:65-155)
   static constexpr int S = 5, D = 4, MAXM = 10;
+  static constexpr bool HAS_LO = true;
+  __device__ static bool refine(const double* corr, const uint8_t* flag, int n, double thresh, Model* m, LoShared& L) {
+    return lo_refine_relpose(corr, flag, n, thresh, m, L);
+  }
   __device__ static int solve(const double* sample, Model* out) {
     double x1[10], x2[10], Es[90];
     for (int i = 0; i < 5; ++i) { x1[2 * i] = sample[4 * i]; x1[2 * i + 1] = sample[4 * i + 1]; x2[2 * i] = sample[4 * i + 2]; x2[2 * i + 1] = sample[4 * i + 3]; }
@@ -481,6 +784,8 @@ struct RelPoseEst {  // RelativePoseEstimator (sfm/estimators/estimate_relative_
 };
 struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator, PnPType::KNEIP (sfm/estimators/estimate_calibrated_absolute_pose.cc:63-172)
   static constexpr int S = 3, D = 5, MAXM = 4;  // datum: feature (x, y), world point (X, Y, Z)
+  static constexpr bool HAS_LO = false;  // its LO is BundleAdjustView on a one-view reconstruction (:120-153): rejected
+  __device__ static bool refine(const double*, const uint8_t*, int, double, Model*, LoShared&) { return false; }
   __device__ static int solve(const double* sample, Model* out) {
     double feat[6], world[9], Rs[36], ts[12];
     for (int i = 0; i < 3; ++i) { feat[2 * i] = sample[5 * i]; feat[2 * i + 1] = sample[5 * i + 1]; for (int k = 0; k < 3; ++k) world[3 * i + k] = sample[5 * i + 2 + k]; }
@@ -503,6 +808,8 @@ struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator, PnPType::KNEIP (sfm/est
 };
 struct HomographyEst {  // HomographyEstimator (sfm/estimators/estimate_homography.cc:62-116); H lives in Model::E
   static constexpr int S = 4, D = 4, MAXM = 1;
+  static constexpr bool HAS_LO = false;
+  __device__ static bool refine(const double*, const uint8_t*, int, double, Model*, LoShared&) { return false; }
   __device__ static int solve(const double* sample, Model* out) {
     for (int k = 0; k < 9; ++k) out->R[k] = 0.0;
     for (int k = 0; k < 3; ++k) out->p[k] = 0.0;
@@ -623,6 +930,10 @@ struct RansacShared {
   int max_iterations, it0, finished, num_iterations, have_best, pair;
   unsigned long long stat_samples, stat_models, stat_data;
   long long cyc[4];  // draw, solve, score, scan
+  // LO-RANSAC: the scan stops at an improved model that has to be refined and resumes after the refinement
+  int scan_b, scan_k, scan_it, lo_pending, num_lo;
+  double lo_ratio;
+  LoShared lo;
 };
 
 // Persistent grid (three CTAs per SM) pulling pairs from an atomic counter: RANSAC iteration counts differ by 100x
@@ -635,7 +946,8 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
                                                   const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
                                                   ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
                                                   int* __restrict__ idx_ws, Model* model_ws, double* cost_ws,
-                                                  int* ninl_ws, int* __restrict__ pair_counter, unsigned long long* __restrict__ stats) {
+                                                  int* ninl_ws, int* __restrict__ pair_counter, unsigned long long* __restrict__ stats,
+                                                  uint8_t* __restrict__ lo_flags_all) {
   constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
@@ -673,6 +985,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     S.it0 = 0; S.finished = 0; S.num_iterations = 0; S.have_best = 0;
     S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
     S.cyc[0] = S.cyc[1] = S.cyc[2] = S.cyc[3] = 0;
+    S.num_lo = 0;
     memset(&S.best, 0, sizeof(Model));
   }
   __syncthreads();
@@ -732,48 +1045,106 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     // ---- scan in (iteration, model) order
     if (t == 0) {
       { const long long now = clock64(); S.cyc[2] += now - tick; tick = now; }
-      int it = it0;
-      for (int b = 0; b < nit; ++b, ++it) {
-        if (it >= S.max_iterations) break;
-        for (int k = 0; k < S.nmodels[b]; ++k) {
-          const double sample_cost = g_cost[b * MAXM + k];
-          if (sample_cost < S.best_cost) {
-            const double inlier_ratio = (double)g_ninl[b * MAXM + k] / (double)n;
-            S.best = M[b * MAXM + k];
-            S.best_cost = sample_cost;
-            S.have_best = 1;
-            if (inlier_ratio < (double)SS / (double)n) continue;
-            const int mi = compute_max_iterations(P, SS, inlier_ratio, log_failure_prob, n);
-            if (mi < S.max_iterations) S.max_iterations = mi;
+      S.scan_b = 0; S.scan_k = 0; S.scan_it = it0;
+    }
+    if constexpr (!Est::HAS_LO) {  // plain replay: one pass of thread 0 over the batch
+      if (t == 0) {
+        int it = it0;
+        for (int b = 0; b < nit; ++b, ++it) {
+          if (it >= S.max_iterations) break;
+          for (int k = 0; k < S.nmodels[b]; ++k) {
+            const double sample_cost = g_cost[b * MAXM + k];
+            if (sample_cost < S.best_cost) {
+              const double inlier_ratio = (double)g_ninl[b * MAXM + k] / (double)n;
+              S.best = M[b * MAXM + k];
+              S.best_cost = sample_cost;
+              S.have_best = 1;
+              if (inlier_ratio < (double)SS / (double)n) continue;
+              const int mi = compute_max_iterations(P, SS, inlier_ratio, log_failure_prob, n);
+              if (mi < S.max_iterations) S.max_iterations = mi;
+            }
           }
         }
+        S.it0 = it;
       }
-      S.it0 = it;
-      S.cyc[3] += clock64() - tick;
+    } else {
+    int pending = 1;  // CTA-uniform
+    while (pending) {
+      if (t == 0) {
+        S.lo_pending = 0;
+        int it = S.scan_it, b = S.scan_b, k = S.scan_k;
+        while (b < nit) {
+          if (k == 0 && it >= S.max_iterations) break;
+          bool hit = false;
+          for (; k < S.nmodels[b]; ++k) {
+            const double sample_cost = g_cost[b * MAXM + k];
+            if (sample_cost < S.best_cost) {
+              const double inlier_ratio = (double)g_ninl[b * MAXM + k] / (double)n;
+              S.best = M[b * MAXM + k];
+              S.best_cost = sample_cost;
+              S.have_best = 1;
+              if (inlier_ratio < (double)SS / (double)n) continue;
+              if (Est::HAS_LO && P.use_lo && it >= P.lo_start_iterations) {  // sample_consensus_estimator.h:372-380
+                S.lo_pending = 1; S.lo_ratio = inlier_ratio; S.scan_b = b; S.scan_k = k + 1; S.scan_it = it;
+                hit = true;
+                break;
+              }
+              const int mi = compute_max_iterations(P, SS, inlier_ratio, log_failure_prob, n);
+              if (mi < S.max_iterations) S.max_iterations = mi;
+            }
+          }
+          if (hit) break;
+          k = 0; ++b; ++it;
+        }
+        if (!S.lo_pending) S.it0 = it;
+      }
+      __syncthreads();
+      pending = S.lo_pending;
+      if (pending) {
+        // inliers of the new best model (it was scored with early abandonment off: its cost is below the bail value), then RefineModel
+        uint8_t* flags = lo_flags_all + off;
+        if (w == 0) { double c_; int n_; unsigned sc_ = 0; score_model<Est>(P, corr, n, S.best, DBL_MAX, flags, &c_, &n_, &sc_); }
+        __syncthreads();
+        const bool refined = Est::refine(corr, flags, n, P.error_thresh, &S.best, S.lo);
+        if (t == 0 && refined) {  // a failed refinement `continue`s: the iteration bound is not updated
+          ++S.num_lo;
+          const int mi = compute_max_iterations(P, SS, S.lo_ratio, log_failure_prob, n);
+          if (mi < S.max_iterations) S.max_iterations = mi;
+        }
+      }
+      __syncthreads();  // S.lo_pending is rewritten by thread 0 at the top of the next round
     }
+    }
+    if (t == 0) S.cyc[3] += clock64() - tick;
     __syncthreads();
   }
   // ---- final inliers of the best model (sample_consensus_estimator.h:396-414)
-  if (w == 0) {
-    double cost; int ninl;
-    unsigned scored = 0;
-    score_model<Est>(P, corr, n, S.best, DBL_MAX, mask, &cost, &ninl, &scored);
-    if (lane == 0) {
-      if (stats) {
-        atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)S.num_iterations); atomicAdd(stats + 2, S.stat_samples);
-        atomicAdd(stats + 3, S.stat_models + 1); atomicAdd(stats + 4, S.stat_data + scored);
-        for (int k = 0; k < 4; ++k) atomicAdd(stats + 6 + k, (unsigned long long)S.cyc[k]);
-      }
-      out->success = 1;
-      out->num_inliers = ninl;
-      out->num_iterations = S.num_iterations;
-      out->num_input_data_points = n;
-      const double ratio = (double)ninl / (double)n;
-      out->confidence = 1.0 - pow(1.0 - pow(ratio, (double)SS), (double)S.num_iterations);
-      out->best_cost = S.best_cost;
-      for (int k = 0; k < 9; ++k) { out->essential_matrix[k] = S.best.E[k]; out->rotation[k] = S.best.R[k]; }
-      for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
+  uint8_t* fmask = mask ? mask : (lo_flags_all ? lo_flags_all + off : nullptr);
+  double f_cost = 0.0; int f_ninl = 0;
+  unsigned f_scored = 0;
+  if (w == 0) score_model<Est>(P, corr, n, S.best, DBL_MAX, fmask, &f_cost, &f_ninl, &f_scored);
+  if (Est::HAS_LO && P.use_lo) {  // :400-405 - the summary's inliers are those of the model BEFORE this last refinement
+    __syncthreads();
+    Est::refine(corr, fmask, n, P.error_thresh, &S.best, S.lo);
+    if (t == 0) ++S.num_lo;
+    __syncthreads();
+  }
+  if (w == 0 && lane == 0) {
+    if (stats) {
+      atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)S.num_iterations); atomicAdd(stats + 2, S.stat_samples);
+      atomicAdd(stats + 3, S.stat_models + 1); atomicAdd(stats + 4, S.stat_data + f_scored);
+      for (int k = 0; k < 4; ++k) atomicAdd(stats + 6 + k, (unsigned long long)S.cyc[k]);
     }
+    out->success = 1;
+    out->num_inliers = f_ninl;
+    out->num_iterations = S.num_iterations;
+    out->num_input_data_points = n;
+    const double ratio = (double)f_ninl / (double)n;
+    out->confidence = 1.0 - pow(1.0 - pow(ratio, (double)SS), (double)S.num_iterations);
+    out->best_cost = S.best_cost;
+    out->num_lo_iterations = S.num_lo; out->reserved0 = 0;
+    for (int k = 0; k < 9; ++k) { out->essential_matrix[k] = S.best.E[k]; out->rotation[k] = S.best.R[k]; }
+    for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
   }
   }  // next pair
 }
@@ -855,7 +1226,11 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   // the reference CHECK-aborts on these (sample_consensus_estimator.h:217-223)
   if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
       p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) THB_FAIL(THB_E_INVALID_ARGUMENT, "invalid RansacParameters");
-  if (p->use_lo) THB_FAIL(THB_E_UNSUPPORTED, "use_lo (LO-RANSAC refinement by bundle adjustment) is not implemented");
+  if (p->use_lo && !Est::HAS_LO) {
+    if (Est::S == 3) THB_FAIL(THB_E_UNSUPPORTED, "use_lo for the absolute-pose estimator (BundleAdjustView on a one-view reconstruction) is not implemented");
+    // HomographyEstimator has no RefineModel: the reference's LO branch is a `continue` that only skips the iteration-bound update
+    THB_FAIL(THB_E_UNSUPPORTED, "use_lo is only implemented for the relative-pose estimator");
+  }
   if (p->ransac_type != 0) THB_FAIL(THB_E_UNSUPPORTED, "only RansacType::RANSAC is implemented");
   if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
   if (b->num_pairs == 0) return THB_OK;
@@ -909,10 +1284,12 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
   int* d_counter = B.get<int>(1);
   unsigned long long* d_stats = B.get<unsigned long long>(10);
+  uint8_t* d_lo_flags = (p->use_lo && Est::HAS_LO) ? B.get<uint8_t>((size_t)total) : nullptr;
+  if (p->use_lo && Est::HAS_LO && !d_lo_flags) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   if (!d_models || !d_cost || !d_ninl || !d_counter || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
   THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
-  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats);
+  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats, d_lo_flags);
   THB_CUDA_CHECK(cudaGetLastError());
   THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
   if (host) {

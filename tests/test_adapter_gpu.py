@@ -168,9 +168,10 @@ def test_EstimateRelativePose():
     assert len(summary.inliers) > 150 and summary.num_input_data_points == 300 and summary.confidence > 0.99
     again = pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)   # the seed field makes it reproducible
     assert again[2].inliers == summary.inliers and again[2].num_iterations == summary.num_iterations
-    params.use_lo = True
-    with pytest.raises(RuntimeError, match="use_lo"):
-        pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)
+    params.use_lo = True; params.lo_start_iterations = 5      # LO-RANSAC (estimate_relative_pose_test.cc:220-279 style)
+    ok_lo, pose_lo, summary_lo = pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)
+    assert ok_lo and summary_lo.num_lo_iterations >= 1
+    assert np.rad2deg(np.arccos(np.clip((np.trace(pose_lo.rotation @ R.T) - 1) / 2, -1, 1))) < 1.0
 
 
 def test_PoseFromThreePoints_and_EstimateCalibratedAbsolutePose():

@@ -95,7 +95,7 @@ def test_k1_shared_camera_kernel_matches_gather_kernel(lib, oracle, monkeypatch,
         runs[mode] = (gpu_solve(lib, pg, opts), pg)
     a, b = runs["gather"], runs["shared"]
     # per-observation values are identical; the cost is summed by one atomic per warp, in arrival order
-    np.testing.assert_allclose(a[0]["iter_cost"], b[0]["iter_cost"], rtol=1e-13)
+    np.testing.assert_allclose(a[0]["iter_cost"], b[0]["iter_cost"], rtol=1e-11)
     assert a[0]["num_iterations"] == b[0]["num_iterations"]
     # (the two instantiations need not contract the same multiply-adds, and the Euclidean 4-vector points have a gauge
     # direction along which last-bit differences drift)

@@ -27,7 +27,12 @@ def _batch(g):
 
 
 def _results(g):
-    return np.frombuffer(np.ascontiguousarray(g["results"]).tobytes(), dtype=capi.RELPOSE_DTYPE)
+    # the committed records are the r01 ThbRelPoseResult (200 bytes); later revisions append fields (num_lo_iterations)
+    raw = np.ascontiguousarray(g["results"])
+    fields = [(n, capi.RELPOSE_DTYPE.fields[n][0]) for n in capi.RELPOSE_DTYPE.names]
+    while sum(dt.itemsize for _, dt in fields) > raw.shape[1]:
+        fields.pop()
+    return np.frombuffer(raw.tobytes(), dtype=np.dtype(fields))
 
 
 def _c4_params(p):

@@ -122,7 +122,7 @@ def test_ransac_device_resident_batch_and_error_codes(lib):
     bb = batch.struct()
     assert lib.thb_ransac_relpose_batch(C.byref(bb), C.byref(bad), _vp(res), None, None) == capi.THB_E_INVALID_ARGUMENT
     bad = synthetic.c4_params(capi.ThbRansacParams()); bad.use_lo = 1
-    assert lib.thb_ransac_relpose_batch(C.byref(bb), C.byref(bad), _vp(res), None, None) == capi.THB_E_UNSUPPORTED
+    assert lib.thb_ransac_abspose_batch(C.byref(bb), C.byref(bad), _vp(res), None, None) == capi.THB_E_UNSUPPORTED
 
 
 def test_c4_full_size_properties(lib):
@@ -274,3 +274,29 @@ def test_fp64_peak_probe(lib):
     t = C.c_double(0.0)
     capi.check(lib.thb_fp64_peak_tflops(3, C.byref(t), None))
     assert 20.0 < t.value < 80.0, t.value
+
+
+@pytest.mark.parametrize("lo_start", [0, 50])
+def test_lo_ransac_relative_pose_matches_oracle(lib, oracle, lo_start):
+    """use_lo (the pipelines' default, reconstruction_estimator_options.h:133): RelativePoseEstimator::RefineModel =
+    BundleAdjustTwoViewsAngular on every improved model from lo_start_iterations on and once on the final inliers. Same
+    iteration counts, LO counts and inlier sets as the oracle; the refined pose agrees to rounding (the device reduces
+    J^T J in block-tree order) and is closer to the truth than the plain RANSAC pose."""
+    batch, gts = synthetic.make_pair_batch_indexed(range(48), n=1200, seed=9)
+    def mk(p, lo):
+        p = synthetic.c4_params(p); p.use_lo = lo; p.lo_start_iterations = lo_start
+        return p
+    res, mask = gpu_ransac(lib, batch, mk(capi.ThbRansacParams(), 1))
+    plain, _ = gpu_ransac(lib, batch, mk(capi.ThbRansacParams(), 0))
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, mk(oracle.ransac_default_params(), 1))
+    assert rc == 0
+    for f in ("success", "num_iterations", "num_lo_iterations", "num_inliers"):
+        np.testing.assert_array_equal(res[f], ores[f], err_msg=f)
+    np.testing.assert_array_equal(mask, omask)
+    assert np.array_equal(res["essential_matrix"], ores["essential_matrix"])      # E is not touched by the refinement
+    np.testing.assert_allclose(res["rotation"], ores["rotation"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(res["position"], ores["position"], rtol=0, atol=1e-9)
+    assert (res["num_lo_iterations"] >= 1).all()
+    def rot_err(r):
+        return np.array([np.rad2deg(np.arccos(np.clip((np.trace(r["rotation"][i] @ gts[i][0].T) - 1) / 2, -1, 1))) for i in range(batch.num_pairs)])
+    assert rot_err(res).mean() < 0.7 * rot_err(plain).mean()
