@@ -346,6 +346,84 @@ int thb_pack_inlier_masks(const uint8_t* mask, const int64_t* pair_offset, const
  */
 int thb_fp64_peak_tflops(int32_t repeats, double* tflops, void* cuda_stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Two-view geometry of image pairs from PIXEL correspondences (what the pipelines call once per pair).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* A view's intrinsics as Camera::SetFromCameraIntrinsicsPriors leaves them (camera.cc), per-model parameter layout. */
+typedef struct ThbViewIntrinsics {
+  int32_t model;               /* THB_MODEL_*                                                           */
+  int32_t image_width;         /* CameraIntrinsicsPrior::image_width / image_height (0 = unknown)        */
+  int32_t image_height;
+  int32_t focal_length_is_set; /* CameraIntrinsicsPrior::focal_length.is_set: both views set = calibrated */
+  double params[THB_INTR_STRIDE];
+} ThbViewIntrinsics;
+
+/* EstimateTwoViewInfoOptions (sfm/estimate_twoview_info.h:51-80) + TwoViewMatchGeometricVerification::Options
+ * (sfm/two_view_match_geometric_verification.h:53-92). Fill with thb_two_view_default_options. */
+typedef struct ThbTwoViewOptions {
+  double max_sampson_error_pixels;   /* 6.0, relative to a 1024-pixel image (reconstruction_estimator_utils.cc:97-110) */
+  double expected_ransac_confidence; /* 0.9999 */
+  int32_t min_ransac_iterations;     /* 10   */
+  int32_t max_ransac_iterations;     /* 1000 */
+  int32_t use_mle;                   /* 1    */
+  int32_t use_lo;                    /* 0    */
+  int32_t lo_start_iterations;       /* 10   */
+  int32_t ransac_type;               /* RANSAC (0) only */
+  /* verification only */
+  int32_t min_num_inlier_matches;    /* 30 */
+  int32_t bundle_adjustment;         /* 1  */
+  double triangulation_max_reprojection_error; /* 15 px */
+  double min_triangulation_angle_degrees;      /* 4     */
+  double final_max_reprojection_error;         /* 5 px  */
+} ThbTwoViewOptions;
+
+/* TwoViewInfo (sfm/twoview_info.h:52-80) + the return value of the call. */
+typedef struct ThbTwoViewInfo {
+  int32_t success;                /* return value of EstimateTwoViewInfo / VerifyMatches               */
+  int32_t num_verified_matches;
+  int32_t num_homography_inliers; /* VerifyMatches only */
+  int32_t visibility_score;       /* the reference computes it from the inlier list BEFORE filling it: always 0 (estimate_twoview_info.cc:186-189) */
+  int32_t num_ransac_iterations;  /* RansacSummary::num_iterations of the relative-pose RANSAC          */
+  int32_t num_triangulated;       /* VerifyMatches: matches that survived TriangulatePoints             */
+  int32_t ba_iterations;          /* VerifyMatches: trust-region iterations of BundleAdjustTwoViews     */
+  int32_t reserved0;
+  double focal_length_1, focal_length_2;
+  double position_2[3];
+  double rotation_2[3];           /* angle-axis */
+  double ba_initial_cost, ba_final_cost;
+} ThbTwoViewInfo;
+
+void thb_two_view_default_options(ThbTwoViewOptions* options);
+
+/*
+ * theia::EstimateTwoViewInfo (sfm/estimate_twoview_info.cc:259-305), calibrated branch (:133-192), for every pair of the
+ * batch in one call: batch->corr holds PIXEL correspondences (x1, y1, x2, y2); they are normalised with each view's inverse
+ * camera model (NormalizeFeatures :67-103 -> Camera::PixelToNormalizedCoordinates, all six models), the per-pair Sampson
+ * threshold is scaled1 * scaled2 / (f1 * f2) (:155-167), then EstimateRelativePose runs with the pair's seed.
+ * intrinsics1 / intrinsics2: [num_pairs]; info: [num_pairs]; inlier_mask: [total] (TwoViewInfo's inlier_indices), may be
+ * NULL. Pairs whose views are not both calibrated return THB_E_UNSUPPORTED (the uncalibrated branch, :194-255, needs the
+ * eight-point estimator). All pointers in batch->memory_space.
+ */
+int thb_estimate_two_view_info_batch(const ThbPairBatch* batch, const ThbViewIntrinsics* intrinsics1,
+                                     const ThbViewIntrinsics* intrinsics2, const ThbTwoViewOptions* options,
+                                     ThbTwoViewInfo* info, uint8_t* inlier_mask, void* cuda_stream);
+
+/*
+ * theia::TwoViewMatchGeometricVerification::VerifyMatches (sfm/two_view_match_geometric_verification.cc:114-183) for every
+ * pair of the batch: CountHomographyInliers (:331-366, EstimateHomography on the pixel matches; its threshold uses the
+ * not-yet-set-up cameras, i.e. max_sampson_error_pixels^2), EstimateTwoViewInfo on the SAME random generator, the
+ * min_num_inlier_matches gates, and - options->bundle_adjustment - BundleAdjustRelativePose (:259-327): TriangulatePoints
+ * (angle test, TriangulateMidpoint, 15 px reprojection gate), BundleAdjustTwoViews (camera 1 fixed, camera 2 extrinsics and
+ * the 4-vector points free, no loss, DENSE_SCHUR; sfm/bundle_adjustment/bundle_adjust_two_views.cc:112-193) and the 5 px
+ * reprojection filter. verified_mask [total]: 1 = the match is in verified_matches. Guided matching needs descriptors and
+ * is not part of this entry. Calibrated pairs only.
+ */
+int thb_verify_two_view_matches_batch(const ThbPairBatch* batch, const ThbViewIntrinsics* intrinsics1,
+                                      const ThbViewIntrinsics* intrinsics2, const ThbTwoViewOptions* options,
+                                      ThbTwoViewInfo* info, uint8_t* verified_mask, void* cuda_stream);
+
 /* theia::PoseFromThreePoints (sfm/pose/perspective_three_point.cc:182-291) for `count` independent samples (host
  * pointers): features [count*3*2], world_points [count*3*3]; R_out [count*4*9] row-major, t_out [count*4*3],
  * num_solutions [count] (0 => collinear world points, the reference returns false). */

@@ -220,5 +220,73 @@ inline bool ReprojectionError(int model, const T* ext, const T* K, const T* X,
   return true;
 }
 
+
+// ---- inverse models (ORACLE): Model::PixelToCameraCoordinates + UndistortPoint, cited in csrc/camera_models.cuh ----------
+inline bool PixelToCamera(int model, const double* K, const double px[2], double out[3]) {
+  out[0] = out[1] = out[2] = 0.0;
+  auto skewed_normalise = [&](double d[2]) {
+    d[1] = (px[1] - K[4]) / (K[0] * K[1]);
+    d[0] = (px[0] - K[3] - d[1] * K[2]) / K[0];
+  };
+  if (model == PINHOLE || model == FISHEYE) {
+    double d[2]; skewed_normalise(d);
+    double u[2] = {d[0], d[1]};
+    for (int it = 0; it < 100; ++it) {
+      const double prev[2] = {u[0], u[1]};
+      const double r_sq = u[0] * u[0] + u[1] * u[1];
+      if (model == PINHOLE) {
+        const double f = 1.0 + r_sq * (K[5] + K[6] * r_sq);
+        u[0] = d[0] / f; u[1] = d[1] / f;
+      } else {
+        const double r = std::sqrt(r_sq);
+        if (r < 1e-8) { u[0] = d[0]; u[1] = d[1]; break; }
+        const double th = std::atan2(r, 1.0), th2 = th * th;
+        const double thd = th * (1.0 + K[5] * th2 + K[6] * th2 * th2 + K[7] * th2 * th2 * th2 + K[8] * th2 * th2 * th2 * th2);
+        u[0] = r * d[0] / thd; u[1] = r * d[1] / thd;
+      }
+      if (std::fabs(u[0] - prev[0]) < 1e-10 && std::fabs(u[1] - prev[1]) < 1e-10) break;
+    }
+    out[0] = u[0]; out[1] = u[1]; out[2] = 1.0;
+    return true;
+  }
+  if (model == FOV) {
+    const double d[2] = {(px[0] - K[2]) / K[0], (px[1] - K[3]) / (K[0] * K[1])};
+    const double w = K[4], rd2 = d[0] * d[0] + d[1] * d[1];
+    double ru;
+    if (w < 1e-3) ru = (w * w * rd2) / 3.0 - w * w / 12.0 + 1.0;
+    else if (rd2 < 1e-3) ru = (w * (w * w * rd2 + 3.0)) / (6.0 * std::tan(w / 2.0));
+    else { const double rd = std::sqrt(rd2); ru = std::tan(rd * w) / (2.0 * rd * std::tan(w / 2.0)); }
+    out[0] = ru * d[0]; out[1] = ru * d[1]; out[2] = 1.0;
+    return true;
+  }
+  if (model == DIVISION_UNDISTORTION) {
+    const double d[2] = {px[0] - K[2], px[1] - K[3]};
+    const double und = 1.0 / (1.0 + K[4] * (d[0] * d[0] + d[1] * d[1]));
+    out[0] = d[0] * und / K[0]; out[1] = d[1] * und / (K[0] * K[1]); out[2] = 1.0;
+    return true;
+  }
+  if (model == DOUBLE_SPHERE) {
+    double d[2]; skewed_normalise(d);
+    const double xi = K[5], al = K[6], r2 = d[0] * d[0] + d[1] * d[1];
+    if (al > 0.5 && r2 >= 1.0 / (2.0 * al - 1.0)) return false;
+    const double s2 = std::sqrt(1.0 - (2.0 * al - 1.0) * r2), n2 = al * s2 + 1.0 - al;
+    const double mz = (1.0 - al * al * r2) / n2, mz2 = mz * mz;
+    const double k = (mz * xi + std::sqrt(mz2 + (1.0 - xi * xi) * r2)) / (mz2 + r2);
+    out[0] = k * d[0]; out[1] = k * d[1]; out[2] = k * mz - xi;
+    return true;
+  }
+  if (model == EXTENDED_UNIFIED) {
+    double d[2]; skewed_normalise(d);
+    const double al = K[5], be = K[6], r2 = d[0] * d[0] + d[1] * d[1], ga = 1.0 - al;
+    if (al > 0.5 && r2 >= 1.0 / ((al - ga) * be)) return false;
+    const double k = (1.0 - al * al * be * r2) / (al * std::sqrt(1.0 - (al - ga) * be * r2) + ga);
+    double nrm = std::sqrt(r2 + k * k);
+    if (nrm < 1e-12) nrm = 1e-12;
+    out[0] = d[0] / nrm; out[1] = d[1] / nrm; out[2] = k / nrm;
+    return true;
+  }
+  return false;
+}
+
 }  // namespace oracle
 #endif  // ORACLE_CAMERA_MODELS_H_

@@ -123,6 +123,17 @@ def ransac_relpose_batch(batch, params, threads=0):
     return ransac_batch("relpose", batch, params, threads)
 
 
+def two_view_batch(batch, intr1, intr2, options, verify):
+    """EstimateTwoViewInfo (verify = False) / VerifyMatches (verify = True) for every pair; returns (rc, info, mask)."""
+    lib = load()
+    lib.oracle_two_view_batch.argtypes = [C.POINTER(capi.ThbPairBatch), C.c_void_p, C.c_void_p, C.POINTER(capi.ThbTwoViewOptions), C.c_void_p, C.c_void_p, C.c_int32]
+    info = np.zeros(batch.num_pairs, capi.TWO_VIEW_INFO_DTYPE)
+    mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
+    b = batch.struct()
+    rc = lib.oracle_two_view_batch(C.byref(b), _vp(intr1), _vp(intr2), C.byref(options), _vp(info), _vp(mask), int(verify))
+    return rc, info, mask
+
+
 def p3p(feat, world):
     """feat [count,3,2], world [count,3,3] -> (R [count,4,3,3], t [count,4,3], n [count])"""
     feat = np.ascontiguousarray(feat, np.float64); world = np.ascontiguousarray(world, np.float64)

@@ -27,6 +27,7 @@
 #include "../include/theia_b200.h"
 #include "eigen_restated.h"
 #include "jet.h"
+#include "camera_models.h"
 
 namespace oracle {
 namespace {
@@ -804,13 +805,19 @@ double Score(const ThbRansacParams& P, const double* data, int n, const Model& m
 
 // SampleConsensusEstimator::Estimate (sample_consensus_estimator.h:299-415) with RandomSampler (random_sampler.cc:53-72)
 template <class Est>
+void EstimatePairWith(std::mt19937& gen, const ThbRansacParams& P, const double* data, int n, ThbRelPoseResult* out, uint8_t* mask);
+template <class Est>
 void EstimatePair(const ThbRansacParams& P, const double* data, int n, uint32_t seed, ThbRelPoseResult* out, uint8_t* mask) {
+  std::mt19937 gen(seed);  // RandomNumberGenerator rng(seed) reseeds the process-wide generator (util/random.cc:54-62)
+  EstimatePairWith<Est>(gen, P, data, n, out, mask);
+}
+template <class Est>
+void EstimatePairWith(std::mt19937& gen, const ThbRansacParams& P, const double* data, int n, ThbRelPoseResult* out, uint8_t* mask) {
   constexpr int S = Est::S;
   std::memset(out, 0, sizeof(*out));
   out->num_input_data_points = n;
   if (mask) std::memset(mask, 0, n);
   if (n < S) return;  // RandomSampler::Initialize CHECK_GE -> reported as failure instead of aborting
-  std::mt19937 gen(seed);
   std::vector<int> sample_indices(n);
   std::iota(sample_indices.begin(), sample_indices.end(), 0);
   const double log_failure_prob = std::log(P.failure_probability);
@@ -871,6 +878,140 @@ void EstimatePair(const ThbRansacParams& P, const double* data, int n, uint32_t 
   if (mask) for (int i : inl) mask[i] = 1;
 }
 
+
+extern "C" int oracle_triangulate_midpoint_batch(const double* org, const double* dir, const int64_t* off, int32_t num_tracks, double* out, uint8_t* ok);
+// ---- EstimateTwoViewInfo (calibrated) and TwoViewMatchGeometricVerification::VerifyMatches for one pair ---------------------
+// estimate_twoview_info.cc:67-192, two_view_match_geometric_verification.cc:114-366. The two RANSACs of VerifyMatches run on
+// ONE generator (homography_params.rng = etvi_options.rng, and every RandomNumberGenerator wraps the same thread_local
+// std::mt19937): CountHomographyInliers consumes it first, EstimateRelativePose continues where it stopped.
+extern "C" int oracle_ba_solve(const ThbBaProblem* p, const ThbBaOptions* o, ThbBaSummary* s);
+extern "C" void oracle_ba_default_options(ThbBaOptions* o);
+
+inline double ScaledThreshold(double t, int w, int h) {  // reconstruction_estimator_utils.cc:97-110
+  if (w == 0 && h == 0) return t;
+  return t * static_cast<double>(std::max(w, h)) / 1024.0;
+}
+inline bool AcceptableReprojection(int model, const double* K, const double ext[6], const double X[4], const double* feat, double sq_max) {
+  const double adj[3] = {X[0] - X[3] * ext[0], X[1] - X[3] * ext[1], X[2] - X[3] * ext[2]};
+  double pc[3], pix[2];
+  AngleAxisRotatePoint(ext + 3, adj, pc);
+  if (pc[2] / X[3] < 0.0) return false;  // Camera::ProjectPoint < 0
+  if (!ProjectByModel<double>(model, K, pc, pix)) return false;
+  const double ex = feat[0] - pix[0], ey = feat[1] - pix[1];
+  return ex * ex + ey * ey < sq_max;
+}
+
+void TwoViewPair(const ThbTwoViewOptions& O, const ThbViewIntrinsics& I1, const ThbViewIntrinsics& I2, const double* px, int n, uint32_t seed,
+                 bool verify, ThbTwoViewInfo* info, uint8_t* out_mask) {
+  std::memset(info, 0, sizeof(*info));
+  if (out_mask) std::memset(out_mask, 0, n);
+  if (verify && n < O.min_num_inlier_matches) return;
+  std::mt19937 gen(seed);
+  ThbRansacParams rp;
+  std::memset(&rp, 0, sizeof(rp));
+  rp.failure_probability = 1.0 - O.expected_ransac_confidence; rp.min_inlier_ratio = 0.0; rp.min_iterations = O.min_ransac_iterations;
+  rp.max_iterations = O.max_ransac_iterations; rp.use_mle = O.use_mle; rp.lo_start_iterations = 50;
+  if (verify) {  // CountHomographyInliers: cameras not set up yet -> image size 0 -> unscaled thresholds
+    ThbRansacParams hp = rp;
+    hp.error_thresh = O.max_sampson_error_pixels * O.max_sampson_error_pixels;
+    ThbRelPoseResult hres;
+    EstimatePairWith<HomographyEst>(gen, hp, px, n, &hres, nullptr);
+    info->num_homography_inliers = hres.num_inliers;
+  }
+  // NormalizeFeatures
+  std::vector<double> norm(4 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    double q1[3], q2[3];
+    PixelToCamera(I1.model, I1.params, px + 4 * (size_t)i, q1);
+    PixelToCamera(I2.model, I2.params, px + 4 * (size_t)i + 2, q2);
+    norm[4 * i] = q1[0] / q1[2]; norm[4 * i + 1] = q1[1] / q1[2]; norm[4 * i + 2] = q2[0] / q2[2]; norm[4 * i + 3] = q2[1] / q2[2];
+  }
+  rp.use_lo = O.use_lo; rp.lo_start_iterations = O.lo_start_iterations;
+  rp.error_thresh = ScaledThreshold(O.max_sampson_error_pixels, I1.image_width, I1.image_height) *
+                    ScaledThreshold(O.max_sampson_error_pixels, I2.image_width, I2.image_height) / (I1.params[0] * I2.params[0]);
+  ThbRelPoseResult res;
+  std::vector<uint8_t> inl(n, 0);
+  EstimatePairWith<RelPoseEst>(gen, rp, norm.data(), n, &res, inl.data());
+  if (!res.success) return;
+  EigenRotationMatrixToAngleAxis(res.rotation, info->rotation_2);
+  for (int k = 0; k < 3; ++k) info->position_2[k] = res.position[k];
+  info->focal_length_1 = I1.params[0]; info->focal_length_2 = I2.params[0];
+  info->num_verified_matches = res.num_inliers;
+  info->visibility_score = 0;  // inlier list still empty when the score is computed (estimate_twoview_info.cc:186-189)
+  info->num_ransac_iterations = res.num_iterations;
+  if (!verify) { info->success = 1; if (out_mask) std::memcpy(out_mask, inl.data(), n); return; }
+  if (res.num_inliers < O.min_num_inlier_matches) return;
+  if (!(O.bundle_adjustment && res.num_inliers > O.min_num_inlier_matches)) {
+    if (out_mask) std::memcpy(out_mask, inl.data(), n);
+    info->success = res.num_inliers > O.min_num_inlier_matches;
+    return;
+  }
+  // SetupCameras + TriangulatePoints
+  double ext1[6] = {0, 0, 0, 0, 0, 0}, ext2[6];
+  for (int k = 0; k < 3; ++k) { ext2[k] = info->position_2[k]; ext2[3 + k] = info->rotation_2[k]; }
+  const double cos_min = std::cos(O.min_triangulation_angle_degrees * 3.14159265358979323846 / 180.0);
+  const double sq_tri = O.triangulation_max_reprojection_error * O.triangulation_max_reprojection_error;
+  std::vector<int> idx;
+  std::vector<double> pts;
+  const double neg_aa[3] = {-ext2[3], -ext2[4], -ext2[5]};
+  for (int i = 0; i < n; ++i) {
+    if (!inl[i]) continue;
+    double q1[3], q2[3], d2[3];
+    PixelToCamera(I1.model, I1.params, px + 4 * (size_t)i, q1);
+    PixelToCamera(I2.model, I2.params, px + 4 * (size_t)i + 2, q2);
+    AngleAxisRotatePoint(neg_aa, q2, d2);  // R^T q2
+    const double n1 = std::sqrt(q1[0] * q1[0] + q1[1] * q1[1] + q1[2] * q1[2]), n2 = std::sqrt(d2[0] * d2[0] + d2[1] * d2[1] + d2[2] * d2[2]);
+    const double d1[3] = {q1[0] / n1, q1[1] / n1, q1[2] / n1};
+    for (double& v : d2) v /= n2;
+    if (!(d1[0] * d2[0] + d1[1] * d2[1] + d1[2] * d2[2] < cos_min)) continue;
+    const double org[6] = {0, 0, 0, ext2[0], ext2[1], ext2[2]}, dir[6] = {d1[0], d1[1], d1[2], d2[0], d2[1], d2[2]};
+    const int64_t roff[2] = {0, 2};
+    double X[4]; uint8_t ok = 0;
+    oracle_triangulate_midpoint_batch(org, dir, roff, 1, X, &ok);
+    if (!ok) continue;
+    if (!AcceptableReprojection(I1.model, I1.params, ext1, X, px + 4 * (size_t)i, sq_tri) ||
+        !AcceptableReprojection(I2.model, I2.params, ext2, X, px + 4 * (size_t)i + 2, sq_tri)) continue;
+    idx.push_back(i);
+    pts.insert(pts.end(), X, X + 4);
+  }
+  info->num_triangulated = static_cast<int>(idx.size());
+  if (static_cast<int>(idx.size()) < O.min_num_inlier_matches) return;
+  // BundleAdjustTwoViews: camera 1 constant, camera 2 free, 4-vector points free, intrinsics constant (calibrated)
+  const int m = static_cast<int>(idx.size());
+  std::vector<double> cam(12), intr(2 * THB_INTR_STRIDE), xy(4 * (size_t)m);
+  std::vector<int32_t> ocam(2 * (size_t)m), opt(2 * (size_t)m), group = {0, 1}, model = {I1.model, I2.model};
+  std::vector<uint8_t> cconst = {THB_CAM_CONST_ALL, 0};
+  for (int k = 0; k < 6; ++k) { cam[k] = ext1[k]; cam[6 + k] = ext2[k]; }
+  for (int k = 0; k < THB_INTR_STRIDE; ++k) { intr[k] = I1.params[k]; intr[THB_INTR_STRIDE + k] = I2.params[k]; }
+  for (int q = 0; q < m; ++q) {
+    ocam[2 * q] = 0; ocam[2 * q + 1] = 1; opt[2 * q] = q; opt[2 * q + 1] = q;
+    for (int k = 0; k < 4; ++k) xy[4 * q + k] = px[4 * (size_t)idx[q] + k];
+  }
+  ThbBaProblem P;
+  std::memset(&P, 0, sizeof(P));
+  P.num_cameras = 2; P.num_groups = 2; P.num_points = m; P.num_observations = 2 * m; P.memory_space = THB_MEM_HOST;
+  P.cam_ext = cam.data(); P.cam_const = cconst.data(); P.cam_group = group.data(); P.intr = intr.data(); P.intr_model = model.data();
+  P.intr_const = nullptr; P.pts = pts.data(); P.pt_const = nullptr; P.obs_cam = ocam.data(); P.obs_pt = opt.data(); P.obs_xy = xy.data();
+  ThbBaOptions bo;
+  oracle_ba_default_options(&bo);
+  bo.use_homogeneous_point_parametrization = 0; bo.use_inner_iterations = 0; bo.max_trust_region_radius = 1e16; bo.max_num_iterations = 100;
+  ThbBaSummary sum;
+  const int rc = oracle_ba_solve(&P, &bo, &sum);
+  info->ba_iterations = sum.num_iterations; info->ba_initial_cost = sum.initial_cost; info->ba_final_cost = sum.final_cost;
+  if (rc != THB_OK || !sum.success) return;
+  const double sq_fin = O.final_max_reprojection_error * O.final_max_reprojection_error;
+  int kept = 0;
+  for (int q = 0; q < m; ++q) {
+    const bool ok = AcceptableReprojection(I1.model, I1.params, &cam[0], &pts[4 * (size_t)q], px + 4 * (size_t)idx[q], sq_fin) &&
+                    AcceptableReprojection(I2.model, I2.params, &cam[6], &pts[4 * (size_t)q], px + 4 * (size_t)idx[q] + 2, sq_fin);
+    if (ok) { ++kept; if (out_mask) out_mask[idx[q]] = 1; }
+  }
+  const double pn = std::sqrt(cam[6] * cam[6] + cam[7] * cam[7] + cam[8] * cam[8]);
+  for (int k = 0; k < 3; ++k) { info->rotation_2[k] = cam[9 + k]; info->position_2[k] = cam[6 + k] / pn; }
+  info->num_verified_matches = kept;
+  info->success = kept > O.min_num_inlier_matches;
+}
+
 template <class Est>
 int RunBatch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
   if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
@@ -907,6 +1048,18 @@ int oracle_five_point(const double* x1, const double* x2, int32_t count, double*
   return THB_OK;
 }
 
+int oracle_two_view_batch(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbViewIntrinsics* i2, const ThbTwoViewOptions* o,
+                          ThbTwoViewInfo* info, uint8_t* mask, int32_t verify) {
+  if (!b || !i1 || !i2 || !o || !info) return THB_E_INVALID_ARGUMENT;
+  for (int i = 0; i < b->num_pairs; ++i) if (!i1[i].focal_length_is_set || !i2[i].focal_length_is_set) return THB_E_UNSUPPORTED;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int i = 0; i < b->num_pairs; ++i) {
+    const int64_t off = b->pair_offset[i];
+    oracle::TwoViewPair(*o, i1[i], i2[i], b->corr + 4 * off, static_cast<int>(b->pair_offset[i + 1] - off), b->seed[i], verify != 0, info + i,
+                        mask ? mask + off : nullptr);
+  }
+  return THB_OK;
+}
 int oracle_ransac_relpose_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* mask, int32_t threads) {
   return oracle::RunBatch<oracle::RelPoseEst>(b, p, results, mask, threads);
 }

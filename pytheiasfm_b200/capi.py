@@ -128,6 +128,28 @@ class ThbRelPoseResult(C.Structure):
     ]
 
 
+class ThbViewIntrinsics(C.Structure):
+    _fields_ = [("model", C.c_int32), ("image_width", C.c_int32), ("image_height", C.c_int32), ("focal_length_is_set", C.c_int32),
+                ("params", C.c_double * THB_INTR_STRIDE)]
+
+
+class ThbTwoViewOptions(C.Structure):
+    _fields_ = [("max_sampson_error_pixels", C.c_double), ("expected_ransac_confidence", C.c_double),
+                ("min_ransac_iterations", C.c_int32), ("max_ransac_iterations", C.c_int32), ("use_mle", C.c_int32), ("use_lo", C.c_int32),
+                ("lo_start_iterations", C.c_int32), ("ransac_type", C.c_int32), ("min_num_inlier_matches", C.c_int32),
+                ("bundle_adjustment", C.c_int32), ("triangulation_max_reprojection_error", C.c_double),
+                ("min_triangulation_angle_degrees", C.c_double), ("final_max_reprojection_error", C.c_double)]
+
+
+VIEW_INTRINSICS_DTYPE = np.dtype([("model", np.int32), ("image_width", np.int32), ("image_height", np.int32), ("focal_length_is_set", np.int32),
+                                  ("params", np.float64, (THB_INTR_STRIDE,))])
+TWO_VIEW_INFO_DTYPE = np.dtype([("success", np.int32), ("num_verified_matches", np.int32), ("num_homography_inliers", np.int32),
+                                ("visibility_score", np.int32), ("num_ransac_iterations", np.int32), ("num_triangulated", np.int32),
+                                ("ba_iterations", np.int32), ("reserved0", np.int32), ("focal_length_1", np.float64), ("focal_length_2", np.float64),
+                                ("position_2", np.float64, (3,)), ("rotation_2", np.float64, (3,)), ("ba_initial_cost", np.float64),
+                                ("ba_final_cost", np.float64)])
+assert VIEW_INTRINSICS_DTYPE.itemsize == C.sizeof(ThbViewIntrinsics)
+
 TRACK_SKIPPED, TRACK_ESTIMATED, TRACK_BAD_ANGLE, TRACK_FAILED_TRIANGULATION, TRACK_BA_FAILED, TRACK_BAD_REPROJECTION = -1, 0, 1, 2, 3, 4
 
 
@@ -227,6 +249,11 @@ def load_library():
     lib.thb_pack_inlier_masks.restype = C.c_int
     lib.thb_fp64_peak_tflops.argtypes = [C.c_int32, C.POINTER(C.c_double), C.c_void_p]
     lib.thb_fp64_peak_tflops.restype = C.c_int
+    lib.thb_two_view_default_options.argtypes = [C.POINTER(ThbTwoViewOptions)]
+    lib.thb_two_view_default_options.restype = None
+    for name in ("thb_estimate_two_view_info_batch", "thb_verify_two_view_matches_batch"):
+        getattr(lib, name).argtypes = [C.POINTER(ThbPairBatch), C.c_void_p, C.c_void_p, C.POINTER(ThbTwoViewOptions), C.c_void_p, C.c_void_p, C.c_void_p]
+        getattr(lib, name).restype = C.c_int
     lib.thb_p3p.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.thb_p3p.restype = C.c_int
     lib.thb_ba_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.POINTER(ThbBaOptions), C.c_void_p, C.c_void_p]

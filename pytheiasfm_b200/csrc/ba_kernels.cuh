@@ -86,31 +86,6 @@ __global__ void k_setup_slots(int no, const int* __restrict__ op_cam, const int*
 // Per-camera record (ba_device.cuh): angle-axis vector plus the scalar coefficients of the rotation
 // (ceres::AngleAxisRotatePoint semantics, incl. the first-order branch for theta^2 <= eps) and of the SO(3) left
 // Jacobian used for d(R v)/d(aa).
-__device__ __forceinline__ void cam_derive_record(const double* __restrict__ cam6, double* __restrict__ o) {
-  const double wx = cam6[3], wy = cam6[4], wz = cam6[5];
-  const double th2 = wx * wx + wy * wy + wz * wz;
-  o[CD_W] = wx; o[CD_W + 1] = wy; o[CD_W + 2] = wz;
-  if (th2 > 2.220446049250313e-16) {
-    const double th = sqrt(th2);
-    double s, co;
-    sincos(th, &s, &co);
-    // R = I + (sin th / th) [w]x + ((1 - cos th) / th^2) [w]x^2; J_l = I + A [w]x + B [w]x^2,
-    // A = (1 - cos th)/th^2, B = (th - sin th)/th^3 (series below 1e-2: the closed forms cancel)
-    double A, B;
-    if (th < 1e-2) {
-      A = 0.5 - th2 / 24.0 + th2 * th2 / 720.0;
-      B = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0;
-    } else {
-      const double sh = sin(0.5 * th);
-      A = 2.0 * sh * sh / th2;
-      B = (th - s) / (th2 * th);
-    }
-    o[CD_A] = s / th; o[CD_B] = A; o[CD_JA] = A; o[CD_JB] = B;
-  } else {
-    o[CD_A] = 1.0; o[CD_B] = 0.0; o[CD_JA] = 0.0; o[CD_JB] = 0.0;
-  }
-  o[CD_C] = cam6[0]; o[CD_C + 1] = cam6[1]; o[CD_C + 2] = cam6[2];
-}
 __global__ void k_cam_derive(const double* __restrict__ cam, double* __restrict__ camd, int nc, const double* __restrict__ cs,
                              const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_group) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,48 +283,6 @@ __global__ void __launch_bounds__(256) k_cost(BaConst K, BaState S, ObsSoA O, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// Small SPD inverse by Cholesky, N in {3,4}; returns false if not positive definite.
-template <int N>
-__device__ __forceinline__ bool spd_inverse(const double* A /*row-major NxN, lower used*/, double* Ainv) {
-  double L[N][N];
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i * N + j];
-#pragma unroll
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[i][i] = sqrt(s);
-      } else {
-        L[i][j] = s / L[j][j];
-      }
-    }
-  double Li[N][N];  // inverse of L (lower)
-#pragma unroll
-  for (int j = 0; j < N; ++j) {
-    Li[j][j] = 1.0 / L[j][j];
-#pragma unroll
-    for (int r = j + 1; r < N; ++r) {
-      double acc = 0.0;
-#pragma unroll
-      for (int k = j; k < r; ++k) acc += L[r][k] * Li[k][j];
-      Li[r][j] = -acc / L[r][r];
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < N; ++i)
-#pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = i; k < N; ++k) s += Li[k][i] * Li[k][j];
-      Ainv[i * N + j] = s; Ainv[j * N + i] = s;
-    }
-  return true;
-}
-
 // K2a: per point, V = sum Jp^T Jp (+ LM diagonal), g_p = sum Jp^T r, V^-1. One thread per point.
 template <int PD>
 __global__ void __launch_bounds__(128) k_point_pass(int np, int no, const int* __restrict__ pt_start,

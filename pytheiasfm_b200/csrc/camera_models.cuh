@@ -158,5 +158,92 @@ THB_HD bool project(int model, const TK* K, const T p[3], T pix[2]) {
   }
 }
 
+
+// ---- inverse models: Model::PixelToCameraCoordinates (pixel -> point on the z = 1 plane, or a ray for the two omnidirectional
+// models), what Camera::PixelToNormalizedCoordinates / PixelToUnitDepthRay call (camera.cc:218-230). Paths under
+// /root/reference/src/theia/sfm/camera/: pinhole_camera_model.h:212-300, fisheye_camera_model.h:192-345,
+// fov_camera_model.h:183-206,260-306, division_undistortion_camera_model.h:231-260,299-320,
+// double_sphere_camera_model.h:188-212,251-286, extended_unified_camera_model.h:188-212,251-285. Returns false where the
+// reference's UndistortPoint returns false (the reference then leaves the point uninitialised; here it is zero).
+THB_HD bool pixel_to_camera(int model, const double* K, const double pixel[2], double pt[3]) {
+  pt[0] = 0.0; pt[1] = 0.0; pt[2] = 0.0;
+  switch (model) {
+    case THB_MODEL_PINHOLE: {
+      const double dy = (pixel[1] - K[4]) / (K[0] * K[1]);
+      const double dx = (pixel[0] - K[3] - dy * K[2]) / K[0];
+      double ux = dx, uy = dy;
+      for (int i = 0; i < 100; ++i) {
+        const double px = ux, py = uy;
+        const double r_sq = ux * ux + uy * uy;
+        const double d = 1.0 + r_sq * (K[5] + K[6] * r_sq);
+        ux = dx / d; uy = dy / d;
+        if (fabs(ux - px) < 1e-10 && fabs(uy - py) < 1e-10) break;
+      }
+      pt[0] = ux; pt[1] = uy; pt[2] = 1.0;
+      return true;
+    }
+    case THB_MODEL_FISHEYE: {
+      const double dy = (pixel[1] - K[4]) / (K[0] * K[1]);
+      const double dx = (pixel[0] - K[3] - dy * K[2]) / K[0];
+      double ux = dx, uy = dy;
+      for (int i = 0; i < 100; ++i) {
+        const double px = ux, py = uy;
+        const double r = sqrt(ux * ux + uy * uy);
+        if (r < 1e-8) { ux = dx; uy = dy; break; }
+        const double theta = atan2(r, 1.0), t2 = theta * theta;
+        const double theta_d = theta * (1.0 + K[5] * t2 + K[6] * t2 * t2 + K[7] * t2 * t2 * t2 + K[8] * t2 * t2 * t2 * t2);
+        ux = r * dx / theta_d; uy = r * dy / theta_d;
+        if (fabs(ux - px) < 1e-10 && fabs(uy - py) < 1e-10) break;
+      }
+      pt[0] = ux; pt[1] = uy; pt[2] = 1.0;
+      return true;
+    }
+    case THB_MODEL_FOV: {
+      const double dx = (pixel[0] - K[2]) / K[0], dy = (pixel[1] - K[3]) / (K[0] * K[1]);
+      const double omega = K[4], r_d_sq = dx * dx + dy * dy;
+      double r_u;
+      if (omega < 1e-3) r_u = (omega * omega * r_d_sq) / 3.0 - omega * omega / 12.0 + 1.0;
+      else if (r_d_sq < 1e-3) r_u = (omega * (omega * omega * r_d_sq + 3.0)) / (6.0 * tan(omega / 2.0));
+      else { const double r_d = sqrt(r_d_sq); r_u = tan(r_d * omega) / (2.0 * r_d * tan(omega / 2.0)); }
+      pt[0] = r_u * dx; pt[1] = r_u * dy; pt[2] = 1.0;
+      return true;
+    }
+    case THB_MODEL_DIVISION_UNDISTORTION: {
+      const double dx = pixel[0] - K[2], dy = pixel[1] - K[3];
+      const double u = 1.0 / (1.0 + K[4] * (dx * dx + dy * dy));
+      pt[0] = dx * u / K[0]; pt[1] = dy * u / (K[0] * K[1]); pt[2] = 1.0;
+      return true;
+    }
+    case THB_MODEL_DOUBLE_SPHERE: {
+      const double dy = (pixel[1] - K[4]) / (K[0] * K[1]);
+      const double dx = (pixel[0] - K[3] - dy * K[2]) / K[0];
+      const double xi = K[5], alpha = K[6], r2 = dx * dx + dy * dy;
+      if (alpha > 0.5 && r2 >= 1.0 / (2.0 * alpha - 1.0)) return false;
+      const double sqrt2 = sqrt(1.0 - (2.0 * alpha - 1.0) * r2);
+      const double norm2 = alpha * sqrt2 + 1.0 - alpha;
+      const double mz = (1.0 - alpha * alpha * r2) / norm2, mz2 = mz * mz;
+      const double norm1 = mz2 + r2;
+      const double sqrt1 = sqrt(mz2 + (1.0 - xi * xi) * r2);
+      const double k = (mz * xi + sqrt1) / norm1;
+      pt[0] = k * dx; pt[1] = k * dy; pt[2] = k * mz - xi;
+      return true;
+    }
+    case THB_MODEL_EXTENDED_UNIFIED: {
+      const double dy = (pixel[1] - K[4]) / (K[0] * K[1]);
+      const double dx = (pixel[0] - K[3] - dy * K[2]) / K[0];
+      const double alpha = K[5], beta = K[6], r2 = dx * dx + dy * dy, gamma = 1.0 - alpha;
+      if (alpha > 0.5 && r2 >= 1.0 / ((alpha - gamma) * beta)) return false;
+      const double tmp1 = 1.0 - alpha * alpha * beta * r2;
+      const double tmp2 = alpha * sqrt(1.0 - (alpha - gamma) * beta * r2) + gamma;
+      const double k = tmp1 / tmp2;
+      double norm = sqrt(r2 + k * k);
+      if (norm < 1e-12) norm = 1e-12;
+      pt[0] = dx / norm; pt[1] = dy / norm; pt[2] = k / norm;
+      return true;
+    }
+    default: return false;
+  }
+}
+
 }  // namespace thb
 #endif  // THB_CAMERA_MODELS_CUH_

@@ -25,23 +25,6 @@ struct InnerLmParams {
   double min_relative_decrease = 1e-3, min_diag = 1e-6, max_diag = 1e32;
 };
 
-// Solve the SPD system A y = b (A row-major N x N, lower triangle read) by Cholesky; false if not positive definite.
-template <int N>
-__device__ __host__ inline bool spd_solve(const double* A, const double* b, double* y) {
-  double L[N * N];
-  for (int i = 0; i < N; ++i)
-    for (int j = 0; j <= i; ++j) {
-      double v = A[i * N + j];
-      for (int k = 0; k < j; ++k) v -= L[i * N + k] * L[j * N + k];
-      if (i == j) { if (!(v > 0.0)) return false; L[i * N + i] = sqrt(v); }
-      else L[i * N + j] = v / L[j * N + j];
-    }
-  double z[N];
-  for (int i = 0; i < N; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= L[i * N + k] * z[k]; z[i] = v / L[i * N + i]; }
-  for (int i = N - 1; i >= 0; --i) { double v = z[i]; for (int k = i + 1; k < N; ++k) v -= L[k * N + i] * y[k]; y[i] = v / L[i * N + i]; }
-  return true;
-}
-
 // ---- cameras ------------------------------------------------------------------------------------------------------------
 constexpr int IC_THREADS = 128;
 constexpr int IC_VALS = 29;  // 21 (J^T J lower) + 6 (J^T r) + cost + failures

@@ -26,6 +26,7 @@
 
 #include "common.cuh"
 #include "small_linalg.cuh"
+#include "ba_device.cuh"
 
 namespace thb {
 namespace {
@@ -942,12 +943,17 @@ struct RansacShared {
 // shared memory, one solver warp: ~15 % of the FP64 issue rate.) The candidate models of a batch live in a per-CTA
 // global scratch area (L2-resident) so that shared memory only holds the pair's correspondences and the control block.
 template <class Est>
-__global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacParams P, int num_pairs, const long long* __restrict__ pair_offset,
+__global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRansacParams P_in, int num_pairs, const long long* __restrict__ pair_offset,
                                                   const double* __restrict__ corr_all, const uint32_t* __restrict__ seed,
                                                   ThbRelPoseResult* __restrict__ results, uint8_t* __restrict__ mask_all,
                                                   int* __restrict__ idx_ws, Model* model_ws, double* cost_ws,
                                                   int* ninl_ws, int* __restrict__ pair_counter, unsigned long long* __restrict__ stats,
-                                                  uint8_t* __restrict__ lo_flags_all) {
+                                                  uint8_t* __restrict__ lo_flags_all, const double* __restrict__ pair_thresh,
+                                                  uint32_t* __restrict__ rng_state, int rng_mode, const uint8_t* __restrict__ pair_skip) {
+  // pair_thresh: per-pair error_thresh (EstimateTwoViewInfo scales it by the pair's focal lengths); rng_state: 625 words per
+  // pair - rng_mode 1 saves the generator after the run, 2 starts from the saved generator instead of seeding it (the
+  // reference runs CountHomographyInliers and EstimateTwoViewInfo on ONE generator); pair_skip: pairs not to run
+  ThbRansacParams P = P_in;
   constexpr int SS = Est::S, DD = Est::D;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RansacShared& S = *reinterpret_cast<RansacShared*>(smem_raw);
@@ -966,7 +972,8 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
   const int n = (int)(pair_offset[pair + 1] - off);
   ThbRelPoseResult* out = results + pair;
   uint8_t* mask = mask_all ? mask_all + off : nullptr;
-  if (n < SS) {  // RandomSampler::Initialize would CHECK-abort; reported as failure
+  if (pair_thresh) P.error_thresh = pair_thresh[pair];
+  if (n < SS || (pair_skip && pair_skip[pair])) {  // RandomSampler::Initialize would CHECK-abort; reported as failure
     if (t == 0) { memset(out, 0, sizeof(*out)); out->num_input_data_points = n; }
     if (mask) for (int i = t; i < n; i += RT) mask[i] = 0;
     continue;
@@ -974,8 +981,13 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
   const double* corr = corr_all + (size_t)off * DD;
   int* sidx = idx_ws + off;  // RandomSampler::sample_indices_ (persistent permutation)
   for (int i = t; i < n; i += RT) sidx[i] = i;
+  if (rng_state && rng_mode == 2) {
+    const uint32_t* src = rng_state + (size_t)pair * 625;
+    for (int i = t; i < 624; i += RT) S.rng.mt[i] = src[i];
+    if (t == 0) S.rng.idx = (int)src[624];
+  }
   if (t == 0) {
-    mt_seed(&S.rng, seed[pair]);
+    if (!(rng_state && rng_mode == 2)) mt_seed(&S.rng, seed[pair]);
     S.best_cost = DBL_MAX;
     S.max_iterations = P.max_iterations;
     if (P.min_inlier_ratio > 0) {
@@ -1146,6 +1158,11 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(ThbRansacPara
     for (int k = 0; k < 9; ++k) { out->essential_matrix[k] = S.best.E[k]; out->rotation[k] = S.best.R[k]; }
     for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
   }
+  if (rng_state && rng_mode == 1) {
+    uint32_t* dst = rng_state + (size_t)pair * 625;
+    for (int i = t; i < 624; i += RT) dst[i] = S.rng.mt[i];
+    if (t == 0) dst[624] = (uint32_t)S.rng.idx;
+  }
   }  // next pair
 }
 
@@ -1220,6 +1237,41 @@ int check_device() {
   return THB_OK;
 }
 
+
+// The device part of a batch: scratch from the stream's pool, one persistent launch. Everything is a device pointer; no
+// synchronisation (the caller's stream order is the only dependency), so pipelines chain it with other kernels.
+template <class Est>
+int launch_ransac(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, const long long* d_off, const double* d_corr,
+                  const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
+                  uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
+  int* d_idx = B.get<int>((size_t)total);
+  if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  // Shared memory holds the control block only. Staging the pair's correspondences there was measured 20 % slower on C4
+  // (41.7k vs 50.5k pairs/s): three staged copies take 207 KB of the SM's 256 KB L1/shared array and the five-point
+  // solver's per-thread work matrices (local memory) then miss L1; a pair's 64 KB stays L1-resident between models anyway.
+  const size_t want = ((sizeof(RansacShared) + 31) / 32) * 32;
+  THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac<Est>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const int grid = std::min(np, RANSAC_CTAS_PER_SM * sms);
+  Model* d_models = B.get<Model>((size_t)grid * BI * MAXM);
+  double* d_cost = B.get<double>((size_t)grid * BI * MAXM);
+  int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
+  int* d_counter = B.get<int>(1);
+  unsigned long long* d_stats = B.get<unsigned long long>(10);
+  uint8_t* d_lo_flags = (p.use_lo && Est::HAS_LO) ? B.get<uint8_t>((size_t)total) : nullptr;
+  if (!d_models || !d_cost || !d_ninl || !d_counter || !d_stats || (p.use_lo && Est::HAS_LO && !d_lo_flags)) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
+  k_ransac<Est><<<grid, RT, want, st>>>(p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats, d_lo_flags,
+                                        d_thresh, d_rng, rng_mode, d_skip);
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
+  return THB_OK;
+}
+
 template <class Est>
 int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask, void* cuda_stream) {
   if (!b || !p || !results) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
@@ -1267,34 +1319,109 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
   } else {
     d_off = (const long long*)b->pair_offset; d_corr = b->corr; d_seed = b->seed; d_res = results; d_mask = inlier_mask;
   }
-  int* d_idx = B.get<int>((size_t)total);
-  if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-  // Shared memory holds the control block only. Staging the pair's correspondences there was measured 20 % slower on C4
-  // (41.7k vs 50.5k pairs/s): three staged copies take 207 KB of the SM's 256 KB L1/shared array and the five-point
-  // solver's per-thread work matrices (local memory) then miss L1; a pair's 64 KB stays L1-resident between models anyway.
-  const size_t want = ((sizeof(RansacShared) + 31) / 32) * 32;
-  THB_CUDA_CHECK(cudaFuncSetAttribute(k_ransac<Est>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (sms <= 0) sms = 148;
-  const int grid = std::min(np, RANSAC_CTAS_PER_SM * sms);
-  Model* d_models = B.get<Model>((size_t)grid * BI * MAXM);
-  double* d_cost = B.get<double>((size_t)grid * BI * MAXM);
-  int* d_ninl = B.get<int>((size_t)grid * BI * MAXM);
-  int* d_counter = B.get<int>(1);
-  unsigned long long* d_stats = B.get<unsigned long long>(10);
-  uint8_t* d_lo_flags = (p->use_lo && Est::HAS_LO) ? B.get<uint8_t>((size_t)total) : nullptr;
-  if (p->use_lo && Est::HAS_LO && !d_lo_flags) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-  if (!d_models || !d_cost || !d_ninl || !d_counter || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
-  THB_CUDA_CHECK(cudaMemsetAsync(d_counter, 0, sizeof(int), st));
-  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
-  k_ransac<Est><<<grid, RT, want, st>>>(*p, np, d_off, d_corr, d_seed, d_res, d_mask, d_idx, d_models, d_cost, d_ninl, d_counter, d_stats, d_lo_flags);
-  THB_CUDA_CHECK(cudaGetLastError());
-  THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
+  rc = launch_ransac<Est>(st, B, *p, np, d_off, d_corr, d_seed, total, d_res, d_mask, nullptr, nullptr, 0, nullptr);
+  if (rc != THB_OK) return rc;
   if (host) {
     THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbRelPoseResult) * np, cudaMemcpyDeviceToHost, st));
     if (inlier_mask) THB_CUDA_CHECK(cudaMemcpyAsync(inlier_mask, d_mask, (size_t)total, cudaMemcpyDeviceToHost, st));
+  }
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return THB_OK;
+}
+
+}  // namespace
+}  // namespace thb
+#include "two_view.cuh"
+namespace thb {
+namespace {
+
+// EstimateTwoViewInfo / VerifyMatches for a batch (include/theia_b200.h). verify = false: stages normalise -> RANSAC -> info.
+int run_two_view(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbViewIntrinsics* i2, const ThbTwoViewOptions* O,
+                 ThbTwoViewInfo* info, uint8_t* out_mask, void* cuda_stream, bool verify) {
+  if (!b || !i1 || !i2 || !O || !info) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
+  if (O->ransac_type != 0) THB_FAIL(THB_E_UNSUPPORTED, "only RansacType::RANSAC is implemented");
+  if (!(O->max_sampson_error_pixels > 0) || !(O->expected_ransac_confidence > 0 && O->expected_ransac_confidence < 1) ||
+      O->max_ransac_iterations < O->min_ransac_iterations) THB_FAIL(THB_E_INVALID_ARGUMENT, "invalid two-view options");
+  if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
+  if (b->num_pairs == 0) return THB_OK;
+  if (!b->pair_offset || !b->seed) THB_FAIL(THB_E_INVALID_ARGUMENT, "null batch array");
+  int rc = check_device();
+  if (rc != THB_OK) return rc;
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int np = b->num_pairs;
+  const bool host = b->memory_space == THB_MEM_HOST;
+  std::vector<long long> h_off(np + 1);
+  if (host) std::memcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1));
+  else THB_CUDA_CHECK(cudaMemcpy(h_off.data(), b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < np; ++i)
+    if (h_off[i + 1] < h_off[i] || h_off[i + 1] - h_off[i] > 2147483647LL || h_off[0] != 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "pair_offset must start at 0 and be non-decreasing");
+  const long long total = h_off[np];
+  if (total > 0 && !b->corr) THB_FAIL(THB_E_INVALID_ARGUMENT, "null corr");
+  Bufs B;
+  B.st = st;
+  const long long* d_off; const double* d_px; const uint32_t* d_seed; const ThbViewIntrinsics *d_i1, *d_i2; ThbTwoViewInfo* d_info; uint8_t* d_out = nullptr;
+  if (host) {
+    long long* o = B.get<long long>(np + 1); double* c = B.get<double>((size_t)total * 4); uint32_t* s = B.get<uint32_t>(np);
+    ThbViewIntrinsics* a1 = B.get<ThbViewIntrinsics>(np); ThbViewIntrinsics* a2 = B.get<ThbViewIntrinsics>(np);
+    d_info = B.get<ThbTwoViewInfo>(np);
+    d_out = B.get<uint8_t>((size_t)total);
+    if (!o || !c || !s || !a1 || !a2 || !d_info || !d_out) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+    THB_CUDA_CHECK(cudaMemcpyAsync(o, b->pair_offset, sizeof(long long) * (np + 1), cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(c, b->corr, sizeof(double) * 4 * total, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(s, b->seed, sizeof(uint32_t) * np, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(a1, i1, sizeof(ThbViewIntrinsics) * np, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(a2, i2, sizeof(ThbViewIntrinsics) * np, cudaMemcpyHostToDevice, st));
+    d_off = o; d_px = c; d_seed = s; d_i1 = a1; d_i2 = a2;
+  } else {
+    d_off = (const long long*)b->pair_offset; d_px = b->corr; d_seed = b->seed; d_i1 = i1; d_i2 = i2; d_info = info;
+    d_out = out_mask ? out_mask : B.get<uint8_t>((size_t)total);
+    if (!d_out) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  }
+  double* d_thresh = B.get<double>(np); uint8_t* d_skip = B.get<uint8_t>(np); int* d_uncal = B.get<int>(1);
+  double* d_norm = B.get<double>((size_t)total * 4);
+  ThbRelPoseResult* d_res = B.get<ThbRelPoseResult>(np);
+  uint8_t* d_inl = B.get<uint8_t>((size_t)total);
+  if (!d_thresh || !d_skip || !d_uncal || !d_norm || !d_res || !d_inl) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemsetAsync(d_uncal, 0, sizeof(int), st));
+  k_tv_prepare<<<(np + 127) / 128, 128, 0, st>>>(np, d_off, d_i1, d_i2, *O, verify ? 1 : 0, d_thresh, d_skip, d_uncal);
+  int h_uncal = 0;
+  THB_CUDA_CHECK(cudaMemcpyAsync(&h_uncal, d_uncal, sizeof(int), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_uncal) THB_FAIL(THB_E_UNSUPPORTED, "a pair has a view without a focal-length prior (or a camera model off the hot path): the uncalibrated branch of EstimateTwoViewInfo is not implemented");
+  ThbRansacParams rp;
+  thb_ransac_default_params(&rp);
+  rp.failure_probability = 1.0 - O->expected_ransac_confidence; rp.min_iterations = O->min_ransac_iterations; rp.max_iterations = O->max_ransac_iterations;
+  rp.use_mle = O->use_mle; rp.error_thresh = 1.0;
+  uint32_t* d_rng = nullptr;
+  ThbRelPoseResult* d_hom = nullptr;
+  if (verify) {  // CountHomographyInliers (:331-366): pixel matches, threshold from the cameras before SetupCameras (image size 0)
+    d_rng = B.get<uint32_t>((size_t)np * 625);
+    d_hom = B.get<ThbRelPoseResult>(np);
+    if (!d_rng || !d_hom) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+    ThbRansacParams hp = rp;
+    hp.error_thresh = O->max_sampson_error_pixels * O->max_sampson_error_pixels;
+    rc = launch_ransac<HomographyEst>(st, B, hp, np, d_off, d_px, d_seed, total, d_hom, nullptr, nullptr, d_rng, 1, d_skip);
+    if (rc != THB_OK) return rc;
+  }
+  k_tv_normalize<<<np, 128, 0, st>>>(d_off, d_px, d_i1, d_i2, d_norm);
+  rp.use_lo = O->use_lo; rp.lo_start_iterations = O->lo_start_iterations;
+  rc = launch_ransac<RelPoseEst>(st, B, rp, np, d_off, d_norm, d_seed, total, d_res, verify ? d_inl : d_out, d_thresh, d_rng, verify ? 2 : 0, d_skip);
+  if (rc != THB_OK) return rc;
+  if (!verify) {
+    k_tv_info<<<(np + 127) / 128, 128, 0, st>>>(np, d_res, d_i1, d_i2, d_skip, d_info);
+  } else {
+    double* d_p0 = B.get<double>((size_t)total * 4); double* d_p1 = B.get<double>((size_t)total * 4); double* d_ps = B.get<double>((size_t)total * 4);
+    uint8_t* d_tri = B.get<uint8_t>((size_t)total); uint8_t* d_zero = B.get<uint8_t>((size_t)total + 16); int* d_two = B.get<int>(2);
+    if (!d_p0 || !d_p1 || !d_ps || !d_tri || !d_zero || !d_two) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+    THB_CUDA_CHECK(cudaMemsetAsync(d_zero, 0, (size_t)total + 16, st));
+    const int two[2] = {0, 1};
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_two, two, sizeof(two), cudaMemcpyHostToDevice, st));
+    k_tv_verify<<<np, TV_THREADS, 0, st>>>(d_off, d_px, d_i1, d_i2, *O, d_res, d_inl, d_hom, d_skip, d_p0, d_p1, d_ps, d_tri, d_zero, d_two, d_info, d_out);
+  }
+  THB_CUDA_CHECK(cudaGetLastError());
+  if (host) {
+    THB_CUDA_CHECK(cudaMemcpyAsync(info, d_info, sizeof(ThbTwoViewInfo) * np, cudaMemcpyDeviceToHost, st));
+    if (out_mask) THB_CUDA_CHECK(cudaMemcpyAsync(out_mask, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
   }
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
   return THB_OK;
@@ -1370,6 +1497,24 @@ int thb_ransac_abspose_batch(const ThbPairBatch* b, const ThbRansacParams* p, Th
 int thb_ransac_homography_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* results, uint8_t* inlier_mask,
                                 void* cuda_stream) {
   return run_batch<HomographyEst>(b, p, results, inlier_mask, cuda_stream);
+}
+
+void thb_two_view_default_options(ThbTwoViewOptions* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  // EstimateTwoViewInfoOptions (estimate_twoview_info.h:51-80), TwoViewMatchGeometricVerification::Options (.h:53-92)
+  o->max_sampson_error_pixels = 6.0; o->expected_ransac_confidence = 0.9999; o->min_ransac_iterations = 10; o->max_ransac_iterations = 1000;
+  o->use_mle = 1; o->use_lo = 0; o->lo_start_iterations = 10; o->ransac_type = 0;
+  o->min_num_inlier_matches = 30; o->bundle_adjustment = 1; o->triangulation_max_reprojection_error = 15.0;
+  o->min_triangulation_angle_degrees = 4.0; o->final_max_reprojection_error = 5.0;
+}
+int thb_estimate_two_view_info_batch(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbViewIntrinsics* i2, const ThbTwoViewOptions* o,
+                                     ThbTwoViewInfo* info, uint8_t* inlier_mask, void* cuda_stream) {
+  return run_two_view(b, i1, i2, o, info, inlier_mask, cuda_stream, false);
+}
+int thb_verify_two_view_matches_batch(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbViewIntrinsics* i2, const ThbTwoViewOptions* o,
+                                      ThbTwoViewInfo* info, uint8_t* verified_mask, void* cuda_stream) {
+  return run_two_view(b, i1, i2, o, info, verified_mask, cuda_stream, true);
 }
 
 int thb_ransac_last_stats(ThbRansacStats* stats) {

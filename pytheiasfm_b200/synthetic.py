@@ -303,3 +303,36 @@ def make_homography_batch(num, n=500, inlier_ratio=0.6, noise=1e-3, seed=0, base
         perm = rng.permutation(n)
         data.append(np.c_[x1, x2][perm]); gts.append((H, flags[perm]))
     return capi.HostPairBatch(data, base_seed + np.arange(num)), gts
+
+
+def make_two_view_batch(num_pairs, n=600, models=(capi.MODEL_PINHOLE,), inlier_ratio=0.7, noise_px=0.5, seed=0, base_seed=5000, image=1000,
+                        planar_fraction=0.0):
+    """Image pairs with PIXEL correspondences for EstimateTwoViewInfo / VerifyMatches: camera 1 at the origin, camera 2 a few
+    degrees and a unit baseline away, points in front of both, each view projected through its own camera model
+    (models[p % len] for view 1, models[(p + 1) % len] for view 2), Gaussian pixel noise, uniform outliers; a fraction of the
+    inliers may lie on a plane (homography inliers). Returns (HostPairBatch, intr1, intr2, ground truth list)."""
+    rng = np.random.default_rng(seed)
+    corrs, gts = [], []
+    intr1 = np.zeros(num_pairs, capi.VIEW_INTRINSICS_DTYPE); intr2 = np.zeros(num_pairs, capi.VIEW_INTRINSICS_DTYPE)
+    for p in range(num_pairs):
+        m1, m2 = models[p % len(models)], models[(p + 1) % len(models)]
+        K1 = default_intrinsics(m1, 0.9 * image if m1 not in (capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED) else 0.4 * image, image / 2, image / 2)
+        K2 = default_intrinsics(m2, 0.95 * image if m2 not in (capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED) else 0.42 * image, image / 2, image / 2)
+        for I, m, K in ((intr1, m1, K1), (intr2, m2, K2)):
+            I[p]["model"] = m; I[p]["image_width"] = image; I[p]["image_height"] = image; I[p]["focal_length_is_set"] = 1; I[p]["params"] = K
+        R = random_rotation(rng, 12.0)
+        c = rng.normal(size=3); c[2] *= 0.3; c /= np.linalg.norm(c)
+        ni = int(round(inlier_ratio * n))
+        X = np.stack([rng.uniform(-2.5, 2.5, ni), rng.uniform(-2.5, 2.5, ni), rng.uniform(5, 11, ni)], -1)
+        npl = int(planar_fraction * ni)
+        if npl:
+            X[:npl, 2] = 8.0 + 0.1 * X[:npl, 0]
+        x1 = project(m1, K1, X)
+        x2 = project(m2, K2, (X - c) @ R.T)
+        x1 = x1 + rng.normal(0, noise_px, x1.shape); x2 = x2 + rng.normal(0, noise_px, x2.shape)
+        out = rng.uniform(0.1 * image, 0.9 * image, (n - ni, 4))
+        corr = np.concatenate([np.concatenate([x1, x2], 1), out], 0)
+        flags = np.concatenate([np.ones(ni, bool), np.zeros(n - ni, bool)])
+        perm = rng.permutation(n)
+        corrs.append(corr[perm]); gts.append((R, c, flags[perm]))
+    return capi.HostPairBatch(corrs, base_seed + np.arange(num_pairs)), intr1, intr2, gts
