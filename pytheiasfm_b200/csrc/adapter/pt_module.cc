@@ -496,6 +496,48 @@ struct EstimateTwoViewInfoOptions {                                             
   int64_t seed = -1;  // ADDITIVE, like RansacParameters::seed: the reference's `rng` member is not bound (sfm.cc:864-885)
 };
 
+// <Model>::SetFromCameraIntrinsicsPriors on a default-constructed model, all six models (e.g. pinhole_camera_model.cc:74-107,
+// double_sphere_camera_model.cc:74-106: prior.radial_distortion = [alpha, xi] but storage [.., XI = 5, ALPHA = 6];
+// fisheye: focal guess 0.4 max(w, h) instead of 1.2; FOV / division reset their distortion when the prior has none)
+int ModelFromString(const std::string& s) {
+  if (s == "PINHOLE") return THB_MODEL_PINHOLE;
+  if (s == "FISHEYE") return THB_MODEL_FISHEYE;
+  if (s == "FOV") return THB_MODEL_FOV;
+  if (s == "DIVISION_UNDISTORTION") return THB_MODEL_DIVISION_UNDISTORTION;
+  if (s == "DOUBLE_SPHERE") return THB_MODEL_DOUBLE_SPHERE;
+  if (s == "EXTENDED_UNIFIED") return THB_MODEL_EXTENDED_UNIFIED;
+  throw std::invalid_argument("camera_intrinsics_model_type '" + s + "' is not on the B200 hot path");
+}
+void IntrinsicsFromPrior(const CameraIntrinsicsPrior& p, Intrinsics* in) {
+  const int m = ModelFromString(p.camera_intrinsics_model_type);
+  if (in->model != m) in->SetType(m);
+  double* K = in->params;
+  const bool sized = p.image_width != 0 && p.image_height != 0;
+  if (p.focal_length.is_set) K[0] = p.focal_length.value[0];
+  else if (sized) K[0] = (m == THB_MODEL_FISHEYE ? 0.4 : 1.2) * (double)std::max(p.image_width, p.image_height);
+  const int cx = in->cx_index();
+  if (p.principal_point.is_set) { K[cx] = p.principal_point.value[0]; K[cx + 1] = p.principal_point.value[1]; }
+  else if (sized) { K[cx] = p.image_width / 2.0; K[cx + 1] = p.image_height / 2.0; }
+  if (p.aspect_ratio.is_set) K[1] = p.aspect_ratio.value[0];
+  if (in->has_skew() && p.skew.is_set) K[2] = p.skew.value[0];
+  const double* rd = p.radial_distortion.value;
+  switch (m) {
+    case THB_MODEL_PINHOLE: if (p.radial_distortion.is_set) { K[5] = rd[0]; K[6] = rd[1]; } break;
+    case THB_MODEL_FISHEYE: if (p.radial_distortion.is_set) for (int k = 0; k < 4; ++k) K[5 + k] = rd[k]; break;
+    case THB_MODEL_FOV: K[4] = p.radial_distortion.is_set ? rd[0] : 0.75; break;
+    case THB_MODEL_DIVISION_UNDISTORTION: K[4] = p.radial_distortion.is_set ? rd[0] : 0.0; break;
+    case THB_MODEL_DOUBLE_SPHERE: if (p.radial_distortion.is_set) { K[6] = rd[0]; K[5] = rd[1]; } break;
+    case THB_MODEL_EXTENDED_UNIFIED: if (p.radial_distortion.is_set) { K[5] = rd[0]; K[6] = rd[1]; } break;
+  }
+}
+ThbViewIntrinsics ViewIntrinsicsFromPrior(const CameraIntrinsicsPrior& p) {
+  Intrinsics in;
+  IntrinsicsFromPrior(p, &in);
+  ThbViewIntrinsics v;
+  v.model = in.model; v.image_width = p.image_width; v.image_height = p.image_height; v.focal_length_is_set = p.focal_length.is_set ? 1 : 0;
+  std::copy(in.params, in.params + THB_INTR_STRIDE, v.params);
+  return v;
+}
 // PinholeCameraModel::SetFromCameraIntrinsicsPriors (pinhole_camera_model.cc:74-107) on a default-constructed model
 void PinholeFromPrior(const CameraIntrinsicsPrior& p, double K[7]) {
   const double def[7] = {1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // f, aspect, skew, cx, cy, k1, k2
@@ -522,6 +564,70 @@ void PinholePixelToNormalized(const double K[7], const double px[2], double out[
     if (std::fabs(ux - pxv) < 1e-10 && std::fabs(uy - pyv) < 1e-10) break;
   }
   out[0] = ux / 1.0; out[1] = uy / 1.0;
+}
+struct VerificationOptions {                                                        // two_view_match_geometric_verification.h:53-92
+  EstimateTwoViewInfoOptions estimate_twoview_info_options;
+  int min_num_inlier_matches = 30;
+  bool guided_matching = false, bundle_adjustment = true;
+  double triangulation_max_reprojection_error = 15.0, min_triangulation_angle_degrees = 4.0, final_max_reprojection_error = 5.0;
+};
+// One call for a whole list of pairs: thb_estimate_two_view_info_batch / thb_verify_two_view_matches_batch. Returns, per pair,
+// what sfm_wrapper.cc:12-26 returns for one: (success, TwoViewInfo, inlier / verified-match indices).
+std::vector<py::tuple> RunTwoViewBatch(const VerificationOptions& vo, const std::vector<CameraIntrinsicsPrior>& p1,
+                                       const std::vector<CameraIntrinsicsPrior>& p2, const std::vector<std::vector<FeatureCorrespondence>>& corr,
+                                       const std::vector<uint32_t>& seeds, bool verify) {
+  const EstimateTwoViewInfoOptions& o = vo.estimate_twoview_info_options;
+  const size_t np = corr.size();
+  if (p1.size() != np || p2.size() != np || (!seeds.empty() && seeds.size() != np)) throw std::invalid_argument("one prior pair (and seed) per list of correspondences");
+  if (vo.guided_matching) throw std::runtime_error("guided_matching needs descriptors: not part of the B200 hot path");
+  std::vector<ThbViewIntrinsics> a1(np), a2(np);
+  std::vector<int64_t> off(np + 1, 0);
+  std::vector<uint32_t> sd(np);
+  for (size_t i = 0; i < np; ++i) {
+    if (!(p1[i].focal_length.is_set && p2[i].focal_length.is_set))
+      throw std::runtime_error("EstimateTwoViewInfo: the uncalibrated branch (EstimateUncalibratedRelativePose, 8-point) is not on the B200 hot path");
+    a1[i] = ViewIntrinsicsFromPrior(p1[i]); a2[i] = ViewIntrinsicsFromPrior(p2[i]);
+    off[i + 1] = off[i] + (int64_t)corr[i].size();
+    sd[i] = seeds.empty() ? (o.seed >= 0 ? (uint32_t)(o.seed + (int64_t)i) : std::random_device{}()) : seeds[i];
+  }
+  std::vector<double> px((size_t)off[np] * 4);
+  for (size_t i = 0; i < np; ++i)
+    for (size_t k = 0; k < corr[i].size(); ++k) {
+      double* d = &px[4 * ((size_t)off[i] + k)];
+      d[0] = corr[i][k].feature1.point[0]; d[1] = corr[i][k].feature1.point[1]; d[2] = corr[i][k].feature2.point[0]; d[3] = corr[i][k].feature2.point[1];
+    }
+  ThbTwoViewOptions t;
+  thb_two_view_default_options(&t);
+  t.max_sampson_error_pixels = o.max_sampson_error_pixels; t.expected_ransac_confidence = o.expected_ransac_confidence;
+  t.min_ransac_iterations = o.min_ransac_iterations; t.max_ransac_iterations = o.max_ransac_iterations; t.use_mle = o.use_mle; t.use_lo = o.use_lo;
+  t.lo_start_iterations = o.lo_start_iterations; t.ransac_type = o.ransac_type;
+  t.min_num_inlier_matches = vo.min_num_inlier_matches; t.bundle_adjustment = vo.bundle_adjustment;
+  t.triangulation_max_reprojection_error = vo.triangulation_max_reprojection_error;
+  t.min_triangulation_angle_degrees = vo.min_triangulation_angle_degrees; t.final_max_reprojection_error = vo.final_max_reprojection_error;
+  ThbPairBatch b = {(int32_t)np, THB_MEM_HOST, off.data(), px.data(), sd.data()};
+  std::vector<ThbTwoViewInfo> info(np);
+  std::vector<uint8_t> mask((size_t)off[np]);
+  int rc;
+  {
+    py::gil_scoped_release nogil;
+    rc = verify ? thb_verify_two_view_matches_batch(&b, a1.data(), a2.data(), &t, info.data(), mask.data(), nullptr)
+                : thb_estimate_two_view_info_batch(&b, a1.data(), a2.data(), &t, info.data(), mask.data(), nullptr);
+  }
+  Check(rc);
+  std::vector<py::tuple> out;
+  for (size_t i = 0; i < np; ++i) {
+    TwoViewInfo ti;
+    std::vector<int> idx;
+    if (info[i].success || info[i].num_verified_matches > 0) {
+      ti.focal_length_1 = info[i].focal_length_1; ti.focal_length_2 = info[i].focal_length_2;
+      std::copy_n(info[i].position_2, 3, ti.position_2); std::copy_n(info[i].rotation_2, 3, ti.rotation_2);
+      ti.num_verified_matches = info[i].num_verified_matches; ti.num_homography_inliers = info[i].num_homography_inliers;
+      ti.visibility_score = info[i].visibility_score;
+      for (int64_t k = off[i]; k < off[i + 1]; ++k) if (mask[(size_t)k]) idx.push_back((int)(k - off[i]));
+    }
+    out.push_back(py::make_tuple(info[i].success != 0, ti, idx));
+  }
+  return out;
 }
 // ---- TrackEstimator (sfm/estimate_track.{h,cc}) over thb_estimate_tracks_batch: every unestimated track in ONE launch ------
 struct TrackEstimatorOptions {                                                      // estimate_track.h:59-84
@@ -579,7 +685,6 @@ struct TrackEstimator {
           f.view_index[v] = ci; f.view_ids.push_back(v);
           f.cam_ext.insert(f.cam_ext.end(), view.camera.ext, view.camera.ext + 6);
           Intrinsics* in = view.camera.intr.get();
-          if (in->model != THB_MODEL_PINHOLE) throw std::runtime_error("TrackEstimator: PixelToUnitDepthRay is implemented for PINHOLE cameras only");
           if (!f.group_index.count(in)) {
             f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
             f.intr_model.push_back(in->model);
@@ -592,10 +697,9 @@ struct TrackEstimator {
         f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
         f.obs_si.push_back(1.0 / std::sqrt(feat.cov[0])); f.obs_si.push_back(1.0 / std::sqrt(feat.cov[3]));
         // Camera::PixelToUnitDepthRay(feature).normalized() (camera.cc:218-226)
-        double n[2], R[9];
-        PinholePixelToNormalized(view.camera.intr->params, feat.point, n);
+        double u[3], R[9];
+        thb::pixel_to_camera(view.camera.intr->model, view.camera.intr->params, feat.point, u);  // PixelToNormalizedCoordinates, any model
         AngleAxisToRotation(view.camera.ext + 3, R);
-        const double u[3] = {n[0], n[1], 1.0};
         double d[3];
         for (int k = 0; k < 3; ++k) d[k] = R[0 * 3 + k] * u[0] + R[1 * 3 + k] * u[1] + R[2 * 3 + k] * u[2];   // R^T u
         const double nd = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
@@ -698,7 +802,20 @@ PYBIND11_MODULE(_pt, m) {
       .def("SetImageSize", &Camera::SetImageSize).def("ImageWidth", [](const Camera& c) { return c.width; }).def("ImageHeight", [](const Camera& c) { return c.height; })
       .def("SetCameraIntrinsicsModelType", &Camera::SetCameraIntrinsicsModelType).def("GetCameraIntrinsicsModelType", &Camera::GetCameraIntrinsicsModelType)
       .def("Parameters", &Camera::Parameters).def("SetParameters", &Camera::SetParameters)
-      .def("ProjectPoint", &Camera::ProjectPoint);
+      .def("ProjectPoint", &Camera::ProjectPoint)
+      .def("SetFromCameraIntrinsicsPriors", [](Camera& c, const CameraIntrinsicsPrior& p) {  // camera.cc:126-136
+        IntrinsicsFromPrior(p, c.intr.get());
+        c.width = p.image_width; c.height = p.image_height; })
+      .def("PixelToNormalizedCoordinates", [](const Camera& c, const Vec& px) {
+        double p[2], out[3]; CopyVec(px, p, 2, "pixel");
+        thb::pixel_to_camera(c.intr->model, c.intr->params, p, out);
+        return MakeVec(out, 3); })
+      .def("PixelToUnitDepthRay", [](const Camera& c, const Vec& px) {  // camera.cc:218-226
+        double p[2], u[3], R[9], d[3]; CopyVec(px, p, 2, "pixel");
+        thb::pixel_to_camera(c.intr->model, c.intr->params, p, u);
+        AngleAxisToRotation(c.ext + 3, R);
+        for (int k = 0; k < 3; ++k) d[k] = R[0 * 3 + k] * u[0] + R[1 * 3 + k] * u[1] + R[2 * 3 + k] * u[2];
+        return MakeVec(d, 3); });
 
   py::class_<Track>(sfm, "Track")
       .def("SetPoint", &Track::SetPoint).def("Point", &Track::Point)
@@ -882,37 +999,35 @@ PYBIND11_MODULE(_pt, m) {
       .def_readwrite("seed", &EstimateTwoViewInfoOptions::seed);
   // sfm_wrapper.cc:12-26: tuple(bool, TwoViewInfo, inlier indices). Calibrated branch (estimate_twoview_info.cc:133-191):
   // normalise by the intrinsics, resolution-scaled Sampson threshold, EstimateRelativePose on the device, fill TwoViewInfo.
+  py::class_<VerificationOptions>(sfm, "TwoViewMatchGeometricVerificationOptions")  // two_view_match_geometric_verification.h:53-92
+      .def(py::init<>())
+      .def_readwrite("estimate_twoview_info_options", &VerificationOptions::estimate_twoview_info_options)
+      .def_readwrite("min_num_inlier_matches", &VerificationOptions::min_num_inlier_matches)
+      .def_readwrite("guided_matching", &VerificationOptions::guided_matching)
+      .def_readwrite("bundle_adjustment", &VerificationOptions::bundle_adjustment)
+      .def_readwrite("triangulation_max_reprojection_error", &VerificationOptions::triangulation_max_reprojection_error)
+      .def_readwrite("min_triangulation_angle_degrees", &VerificationOptions::min_triangulation_angle_degrees)
+      .def_readwrite("final_max_reprojection_error", &VerificationOptions::final_max_reprojection_error);
   sfm.def("EstimateTwoViewInfo", [](const EstimateTwoViewInfoOptions& o, const CameraIntrinsicsPrior& i1, const CameraIntrinsicsPrior& i2,
                                     const std::vector<FeatureCorrespondence>& c) -> py::tuple {
-    if (!(i1.focal_length.is_set && i2.focal_length.is_set))
-      throw std::runtime_error("EstimateTwoViewInfo: the uncalibrated branch (EstimateUncalibratedRelativePose, 8-point) is not on the B200 hot path");
-    if (i1.camera_intrinsics_model_type != "PINHOLE" || i2.camera_intrinsics_model_type != "PINHOLE")
-      throw std::runtime_error("EstimateTwoViewInfo: only PINHOLE priors are implemented for the feature normalisation");
-    double K1[7], K2[7];
-    PinholeFromPrior(i1, K1); PinholeFromPrior(i2, K2);
-    std::vector<double> d(c.size() * 4);
-    for (size_t k = 0; k < c.size(); ++k) {
-      PinholePixelToNormalized(K1, c[k].feature1.point, &d[4 * k]);
-      PinholePixelToNormalized(K2, c[k].feature2.point, &d[4 * k + 2]);
-    }
-    RansacParameters q;
-    q.failure_probability = 1.0 - o.expected_ransac_confidence;
-    q.min_iterations = o.min_ransac_iterations; q.max_iterations = o.max_ransac_iterations;
-    q.use_lo = o.use_lo; q.lo_start_iterations = o.lo_start_iterations; q.use_mle = o.use_mle; q.seed = o.seed;
-    const double t1 = ComputeResolutionScaledThreshold(o.max_sampson_error_pixels, i1.image_width, i1.image_height);
-    const double t2 = ComputeResolutionScaledThreshold(o.max_sampson_error_pixels, i2.image_width, i2.image_height);
-    q.error_thresh = t1 * t2 / (i1.focal_length.value[0] * i2.focal_length.value[0]);
-    ThbRelPoseResult res; RansacSummary sum; TwoViewInfo info;
-    if (!RunOne(thb_ransac_relpose_batch, q, o.ransac_type, d, 4, &res, &sum)) return py::make_tuple(false, info, std::vector<int>());
-    RotationToAngleAxis(res.rotation, info.rotation_2);
-    std::copy_n(res.position, 3, info.position_2);
-    info.focal_length_1 = i1.focal_length.value[0]; info.focal_length_2 = i2.focal_length.value[0];
-    info.num_verified_matches = (int)sum.inliers.size();
-    // The reference scores the visibility pyramid over *inlier_indices BEFORE assigning it (estimate_twoview_info.cc:186-189),
-    // i.e. over an empty list: the score is 0 whatever the inliers are. Reproduced, not fixed.
-    info.visibility_score = 0;
-    return py::make_tuple(true, info, sum.inliers);
+    std::vector<std::vector<FeatureCorrespondence>> one(1, c);
+    VerificationOptions vo; vo.estimate_twoview_info_options = o;
+    return py::tuple(RunTwoViewBatch(vo, {i1}, {i2}, one, {}, false)[0]);
   });
+  // ADDITIVE: the pair loop of the pipelines (pytests/sfm_pipeline.py:232-238) as ONE call - all pairs of a view graph
+  sfm.def("EstimateTwoViewInfoBatch", [](const EstimateTwoViewInfoOptions& o, const std::vector<CameraIntrinsicsPrior>& i1,
+                                         const std::vector<CameraIntrinsicsPrior>& i2, const std::vector<std::vector<FeatureCorrespondence>>& c,
+                                         const std::vector<uint32_t>& seeds) {
+    VerificationOptions vo; vo.estimate_twoview_info_options = o;
+    return RunTwoViewBatch(vo, i1, i2, c, seeds, false);
+  }, py::arg("options"), py::arg("intrinsics1"), py::arg("intrinsics2"), py::arg("correspondences"), py::arg("seeds") = std::vector<uint32_t>());
+  // TwoViewMatchGeometricVerification::VerifyMatches (C++ only upstream, two_view_match_geometric_verification.cc:114-183) for a
+  // batch of pairs: tuple(success, TwoViewInfo, indices of the verified matches) per pair
+  sfm.def("VerifyTwoViewMatchesBatch", [](const VerificationOptions& vo, const std::vector<CameraIntrinsicsPrior>& i1,
+                                          const std::vector<CameraIntrinsicsPrior>& i2, const std::vector<std::vector<FeatureCorrespondence>>& c,
+                                          const std::vector<uint32_t>& seeds) {
+    return RunTwoViewBatch(vo, i1, i2, c, seeds, true);
+  }, py::arg("options"), py::arg("intrinsics1"), py::arg("intrinsics2"), py::arg("correspondences"), py::arg("seeds") = std::vector<uint32_t>());
 
   // sfm.cc:1095-1135
   py::class_<TrackEstimatorOptions>(sfm, "TrackEstimatorOptions")

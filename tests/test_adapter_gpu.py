@@ -265,6 +265,68 @@ def test_EstimateTwoViewInfo_against_the_oracle():
         pt.sfm.EstimateTwoViewInfo(opts, pr1, pr2, corrs)
 
 
+def _prior_from_view_intrinsics(v):
+    """CameraIntrinsicsPrior that reproduces a synthetic.make_two_view_batch view (prior order of the distortion slots)."""
+    from pytheiasfm_b200 import capi
+    names = {capi.MODEL_PINHOLE: "PINHOLE", capi.MODEL_FISHEYE: "FISHEYE", capi.MODEL_FOV: "FOV", capi.MODEL_DIVISION_UNDISTORTION: "DIVISION_UNDISTORTION",
+             capi.MODEL_DOUBLE_SPHERE: "DOUBLE_SPHERE", capi.MODEL_EXTENDED_UNIFIED: "EXTENDED_UNIFIED"}
+    m, K = int(v["model"]), v["params"]
+    pr = pt.sfm.CameraIntrinsicsPrior()
+    pr.camera_intrinsics_model_type = names[m]
+    pr.image_width, pr.image_height = int(v["image_width"]), int(v["image_height"])
+    pr.focal_length.value = [K[0]]; pr.aspect_ratio.value = [K[1]]
+    if m in (capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION):
+        pr.principal_point.value = [K[2], K[3]]; pr.radial_distortion.value = [K[4], 0, 0, 0]
+    else:
+        pr.skew.value = [K[2]]; pr.principal_point.value = [K[3], K[4]]
+        rd = [K[5], K[6], K[7], K[8]]
+        if m == capi.MODEL_DOUBLE_SPHERE:
+            rd = [K[6], K[5], 0, 0]          # prior order [alpha, xi], storage [xi, alpha]
+        pr.radial_distortion.value = rd
+    return pr
+
+
+def test_batched_two_view_entries_all_models():
+    """EstimateTwoViewInfoBatch / VerifyTwoViewMatchesBatch (one call for a list of pairs) against the C-ABI on the same input,
+    for views of all six camera models; Camera.SetFromCameraIntrinsicsPriors + PixelToUnitDepthRay round trip."""
+    import ctypes as C
+    from pytheiasfm_b200 import capi, synthetic
+    models = (capi.MODEL_PINHOLE, capi.MODEL_FISHEYE, capi.MODEL_FOV, capi.MODEL_DIVISION_UNDISTORTION, capi.MODEL_DOUBLE_SPHERE, capi.MODEL_EXTENDED_UNIFIED)
+    batch, i1, i2, gts = synthetic.make_two_view_batch(6, n=400, models=models, seed=21)
+    priors1 = [_prior_from_view_intrinsics(v) for v in i1]; priors2 = [_prior_from_view_intrinsics(v) for v in i2]
+    corrs = [[pt.matching.FeatureCorrespondence(pt.sfm.Feature(r[:2]), pt.sfm.Feature(r[2:])) for r in batch.corr[batch.pair_offset[i]:batch.pair_offset[i + 1]]]
+             for i in range(6)]
+    lib = capi.load_library()
+    o = capi.ThbTwoViewOptions(); lib.thb_two_view_default_options(C.byref(o))
+    for verify in (False, True):
+        info = np.zeros(6, capi.TWO_VIEW_INFO_DTYPE); mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
+        b = batch.struct()
+        fn = lib.thb_verify_two_view_matches_batch if verify else lib.thb_estimate_two_view_info_batch
+        capi.check(fn(C.byref(b), i1.ctypes.data_as(C.c_void_p), i2.ctypes.data_as(C.c_void_p), C.byref(o), info.ctypes.data_as(C.c_void_p),
+                      mask.ctypes.data_as(C.c_void_p), None))
+        if verify:
+            out = pt.sfm.VerifyTwoViewMatchesBatch(pt.sfm.TwoViewMatchGeometricVerificationOptions(), priors1, priors2, corrs, list(batch.seed))
+        else:
+            out = pt.sfm.EstimateTwoViewInfoBatch(pt.sfm.EstimateTwoViewInfoOptions(), priors1, priors2, corrs, list(batch.seed))
+        assert len(out) == 6
+        for i, (ok, tvi, idx) in enumerate(out):
+            assert ok == bool(info["success"][i])
+            assert idx == list(np.nonzero(mask[batch.pair_offset[i]:batch.pair_offset[i + 1]])[0])
+            np.testing.assert_allclose(tvi.rotation_2, info["rotation_2"][i], rtol=0, atol=1e-12)
+            assert tvi.num_verified_matches == info["num_verified_matches"][i] and tvi.num_homography_inliers == info["num_homography_inliers"][i]
+    # one pair through the reference-named entry
+    opts = pt.sfm.EstimateTwoViewInfoOptions(); opts.seed = int(batch.seed[4])
+    ok, tvi, idx = pt.sfm.EstimateTwoViewInfo(opts, priors1[4], priors2[4], corrs[4])
+    assert ok and tvi.focal_length_1 == i1["params"][4, 0]
+    cam = pt.sfm.Camera()
+    cam.SetFromCameraIntrinsicsPriors(priors1[4])
+    assert cam.GetCameraIntrinsicsModelType() == int(i1["model"][4])
+    np.testing.assert_allclose(cam.Parameters(), i1["params"][4][:len(cam.Parameters())], rtol=0, atol=0)
+    ray = cam.PixelToUnitDepthRay(np.array([612.0, 377.0]))
+    depth, pix = cam.ProjectPoint(np.append(3.0 * ray, 1.0))
+    np.testing.assert_allclose(pix, [612.0, 377.0], atol=1e-6)      # camera-model round trip (the reference's ReprojectionTest)
+
+
 def test_TriangulateMidpoint():
     """pytests-style call of pt.sfm.TriangulateMidpoint (sfm.cc:854, triangulation_test.cc:312-335): (success, point)."""
     X = np.array([5.0, 20.0, 23.0])
