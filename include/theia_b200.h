@@ -486,6 +486,21 @@ typedef struct ThbTrackEstimatorOptions {
 int thb_estimate_tracks_batch(const ThbBaProblem* problem, const double* ray_directions, const ThbTrackEstimatorOptions* options,
                               const ThbBaOptions* ba_options, int32_t* status, ThbTrackBaResult* ba_results, void* cuda_stream);
 
+#define THB_OUTLIER_KEPT 0
+#define THB_OUTLIER_BAD_REPROJECTION 1   /* a view sees the point behind it, or the mean squared reprojection error is too large */
+#define THB_OUTLIER_BAD_ANGLE 2          /* no two viewing rays are at least min_triangulation_angle_degrees apart               */
+#define THB_OUTLIER_SKIPPED (-1)         /* pt_const[p] != 0: the caller's "not estimated" tracks are not looked at              */
+
+/*
+ * theia::SetOutlierTracksToUnestimated (sfm/set_outlier_tracks_to_unestimated.cc:62-137), the filter every pipeline runs
+ * after bundle adjustment (global_reconstruction_estimator.cc:266-270), for all tracks in one launch. The problem holds
+ * the observations of the ESTIMATED views only (the reference skips the others, :86-88); points with pt_const != 0 are
+ * skipped (tracks that are not estimated, :76-78). status [num_points] receives THB_OUTLIER_*; the caller sets every track
+ * with status > 0 to unestimated. *num_removed = the function's return value. Any memory space.
+ */
+int thb_set_outlier_tracks_batch(const ThbBaProblem* problem, double max_inlier_reprojection_error,
+                                 double min_triangulation_angle_degrees, int32_t* status, int32_t* num_removed, void* cuda_stream);
+
 /*
  * theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157) for a batch of tracks: track t owns the rays
  * ray_offset[t] .. ray_offset[t+1]-1 (origin and direction, 3 doubles each; directions as the caller passes them, the

@@ -1018,6 +1018,51 @@ int oracle_ba_cost(const ThbBaProblem* p, const ThbBaOptions* o, double* cost) {
   return ok0 && ok1 ? THB_OK : THB_E_NUMERICAL;
 }
 
+// SetOutlierTracksToUnestimated (sfm/set_outlier_tracks_to_unestimated.cc:62-137) over the flattened problem: the
+// observations are those of estimated views, pt_const marks tracks that are not estimated. status as THB_OUTLIER_*.
+int oracle_set_outlier_tracks(const ThbBaProblem* p, double max_err, double min_angle_deg, int32_t* status) {
+  if (!p || !status) return THB_E_INVALID_ARGUMENT;
+  const int np = p->num_points, no = p->num_observations;
+  std::vector<std::vector<int>> obs(np);
+  for (int i = 0; i < no; ++i) obs[p->obs_pt[i]].push_back(i);
+  const double sq_max = max_err * max_err, cos_min = std::cos(min_angle_deg * 3.14159265358979323846 / 180.0);
+  int removed = 0;
+  for (int t = 0; t < np; ++t) {
+    if (p->pt_const && p->pt_const[t]) { status[t] = THB_OUTLIER_SKIPPED; continue; }
+    const double* X = p->pts + 4 * (size_t)t;
+    int st = THB_OUTLIER_KEPT, nproj = 0;
+    double sum = 0.0;
+    std::vector<std::array<double, 3>> rays;
+    for (int i : obs[t]) {
+      const int c = p->obs_cam[i], g = p->cam_group[c];
+      const double* ext = p->cam_ext + 6 * (size_t)c;
+      std::array<double, 3> ray = {X[0] / X[3] - ext[0], X[1] / X[3] - ext[1], X[2] / X[3] - ext[2]};
+      const double nr = std::sqrt(ray[0] * ray[0] + ray[1] * ray[1] + ray[2] * ray[2]);
+      for (double& v : ray) v /= nr;
+      rays.push_back(ray);
+      const double adj[3] = {X[0] - X[3] * ext[0], X[1] - X[3] * ext[1], X[2] - X[3] * ext[2]};
+      double pc[3], pix[2] = {0, 0};
+      oracle::AngleAxisRotatePoint(ext + 3, adj, pc);
+      if (pc[2] / X[3] < 0.0) { st = THB_OUTLIER_BAD_REPROJECTION; break; }
+      oracle::ProjectByModel<double>(p->intr_model[g], p->intr + (size_t)g * THB_INTR_STRIDE, pc, pix);
+      const double ex = pix[0] - p->obs_xy[2 * (size_t)i], ey = pix[1] - p->obs_xy[2 * (size_t)i + 1];
+      sum += ex * ex + ey * ey;
+      ++nproj;
+    }
+    if (st == THB_OUTLIER_KEPT && sum / static_cast<double>(nproj) > sq_max) st = THB_OUTLIER_BAD_REPROJECTION;
+    if (st == THB_OUTLIER_KEPT) {
+      bool wide = false;
+      for (size_t a = 0; a < rays.size() && !wide; ++a)
+        for (size_t b = a + 1; b < rays.size(); ++b)
+          if (rays[a][0] * rays[b][0] + rays[a][1] * rays[b][1] + rays[a][2] * rays[b][2] < cos_min) { wide = true; break; }
+      if (!wide) st = THB_OUTLIER_BAD_ANGLE;
+    }
+    status[t] = st;
+    removed += st > 0;
+  }
+  return removed;
+}
+
 // Thread control for the timed baselines: torchrun exports OMP_NUM_THREADS=1, the CPU arm must say how many it used.
 int oracle_set_num_threads(int n) {
   if (n > 0) omp_set_num_threads(n);

@@ -134,6 +134,15 @@ def two_view_batch(batch, intr1, intr2, options, verify):
     return rc, info, mask
 
 
+def set_outlier_tracks(prob, max_err, min_angle_deg):
+    lib = load()
+    lib.oracle_set_outlier_tracks.argtypes = [C.POINTER(capi.ThbBaProblem), C.c_double, C.c_double, C.c_void_p]
+    status = np.zeros(prob.num_points, np.int32)
+    p = prob.struct()
+    removed = lib.oracle_set_outlier_tracks(C.byref(p), max_err, min_angle_deg, _vp(status))
+    return removed, status
+
+
 def p3p(feat, world):
     """feat [count,3,2], world [count,3,3] -> (R [count,4,3,3], t [count,4,3], n [count])"""
     feat = np.ascontiguousarray(feat, np.float64); world = np.ascontiguousarray(world, np.float64)

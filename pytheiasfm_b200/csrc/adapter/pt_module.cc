@@ -896,6 +896,57 @@ PYBIND11_MODULE(_pt, m) {
     UpdateInverseDepth(TracksOfViews(v, &r), &r);
     return s;
   });
+  // SetOutlierTracksToUnestimated (sfm_wrapper.cc:46-57 -> set_outlier_tracks_to_unestimated.cc:62-137): every listed track in
+  // one launch over thb_set_outlier_tracks_batch; tracks with status > 0 become unestimated. Returns the number removed.
+  sfm.def("SetOutlierTracksToUnestimated", [](const std::unordered_set<TrackId>& track_ids, double max_err, double min_angle, Reconstruction& r) {
+    Flat f;
+    for (TrackId t : track_ids) {
+      auto it = r.tracks.find(t);
+      if (it == r.tracks.end() || !it->second.estimated) continue;                       // :76-78
+      const int pi = (int)f.track_ids.size();
+      f.track_ids.push_back(t);
+      f.pts.insert(f.pts.end(), it->second.point, it->second.point + 4);
+      for (ViewId v : it->second.views) {
+        const View& view = r.views.at(v);
+        if (!view.estimated) continue;                                                    // :86-88
+        int ci;
+        auto vi = f.view_index.find(v);
+        if (vi != f.view_index.end()) ci = vi->second;
+        else {
+          ci = (int)f.view_ids.size();
+          f.view_index[v] = ci; f.view_ids.push_back(v);
+          f.cam_ext.insert(f.cam_ext.end(), view.camera.ext, view.camera.ext + 6);
+          Intrinsics* in = view.camera.intr.get();
+          if (!f.group_index.count(in)) {
+            f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
+            f.intr_model.push_back(in->model);
+            f.intr.insert(f.intr.end(), in->params, in->params + THB_INTR_STRIDE);
+          }
+          f.cam_group.push_back(f.group_index[in]);
+        }
+        const Feature& feat = view.features.at(t);
+        f.obs_cam.push_back(ci); f.obs_pt.push_back(pi);
+        f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
+      }
+    }
+    if (f.track_ids.empty()) return 0;
+    ThbBaProblem p;
+    std::memset(&p, 0, sizeof(p));
+    p.num_cameras = (int)f.view_ids.size(); p.num_groups = (int)f.groups.size(); p.num_points = (int)f.track_ids.size();
+    p.num_observations = (int)f.obs_cam.size(); p.memory_space = THB_MEM_HOST;
+    p.cam_ext = f.cam_ext.data(); p.cam_group = f.cam_group.data(); p.intr = f.intr.data(); p.intr_model = f.intr_model.data();
+    p.pts = f.pts.data(); p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data();
+    std::vector<int32_t> status(f.track_ids.size());
+    int32_t removed = 0;
+    int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = thb_set_outlier_tracks_batch(&p, max_err, min_angle, status.data(), &removed, nullptr);
+    }
+    Check(rc);
+    for (size_t i = 0; i < f.track_ids.size(); ++i) if (status[i] > 0) r.tracks.at(f.track_ids[i]).estimated = false;
+    return (int)removed;
+  });
   sfm.def("BundleAdjustTrack", [](Reconstruction& r, const BundleAdjustmentOptions& o, TrackId t) {
     BundleAdjustmentSummary s = RunBa(o, {}, {t}, &r, true);   // no inner iterations (:267)
     UpdateInverseDepth({t}, &r);

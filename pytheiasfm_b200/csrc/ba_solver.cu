@@ -1283,6 +1283,74 @@ int thb_estimate_tracks_batch(const ThbBaProblem* P, const double* ray_direction
   return RunTrackBatch(P, O, ray_directions, E, status, results, cuda_stream);
 }
 
+int thb_set_outlier_tracks_batch(const ThbBaProblem* P, double max_err, double min_angle_deg, int32_t* status, int32_t* num_removed, void* cuda_stream) {
+  if (!P || !status) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem or status");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  const int nc = P->num_cameras, ng = P->num_groups, np = P->num_points, no = P->num_observations, sp = P->memory_space;
+  if (nc < 0 || ng < 0 || np < 0 || no < 0 || (sp != THB_MEM_HOST && sp != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad size or memory space");
+  if (num_removed && sp == THB_MEM_HOST) *num_removed = 0;
+  if (np == 0) return THB_OK;
+  if (!P->pts || (no > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->obs_cam || !P->obs_pt || !P->obs_xy)))
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool host = sp == THB_MEM_HOST;
+  const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  ConfigurePoolOnce();
+  struct ScopedArena : Arena { ~ScopedArena() { Release(); } } M;
+  M.st = st;
+  std::vector<int> h_model;
+  if ((rc = FetchToHost(P->intr_model, ng, sp, &h_model)) != THB_OK) return rc;
+  for (int g = 0; g < ng; ++g) if (num_intrinsics(h_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
+  BaState X{};
+  int *d_group = nullptr, *d_model = nullptr, *d_start = nullptr, *d_perm = nullptr, *d_oc = nullptr, *d_op = nullptr, *d_status = nullptr, *d_flags = nullptr, *d_cstart = nullptr, *d_used = nullptr;
+  uint8_t *d_cc = nullptr, *d_pc = nullptr;
+  double2* d_xy = nullptr;
+  if ((rc = M.Get(&X.cam, (size_t)nc * 6)) != THB_OK || (rc = M.Get(&X.camd, (size_t)nc * CAMD)) != THB_OK || (rc = M.Get(&X.intr, (size_t)ng * KS)) != THB_OK ||
+      (rc = M.Get(&X.pts, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_group, nc)) != THB_OK || (rc = M.Get(&d_model, ng)) != THB_OK ||
+      (rc = M.Get(&d_start, np + 1)) != THB_OK || (rc = M.Get(&d_perm, no)) != THB_OK || (rc = M.Get(&d_oc, no)) != THB_OK || (rc = M.Get(&d_op, no)) != THB_OK ||
+      (rc = M.Get(&d_xy, no)) != THB_OK || (rc = M.Get(&d_cc, nc)) != THB_OK || (rc = M.Get(&d_pc, np)) != THB_OK || (rc = M.Get(&d_status, np)) != THB_OK ||
+      (rc = M.Get(&d_flags, SF_COUNT + 1)) != THB_OK || (rc = M.Get(&d_cstart, nc + 1)) != THB_OK || (rc = M.Get(&d_used, ng)) != THB_OK)
+    return rc;
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * 6 * nc, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * KS * ng, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * 4 * np, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, P->cam_group, sizeof(int) * nc, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, h_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_oc, P->obs_cam, sizeof(int) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_op, P->obs_pt, sizeof(int) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_xy, P->obs_xy, sizeof(double2) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, 0, std::max(nc, 1), st));
+  if (P->pt_const) THB_CUDA_CHECK(cudaMemcpyAsync(d_pc, P->pt_const, np, kin, st));
+  else THB_CUDA_CHECK(cudaMemsetAsync(d_pc, 0, np, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_start, 0, sizeof(int) * (np + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cstart, 0, sizeof(int) * (nc + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, sizeof(int) * std::max(ng, 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_flags, 0, sizeof(int) * (SF_COUNT + 1), st));
+  if (nc > 0) k_setup_check_groups<<<cdiv(nc, 256), 256, 0, st>>>(nc, ng, d_group, d_flags);
+  if (no > 0) k_setup_count<<<cdiv(no, 256), 256, 0, st>>>(no, nc, np, ng, d_oc, d_op, d_group, d_start, d_cstart, d_used, d_flags);
+  int h_flags[SF_COUNT + 1];
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flags[SF_BAD_GROUP]) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
+  if (h_flags[SF_BAD_INDEX]) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
+  if ((rc = GroupByKey(d_op, no, np, d_start, d_perm, st)) != THB_OK) return rc;
+  if (nc > 0) k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc, nullptr, d_cc, d_group);
+  BaConst K{};
+  K.nc = nc; K.ng = ng; K.np = np; K.no = no; K.cam_group = d_group; K.intr_model = d_model; K.cam_const = d_cc; K.pt_const = d_pc;
+  K.loss_type = THB_LOSS_TRIVIAL; K.loss_width = 1.0;
+  int* d_removed = d_flags + SF_COUNT;
+  k_outlier_tracks<<<cdiv(np, 128), 128, 0, st>>>(K, X, d_start, d_perm, d_oc, d_xy, max_err * max_err,
+                                                 std::cos(min_angle_deg * 3.14159265358979323846 / 180.0), d_status, d_removed);
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * np, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  int h_removed = 0;
+  THB_CUDA_CHECK(cudaMemcpyAsync(&h_removed, d_removed, sizeof(int), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (num_removed) *num_removed = h_removed;
+  return THB_OK;
+}
+
 int thb_ba_evaluate(const ThbBaProblem* P, double* residuals, double* jac_cam, double* jac_intr, double* jac_pt,
                     uint8_t* ok, void* cuda_stream) {
   if (!P) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem");

@@ -247,5 +247,55 @@ __global__ void __launch_bounds__(128) k_track_ba(BaConst K, BaState X, BaState 
   }
 }
 
+
+// SetOutlierTracksToUnestimated (set_outlier_tracks_to_unestimated.cc:62-137), one thread per track; observations reached
+// through perm (point-major order of the caller's observation arrays).
+__global__ void __launch_bounds__(128) k_outlier_tracks(BaConst K, BaState St, const int* __restrict__ pt_start, const int* __restrict__ perm,
+                                                        const int* __restrict__ obs_cam, const double2* __restrict__ obs_xy, double sq_max,
+                                                        double cos_min, int* __restrict__ status, int* __restrict__ removed) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= K.np) return;
+  if (K.pt_const[p]) { status[p] = THB_OUTLIER_SKIPPED; return; }
+  const int q0 = pt_start[p], q1 = pt_start[p + 1];
+  const double* Xp = St.pts + (size_t)p * 4;
+  const double X[4] = {Xp[0], Xp[1], Xp[2], Xp[3]};
+  int st = THB_OUTLIER_KEPT, nproj = 0;
+  double sum = 0.0;
+  for (int q = q0; q < q1; ++q) {
+    const int i = perm[q], c = obs_cam[i];
+    const double* cd = St.camd + (size_t)c * CAMD;
+    const double adj[3] = {X[0] - X[3] * cd[CD_C], X[1] - X[3] * cd[CD_C + 1], X[2] - X[3] * cd[CD_C + 2]};
+    double pc[3];
+    rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2], adj, pc);
+    if (pc[2] / X[3] < 0.0) { st = THB_OUTLIER_BAD_REPROJECTION; break; }   // depth < 0 (:102-106)
+    const int g = K.ng > 1 ? K.cam_group[c] : 0;
+    double pix[2] = {0.0, 0.0};
+    project<-1, double, double>(K.intr_model[g], St.intr + (size_t)g * KS, pc, pix);
+    const double2 xy = obs_xy[i];
+    sum += (pix[0] - xy.x) * (pix[0] - xy.x) + (pix[1] - xy.y) * (pix[1] - xy.y);
+    ++nproj;
+  }
+  if (st == THB_OUTLIER_KEPT && sum / (double)nproj > sq_max) st = THB_OUTLIER_BAD_REPROJECTION;  // 0 / 0 = NaN compares false
+  if (st == THB_OUTLIER_KEPT) {  // SufficientTriangulationAngle over the rays (point - camera position), triangulation.cc:236-250
+    bool wide = false;
+    const double h[3] = {X[0] / X[3], X[1] / X[3], X[2] / X[3]};
+    for (int a = q0; a < q1 && !wide; ++a) {
+      const double* ca = St.camd + (size_t)obs_cam[perm[a]] * CAMD + CD_C;
+      double u[3] = {h[0] - ca[0], h[1] - ca[1], h[2] - ca[2]};
+      const double nu = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+      u[0] /= nu; u[1] /= nu; u[2] /= nu;
+      for (int b = a + 1; b < q1; ++b) {
+        const double* cb = St.camd + (size_t)obs_cam[perm[b]] * CAMD + CD_C;
+        double v[3] = {h[0] - cb[0], h[1] - cb[1], h[2] - cb[2]};
+        const double nv = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        if (u[0] * (v[0] / nv) + u[1] * (v[1] / nv) + u[2] * (v[2] / nv) < cos_min) { wide = true; break; }
+      }
+    }
+    if (!wide) st = THB_OUTLIER_BAD_ANGLE;
+  }
+  status[p] = st;
+  if (st > 0) atomicAdd(removed, 1);
+}
+
 }  // namespace thb
 #endif  // THB_TRACK_BA_CUH_

@@ -141,6 +141,17 @@ def test_BundleAdjustReconstruction_full_and_partial(gen, ba_options):
     assert result.success and result.final_cost < 1e-6 * result.initial_cost + 1e-9
 
 
+def test_SetOutlierTracksToUnestimated(gen):
+    """sfm.cc:935 / set_outlier_tracks_to_unestimated.cc: a displaced track and a far-away track lose their estimated flag."""
+    tids = gen.recon.TrackIds()
+    bad = gen.recon.MutableTrack(tids[0]); p = bad.Point(); p[:3] += 0.3 * p[3]; bad.SetPoint(p)
+    far = gen.recon.MutableTrack(tids[1]); q = far.Point(); q[:3] = q[:3] * 5000.0; far.SetPoint(q)
+    n = pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon)
+    assert n >= 2 and not gen.recon.Track(tids[0]).IsEstimated() and not gen.recon.Track(tids[1]).IsEstimated()
+    assert gen.recon.Track(tids[2]).IsEstimated()
+    assert pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon) == 0      # idempotent
+
+
 def _two_view_corrs(n=300, outliers=0.3, noise=1e-3, seed=65):
     rng = np.random.default_rng(seed)
     ang = np.deg2rad(10.0)

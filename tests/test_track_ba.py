@@ -227,3 +227,40 @@ def test_estimate_tracks_matches_the_composed_oracle(lib, oracle, min_angle, wit
     assert (status == capi.TRACK_ESTIMATED).sum() > (5 if min_angle > 10 else 140)
     if min_angle > 10:
         assert (status == capi.TRACK_BAD_ANGLE).sum() > 5
+
+
+def test_set_outlier_tracks_batch_matches_oracle(lib, oracle):
+    """SetOutlierTracksToUnestimated (set_outlier_tracks_to_unestimated.cc:62-137) for all tracks in one launch: tracks behind
+    a camera, with a large mean reprojection error, or seen under too small an angle, for mixed camera models; host and
+    device memory."""
+    import torch
+    prob, gt = synthetic.make_ba_problem(12, 2000, 4, models=(capi.MODEL_PINHOLE, capi.MODEL_DOUBLE_SPHERE, capi.MODEL_FISHEYE), seed=51)
+    prob.a["cam_ext"][:] = gt["cam_ext"]; prob.a["pts"][:] = gt["pts"]
+    rng = np.random.default_rng(3)
+    P = prob.a["pts"]
+    P[::9, :3] += rng.normal(0, 0.05, (len(P[::9]), 3))          # large reprojection errors
+    far = np.arange(5, 2000, 37)
+    P[far, :3] = P[far, :3] * 400.0                                # far away: rays nearly parallel ...
+    for i in np.nonzero(np.isin(prob.a["obs_pt"], far))[0]:        # ... but perfectly reprojected: only the angle test fails
+        c = prob.a["obs_cam"][i]; g = prob.a["cam_group"][c]
+        pc = synthetic.rotmat_from_rotvec(prob.a["cam_ext"][c, 3:]) @ (P[prob.a["obs_pt"][i], :3] - prob.a["cam_ext"][c, :3])
+        if pc[2] > 0:
+            prob.a["obs_xy"][i] = synthetic.project(int(prob.a["intr_model"][g]), prob.a["intr"][g], pc[None])[0]
+    behind = np.arange(7, 2000, 53)
+    P[behind, :3] = prob.a["cam_ext"][prob.a["obs_cam"][np.searchsorted(np.sort(prob.a["obs_pt"]), behind)] % 12, :3] * 1.5   # pushed behind some camera
+    prob.a["pt_const"][::11] = 1
+    P[3] *= 2.5                                                     # homogeneous scale must not matter
+    removed_o, status_o = oracle.set_outlier_tracks(prob, 4.0, 3.0)
+    status = np.zeros(prob.num_points, np.int32); removed = C.c_int32(0)
+    p = prob.struct()
+    capi.check(lib.thb_set_outlier_tracks_batch(C.byref(p), 4.0, 3.0, status.ctypes.data_as(C.c_void_p), C.byref(removed), None))
+    np.testing.assert_array_equal(status, status_o)
+    assert removed.value == removed_o == int((status > 0).sum())
+    assert {capi_s for capi_s in set(status.tolist())} >= {-1, 0, 1, 2}
+    dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
+    pd = prob.struct(); pd.memory_space = capi.THB_MEM_DEVICE
+    for k, v in dev.items():
+        setattr(pd, k, None if v is None else v.data_ptr())
+    d_status = torch.zeros(prob.num_points, dtype=torch.int32, device="cuda")
+    capi.check(lib.thb_set_outlier_tracks_batch(C.byref(pd), 4.0, 3.0, C.c_void_p(d_status.data_ptr()), C.byref(removed), None))
+    np.testing.assert_array_equal(d_status.cpu().numpy(), status_o)
