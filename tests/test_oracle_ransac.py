@@ -189,7 +189,9 @@ def test_ransac_is_deterministic_in_the_seed_and_rejects_bad_params(oracle):
     params.error_thresh = -1.0
     assert oracle.ransac_relpose_batch(batch, params)[0] == capi.THB_E_INVALID_ARGUMENT
     params = synthetic.c4_params(oracle.ransac_default_params()); params.use_lo = 1
-    assert oracle.ransac_relpose_batch(batch, params)[0] == capi.THB_E_UNSUPPORTED
+    assert oracle.ransac_batch("abspose", synthetic.make_abspose_batch(2, n=50, seed=1)[0], params)[0] == capi.THB_E_UNSUPPORTED
+    lo = oracle.ransac_relpose_batch(batch, params)          # LO-RANSAC for the relative pose: RefineModel runs at least once per pair
+    assert lo[0] == 0 and (lo[1]["num_lo_iterations"] >= 1).all()
 
 
 def test_default_ransac_parameters(oracle):
