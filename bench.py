@@ -422,6 +422,163 @@ def run_ransac_leg(args, lib, rank, local_rank, world, stream, K, W):
     return obj
 
 
+def adapter_e2e(prob, iterations_per_solve, repeats=3):
+    """The call a pipeline user makes: pt.sfm.BundleAdjustReconstruction(options, reconstruction) through the pybind adapter on
+    the full C2 scene, INCLUDING the adapter's gather of the hash-map Reconstruction into the flat arrays and the scatter
+    back. The reconstruction is rebuilt to the initial estimate before every timed call (not timed)."""
+    from pytheiasfm_b200 import _pt as pt
+    a = prob.a
+    recon = pt.sfm.Reconstruction()
+    vids, tids = [], []
+    for c in range(prob.num_cameras):
+        v = recon.AddView(str(c), 0, float(c))
+        cam = recon.View(v).MutableCamera()
+        cam.SetFocalLength(float(a["intr"][0, 0])); cam.SetPrincipalPoint(float(a["intr"][0, 3]), float(a["intr"][0, 4]))
+        recon.View(v).SetIsEstimated(True)
+        vids.append(v)
+    for p in range(prob.num_points):
+        t = recon.AddTrack()
+        recon.MutableTrack(t).SetIsEstimated(True)
+        tids.append(t)
+    oc, op, xy = a["obs_cam"], a["obs_pt"], a["obs_xy"]
+    for i in range(prob.num_observations):
+        recon.AddObservation(vids[oc[i]], tids[op[i]], pt.sfm.Feature(xy[i]))
+
+    def reset():
+        for c, v in enumerate(vids):
+            cam = recon.View(v).MutableCamera()
+            cam.SetPosition(a["cam_ext"][c, :3].copy()); cam.SetOrientationFromAngleAxis(a["cam_ext"][c, 3:].copy())
+        for p, t in enumerate(tids):
+            recon.MutableTrack(t).SetPoint(a["pts"][p].copy())
+
+    opts = pt.sfm.BundleAdjustmentOptions()
+    opts.use_inner_iterations = False
+    walls, solves, setups, cost = [], [], [], None
+    for r in range(repeats + 1):
+        reset()
+        t0 = time.perf_counter()
+        summ = pt.sfm.BundleAdjustReconstruction(opts, recon)
+        wall = time.perf_counter() - t0
+        if r > 0:
+            walls.append(wall); solves.append(summ.solve_time_in_seconds); setups.append(summ.setup_time_in_seconds)
+        cost = summ.final_cost
+    wall = float(np.median(walls))
+    return {"value": iterations_per_solve / wall, "unit": UNIT, "ms_per_call": 1e3 * wall, "iterations_per_call": iterations_per_solve,
+            "solver_ms": 1e3 * float(np.median(solves)), "device_setup_ms": 1e3 * float(np.median(setups)),
+            "gather_scatter_ms": 1e3 * (wall - float(np.median(solves)) - float(np.median(setups))), "final_cost": cost,
+            "note": "pt.sfm.BundleAdjustReconstruction on a Reconstruction of hash maps (1 call = 1 complete solve); gather_scatter = wall - device setup - solve"}
+
+
+def run_c5_leg(args, lib, rank, local_rank, world, stream, K):
+    """BASELINE configs[4]: the hot-path stages of a global SfM pipeline on the south-building-shaped scene, end to end from
+    host buffers: two-view verification of every image pair (TwoViewMatchGeometricVerification, pairs dealt over the ranks),
+    TrackEstimator (triangulation + per-track BA), BundleAdjustReconstruction with the pipeline's options (Huber width 10,
+    inner iterations) and SetOutlierTracksToUnestimated. View-graph filtering and rotation / position averaging between
+    verification and the track stage are outside the hot path: the cameras enter the track stage as the
+    generator's poses plus noise. Returns the `c5` object (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+    from pytheiasfm_b200 import capi, sharding, synthetic
+    sptr = C.c_void_p(stream.cuda_stream)
+    scene = synthetic.config_c5()
+    pairs, intr, prob0 = scene["pairs"], scene["intrinsics"], scene["problem"]
+    idx = sharding.block_cyclic_indices(pairs.num_pairs, rank, world, 4)
+    mine = capi.HostPairBatch([pairs.corr[pairs.pair_offset[i]:pairs.pair_offset[i + 1]] for i in idx], pairs.seed[idx])
+    mi = np.ascontiguousarray(intr[idx])
+    tvo = capi.ThbTwoViewOptions(); lib.thb_two_view_default_options(C.byref(tvo))
+    info = np.zeros(mine.num_pairs, capi.TWO_VIEW_INFO_DTYPE); vmask = np.zeros(int(mine.pair_offset[-1]), np.uint8)
+    rays = synthetic.pinhole_rays(prob0)
+    teo = capi.ThbTrackEstimatorOptions()
+    bo = capi.default_options(lib)
+    bo.loss_function_type = capi.LOSS_HUBER; bo.robust_loss_width = 10.0; bo.use_inner_iterations = 1; bo.max_num_iterations = 50
+    tbo = capi.default_options(lib)
+    counts = [len(sharding.block_cyclic_indices(pairs.num_pairs, r, world, 4)) for r in range(world)]
+    rec = capi.TWO_VIEW_INFO_DTYPE.itemsize
+    out = {}
+
+    def vp(a):
+        return a.ctypes.data_as(C.c_void_p)
+
+    def once():
+        t = {}
+        t0 = time.perf_counter()
+        if mine.num_pairs:
+            b = mine.struct()
+            capi.check(lib.thb_verify_two_view_matches_batch(C.byref(b), vp(mi), vp(mi), C.byref(tvo), vp(info), vp(vmask), sptr))
+        if world > 1:
+            local = torch.from_numpy(info.view(np.uint8).reshape(-1).copy()).cuda()
+            parts = sharding.all_gather_padded(local, [c * rec for c in counts])
+            out["info_all"] = np.concatenate([np.frombuffer(x.cpu().numpy().tobytes(), capi.TWO_VIEW_INFO_DTYPE) for x in parts])
+        else:
+            out["info_all"] = info
+        torch.cuda.synchronize()
+        t["verification"] = time.perf_counter() - t0
+        if rank == 0:
+            prob = prob0.copy()
+            status = np.zeros(prob.num_points, np.int32)
+            t0 = time.perf_counter()
+            p = prob.struct()
+            capi.check(lib.thb_estimate_tracks_batch(C.byref(p), vp(rays), C.byref(teo), C.byref(tbo), vp(status), None, sptr))
+            t["tracks"] = time.perf_counter() - t0
+            # BundleAdjustReconstruction adds estimated tracks only (bundle_adjuster.cc:142,178): drop the others' observations
+            t0 = time.perf_counter()
+            keep = status[prob.a["obs_pt"]] == capi.TRACK_ESTIMATED
+            a = dict(prob.a)
+            for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+                a[k] = prob.a[k][keep]
+            a["pt_const"] = (status != capi.TRACK_ESTIMATED).astype(np.uint8)
+            prob = capi.HostBaProblem(a)
+            t["select_estimated"] = time.perf_counter() - t0
+            summ = capi.ThbBaSummary()
+            t0 = time.perf_counter()
+            p = prob.struct()
+            capi.check(lib.thb_ba_solve(C.byref(p), C.byref(bo), C.byref(summ), sptr))
+            t["bundle_adjustment"] = time.perf_counter() - t0
+            ostat = np.zeros(prob.num_points, np.int32); removed = C.c_int32(0)
+            t0 = time.perf_counter()
+            p = prob.struct()
+            capi.check(lib.thb_set_outlier_tracks_batch(C.byref(p), 4.0, 2.0, vp(ostat), C.byref(removed), sptr))
+            t["outlier_filter"] = time.perf_counter() - t0
+            out.update(status=status, summ=summ.as_dict(), removed=removed.value, prob=prob)
+        if world > 1:
+            dist.barrier()
+        return t
+
+    once()
+    runs = [once() for _ in range(K)]
+    if rank != 0:
+        return None
+    stages = {k: 1e3 * float(np.mean([r[k] for r in runs])) for k in runs[0]}
+    total = sum(stages.values())
+    gt = scene["gt"]
+    est = out["status"] == capi.TRACK_ESTIMATED
+    X = out["prob"].a["pts"]
+    err = np.linalg.norm(X[est, :3] / X[est, 3:4] - gt["pts"][est], axis=1)
+    obj = {"metric": "C5 hot-path pipeline (verification + tracks + BA + filter) runs/s", "value": 1e3 / total, "unit": "runs/s", "n_gpus": world, "steps": K,
+           "config": {"workload": "C5 south-building-shaped synthetic: %d cams, %d tracks, %d observations, %d image pairs x ~%d matches" % (
+               prob0.num_cameras, prob0.num_points, prob0.num_observations, pairs.num_pairs, int(np.diff(pairs.pair_offset).mean())),
+               "stages": "VerifyMatches batched over the ranks (pairs dealt block-cyclically), then on rank 0: TrackEstimator, BundleAdjustReconstruction "
+                         "(Huber 10, inner iterations, <= 50 iterations), SetOutlierTracksToUnestimated; all from host buffers",
+               "not_timed": "view-graph filtering, rotation / position averaging (outside the hot path)"},
+           "stage_ms": stages, "total_ms": total,
+           "pairs_verified": int(out["info_all"]["success"].sum()), "pairs": int(pairs.num_pairs),
+           "tracks_estimated": int(est.sum()), "ba": {k: out["summ"][k] for k in ("num_iterations", "initial_cost", "final_cost", "termination_type")},
+           "tracks_removed_by_filter": int(out["removed"]), "median_point_error": float(np.median(err))}
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle_py
+        threads = oracle_threads()
+        nsub = 64
+        sub = capi.HostPairBatch([pairs.corr[pairs.pair_offset[i]:pairs.pair_offset[i + 1]] for i in range(nsub)], pairs.seed[:nsub])
+        t0 = time.time(); rc, oinfo, omask = oracle_py.two_view_batch(sub, intr[:nsub], intr[:nsub], tvo, True); tv = time.time() - t0
+        same = bool(np.array_equal(oinfo["success"], out["info_all"]["success"][:nsub]) and
+                    np.array_equal(oinfo["num_verified_matches"], out["info_all"]["num_verified_matches"][:nsub]))
+        obj["cpu_baseline"] = {"kind": "port", "cores": threads, "verification_ms_all_pairs": 1e3 * tv * pairs.num_pairs / nsub,
+                               "sample": "oracle VerifyMatches on the first %d of the %d pairs, scaled to all pairs (%d threads)" % (nsub, pairs.num_pairs, threads),
+                               "verification_identical_on_sample": same}
+        assert same, "C5 verification differs from the oracle on the sampled pairs"
+    return obj
+
+
 def run_ba_leg(args, lib, rank, local_rank, world, stream, K, W):
     """First half of the metric: BA iterations/s on C2. Returns the line (rank 0) or None."""
     import torch
@@ -549,6 +706,9 @@ def run_ba_leg(args, lib, rank, local_rank, world, stream, K, W):
         line["cpu_baseline"] = cb
         line["parity"] = {"iter_cost_gpu": ours, "iter_cost_oracle": theirs, "max_rel_diff": rel, "tolerance": 1e-6}
         assert len(ours) == len(theirs) and rel <= 1e-6, ("BA cost sequence differs from the oracle", ours, theirs)
+    if world == 1 and not args.no_adapter:
+        line["adapter_e2e"] = adapter_e2e(prob, summ["num_iterations"])
+        assert abs(line["adapter_e2e"]["final_cost"] - summ["final_cost"]) <= 1e-6 * summ["final_cost"]
     return line
 
 
@@ -564,6 +724,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the BA workload (debug only; 1.0 = BASELINE config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 pipeline leg (configs[4])")
+    ap.add_argument("--no-adapter", action="store_true", help="skip the pybind adapter timing")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -596,6 +758,10 @@ def main():
                 line = dict(r, vs_baseline=None, dtype="f64", data="synthetic")
             else:
                 line["ransac"] = r
+    if args.workload == "both" and not args.no_c5:
+        c5 = run_c5_leg(args, lib, rank, local_rank, world, stream, min(K, 5))
+        if rank == 0:
+            line["c5"] = c5
     if rank == 0:
         emit(line)
     if world > 1:

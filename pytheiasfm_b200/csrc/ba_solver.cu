@@ -12,6 +12,8 @@
 #include <cstring>
 #include <limits>
 #include <mutex>
+#include <set>
+#include <tuple>
 #include <vector>
 
 #include "ba_kernels.cuh"
@@ -212,20 +214,24 @@ int CheckDevice() {
 }
 
 // K1 uses no shared memory: ask for the largest L1 so the 128-byte camera records stay resident.
-// Function attributes are per device: one once_flag per (kernel instantiation, device), safe under concurrent callers.
+// Function attributes are per (device, kernel): applied once each, safe under concurrent callers. Keyed by the kernel's
+// ADDRESS - every instantiation of a kernel template has the same function-pointer type, so a per-type flag would set the
+// attribute for the first instantiation only.
+bool FirstUse(const void* kern, int what) {
+  static std::mutex mu;
+  static std::set<std::tuple<int, const void*, int>> seen;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  std::lock_guard<std::mutex> lk(mu);
+  return seen.insert(std::make_tuple(dev, kern, what)).second;
+}
 template <typename Kern>
 void PreferL1Once(Kern kern) {
-  static std::once_flag once[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-  std::call_once(once[dev], [kern] { cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1); });
+  if (FirstUse(reinterpret_cast<const void*>(kern), 0)) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
 }
 template <typename Kern>
 void MaxDynamicSmemOnce(Kern kern, int bytes) {
-  static std::once_flag once[64];
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return;
-  std::call_once(once[dev], [kern, bytes] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); });
+  if (FirstUse(reinterpret_cast<const void*>(kern), 1)) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 int SmCount() {
   int dev = 0, sms = 0;

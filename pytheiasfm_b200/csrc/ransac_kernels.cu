@@ -1159,6 +1159,16 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRans
     for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
   }
   if (rng_state && rng_mode == 1) {
+    // The batches draw their samples ahead of the replay: when the loop stops inside a batch the generator has run past the
+    // reference's. Rebuild the state the sequential loop leaves behind: num_iterations x SampleSize draws (the draws depend on
+    // the ranges only, not on the permutation).
+    __syncthreads();
+    if (t == 0) {
+      mt_seed(&S.rng, seed[pair]);
+      for (int it = 0; it < S.num_iterations; ++it)
+        for (int i = 0; i < SS; ++i) (void)mt_uniform_int(&S.rng, i, n - 1);
+    }
+    __syncthreads();
     uint32_t* dst = rng_state + (size_t)pair * 625;
     for (int i = t; i < 624; i += RT) dst[i] = S.rng.mt[i];
     if (t == 0) dst[624] = (uint32_t)S.rng.idx;

@@ -336,3 +336,74 @@ def make_two_view_batch(num_pairs, n=600, models=(capi.MODEL_PINHOLE,), inlier_r
         perm = rng.permutation(n)
         corrs.append(corr[perm]); gts.append((R, c, flags[perm]))
     return capi.HostPairBatch(corrs, base_seed + np.arange(num_pairs)), intr1, intr2, gts
+
+
+def config_c5(seed=5, num_cameras=128, num_points=60000, window=6, pair_reach=4, outlier_ratio=0.15, pixel_sigma=0.5, image=1000.0, focal=1000.0):
+    """BASELINE configs[4]: south-building-shaped scene - `num_cameras` Pinhole cameras on two rings around a box of
+    `num_points` points, every point seen by `window` neighbouring cameras of one ring (~6 observations per track), image
+    pairs = cameras within `pair_reach` ring neighbours (4 * num_cameras pairs of ~1-2k matches), `outlier_ratio` wrong matches
+    per pair. Returns a dict: the flattened reconstruction (HostBaProblem with perturbed cameras / ground-truth-free points),
+    the pair table in PIXELS (HostPairBatch + per-pair view indices + ThbViewIntrinsics arrays) and the ground truth."""
+    rng = np.random.default_rng(seed)
+    per_ring = num_cameras // 2
+    idx = np.arange(num_cameras)
+    ring = idx // per_ring
+    ang = 2 * np.pi * (idx % per_ring) / per_ring + 0.05 * ring
+    Cw = np.stack([12.0 * np.cos(ang), 12.0 * np.sin(ang), np.where(ring == 0, 1.0, 3.5)], -1)
+    R = _look_at(Cw, rng.normal(0.0, 0.1, size=(num_cameras, 3)) + np.array([0.0, 0.0, 1.5]))
+    aa = _rotvec_from_matrix(R)
+    K = default_intrinsics(capi.MODEL_PINHOLE, focal, image / 2, image / 2)
+    # points on / near the faces of a box, so that neighbouring cameras see them at similar scale
+    pts = (rng.random((num_points, 3)) * 2.0 - 1.0) * np.array([3.0, 3.0, 2.0]) + np.array([0.0, 0.0, 1.5])
+    pring = rng.integers(0, 2, num_points)
+    centre = (np.round((np.arctan2(pts[:, 1], pts[:, 0]) % (2 * np.pi)) / (2 * np.pi) * per_ring).astype(int)) % per_ring
+    offs = np.arange(window) - window // 2
+    obs_cam = (pring[:, None] * per_ring + (centre[:, None] + offs[None, :]) % per_ring).astype(np.int32).reshape(-1)
+    obs_pt = np.repeat(np.arange(num_points, dtype=np.int32), window)
+    pc = np.einsum("nij,nj->ni", R[obs_cam], pts[obs_pt] - Cw[obs_cam])
+    xy_true = project(capi.MODEL_PINHOLE, K, pc)
+    ok = (pc[:, 2] > 0.5) & np.all((xy_true > 0.02 * image) & (xy_true < 0.98 * image), axis=1)
+    obs_cam, obs_pt, xy_true = obs_cam[ok], obs_pt[ok], xy_true[ok]
+    xy = xy_true + rng.normal(0.0, pixel_sigma, xy_true.shape)
+    # pair table: shared tracks of cameras within pair_reach neighbours on the same ring
+    order = np.lexsort((obs_pt, obs_cam))
+    oc, op, oxy = obs_cam[order], obs_pt[order], xy[order]
+    start = np.searchsorted(oc, np.arange(num_cameras + 1))
+    corrs, pair_views = [], []
+    for a in range(num_cameras):
+        for d in range(1, pair_reach + 1):
+            b = (a // per_ring) * per_ring + ((a % per_ring) + d) % per_ring
+            pa, pb = op[start[a]:start[a + 1]], op[start[b]:start[b + 1]]
+            common, ia, ib = np.intersect1d(pa, pb, return_indices=True)
+            m = np.concatenate([oxy[start[a]:start[a + 1]][ia], oxy[start[b]:start[b + 1]][ib]], 1)
+            nout = int(outlier_ratio * len(m))
+            if nout and len(pa) and len(pb):
+                wrong = np.concatenate([oxy[start[a]:start[a + 1]][rng.integers(0, len(pa), nout)], oxy[start[b]:start[b + 1]][rng.integers(0, len(pb), nout)]], 1)
+                m = np.concatenate([m, wrong], 0)
+            corrs.append(m[rng.permutation(len(m))]); pair_views.append((a, b))
+    pairs = capi.HostPairBatch(corrs, 9000 + np.arange(len(corrs)))
+    intr = np.zeros(len(corrs), capi.VIEW_INTRINSICS_DTYPE)
+    intr["model"] = capi.MODEL_PINHOLE; intr["image_width"] = int(image); intr["image_height"] = int(image); intr["focal_length_is_set"] = 1
+    intr["params"] = K
+    cam0 = np.concatenate([Cw, aa], 1)
+    cam0[:, :3] += rng.normal(0, 0.01, (num_cameras, 3)); cam0[:, 3:] += rng.normal(0, 0.001, (num_cameras, 3))
+    prob = capi.HostBaProblem(dict(
+        cam_ext=cam0, cam_const=np.zeros(num_cameras, np.uint8), cam_group=np.zeros(num_cameras, np.int32), intr=K[None].copy(),
+        intr_model=np.array([capi.MODEL_PINHOLE], np.int32), intr_const=np.array([(1 << 7) - 1], np.uint16),
+        pts=np.concatenate([np.zeros((num_points, 3)), np.ones((num_points, 1))], 1), pt_const=np.zeros(num_points, np.uint8),
+        obs_cam=obs_cam, obs_pt=obs_pt, obs_xy=xy, obs_sqrt_info=np.ones_like(xy)))
+    return dict(problem=prob, pairs=pairs, pair_views=np.array(pair_views, np.int32), intrinsics=intr,
+                gt=dict(cam_ext=np.concatenate([Cw, aa], 1), pts=pts, K=K))
+
+
+def pinhole_rays(prob):
+    """Camera::PixelToUnitDepthRay(feature).normalized() for every observation of an undistorted-Pinhole problem (what the
+    caller of thb_estimate_tracks_batch provides)."""
+    a = prob.a
+    K = a["intr"][a["cam_group"][a["obs_cam"]]]
+    y = (a["obs_xy"][:, 1] - K[:, 4]) / (K[:, 0] * K[:, 1])
+    x = (a["obs_xy"][:, 0] - K[:, 3] - y * K[:, 2]) / K[:, 0]
+    u = np.stack([x, y, np.ones_like(x)], -1)
+    Rm = rotmat_from_rotvec(a["cam_ext"][a["obs_cam"], 3:])
+    d = np.einsum("nji,nj->ni", Rm, u)
+    return np.ascontiguousarray(d / np.linalg.norm(d, axis=1, keepdims=True))

@@ -125,3 +125,20 @@ def test_verify_gates_and_options(lib, oracle):
     b = mixed.struct()
     out = np.zeros(6, capi.TWO_VIEW_INFO_DTYPE)
     assert lib.thb_verify_two_view_matches_batch(C.byref(b), _vp(a1), _vp(a2), C.byref(o), _vp(out), None, None) == capi.THB_E_UNSUPPORTED
+
+
+def test_verify_c5_pairs_generator_state_after_early_termination(lib, oracle):
+    """C5 pairs (box faces: the homography RANSAC ends inside a batch of 128 draws): the relative-pose RANSAC must continue
+    from the generator state the SEQUENTIAL loop leaves behind, not from the batch's read-ahead."""
+    sc = synthetic.config_c5(num_points=20000)
+    pairs, intr = sc["pairs"], sc["intrinsics"]
+    n = 40
+    sub = capi.HostPairBatch([pairs.corr[pairs.pair_offset[i]:pairs.pair_offset[i + 1]] for i in range(n)], pairs.seed[:n])
+    ii = np.ascontiguousarray(intr[:n])
+    o = default_opts(lib)
+    info, mask = gpu_two_view(lib, sub, ii, ii, o, True)
+    rc, oinfo, omask = oracle.two_view_batch(sub, ii, ii, o, True)
+    for f in ("success", "num_homography_inliers", "num_ransac_iterations", "num_triangulated", "ba_iterations", "num_verified_matches"):
+        np.testing.assert_array_equal(info[f], oinfo[f], err_msg=f)
+    np.testing.assert_array_equal(mask, omask)
+    assert (info["num_ransac_iterations"] % 128 != 0).any()
