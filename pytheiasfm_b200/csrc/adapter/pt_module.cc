@@ -24,6 +24,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <atomic>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -176,6 +177,8 @@ struct Track {
   double inverse_depth = 0.0;
   ViewId reference_view = kInvalid;
   std::vector<ViewId> views;  // insertion order; the first view added is the reference view (track.cc:78-83)
+  mutable int flat_index = -1;          // slot of this track in the gather of the current BundleAdjust* call ...
+  mutable uint64_t flat_epoch = 0;      // ... valid when it carries that call's epoch (saves a hash look-up per observation)
   void SetPoint(const Vec& p) { CopyVec(p, point, 4, "point"); }
   Vec Point() const { return MakeVec(point, 4); }
 };
@@ -330,12 +333,13 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     f.cam_group.push_back(g);
     return idx;
   };
-  auto add_track = [&](TrackId t, bool free_pt) {
-    auto it = f.track_index.find(t);
-    if (it != f.track_index.end()) { if (free_pt) f.pt_const[it->second] = 0; return it->second; }
+  static std::atomic<uint64_t> g_epoch{0};
+  const uint64_t epoch = ++g_epoch;
+  auto add_track = [&](TrackId t, const Track& tr, bool free_pt) {
+    if (tr.flat_epoch == epoch) { if (free_pt) f.pt_const[tr.flat_index] = 0; return tr.flat_index; }
     const int idx = (int)f.track_ids.size();
-    f.track_index[t] = idx; f.track_ids.push_back(t);
-    const Track& tr = r->tracks.at(t);
+    tr.flat_epoch = epoch; tr.flat_index = idx;
+    f.track_ids.push_back(t);
     f.pts.insert(f.pts.end(), tr.point, tr.point + 4);
     f.pt_const.push_back(free_pt ? 0 : 1);
     return idx;
@@ -345,6 +349,14 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
     f.obs_si.push_back(1.0 / std::sqrt(feat.cov[0])); f.obs_si.push_back(1.0 / std::sqrt(feat.cov[3]));   // reprojection_error.h:96-103
   };
+  {  // one pass over the sizes so that the flat arrays grow once
+    size_t nobs = 0;
+    for (ViewId v : views) { auto vi = r->views.find(v); if (vi != r->views.end()) nobs += vi->second.track_order.size(); }
+    f.obs_cam.reserve(nobs); f.obs_pt.reserve(nobs); f.obs_xy.reserve(2 * nobs); f.obs_si.reserve(2 * nobs);
+    f.pts.reserve(4 * r->tracks.size()); f.pt_const.reserve(r->tracks.size()); f.track_ids.reserve(r->tracks.size());
+  }
+  bool all_views_optimised = vset.size() >= r->views.size();
+  if (all_views_optimised) for (const auto& kv : r->views) if (!vset.count(kv.first)) { all_views_optimised = false; break; }
   for (ViewId v : views) {                                                 // AddView
     auto vi = r->views.find(v);
     if (vi == r->views.end()) throw std::invalid_argument("unknown view id");   // the reference CHECK-aborts (bundle_adjuster.cc:117)
@@ -353,14 +365,15 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     for (TrackId t : vi->second.track_order) {
       const Track& tr = r->tracks.at(t);
       if (!tr.estimated) continue;
-      add_obs(ci, add_track(t, false), vi->second.features.at(t));
+      add_obs(ci, add_track(t, tr, false), vi->second.features.at(t));
     }
   }
   for (TrackId t : tracks) {                                               // AddTrack
     auto ti = r->tracks.find(t);
     if (ti == r->tracks.end()) throw std::invalid_argument("unknown track id");
     if (!ti->second.estimated) continue;
-    const int pi = add_track(t, true);
+    const int pi = add_track(t, ti->second, true);
+    if (all_views_optimised) continue;  // every observing view is already in (or unestimated): nothing to add (bundle_adjuster.cc:192-198)
     for (ViewId v : ti->second.views) {
       View& view = r->views.at(v);
       if (vset.count(v) || !view.estimated) continue;
