@@ -124,9 +124,10 @@ typedef struct ThbBaOptions {
   double min_lm_diagonal;             /* 1e-6  */
   double max_lm_diagonal;             /* 1e32  */
   double max_solver_time_in_seconds;
-  /* THB_SOLVER_SCHUR_PCG only */
-  double pcg_tolerance;               /* relative residual; default 1e-12              */
-  int32_t pcg_max_iterations;         /* default 500                                   */
+  /* THB_SOLVER_SCHUR_PCG only (ceres ITERATIVE_SCHUR + SCHUR_JACOBI) */
+  double pcg_eta;                     /* Solver::Options::eta, the forcing term: CG stops when the relative decrease of
+                                         the quadratic model, i * (Q_i - Q_{i-1}) / Q_i, drops below it; default 0.1   */
+  int32_t pcg_max_iterations;         /* Solver::Options::max_linear_solver_iterations; default 500                    */
   int32_t reserved0;
 } ThbBaOptions;
 
@@ -153,7 +154,7 @@ typedef struct ThbBaSummary {
   double ms_solve;          /* K4 reduced camera system factor/solve                   */
   double ms_update;         /* K5 back-substitution, Plus, cost evaluation             */
   int32_t iter_log_count;
-  int32_t reserved0;
+  int32_t num_linear_solver_iterations; /* THB_SOLVER_SCHUR_PCG: conjugate-gradient iterations over all linear solves */
   double iter_cost[THB_MAX_ITER_LOG];   /* cost after each iteration (index 0 = initial) */
   double iter_radius[THB_MAX_ITER_LOG]; /* trust-region radius after each iteration      */
 } ThbBaSummary;

@@ -555,8 +555,12 @@ class BaOracle {
     if (!ok) return false;
     std::vector<double> yr(rhs);
     if (nr) {
-      if (!CholeskyLower(S.data(), nr)) return false;
-      CholeskySolveLower(S.data(), nr, yr.data());
+      if (O.linear_solver == THB_SOLVER_SCHUR_PCG) {
+        if (!ConjugateGradients(S, rhs, &yr)) return false;
+      } else {
+        if (!CholeskyLower(S.data(), nr)) return false;
+        CholeskySolveLower(S.data(), nr, yr.data());
+      }
       for (int k = 0; k < nr; ++k) (*y)[n_pt_tan + k] = yr[k];
     }
     // back substitution: y_p = V^-1 (g_p - sum_i E_i^T y_red)
@@ -584,6 +588,102 @@ class BaOracle {
       }
     }
     for (double v : *y) if (!std::isfinite(v)) return false;
+    return true;
+  }
+
+  // ceres ITERATIVE_SCHUR with the SCHUR_JACOBI preconditioner on the reduced camera system (iterative_schur_complement_solver.cc,
+  // conjugate_gradients_solver.h of Ceres 2.2, restated): preconditioned CG from x = 0 on S y = rhs, S given by its lower triangle.
+  // The preconditioner is the inverse of the block diagonal of S, one block per reduced parameter block (camera extrinsics,
+  // shared intrinsics), each inverted through its Cholesky factor. Termination: Ceres' Q-test with q_tolerance = eta (the
+  // residual test is disabled by the Levenberg-Marquardt strategy, r_tolerance = -1), max_linear_solver_iterations, the residual
+  // recomputed from scratch every 10th iteration. Ceres multiplies with the implicit Schur complement; the product with the
+  // explicit S is the same operator up to round-off. Returns false on LINEAR_SOLVER_FAILURE; a run that hits the iteration
+  // limit or an indefinite direction keeps its current iterate (NO_CONVERGENCE is a usable step for the trust-region loop).
+  bool ConjugateGradients(const std::vector<double>& S, const std::vector<double>& b, std::vector<double>* xout) {
+    const int nr = n_red;
+    struct Blk { int off, dim; };
+    std::vector<Blk> blocks;
+    for (int g = 0; g < ng; ++g) if (intr_td[g]) blocks.push_back({intr_off[g] - n_pt_tan, intr_td[g]});
+    for (int c = 0; c < nc; ++c) if (cam_td[c]) blocks.push_back({cam_off[c] - n_pt_tan, cam_td[c]});
+    std::vector<double> Minv(blocks.size() * 81, 0.0);
+    bool pd = true;
+#pragma omp parallel for schedule(static)
+    for (int bi = 0; bi < (int)blocks.size(); ++bi) {
+      const int o = blocks[bi].off, d = blocks[bi].dim;
+      double Bk[81], e[9], col[9];
+      for (int i = 0; i < d; ++i) for (int j = 0; j < d; ++j) Bk[i * d + j] = i >= j ? S[(size_t)(o + i) * nr + o + j] : S[(size_t)(o + j) * nr + o + i];
+      for (int j = 0; j < d; ++j) {
+        for (int i = 0; i < d; ++i) e[i] = i == j ? 1.0 : 0.0;
+        if (!DenseCholeskySolve(d, Bk, e, col)) {
+#pragma omp atomic write
+          pd = false;
+        }
+        for (int i = 0; i < d; ++i) Minv[(size_t)bi * 81 + i * d + j] = col[i];
+      }
+    }
+    if (!pd) return false;
+    auto multiply = [&](const std::vector<double>& v, std::vector<double>* out) {  // out = S v, symmetric, lower triangle stored
+      out->assign(nr, 0.0);
+      std::vector<double> upper(nr, 0.0);
+#pragma omp parallel
+      {
+        std::vector<double> loc(nr, 0.0);
+#pragma omp for schedule(dynamic, 16)
+        for (int i = 0; i < nr; ++i) {
+          const double* row = &S[(size_t)i * nr];
+          double acc = 0.0;
+          const double vi = v[i];
+          for (int j = 0; j < i; ++j) { acc += row[j] * v[j]; loc[j] += row[j] * vi; }
+          (*out)[i] = acc + row[i] * vi;
+        }
+#pragma omp critical
+        for (int i = 0; i < nr; ++i) upper[i] += loc[i];
+      }
+      for (int i = 0; i < nr; ++i) (*out)[i] += upper[i];
+    };
+    auto dot = [&](const std::vector<double>& u, const std::vector<double>& v) { double a = 0.0; for (int i = 0; i < nr; ++i) a += u[i] * v[i]; return a; };
+    auto zero_or_inf = [](double v) { return v == 0.0 || std::isinf(v); };
+    std::vector<double>& x = *xout;
+    x.assign(nr, 0.0);
+    double norm_b = std::sqrt(dot(b, b));
+    if (norm_b == 0.0) return true;
+    std::vector<double> r(b), z(nr), p(nr), q, tmp(nr);
+    double rho = 1.0, Q0 = 0.0;  // Q0 = -x.(b + r) at x = 0
+    const int max_it = std::max(1, O.pcg_max_iterations);
+    for (int it = 1;; ++it) {
+      for (size_t bi = 0; bi < blocks.size(); ++bi) {
+        const int o = blocks[bi].off, d = blocks[bi].dim;
+        for (int i = 0; i < d; ++i) {
+          double a = 0.0;
+          for (int j = 0; j < d; ++j) a += Minv[bi * 81 + i * d + j] * r[o + j];
+          z[o + i] = a;
+        }
+      }
+      const double last_rho = rho;
+      rho = dot(r, z);
+      if (zero_or_inf(rho)) return false;
+      if (it == 1) p = z;
+      else {
+        const double beta = rho / last_rho;
+        if (zero_or_inf(beta)) return false;
+        for (int i = 0; i < nr; ++i) p[i] = z[i] + beta * p[i];
+      }
+      multiply(p, &q);
+      const double pq = dot(p, q);
+      if (pq <= 0.0 || std::isinf(pq)) break;  // NO_CONVERGENCE: keep x
+      const double alpha = rho / pq;
+      if (std::isinf(alpha)) return false;
+      for (int i = 0; i < nr; ++i) x[i] += alpha * p[i];
+      if (it % 10 == 0) { multiply(x, &tmp); for (int i = 0; i < nr; ++i) r[i] = b[i] - tmp[i]; }
+      else for (int i = 0; i < nr; ++i) r[i] -= alpha * q[i];
+      double Q1 = 0.0;
+      for (int i = 0; i < nr; ++i) Q1 -= x[i] * (b[i] + r[i]);
+      const double zeta = it * (Q1 - Q0) / Q1;
+      ++n_cg_iterations;
+      if (zeta < O.pcg_eta) break;
+      Q0 = Q1;
+      if (it >= max_it) break;
+    }
     return true;
   }
 
@@ -932,7 +1032,7 @@ class BaOracle {
     sum->num_iterations = iteration;
     sum->final_cost = min_cost + fixed_cost;
     sum->success = sum->termination_type != THB_TERM_FAILURE;
-    sum->num_jacobian_evaluations = n_jac_eval; sum->num_cost_evaluations = n_cost_eval; sum->num_linear_solves = n_solves;
+    sum->num_jacobian_evaluations = n_jac_eval; sum->num_cost_evaluations = n_cost_eval; sum->num_linear_solves = n_solves; sum->num_linear_solver_iterations = n_cg_iterations;
     sum->solve_time_in_seconds = elapsed();
     if (sum->success) {
       std::memcpy(P.cam_ext, x.cam.data(), sizeof(double) * x.cam.size());
@@ -953,7 +1053,7 @@ class BaOracle {
   bool is_constrained = false;
   std::vector<double> res, Jc, Ji, Jp, grad, scale;
   double x_cost = 0.0, gradient_max_norm = 0.0;
-  int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0;
+  int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0, n_cg_iterations = 0;
 };
 
 }  // namespace
@@ -973,7 +1073,7 @@ void oracle_ba_default_options(ThbBaOptions* o) {
   o->max_trust_region_radius = 1e12; o->initial_trust_region_radius = 1e4;
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3;
   o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->max_solver_time_in_seconds = 3600.0;
-  o->pcg_tolerance = 1e-12; o->pcg_max_iterations = 500;
+  o->pcg_eta = 0.1; o->pcg_max_iterations = 500;
 }
 
 int oracle_ba_solve(const ThbBaProblem* p, const ThbBaOptions* o, ThbBaSummary* s) {

@@ -71,7 +71,7 @@ class ThbBaOptions(C.Structure):
         ("max_trust_region_radius", C.c_double), ("initial_trust_region_radius", C.c_double),
         ("min_trust_region_radius", C.c_double), ("min_relative_decrease", C.c_double),
         ("min_lm_diagonal", C.c_double), ("max_lm_diagonal", C.c_double),
-        ("max_solver_time_in_seconds", C.c_double), ("pcg_tolerance", C.c_double),
+        ("max_solver_time_in_seconds", C.c_double), ("pcg_eta", C.c_double),
         ("pcg_max_iterations", C.c_int32), ("reserved0", C.c_int32),
     ]
 
@@ -86,7 +86,7 @@ class ThbBaSummary(C.Structure):
         ("setup_time_in_seconds", C.c_double), ("solve_time_in_seconds", C.c_double),
         ("ms_jacobian", C.c_double), ("ms_normal", C.c_double), ("ms_solve", C.c_double),
         ("ms_update", C.c_double),
-        ("iter_log_count", C.c_int32), ("reserved0", C.c_int32),
+        ("iter_log_count", C.c_int32), ("num_linear_solver_iterations", C.c_int32),
         ("iter_cost", C.c_double * THB_MAX_ITER_LOG), ("iter_radius", C.c_double * THB_MAX_ITER_LOG),
     ]
 

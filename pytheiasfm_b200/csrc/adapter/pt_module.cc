@@ -296,8 +296,8 @@ ThbBaOptions MapOptions(const BundleAdjustmentOptions& o, bool force_no_inner) {
   opt.parameter_tolerance = o.parameter_tolerance; opt.max_trust_region_radius = o.max_trust_region_radius;
   opt.max_solver_time_in_seconds = o.max_solver_time_in_seconds; opt.verbose = o.verbose;
   opt.linear_solver = THB_SOLVER_SCHUR_CHOLESKY;                           // every exact ceres solver type maps here
-  if (o.linear_solver_type == ITERATIVE_SCHUR || o.linear_solver_type == CGNR)
-    throw std::runtime_error("iterative linear solvers are not implemented; use SPARSE_SCHUR / DENSE_SCHUR / DENSE_QR");
+  if (o.linear_solver_type == ITERATIVE_SCHUR) opt.linear_solver = THB_SOLVER_SCHUR_PCG;  // SCHUR_JACOBI, ceres' default eta / iteration cap
+  if (o.linear_solver_type == CGNR) throw std::runtime_error("CGNR is not implemented; use ITERATIVE_SCHUR or an exact Schur solver");
   return opt;
 }
 

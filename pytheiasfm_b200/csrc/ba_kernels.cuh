@@ -15,7 +15,7 @@ enum { SC_COST_X = 0, SC_COST_CAND = 1, SC_STEP2 = 2, SC_XNEW2 = 3, SC_GTD = 4, 
 // parameter count keep zero Jacobian columns and a unit diagonal, so their step is exactly zero.
 constexpr int NI = 9;
 constexpr int MAX_VG = 8;
-enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_EVAL_INNER = 4, FL_COUNT = 8 };
+enum { FL_EVAL_X = 0, FL_EVAL_CAND = 1, FL_CHOL = 2, FL_POINT = 3, FL_EVAL_INNER = 4, FL_PCG_ITERS = 5, FL_COUNT = 8 };
 
 // ---------------------------------------------------------------------------------------------
 // Problem setup on the device (ValidateAndCreate): what BundleAdjuster::AddView/AddTrack decide while walking the

@@ -21,6 +21,7 @@
 #include "inner_iter.cuh"
 #include "ba_setup.cuh"
 #include "dense_chol.cuh"
+#include "schur_pcg.cuh"
 
 namespace thb {
 namespace {
@@ -148,6 +149,8 @@ struct ThbBaSession {
   int* h_flag = nullptr;     // pinned
   void* d_flush = nullptr;
   DenseChol chol;
+  SchurPcg pcg;  // THB_SOLVER_SCHUR_PCG: conjugate gradients on the S that chol.A holds
+  bool use_pcg = false;
   // trust-region state (ceres TrustRegionMinimizer / LevenbergMarquardtStrategy)
   double radius = 1e4, decrease_factor = 2.0;
   double x_cost = 0.0, x_norm = 0.0, min_cost = 0.0, fixed_cost = 0.0, gradient_max_norm = 0.0;
@@ -175,6 +178,7 @@ namespace {
 void FreeSession(ThbBaSession* s) {
   if (!s) return;
   s->chol.Free(s->st);
+  if (s->use_pcg) s->pcg.Free(s->st);
   s->arena.Release();
   g_pinned.Put(s->h_block);
   s->t_jac.Free(); s->t_normal.Free(); s->t_solve.Free(); s->t_update.Free();
@@ -332,6 +336,7 @@ int ReadScalars(ThbBaSession* s) {
   THB_CUDA_CHECK(cudaMemcpyAsync(s->h_scal, s->d_scal, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, s->st));
   THB_CUDA_CHECK(cudaMemcpyAsync(s->h_flag, s->d_flag, sizeof(int) * FL_COUNT, cudaMemcpyDeviceToHost, s->st));
   THB_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  s->sum.num_linear_solver_iterations = s->h_flag[FL_PCG_ITERS];
   s->sum.ms_jacobian += s->t_jac.CollectMs();
   s->sum.ms_normal += s->t_normal.CollectMs();
   s->sum.ms_solve += s->t_solve.CollectMs();
@@ -440,7 +445,10 @@ int SolveAndStep(ThbBaSession* s) {
     ++s->sum.gpu_launches;
     s->t_normal.End();
     s->t_solve.Begin();
-    if (s->chol.FactorAndSolve(s->st, s->d_flag + FL_CHOL, &s->sum.gpu_launches) != THB_OK) return THB_E_CUDA;
+    if (s->use_pcg) {
+      if (s->pcg.Solve(s->st, s->chol.A, s->chol.ld, s->chol.RhsRow(), s->chol.x, s->opt.pcg_eta, s->opt.pcg_max_iterations, s->d_flag + FL_CHOL,
+                       s->d_flag + FL_PCG_ITERS, &s->sum.gpu_launches) != THB_OK) return THB_E_CUDA;
+    } else if (s->chol.FactorAndSolve(s->st, s->d_flag + FL_CHOL, &s->sum.gpu_launches) != THB_OK) return THB_E_CUDA;
     s->t_solve.End();
   } else {
     THB_CUDA_CHECK(cudaMemsetAsync(s->chol.x, 0, sizeof(double) * s->chol.n_pad, s->st));
@@ -749,7 +757,9 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   if (P->memory_space != THB_MEM_HOST && P->memory_space != THB_MEM_DEVICE) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad memory_space");
   if (P->num_observations > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->pts || !P->obs_cam || !P->obs_pt || !P->obs_xy))
     THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
-  if (O->linear_solver != THB_SOLVER_SCHUR_CHOLESKY) THB_FAIL(THB_E_UNSUPPORTED, "only THB_SOLVER_SCHUR_CHOLESKY is implemented");
+  if (O->linear_solver != THB_SOLVER_SCHUR_CHOLESKY && O->linear_solver != THB_SOLVER_SCHUR_PCG) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad linear_solver");
+  if (O->linear_solver == THB_SOLVER_SCHUR_PCG && (!(O->pcg_eta > 0.0) || O->pcg_max_iterations < 1))
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "pcg_eta must be positive and pcg_max_iterations at least 1");
   if (O->loss_function_type < THB_LOSS_TRIVIAL || O->loss_function_type > THB_LOSS_TRUNCATED) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad loss type");
 
   ThbBaSession* s = new ThbBaSession();
@@ -883,6 +893,14 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
     THB_TRY(M.Get(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
   }
   THB_TRY(s->chol.Init(std::max(1, s->n_red), st));
+  s->use_pcg = O->linear_solver == THB_SOLVER_SCHUR_PCG;
+  if (s->use_pcg) {  // SCHUR_JACOBI: one diagonal block per camera and per shared intrinsics block
+    std::vector<int2> blocks;
+    for (int c = 0; c < nc; ++c) blocks.push_back(make_int2(6 * c, 6));
+    for (int sl = 0; sl < s->nvg; ++sl) blocks.push_back(make_int2(6 * nc + NI * sl, NI));
+    static_assert(NI <= kPcgMaxBlockDim, "preconditioner block size");
+    THB_TRY(s->pcg.Init(s->chol.n_pad, blocks, st));
+  }
   // the preprocessor disables inner iterations on programs with fewer than two parameter blocks (ceres)
   s->inner_enabled = O->use_inner_iterations != 0 && h_setup[SF_NUM_CAM_VAR] + h_setup[SF_NUM_PT_VAR] + s->nvg >= 2;
   if (s->inner_enabled) {
@@ -1005,7 +1023,7 @@ void thb_ba_default_options(ThbBaOptions* o) {
   o->max_trust_region_radius = 1e12; o->initial_trust_region_radius = 1e4;
   o->min_trust_region_radius = 1e-32; o->min_relative_decrease = 1e-3;
   o->min_lm_diagonal = 1e-6; o->max_lm_diagonal = 1e32; o->max_solver_time_in_seconds = 3600.0;
-  o->pcg_tolerance = 1e-12; o->pcg_max_iterations = 500;
+  o->pcg_eta = 0.1; o->pcg_max_iterations = 500;
 }
 
 int thb_ba_create(const ThbBaProblem* problem, const ThbBaOptions* options, void* cuda_stream, ThbBaSession** session) {

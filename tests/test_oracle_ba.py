@@ -201,3 +201,21 @@ def test_inner_iterations_coordinate_descent(oracle):
     o.use_inner_iterations = 1
     rb = oracle.ba_solve(b, o)
     assert ra["iter_cost"] == rb["iter_cost"]
+
+
+def test_iterative_schur_reaches_the_exact_minimum(oracle):
+    """ITERATIVE_SCHUR + SCHUR_JACOBI restated (ceres conjugate_gradients_solver.h): inexact Newton steps, so more LM iterations
+    than the exact solver, the same minimum; a tighter forcing term eta follows the exact trajectory more closely."""
+    for make in (lambda: synthetic.config_c1()[0], lambda: synthetic.config_c2(scale=0.02)[0]):
+        exact = oracle.ba_solve(make(), oracle.default_options())
+        o = oracle.default_options(); o.linear_solver = capi.SOLVER_SCHUR_PCG
+        it = oracle.ba_solve(make(), o)
+        assert it["rc"] == 0 and it["success"] == 1 and it["termination_type"] == capi.TERM_CONVERGENCE
+        assert it["num_linear_solver_iterations"] > 0 and exact["num_linear_solver_iterations"] == 0
+        assert abs(it["final_cost"] - exact["final_cost"]) <= 1e-4 * exact["final_cost"]
+        assert np.all(np.diff(it["iter_cost"]) <= 0)
+        o.pcg_eta = 1e-8
+        tight = oracle.ba_solve(make(), o)
+        assert tight["num_linear_solver_iterations"] > it["num_linear_solver_iterations"]
+        n = min(len(tight["iter_cost"]), len(exact["iter_cost"]))
+        np.testing.assert_allclose(tight["iter_cost"][:n], exact["iter_cost"][:n], rtol=1e-3)

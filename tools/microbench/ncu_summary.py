@@ -21,6 +21,9 @@ for r in rows[2:]:
     for w in WANT:
         if w in ix:
             print("  %-70s %s %s" % (w, r[ix[w]], units[ix[w]]))
+    for h in hdr:  # DMMA runs on the tensor pipe: its activity is not in sm__pipe_fp64_*
+        if ("pipe_tensor_cycles_active_realtime.avg.pct" in h or "subpipe_dmma_cycles_active.avg" in h) and r[ix[h]]:
+            print("  %-70s %s %s" % (h.split("TriageCompute.")[-1], r[ix[h]], units[ix[h]]))
     st = {h.split("issue_stalled_")[1].replace("_per_issue_active.ratio", ""): float(r[ix[h]]) for h in hdr
           if "issue_stalled" in h and h.endswith("per_issue_active.ratio") and "not_issued" not in h and r[ix[h]]}
     print("  stalled warps per issue: " + " ".join("%s=%.2f" % kv for kv in sorted(st.items(), key=lambda kv: -kv[1])[:8]))
