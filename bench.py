@@ -647,6 +647,28 @@ def run_ba_leg(args, lib, rank, local_rank, world, stream, K, W):
     fp64_peak = C.c_double(0.0)
     capi.check(lib.thb_fp64_peak_tflops(5, C.byref(fp64_peak), sptr))
 
+    # ---- the reference's other solver option on the same workload: ITERATIVE_SCHUR (THB_SOLVER_SCHUR_PCG), complete solves ----
+    def solve_pcg():
+        restore_dev()
+        summ_ = capi.ThbBaSummary()
+        opts_ = make_options(capi.default_options(lib), 100)
+        opts_.linear_solver = capi.SOLVER_SCHUR_PCG
+        capi.check(lib.thb_ba_solve(C.byref(pd), C.byref(opts_), C.byref(summ_), sptr))
+        return summ_.as_dict()
+    solve_pcg()
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    pcg_sums = [solve_pcg() for _ in range(5)]
+    p1.record(stream)
+    torch.cuda.synchronize()
+    pcg_ms = p0.elapsed_time(p1) / len(pcg_sums)
+    ps = pcg_sums[0]
+    pcg = {"linear_solver": "ITERATIVE_SCHUR + SCHUR_JACOBI (eta 0.1), complete solves to the reference's default tolerances, inputs in HBM",
+           "ms_per_solve": pcg_ms, "iterations_per_solve": ps["num_iterations"], "cg_iterations_per_solve": ps["num_linear_solver_iterations"],
+           "iterations_per_s": ps["num_iterations"] / (pcg_ms * 1e-3), "ms_linear_solve": ps["ms_solve"] / max(1, ps["num_linear_solves"]),
+           "final_cost": ps["final_cost"], "exact_solver_ms_per_solve": ms / len(sums)}
+
     # ---- end-to-end arm: the call a user makes, pinned HOST buffers, H2D + setup + iterations + D2H timed ----
     pin = {k: (None if v is None else torch.from_numpy(v.copy()).pin_memory()) for k, v in prob.a.items()}
     solve_host, restore_host = make_arm(pin, capi.THB_MEM_HOST)
@@ -699,6 +721,8 @@ def run_ba_leg(args, lib, rank, local_rank, world, stream, K, W):
         "final_cost": summ["final_cost"], "initial_cost": summ["initial_cost"],
         "termination_type": summ["termination_type"], "clocks": sampler.summary(),
     }
+    line["iterative_schur"] = pcg
+    assert abs(pcg["final_cost"] - summ["final_cost"]) <= 1e-4 * summ["final_cost"], ("ITERATIVE_SCHUR ends at a different minimum", pcg["final_cost"])
     if not args.no_cpu_baseline and world == 1:
         cb = cpu_baseline(prob, iters=2)
         ours, theirs = summ["iter_cost"][:3], cb.pop("iter_cost")[:3]
