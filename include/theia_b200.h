@@ -503,6 +503,26 @@ int thb_set_outlier_tracks_batch(const ThbBaProblem* problem, double max_inlier_
                                  double min_triangulation_angle_degrees, int32_t* status, int32_t* num_removed, void* cuda_stream);
 
 /*
+ * theia::SelectGoodTracksForBundleAdjustment (sfm/select_good_tracks_for_bundle_adjustment.cc:263-325): the subset of tracks a
+ * large bundle adjustment optimises. The problem holds the estimated views and estimated tracks with their observations
+ * (the reference skips the others, :94-96,132-136,174-176). Per track: truncated length min(#views, long_track_length_threshold)
+ * and mean squared reprojection error over all its views (:80-107). Stage 1 (:152-195): in every selected view the image is cut
+ * into grid_cell_size_pixels cells ((int)(x / size), (int)(y / size), truncation as the reference's cast) and the track with the
+ * smallest (truncated length, mean error) pair of each cell is chosen - std::pair's operator<, as the reference's
+ * CompareGridCellElements. Stage 2 (:199-254), view after view: a view with fewer than min_num_optimized_tracks_per_view
+ * chosen tracks gets its not-yet-chosen tracks in ascending track order until it has enough (std::partial_sort on
+ * pair<TrackId, statistics> orders by TrackId first). Where the reference's order is unspecified (unordered containers: the
+ * order of the views in stage 2, ties between equal statistics in a cell) this entry uses ascending index order: views and
+ * tracks of the problem must be in ascending ViewId / TrackId order to reproduce a run of the reference that iterates
+ * that way.
+ * cam_selected [num_cameras]: the view_ids subset of the second overload (NULL = every view); selected [num_points]: in / out,
+ * the caller's tracks_to_optimize (non-zero = chosen; normally zero on entry). *num_selected may be NULL. Any memory space.
+ */
+int thb_select_good_tracks_batch(const ThbBaProblem* problem, const uint8_t* cam_selected, int32_t long_track_length_threshold,
+                                 int32_t grid_cell_size_pixels, int32_t min_num_optimized_tracks_per_view, uint8_t* selected,
+                                 int32_t* num_selected, void* cuda_stream);
+
+/*
  * theia::TriangulateMidpoint (sfm/triangulation/triangulation.cc:130-157) for a batch of tracks: track t owns the rays
  * ray_offset[t] .. ray_offset[t+1]-1 (origin and direction, 3 doubles each; directions as the caller passes them, the
  * reference does not normalise). A = sum (I4 - d d^T) with d = (direction, 0), b = sum (I4 - d d^T) (origin, 1), 4x4

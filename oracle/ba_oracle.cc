@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <map>
 #include <vector>
 
 #include "../include/theia_b200.h"
@@ -1161,6 +1162,61 @@ int oracle_set_outlier_tracks(const ThbBaProblem* p, double max_err, double min_
     removed += st > 0;
   }
   return removed;
+}
+
+// theia::SelectGoodTracksForBundleAdjustment (sfm/select_good_tracks_for_bundle_adjustment.cc:263-325) over the flat problem
+// (estimated views and tracks only). Unspecified orders of the reference (unordered containers) are fixed to ascending index:
+// see include/theia_b200.h. Returns the number of chosen tracks.
+int oracle_select_good_tracks(const ThbBaProblem* p, const uint8_t* cam_selected, int long_thr, int cell_size, int min_per_view, uint8_t* selected) {
+  if (!p || !selected || cell_size <= 0) return THB_E_INVALID_ARGUMENT;
+  const int nc = p->num_cameras, np = p->num_points, no = p->num_observations;
+  // ComputeStatisticsForTrack (:80-107): truncated length, mean squared reprojection error over every view of the track
+  std::vector<int> len(np, 0);
+  std::vector<double> sum(np, 0.0), mean(np, 0.0);
+  for (int i = 0; i < no; ++i) {
+    const int c = p->obs_cam[i], g = p->cam_group[c], t = p->obs_pt[i];
+    const double* X = p->pts + 4 * (size_t)t;
+    const double* ext = p->cam_ext + 6 * (size_t)c;
+    const double adj[3] = {X[0] - X[3] * ext[0], X[1] - X[3] * ext[1], X[2] - X[3] * ext[2]};
+    double pc[3], pix[2] = {0, 0};
+    oracle::AngleAxisRotatePoint(ext + 3, adj, pc);
+    oracle::ProjectByModel<double>(p->intr_model[g], p->intr + (size_t)g * THB_INTR_STRIDE, pc, pix);
+    const double ex = pix[0] - p->obs_xy[2 * (size_t)i], ey = pix[1] - p->obs_xy[2 * (size_t)i + 1];
+    sum[t] += ex * ex + ey * ey;
+    ++len[t];
+  }
+  for (int t = 0; t < np; ++t) { mean[t] = sum[t] / static_cast<double>(len[t]); len[t] = std::min(len[t], long_thr); }
+  std::vector<std::vector<int>> by_cam(nc);
+  for (int i = 0; i < no; ++i) by_cam[p->obs_cam[i]].push_back(i);
+  const double inv = 1.0 / cell_size;
+  // SelectBestTracksFromEachImageGridCell (:152-195): min over std::pair<int, double> in every occupied cell
+  for (int c = 0; c < nc; ++c) {
+    if (cam_selected && !cam_selected[c]) continue;
+    std::map<std::pair<int, int>, int> best;  // cell -> observation
+    for (int i : by_cam[c]) {
+      const std::pair<int, int> cell(static_cast<int>(p->obs_xy[2 * (size_t)i] * inv), static_cast<int>(p->obs_xy[2 * (size_t)i + 1] * inv));
+      auto it = best.find(cell);
+      if (it == best.end()) { best[cell] = i; continue; }
+      const int a = p->obs_pt[i], b = p->obs_pt[it->second];
+      if (std::make_pair(len[a], mean[a]) < std::make_pair(len[b], mean[b])) it->second = i;
+    }
+    for (const auto& kv : best) selected[p->obs_pt[kv.second]] = 1;
+  }
+  // SelectTopRankedTracksInView (:199-254): partial_sort on pair<TrackId, statistics> = ascending track id
+  for (int c = 0; c < nc; ++c) {
+    if (cam_selected && !cam_selected[c]) continue;
+    std::vector<int> cand;
+    int n_opt = 0;
+    const int n_est = (int)by_cam[c].size();
+    for (int i : by_cam[c]) { if (selected[p->obs_pt[i]]) ++n_opt; else cand.push_back(p->obs_pt[i]); }
+    if (n_opt >= min_per_view || n_opt == n_est) continue;
+    const int needed = std::min(min_per_view - n_opt, n_est - n_opt);
+    std::sort(cand.begin(), cand.end());
+    for (int k = 0; k < needed; ++k) selected[cand[k]] = 1;
+  }
+  int count = 0;
+  for (int t = 0; t < np; ++t) count += selected[t] != 0;
+  return count;
 }
 
 // Thread control for the timed baselines: torchrun exports OMP_NUM_THREADS=1, the CPU arm must say how many it used.

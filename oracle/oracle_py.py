@@ -143,6 +143,16 @@ def set_outlier_tracks(prob, max_err, min_angle_deg):
     return removed, status
 
 
+def select_good_tracks(prob, long_thr, cell_size, min_per_view, cam_selected=None, selected=None):
+    lib = load()
+    lib.oracle_select_good_tracks.argtypes = [C.POINTER(capi.ThbBaProblem), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    sel = np.zeros(prob.num_points, np.uint8) if selected is None else np.ascontiguousarray(selected, np.uint8).copy()
+    cs = None if cam_selected is None else np.ascontiguousarray(cam_selected, np.uint8)
+    p = prob.struct()
+    n = lib.oracle_select_good_tracks(C.byref(p), None if cs is None else _vp(cs), long_thr, cell_size, min_per_view, _vp(sel))
+    return n, sel
+
+
 def p3p(feat, world):
     """feat [count,3,2], world [count,3,3] -> (R [count,4,3,3], t [count,4,3], n [count])"""
     feat = np.ascontiguousarray(feat, np.float64); world = np.ascontiguousarray(world, np.float64)

@@ -251,6 +251,9 @@ def load_library():
     lib.thb_fp64_peak_tflops.restype = C.c_int
     lib.thb_set_outlier_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     lib.thb_set_outlier_tracks_batch.restype = C.c_int
+    lib.thb_select_good_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                                 C.POINTER(C.c_int32), C.c_void_p]
+    lib.thb_select_good_tracks_batch.restype = C.c_int
     lib.thb_two_view_default_options.argtypes = [C.POINTER(ThbTwoViewOptions)]
     lib.thb_two_view_default_options.restype = None
     for name in ("thb_estimate_two_view_info_batch", "thb_verify_two_view_matches_batch"):

@@ -960,6 +960,72 @@ PYBIND11_MODULE(_pt, m) {
     for (size_t i = 0; i < f.track_ids.size(); ++i) if (status[i] > 0) r.tracks.at(f.track_ids[i]).estimated = false;
     return (int)removed;
   });
+  // SelectGoodTracksForBundleAdjustment (sfm_wrapper.cc:28-44 -> select_good_tracks_for_bundle_adjustment.cc:263-325) over
+  // thb_select_good_tracks_batch: views and tracks flattened in ascending id order (the order the C-ABI entry fixes where the
+  // reference's unordered containers leave it open). Views of view_ids that are not estimated are skipped.
+  sfm.def("SelectGoodTracksForBundleAdjustment", [](const Reconstruction& r, const std::unordered_set<ViewId>& view_ids, int long_track_length_threshold,
+                                                  int image_grid_cell_size_pixels, int min_num_optimized_tracks_per_view) {
+    Flat f;
+    std::vector<ViewId> views;
+    for (const auto& kv : r.views) if (kv.second.estimated) views.push_back(kv.first);
+    std::sort(views.begin(), views.end());
+    std::vector<uint8_t> cam_selected;
+    for (ViewId v : views) {
+      const View& view = r.views.at(v);
+      f.view_index[v] = (int)f.view_ids.size(); f.view_ids.push_back(v);
+      cam_selected.push_back(view_ids.count(v) ? 1 : 0);
+      f.cam_ext.insert(f.cam_ext.end(), view.camera.ext, view.camera.ext + 6);
+      Intrinsics* in = view.camera.intr.get();
+      if (!f.group_index.count(in)) {
+        f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
+        f.intr_model.push_back(in->model);
+        f.intr.insert(f.intr.end(), in->params, in->params + THB_INTR_STRIDE);
+      }
+      f.cam_group.push_back(f.group_index[in]);
+    }
+    std::vector<TrackId> tracks;                                     // estimated tracks seen by a selected view (:118-141)
+    for (const auto& kv : r.tracks) {
+      if (!kv.second.estimated) continue;
+      bool seen = false;
+      for (ViewId v : kv.second.views) if (view_ids.count(v) && f.view_index.count(v)) { seen = true; break; }
+      if (seen) tracks.push_back(kv.first);
+    }
+    std::sort(tracks.begin(), tracks.end());
+    for (TrackId t : tracks) {
+      const Track& tr = r.tracks.at(t);
+      const int pi = (int)f.track_ids.size();
+      f.track_ids.push_back(t);
+      f.pts.insert(f.pts.end(), tr.point, tr.point + 4);
+      std::vector<ViewId> obs(tr.views.begin(), tr.views.end());
+      std::sort(obs.begin(), obs.end());
+      for (ViewId v : obs) {
+        auto vi = f.view_index.find(v);
+        if (vi == f.view_index.end()) continue;                      // not estimated (:94-96)
+        const Feature& feat = r.views.at(v).features.at(t);
+        f.obs_cam.push_back(vi->second); f.obs_pt.push_back(pi);
+        f.obs_xy.push_back(feat.point[0]); f.obs_xy.push_back(feat.point[1]);
+      }
+    }
+    std::unordered_set<TrackId> out;
+    if (f.track_ids.empty()) return std::make_tuple(true, out);
+    ThbBaProblem p;
+    std::memset(&p, 0, sizeof(p));
+    p.num_cameras = (int)f.view_ids.size(); p.num_groups = (int)f.groups.size(); p.num_points = (int)f.track_ids.size();
+    p.num_observations = (int)f.obs_cam.size(); p.memory_space = THB_MEM_HOST;
+    p.cam_ext = f.cam_ext.data(); p.cam_group = f.cam_group.data(); p.intr = f.intr.data(); p.intr_model = f.intr_model.data();
+    p.pts = f.pts.data(); p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data();
+    std::vector<uint8_t> selected(f.track_ids.size(), 0);
+    int32_t count = 0;
+    int rc;
+    {
+      py::gil_scoped_release nogil;
+      rc = thb_select_good_tracks_batch(&p, cam_selected.data(), long_track_length_threshold, image_grid_cell_size_pixels,
+                                        min_num_optimized_tracks_per_view, selected.data(), &count, nullptr);
+    }
+    Check(rc);
+    for (size_t i = 0; i < selected.size(); ++i) if (selected[i]) out.insert(f.track_ids[i]);
+    return std::make_tuple(true, out);
+  });
   sfm.def("BundleAdjustTrack", [](Reconstruction& r, const BundleAdjustmentOptions& o, TrackId t) {
     BundleAdjustmentSummary s = RunBa(o, {}, {t}, &r, true);   // no inner iterations (:267)
     UpdateInverseDepth({t}, &r);

@@ -36,4 +36,16 @@ int GroupByKey(const int* d_key, int no, int nkeys, int* d_count, int* d_perm, c
   return THB_OK;
 }
 
+int SortPairsU64(const unsigned long long* d_key_in, unsigned long long* d_key_out, const int* d_val_in, int* d_val_out, int n, cudaStream_t st) {
+  if (n <= 0) return THB_OK;
+  size_t bytes = 0;
+  THB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_key_in, d_key_out, d_val_in, d_val_out, n, 0, 64, st));
+  void* d_tmp = nullptr;
+  THB_CUDA_CHECK(cudaMallocAsync(&d_tmp, bytes + 256, st));
+  const cudaError_t e = cub::DeviceRadixSort::SortPairs(d_tmp, bytes, d_key_in, d_key_out, d_val_in, d_val_out, n, 0, 64, st);
+  cudaFreeAsync(d_tmp, st);
+  THB_CUDA_CHECK(e);
+  return THB_OK;
+}
+
 }  // namespace thb

@@ -12,6 +12,8 @@ namespace thb {
 // exclusive prefix sum (d_count[nkeys] = no). d_perm[q] = caller index of the q-th observation in key-major order; equal
 // keys keep the caller's order (stable), so the summation order of every block is the caller's observation order.
 int GroupByKey(const int* d_key, int no, int nkeys, int* d_count, int* d_perm, cudaStream_t st);
+// Stable sort of (key, value) pairs by a 64-bit key.
+int SortPairsU64(const unsigned long long* d_key_in, unsigned long long* d_key_out, const int* d_val_in, int* d_val_out, int n, cudaStream_t st);
 
 }  // namespace thb
 #endif

@@ -1375,6 +1375,93 @@ int thb_set_outlier_tracks_batch(const ThbBaProblem* P, double max_err, double m
   return THB_OK;
 }
 
+int thb_select_good_tracks_batch(const ThbBaProblem* P, const uint8_t* cam_selected, int32_t long_thr, int32_t cell_size, int32_t min_per_view,
+                                 uint8_t* selected, int32_t* num_selected, void* cuda_stream) {
+  if (!P || !selected) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem or selected");
+  if (cell_size <= 0 || long_thr < 0 || min_per_view < 0) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad grid cell size / thresholds");
+  int rc = CheckDevice();
+  if (rc != THB_OK) return rc;
+  const int nc = P->num_cameras, ng = P->num_groups, np = P->num_points, no = P->num_observations, sp = P->memory_space;
+  if (nc < 0 || ng < 0 || np < 0 || no < 0 || (sp != THB_MEM_HOST && sp != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad size or memory space");
+  if (nc >= (1 << 22)) THB_FAIL(THB_E_UNSUPPORTED, "more than 4M views");
+  if (num_selected) *num_selected = 0;
+  if (np == 0) return THB_OK;
+  if (!P->pts || (no > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->obs_cam || !P->obs_pt || !P->obs_xy)))
+    THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool host = sp == THB_MEM_HOST;
+  const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  ConfigurePoolOnce();
+  struct ScopedArena : Arena { ~ScopedArena() { Release(); } } M;
+  M.st = st;
+  std::vector<int> h_model;
+  if ((rc = FetchToHost(P->intr_model, ng, sp, &h_model)) != THB_OK) return rc;
+  for (int g = 0; g < ng; ++g) if (num_intrinsics(h_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
+  BaState X{};
+  int *d_group = nullptr, *d_model = nullptr, *d_start = nullptr, *d_perm = nullptr, *d_oc = nullptr, *d_op = nullptr, *d_flags = nullptr, *d_cstart = nullptr,
+      *d_used = nullptr, *d_len = nullptr, *d_iota = nullptr, *d_sorted_obs = nullptr, *d_cperm = nullptr;
+  uint8_t *d_cc = nullptr, *d_sel = nullptr, *d_csel = nullptr;
+  double2* d_xy = nullptr;
+  double* d_mean = nullptr;
+  unsigned long long *d_ckey = nullptr, *d_tkey = nullptr, *d_ckey_s = nullptr, *d_tkey_s = nullptr;
+  const size_t no1 = std::max(no, 1);
+  if ((rc = M.Get(&X.cam, (size_t)nc * 6)) != THB_OK || (rc = M.Get(&X.camd, (size_t)nc * CAMD)) != THB_OK || (rc = M.Get(&X.intr, (size_t)ng * KS)) != THB_OK ||
+      (rc = M.Get(&X.pts, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_group, nc)) != THB_OK || (rc = M.Get(&d_model, ng)) != THB_OK ||
+      (rc = M.Get(&d_start, np + 1)) != THB_OK || (rc = M.Get(&d_perm, no1)) != THB_OK || (rc = M.Get(&d_oc, no1)) != THB_OK || (rc = M.Get(&d_op, no1)) != THB_OK ||
+      (rc = M.Get(&d_xy, no1)) != THB_OK || (rc = M.Get(&d_cc, std::max(nc, 1))) != THB_OK || (rc = M.Get(&d_sel, np)) != THB_OK || (rc = M.Get(&d_csel, std::max(nc, 1))) != THB_OK ||
+      (rc = M.Get(&d_flags, SF_COUNT + 1)) != THB_OK || (rc = M.Get(&d_cstart, nc + 1)) != THB_OK || (rc = M.Get(&d_used, std::max(ng, 1))) != THB_OK ||
+      (rc = M.Get(&d_len, np)) != THB_OK || (rc = M.Get(&d_mean, np)) != THB_OK || (rc = M.Get(&d_iota, no1)) != THB_OK || (rc = M.Get(&d_sorted_obs, no1)) != THB_OK ||
+      (rc = M.Get(&d_cperm, no1)) != THB_OK || (rc = M.Get(&d_ckey, no1)) != THB_OK || (rc = M.Get(&d_tkey, no1)) != THB_OK || (rc = M.Get(&d_ckey_s, no1)) != THB_OK ||
+      (rc = M.Get(&d_tkey_s, no1)) != THB_OK)
+    return rc;
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * 6 * nc, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * KS * ng, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * 4 * np, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, P->cam_group, sizeof(int) * nc, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, h_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_oc, P->obs_cam, sizeof(int) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_op, P->obs_pt, sizeof(int) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_xy, P->obs_xy, sizeof(double2) * no, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_sel, selected, np, kin, st));
+  if (cam_selected) THB_CUDA_CHECK(cudaMemcpyAsync(d_csel, cam_selected, nc, kin, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, 0, std::max(nc, 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_start, 0, sizeof(int) * (np + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cstart, 0, sizeof(int) * (nc + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, sizeof(int) * std::max(ng, 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_flags, 0, sizeof(int) * (SF_COUNT + 1), st));
+  if (nc > 0) k_setup_check_groups<<<cdiv(nc, 256), 256, 0, st>>>(nc, ng, d_group, d_flags);
+  if (no > 0) k_setup_count<<<cdiv(no, 256), 256, 0, st>>>(no, nc, np, ng, d_oc, d_op, d_group, d_start, d_cstart, d_used, d_flags);
+  int h_flags[SF_COUNT + 1];
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flags[SF_BAD_GROUP]) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
+  if (h_flags[SF_BAD_INDEX]) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
+  if (no > 0) {
+    if ((rc = GroupByKey(d_op, no, np, d_start, d_perm, st)) != THB_OK) return rc;
+    if ((rc = GroupByKey(d_oc, no, nc, d_cstart, d_cperm, st)) != THB_OK) return rc;  // only the per-view offsets are used
+    k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc, nullptr, d_cc, d_group);
+    BaConst K{};
+    K.nc = nc; K.ng = ng; K.np = np; K.no = no; K.cam_group = d_group; K.intr_model = d_model; K.cam_const = d_cc; K.pt_const = nullptr;
+    K.loss_type = THB_LOSS_TRIVIAL; K.loss_width = 1.0;
+    k_track_stats<<<cdiv(np, 128), 128, 0, st>>>(K, X, d_start, d_perm, d_oc, d_xy, long_thr, d_len, d_mean);
+    k_select_keys<<<cdiv(no, 256), 256, 0, st>>>(no, d_oc, d_op, d_xy, cam_selected ? d_csel : nullptr, 1.0 / (double)cell_size, d_ckey, d_tkey, d_iota);
+    if ((rc = SortPairsU64(d_ckey, d_ckey_s, d_iota, d_sorted_obs, no, st)) != THB_OK) return rc;
+    k_select_cells<<<cdiv(no, 256), 256, 0, st>>>(no, d_ckey_s, d_sorted_obs, d_op, d_len, d_mean, d_sel);
+    if ((rc = SortPairsU64(d_tkey, d_tkey_s, d_iota, d_cperm, no, st)) != THB_OK) return rc;
+    k_select_top_ranked<<<1, 1024, 0, st>>>(nc, cam_selected ? d_csel : nullptr, d_cstart, d_tkey_s, min_per_view, d_sel);
+  }
+  int* d_count = d_flags + SF_COUNT;
+  THB_CUDA_CHECK(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+  k_count_selected<<<cdiv(np, 256), 256, 0, st>>>(np, d_sel, d_count);
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(selected, d_sel, np, host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  int h_count = 0;
+  THB_CUDA_CHECK(cudaMemcpyAsync(&h_count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (num_selected) *num_selected = h_count;
+  return THB_OK;
+}
+
 int thb_ba_evaluate(const ThbBaProblem* P, double* residuals, double* jac_cam, double* jac_intr, double* jac_pt,
                     uint8_t* ok, void* cuda_stream) {
   if (!P) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem");

@@ -297,5 +297,118 @@ __global__ void __launch_bounds__(128) k_outlier_tracks(BaConst K, BaState St, c
   if (st > 0) atomicAdd(removed, 1);
 }
 
+// ---- SelectGoodTracksForBundleAdjustment (select_good_tracks_for_bundle_adjustment.cc:263-325) --------------------------
+// ComputeStatisticsForTrack (:80-107), one thread per track: truncated length and mean squared reprojection error.
+__global__ void __launch_bounds__(128) k_track_stats(BaConst K, BaState St, const int* __restrict__ pt_start, const int* __restrict__ perm,
+                                                     const int* __restrict__ obs_cam, const double2* __restrict__ obs_xy, int long_thr,
+                                                     int* __restrict__ len, double* __restrict__ mean) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= K.np) return;
+  const int q0 = pt_start[p], q1 = pt_start[p + 1];
+  const double* Xp = St.pts + (size_t)p * 4;
+  const double X[4] = {Xp[0], Xp[1], Xp[2], Xp[3]};
+  double sum = 0.0;
+  for (int q = q0; q < q1; ++q) {
+    const int i = perm[q], c = obs_cam[i];
+    const double* cd = St.camd + (size_t)c * CAMD;
+    const double adj[3] = {X[0] - X[3] * cd[CD_C], X[1] - X[3] * cd[CD_C + 1], X[2] - X[3] * cd[CD_C + 2]};
+    double pc[3];
+    rot_apply(cd + CD_W, cd[CD_A], cd[CD_B], cd[0] * cd[0] + cd[1] * cd[1] + cd[2] * cd[2], adj, pc);
+    const int g = K.ng > 1 ? K.cam_group[c] : 0;
+    double pix[2] = {0.0, 0.0};
+    project<-1, double, double>(K.intr_model[g], St.intr + (size_t)g * KS, pc, pix);
+    const double2 xy = obs_xy[i];
+    sum += (pix[0] - xy.x) * (pix[0] - xy.x) + (pix[1] - xy.y) * (pix[1] - xy.y);
+  }
+  len[p] = min(q1 - q0, long_thr);
+  mean[p] = sum / (double)(q1 - q0);
+}
+
+// sort keys of the two passes: (view, grid cell) for stage 1, (view, track) for stage 2; views outside the subset sort last
+__global__ void k_select_keys(int no, const int* __restrict__ obs_cam, const int* __restrict__ obs_pt, const double2* __restrict__ obs_xy,
+                              const uint8_t* __restrict__ cam_sel, double inv_cell, unsigned long long* __restrict__ cell_key,
+                              unsigned long long* __restrict__ track_key, int* __restrict__ iota) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= no) return;
+  const int c = obs_cam[i];
+  iota[i] = i;
+  track_key[i] = ((unsigned long long)(unsigned)c << 32) | (unsigned)obs_pt[i];
+  if (cam_sel && !cam_sel[c]) { cell_key[i] = ~0ull; return; }
+  const double2 xy = obs_xy[i];
+  const int cx = (int)(xy.x * inv_cell), cy = (int)(xy.y * inv_cell);  // Eigen's cast<int>: truncation
+  cell_key[i] = ((unsigned long long)(unsigned)c << 42) | ((unsigned long long)((unsigned)cx & 0x1fffffu) << 21) | ((unsigned)cy & 0x1fffffu);
+}
+
+// SelectBestTracksFromEachImageGridCell (:152-195): the first observation of every (view, cell) segment walks its segment
+__global__ void k_select_cells(int no, const unsigned long long* __restrict__ key, const int* __restrict__ obs, const int* __restrict__ obs_pt,
+                               const int* __restrict__ len, const double* __restrict__ mean, uint8_t* __restrict__ selected) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= no) return;
+  const unsigned long long k = key[j];
+  if (k == ~0ull || (j > 0 && key[j - 1] == k)) return;
+  int best = obs_pt[obs[j]];
+  for (int q = j + 1; q < no && key[q] == k; ++q) {
+    const int t = obs_pt[obs[q]];
+    if (len[t] < len[best] || (len[t] == len[best] && mean[t] < mean[best])) best = t;  // std::pair<int, double>::operator<
+  }
+  selected[best] = 1;
+}
+
+// SelectTopRankedTracksInView (:199-254). The views depend on each other through the growing set, so ONE CTA walks them in
+// order; inside a view the count and the "first `needed` tracks not yet chosen, ascending track id" are block-parallel.
+__global__ void __launch_bounds__(1024) k_select_top_ranked(int nc, const uint8_t* __restrict__ cam_sel, const int* __restrict__ cam_start,
+                                                            const unsigned long long* __restrict__ track_key, int min_per_view,
+                                                            volatile uint8_t* selected) {
+  __shared__ int s_warp[32];
+  __shared__ int s_total;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  auto block_count = [&](int flag, int* rank) {  // exclusive rank of this thread's flag, returns the block total
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) s_warp[w] = __popc(m);
+    __syncthreads();
+    if (w == 0) {
+      const int v = s_warp[lane];
+      int inc = v;
+      for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+      s_warp[lane] = inc - v;
+      if (lane == 31) s_total = inc;
+    }
+    __syncthreads();
+    *rank = s_warp[w] + __popc(m & ((1u << lane) - 1));
+    const int tot = s_total;
+    __syncthreads();
+    return tot;
+  };
+  for (int c = 0; c < nc; ++c) {
+    if (cam_sel && !cam_sel[c]) continue;
+    const int q0 = cam_start[c], q1 = cam_start[c + 1], n_est = q1 - q0;
+    int n_opt = 0, rank;
+    for (int base = q0; base < q1; base += 1024) {
+      const int q = base + t;
+      n_opt += block_count(q < q1 && selected[(unsigned)(track_key[q < q1 ? q : q0] & 0xffffffffu)] != 0, &rank);
+    }
+    if (n_opt >= min_per_view || n_opt == n_est) continue;
+    const int needed = min(min_per_view - n_opt, n_est - n_opt);
+    int taken = 0;
+    for (int base = q0; base < q1 && taken < needed; base += 1024) {
+      const int q = base + t;
+      const unsigned pt = (unsigned)(track_key[q < q1 ? q : q0] & 0xffffffffu);
+      const int flag = q < q1 && selected[pt] == 0;
+      const int tot = block_count(flag, &rank);
+      if (flag && taken + rank < needed) selected[pt] = 1;
+      taken += tot;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+}
+
+__global__ void k_count_selected(int np, const uint8_t* __restrict__ selected, int* __restrict__ count) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int f = p < np && selected[p] != 0;
+  const unsigned m = __ballot_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
 }  // namespace thb
 #endif  // THB_TRACK_BA_CUH_

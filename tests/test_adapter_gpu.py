@@ -152,6 +152,22 @@ def test_SetOutlierTracksToUnestimated(gen):
     assert pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon) == 0      # idempotent
 
 
+def test_SelectGoodTracksForBundleAdjustment(gen):
+    """sfm.cc:933 / select_good_tracks_for_bundle_adjustment.cc: (success, set of track ids); every view keeps its quota, the
+    set is a strict subset when the quota is small, and BundleAdjustPartialReconstruction accepts it."""
+    vids = gen.recon.ViewIds()
+    ok, chosen = pt.sfm.SelectGoodTracksForBundleAdjustment(gen.recon, set(vids), 10, 200, 5)
+    assert ok and 0 < len(chosen) < len(gen.recon.TrackIds())
+    for v in vids:
+        seen = [t for t in gen.recon.View(v).TrackIds() if gen.recon.Track(t).IsEstimated()]
+        assert len([t for t in seen if t in chosen]) >= min(5, len(seen))
+    ok2, all_of_them = pt.sfm.SelectGoodTracksForBundleAdjustment(gen.recon, set(vids), 10, 200, 10 ** 6)
+    assert ok2 and all_of_them == {t for t in gen.recon.TrackIds() if gen.recon.Track(t).IsEstimated()}
+    opts = pt.sfm.BundleAdjustmentOptions()
+    res = pt.sfm.BundleAdjustPartialReconstruction(opts, list(vids), sorted(chosen), gen.recon)
+    assert res.success
+
+
 def _two_view_corrs(n=300, outliers=0.3, noise=1e-3, seed=65):
     rng = np.random.default_rng(seed)
     ang = np.deg2rad(10.0)

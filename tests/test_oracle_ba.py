@@ -219,3 +219,23 @@ def test_iterative_schur_reaches_the_exact_minimum(oracle):
         assert tight["num_linear_solver_iterations"] > it["num_linear_solver_iterations"]
         n = min(len(tight["iter_cost"]), len(exact["iter_cost"]))
         np.testing.assert_allclose(tight["iter_cost"][:n], exact["iter_cost"][:n], rtol=1e-3)
+
+
+def test_select_good_tracks_oracle_properties(oracle):
+    """select_good_tracks_for_bundle_adjustment.cc:263-325 restated: a subset, every view reaches its quota, a finer grid chooses
+    more tracks, a caller-provided starting set is kept, views outside the subset impose no quota."""
+    prob, _ = synthetic.make_ba_problem(14, 1500, 5, seed=3)
+    n, sel = oracle.select_good_tracks(prob, 10, 100, 50)
+    assert 0 < n < prob.num_points and n == int((sel != 0).sum())
+    for c in range(prob.num_cameras):
+        pts = prob.a["obs_pt"][prob.a["obs_cam"] == c]
+        assert (sel[pts] != 0).sum() >= min(50, len(pts))
+    n_fine, _ = oracle.select_good_tracks(prob, 10, 25, 1)
+    n_coarse, _ = oracle.select_good_tracks(prob, 10, 400, 1)
+    assert n_fine > n_coarse >= 1
+    start = np.zeros(prob.num_points, np.uint8); start[5] = 1
+    cam_sel = np.zeros(prob.num_cameras, np.uint8); cam_sel[0] = 1
+    n_sub, sel_sub = oracle.select_good_tracks(prob, 10, 100, 50, cam_selected=cam_sel, selected=start)
+    assert sel_sub[5] == 1 and n_sub < n
+    pts0 = prob.a["obs_pt"][prob.a["obs_cam"] == 0]
+    assert set(np.nonzero(sel_sub)[0]) - {5} <= set(pts0.tolist())

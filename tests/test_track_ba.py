@@ -264,3 +264,50 @@ def test_set_outlier_tracks_batch_matches_oracle(lib, oracle):
     d_status = torch.zeros(prob.num_points, dtype=torch.int32, device="cuda")
     capi.check(lib.thb_set_outlier_tracks_batch(C.byref(pd), 4.0, 3.0, C.c_void_p(d_status.data_ptr()), C.byref(removed), None))
     np.testing.assert_array_equal(d_status.cpu().numpy(), status_o)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["default", "coarse_grid_small_quota", "view_subset_preselected", "c2_scaled"])
+def test_select_good_tracks_batch_matches_oracle(lib, oracle, case):
+    """SelectGoodTracksForBundleAdjustment (select_good_tracks_for_bundle_adjustment.cc:263-325): per-track statistics, the
+    best track of every image grid cell, then the per-view quota filled in ascending track order; index work, so the chosen set
+    must equal the oracle's exactly. Mixed camera models, a view subset with a caller-provided starting set, host and device memory."""
+    import torch
+    if case == "c2_scaled":
+        prob, gt = synthetic.config_c2(scale=0.05)
+        args = (10, 100, 100)
+    else:
+        prob, gt = synthetic.make_ba_problem(14, 3000, 5, models=(capi.MODEL_PINHOLE, capi.MODEL_EXTENDED_UNIFIED, capi.MODEL_FOV), seed=77)
+        args = {"default": (10, 100, 100), "coarse_grid_small_quota": (3, 400, 20), "view_subset_preselected": (4, 150, 60)}[case]
+    rng = np.random.default_rng(9)
+    prob.a["pts"][:, :3] += rng.normal(0, 0.01, (prob.num_points, 3))      # distinct mean reprojection errors
+    cam_sel = None
+    start = np.zeros(prob.num_points, np.uint8)
+    if case == "view_subset_preselected":
+        cam_sel = (np.arange(prob.num_cameras) % 3 != 1).astype(np.uint8)
+        start[::17] = 1
+    n_o, sel_o = oracle.select_good_tracks(prob, *args, cam_selected=cam_sel, selected=start)
+    sel = start.copy(); count = C.c_int32(0)
+    p = prob.struct()
+    capi.check(lib.thb_select_good_tracks_batch(C.byref(p), None if cam_sel is None else cam_sel.ctypes.data_as(C.c_void_p), *args,
+                                                sel.ctypes.data_as(C.c_void_p), C.byref(count), None))
+    np.testing.assert_array_equal(sel != 0, sel_o != 0)
+    assert count.value == n_o == int((sel != 0).sum())
+    assert 0 < n_o < prob.num_points and np.all(sel[start != 0] != 0)
+    # every selected view has its quota (or all of its tracks)
+    chosen = sel != 0
+    for c in range(prob.num_cameras):
+        if cam_sel is not None and not cam_sel[c]:
+            continue
+        pts = prob.a["obs_pt"][prob.a["obs_cam"] == c]
+        assert chosen[pts].sum() >= min(args[2], len(pts))
+    dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in prob.a.items()}
+    pd = prob.struct(); pd.memory_space = capi.THB_MEM_DEVICE
+    for k, v in dev.items():
+        setattr(pd, k, None if v is None else v.data_ptr())
+    d_sel = torch.from_numpy(start.copy()).cuda()
+    d_cs = None if cam_sel is None else torch.from_numpy(cam_sel).cuda()
+    capi.check(lib.thb_select_good_tracks_batch(C.byref(pd), None if d_cs is None else C.c_void_p(d_cs.data_ptr()), *args,
+                                                C.c_void_p(d_sel.data_ptr()), C.byref(count), None))
+    np.testing.assert_array_equal(d_sel.cpu().numpy() != 0, sel_o != 0)
+    assert lib.thb_select_good_tracks_batch(C.byref(p), None, 10, 0, 100, sel.ctypes.data_as(C.c_void_p), None, None) == capi.THB_E_INVALID_ARGUMENT
