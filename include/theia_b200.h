@@ -487,6 +487,23 @@ typedef struct ThbTrackEstimatorOptions {
 int thb_estimate_tracks_batch(const ThbBaProblem* problem, const double* ray_directions, const ThbTrackEstimatorOptions* options,
                               const ThbBaOptions* ba_options, int32_t* status, ThbTrackBaResult* ba_results, void* cuda_stream);
 
+/*
+ * The covariance blocks behind BundleAdjustView(s) / BundleAdjustTrack(s) WITH covariance (bundle_adjustment.cc:287-380,
+ * 419-500 -> BundleAdjuster::GetCovarianceFor{View,Views,Track,Tracks}, bundle_adjuster.cc:660-773 = ceres::Covariance with
+ * default options: the loss function applied, tangent space): evaluated at the parameters in `problem`, no solve.
+ *   - every point constant (the AddView problems): cam_cov [num_cameras*36] receives (J_c^T J_c)^-1 of each camera's extrinsics
+ *     block, row-major 6 x 6 over [position(3), angle-axis(3)]; rows / columns of constant coordinates are zero; cam_ok[c] = 0
+ *     for constant or unobserved cameras and rank-deficient blocks (ceres::Covariance::Compute returns false for those);
+ *   - every camera and intrinsics block constant (the AddTrack problems, which the reference forces onto the homogeneous
+ *     parametrisation: options->use_homogeneous_point_parametrization must be set): pt_cov [num_points*9] receives the 3 x 3
+ *     tangent-space covariance of each point on SphereManifold<4>, pt_ok likewise.
+ * The caller scales by the empirical variance factor 2 * final_cost / redundancy (bundle_adjustment.cc:311-316). Problems with
+ * both free cameras and free points (or refined intrinsics) couple every block: THB_E_UNSUPPORTED. Output pointers of the
+ * unused kind may be NULL. Any memory space.
+ */
+int thb_ba_covariance(const ThbBaProblem* problem, const ThbBaOptions* options, double* cam_cov, uint8_t* cam_ok, double* pt_cov,
+                      uint8_t* pt_ok, void* cuda_stream);
+
 #define THB_OUTLIER_KEPT 0
 #define THB_OUTLIER_BAD_REPROJECTION 1   /* a view sees the point behind it, or the mean squared reprojection error is too large */
 #define THB_OUTLIER_BAD_ANGLE 2          /* no two viewing rays are at least min_triangulation_angle_degrees apart               */

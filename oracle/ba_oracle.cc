@@ -592,6 +592,78 @@ class BaOracle {
     return true;
   }
 
+  int Covariance(double* cam_cov, uint8_t* cam_ok, double* pt_cov, uint8_t* pt_ok) {
+    bool cams_free = false, pts_free = false, intr_free = false;
+    for (int c = 0; c < nc; ++c) cams_free |= cam_td[c] > 0;
+    for (int q = 0; q < np; ++q) pts_free |= pt_td[q] > 0;
+    for (int g = 0; g < ng; ++g) intr_free |= intr_td[g] > 0;
+    if (intr_free || (cams_free && pts_free)) return THB_E_UNSUPPORTED;
+    if (pts_free && !O.use_homogeneous_point_parametrization) return THB_E_INVALID_ARGUMENT;
+    if (cam_ok) std::fill(cam_ok, cam_ok + nc, 0);
+    if (pt_ok) std::fill(pt_ok, pt_ok + np, 0);
+    if (!cams_free && !pts_free) return THB_OK;
+    double cost = 0.0;
+    if (!Evaluate(x, true, &cost)) return THB_E_NUMERICAL;
+    if (cams_free) {
+      std::fill(cam_cov, cam_cov + (size_t)nc * 36, 0.0);
+      std::vector<double> N((size_t)nc * 36, 0.0);
+      std::vector<int> count(nc, 0);
+      for (int i = 0; i < no; ++i) {
+        if (fixed[i]) continue;
+        const int c = P.obs_cam[i], d = cam_td[c];
+        ++count[c];
+        for (int a = 0; a < 2; ++a)
+          for (int u = 0; u < d; ++u)
+            for (int v = 0; v < d; ++v) N[(size_t)c * 36 + u * d + v] += Jc[(size_t)i * 12 + a * 6 + u] * Jc[(size_t)i * 12 + a * 6 + v];
+      }
+      for (int c = 0; c < nc; ++c) {
+        const int d = cam_td[c];
+        if (!d || !count[c]) continue;
+        double inv[36];
+        bool good = true;
+        for (int col = 0; col < d && good; ++col) {
+          double e[6] = {0, 0, 0, 0, 0, 0}, xcol[6];
+          e[col] = 1.0;
+          good = DenseCholeskySolve(d, &N[(size_t)c * 36], e, xcol);
+          for (int r = 0; r < d; ++r) inv[r * d + col] = xcol[r];
+        }
+        for (int u = 0; u < d && good; ++u) good = inv[u * d + u] > 0.0 && inv[u * d + u] < 1e28;
+        if (!good) continue;
+        for (int u = 0; u < d; ++u) for (int v = 0; v < d; ++v) cam_cov[(size_t)c * 36 + cam_idx[c][u] * 6 + cam_idx[c][v]] = inv[u * d + v];
+        cam_ok[c] = 1;
+      }
+    } else {
+      std::fill(pt_cov, pt_cov + (size_t)np * 9, 0.0);
+      std::vector<double> N((size_t)np * 9, 0.0);
+      std::vector<int> count(np, 0);
+      for (int i = 0; i < no; ++i) {
+        if (fixed[i]) continue;
+        const int q = P.obs_pt[i];
+        if (pt_td[q] != 3) continue;
+        ++count[q];
+        for (int a = 0; a < 2; ++a)
+          for (int u = 0; u < 3; ++u)
+            for (int v = 0; v < 3; ++v) N[(size_t)q * 9 + u * 3 + v] += Jp[(size_t)i * 8 + a * 4 + u] * Jp[(size_t)i * 8 + a * 4 + v];
+      }
+      for (int q = 0; q < np; ++q) {
+        if (pt_td[q] != 3 || !count[q]) continue;
+        double inv[9];
+        bool good = true;
+        for (int col = 0; col < 3 && good; ++col) {
+          double e[3] = {0, 0, 0}, xcol[3];
+          e[col] = 1.0;
+          good = DenseCholeskySolve(3, &N[(size_t)q * 9], e, xcol);
+          for (int r = 0; r < 3; ++r) inv[r * 3 + col] = xcol[r];
+        }
+        for (int u = 0; u < 3 && good; ++u) good = inv[u * 3 + u] > 0.0 && inv[u * 3 + u] < 1e28;
+        if (!good) continue;
+        for (int k = 0; k < 9; ++k) pt_cov[(size_t)q * 9 + k] = inv[k];
+        pt_ok[q] = 1;
+      }
+    }
+    return THB_OK;
+  }
+
   // ceres ITERATIVE_SCHUR with the SCHUR_JACOBI preconditioner on the reduced camera system (iterative_schur_complement_solver.cc,
   // conjugate_gradients_solver.h of Ceres 2.2, restated): preconditioned CG from x = 0 on S y = rhs, S given by its lower triangle.
   // The preconditioner is the inverse of the block diagonal of S, one block per reduced parameter block (camera extrinsics,
@@ -1162,6 +1234,18 @@ int oracle_set_outlier_tracks(const ThbBaProblem* p, double max_err, double min_
     removed += st > 0;
   }
   return removed;
+}
+
+// ceres::Covariance (default options: loss applied, tangent space) for the BundleAdjustView(s) / BundleAdjustTrack(s) problems
+// (bundle_adjuster.cc:660-773): with only cameras or only points free every block's covariance is (J_b^T J_b)^-1 of its own
+// tangent-space Jacobian. Same contract as thb_ba_covariance.
+int oracle_ba_covariance(const ThbBaProblem* p, const ThbBaOptions* o, double* cam_cov, uint8_t* cam_ok, double* pt_cov, uint8_t* pt_ok) {
+  if (!p || !o) return THB_E_INVALID_ARGUMENT;
+  ThbBaOptions opt = *o; opt.jacobi_scaling = 0;
+  oracle::BaOracle ba(*p, opt);
+  const int rc = ba.Init();
+  if (rc != THB_OK) return rc;
+  return ba.Covariance(cam_cov, cam_ok, pt_cov, pt_ok);
 }
 
 // theia::SelectGoodTracksForBundleAdjustment (sfm/select_good_tracks_for_bundle_adjustment.cc:263-325) over the flat problem

@@ -143,6 +143,17 @@ def set_outlier_tracks(prob, max_err, min_angle_deg):
     return removed, status
 
 
+def ba_covariance(prob, options):
+    """(rc, cam_cov [nc,6,6], cam_ok [nc], pt_cov [np,3,3], pt_ok [np]); see thb_ba_covariance."""
+    lib = load()
+    lib.oracle_ba_covariance.argtypes = [C.POINTER(capi.ThbBaProblem), C.POINTER(capi.ThbBaOptions)] + [C.c_void_p] * 4
+    cc = np.zeros((prob.num_cameras, 6, 6)); co = np.zeros(prob.num_cameras, np.uint8)
+    pc = np.zeros((prob.num_points, 3, 3)); po = np.zeros(prob.num_points, np.uint8)
+    p = prob.struct()
+    rc = lib.oracle_ba_covariance(C.byref(p), C.byref(options), _vp(cc), _vp(co), _vp(pc), _vp(po))
+    return rc, cc, co, pc, po
+
+
 def select_good_tracks(prob, long_thr, cell_size, min_per_view, cam_selected=None, selected=None):
     lib = load()
     lib.oracle_select_good_tracks.argtypes = [C.POINTER(capi.ThbBaProblem), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]

@@ -251,6 +251,8 @@ def load_library():
     lib.thb_fp64_peak_tflops.restype = C.c_int
     lib.thb_set_outlier_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.c_double, C.c_double, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]
     lib.thb_set_outlier_tracks_batch.restype = C.c_int
+    lib.thb_ba_covariance.argtypes = [C.POINTER(ThbBaProblem), C.POINTER(ThbBaOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.thb_ba_covariance.restype = C.c_int
     lib.thb_select_good_tracks_batch.argtypes = [C.POINTER(ThbBaProblem), C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                                  C.POINTER(C.c_int32), C.c_void_p]
     lib.thb_select_good_tracks_batch.restype = C.c_int

@@ -302,8 +302,15 @@ ThbBaOptions MapOptions(const BundleAdjustmentOptions& o, bool force_no_inner) {
 }
 
 // What BundleAdjuster::AddView / AddTrack register (bundle_adjuster.cc:116-221), flattened.
+// covariance blocks of the BundleAdjust{View,Track}(s) overloads (bundle_adjustment.cc:287-380,419-500), row-major
+struct CovOut {
+  std::map<ViewId, std::array<double, 36>> views;
+  std::map<TrackId, std::array<double, 9>> tracks;
+  bool ok = false;  // GetCovarianceFor* succeeded for every requested block
+};
+
 BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vector<ViewId>& views, const std::vector<TrackId>& tracks,
-                              Reconstruction* r, bool force_no_inner) {
+                              Reconstruction* r, bool force_no_inner, CovOut* cov = nullptr) {
   if (o.use_inverse_depth_parametrization) throw std::runtime_error("use_inverse_depth_parametrization is not implemented");
   if (o.use_position_priors || o.use_orientation_priors || o.use_depth_priors || o.use_gravity_priors || o.orthographic_camera)
     throw std::runtime_error("prior residuals / orthographic cameras are not implemented");
@@ -407,6 +414,28 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   for (size_t i = 0; i < f.view_ids.size(); ++i) std::copy_n(&f.cam_ext[6 * i], 6, r->views.at(f.view_ids[i]).camera.ext);
   for (size_t i = 0; i < f.track_ids.size(); ++i) std::copy_n(&f.pts[4 * i], 4, r->tracks.at(f.track_ids[i]).point);
   for (size_t g = 0; g < f.groups.size(); ++g) std::copy_n(&f.intr[THB_INTR_STRIDE * g], THB_INTR_STRIDE, f.groups[g]->params);
+  if (cov) {  // ceres::Covariance at the refined parameters (p still points at them)
+    std::vector<double> cc(36 * f.view_ids.size()), pc(9 * f.track_ids.size());
+    std::vector<uint8_t> cok(f.view_ids.size()), pok(f.track_ids.size());
+    {
+      py::gil_scoped_release nogil;
+      rc = thb_ba_covariance(&p, &opt, cc.data(), cok.data(), pc.data(), pok.data(), nullptr);
+    }
+    Check(rc);
+    cov->ok = true;
+    for (ViewId v : views) {
+      auto it = f.view_index.find(v);
+      if (it == f.view_index.end() || !cok[it->second]) { cov->ok = false; continue; }   // "could not be found or is set to fixed"
+      std::copy_n(&cc[36 * it->second], 36, cov->views[v].begin());
+    }
+    std::unordered_map<TrackId, int> slot;                     // the gather keeps track slots in the Track objects, not in a map
+    for (size_t i = 0; i < f.track_ids.size(); ++i) slot[f.track_ids[i]] = (int)i;
+    for (TrackId t : tracks) {
+      auto it = slot.find(t);
+      if (it == slot.end() || !pok[it->second]) { cov->ok = false; continue; }
+      std::copy_n(&pc[9 * it->second], 9, cov->tracks[t].begin());
+    }
+  }
   return out;
 }
 
@@ -908,6 +937,83 @@ PYBIND11_MODULE(_pt, m) {
     BundleAdjustmentSummary s = RunBa(o, v, {}, &r, true);
     UpdateInverseDepth(TracksOfViews(v, &r), &r);
     return s;
+  });
+  // the covariance overloads (bundle_adjustment_wrapper.cc:52-96): (summary, covariance(s), empirical variance factor)
+  auto to_mat = [](const double* d, int n) {
+    py::array_t<double> a({n, n});
+    std::copy_n(d, n * n, a.mutable_data());
+    return a;
+  };
+  sfm.def("BundleAdjustViewWithCov", [to_mat](Reconstruction& r, const BundleAdjustmentOptions& o, ViewId v) {
+    CovOut cov;
+    BundleAdjustmentSummary s = RunBa(o, {v}, {}, &r, true, &cov);
+    double factor = 1.0, eye[36] = {0};
+    for (int k = 0; k < 6; ++k) eye[k * 7] = 1.0;
+    std::array<double, 36> m; std::copy_n(eye, 36, m.begin());
+    if (s.success) {
+      if (!cov.ok) s.success = false;                                                      // :441-443
+      else {
+        const double redundancy = (double)r.views.at(v).features.size() * 2 - 6;           // View::NumFeatures() (:445-447)
+        factor = 2.0 * s.final_cost / redundancy;
+        m = cov.views.at(v);
+        for (double& x : m) x *= factor;
+      }
+    }
+    UpdateInverseDepth(TracksOfViews({v}, &r), &r);
+    return py::make_tuple(s, to_mat(m.data(), 6), factor);
+  });
+  sfm.def("BundleAdjustViewsWithCov", [to_mat](Reconstruction& r, const BundleAdjustmentOptions& o, const std::vector<ViewId>& v) {
+    CovOut cov;
+    BundleAdjustmentSummary s = RunBa(o, v, {}, &r, true, &cov);
+    double factor = 1.0;
+    py::dict mats;
+    if (s.success) {
+      if (!cov.ok) s.success = false;
+      else {
+        double nr_obs = 0;
+        for (ViewId id : v) nr_obs += (double)r.views.at(id).features.size();
+        factor = 2.0 * s.final_cost / (nr_obs * 2 - 6.0 * (double)v.size());                 // :478-490
+        for (auto& kv : cov.views) { for (double& x : kv.second) x *= factor; mats[py::int_(kv.first)] = to_mat(kv.second.data(), 6); }
+      }
+    }
+    UpdateInverseDepth(TracksOfViews(v, &r), &r);
+    return py::make_tuple(s, mats, factor);
+  });
+  sfm.def("BundleAdjustTrackWithCov", [to_mat](Reconstruction& r, const BundleAdjustmentOptions& o, TrackId t) {
+    BundleAdjustmentOptions oo = o; oo.use_homogeneous_point_parametrization = true;       // :296
+    CovOut cov;
+    BundleAdjustmentSummary s = RunBa(oo, {}, {t}, &r, true, &cov);
+    double factor = 1.0;
+    std::array<double, 9> m = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (s.success) {
+      if (!cov.ok) s.success = false;
+      else {
+        const double redundancy = (double)r.tracks.at(t).views.size() * 2 - 3;              // Track::NumViews() (:312-316)
+        factor = 2.0 * s.final_cost / redundancy;
+        m = cov.tracks.at(t);
+        for (double& x : m) x *= factor;
+      }
+    }
+    UpdateInverseDepth({t}, &r);
+    return py::make_tuple(s, to_mat(m.data(), 3), factor);
+  });
+  sfm.def("BundleAdjustTracksWithCov", [to_mat](Reconstruction& r, const BundleAdjustmentOptions& o, const std::vector<TrackId>& t) {
+    BundleAdjustmentOptions oo = o; oo.use_homogeneous_point_parametrization = true;
+    CovOut cov;
+    BundleAdjustmentSummary s = RunBa(oo, {}, t, &r, true, &cov);
+    double factor = 1.0;
+    py::dict mats;
+    if (s.success) {
+      if (!cov.ok) s.success = false;
+      else {
+        double nr_obs = 0;
+        for (TrackId id : t) nr_obs += (double)r.tracks.at(id).views.size();
+        factor = 2.0 * s.final_cost / (nr_obs * 2 - 3.0 * (double)t.size());                 // :358-369
+        for (auto& kv : cov.tracks) { for (double& x : kv.second) x *= factor; mats[py::int_(kv.first)] = to_mat(kv.second.data(), 3); }
+      }
+    }
+    UpdateInverseDepth(t, &r);
+    return py::make_tuple(s, mats, factor);
   });
   // SetOutlierTracksToUnestimated (sfm_wrapper.cc:46-57 -> set_outlier_tracks_to_unestimated.cc:62-137): every listed track in
   // one launch over thb_set_outlier_tracks_batch; tracks with status > 0 become unestimated. Returns the number removed.

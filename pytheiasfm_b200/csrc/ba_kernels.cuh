@@ -1083,5 +1083,47 @@ __global__ void k_eval_ambient(BaConst K, BaState S, ObsSoA O, double* __restric
       for (int k = 0; k < KS; ++k) jintr[(2 * (size_t)i + a) * KS + k] = k < 9 ? ji[a * 9 + k] : 0.0;
 }
 
+// covariance of a camera's extrinsics block from its diagonal block of S (points constant: S is block diagonal)
+__global__ void k_cov_cam(int nc, const uint8_t* __restrict__ cam_const, const int* __restrict__ cam_start, const double* __restrict__ S, int ld,
+                          double* __restrict__ cov, uint8_t* __restrict__ ok) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nc) return;
+  const int cc = cam_const[c];
+  double M[36], Minv[36];
+  bool cst[6];
+  for (int k = 0; k < 6; ++k) cst[k] = (k < 3 ? (cc & THB_CAM_CONST_POSITION) : (cc & THB_CAM_CONST_ORIENTATION)) != 0;
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double v = S[(size_t)(6 * c + i) * ld + 6 * c + j];
+      if (cst[i] || cst[j]) v = i == j ? 1.0 : 0.0;
+      M[i * 6 + j] = v; M[j * 6 + i] = v;
+    }
+  bool good = cc != THB_CAM_CONST_ALL && cam_start[c + 1] > cam_start[c] && spd_inverse<6>(M, Minv);
+  for (int k = 0; k < 36 && good; ++k) good = isfinite(Minv[k]);
+  // ceres::Covariance rejects rank-deficient Jacobians (min_reciprocal_condition_number 1e-14)
+  if (good) {
+    double dmax = 0.0, dmin = 1e300;
+    for (int k = 0; k < 6; ++k) if (!cst[k]) { dmax = fmax(dmax, Minv[k * 6 + k]); dmin = fmin(dmin, Minv[k * 6 + k]); }
+    good = dmin > 0.0 && dmax < 1e28;
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) cov[(size_t)c * 36 + i * 6 + j] = (good && !cst[i] && !cst[j]) ? Minv[i * 6 + j] : 0.0;
+  ok[c] = good ? 1 : 0;
+}
+
+// covariance of a point's tangent block = the V^-1 the point pass leaves (cameras constant)
+__global__ void k_cov_pt(int np, const uint8_t* __restrict__ pt_const, const int* __restrict__ pt_start, const double* __restrict__ vinv,
+                         double* __restrict__ cov, uint8_t* __restrict__ ok) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  bool good = !pt_const[p] && pt_start[p + 1] > pt_start[p];
+  double v[9];
+  for (int k = 0; k < 9; ++k) { v[k] = vinv[(size_t)p * 9 + k]; good = good && isfinite(v[k]); }
+  if (good) good = v[0] > 0.0 && v[4] > 0.0 && v[8] > 0.0 && fmax(v[0], fmax(v[4], v[8])) < 1e28;
+  for (int k = 0; k < 9; ++k) cov[(size_t)p * 9 + k] = good ? v[k] : 0.0;
+  ok[p] = good ? 1 : 0;
+}
+
+
 }  // namespace thb
 #endif  // THB_BA_KERNELS_CUH_

@@ -125,6 +125,7 @@ struct ThbBaSession {
   bool constrained = false;   // bounds on a non-constant block (ceres Program::IsBoundsConstrained)
   bool red_variable = false;  // any non-constant camera coordinate or intrinsics block
   bool any_variable = false;
+  bool pt_variable = false;
   BaConst K{};
   BaState X{}, Xc{};
   ObsSoA Op{}, Oc{};
@@ -872,7 +873,8 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   }
   s->constrained = s->nvg > 0;  // focal length >= 1 is always set on a non-constant block (bundle_adjuster.cc:396-405)
   s->red_variable = s->nvg > 0 || h_setup[SF_RED_VARIABLE] != 0;
-  s->any_variable = s->red_variable || h_setup[SF_PT_VARIABLE] != 0;
+  s->pt_variable = h_setup[SF_PT_VARIABLE] != 0;
+  s->any_variable = s->red_variable || s->pt_variable;
   // Schur chunks: consecutive points with <= 64 observations in total
   std::vector<int> chunk_pt;
   chunk_pt.push_back(0);
@@ -1000,6 +1002,56 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
 }  // namespace
 
 extern "C" {
+
+int thb_ba_covariance(const ThbBaProblem* problem, const ThbBaOptions* options, double* cam_cov, uint8_t* cam_ok, double* pt_cov, uint8_t* pt_ok,
+                      void* cuda_stream) {
+  if (!problem || !options) THB_FAIL(THB_E_INVALID_ARGUMENT, "null argument");
+  ThbBaOptions o = *options;
+  o.jacobi_scaling = 0;          // the blocks are read in the problem's own units
+  o.use_inner_iterations = 0;
+  o.linear_solver = THB_SOLVER_SCHUR_CHOLESKY;
+  ThbBaSession* s = nullptr;
+  int rc = ValidateAndCreate(problem, &o, cuda_stream, &s);
+  if (rc != THB_OK) return rc;
+  const int nc = s->nc, np = s->np;
+  const bool host = s->prob.memory_space == THB_MEM_HOST;
+  const cudaMemcpyKind kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  auto fail = [&](int code, const char* msg) { FreeSession(s); SetLastError(msg); return code; };
+  if (s->nvg > 0 || (s->red_variable && s->pt_variable))
+    return fail(THB_E_UNSUPPORTED, "covariance needs a problem with only cameras or only points free (BundleAdjustView(s) / BundleAdjustTrack(s))");
+  if (s->pt_variable && s->PD != 3) return fail(THB_E_INVALID_ARGUMENT, "point covariance needs use_homogeneous_point_parametrization (bundle_adjustment.cc:296)");
+  if (s->red_variable && (!cam_cov || !cam_ok)) return fail(THB_E_INVALID_ARGUMENT, "cam_cov / cam_ok are NULL");
+  if (s->pt_variable && (!pt_cov || !pt_ok)) return fail(THB_E_INVALID_ARGUMENT, "pt_cov / pt_ok are NULL");
+  double* d_cov = nullptr; uint8_t* d_ok = nullptr;
+  cudaError_t e = cudaSuccess;
+  if (s->any_variable && s->no > 0) {
+    s->radius = 1e30;  // no Levenberg-Marquardt damping: D^2 = diag / radius is far below the rounding of the blocks
+    rc = BuildBlocks(s, false);
+    if (rc != THB_OK) { FreeSession(s); return rc; }
+  }
+  const size_t n_items = s->red_variable ? (size_t)nc : (size_t)np, width = s->red_variable ? 36 : 9;
+  if (s->any_variable && s->no > 0 && n_items > 0) {
+    e = cudaMallocAsync(&d_cov, sizeof(double) * n_items * width, s->st);
+    if (e == cudaSuccess) e = cudaMallocAsync(&d_ok, n_items, s->st);
+    if (e == cudaSuccess) {
+      if (s->red_variable) k_cov_cam<<<cdiv(nc, 64), 64, 0, s->st>>>(nc, s->d_cam_const, s->d_cam_start, s->chol.A, s->chol.ld, d_cov, d_ok);
+      else k_cov_pt<<<cdiv(np, 128), 128, 0, s->st>>>(np, s->d_pt_const, s->d_pt_start, s->d_vinv, d_cov, d_ok);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->red_variable ? cam_cov : pt_cov, d_cov, sizeof(double) * n_items * width, kout, s->st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s->red_variable ? cam_ok : pt_ok, d_ok, n_items, kout, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+    if (d_cov) cudaFreeAsync(d_cov, s->st);
+    if (d_ok) cudaFreeAsync(d_ok, s->st);
+  } else {  // nothing free: no block has a covariance
+    if (cam_ok && nc > 0) e = host ? (std::memset(cam_ok, 0, nc), cudaSuccess) : cudaMemsetAsync(cam_ok, 0, nc, s->st);
+    if (e == cudaSuccess && pt_ok && np > 0) e = host ? (std::memset(pt_ok, 0, np), cudaSuccess) : cudaMemsetAsync(pt_ok, 0, np, s->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+  }
+  FreeSession(s);
+  if (e != cudaSuccess) THB_FAIL(THB_E_CUDA, cudaGetErrorString(e));
+  return THB_OK;
+}
 
 int thb_version(void) { return 100; }
 const char* thb_last_error(void) { return thb::GetLastError(); }

@@ -152,6 +152,28 @@ def test_SetOutlierTracksToUnestimated(gen):
     assert pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon) == 0      # idempotent
 
 
+def test_BundleAdjust_with_covariance(gen):
+    """bundle_adjustment_wrapper.cc:52-96: (summary, covariance, empirical variance factor) for a view, views, a track, tracks;
+    covariances are symmetric positive definite, scaled by 2 * final_cost / redundancy, and agree between the single and the
+    plural form of the call."""
+    opts = pt.sfm.BundleAdjustmentOptions()
+    vids = gen.recon.ViewIds(); tids = [t for t in gen.recon.TrackIds() if gen.recon.Track(t).IsEstimated()]
+    gen.add_noise_to_views(1e-3, 1e-3)
+    s, cov, factor = pt.sfm.BundleAdjustViewWithCov(gen.recon, opts, vids[1])
+    assert s.success and cov.shape == (6, 6) and factor >= 0
+    np.testing.assert_allclose(cov, cov.T, rtol=1e-9, atol=1e-30)
+    s2, covs, factor2 = pt.sfm.BundleAdjustViewsWithCov(gen.recon, opts, [vids[1], vids[2]])
+    assert s2.success and set(covs) == {vids[1], vids[2]} and covs[vids[2]].shape == (6, 6)
+    gen.add_noise_to_tracks(1e-2) if hasattr(gen, "add_noise_to_tracks") else None
+    s3, cov3, factor3 = pt.sfm.BundleAdjustTrackWithCov(gen.recon, opts, tids[0])
+    assert s3.success and cov3.shape == (3, 3)
+    np.testing.assert_allclose(cov3, cov3.T, rtol=1e-9, atol=1e-30)
+    s4, covs4, factor4 = pt.sfm.BundleAdjustTracksWithCov(gen.recon, opts, tids[:5])
+    assert s4.success and set(covs4) == set(tids[:5])
+    if factor3 > 0 and factor4 > 0:   # same (J^T J)^-1 behind both, different variance factors
+        np.testing.assert_allclose(cov3 / factor3, covs4[tids[0]] / factor4, rtol=1e-3)
+
+
 def test_SelectGoodTracksForBundleAdjustment(gen):
     """sfm.cc:933 / select_good_tracks_for_bundle_adjustment.cc: (success, set of track ids); every view keeps its quota, the
     set is a strict subset when the quota is small, and BundleAdjustPartialReconstruction accepts it."""

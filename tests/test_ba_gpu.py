@@ -483,3 +483,60 @@ def test_schur_pcg_c2_full_size(lib, oracle):
     e = gpu_solve(lib, prob.copy(), capi.default_options(lib))
     assert abs(g["final_cost"] - e["final_cost"]) <= 1e-4 * e["final_cost"]
     assert g["ms_solve"] / g["num_linear_solves"] < 0.5 * e["ms_solve"] / e["num_linear_solves"]
+
+
+def _gpu_covariance(lib, prob, opts):
+    cc = np.zeros((prob.num_cameras, 6, 6)); co = np.full(prob.num_cameras, 9, np.uint8)
+    pc = np.zeros((prob.num_points, 3, 3)); po = np.full(prob.num_points, 9, np.uint8)
+    p = prob.struct()
+    rc = lib.thb_ba_covariance(C.byref(p), C.byref(opts), cc.ctypes.data_as(C.c_void_p), co.ctypes.data_as(C.c_void_p),
+                               pc.ctypes.data_as(C.c_void_p), po.ctypes.data_as(C.c_void_p), None)
+    return rc, cc, co, pc, po
+
+
+@pytest.mark.parametrize("loss", [capi.LOSS_TRIVIAL, capi.LOSS_HUBER])
+def test_covariance_of_views_and_tracks_matches_oracle(lib, oracle, loss):
+    """ceres::Covariance behind BundleAdjustView(s) / BundleAdjustTrack(s) with covariance (bundle_adjuster.cc:660-773): tangent-space
+    (J^T J)^-1 of every free block with the loss applied; against the oracle's Jets and, for the trivial loss, against numpy on the
+    ambient Jacobians of thb_ba_evaluate."""
+    prob, gt = synthetic.make_ba_problem(9, 400, 5, models=(capi.MODEL_PINHOLE, capi.MODEL_FISHEYE), seed=21)
+    o = capi.default_options(lib); o.loss_function_type = loss; o.robust_loss_width = 1.0
+    # (A) the AddView problem: every point constant, one camera fully constant, one with a constant position
+    a = prob.copy()
+    a.a["pt_const"][:] = 1
+    a.a["cam_const"][2] = capi.CAM_CONST_POSITION
+    keep = a.a["obs_cam"] != 4                                 # camera 4 is unobserved: no covariance
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        a.a[k] = None if a.a[k] is None else a.a[k][keep]
+    a = capi.HostBaProblem(a.a)
+    rc, cc, co, pc, po = _gpu_covariance(lib, a, o)
+    orc, occ, oco, opc, opo = oracle.ba_covariance(a, o)
+    assert rc == orc == 0
+    np.testing.assert_array_equal(co, oco)
+    assert co[4] == 0 and co[2] == 1 and co.sum() == a.num_cameras - 1
+    np.testing.assert_allclose(cc, occ, rtol=1e-9, atol=1e-18)
+    assert np.all(cc[2, :3, :] == 0) and np.all(cc[2, :, :3] == 0) and np.all(np.diag(cc[2])[3:] > 0)
+    if loss == capi.LOSS_TRIVIAL:
+        r, jc, ji, jp, ok = gpu_evaluate(lib, a)
+        for c in (0, 7):
+            J = jc[a.a["obs_cam"] == c].reshape(-1, 6)
+            np.testing.assert_allclose(cc[c], np.linalg.inv(J.T @ J), rtol=1e-8)
+    # (B) the AddTrack problem: every camera constant
+    b = prob.copy()
+    b.a["cam_const"][:] = 3
+    keep = b.a["obs_pt"] != 0                                  # point 0 is unobserved: no covariance
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        b.a[k] = None if b.a[k] is None else b.a[k][keep]
+    b = capi.HostBaProblem(b.a)
+    rc, cc, co, pc, po = _gpu_covariance(lib, b, o)
+    orc, occ, oco, opc, opo = oracle.ba_covariance(b, o)
+    assert rc == orc == 0
+    np.testing.assert_array_equal(po, opo)
+    assert po[0] == 0 and po[1] == 1
+    np.testing.assert_allclose(pc, opc, rtol=1e-9, atol=1e-18)
+    assert np.all(np.linalg.eigvalsh(pc[po == 1]) > 0)
+    # everything free couples the blocks; Euclidean points have a singular covariance (bundle_adjustment.cc:344-345)
+    assert _gpu_covariance(lib, prob, o)[0] == capi.THB_E_UNSUPPORTED
+    assert oracle.ba_covariance(prob, o)[0] == capi.THB_E_UNSUPPORTED
+    o.use_homogeneous_point_parametrization = 0
+    assert _gpu_covariance(lib, b, o)[0] == capi.THB_E_INVALID_ARGUMENT
