@@ -325,8 +325,8 @@ typedef struct ThbRansacStats {
   uint64_t models_scored;   /* candidate models that entered scoring                                              */
   uint64_t data_scored;     /* per-datum error evaluations actually executed (early abandonment included)         */
   uint64_t reserved0;
-  uint64_t cycles_draw;     /* SM clock cycles the CTAs spent in each phase of the batches (summed over CTAs): where */
-  uint64_t cycles_solve;    /* a pair's wall time goes                                                            */
+  uint64_t cycles_draw;     /* where the time goes, per phase. Round-synchronous path: device time of the phase kernels in  */
+  uint64_t cycles_solve;    /* nanoseconds; fused (LO) kernel: SM clock cycles the CTAs spent in the phase, summed over CTAs */
   uint64_t cycles_score;
   uint64_t cycles_scan;
 } ThbRansacStats;

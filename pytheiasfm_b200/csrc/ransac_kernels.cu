@@ -19,9 +19,13 @@
 //            bound, and discards everything past the terminating iteration
 // This file is compiled with -fmad=false (see small_linalg.cuh); the scoring formulas use explicit fma() in a
 // fixed order so that they are both fast and bit-reproducible against the CPU oracle.
+#include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -1176,6 +1180,221 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRans
   }  // next pair
 }
 
+// ---- round-synchronous form of the same loop (no LO) ---------------------------------------------------------------
+// The fused kernel above keeps a pair on ONE CTA, so a batch smaller than the grid leaves SMs idle and a single pair runs on four
+// warps. Here a ROUND = the same batch of BI iterations for EVERY active pair, one kernel per phase: draw and scan run one pair
+// per thread, solve one hypothesis per thread over all pairs, score one warp per (pair, iteration) - a pair's round is spread over
+// 33 CTAs. The arithmetic of every hypothesis and of every model score is the code above, unchanged (same Est::solve, same
+// score_model, same scan), so results stay bit-identical to the fused kernel and to the oracle.
+// Measured (r02, B200, C4-shaped pairs): faster than the fused kernel up to ~1 000 pairs (1 pair 2.5 vs ~6 ms per call), 4 % slower
+// at 10 000 pairs (215 vs 208 ms): the solve phase is the same thread-per-hypothesis code and takes 140 ms alone - ~1.5 M cycles
+// of dependent FP64 / local-memory latency per hypothesis, throughput saturating at ~65 solves per Mcycle per SM from 4 warps up
+// (THB_RS_PROF=1 prints the distribution) - and run as its own kernel it no longer overlaps the score phase of other pairs.
+// Also measured and dropped: the solver's 10 x 10 work matrices in shared memory, interleaved per thread (conflict-free for its
+// data-dependent indexing; 159 vs 140 ms: the latency is in the dependent arithmetic, not in those loads), 1 / 2 / 4 solver CTAs
+// per SM (188-210 ms with a grid-stride loop), 8- and 16-warp score CTAs (67 / 77 vs 64 ms).
+struct PairState {
+  Mt19937 rng;
+  Model best;
+  double best_cost, thresh;
+  long long off;
+  int n, pair, max_iterations, it0, num_iterations, have_best, nit, pad;
+  unsigned long long stat_samples, stat_models, stat_data;
+};
+
+template <class Est>
+__global__ void __launch_bounds__(128) k_rs_init(const ThbRansacParams P, int pair0, int count, const long long* __restrict__ pair_offset,
+                                                 const uint32_t* __restrict__ seed, ThbRelPoseResult* __restrict__ results,
+                                                 uint8_t* __restrict__ mask_all, int* __restrict__ idx_ws, PairState* __restrict__ states,
+                                                 int* __restrict__ active, int* __restrict__ counters, const double* __restrict__ pair_thresh,
+                                                 const uint32_t* __restrict__ rng_state, int rng_mode, const uint8_t* __restrict__ pair_skip) {
+  const int slot = blockIdx.x, pair = pair0 + slot, t = threadIdx.x;
+  if (slot >= count) return;
+  const long long off = pair_offset[pair];
+  const int n = (int)(pair_offset[pair + 1] - off);
+  PairState& S = states[slot];
+  if (n < Est::S || (pair_skip && pair_skip[pair])) {
+    if (t == 0) { memset(results + pair, 0, sizeof(ThbRelPoseResult)); results[pair].num_input_data_points = n; S.n = -1; S.pair = pair; }
+    if (mask_all) for (int i = t; i < n; i += blockDim.x) mask_all[off + i] = 0;
+    return;
+  }
+  int* sidx = idx_ws + off;
+  for (int i = t; i < n; i += blockDim.x) sidx[i] = i;
+  if (rng_state && rng_mode == 2) {
+    const uint32_t* src = rng_state + (size_t)pair * 625;
+    for (int i = t; i < 624; i += blockDim.x) S.rng.mt[i] = src[i];
+    if (t == 0) S.rng.idx = (int)src[624];
+  }
+  if (t == 0) {
+    if (!(rng_state && rng_mode == 2)) mt_seed(&S.rng, seed[pair]);
+    ThbRansacParams Pl = P;
+    S.thresh = pair_thresh ? pair_thresh[pair] : P.error_thresh;
+    S.best_cost = DBL_MAX;
+    S.max_iterations = P.max_iterations;
+    if (P.min_inlier_ratio > 0) {
+      const int mi = compute_max_iterations(Pl, Est::S, P.min_inlier_ratio, log(P.failure_probability), n);
+      S.max_iterations = mi < P.max_iterations ? mi : P.max_iterations;
+    }
+    S.off = off; S.n = n; S.pair = pair; S.it0 = 0; S.num_iterations = 0; S.have_best = 0; S.nit = 0;
+    S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
+    memset(&S.best, 0, sizeof(Model));
+    if (S.it0 >= S.max_iterations) S.num_iterations = S.it0;  // finished before the first round
+    else active[atomicAdd(&counters[0], 1)] = slot;
+  }
+}
+
+// draw: RandomSampler for the BI iterations of this round, one pair per thread (the generator is sequential)
+template <class Est>
+__global__ void __launch_bounds__(64) k_rs_draw(int na, const int* __restrict__ active, PairState* __restrict__ states, int* __restrict__ idx_ws,
+                                                int* __restrict__ samples) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int slot = active[a];
+  PairState& S = states[slot];
+  const int n = S.n, nit = min(BI, S.max_iterations - S.it0);
+  int* sidx = idx_ws + S.off;
+  int* out = samples + (size_t)slot * BI * 5;
+  for (int b = 0; b < nit; ++b)
+    for (int i = 0; i < Est::S; ++i) {
+      const int j = mt_uniform_int(&S.rng, i, n - 1);
+      const int u = sidx[i], c = sidx[j];
+      sidx[i] = c; sidx[j] = u;
+      out[b * 5 + i] = c;
+    }
+  S.nit = nit;
+  S.stat_samples += nit;
+}
+
+// solve: thread (a, b) = hypothesis b of active pair a
+template <class Est>
+__global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_rs_solve(int na, const int* __restrict__ active, const PairState* __restrict__ states,
+                                                                      const double* __restrict__ corr_all, const int* __restrict__ samples,
+                                                                      Model* __restrict__ model_ws, int* __restrict__ nmodels, long long* __restrict__ prof) {
+  constexpr int SS = Est::S, DD = Est::D;
+  const int b = threadIdx.x;
+  for (int a = blockIdx.x; a < na; a += gridDim.x) {
+    const long long t0 = prof ? clock64() : 0;  // the grid bounds the solver threads per SM (their work matrices live in L1)
+    const int slot = active[a];
+    const PairState& S = states[slot];
+    int nm = 0;
+    if (b < S.nit) {
+      const double* corr = corr_all + (size_t)S.off * DD;
+      const int* smp = samples + ((size_t)slot * BI + b) * 5;
+      double sample[SS * DD];
+      for (int i = 0; i < SS; ++i)
+        for (int k = 0; k < DD; ++k) sample[DD * i + k] = corr[(size_t)smp[i] * DD + k];
+      nm = Est::solve(sample, model_ws + ((size_t)slot * BI + b) * MAXM);
+    }
+    nmodels[(size_t)slot * BI + b] = nm;
+    if (prof) prof[(size_t)a * BI + b] = clock64() - t0;
+  }
+}
+
+// score: warp (a, b) scores the models of hypothesis b of active pair a; consecutive warps share the pair's correspondences
+template <class Est, int WARPS, int CTAS>
+__global__ void __launch_bounds__(32 * WARPS, CTAS) k_rs_score(const ThbRansacParams P, const int* __restrict__ active, PairState* __restrict__ states,
+                                                     const double* __restrict__ corr_all, const Model* __restrict__ model_ws,
+                                                     const int* __restrict__ nmodels, double* __restrict__ cost_ws, int* __restrict__ ninl_ws) {
+  const int slot = active[blockIdx.x / (BI / WARPS)], w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = (blockIdx.x % (BI / WARPS)) * WARPS + w;
+  PairState& S = states[slot];
+  const int nm = nmodels[(size_t)slot * BI + b];
+  if (nm == 0) return;
+  ThbRansacParams Pl = P;
+  Pl.error_thresh = S.thresh;
+  const double* corr = corr_all + (size_t)S.off * Est::D;
+  const double bail = S.best_cost;
+  unsigned scored = 0;
+  for (int k = 0; k < nm; ++k) {
+    const size_t m = ((size_t)slot * BI + b) * MAXM + k;
+    double cost; int ninl;
+    score_model<Est>(Pl, corr, S.n, model_ws[m], bail, nullptr, &cost, &ninl, &scored);
+    if (lane == 0) { cost_ws[m] = cost; ninl_ws[m] = ninl; }
+  }
+  if (lane == 0) { atomicAdd(&S.stat_data, (unsigned long long)scored); atomicAdd(&S.stat_models, (unsigned long long)nm); }
+}
+
+// scan: the sequential replay of the round in (iteration, model) order, one pair per thread; pairs that go on are appended to
+// the next active list
+template <class Est>
+__global__ void __launch_bounds__(64) k_rs_scan(const ThbRansacParams P, int na, const int* __restrict__ active, PairState* __restrict__ states,
+                                                const Model* __restrict__ model_ws, const int* __restrict__ nmodels,
+                                                const double* __restrict__ cost_ws, const int* __restrict__ ninl_ws,
+                                                int* __restrict__ next_active, int* __restrict__ next_count) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int slot = active[a];
+  PairState& S = states[slot];
+  ThbRansacParams Pl = P;
+  Pl.error_thresh = S.thresh;
+  const double log_failure_prob = log(P.failure_probability);
+  const int n = S.n, nit = S.nit;
+  int it = S.it0, max_it = S.max_iterations;
+  double best_cost = S.best_cost;
+  for (int b = 0; b < nit; ++b, ++it) {
+    if (it >= max_it) break;
+    const int nm = nmodels[(size_t)slot * BI + b];
+    for (int k = 0; k < nm; ++k) {
+      const size_t m = ((size_t)slot * BI + b) * MAXM + k;
+      const double sample_cost = cost_ws[m];
+      if (sample_cost < best_cost) {
+        const double inlier_ratio = (double)ninl_ws[m] / (double)n;
+        S.best = model_ws[m];
+        best_cost = sample_cost;
+        S.have_best = 1;
+        if (inlier_ratio < (double)Est::S / (double)n) continue;
+        const int mi = compute_max_iterations(Pl, Est::S, inlier_ratio, log_failure_prob, n);
+        if (mi < max_it) max_it = mi;
+      }
+    }
+  }
+  S.best_cost = best_cost; S.max_iterations = max_it; S.it0 = it;
+  if (it >= max_it) S.num_iterations = it;
+  else next_active[atomicAdd(next_count, 1)] = slot;
+}
+
+// final inliers of the best model and the result record (sample_consensus_estimator.h:396-414), one warp per pair
+template <class Est>
+__global__ void __launch_bounds__(128) k_rs_final(const ThbRansacParams P, int count, PairState* __restrict__ states, const double* __restrict__ corr_all,
+                                                  const uint32_t* __restrict__ seed, ThbRelPoseResult* __restrict__ results,
+                                                  uint8_t* __restrict__ mask_all, unsigned long long* __restrict__ stats,
+                                                  uint32_t* __restrict__ rng_state, int rng_mode) {
+  const int slot = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (slot >= count) return;
+  PairState& S = states[slot];
+  if (S.n < 0) return;  // rejected by k_rs_init
+  ThbRansacParams Pl = P;
+  Pl.error_thresh = S.thresh;
+  const double* corr = corr_all + (size_t)S.off * Est::D;
+  double f_cost = 0.0; int f_ninl = 0; unsigned f_scored = 0;
+  score_model<Est>(Pl, corr, S.n, S.best, DBL_MAX, mask_all ? mask_all + S.off : nullptr, &f_cost, &f_ninl, &f_scored);
+  if (lane == 0) {
+    ThbRelPoseResult* out = results + S.pair;
+    if (stats) {
+      atomicAdd(stats + 0, 1ull); atomicAdd(stats + 1, (unsigned long long)S.num_iterations); atomicAdd(stats + 2, S.stat_samples);
+      atomicAdd(stats + 3, S.stat_models + 1); atomicAdd(stats + 4, S.stat_data + f_scored);
+    }
+    out->success = 1;
+    out->num_inliers = f_ninl;
+    out->num_iterations = S.num_iterations;
+    out->num_input_data_points = S.n;
+    const double ratio = (double)f_ninl / (double)S.n;
+    out->confidence = 1.0 - pow(1.0 - pow(ratio, (double)Est::S), (double)S.num_iterations);
+    out->best_cost = S.best_cost;
+    out->num_lo_iterations = 0; out->reserved0 = 0;
+    for (int k = 0; k < 9; ++k) { out->essential_matrix[k] = S.best.E[k]; out->rotation[k] = S.best.R[k]; }
+    for (int k = 0; k < 3; ++k) out->position[k] = S.best.p[k];
+    if (rng_state && rng_mode == 1) {  // the generator as the sequential loop leaves it: num_iterations x SampleSize draws from the seed
+      mt_seed(&S.rng, seed[S.pair]);
+      for (int it = 0; it < S.num_iterations; ++it)
+        for (int i = 0; i < Est::S; ++i) (void)mt_uniform_int(&S.rng, i, S.n - 1);
+      uint32_t* dst = rng_state + (size_t)S.pair * 625;
+      for (int i = 0; i < 624; ++i) dst[i] = S.rng.mt[i];
+      dst[624] = (uint32_t)S.rng.idx;
+    }
+  }
+}
+
 __global__ void k_five_point(const double* __restrict__ x1, const double* __restrict__ x2, int count, double* __restrict__ E_out,
                              int* __restrict__ nsol) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1250,10 +1469,97 @@ int check_device() {
 
 // The device part of a batch: scratch from the stream's pool, one persistent launch. Everything is a device pointer; no
 // synchronisation (the caller's stream order is the only dependency), so pipelines chain it with other kernels.
+// Round-synchronous driver (k_rs_*): chunks of pairs, per round one launch per phase over the chunk's active pairs. The host
+// reads the number of active pairs after every round (4 bytes), so unlike the fused kernel this path synchronises the stream.
+template <class Est>
+int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, const long long* d_off, const double* d_corr,
+                         const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
+                         uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
+  constexpr int kChunk = 4096;
+  const int C = std::min(np, kChunk);
+  int* d_idx = B.get<int>((size_t)total);
+  PairState* d_states = B.get<PairState>((size_t)C);
+  int* d_samples = B.get<int>((size_t)C * BI * 5);
+  Model* d_models = B.get<Model>((size_t)C * BI * MAXM);
+  double* d_cost = B.get<double>((size_t)C * BI * MAXM);
+  int* d_ninl = B.get<int>((size_t)C * BI * MAXM);
+  int* d_nm = B.get<int>((size_t)C * BI);
+  int* d_active = B.get<int>((size_t)2 * C);
+  int* d_count = B.get<int>(2);
+  unsigned long long* d_stats = B.get<unsigned long long>(10);
+  if (!d_idx || !d_states || !d_samples || !d_models || !d_cost || !d_ninl || !d_nm || !d_active || !d_count || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
+  THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
+  cudaEvent_t ev[5];
+  for (auto& e : ev) THB_CUDA_CHECK(cudaEventCreate(&e));
+  double phase_ms[4] = {0, 0, 0, 0};
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  long long* d_prof = getenv("THB_RS_PROF") ? B.get<long long>((size_t)C * BI) : nullptr;
+  int rc = THB_OK;
+  for (int pair0 = 0; pair0 < np && rc == THB_OK; pair0 += C) {
+    const int count = std::min(C, np - pair0);
+    cudaMemsetAsync(d_count, 0, sizeof(int) * 2, st);
+    k_rs_init<Est><<<count, 128, 0, st>>>(p, pair0, count, d_off, d_seed, d_res, d_mask, d_idx, d_states, d_active, d_count, d_thresh, d_rng, rng_mode, d_skip);
+    int na = 0, cur = 0;
+    if (cudaMemcpyAsync(&na, d_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = THB_E_CUDA; break; }
+    while (na > 0) {
+      int* act = d_active + (size_t)cur * C;
+      int* nxt = d_active + (size_t)(1 - cur) * C;
+      cudaEventRecord(ev[0], st);
+      k_rs_draw<Est><<<(na + 63) / 64, 64, 0, st>>>(na, act, d_states, d_idx, d_samples);
+      cudaEventRecord(ev[1], st);
+      k_rs_solve<Est><<<na, RT, 0, st>>>(na, act, d_states, d_corr, d_samples, d_models, d_nm, d_prof);
+      if (d_prof) {  // THB_RS_PROF: distribution of the per-hypothesis solve time (SM cycles)
+        std::vector<long long> h((size_t)na * BI);
+        cudaMemcpyAsync(h.data(), d_prof, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        std::vector<long long> v(h), cta_max;
+        for (int a2 = 0; a2 < na; ++a2) cta_max.push_back(*std::max_element(h.begin() + (size_t)a2 * BI, h.begin() + (size_t)(a2 + 1) * BI));
+        std::sort(v.begin(), v.end()); std::sort(cta_max.begin(), cta_max.end());
+        double mean = 0; for (long long x : v) mean += (double)x; mean /= (double)v.size();
+        double cmean = 0; for (long long x : cta_max) cmean += (double)x; cmean /= (double)cta_max.size();
+        fprintf(stderr, "RSPROF na=%d threads: mean %.0f p50 %lld p90 %lld p99 %lld max %lld | cta max: mean %.0f p50 %lld max %lld\n", na, mean, v[v.size() / 2],
+                v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back(), cmean, cta_max[cta_max.size() / 2], cta_max.back());
+      }
+      cudaEventRecord(ev[2], st);
+      k_rs_score<Est, 4, 6><<<na * (BI / 4), 128, 0, st>>>(p, act, d_states, d_corr, d_models, d_nm, d_cost, d_ninl);
+      cudaEventRecord(ev[3], st);
+      cudaMemsetAsync(d_count + (1 - cur), 0, sizeof(int), st);
+      k_rs_scan<Est><<<(na + 63) / 64, 64, 0, st>>>(p, na, act, d_states, d_models, d_nm, d_cost, d_ninl, nxt, d_count + (1 - cur));
+      cudaEventRecord(ev[4], st);
+      if (cudaMemcpyAsync(&na, d_count + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = THB_E_CUDA; break; }
+      for (int k = 0; k < 4; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) phase_ms[k] += ms; }
+      cur = 1 - cur;
+    }
+    if (rc != THB_OK) break;
+    k_rs_final<Est><<<(count + 3) / 4, 128, 0, st>>>(p, count, d_states, d_corr, d_seed, d_res, d_mask, d_stats, d_rng, rng_mode);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (rc != THB_OK) THB_FAIL(rc, "round-synchronous RANSAC: CUDA error");
+  THB_CUDA_CHECK(cudaGetLastError());
+  THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  // phase shares: device time of the phase kernels in nanoseconds (the fused kernel reports CTA cycles in the same fields)
+  g_last_stats.cycles_draw = (uint64_t)(phase_ms[0] * 1e6); g_last_stats.cycles_solve = (uint64_t)(phase_ms[1] * 1e6);
+  g_last_stats.cycles_score = (uint64_t)(phase_ms[2] * 1e6); g_last_stats.cycles_scan = (uint64_t)(phase_ms[3] * 1e6);
+  return THB_OK;
+}
+
 template <class Est>
 int launch_ransac(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, const long long* d_off, const double* d_corr,
                   const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
                   uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
+  {  // Small batches cannot fill the GPU with one CTA per pair: the round-synchronous kernels spread a pair over many CTAs
+     // (measured, C4-shaped pairs: 1 pair 2.5 vs ~6 ms, 16 pairs 4.7 vs 7.1 ms, 148 pairs 7.9 vs 9.4 ms, 1000 pairs 27.5 vs 29.1 ms;
+     // 10 000 pairs 215 vs 208 ms - there the fused kernel's mix of phases per SM wins). THB_RANSAC_MODE=fused|rounds forces one.
+    const char* m = getenv("THB_RANSAC_MODE");  // read per call: tests switch it
+    const int mode = !m ? 0 : std::string(m) == "fused" ? 1 : std::string(m) == "rounds" ? 2 : 0;
+    const bool rounds = mode == 2 || (mode == 0 && np <= 2048);
+    if (!(p.use_lo && Est::HAS_LO) && rounds)
+      return launch_ransac_rounds<Est>(st, B, p, np, d_off, d_corr, d_seed, total, d_res, d_mask, d_thresh, d_rng, rng_mode, d_skip);
+  }
   int* d_idx = B.get<int>((size_t)total);
   if (!d_idx) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   // Shared memory holds the control block only. Staging the pair's correspondences there was measured 20 % slower on C4

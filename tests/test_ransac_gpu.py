@@ -300,3 +300,34 @@ def test_lo_ransac_relative_pose_matches_oracle(lib, oracle, lo_start):
     def rot_err(r):
         return np.array([np.rad2deg(np.arccos(np.clip((np.trace(r["rotation"][i] @ gts[i][0].T) - 1) / 2, -1, 1))) for i in range(batch.num_pairs)])
     assert rot_err(res).mean() < 0.7 * rot_err(plain).mean()
+
+
+def test_fused_and_round_synchronous_paths_are_bit_identical(lib, oracle, monkeypatch):
+    """The two schedules of the same RANSAC loop (one CTA per pair vs one kernel per phase over all pairs, chosen by batch size)
+    must give the same records and masks bit for bit, for all three estimators, ragged pairs and per-pair early termination."""
+    batch, _ = synthetic.make_pair_batch(40, n=700, seed=21, base_seed=1234)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    out = {}
+    for mode in ("fused", "rounds"):
+        monkeypatch.setenv("THB_RANSAC_MODE", mode)
+        res = np.zeros(batch.num_pairs, capi.RELPOSE_DTYPE); mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
+        b = batch.struct()
+        capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None))
+        out[mode] = (res.copy(), mask.copy())
+    assert out["fused"][0].tobytes() == out["rounds"][0].tobytes()
+    np.testing.assert_array_equal(out["fused"][1], out["rounds"][1])
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, params)
+    np.testing.assert_array_equal(out["rounds"][1], omask)
+    np.testing.assert_array_equal(out["rounds"][0]["num_iterations"], ores["num_iterations"])
+    for make, entry in ((synthetic.make_abspose_batch, "thb_ransac_abspose_batch"), (synthetic.make_homography_batch, "thb_ransac_homography_batch")):
+        hb, _ = make(12, n=300, seed=5)
+        params.error_thresh = (3e-3) ** 2
+        got = {}
+        for mode in ("fused", "rounds"):
+            monkeypatch.setenv("THB_RANSAC_MODE", mode)
+            res = np.zeros(hb.num_pairs, capi.RELPOSE_DTYPE); mask = np.zeros(int(hb.pair_offset[-1]), np.uint8)
+            bb = hb.struct()
+            capi.check(getattr(lib, entry)(C.byref(bb), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None))
+            got[mode] = (res.tobytes(), mask.copy())
+        assert got["fused"][0] == got["rounds"][0]
+        np.testing.assert_array_equal(got["fused"][1], got["rounds"][1])
