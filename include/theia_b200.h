@@ -456,7 +456,7 @@ typedef struct ThbTrackBaResult {
  * from a thread pool (sfm/estimate_track.cc:286-290). problem->cam_const / intr_const are ignored (everything but the
  * points is constant), problem->pt_const selects the tracks, options as for thb_ba_solve (use_inner_iterations must be 0,
  * as BundleAdjustTrack forces, bundle_adjustment.cc:267). Refines problem->pts in place; results [num_points] may be NULL.
- * Host memory only for now (THB_E_UNSUPPORTED for THB_MEM_DEVICE).
+ * Any memory space (results in problem->memory_space); the observations are grouped by track on the device.
  */
 int thb_ba_tracks_batch(const ThbBaProblem* problem, const ThbBaOptions* options, ThbTrackBaResult* results, void* cuda_stream);
 
@@ -482,7 +482,7 @@ typedef struct ThbTrackEstimatorOptions {
  * Camera::PixelToUnitDepthRay(feature).normalized() gives, estimate_track.cc:80-87), BundleAdjustTrack, and the
  * reprojection test (AcceptableReprojectionError, :93-119). status [num_points] receives THB_TRACK_*; problem->pts is
  * written for THB_TRACK_ESTIMATED tracks only (the caller sets those estimated); ba_results may be NULL. The starting
- * values in problem->pts are ignored. Host memory only for now.
+ * values in problem->pts are ignored. Any memory space (ray_directions, status and ba_results in problem->memory_space).
  */
 int thb_estimate_tracks_batch(const ThbBaProblem* problem, const double* ray_directions, const ThbTrackEstimatorOptions* options,
                               const ThbBaOptions* ba_options, int32_t* status, ThbTrackBaResult* ba_results, void* cuda_stream);

@@ -1230,12 +1230,15 @@ int thb_dense_spd_time(int32_t n, int32_t repeats, double* avg_ms, double* rel_r
 
 }  // extern "C"
 namespace {
-// shared by thb_ba_tracks_batch (rays == nullptr) and thb_estimate_tracks_batch
+// shared by thb_ba_tracks_batch (rays == nullptr) and thb_estimate_tracks_batch. Host or device buffers: the observations are
+// grouped by track ON THE DEVICE (histogram + stable radix sort, as the BA setup), so a host caller pays one H2D of its arrays
+// and a device caller pays nothing but the kernels.
 int RunTrackBatch(const ThbBaProblem* P, const ThbBaOptions* O, const double* rays, const ThbTrackEstimatorOptions* E, int32_t* status,
                   ThbTrackBaResult* results, void* cuda_stream) {
   if (!P || !O) THB_FAIL(THB_E_INVALID_ARGUMENT, "null problem or options");
   if (O->use_inner_iterations) THB_FAIL(THB_E_UNSUPPORTED, "BundleAdjustTrack runs without inner iterations (bundle_adjustment.cc:267)");
-  if (P->memory_space != THB_MEM_HOST) THB_FAIL(THB_E_UNSUPPORTED, "thb_ba_tracks_batch takes host buffers");
+  const int sp = P->memory_space;
+  if (sp != THB_MEM_HOST && sp != THB_MEM_DEVICE) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad memory_space");
   int rc = CheckDevice();
   if (rc != THB_OK) return rc;
   const int nc = P->num_cameras, ng = P->num_groups, np = P->num_points, no = P->num_observations;
@@ -1243,65 +1246,84 @@ int RunTrackBatch(const ThbBaProblem* P, const ThbBaOptions* O, const double* ra
   if (np == 0) return THB_OK;
   if (!P->pts || (no > 0 && (!P->cam_ext || !P->cam_group || !P->intr || !P->intr_model || !P->obs_cam || !P->obs_pt || !P->obs_xy)))
     THB_FAIL(THB_E_INVALID_ARGUMENT, "null array");
-  for (int g = 0; g < ng; ++g) if (num_intrinsics(P->intr_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
-  for (int c = 0; c < nc; ++c) if (P->cam_group[c] < 0 || P->cam_group[c] >= ng) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
-  // observations grouped by track (stable counting sort), as AddTrack walks track->ViewIds()
-  std::vector<int> start(np + 1, 0), h_cam(no);
-  std::vector<double> h_xy((size_t)no * 2), h_si((size_t)no * 2), h_ray(rays ? (size_t)no * 3 : 0);
-  for (int i = 0; i < no; ++i) {
-    if (P->obs_cam[i] < 0 || P->obs_cam[i] >= nc || P->obs_pt[i] < 0 || P->obs_pt[i] >= np) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
-    ++start[P->obs_pt[i] + 1];
-  }
-  for (int p = 0; p < np; ++p) start[p + 1] += start[p];
-  {
-    std::vector<int> cursor(start.begin(), start.end() - 1);
-    for (int i = 0; i < no; ++i) {
-      const int q = cursor[P->obs_pt[i]]++;
-      h_cam[q] = P->obs_cam[i];
-      h_xy[2 * (size_t)q] = P->obs_xy[2 * (size_t)i]; h_xy[2 * (size_t)q + 1] = P->obs_xy[2 * (size_t)i + 1];
-      h_si[2 * (size_t)q] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i] : 1.0;
-      h_si[2 * (size_t)q + 1] = P->obs_sqrt_info ? P->obs_sqrt_info[2 * (size_t)i + 1] : 1.0;
-      if (rays) for (int k = 0; k < 3; ++k) h_ray[3 * (size_t)q + k] = rays[3 * (size_t)i + k];
-    }
-  }
+  std::vector<int> h_model;
+  if ((rc = FetchToHost(P->intr_model, ng, sp, &h_model)) != THB_OK) return rc;
+  for (int g = 0; g < ng; ++g) if (num_intrinsics(h_model[g]) < 0) THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path");
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool host = sp == THB_MEM_HOST;
+  const cudaMemcpyKind kin = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, kout = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
   const int PD = O->use_homogeneous_point_parametrization ? 3 : 4;
   // stream-ordered blocks from the device pool (kept across calls: TrackEstimator calls this once per batch of new tracks)
   ConfigurePoolOnce();
   struct ScopedArena : Arena { ~ScopedArena() { Release(); } } M;
   M.st = st;
   BaState X{}, Xc{};
-  int *d_group = nullptr, *d_model = nullptr, *d_start = nullptr, *d_oc = nullptr;
+  int *d_group = nullptr, *d_model = nullptr, *d_start = nullptr, *d_cstart = nullptr, *d_used = nullptr, *d_flags = nullptr, *d_perm = nullptr, *d_oc = nullptr,
+      *d_op = nullptr, *d_raw_cam = nullptr, *d_raw_pt = nullptr;
   uint8_t *d_cc = nullptr, *d_pc = nullptr;
-  double2 *d_xy = nullptr, *d_si = nullptr;
-  double* d_ps = nullptr;
+  double2 *d_xy = nullptr, *d_si = nullptr, *d_raw_xy = nullptr, *d_raw_si = nullptr;
+  double *d_ps = nullptr, *d_orig = nullptr, *d_ray = nullptr, *d_raw_ray = nullptr;
+  int* d_status = nullptr;
   ThbTrackBaResult* d_res = nullptr;
+  const size_t no1 = std::max(no, 1);
   if ((rc = M.Get(&X.cam, (size_t)nc * 6)) != THB_OK || (rc = M.Get(&X.camd, (size_t)nc * CAMD)) != THB_OK || (rc = M.Get(&X.intr, (size_t)ng * KS)) != THB_OK ||
-      (rc = M.Get(&X.pts, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_group, nc)) != THB_OK || (rc = M.Get(&d_model, ng)) != THB_OK ||
-      (rc = M.Get(&d_start, np + 1)) != THB_OK || (rc = M.Get(&d_oc, no)) != THB_OK || (rc = M.Get(&d_cc, nc)) != THB_OK || (rc = M.Get(&d_pc, np)) != THB_OK ||
-      (rc = M.Get(&d_xy, no)) != THB_OK || (rc = M.Get(&d_si, no)) != THB_OK || (rc = M.Get(&d_ps, (size_t)np * PD)) != THB_OK || (rc = M.Get(&d_res, np)) != THB_OK)
+      (rc = M.Get(&X.pts, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_orig, (size_t)np * 4)) != THB_OK || (rc = M.Get(&d_group, nc)) != THB_OK ||
+      (rc = M.Get(&d_model, ng)) != THB_OK || (rc = M.Get(&d_start, np + 1)) != THB_OK || (rc = M.Get(&d_cstart, nc + 1)) != THB_OK ||
+      (rc = M.Get(&d_used, std::max(ng, 1))) != THB_OK || (rc = M.Get(&d_flags, SF_COUNT)) != THB_OK || (rc = M.Get(&d_perm, no1)) != THB_OK ||
+      (rc = M.Get(&d_oc, no1)) != THB_OK || (rc = M.Get(&d_op, no1)) != THB_OK || (rc = M.Get(&d_cc, std::max(nc, 1))) != THB_OK || (rc = M.Get(&d_pc, np)) != THB_OK ||
+      (rc = M.Get(&d_xy, no1)) != THB_OK || (rc = M.Get(&d_si, no1)) != THB_OK || (rc = M.Get(&d_ps, (size_t)np * PD)) != THB_OK || (rc = M.Get(&d_res, np)) != THB_OK)
     return rc;
   Xc = X;
   if ((rc = M.Get(&Xc.pts, (size_t)np * 4)) != THB_OK) return rc;
-  double* d_ray = nullptr;
-  int* d_status = nullptr;
-  if (rays) {
-    if ((rc = M.Get(&d_ray, (size_t)no * 3)) != THB_OK || (rc = M.Get(&d_status, np)) != THB_OK) return rc;
-    THB_CUDA_CHECK(cudaMemcpyAsync(d_ray, h_ray.data(), sizeof(double) * 3 * no, cudaMemcpyHostToDevice, st));
+  // the caller's observation arrays: used in place when they are device memory
+  const int *raw_cam = P->obs_cam, *raw_pt = P->obs_pt;
+  const double2 *raw_xy = reinterpret_cast<const double2*>(P->obs_xy), *raw_si = reinterpret_cast<const double2*>(P->obs_sqrt_info);
+  const double* raw_ray = rays;
+  if (host && no > 0) {
+    if ((rc = M.Get(&d_raw_cam, no1)) != THB_OK || (rc = M.Get(&d_raw_pt, no1)) != THB_OK || (rc = M.Get(&d_raw_xy, no1)) != THB_OK) return rc;
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_raw_cam, P->obs_cam, sizeof(int) * no, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_raw_pt, P->obs_pt, sizeof(int) * no, cudaMemcpyHostToDevice, st));
+    THB_CUDA_CHECK(cudaMemcpyAsync(d_raw_xy, P->obs_xy, sizeof(double2) * no, cudaMemcpyHostToDevice, st));
+    raw_cam = d_raw_cam; raw_pt = d_raw_pt; raw_xy = d_raw_xy;
+    if (P->obs_sqrt_info) {
+      if ((rc = M.Get(&d_raw_si, no1)) != THB_OK) return rc;
+      THB_CUDA_CHECK(cudaMemcpyAsync(d_raw_si, P->obs_sqrt_info, sizeof(double2) * no, cudaMemcpyHostToDevice, st));
+      raw_si = d_raw_si;
+    }
+    if (rays) {
+      if ((rc = M.Get(&d_raw_ray, (size_t)no1 * 3)) != THB_OK) return rc;
+      THB_CUDA_CHECK(cudaMemcpyAsync(d_raw_ray, rays, sizeof(double) * 3 * no, cudaMemcpyHostToDevice, st));
+      raw_ray = d_raw_ray;
+    }
   }
-  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, P->pts, sizeof(double) * np * 4, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, P->cam_group, sizeof(int) * nc, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, P->intr_model, sizeof(int) * ng, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_start, start.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_oc, h_cam.data(), sizeof(int) * no, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_xy, h_xy.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(d_si, h_si.data(), sizeof(double) * 2 * no, cudaMemcpyHostToDevice, st));
-  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, THB_CAM_CONST_ALL, nc, st));
-  if (P->pt_const) THB_CUDA_CHECK(cudaMemcpyAsync(d_pc, P->pt_const, np, cudaMemcpyHostToDevice, st));
+  if (rays && ((rc = M.Get(&d_ray, (size_t)no1 * 3)) != THB_OK || (rc = M.Get(&d_status, np)) != THB_OK)) return rc;
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.cam, P->cam_ext, sizeof(double) * nc * 6, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.intr, P->intr, sizeof(double) * ng * KS, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_orig, P->pts, sizeof(double) * np * 4, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(X.pts, d_orig, sizeof(double) * np * 4, cudaMemcpyDeviceToDevice, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_group, P->cam_group, sizeof(int) * nc, kin, st));
+  THB_CUDA_CHECK(cudaMemcpyAsync(d_model, h_model.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cc, THB_CAM_CONST_ALL, std::max(nc, 1), st));
+  if (P->pt_const) THB_CUDA_CHECK(cudaMemcpyAsync(d_pc, P->pt_const, np, kin, st));
   else THB_CUDA_CHECK(cudaMemsetAsync(d_pc, 0, np, st));
-  k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc, nullptr, d_cc, d_group);
+  THB_CUDA_CHECK(cudaMemsetAsync(d_start, 0, sizeof(int) * (np + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_cstart, 0, sizeof(int) * (nc + 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_used, 0, sizeof(int) * std::max(ng, 1), st));
+  THB_CUDA_CHECK(cudaMemsetAsync(d_flags, 0, sizeof(int) * SF_COUNT, st));
+  if (nc > 0) k_setup_check_groups<<<cdiv(nc, 256), 256, 0, st>>>(nc, ng, d_group, d_flags);
+  if (no > 0) k_setup_count<<<cdiv(no, 256), 256, 0, st>>>(no, nc, np, ng, raw_cam, raw_pt, d_group, d_start, d_cstart, d_used, d_flags);
+  int h_flags[SF_COUNT];
+  THB_CUDA_CHECK(cudaMemcpyAsync(h_flags, d_flags, sizeof(h_flags), cudaMemcpyDeviceToHost, st));
+  THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_flags[SF_BAD_GROUP]) THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range");
+  if (h_flags[SF_BAD_INDEX]) THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range");
+  // observations grouped by track, in the caller's order inside a track (stable), as AddTrack walks track->ViewIds()
+  if ((rc = GroupByKey(raw_pt, no, np, d_start, d_perm, st)) != THB_OK) return rc;
+  if (no > 0) {
+    k_setup_gather<<<cdiv(no, 256), 256, 0, st>>>(no, d_perm, raw_cam, raw_pt, raw_xy, raw_si, d_oc, d_op, d_xy, d_si);
+    if (rays) k_gather_rays<<<cdiv(no, 256), 256, 0, st>>>(no, d_perm, raw_ray, d_ray);
+  }
+  if (nc > 0) k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(X.cam, X.camd, nc, nullptr, d_cc, d_group);
   BaConst K{};
   K.nc = nc; K.ng = ng; K.np = np; K.no = no;
   K.cam_group = d_group; K.intr_model = d_model; K.cam_const = d_cc; K.intr_const = nullptr; K.pt_const = d_pc; K.intr_slot = nullptr;
@@ -1333,17 +1355,12 @@ int RunTrackBatch(const ThbBaProblem* P, const ThbBaOptions* O, const double* ra
     fprintf(stderr, "k_track_ba<%d>: %d tracks, %d-thread CTAs, %.3f ms\n", PD, np, cta, ms);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
   }
-  std::vector<ThbTrackBaResult> h_res(np);
-  std::vector<double> h_pts((size_t)np * 4);
-  THB_CUDA_CHECK(cudaMemcpyAsync(h_res.data(), d_res, sizeof(ThbTrackBaResult) * np, cudaMemcpyDeviceToHost, st));
-  THB_CUDA_CHECK(cudaMemcpyAsync(h_pts.data(), X.pts, sizeof(double) * np * 4, cudaMemcpyDeviceToHost, st));
-  if (rays) THB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, st));
+  // IsSolutionUsable() == false leaves the track as it was; EstimateTrack keeps only estimated tracks
+  k_track_commit<<<cdiv(np, 256), 256, 0, st>>>(np, d_status, d_res, X.pts, d_orig);
+  THB_CUDA_CHECK(cudaMemcpyAsync(P->pts, d_orig, sizeof(double) * np * 4, kout, st));
+  if (results) THB_CUDA_CHECK(cudaMemcpyAsync(results, d_res, sizeof(ThbTrackBaResult) * np, kout, st));
+  if (rays) THB_CUDA_CHECK(cudaMemcpyAsync(status, d_status, sizeof(int32_t) * np, kout, st));
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
-  for (int p = 0; p < np; ++p) {  // IsSolutionUsable() == false leaves the track as it was; EstimateTrack keeps only estimated tracks
-    const bool keep = rays ? status[p] == THB_TRACK_ESTIMATED : (h_res[p].num_iterations >= 0 && h_res[p].termination_type != THB_TERM_FAILURE);
-    if (keep) for (int k = 0; k < 4; ++k) P->pts[4 * (size_t)p + k] = h_pts[4 * (size_t)p + k];
-    if (results) results[p] = h_res[p];
-  }
   return THB_OK;
 }
 }  // namespace

@@ -297,6 +297,24 @@ __global__ void __launch_bounds__(128) k_outlier_tracks(BaConst K, BaState St, c
   if (st > 0) atomicAdd(removed, 1);
 }
 
+// rays in the track-major order of the gathered observations
+__global__ void k_gather_rays(int no, const int* __restrict__ perm, const double* __restrict__ raw, double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= no) return;
+  const int i = perm[q];
+  out[3 * (size_t)q] = raw[3 * (size_t)i]; out[3 * (size_t)q + 1] = raw[3 * (size_t)i + 1]; out[3 * (size_t)q + 2] = raw[3 * (size_t)i + 2];
+}
+
+// the caller's points receive the refined track only when the reference would keep it (status == nullptr: BundleAdjustTrack,
+// a usable solution; else EstimateTrack: THB_TRACK_ESTIMATED)
+__global__ void k_track_commit(int np, const int* __restrict__ status, const ThbTrackBaResult* __restrict__ res, const double* __restrict__ refined,
+                               double* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const bool keep = status ? status[p] == THB_TRACK_ESTIMATED : (res[p].num_iterations >= 0 && res[p].termination_type != THB_TERM_FAILURE);
+  if (keep) for (int k = 0; k < 4; ++k) out[4 * (size_t)p + k] = refined[4 * (size_t)p + k];
+}
+
 // ---- SelectGoodTracksForBundleAdjustment (select_good_tracks_for_bundle_adjustment.cc:263-325) --------------------------
 // ComputeStatisticsForTrack (:80-107), one thread per track: truncated length and mean squared reprojection error.
 __global__ void __launch_bounds__(128) k_track_stats(BaConst K, BaState St, const int* __restrict__ pt_start, const int* __restrict__ perm,

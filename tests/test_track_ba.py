@@ -311,3 +311,45 @@ def test_select_good_tracks_batch_matches_oracle(lib, oracle, case):
                                                 C.c_void_p(d_sel.data_ptr()), C.byref(count), None))
     np.testing.assert_array_equal(d_sel.cpu().numpy() != 0, sel_o != 0)
     assert lib.thb_select_good_tracks_batch(C.byref(p), None, 10, 0, 100, sel.ctypes.data_as(C.c_void_p), None, None) == capi.THB_E_INVALID_ARGUMENT
+
+
+def test_track_entries_take_device_memory(lib):
+    """thb_ba_tracks_batch / thb_estimate_tracks_batch with every pointer in HBM (the C5 pipeline keeps the scene on the device):
+    identical results to the host-buffer call, observations in arbitrary (not track-major) order."""
+    import torch
+    prob = perturbed(10, 600, 4, seed=77)
+    order = np.random.default_rng(5).permutation(prob.num_observations)          # shuffled: the grouping happens on the device
+    for k in ("obs_cam", "obs_pt", "obs_xy", "obs_sqrt_info"):
+        if prob.a[k] is not None:
+            prob.a[k] = np.ascontiguousarray(prob.a[k][order])
+    prob = capi.HostBaProblem(prob.a)
+    opts = capi.default_options(lib); opts.use_inner_iterations = 0
+    host = prob.copy()
+    res_h = gpu_tracks(lib, host, opts)
+
+    def to_device(p):
+        dev = {k: (None if v is None else torch.from_numpy(v).cuda()) for k, v in p.a.items()}
+        pd = p.struct(); pd.memory_space = capi.THB_MEM_DEVICE
+        for k, v in dev.items():
+            setattr(pd, k, None if v is None else v.data_ptr())
+        return dev, pd
+    dev, pd = to_device(prob.copy())
+    d_res = torch.zeros(prob.num_points * capi.TRACK_BA_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    capi.check(lib.thb_ba_tracks_batch(C.byref(pd), C.byref(opts), C.c_void_p(d_res.data_ptr()), None))
+    res_d = d_res.cpu().numpy().view(capi.TRACK_BA_DTYPE)
+    assert res_d.tobytes() == res_h.tobytes()
+    np.testing.assert_array_equal(dev["pts"].cpu().numpy(), host.a["pts"])
+    # EstimateTrack for all tracks, device memory against host memory
+    rays = pinhole_rays(prob)
+    eopts = capi.ThbTrackEstimatorOptions()
+    eopts.min_triangulation_angle_degrees = 2.0; eopts.bundle_adjustment = 1
+    ph = prob.copy()
+    status_h, res_h2 = gpu_estimate(lib, ph, rays, eopts, opts)
+    dev, pd = to_device(prob.copy())
+    d_rays = torch.from_numpy(np.ascontiguousarray(rays)).cuda()
+    d_status = torch.zeros(prob.num_points, dtype=torch.int32, device="cuda")
+    capi.check(lib.thb_estimate_tracks_batch(C.byref(pd), C.c_void_p(d_rays.data_ptr()), C.byref(eopts), C.byref(opts),
+                                             C.c_void_p(d_status.data_ptr()), C.c_void_p(d_res.data_ptr()), None))
+    np.testing.assert_array_equal(d_status.cpu().numpy(), status_h)
+    np.testing.assert_array_equal(dev["pts"].cpu().numpy(), ph.a["pts"])
+    assert (status_h == capi.TRACK_ESTIMATED).sum() > 0
