@@ -804,6 +804,45 @@ double Score(const ThbRansacParams& P, const double* data, int n, const Model& m
 }
 
 // SampleConsensusEstimator::Estimate (sample_consensus_estimator.h:299-415) with RandomSampler (random_sampler.cc:53-72)
+// ProsacSampler (solvers/prosac_sampler.cc:53-131): the k-th sample draws from the top n data points (data sorted by quality),
+// n grown by the schedule of Chum & Matas (Eq. 3-5) with T_N = 20000. The reference recomputes the schedule from t = 1 on every
+// call; carrying (t_n, t_n_prime, n) from call to call performs the same operations in the same order. Its last index `n` can
+// equal the number of data points once the schedule has reached the whole set (an out-of-bounds read there): clamped here.
+struct ProsacSampler {
+  double t_n = 0.0, t_n_prime = 1.0;
+  int n = 0, k = 1, N = 0, m = 0;
+  void Initialize(int num_datapoints, int min_num_samples) {
+    N = num_datapoints; m = min_num_samples; k = 1; n = m; t_n_prime = 1.0;
+    t_n = 20000.0;
+    for (int i = 0; i < m; ++i) t_n *= static_cast<double>(n - i) / (N - i);
+  }
+  void Sample(std::mt19937& gen, int* subset) {
+    const int t = k;  // the schedule step of this call (the reference's loop body for t = k)
+    if (t > t_n_prime && n < N) {
+      const double t_n_plus1 = (t_n * (n + 1.0)) / (n + 1.0 - m);
+      t_n_prime += std::ceil(t_n_plus1 - t_n);
+      t_n = t_n_plus1;
+      ++n;
+    }
+    auto draw_unique = [&](int count, int hi) {
+      for (int i = 0; i < count; ++i) {
+        int r;
+        bool dup;
+        do {
+          std::uniform_int_distribution<int> dist(0, hi);
+          r = dist(gen);
+          dup = false;
+          for (int j = 0; j < i; ++j) dup |= subset[j] == r;
+        } while (dup);
+        subset[i] = r;
+      }
+    };
+    if (t_n_prime < k) draw_unique(m, n - 1);
+    else { draw_unique(m - 1, n - 2); subset[m - 1] = std::min(n, N - 1); }
+    ++k;
+  }
+};
+
 template <class Est>
 void EstimatePairWith(std::mt19937& gen, const ThbRansacParams& P, const double* data, int n, ThbRelPoseResult* out, uint8_t* mask);
 template <class Est>
@@ -833,13 +872,21 @@ void EstimatePairWith(std::mt19937& gen, const ThbRansacParams& P, const double*
     inl_data.resize(idx.size() * Est::D);
     for (size_t q = 0; q < idx.size(); ++q) for (int k = 0; k < Est::D; ++k) inl_data[q * Est::D + k] = data[Est::D * (size_t)idx[q] + k];
   };
+  ProsacSampler prosac;
+  if (P.ransac_type == 1) prosac.Initialize(n, S);
   int it;
   for (it = 0; it < max_iterations; ++it) {
     double sample[S * Est::D];
-    for (int i = 0; i < S; ++i) {
-      std::uniform_int_distribution<int> dist(i, n - 1);
-      std::swap(sample_indices[i], sample_indices[dist(gen)]);
-      for (int k = 0; k < Est::D; ++k) sample[Est::D * i + k] = data[Est::D * (size_t)sample_indices[i] + k];
+    if (P.ransac_type == 1) {  // RansacType::PROSAC (create_and_initialize_ransac_variant.h)
+      int subset[S];
+      prosac.Sample(gen, subset);
+      for (int i = 0; i < S; ++i) for (int k = 0; k < Est::D; ++k) sample[Est::D * i + k] = data[Est::D * (size_t)subset[i] + k];
+    } else {
+      for (int i = 0; i < S; ++i) {
+        std::uniform_int_distribution<int> dist(i, n - 1);
+        std::swap(sample_indices[i], sample_indices[dist(gen)]);
+        for (int k = 0; k < Est::D; ++k) sample[Est::D * i + k] = data[Est::D * (size_t)sample_indices[i] + k];
+      }
     }
     Model models[Est::MAXM];
     const int nm = Est::Solve(sample, models);
@@ -1017,7 +1064,7 @@ int RunBatch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* 
   if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
   if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
       p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) return THB_E_INVALID_ARGUMENT;
-  if ((p->use_lo && !Est::HAS_LO) || p->ransac_type != 0) return THB_E_UNSUPPORTED;
+  if ((p->use_lo && !Est::HAS_LO) || (p->ransac_type != 0 && p->ransac_type != 1)) return THB_E_UNSUPPORTED;
   const int nt = threads > 0 ? threads : omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
   for (int i = 0; i < b->num_pairs; ++i) {

@@ -869,6 +869,43 @@ __device__ int mt_uniform_int(Mt19937* g, int lo, int hi) {
   return lo + (int)(product >> 32);
 }
 
+// ProsacSampler (solvers/prosac_sampler.cc:53-131), RansacType::PROSAC: the k-th sample comes from the top n data points of a
+// quality-sorted input, n grown by the schedule of Chum & Matas with T_N = 20000. The reference recomputes the schedule from
+// t = 1 on every call; carrying (t_n, t_n_prime, n) performs the same operations in the same order. Its last index `n` may equal
+// the number of data points once the schedule covers the whole set (an out-of-bounds read in the reference): clamped.
+struct ProsacState {
+  double t_n, t_n_prime;
+  int n, k, N, m;
+};
+__device__ void prosac_init(ProsacState* s, int num_datapoints, int min_num_samples) {
+  s->N = num_datapoints; s->m = min_num_samples; s->k = 1; s->n = min_num_samples; s->t_n_prime = 1.0;
+  double t_n = 20000.0;
+  for (int i = 0; i < min_num_samples; ++i) t_n *= (double)(s->n - i) / (double)(num_datapoints - i);
+  s->t_n = t_n;
+}
+__device__ void prosac_sample(ProsacState* s, Mt19937* g, int* subset) {
+  if ((double)s->k > s->t_n_prime && s->n < s->N) {
+    const double t_n_plus1 = (s->t_n * (s->n + 1.0)) / (s->n + 1.0 - s->m);
+    s->t_n_prime += ceil(t_n_plus1 - s->t_n);
+    s->t_n = t_n_plus1;
+    ++s->n;
+  }
+  const bool from_top_n = s->t_n_prime < (double)s->k;
+  const int count = from_top_n ? s->m : s->m - 1, hi = from_top_n ? s->n - 1 : s->n - 2;
+  for (int i = 0; i < count; ++i) {
+    int r;
+    bool dup;
+    do {
+      r = mt_uniform_int(g, 0, hi);
+      dup = false;
+      for (int j = 0; j < i; ++j) dup |= subset[j] == r;
+    } while (dup);
+    subset[i] = r;
+  }
+  if (!from_top_n) subset[s->m - 1] = s->n < s->N - 1 ? s->n : s->N - 1;
+  ++s->k;
+}
+
 // SampleConsensusEstimator::ComputeMaxIterations (sample_consensus_estimator.h:251-297)
 __device__ int compute_max_iterations(const ThbRansacParams& P, double min_sample_size, double inlier_ratio,
                                       double log_failure_prob, int total) {
@@ -931,6 +968,7 @@ struct RansacShared {
   int model_start[BI + 1];
   int samples[BI][5];  // up to 5 indices per sample
   Mt19937 rng;
+  ProsacState prosac;
   double best_cost;
   int max_iterations, it0, finished, num_iterations, have_best, pair;
   unsigned long long stat_samples, stat_models, stat_data;
@@ -1003,6 +1041,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRans
     S.cyc[0] = S.cyc[1] = S.cyc[2] = S.cyc[3] = 0;
     S.num_lo = 0;
     memset(&S.best, 0, sizeof(Model));
+    if (P.ransac_type == 1) prosac_init(&S.prosac, n, SS);
   }
   __syncthreads();
   while (true) {
@@ -1014,13 +1053,17 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRans
     // ---- draw
     long long tick = clock64();
     if (t == 0) {
-      for (int b = 0; b < nit; ++b)
-        for (int i = 0; i < SS; ++i) {
-          const int j = mt_uniform_int(&S.rng, i, n - 1);
-          const int a = sidx[i], c = sidx[j];
-          sidx[i] = c; sidx[j] = a;
-          S.samples[b][i] = c;
-        }
+      if (P.ransac_type == 1) {
+        for (int b = 0; b < nit; ++b) prosac_sample(&S.prosac, &S.rng, S.samples[b]);
+      } else {
+        for (int b = 0; b < nit; ++b)
+          for (int i = 0; i < SS; ++i) {
+            const int j = mt_uniform_int(&S.rng, i, n - 1);
+            const int a = sidx[i], c = sidx[j];
+            sidx[i] = c; sidx[j] = a;
+            S.samples[b][i] = c;
+          }
+      }
     }
     __syncthreads();
     if (t == 0) { const long long now = clock64(); S.cyc[0] += now - tick; tick = now; }
@@ -1195,6 +1238,7 @@ __global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_ransac(const ThbRans
 // per SM (188-210 ms with a grid-stride loop), 8- and 16-warp score CTAs (67 / 77 vs 64 ms).
 struct PairState {
   Mt19937 rng;
+  ProsacState prosac;
   Model best;
   double best_cost, thresh;
   long long off;
@@ -1238,6 +1282,7 @@ __global__ void __launch_bounds__(128) k_rs_init(const ThbRansacParams P, int pa
     S.off = off; S.n = n; S.pair = pair; S.it0 = 0; S.num_iterations = 0; S.have_best = 0; S.nit = 0;
     S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
     memset(&S.best, 0, sizeof(Model));
+    if (P.ransac_type == 1) prosac_init(&S.prosac, n, Est::S);
     if (S.it0 >= S.max_iterations) S.num_iterations = S.it0;  // finished before the first round
     else active[atomicAdd(&counters[0], 1)] = slot;
   }
@@ -1245,8 +1290,8 @@ __global__ void __launch_bounds__(128) k_rs_init(const ThbRansacParams P, int pa
 
 // draw: RandomSampler for the BI iterations of this round, one pair per thread (the generator is sequential)
 template <class Est>
-__global__ void __launch_bounds__(64) k_rs_draw(int na, const int* __restrict__ active, PairState* __restrict__ states, int* __restrict__ idx_ws,
-                                                int* __restrict__ samples) {
+__global__ void __launch_bounds__(64) k_rs_draw(int ransac_type, int na, const int* __restrict__ active, PairState* __restrict__ states,
+                                                int* __restrict__ idx_ws, int* __restrict__ samples) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= na) return;
   const int slot = active[a];
@@ -1254,13 +1299,17 @@ __global__ void __launch_bounds__(64) k_rs_draw(int na, const int* __restrict__ 
   const int n = S.n, nit = min(BI, S.max_iterations - S.it0);
   int* sidx = idx_ws + S.off;
   int* out = samples + (size_t)slot * BI * 5;
-  for (int b = 0; b < nit; ++b)
-    for (int i = 0; i < Est::S; ++i) {
-      const int j = mt_uniform_int(&S.rng, i, n - 1);
-      const int u = sidx[i], c = sidx[j];
-      sidx[i] = c; sidx[j] = u;
-      out[b * 5 + i] = c;
-    }
+  if (ransac_type == 1) {
+    for (int b = 0; b < nit; ++b) prosac_sample(&S.prosac, &S.rng, out + b * 5);
+  } else {
+    for (int b = 0; b < nit; ++b)
+      for (int i = 0; i < Est::S; ++i) {
+        const int j = mt_uniform_int(&S.rng, i, n - 1);
+        const int u = sidx[i], c = sidx[j];
+        sidx[i] = c; sidx[j] = u;
+        out[b * 5 + i] = c;
+      }
+  }
   S.nit = nit;
   S.stat_samples += nit;
 }
@@ -1508,7 +1557,7 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
       int* act = d_active + (size_t)cur * C;
       int* nxt = d_active + (size_t)(1 - cur) * C;
       cudaEventRecord(ev[0], st);
-      k_rs_draw<Est><<<(na + 63) / 64, 64, 0, st>>>(na, act, d_states, d_idx, d_samples);
+      k_rs_draw<Est><<<(na + 63) / 64, 64, 0, st>>>(p.ransac_type, na, act, d_states, d_idx, d_samples);
       cudaEventRecord(ev[1], st);
       k_rs_solve<Est><<<na, RT, 0, st>>>(na, act, d_states, d_corr, d_samples, d_models, d_nm, d_prof);
       if (d_prof) {  // THB_RS_PROF: distribution of the per-hypothesis solve time (SM cycles)
@@ -1599,7 +1648,7 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
     // HomographyEstimator has no RefineModel: the reference's LO branch is a `continue` that only skips the iteration-bound update
     THB_FAIL(THB_E_UNSUPPORTED, "use_lo is only implemented for the relative-pose estimator");
   }
-  if (p->ransac_type != 0) THB_FAIL(THB_E_UNSUPPORTED, "only RansacType::RANSAC is implemented");
+  if (p->ransac_type != 0 && p->ransac_type != 1) THB_FAIL(THB_E_UNSUPPORTED, "RansacType::RANSAC and PROSAC are implemented (LMED, EXHAUSTIVE are not)");
   if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
   if (b->num_pairs == 0) return THB_OK;
   if (!b->pair_offset || !b->seed) THB_FAIL(THB_E_INVALID_ARGUMENT, "null batch array");

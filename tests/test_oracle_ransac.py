@@ -305,3 +305,23 @@ def test_absolute_pose_and_homography_ransac(oracle):
         assert res["success"][i] == 1 and equal_up_to_scale(res["essential_matrix"][i], H, 2e-2)
         m = mask[batch.pair_offset[i]: batch.pair_offset[i + 1]].astype(bool)
         assert (m & flags).sum() >= 0.75 * flags.sum() and (m & ~flags).sum() <= 0.05 * (~flags).sum()
+
+
+def test_prosac_needs_fewer_iterations_on_quality_sorted_data(oracle):
+    """RansacType::PROSAC (solvers/prosac_sampler.cc:53-131): with the inliers sorted to the front the progressive sampler finds the
+    model in far fewer iterations than the uniform sampler, and the model has the same support."""
+    batch, _ = synthetic.make_pair_batch(12, n=500, seed=8, base_seed=55)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    rc, res, mask = oracle.ransac_relpose_batch(batch, params)
+    lists = []
+    for p in range(batch.num_pairs):
+        a, b = int(batch.pair_offset[p]), int(batch.pair_offset[p + 1])
+        lists.append(batch.corr[a:b][np.argsort(-mask[a:b].astype(np.int32), kind="stable")])
+    sorted_batch = capi.HostPairBatch(lists, batch.seed)
+    params.ransac_type = 1
+    rc2, res2, mask2 = oracle.ransac_relpose_batch(sorted_batch, params)
+    assert rc == rc2 == 0 and (res2["success"] == 1).all()
+    assert res2["num_iterations"].mean() < 0.8 * res["num_iterations"].mean()   # the confidence bound still asks for ~150 iterations
+    assert (res2["num_inliers"] >= 0.9 * res["num_inliers"]).all()
+    params.ransac_type = 2
+    assert oracle.ransac_relpose_batch(sorted_batch, params)[0] == capi.THB_E_UNSUPPORTED

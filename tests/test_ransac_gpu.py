@@ -331,3 +331,35 @@ def test_fused_and_round_synchronous_paths_are_bit_identical(lib, oracle, monkey
             got[mode] = (res.tobytes(), mask.copy())
         assert got["fused"][0] == got["rounds"][0]
         np.testing.assert_array_equal(got["fused"][1], got["rounds"][1])
+
+
+def test_prosac_sampler_matches_oracle(lib, oracle, monkeypatch):
+    """RansacType::PROSAC (solvers/prosac_sampler.cc:53-131): quality-sorted correspondences (inliers first), the progressive
+    sampling schedule and its rejection-sampled unique indices on the same mt19937 stream: iteration counts, inlier masks and
+    models bit-equal to the oracle in both schedules; fewer iterations than RANSAC on sorted data."""
+    batch, _ = synthetic.make_pair_batch(24, n=600, seed=31, base_seed=777)
+    # sort every pair's correspondences by "quality": the generator puts outliers at random positions, so order by true residual
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    rc, ref_res, ref_mask = oracle.ransac_relpose_batch(batch, params)
+    lists = []
+    for p in range(batch.num_pairs):
+        a, b = int(batch.pair_offset[p]), int(batch.pair_offset[p + 1])
+        order = np.argsort(-ref_mask[a:b].astype(np.int32), kind="stable")   # RANSAC inliers first
+        lists.append(batch.corr[a:b][order])
+    batch = capi.HostPairBatch(lists, batch.seed)
+    params.ransac_type = 1
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, params)
+    assert rc == 0
+    for mode in ("fused", "rounds"):
+        monkeypatch.setenv("THB_RANSAC_MODE", mode)
+        res = np.zeros(batch.num_pairs, capi.RELPOSE_DTYPE); mask = np.zeros(int(batch.pair_offset[-1]), np.uint8)
+        b = batch.struct()
+        capi.check(lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None))
+        np.testing.assert_array_equal(res["num_iterations"], ores["num_iterations"])
+        np.testing.assert_array_equal(mask, omask)
+        for f in ("essential_matrix", "rotation", "position"):
+            assert np.array_equal(res[f], ores[f], equal_nan=True), f
+    assert ores["num_iterations"].mean() < ref_res["num_iterations"].mean()
+    params.ransac_type = 2
+    b = batch.struct()
+    assert lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None) == capi.THB_E_UNSUPPORTED
