@@ -766,6 +766,7 @@ __device__ bool lo_refine_relpose(const double* __restrict__ corr, const uint8_t
 // ---- estimator policies (solvers/estimator.h): sample size, datum width, model estimation, per-datum error ----
 struct RelPoseEst {  // RelativePoseEstimator (sfm/estimators/estimate_relative_pose.cc:65-155)
   static constexpr int S = 5, D = 4, MAXM = 10;
+  static constexpr int SOLVE_CTAS = RANSAC_CTAS_PER_SM;  // resident solver CTAs per SM in the round-synchronous schedule
   static constexpr bool HAS_LO = true;
   __device__ static bool refine(const double* corr, const uint8_t* flag, int n, double thresh, Model* m, LoShared& L) {
     return lo_refine_relpose(corr, flag, n, thresh, m, L);
@@ -789,6 +790,7 @@ struct RelPoseEst {  // RelativePoseEstimator (sfm/estimators/estimate_relative_
 };
 struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator, PnPType::KNEIP (sfm/estimators/estimate_calibrated_absolute_pose.cc:63-172)
   static constexpr int S = 3, D = 5, MAXM = 4;  // datum: feature (x, y), world point (X, Y, Z)
+  static constexpr int SOLVE_CTAS = RANSAC_CTAS_PER_SM;
   static constexpr bool HAS_LO = false;  // its LO is BundleAdjustView on a one-view reconstruction (:120-153): rejected
   __device__ static bool refine(const double*, const uint8_t*, int, double, Model*, LoShared&) { return false; }
   __device__ static int solve(const double* sample, Model* out) {
@@ -813,6 +815,7 @@ struct AbsPoseEst {  // CalibratedAbsolutePoseEstimator, PnPType::KNEIP (sfm/est
 };
 struct HomographyEst {  // HomographyEstimator (sfm/estimators/estimate_homography.cc:62-116); H lives in Model::E
   static constexpr int S = 4, D = 4, MAXM = 1;
+  static constexpr int SOLVE_CTAS = 4;  // 128 registers: a C5 view graph (512 pairs) is one wave of solver CTAs instead of two
   static constexpr bool HAS_LO = false;
   __device__ static bool refine(const double*, const uint8_t*, int, double, Model*, LoShared&) { return false; }
   __device__ static int solve(const double* sample, Model* out) {
@@ -1316,7 +1319,7 @@ __global__ void __launch_bounds__(64) k_rs_draw(int ransac_type, int na, const i
 
 // solve: thread (a, b) = hypothesis b of active pair a
 template <class Est>
-__global__ void __launch_bounds__(RT, RANSAC_CTAS_PER_SM) k_rs_solve(int na, const int* __restrict__ active, const PairState* __restrict__ states,
+__global__ void __launch_bounds__(RT, Est::SOLVE_CTAS) k_rs_solve(int na, const int* __restrict__ active, const PairState* __restrict__ states,
                                                                       const double* __restrict__ corr_all, const int* __restrict__ samples,
                                                                       Model* __restrict__ model_ws, int* __restrict__ nmodels, long long* __restrict__ prof) {
   constexpr int SS = Est::S, DD = Est::D;
@@ -1546,7 +1549,7 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (sms <= 0) sms = 148;
   long long* d_prof = getenv("THB_RS_PROF") ? B.get<long long>((size_t)C * BI) : nullptr;
-  int rc = THB_OK;
+  int rc = THB_OK, num_rounds = 0;
   for (int pair0 = 0; pair0 < np && rc == THB_OK; pair0 += C) {
     const int count = std::min(C, np - pair0);
     cudaMemsetAsync(d_count, 0, sizeof(int) * 2, st);
@@ -1581,6 +1584,7 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
       if (cudaMemcpyAsync(&na, d_count + (1 - cur), sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = THB_E_CUDA; break; }
       for (int k = 0; k < 4; ++k) { float ms = 0.f; if (cudaEventElapsedTime(&ms, ev[k], ev[k + 1]) == cudaSuccess) phase_ms[k] += ms; }
       cur = 1 - cur;
+      ++num_rounds;
     }
     if (rc != THB_OK) break;
     k_rs_final<Est><<<(count + 3) / 4, 128, 0, st>>>(p, count, d_states, d_corr, d_seed, d_res, d_mask, d_stats, d_rng, rng_mode);
@@ -1590,6 +1594,8 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
   THB_CUDA_CHECK(cudaGetLastError());
   THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (getenv("THB_TV_TIMING"))
+    fprintf(stderr, "  rounds<S=%d>: %d pairs, %d rounds, draw %.2f solve %.2f score %.2f scan %.2f ms\n", Est::S, np, num_rounds, phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3]);
   // phase shares: device time of the phase kernels in nanoseconds (the fused kernel reports CTA cycles in the same fields)
   g_last_stats.cycles_draw = (uint64_t)(phase_ms[0] * 1e6); g_last_stats.cycles_solve = (uint64_t)(phase_ms[1] * 1e6);
   g_last_stats.cycles_score = (uint64_t)(phase_ms[2] * 1e6); g_last_stats.cycles_scan = (uint64_t)(phase_ms[3] * 1e6);
@@ -1753,6 +1759,11 @@ int run_two_view(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbVi
   THB_CUDA_CHECK(cudaMemcpyAsync(&h_uncal, d_uncal, sizeof(int), cudaMemcpyDeviceToHost, st));
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
   if (h_uncal) THB_FAIL(THB_E_UNSUPPORTED, "a pair has a view without a focal-length prior (or a camera model off the hot path): the uncalibrated branch of EstimateTwoViewInfo is not implemented");
+  // THB_TV_TIMING=1: device time of the stages (homography RANSAC, relative-pose RANSAC, triangulation + two-view BA) on stderr
+  const bool timing = getenv("THB_TV_TIMING") != nullptr;
+  const int use_lo_for_log = O->use_lo;
+  cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (timing) { for (auto& e : tev) cudaEventCreate(&e); cudaEventRecord(tev[0], st); }
   ThbRansacParams rp;
   thb_ransac_default_params(&rp);
   rp.failure_probability = 1.0 - O->expected_ransac_confidence; rp.min_iterations = O->min_ransac_iterations; rp.max_iterations = O->max_ransac_iterations;
@@ -1768,10 +1779,12 @@ int run_two_view(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbVi
     rc = launch_ransac<HomographyEst>(st, B, hp, np, d_off, d_px, d_seed, total, d_hom, nullptr, nullptr, d_rng, 1, d_skip);
     if (rc != THB_OK) return rc;
   }
+  if (timing) cudaEventRecord(tev[1], st);
   k_tv_normalize<<<np, 128, 0, st>>>(d_off, d_px, d_i1, d_i2, d_norm);
   rp.use_lo = O->use_lo; rp.lo_start_iterations = O->lo_start_iterations;
   rc = launch_ransac<RelPoseEst>(st, B, rp, np, d_off, d_norm, d_seed, total, d_res, verify ? d_inl : d_out, d_thresh, d_rng, verify ? 2 : 0, d_skip);
   if (rc != THB_OK) return rc;
+  if (timing) cudaEventRecord(tev[2], st);
   if (!verify) {
     k_tv_info<<<(np + 127) / 128, 128, 0, st>>>(np, d_res, d_i1, d_i2, d_skip, d_info);
   } else {
@@ -1784,6 +1797,14 @@ int run_two_view(const ThbPairBatch* b, const ThbViewIntrinsics* i1, const ThbVi
     k_tv_verify<<<np, TV_THREADS, 0, st>>>(d_off, d_px, d_i1, d_i2, *O, d_res, d_inl, d_hom, d_skip, d_p0, d_p1, d_ps, d_tri, d_zero, d_two, d_info, d_out);
   }
   THB_CUDA_CHECK(cudaGetLastError());
+  if (timing) {
+    cudaEventRecord(tev[3], st); cudaEventSynchronize(tev[3]);
+    float a = 0.f, b2 = 0.f, c = 0.f;
+    cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b2, tev[1], tev[2]); cudaEventElapsedTime(&c, tev[2], tev[3]);
+    fprintf(stderr, "two-view batch of %d pairs: homography RANSAC %.2f ms, normalise + relative-pose RANSAC (LO %d) %.2f ms, info / triangulation + two-view BA %.2f ms\n",
+            np, a, b2, use_lo_for_log, c);
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   if (host) {
     THB_CUDA_CHECK(cudaMemcpyAsync(info, d_info, sizeof(ThbTwoViewInfo) * np, cudaMemcpyDeviceToHost, st));
     if (out_mask) THB_CUDA_CHECK(cudaMemcpyAsync(out_mask, d_out, (size_t)total, cudaMemcpyDeviceToHost, st));
