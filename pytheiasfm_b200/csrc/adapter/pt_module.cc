@@ -928,6 +928,16 @@ PYBIND11_MODULE(_pt, m) {
     UpdateInverseDepth(t, &r);
     return s;
   });
+  // BundleAdjustPartialViewsConstant (bundle_adjustment.cc:146-186): the listed views free, every other view that observes a track
+  // constant, all tracks free - AddView(var) + AddView(const) + SetCameraExtrinsicsConstant(const) + AddTrack(all) flattens to the
+  // same blocks as AddView(var) + AddTrack(all) (AddTrack registers the remaining observers as constant cameras, :199-204).
+  sfm.def("BundleAdjustPartialViewsConstant", [](const BundleAdjustmentOptions& o, const std::vector<ViewId>& var_views, const std::vector<ViewId>& const_views,
+                                               Reconstruction& r) {
+    (void)const_views;
+    BundleAdjustmentSummary s = RunBa(o, var_views, r.track_order, &r, false);
+    UpdateInverseDepth(r.track_order, &r);
+    return s;
+  });
   sfm.def("BundleAdjustView", [](Reconstruction& r, const BundleAdjustmentOptions& o, ViewId v) {
     BundleAdjustmentSummary s = RunBa(o, {v}, {}, &r, true);   // forces DENSE_QR, no inner iterations (:225)
     UpdateInverseDepth(TracksOfViews({v}, &r), &r);

@@ -152,6 +152,21 @@ def test_SetOutlierTracksToUnestimated(gen):
     assert pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon) == 0      # idempotent
 
 
+def test_BundleAdjustPartialViewsConstant(gen):
+    """bundle_adjustment.cc:146-186: the constant views keep their pose, the variable views and all tracks are refined."""
+    vids = gen.recon.ViewIds()
+    gen.add_noise_to_views(1e-2, 1e-1)
+    const = vids[:3]; var = vids[3:]
+    before = {v: (gen.recon.View(v).Camera().GetPosition().copy(), gen.recon.View(v).Camera().GetOrientationAsAngleAxis().copy()) for v in vids}
+    opts = pt.sfm.BundleAdjustmentOptions()
+    res = pt.sfm.BundleAdjustPartialViewsConstant(opts, var, const, gen.recon)
+    assert res.success and res.final_cost < res.initial_cost
+    for v in const:
+        np.testing.assert_array_equal(gen.recon.View(v).Camera().GetPosition(), before[v][0])
+        np.testing.assert_array_equal(gen.recon.View(v).Camera().GetOrientationAsAngleAxis(), before[v][1])
+    assert any(np.abs(gen.recon.View(v).Camera().GetPosition() - before[v][0]).max() > 0 for v in var)
+
+
 def test_BundleAdjust_with_covariance(gen):
     """bundle_adjustment_wrapper.cc:52-96: (summary, covariance, empirical variance factor) for a view, views, a track, tracks;
     covariances are symmetric positive definite, scaled by 2 * final_cost / redundancy, and agree between the single and the
