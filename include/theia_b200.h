@@ -99,6 +99,13 @@ typedef struct ThbBaProblem {
   const double* obs_xy;      /* [num_observations*2]  Feature::point_                      */
   const double* obs_sqrt_info;/*[num_observations*2]  1/sqrt(cov(0,0)), 1/sqrt(cov(1,1));  */
                              /*                  NULL => 1 (reprojection_error.h:96-103)   */
+  /* BundleAdjustmentOptions::use_position_priors (bundle_adjuster.cc:160-163, position_error.h:44-80): a camera with
+   * cam_has_position_prior[c] != 0 gets the 3 residuals sqrt_info * (prior - position), no loss function. All three
+   * pointers NULL (a zero-initialised struct) = no priors. A prior on a fully constant camera is a constant of the cost and
+   * is left out. thb_ba_solve / create / iterate / covariance honour them; the track entries keep every camera constant. */
+  const uint8_t* cam_has_position_prior;      /* [num_cameras]   View::HasPositionPrior()                          */
+  const double* cam_position_prior;           /* [num_cameras*3] View::GetPositionPrior()                          */
+  const double* cam_position_prior_sqrt_info; /* [num_cameras*9] View::GetPositionPriorSqrtInformation(), row-major */
 } ThbBaProblem;
 
 /* BundleAdjustmentOptions (bundle_adjustment.h:87-167) restricted to what reaches

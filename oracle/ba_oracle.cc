@@ -343,6 +343,26 @@ class BaOracle {
     if (want_jac)
       for (int t = 0; t < nth; ++t)
         for (int k = 0; k < n_red; ++k) grad[n_pt_tan + k] += gth[t][k];
+    if (!only_fixed && P.cam_has_position_prior) {
+      if (want_jac) { prior_r.assign((size_t)nc * 3, 0.0); prior_J.assign((size_t)nc * 18, 0.0); }
+      for (int c = 0; c < nc; ++c) {
+        if (!HasPrior(c)) continue;
+        double r[3];
+        PriorResidual(s, c, r);
+        total += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        if (!want_jac) continue;
+        const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)c;
+        for (int k = 0; k < 3; ++k) {
+          prior_r[(size_t)c * 3 + k] = r[k];
+          for (int t = 0; t < cam_td[c]; ++t) {
+            const int col = cam_idx[c][t];
+            const double j = col < 3 ? -A[3 * k + col] : 0.0;
+            prior_J[(size_t)c * 18 + k * 6 + t] = j;
+            grad[cam_off[c] + t] += j * r[k];
+          }
+        }
+      }
+    }
     *cost = total;
     return all_ok;
   }
@@ -360,8 +380,17 @@ class BaOracle {
     }
   }
 
+  void ScalePriorColumns() {
+    if (prior_J.empty()) return;
+    for (int c = 0; c < nc; ++c)
+      if (HasPrior(c)) for (int k = 0; k < 3; ++k) for (int t = 0; t < cam_td[c]; ++t) prior_J[(size_t)c * 18 + k * 6 + t] *= scale[cam_off[c] + t];
+  }
+
   void SquaredColumnNorm(std::vector<double>* out) const {
     out->assign(n_tan, 0.0);
+    if (!prior_J.empty())
+      for (int c = 0; c < nc; ++c)
+        if (HasPrior(c)) for (int k = 0; k < 3; ++k) for (int t = 0; t < cam_td[c]; ++t) { const double v = prior_J[(size_t)c * 18 + k * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
     for (int i = 0; i < no; ++i) {
       if (fixed[i]) continue;
       const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
@@ -383,6 +412,7 @@ class BaOracle {
         for (int k = 0; k < n_tan; ++k) scale[k] = 1.0 / (1.0 + std::sqrt(cn[k]));
       }
       ScaleJacobianColumns();
+      ScalePriorColumns();
     }
     // unconstrained: max-norm of the gradient; constrained: max |Plus(x,-g) - x|.
     if (!is_constrained) {
@@ -445,6 +475,17 @@ class BaOracle {
     const int nr = n_red;
     std::vector<double> S((size_t)nr * nr, 0.0), rhs(nr, 0.0);
     for (int k = 0; k < nr; ++k) S[(size_t)k * nr + k] = D[n_pt_tan + k] * D[n_pt_tan + k];
+    if (!prior_J.empty())
+      for (int c = 0; c < nc; ++c) {
+        if (!HasPrior(c)) continue;
+        const int o = cam_off[c] - n_pt_tan;
+        for (int k = 0; k < 3; ++k)
+          for (int a = 0; a < cam_td[c]; ++a) {
+            const double ja = prior_J[(size_t)c * 18 + k * 6 + a];
+            rhs[o + a] += ja * prior_r[(size_t)c * 3 + k];
+            for (int b = 0; b <= a; ++b) S[(size_t)(o + a) * nr + o + b] += ja * prior_J[(size_t)c * 18 + k * 6 + b];
+          }
+      }
     std::vector<omp_lock_t> locks(std::max(1, nc + ng));
     for (auto& l : locks) omp_init_lock(&l);
     std::vector<double> Vinv((size_t)np * 16, 0.0), gpv((size_t)np * 4, 0.0);
@@ -616,6 +657,11 @@ class BaOracle {
           for (int u = 0; u < d; ++u)
             for (int v = 0; v < d; ++v) N[(size_t)c * 36 + u * d + v] += Jc[(size_t)i * 12 + a * 6 + u] * Jc[(size_t)i * 12 + a * 6 + v];
       }
+      for (int c = 0; c < nc; ++c)
+        if (HasPrior(c))
+          for (int k = 0; k < 3; ++k)
+            for (int u = 0; u < cam_td[c]; ++u)
+              for (int v = 0; v < cam_td[c]; ++v) N[(size_t)c * 36 + u * cam_td[c] + v] += prior_J[(size_t)c * 18 + k * 6 + u] * prior_J[(size_t)c * 18 + k * 6 + v];
       for (int c = 0; c < nc; ++c) {
         const int d = cam_td[c];
         if (!d || !count[c]) continue;
@@ -775,6 +821,15 @@ class BaOracle {
       }
       acc += -(m[0] * (res[2 * (size_t)i] + m[0] / 2.0) + m[1] * (res[2 * (size_t)i + 1] + m[1] / 2.0));
     }
+    if (!prior_J.empty())
+      for (int c = 0; c < nc; ++c) {
+        if (!HasPrior(c)) continue;
+        for (int k = 0; k < 3; ++k) {
+          double m = 0.0;
+          for (int t = 0; t < cam_td[c]; ++t) m += prior_J[(size_t)c * 18 + k * 6 + t] * step[cam_off[c] + t];
+          acc += -(m * (prior_r[(size_t)c * 3 + k] + m / 2.0));
+        }
+      }
     return acc;
   }
 
@@ -841,6 +896,18 @@ class BaOracle {
       (*r_out)[2 * q] = r[0] * residual_scaling; (*r_out)[2 * q + 1] = r[1] * residual_scaling;
       for (int a = 0; a < 2; ++a) for (int k = 0; k < dim; ++k) (*J_out)[((size_t)2 * q + a) * dim + k] = t[a][k];
     }
+    if (kind == BLK_CAM && HasPrior(idx)) {  // the camera's position prior is one more residual block of this parameter block
+      double r[3];
+      PriorResidual(s, idx, r);
+      total += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      if (want_jac) {
+        const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)idx;
+        for (int k = 0; k < 3; ++k) {
+          r_out->push_back(r[k]);
+          for (int t = 0; t < dim; ++t) J_out->push_back(cam_idx[idx][t] < 3 ? -A[3 * k + cam_idx[idx][t]] : 0.0);
+        }
+      }
+    }
     *cost = total;
     return true;
   }
@@ -878,9 +945,9 @@ class BaOracle {
     double x_cost = 0.0, scale[KS], g[KS], diag[KS];
     auto evaluate_gj = [&](bool first) {
       if (!EvalBlock(*s, kind, idx, list, n, true, &x_cost, &r, &J, dim)) return false;
-      for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * r[q]; g[k] = a; }
-      if (first) for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; scale[k] = 1.0 / (1.0 + std::sqrt(a)); }
-      for (int q = 0; q < 2 * n; ++q) for (int k = 0; k < dim; ++k) J[(size_t)q * dim + k] *= scale[k];
+      for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < (int)r.size(); ++q) a += J[(size_t)q * dim + k] * r[q]; g[k] = a; }
+      if (first) for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < (int)r.size(); ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; scale[k] = 1.0 / (1.0 + std::sqrt(a)); }
+      for (int q = 0; q < (int)r.size(); ++q) for (int k = 0; k < dim; ++k) J[(size_t)q * dim + k] *= scale[k];
       return true;
     };
     if (!evaluate_gj(true)) return;  // IterationZero fails: FAILURE, parameters untouched
@@ -894,20 +961,20 @@ class BaOracle {
       ++iteration;
       step_ok = false;
       if (!reuse_diagonal)
-        for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < 2 * n; ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; diag[k] = std::min(std::max(a, 1e-6), 1e32); }
+        for (int k = 0; k < dim; ++k) { double a = 0.0; for (int q = 0; q < (int)r.size(); ++q) a += J[(size_t)q * dim + k] * J[(size_t)q * dim + k]; diag[k] = std::min(std::max(a, 1e-6), 1e32); }
       reuse_diagonal = true;
       // (J^T J + D^2) y = J^T r with D^2 = diag / radius; step = -y (DENSE_QR on [J; D] in Ceres: the same least squares)
       double M[KS * KS], b[KS], y[KS];
       for (int a = 0; a < dim; ++a) {
-        double bb = 0.0; for (int q = 0; q < 2 * n; ++q) bb += J[(size_t)q * dim + a] * r[q]; b[a] = bb;
-        for (int c = 0; c <= a; ++c) { double v = 0.0; for (int q = 0; q < 2 * n; ++q) v += J[(size_t)q * dim + a] * J[(size_t)q * dim + c]; M[a * dim + c] = v; M[c * dim + a] = v; }
+        double bb = 0.0; for (int q = 0; q < (int)r.size(); ++q) bb += J[(size_t)q * dim + a] * r[q]; b[a] = bb;
+        for (int c = 0; c <= a; ++c) { double v = 0.0; for (int q = 0; q < (int)r.size(); ++q) v += J[(size_t)q * dim + a] * J[(size_t)q * dim + c]; M[a * dim + c] = v; M[c * dim + a] = v; }
         M[a * dim + a] += diag[a] / radius;
       }
       bool valid = DenseCholeskySolve(dim, M, b, y);
       double step[KS], mcc = 0.0;
       if (valid) {
         for (int k = 0; k < dim; ++k) step[k] = -y[k];
-        for (int q = 0; q < 2 * n; ++q) { double m = 0.0; for (int k = 0; k < dim; ++k) m += J[(size_t)q * dim + k] * step[k]; mcc += -(m * (r[q] + m / 2.0)); }
+        for (int q = 0; q < (int)r.size(); ++q) { double m = 0.0; for (int k = 0; k < dim; ++k) m += J[(size_t)q * dim + k] * step[k]; mcc += -(m * (r[q] + m / 2.0)); }
         valid = std::isfinite(mcc) && mcc > 0.0;
       }
       if (!valid) {
@@ -1127,6 +1194,16 @@ class BaOracle {
   std::vector<double> res, Jc, Ji, Jp, grad, scale;
   double x_cost = 0.0, gradient_max_norm = 0.0;
   int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0, n_cg_iterations = 0;
+  // position priors (bundle_adjuster.cc:160-163, position_error.h:44-80): residual sqrt_info * (prior - position), no loss;
+  // prior_r / prior_J hold the 3 residuals and the 3 x cam_td tangent Jacobian of every camera that has one
+  std::vector<double> prior_r, prior_J;
+  bool HasPrior(int c) const { return P.cam_has_position_prior && P.cam_position_prior && P.cam_position_prior_sqrt_info && P.cam_has_position_prior[c] && cam_td[c] > 0; }
+  void PriorResidual(const State& s, int c, double r[3]) const {
+    const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)c;
+    const double* pr = P.cam_position_prior + 3 * (size_t)c;
+    const double d[3] = {pr[0] - s.cam[(size_t)c * 6], pr[1] - s.cam[(size_t)c * 6 + 1], pr[2] - s.cam[(size_t)c * 6 + 2]};
+    for (int k = 0; k < 3; ++k) r[k] = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
+  }
 };
 
 }  // namespace

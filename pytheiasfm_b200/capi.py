@@ -57,6 +57,7 @@ class ThbBaProblem(C.Structure):
         ("pts", C.c_void_p), ("pt_const", C.c_void_p),
         ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_xy", C.c_void_p),
         ("obs_sqrt_info", C.c_void_p),
+        ("cam_has_position_prior", C.c_void_p), ("cam_position_prior", C.c_void_p), ("cam_position_prior_sqrt_info", C.c_void_p),
     ]
 
 
@@ -314,6 +315,7 @@ class HostBaProblem:
         ("intr", np.float64), ("intr_model", np.int32), ("intr_const", np.uint16),
         ("pts", np.float64), ("pt_const", np.uint8),
         ("obs_cam", np.int32), ("obs_pt", np.int32), ("obs_xy", np.float64), ("obs_sqrt_info", np.float64),
+        ("cam_has_position_prior", np.uint8), ("cam_position_prior", np.float64), ("cam_position_prior_sqrt_info", np.float64),
     ]
 
     def __init__(self, arrays):

@@ -190,6 +190,9 @@ struct View {
   Camera camera;
   std::unordered_map<TrackId, Feature> features;
   std::vector<TrackId> track_order;
+  bool has_position_prior = false;                       // view.h:101-106
+  double position_prior[3] = {0, 0, 0};
+  double position_prior_sqrt_info[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};  // row-major
   std::vector<TrackId> TrackIds() const { return track_order; }
   const Feature* GetFeature(TrackId t) const { auto it = features.find(t); return it == features.end() ? nullptr : &it->second; }
 };
@@ -282,6 +285,8 @@ struct Flat {
   std::vector<double> cam_ext, intr, pts, obs_xy, obs_si;
   std::vector<uint8_t> cam_const, pt_const; std::vector<uint16_t> intr_const;
   std::vector<int32_t> cam_group, intr_model, obs_cam, obs_pt;
+  std::vector<uint8_t> has_prior; std::vector<double> prior, prior_sqrt_info;   // position priors of the AddView cameras
+  bool any_prior = false;
 };
 
 // SetSolverOptions, bundle_adjuster.cc:63-89
@@ -312,8 +317,8 @@ struct CovOut {
 BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vector<ViewId>& views, const std::vector<TrackId>& tracks,
                               Reconstruction* r, bool force_no_inner, CovOut* cov = nullptr) {
   if (o.use_inverse_depth_parametrization) throw std::runtime_error("use_inverse_depth_parametrization is not implemented");
-  if (o.use_position_priors || o.use_orientation_priors || o.use_depth_priors || o.use_gravity_priors || o.orthographic_camera)
-    throw std::runtime_error("prior residuals / orthographic cameras are not implemented");
+  if (o.use_orientation_priors || o.use_depth_priors || o.use_gravity_priors || o.orthographic_camera)
+    throw std::runtime_error("orientation / gravity / depth prior residuals and orthographic cameras are not implemented (position priors are)");
   Flat f;
   const std::unordered_set<ViewId> vset(views.begin(), views.end());
   const std::unordered_set<TrackId> tset(tracks.begin(), tracks.end());
@@ -328,6 +333,11 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     if (o.constant_camera_position) c |= THB_CAM_CONST_POSITION;          // bundle_adjuster.cc:357-380
     if (o.constant_camera_orientation) c |= THB_CAM_CONST_ORIENTATION;
     f.cam_const.push_back(c);
+    const bool prior = free_cam && o.use_position_priors && view.has_position_prior;    // AddView only (bundle_adjuster.cc:160-163)
+    f.has_prior.push_back(prior ? 1 : 0);
+    f.prior.insert(f.prior.end(), view.position_prior, view.position_prior + 3);
+    f.prior_sqrt_info.insert(f.prior_sqrt_info.end(), view.position_prior_sqrt_info, view.position_prior_sqrt_info + 9);
+    f.any_prior |= prior;
     Intrinsics* in = view.camera.intr.get();
     if (!f.group_index.count(in)) {
       f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
@@ -398,6 +408,7 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   p.intr = f.intr.data(); p.intr_model = f.intr_model.data(); p.intr_const = f.intr_const.data();
   p.pts = f.pts.data(); p.pt_const = f.pt_const.data();
   p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data(); p.obs_sqrt_info = f.obs_si.data();
+  if (f.any_prior) { p.cam_has_position_prior = f.has_prior.data(); p.cam_position_prior = f.prior.data(); p.cam_position_prior_sqrt_info = f.prior_sqrt_info.data(); }
   const ThbBaOptions opt = MapOptions(o, force_no_inner);
   ThbBaSummary s;
   int rc;
@@ -871,6 +882,15 @@ PYBIND11_MODULE(_pt, m) {
       .def("Camera", [](View& v) -> Camera& { return v.camera; }, py::return_value_policy::reference_internal)
       .def("MutableCamera", [](View& v) -> Camera& { return v.camera; }, py::return_value_policy::reference_internal)
       .def("NumFeatures", [](const View& v) { return (int)v.features.size(); }).def("TrackIds", &View::TrackIds)
+      .def("SetPositionPrior", [](View& v, const Vec& prior, const py::array_t<double, py::array::c_style | py::array::forcecast>& sqrt_information) {
+        CopyVec(prior, v.position_prior, 3, "position prior");
+        if (sqrt_information.ndim() != 2 || sqrt_information.shape(0) != 3 || sqrt_information.shape(1) != 3) throw std::invalid_argument("sqrt information must be 3 x 3");
+        std::copy_n(sqrt_information.data(), 9, v.position_prior_sqrt_info);
+        v.has_position_prior = true;
+      })
+      .def("HasPositionPrior", [](const View& v) { return v.has_position_prior; })
+      .def("GetPositionPrior", [](const View& v) { py::array_t<double> a(3); std::copy_n(v.position_prior, 3, a.mutable_data()); return a; })
+      .def("GetPositionPriorSqrtInformation", [](const View& v) { py::array_t<double> a({3, 3}); std::copy_n(v.position_prior_sqrt_info, 9, a.mutable_data()); return a; })
       .def("GetFeature", [](const View& v, TrackId t) { const Feature* f = v.GetFeature(t); if (!f) throw std::invalid_argument("no such feature"); return *f; });
 
   py::class_<Reconstruction>(sfm, "Reconstruction")

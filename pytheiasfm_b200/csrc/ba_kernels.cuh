@@ -335,7 +335,8 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
                                                   double inv_radius, double min_diag, double max_diag,
                                                   double* __restrict__ Smat, int ld, double* __restrict__ rhs,
                                                   double* __restrict__ braw, double* __restrict__ cdiag,
-                                                  int* __restrict__ iflag) {
+                                                  int* __restrict__ iflag, const uint8_t* __restrict__ has_prior,
+                                                  const double* __restrict__ prior) {
   constexpr int NA = 21 + 6 + 6;  // U_total(lower 21), raw b, schur-corrected b  (raw diag = separate 6)
   __shared__ double red[4][NA + 6];
   const int c = blockIdx.x;
@@ -396,6 +397,23 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
   if (threadIdx.x < NA + 6) {
     const int k = threadIdx.x;
     red[0][k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
+  }
+  __syncthreads();
+  if (has_prior && has_prior[c] && !(K.cam_const[c] & THB_CAM_CONST_POSITION) && threadIdx.x == 0) {  // constant position: a constant of the cost
+    // position prior (position_error.h:44-80): r = A (prior - C), J = -A on the position columns (scaled like every column)
+    const double* A = prior + 12 * (size_t)c;
+    const double d[3] = {A[9] - S.cam[6 * (size_t)c], A[10] - S.cam[6 * (size_t)c + 1], A[11] - S.cam[6 * (size_t)c + 2]};
+    double r[3], J[3][3];
+    for (int k = 0; k < 3; ++k) {
+      r[k] = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
+      for (int a = 0; a < 3; ++a) J[k][a] = -A[3 * k + a] * cs[6 * c + a];
+    }
+    for (int a = 0; a < 3; ++a) {
+      const double b = J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
+      red[0][21 + a] += b; red[0][27 + a] += b;
+      red[0][33 + a] += J[0][a] * J[0][a] + J[1][a] * J[1][a] + J[2][a] * J[2][a];
+      for (int b2 = 0; b2 <= a; ++b2) red[0][a * (a + 1) / 2 + b2] += J[0][a] * J[0][b2] + J[1][a] * J[1][b2] + J[2][a] * J[2][b2];
+    }
   }
   __syncthreads();
   if (threadIdx.x < 21) {
@@ -1081,6 +1099,41 @@ __global__ void k_eval_ambient(BaConst K, BaState S, ObsSoA O, double* __restric
   if (jintr)
     for (int a = 0; a < 2; ++a)
       for (int k = 0; k < KS; ++k) jintr[(2 * (size_t)i + a) * KS + k] = k < 9 ? ji[a * 9 + k] : 0.0;
+}
+
+// position priors: cost 0.5 |A (prior - C)|^2 of every free camera that has one, added to a cost slot
+__global__ void k_prior_cost(int nc, const uint8_t* __restrict__ has_prior, const double* __restrict__ prior, const uint8_t* __restrict__ cam_const,
+                             const double* __restrict__ cam, double* __restrict__ slot) {
+  __shared__ double red[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (c < nc && has_prior[c] && cam_const[c] != THB_CAM_CONST_ALL) {
+    const double* A = prior + 12 * (size_t)c;
+    const double d[3] = {A[9] - cam[6 * (size_t)c], A[10] - cam[6 * (size_t)c + 1], A[11] - cam[6 * (size_t)c + 2]};
+    for (int k = 0; k < 3; ++k) { const double r = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2]; v += 0.5 * r * r; }
+  }
+  v = block_sum(v, red);
+  if (threadIdx.x == 0 && v != 0.0) atomicAdd(slot, v);
+}
+
+// their share of the model cost change -(J s)^T (r + J s / 2) with s = -y (scaled space)
+__global__ void k_prior_mcc(int nc, const uint8_t* __restrict__ has_prior, const double* __restrict__ prior, const uint8_t* __restrict__ cam_const,
+                            const double* __restrict__ cam, const double* __restrict__ cs, const double* __restrict__ yred, double* __restrict__ scal) {
+  __shared__ double red[32];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double v = 0.0;
+  if (c < nc && has_prior[c] && !(cam_const[c] & THB_CAM_CONST_POSITION)) {
+    const double* A = prior + 12 * (size_t)c;
+    const double d[3] = {A[9] - cam[6 * (size_t)c], A[10] - cam[6 * (size_t)c + 1], A[11] - cam[6 * (size_t)c + 2]};
+    const double u[3] = {cs[6 * c] * yred[6 * c], cs[6 * c + 1] * yred[6 * c + 1], cs[6 * c + 2] * yred[6 * c + 2]};
+    for (int k = 0; k < 3; ++k) {
+      const double r = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
+      const double m = A[3 * k] * u[0] + A[3 * k + 1] * u[1] + A[3 * k + 2] * u[2];  // J s = (-A diag(cs)) (-y)
+      v += -(m * (r + 0.5 * m));
+    }
+  }
+  v = block_sum(v, red);
+  if (threadIdx.x == 0 && v != 0.0) atomicAdd(scal + SC_MCC, v);
 }
 
 // covariance of a camera's extrinsics block from its diagonal block of S (points constant: S is block diagonal)

@@ -132,6 +132,8 @@ struct ThbBaSession {
   // owned device memory
   int *d_cam_group = nullptr, *d_intr_model = nullptr, *d_intr_slot = nullptr;
   uint8_t *d_cam_const = nullptr, *d_pt_const = nullptr;
+  uint8_t* d_has_prior = nullptr;  // position priors (ThbBaProblem::cam_has_position_prior), nullptr when the problem has none
+  double* d_prior = nullptr;       // [nc][12]: sqrt information (9, row-major), prior position (3)
   uint16_t* d_intr_const = nullptr;
   int *d_op_cam = nullptr, *d_op_pt = nullptr, *d_oc_cam = nullptr, *d_oc_pt = nullptr;
   double2 *d_op_xy = nullptr, *d_op_si = nullptr, *d_oc_xy = nullptr, *d_oc_si = nullptr;
@@ -304,7 +306,7 @@ template <int MODEL, int PD>
 void LaunchCamPass(ThbBaSession* s, double inv_radius) {
   k_cam_pass<MODEL, PD><<<s->nc, 128, 0, s->st>>>(s->K, s->X, s->Oc, s->d_cam_start, s->d_cs, s->d_ps, s->d_vinv, s->d_gp, inv_radius,
                                                  s->opt.min_lm_diagonal, s->opt.max_lm_diagonal, s->chol.A, s->chol.ld,
-                                                 s->chol.RhsRow(), s->d_braw, s->d_cdiag, s->d_flag);
+                                                 s->chol.RhsRow(), s->d_braw, s->d_cdiag, s->d_flag, s->d_has_prior, s->d_prior);
 }
 template <int PD>
 void DispatchCamPass(ThbBaSession* s, double inv_radius) {
@@ -319,6 +321,13 @@ void DispatchCamPass(ThbBaSession* s, double inv_radius) {
   }
 }
 
+// position priors are residual blocks of their own: their cost joins whatever slot the reprojection blocks were summed into
+void AddPriorCost(ThbBaSession* s, const BaState& st, int slot) {
+  if (!s->d_has_prior) return;
+  k_prior_cost<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, st.cam, s->d_scal + slot);
+  ++s->sum.gpu_launches;
+}
+
 void RunCost(ThbBaSession* s, const BaState& st, int slot, int flag_slot) {
   const int g = cdiv(s->no, 256);
   switch (s->model) {
@@ -331,6 +340,7 @@ void RunCost(ThbBaSession* s, const BaState& st, int slot, int flag_slot) {
     default: k_cost<-1><<<g, 256, 0, s->st>>>(s->K, st, s->Op, s->d_scal, slot, s->d_flag, flag_slot); break;
   }
   ++s->sum.gpu_launches;
+  AddPriorCost(s, st, slot);
 }
 
 int ReadScalars(ThbBaSession* s) {
@@ -360,6 +370,7 @@ int EvaluateJacobian(ThbBaSession* s) {
   s->t_jac.Begin();
   RunJacobian(s, s->d_cs, s->d_ps);
   s->t_jac.End();
+  AddPriorCost(s, s->X, SC_COST_X);
   ++s->sum.num_jacobian_evaluations;
   return THB_OK;
 }
@@ -474,6 +485,10 @@ int SolveAndStep(ThbBaSession* s) {
       k_backsub_obs2<4><<<gq, 256, 0, s->st>>>(s->no, s->d_op_pt, s->d_r, s->d_jp, s->d_jy, s->d_yp, s->d_scal);
     }
     s->sum.gpu_launches += 3;
+    if (s->d_has_prior) {
+      k_prior_mcc<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, s->X.cam, s->d_cs, s->chol.x, s->d_scal);
+      ++s->sum.gpu_launches;
+    }
   }
   const int rc = ComputeCandidate(s, 1.0);
   s->t_update.End();
@@ -599,7 +614,7 @@ int DoInnerIterations(ThbBaSession* s) {
   const InnerLmParams P;
   // group 0: camera extrinsics
   if (nc > 0) {
-    k_inner_cam<PD><<<nc, IC_THREADS, 0, st>>>(s->K, s->Xc, s->Oc, s->d_cam_start, P);
+    k_inner_cam<PD><<<nc, IC_THREADS, 0, st>>>(s->K, s->Xc, s->Oc, s->d_cam_start, P, s->d_has_prior, s->d_prior);
     k_cam_derive<<<cdiv(nc, 128), 128, 0, st>>>(s->Xc.cam, s->Xc.camd, nc, s->d_cs, s->d_cam_const, s->d_cam_group);
     s->sum.gpu_launches += 2;
   }
@@ -827,6 +842,13 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, P->cam_group, sizeof(int) * nc, kin, st));
   if (P->cam_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, P->cam_const, nc, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_const, 0, std::max(nc, 1), st));
+  if (P->cam_has_position_prior && nc > 0) {  // position priors: packed [sqrt information (9) | prior (3)] per camera
+    if (!P->cam_position_prior || !P->cam_position_prior_sqrt_info) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_has_position_prior without prior / sqrt information arrays"); }
+    THB_TRY(M.Get(&s->d_has_prior, nc)); THB_TRY(M.Get(&s->d_prior, (size_t)nc * 12));
+    THB_TRY_CUDA(cudaMemcpyAsync(s->d_has_prior, P->cam_has_position_prior, nc, kin, st));
+    THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior, 12 * sizeof(double), P->cam_position_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
+    THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 9, 12 * sizeof(double), P->cam_position_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
+  }
   if (P->pt_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, P->pt_const, np, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_const, 0, std::max(np, 1), st));
 

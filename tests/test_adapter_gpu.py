@@ -152,6 +152,29 @@ def test_SetOutlierTracksToUnestimated(gen):
     assert pt.sfm.SetOutlierTracksToUnestimated(set(tids), 4.0, 2.0, gen.recon) == 0      # idempotent
 
 
+def test_position_priors_through_the_adapter(gen):
+    """View.SetPositionPrior + BundleAdjustmentOptions.use_position_priors: the priors (shifted by a common offset) drag the whole
+    reconstruction along its translation gauge; without the option they are ignored."""
+    vids = gen.recon.ViewIds()
+    shift = np.array([0.3, -0.2, 0.1])
+    for v in vids:
+        view = gen.recon.View(v)
+        assert not view.HasPositionPrior()
+        view.SetPositionPrior(view.Camera().GetPosition() + shift, 100.0 * np.eye(3))
+        assert view.HasPositionPrior()
+        np.testing.assert_allclose(view.GetPositionPriorSqrtInformation(), 100.0 * np.eye(3))
+    before = {v: gen.recon.View(v).Camera().GetPosition().copy() for v in vids}
+    opts = pt.sfm.BundleAdjustmentOptions()
+    res = pt.sfm.BundleAdjustReconstruction(opts, gen.recon)
+    assert res.success
+    assert max(np.abs(gen.recon.View(v).Camera().GetPosition() - before[v]).max() for v in vids) < 1e-3   # ignored
+    opts.use_position_priors = True
+    res = pt.sfm.BundleAdjustReconstruction(opts, gen.recon)
+    assert res.success
+    for v in vids:
+        np.testing.assert_allclose(gen.recon.View(v).Camera().GetPosition(), before[v] + shift, atol=2e-2)
+
+
 def test_BundleAdjustPartialViewsConstant(gen):
     """bundle_adjustment.cc:146-186: the constant views keep their pose, the variable views and all tracks are refined."""
     vids = gen.recon.ViewIds()

@@ -540,3 +540,59 @@ def test_covariance_of_views_and_tracks_matches_oracle(lib, oracle, loss):
     assert oracle.ba_covariance(prob, o)[0] == capi.THB_E_UNSUPPORTED
     o.use_homogeneous_point_parametrization = 0
     assert _gpu_covariance(lib, b, o)[0] == capi.THB_E_INVALID_ARGUMENT
+
+
+def _with_position_priors(prob, gt, bias, weight, every=1, seed=0):
+    rng = np.random.default_rng(seed)
+    a = dict(prob.a)
+    nc = prob.num_cameras
+    has = np.zeros(nc, np.uint8); has[::every] = 1
+    a["cam_has_position_prior"] = has
+    a["cam_position_prior"] = gt["cam_ext"][:, :3] + bias + rng.normal(0, 0.01, (nc, 3))
+    info = np.zeros((nc, 9))
+    for c in range(nc):
+        M = rng.normal(size=(3, 3)) * 0.2 + np.eye(3)            # a general (non-symmetric) square-root information matrix
+        info[c] = (weight * M).reshape(9)
+    a["cam_position_prior_sqrt_info"] = info
+    return capi.HostBaProblem(a)
+
+
+@pytest.mark.parametrize("case", ["c1", "inner", "pcg", "const_position_huber", "views_covariance"])
+def test_position_priors_match_oracle(lib, oracle, case):
+    """BundleAdjustmentOptions::use_position_priors (bundle_adjuster.cc:160-163, position_error.h:44-80): 3 residuals
+    sqrt_info * (prior - position) per camera, no loss. Same LM trajectory and final cost as the oracle with the exact and the
+    iterative solver, with inner iterations, next to constant positions (the prior is then a constant of the cost), and the
+    cameras are pulled to the (biased) priors: the free gauge of the scene is fixed by them."""
+    prob, gt = synthetic.config_c1()
+    o = capi.default_options(lib)
+    every = 1
+    if case == "inner":
+        o.use_inner_iterations = 1
+    elif case == "pcg":
+        o.linear_solver = capi.SOLVER_SCHUR_PCG
+    elif case == "const_position_huber":
+        prob.a["cam_const"][1::3] = capi.CAM_CONST_POSITION
+        o.loss_function_type = capi.LOSS_HUBER; o.robust_loss_width = 2.0
+        every = 2
+    pp = _with_position_priors(prob, gt, bias=0.5, weight=30.0, every=every, seed=4)
+    if case == "views_covariance":                          # the AddView problem: priors enter the covariance as well
+        pp.a["pt_const"][:] = 1
+        pp = capi.HostBaProblem(pp.a)
+        rc, cc, co, pc, po = _gpu_covariance(lib, pp, o)
+        orc, occ, oco, opc, opo = oracle.ba_covariance(pp, o)
+        assert rc == orc == 0
+        np.testing.assert_array_equal(co, oco)
+        np.testing.assert_allclose(cc, occ, rtol=1e-9, atol=1e-18)
+        no_prior = capi.HostBaProblem({k: v for k, v in pp.a.items() if "prior" not in k})
+        rc2, cc2, _, _, _ = _gpu_covariance(lib, no_prior, o)
+        assert np.all(np.diagonal(cc, axis1=1, axis2=2)[:, :3] < np.diagonal(cc2, axis1=1, axis2=2)[:, :3])   # the prior adds information
+        return
+    g, orc, pg, po = _compare_solves(lib, oracle, pp, o)
+    free = np.nonzero((pp.a["cam_const"] & capi.CAM_CONST_POSITION) == 0)[0] if pp.a["cam_const"] is not None else np.arange(pp.num_cameras)
+    with_prior = [c for c in free if pp.a["cam_has_position_prior"][c]]
+    if case != "const_position_huber":
+        d = pg.a["cam_ext"][with_prior, :3] - pp.a["cam_position_prior"][with_prior]
+        assert np.abs(d).max() < 0.05                        # the cameras sit on their priors (0.5 away from the ground truth)
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], rtol=0, atol=1e-6)
+    plain = gpu_solve(lib, capi.HostBaProblem({k: v for k, v in pp.a.items() if "prior" not in k}), o)
+    assert g["initial_cost"] > plain["initial_cost"]

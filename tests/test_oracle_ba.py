@@ -239,3 +239,28 @@ def test_select_good_tracks_oracle_properties(oracle):
     assert sel_sub[5] == 1 and n_sub < n
     pts0 = prob.a["obs_pt"][prob.a["obs_cam"] == 0]
     assert set(np.nonzero(sel_sub)[0]) - {5} <= set(pts0.tolist())
+
+
+def test_position_priors_fix_the_gauge(oracle):
+    """use_position_priors (bundle_adjuster.cc:160-163, position_error.h:44-80): priors shifted by a common offset move the whole
+    scene along its free translation; the reprojection part of the final cost stays at the no-prior minimum; a prior on a
+    camera with a constant position only adds a constant to the cost."""
+    prob, gt = synthetic.config_c1()
+    base = oracle.ba_solve(prob.copy(), oracle.default_options())
+    a = dict(prob.a)
+    nc = prob.num_cameras
+    a["cam_has_position_prior"] = np.ones(nc, np.uint8)
+    a["cam_position_prior"] = gt["cam_ext"][:, :3] + np.array([0.4, 0.0, -0.3])
+    a["cam_position_prior_sqrt_info"] = np.tile((np.eye(3) * 50.0).reshape(1, 9), (nc, 1))
+    pp = capi.HostBaProblem(a)
+    s = oracle.ba_solve(pp, oracle.default_options())
+    assert s["rc"] == 0 and s["success"] == 1
+    assert s["initial_cost"] > base["initial_cost"]
+    assert abs(s["final_cost"] - base["final_cost"]) < 0.05 * base["final_cost"]
+    np.testing.assert_allclose(pp.a["cam_ext"][:, :3], a["cam_position_prior"], atol=0.05)
+    q = dict(a); q["cam_const"] = np.full(nc, capi.CAM_CONST_POSITION, np.uint8)
+    c0 = oracle.ba_solve(capi.HostBaProblem({k: v for k, v in q.items() if "prior" not in k}), oracle.default_options())
+    c1 = oracle.ba_solve(capi.HostBaProblem(q), oracle.default_options())
+    prior_cost = 0.5 * np.sum((50.0 * (a["cam_position_prior"] - prob.a["cam_ext"][:, :3])) ** 2)
+    np.testing.assert_allclose(c1["final_cost"] - c0["final_cost"], prior_cost, rtol=1e-9)
+    assert c1["num_iterations"] == c0["num_iterations"]
