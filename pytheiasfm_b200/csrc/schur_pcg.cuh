@@ -14,6 +14,8 @@
 #define THB_SCHUR_PCG_CUH_
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -68,21 +70,42 @@ struct PcgArgs {
   const int2* tasks; int ntasks;
   double eta; int max_it;
   int* sync; double* vals; int* fail; int* iters_total;
+  long long* prof;  // THB_PCG_PROF: 3 accumulators (ns) or nullptr
 };
 
 // z = M^-1 r, returns this thread's share of r.z
 __device__ __forceinline__ double pcg_apply_precond(const PcgArgs& a) {
+  // restrict-qualified views: without them every store to z orders the loads of the next block behind it (one L2 round trip each)
+  const double* __restrict__ R = a.r;
+  double* __restrict__ Z = a.z;
+  const double* __restrict__ Minv = a.minv;
+  const int2* __restrict__ blk = a.blk;
   double part = 0.0;
+#pragma unroll 2
   for (int b = threadIdx.x; b < a.nblk; b += blockDim.x) {
-    const int o = a.blk[b].x, d = a.blk[b].y;
-    const double* M = a.minv + (size_t)b * kPcgMaxBlockDim * kPcgMaxBlockDim;
-    double rr[kPcgMaxBlockDim];
-    for (int j = 0; j < d; ++j) rr[j] = a.r[o + j];
-    for (int i = 0; i < d; ++i) {
-      double v = 0.0;
-      for (int j = 0; j < d; ++j) v += M[i * d + j] * rr[j];
-      a.z[o + i] = v;
-      part += rr[i] * v;
+    const int o = blk[b].x, d = blk[b].y;
+    const double* __restrict__ M = Minv + (size_t)b * kPcgMaxBlockDim * kPcgMaxBlockDim;
+    double rr[kPcgMaxBlockDim], m[kPcgMaxBlockDim * kPcgMaxBlockDim];
+#pragma unroll
+    for (int j = 0; j < kPcgMaxBlockDim; ++j) rr[j] = j < d ? R[o + j] : 0.0;
+#pragma unroll
+    for (int e = 0; e < kPcgMaxBlockDim * kPcgMaxBlockDim; ++e) m[e] = e < d * d ? M[e] : 0.0;  // all loads of the block in flight at once
+    if (d == 6) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v += m[i * 6 + j] * rr[j];
+        Z[o + i] = v;
+        part += rr[i] * v;
+      }
+    } else {
+      for (int i = 0; i < d; ++i) {
+        double v = 0.0;
+        for (int j = 0; j < d; ++j) v += M[i * d + j] * rr[j];
+        Z[o + i] = v;
+        part += rr[i] * v;
+      }
     }
   }
   return part;
@@ -166,10 +189,17 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg(PcgArgs a) {
   const int t = threadIdx.x;
   int gen = 0, it = 1;
   int cmd = a.sync[PCG_CMD];  // written by k_pcg_init
+  double rho_cur = a.vals[PCG_RHO], q0_cur = a.vals[PCG_Q0];  // CTA 0 keeps the CG scalars in registers (every thread the same value)
+  auto now = []() { long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); return g; };
+  long long t_mark = (a.prof && blockIdx.x == 0 && t == 0) ? now() : 0;
+  auto lap = [&](int slot) {  // THB_PCG_PROF: nanoseconds CTA 0 spends in its own tiles / waiting for the grid / in the vector work
+    if (a.prof && blockIdx.x == 0 && t == 0) { const long long n = now(); a.prof[slot] += n - t_mark; t_mark = n; }
+  };
   while (cmd != PCG_CMD_EXIT) {
     pcg_symv_tiles(a, cmd == PCG_CMD_SP ? a.p : a.x, cmd == PCG_CMD_SP ? a.q : a.tmp, colsum);
     __threadfence();
     __syncthreads();
+    lap(0);
     if (blockIdx.x != 0) {
       if (t == 0) {
         atomicAdd(&a.sync[PCG_ARRIVE], 1);
@@ -199,48 +229,59 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg(PcgArgs a) {
       s_cmd = ok;
     }
     __syncthreads();
+    lap(1);
     int next = PCG_CMD_SP, term = -1;
     if (!s_cmd) { next = PCG_CMD_EXIT; term = PCG_TERM_FAILURE; }
     __syncthreads();
     bool have_r = false;
+    // CTA 0 alone touches x, r, p, z between the barriers (the other CTAs read p / x through L2 after the release); q and tmp
+    // are summed by every SM's atomics, hence __ldcg. restrict + unrolling keeps ~8 independent L2 round trips in flight per
+    // thread: with plain struct members every store ordered the next load behind it (39 us of vector work per CG iteration).
+    double* __restrict__ X = a.x; double* __restrict__ R = a.r; double* __restrict__ Pv = a.p;
+    const double* __restrict__ Zv = a.z; double* __restrict__ Q = a.q; double* __restrict__ TMP = a.tmp;
+    const double* __restrict__ Bv = a.b;
+    const int n_pad = a.n_pad;
     if (next != PCG_CMD_EXIT && cmd == PCG_CMD_SP) {
       double pq = 0.0;
-      for (int i = t; i < a.n_pad; i += kPcgThreads) pq += a.p[i] * __ldcg(a.q + i);
+#pragma unroll 8
+      for (int i = t; i < n_pad; i += kPcgThreads) pq += Pv[i] * __ldcg(Q + i);
       pq = block_sum(pq, red);
       if (t == 0) s_val[0] = pq;
       __syncthreads();
       pq = s_val[0];
-      const double rho = a.vals[PCG_RHO];
+      const double rho = rho_cur;
       const double alpha = rho / pq;
       if (pq <= 0.0 || isinf(pq) || isnan(pq)) { next = PCG_CMD_EXIT; term = PCG_TERM_NO_CONVERGENCE; }  // indefinite direction: keep x
       else if (isinf(alpha)) { next = PCG_CMD_EXIT; term = PCG_TERM_FAILURE; }
       else {
-        if (t == 0) a.vals[PCG_ALPHA] = alpha;
         if (it % kPcgResetPeriod == 0) {
-          for (int i = t; i < a.n_pad; i += kPcgThreads) { a.x[i] += alpha * a.p[i]; a.q[i] = 0.0; }
+#pragma unroll 8
+          for (int i = t; i < n_pad; i += kPcgThreads) { X[i] += alpha * Pv[i]; Q[i] = 0.0; }
           next = PCG_CMD_SX;  // r = b - S x needs another pass over S
         } else {
-          for (int i = t; i < a.n_pad; i += kPcgThreads) { a.x[i] += alpha * a.p[i]; a.r[i] -= alpha * __ldcg(a.q + i); a.q[i] = 0.0; }
+#pragma unroll 8
+          for (int i = t; i < n_pad; i += kPcgThreads) { const double qi = __ldcg(Q + i); X[i] += alpha * Pv[i]; R[i] -= alpha * qi; Q[i] = 0.0; }
           have_r = true;
         }
       }
       __syncthreads();
     } else if (next != PCG_CMD_EXIT) {  // cmd == PCG_CMD_SX
-      for (int i = t; i < a.n_pad; i += kPcgThreads) { a.r[i] = a.b[i] - __ldcg(a.tmp + i); a.tmp[i] = 0.0; }
+#pragma unroll 8
+      for (int i = t; i < n_pad; i += kPcgThreads) { R[i] = Bv[i] - __ldcg(TMP + i); TMP[i] = 0.0; }
       have_r = true;
       __syncthreads();
     }
     if (have_r) {
       double q1 = 0.0;
-      for (int i = t; i < a.n_pad; i += kPcgThreads) q1 -= a.x[i] * (a.b[i] + a.r[i]);
+#pragma unroll 8
+      for (int i = t; i < n_pad; i += kPcgThreads) q1 -= X[i] * (Bv[i] + R[i]);
       q1 = block_sum(q1, red);
       if (t == 0) s_val[0] = q1;
       __syncthreads();
       q1 = s_val[0];
-      const double q0 = a.vals[PCG_Q0];
-      const double zeta = it * (q1 - q0) / q1;
-      __syncthreads();
-      if (t == 0) { a.vals[PCG_Q0] = q1; a.vals[PCG_ZETA] = zeta; a.sync[PCG_ITERS] = it; }
+      const double zeta = it * (q1 - q0_cur) / q1;
+      q0_cur = q1;
+      if (t == 0) { a.vals[PCG_ZETA] = zeta; a.sync[PCG_ITERS] = it; }
       if (zeta < a.eta) { next = PCG_CMD_EXIT; term = PCG_TERM_SUCCESS; }
       else if (it >= a.max_it) { next = PCG_CMD_EXIT; term = PCG_TERM_NO_CONVERGENCE; }
       else {
@@ -250,13 +291,12 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg(PcgArgs a) {
         if (t == 0) s_val[1] = rho;
         __syncthreads();
         rho = s_val[1];
-        const double last_rho = a.vals[PCG_RHO];
-        const double beta = rho / last_rho;
-        __syncthreads();
+        const double beta = rho / rho_cur;
         if (rho == 0.0 || isinf(rho) || isnan(rho) || beta == 0.0 || isinf(beta)) { next = PCG_CMD_EXIT; term = PCG_TERM_FAILURE; }
         else {
-          if (t == 0) a.vals[PCG_RHO] = rho;
-          for (int i = t; i < a.n_pad; i += kPcgThreads) a.p[i] = a.z[i] + beta * a.p[i];
+          rho_cur = rho;
+#pragma unroll 8
+          for (int i = t; i < n_pad; i += kPcgThreads) Pv[i] = Zv[i] + beta * Pv[i];
           next = PCG_CMD_SP;
         }
       }
@@ -270,6 +310,7 @@ __global__ void __launch_bounds__(kPcgThreads, 2) k_pcg(PcgArgs a) {
       __threadfence();
       pcg_st_release(&a.sync[PCG_GEN], gen + 1);
     }
+    lap(2);
     ++gen;
     cmd = next;
     __syncthreads();
@@ -323,11 +364,21 @@ struct SchurPcg {
     a.A = A; a.ld = ld; a.n_pad = n_pad; a.b = rhs; a.x = x; a.r = r; a.p = p; a.z = z; a.q = q; a.tmp = tmp;
     a.minv = minv; a.blk = blk; a.nblk = nblk; a.tasks = tasks; a.ntasks = ntasks; a.eta = eta; a.max_it = std::max(1, max_it);
     a.sync = sync; a.vals = vals; a.fail = fail; a.iters_total = iters_total;
+    a.prof = nullptr;
+    long long* d_prof = nullptr;
+    if (getenv("THB_PCG_PROF")) { cudaMalloc(&d_prof, sizeof(long long) * 4); cudaMemsetAsync(d_prof, 0, sizeof(long long) * 4, st); a.prof = d_prof; }
     if (nblk) k_pcg_precond<<<(nblk + 127) / 128, 128, 0, st>>>(nblk, blk, A, ld, minv, fail);
     k_pcg_init<<<1, kPcgThreads, 0, st>>>(a);
     void* args[] = {&a};
     THB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_pcg, dim3(grid), dim3(kPcgThreads), args, 0, st));
     *launches += 3;
+    if (d_prof) {
+      long long h[4] = {0, 0, 0, 0};
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+      cudaFree(d_prof);
+      fprintf(stderr, "PCGPROF CTA 0: own tiles %.1f us, waiting for the grid %.1f us, vector work + publish %.1f us\n", h[0] * 1e-3, h[1] * 1e-3, h[2] * 1e-3);
+    }
     return THB_OK;
   }
 };
