@@ -16,7 +16,7 @@
 namespace thb {
 namespace {
 
-constexpr int TV_THREADS = 128;
+constexpr int TV_THREADS = 256;
 
 // ComputeResolutionScaledThreshold (reconstruction_estimator_utils.cc:97-110)
 __device__ __host__ inline double resolution_scaled_threshold(double threshold_pixels, int w, int h) {
