@@ -389,7 +389,7 @@ __device__ bool four_point_h(const double* corr, double* H) {
   double n1[8], n2[8], T1[9], T2[9];
   normalize_image_points(corr, 4, 4, n1, T1);
   normalize_image_points(corr + 2, 4, 4, n2, T2);
-  double AtA[81], W[81], U[81], V[81], S[9];
+  double AtA[81], W[81], V[81], S[9];
   {
     double A[8 * 9];
     for (int i = 0; i < 4; ++i) {
@@ -400,7 +400,7 @@ __device__ bool four_point_h(const double* corr, double* H) {
     }
     for (int r = 0; r < 9; ++r) for (int c = 0; c < 9; ++c) { double s = 0.0; for (int k = 0; k < 8; ++k) s += A[k * 9 + r] * A[k * 9 + c]; AtA[r * 9 + c] = s; }
   }
-  sl::jacobi_svd<9>(AtA, W, U, S, V);
+  sl::jacobi_svd<9, false>(AtA, W, nullptr, S, V);  // jacobiSvd(ComputeFullV): only the null vector is used
   double Hn[9], T2i[9], tmp[9];
   for (int k = 0; k < 9; ++k) Hn[k] = V[k * 9 + 8];
   inverse3(T2, T2i);

@@ -141,13 +141,14 @@ __device__ __forceinline__ void rot_right(double* M, int p, int q, Rot j) {
   }
 }
 // Square two-sided Jacobi SVD, row-major N x N; W is caller-provided N*N scratch (may alias nothing else).
-template <int N>
+// WANT_U = false skips the accumulation of U (Eigen's ComputeFullV-only decomposition): W, S and V are unaffected, U may be nullptr.
+template <int N, bool WANT_U = true>
 __device__ inline void jacobi_svd(const double* A, double* W, double* U, double* S, double* V) {
   const double precision = 2.0 * kEps;
   double scale = 0.0;
   for (int i = 0; i < N * N; ++i) scale = fmax(scale, fabs(A[i]));
   if (scale == 0.0) scale = 1.0;
-  for (int i = 0; i < N * N; ++i) { W[i] = A[i] / scale; U[i] = V[i] = (i / N == i % N) ? 1.0 : 0.0; }
+  for (int i = 0; i < N * N; ++i) { W[i] = A[i] / scale; V[i] = (i / N == i % N) ? 1.0 : 0.0; if (WANT_U) U[i] = V[i]; }
   double maxDiag = 0.0;
   for (int i = 0; i < N; ++i) maxDiag = fmax(maxDiag, fabs(W[i * N + i]));
   bool finished = false;
@@ -171,7 +172,7 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
           const Rot jrt{jr.c, -jr.s};
           const Rot jl{rot1.c * jrt.c - rot1.s * jrt.s, rot1.c * jrt.s + rot1.s * jrt.c};
           rot_left<N>(W, p, q, jl);
-          rot_right<N>(U, p, q, Rot{jl.c, -jl.s});
+          if (WANT_U) rot_right<N>(U, p, q, Rot{jl.c, -jl.s});
           rot_right<N>(W, p, q, jr);
           rot_right<N>(V, p, q, jr);
           maxDiag = fmax(maxDiag, fmax(fabs(W[p * N + p]), fabs(W[q * N + q])));
@@ -181,7 +182,7 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
   for (int i = 0; i < N; ++i) {
     const double a = W[i * N + i];
     S[i] = fabs(a);
-    if (a < 0.0) for (int r = 0; r < N; ++r) U[r * N + i] = -U[r * N + i];
+    if (WANT_U && a < 0.0) for (int r = 0; r < N; ++r) U[r * N + i] = -U[r * N + i];
   }
   for (int i = 0; i < N; ++i) S[i] *= scale;
   for (int i = 0; i < N; ++i) {
@@ -191,7 +192,7 @@ __device__ inline void jacobi_svd(const double* A, double* W, double* U, double*
     if (best == 0.0) break;
     if (pos != i) {
       dswap(S[i], S[pos]);
-      for (int r = 0; r < N; ++r) { dswap(U[r * N + i], U[r * N + pos]); dswap(V[r * N + i], V[r * N + pos]); }
+      for (int r = 0; r < N; ++r) { if (WANT_U) dswap(U[r * N + i], U[r * N + pos]); dswap(V[r * N + i], V[r * N + pos]); }
     }
   }
 }
