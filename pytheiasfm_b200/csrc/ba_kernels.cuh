@@ -439,13 +439,22 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
 // active); what remains is the RED rate of the SM's load/store path: 162 M atomics in 0.9 ms = 1.3 per clock per SM,
 // whether their sectors hit L2 or not (row-banded passes that keep S in L2 take a third of the time each - measured).
 // There is no vector form of red.add.f64 (ptxas rejects .v2.f64), so the count itself has to go down to go faster.
-template <int PD>
+// r02: BULK = true issues ONE TMA reduce-add per 48-byte row of a block (cp.reduce.async.bulk ... .add.f64, SASS
+// UBLKRED.G.S.ADD.F64) from a per-thread staging slot in shared memory instead of six scalar REDs: 27 M bulk operations instead
+// of 162 M atomics on C2. In isolation that is 2.3x faster (tools/microbench/red_micro.cu: 0.71 vs 1.62 ms for 27 M scattered
+// rows); in this kernel 0.87 vs 0.90 ms, because both forms end in the same L2 read-modify-write units: ncu shows 2.2 GB of
+// DRAM traffic for the 145 MB triangle (it does not stay in L2 next to the operand planes). Measured and dropped: row bands that
+// keep the written part of S L2-resident (every extra pass re-stages the operands: +0.2 ms per pass, 1.17 / 1.41 / 1.63 ms of normal
+// equations for 2 / 3 / 4 bands), and splitting the rows of a block between the TMA and the RED path (+0.07 ms per scalar row).
+// BULK = false is the r01 form (THB_K3_MODE=red).
+template <int PD, bool BULK>
 __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __restrict__ chunk_pt, const int* __restrict__ pt_start,
                                                        const int* __restrict__ o_cam, const double* __restrict__ jc_pl,
                                                        const double* __restrict__ jp_pl, const double* __restrict__ vinv,
                                                        double* __restrict__ Smat, int ld) {
   constexpr int CH = 64;
   constexpr int MAXPAIRS = CH * (CH - 1) / 2;
+  __shared__ __align__(16) double sStage[BULK ? 2 : 1][BULK ? 128 : 1][6];  // one 48-byte row per thread, double-buffered
   __shared__ double sW[CH][6 * PD];
   __shared__ double sT[CH][6 * PD];
   __shared__ int sC[CH];
@@ -487,6 +496,41 @@ __global__ void __launch_bounds__(128) k_schur_offdiag(int no, const int* __rest
     }
     if (threadIdx.x == 0) sNumPairs = pair_base;
     __syncthreads();
+    if constexpr (BULK) {
+      const int rows = sNumPairs * 6;
+      int it = 0;
+      for (int e = threadIdx.x; e < rows; e += blockDim.x, ++it) {
+        const int pair = e / 6, r = e - 6 * pair;
+        const int lp = sPair[pair], li = lp & 255, lj = lp >> 8;
+        const int ci = sC[li], cj = sC[lj];
+        if (ci == cj) {  // two observations of one camera: entries of a diagonal block, scalar atomics as before
+          for (int b = 0; b < 6; ++b) {
+            double v = 0.0;
+#pragma unroll
+            for (int t = 0; t < PD; ++t) v += sT[li][r * PD + t] * sW[lj][b * PD + t];
+            atomicAdd(&Smat[(size_t)(6 * ci + max(r, b)) * ld + 6 * ci + min(r, b)], r == b ? -2.0 * v : -v);
+          }
+          continue;
+        }
+        double* slot = sStage[it & 1][threadIdx.x];
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // the operation that read this slot two rows ago is done with it
+        // row r of the block in the lower triangle: S[ci, cj] -= T_i W_j^T for ci > cj, its transpose for ci < cj
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          double v = 0.0;
+#pragma unroll
+          for (int t = 0; t < PD; ++t) v += ci > cj ? sT[li][r * PD + t] * sW[lj][k * PD + t] : sT[li][k * PD + t] * sW[lj][r * PD + t];
+          slot[k] = -v;
+        }
+        double* dst = ci > cj ? &Smat[(size_t)(6 * ci + r) * ld + 6 * cj] : &Smat[(size_t)(6 * cj + r) * ld + 6 * ci];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(slot);
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst), "r"(sa), "r"(48) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      return;
+    }
     const int items = sNumPairs * 36;
     for (int e = threadIdx.x; e < items; e += blockDim.x) {
       const int pair = e / 36, ab = e - 36 * pair, a = ab / 6, b = ab - 6 * a;

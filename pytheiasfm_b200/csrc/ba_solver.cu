@@ -14,6 +14,7 @@
 #include <mutex>
 #include <set>
 #include <tuple>
+#include <string>
 #include <vector>
 
 #include "ba_kernels.cuh"
@@ -450,10 +451,14 @@ int SolveAndStep(ThbBaSession* s) {
   THB_CUDA_CHECK(cudaMemsetAsync(s->d_scal + SC_MCC, 0, sizeof(double), s->st));
   if (s->red_variable) {
     s->t_normal.Begin();
-    if (s->PD == 3)
-      k_schur_offdiag<3><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
-    else
-      k_schur_offdiag<4><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+    static const bool k3_red = []() { const char* m = getenv("THB_K3_MODE"); return m && std::string(m) == "red"; }();  // A/B: the r01 scalar-RED form
+    if (s->PD == 3) {
+      if (k3_red) k_schur_offdiag<3, false><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+      else k_schur_offdiag<3, true><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+    } else {
+      if (k3_red) k_schur_offdiag<4, false><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+      else k_schur_offdiag<4, true><<<s->nchunks, 128, 0, s->st>>>(s->no, s->d_chunk_pt, s->d_pt_start, s->d_op_cam, s->d_jc, s->d_jp, s->d_vinv, s->chol.A, s->chol.ld);
+    }
     ++s->sum.gpu_launches;
     s->t_normal.End();
     s->t_solve.Begin();
