@@ -363,3 +363,16 @@ def test_prosac_sampler_matches_oracle(lib, oracle, monkeypatch):
     params.ransac_type = 2
     b = batch.struct()
     assert lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None) == capi.THB_E_UNSUPPORTED
+
+
+def test_distributed_front_end_single_rank(lib, oracle):
+    """pytheiasfm_b200.distributed.estimate_relative_poses without a process group (world = 1): the same records and masks as the
+    direct C-ABI call, through the deal / pack / gather / reassemble path the multi-GPU runs use."""
+    from pytheiasfm_b200 import distributed as ptd
+    batch, _ = synthetic.make_pair_batch(19, n=300, seed=12, base_seed=900)
+    params = synthetic.c4_params(capi.ThbRansacParams())
+    records, masks = ptd.estimate_relative_poses(batch, params)
+    res, mask = gpu_ransac(lib, batch, params)
+    assert records.tobytes() == res.tobytes()
+    for i in range(batch.num_pairs):
+        np.testing.assert_array_equal(masks[i], mask[batch.pair_offset[i]:batch.pair_offset[i + 1]])

@@ -117,3 +117,39 @@ def test_track_shard_and_gather_over_gloo():
     ret = mgr.dict()
     mp.spawn(_track_worker, args=(2, port, ret), nprocs=2, join=True)
     assert all(ret.get(r) for r in range(2))
+
+
+def _worker_pairs(rank, world, port, ret):
+    import torch.distributed as dist
+    from oracle import oracle_py
+    from pytheiasfm_b200 import distributed as ptd, synthetic
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        batch, _ = synthetic.make_pair_batch(21, n=150, seed=9, base_seed=500)
+        params = synthetic.c4_params(oracle_py.ransac_default_params())
+
+        def run_local(sub, p):  # the CPU stand-in of the device call: the oracle on this rank's blocks
+            rc, res, mask = oracle_py.ransac_relpose_batch(sub, p)
+            assert rc == 0
+            return res, mask
+        records, masks = ptd.run_pairs_sharded(batch, params, run_local)
+        rc, full, full_mask = oracle_py.ransac_relpose_batch(batch, params)
+        assert records.tobytes() == full.tobytes()
+        for i in range(batch.num_pairs):
+            np.testing.assert_array_equal(masks[i], full_mask[batch.pair_offset[i]:batch.pair_offset[i + 1]])
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_pair_verification_front_end_over_gloo(world):
+    """pytheiasfm_b200.distributed.run_pairs_sharded: block-cyclic deal, local runs, one all_gather of records + bit-packed
+    masks; every rank ends with the table the single-process call gives (the oracle stands in for the device call on CPU)."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_pairs, args=(world, port, ret), nprocs=world, join=True)
+    assert all(ret.get(r) for r in range(world))
