@@ -106,6 +106,11 @@ typedef struct ThbBaProblem {
   const uint8_t* cam_has_position_prior;      /* [num_cameras]   View::HasPositionPrior()                          */
   const double* cam_position_prior;           /* [num_cameras*3] View::GetPositionPrior()                          */
   const double* cam_position_prior_sqrt_info; /* [num_cameras*9] View::GetPositionPriorSqrtInformation(), row-major */
+  /* BundleAdjustmentOptions::use_gravity_priors (bundle_adjuster.cc:165-168, gravity_error.h:44-86): the 3 residuals
+   * sqrt_info * (R(angle_axis) * (0, 0, -1) - gravity_prior) on the camera orientation, no loss function. Same conventions. */
+  const uint8_t* cam_has_gravity_prior;       /* [num_cameras]   View::HasGravityPrior()                           */
+  const double* cam_gravity_prior;            /* [num_cameras*3] View::GetGravityPrior()                           */
+  const double* cam_gravity_prior_sqrt_info;  /* [num_cameras*9] View::GetGravityPriorSqrtInformation(), row-major  */
 } ThbBaProblem;
 
 /* BundleAdjustmentOptions (bundle_adjustment.h:87-167) restricted to what reaches

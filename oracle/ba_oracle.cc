@@ -343,21 +343,19 @@ class BaOracle {
     if (want_jac)
       for (int t = 0; t < nth; ++t)
         for (int k = 0; k < n_red; ++k) grad[n_pt_tan + k] += gth[t][k];
-    if (!only_fixed && P.cam_has_position_prior) {
-      if (want_jac) { prior_r.assign((size_t)nc * 3, 0.0); prior_J.assign((size_t)nc * 18, 0.0); }
+    if (!only_fixed && AnyPrior()) {
+      if (want_jac) { prior_n.assign(nc, 0); prior_r.assign((size_t)nc * 6, 0.0); prior_J.assign((size_t)nc * 36, 0.0); }
       for (int c = 0; c < nc; ++c) {
-        if (!HasPrior(c)) continue;
-        double r[3];
-        PriorResidual(s, c, r);
-        total += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        double r[6], Ja[6][6];
+        const int n = PriorRows(s, c, r, Ja);
+        for (int k = 0; k < n; ++k) total += 0.5 * r[k] * r[k];
         if (!want_jac) continue;
-        const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)c;
-        for (int k = 0; k < 3; ++k) {
-          prior_r[(size_t)c * 3 + k] = r[k];
+        prior_n[c] = n;
+        for (int k = 0; k < n; ++k) {
+          prior_r[(size_t)c * 6 + k] = r[k];
           for (int t = 0; t < cam_td[c]; ++t) {
-            const int col = cam_idx[c][t];
-            const double j = col < 3 ? -A[3 * k + col] : 0.0;
-            prior_J[(size_t)c * 18 + k * 6 + t] = j;
+            const double j = Ja[k][cam_idx[c][t]];
+            prior_J[(size_t)c * 36 + k * 6 + t] = j;
             grad[cam_off[c] + t] += j * r[k];
           }
         }
@@ -383,14 +381,14 @@ class BaOracle {
   void ScalePriorColumns() {
     if (prior_J.empty()) return;
     for (int c = 0; c < nc; ++c)
-      if (HasPrior(c)) for (int k = 0; k < 3; ++k) for (int t = 0; t < cam_td[c]; ++t) prior_J[(size_t)c * 18 + k * 6 + t] *= scale[cam_off[c] + t];
+      for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) prior_J[(size_t)c * 36 + k * 6 + t] *= scale[cam_off[c] + t];
   }
 
   void SquaredColumnNorm(std::vector<double>* out) const {
     out->assign(n_tan, 0.0);
     if (!prior_J.empty())
       for (int c = 0; c < nc; ++c)
-        if (HasPrior(c)) for (int k = 0; k < 3; ++k) for (int t = 0; t < cam_td[c]; ++t) { const double v = prior_J[(size_t)c * 18 + k * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
+        for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) { const double v = prior_J[(size_t)c * 36 + k * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
     for (int i = 0; i < no; ++i) {
       if (fixed[i]) continue;
       const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
@@ -477,13 +475,12 @@ class BaOracle {
     for (int k = 0; k < nr; ++k) S[(size_t)k * nr + k] = D[n_pt_tan + k] * D[n_pt_tan + k];
     if (!prior_J.empty())
       for (int c = 0; c < nc; ++c) {
-        if (!HasPrior(c)) continue;
         const int o = cam_off[c] - n_pt_tan;
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < prior_n[c]; ++k)
           for (int a = 0; a < cam_td[c]; ++a) {
-            const double ja = prior_J[(size_t)c * 18 + k * 6 + a];
-            rhs[o + a] += ja * prior_r[(size_t)c * 3 + k];
-            for (int b = 0; b <= a; ++b) S[(size_t)(o + a) * nr + o + b] += ja * prior_J[(size_t)c * 18 + k * 6 + b];
+            const double ja = prior_J[(size_t)c * 36 + k * 6 + a];
+            rhs[o + a] += ja * prior_r[(size_t)c * 6 + k];
+            for (int b = 0; b <= a; ++b) S[(size_t)(o + a) * nr + o + b] += ja * prior_J[(size_t)c * 36 + k * 6 + b];
           }
       }
     std::vector<omp_lock_t> locks(std::max(1, nc + ng));
@@ -657,11 +654,11 @@ class BaOracle {
           for (int u = 0; u < d; ++u)
             for (int v = 0; v < d; ++v) N[(size_t)c * 36 + u * d + v] += Jc[(size_t)i * 12 + a * 6 + u] * Jc[(size_t)i * 12 + a * 6 + v];
       }
-      for (int c = 0; c < nc; ++c)
-        if (HasPrior(c))
-          for (int k = 0; k < 3; ++k)
+      if (!prior_J.empty())
+        for (int c = 0; c < nc; ++c)
+          for (int k = 0; k < prior_n[c]; ++k)
             for (int u = 0; u < cam_td[c]; ++u)
-              for (int v = 0; v < cam_td[c]; ++v) N[(size_t)c * 36 + u * cam_td[c] + v] += prior_J[(size_t)c * 18 + k * 6 + u] * prior_J[(size_t)c * 18 + k * 6 + v];
+              for (int v = 0; v < cam_td[c]; ++v) N[(size_t)c * 36 + u * cam_td[c] + v] += prior_J[(size_t)c * 36 + k * 6 + u] * prior_J[(size_t)c * 36 + k * 6 + v];
       for (int c = 0; c < nc; ++c) {
         const int d = cam_td[c];
         if (!d || !count[c]) continue;
@@ -822,14 +819,12 @@ class BaOracle {
       acc += -(m[0] * (res[2 * (size_t)i] + m[0] / 2.0) + m[1] * (res[2 * (size_t)i + 1] + m[1] / 2.0));
     }
     if (!prior_J.empty())
-      for (int c = 0; c < nc; ++c) {
-        if (!HasPrior(c)) continue;
-        for (int k = 0; k < 3; ++k) {
+      for (int c = 0; c < nc; ++c)
+        for (int k = 0; k < prior_n[c]; ++k) {
           double m = 0.0;
-          for (int t = 0; t < cam_td[c]; ++t) m += prior_J[(size_t)c * 18 + k * 6 + t] * step[cam_off[c] + t];
-          acc += -(m * (prior_r[(size_t)c * 3 + k] + m / 2.0));
+          for (int t = 0; t < cam_td[c]; ++t) m += prior_J[(size_t)c * 36 + k * 6 + t] * step[cam_off[c] + t];
+          acc += -(m * (prior_r[(size_t)c * 6 + k] + m / 2.0));
         }
-      }
     return acc;
   }
 
@@ -896,15 +891,14 @@ class BaOracle {
       (*r_out)[2 * q] = r[0] * residual_scaling; (*r_out)[2 * q + 1] = r[1] * residual_scaling;
       for (int a = 0; a < 2; ++a) for (int k = 0; k < dim; ++k) (*J_out)[((size_t)2 * q + a) * dim + k] = t[a][k];
     }
-    if (kind == BLK_CAM && HasPrior(idx)) {  // the camera's position prior is one more residual block of this parameter block
-      double r[3];
-      PriorResidual(s, idx, r);
-      total += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-      if (want_jac) {
-        const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)idx;
-        for (int k = 0; k < 3; ++k) {
+    if (kind == BLK_CAM && AnyPrior()) {  // the camera's prior blocks are residual blocks of this parameter block as well
+      double r[6], Ja[6][6];
+      const int n = PriorRows(s, idx, r, Ja);
+      for (int k = 0; k < n; ++k) {
+        total += 0.5 * r[k] * r[k];
+        if (want_jac) {
           r_out->push_back(r[k]);
-          for (int t = 0; t < dim; ++t) J_out->push_back(cam_idx[idx][t] < 3 ? -A[3 * k + cam_idx[idx][t]] : 0.0);
+          for (int t = 0; t < dim; ++t) J_out->push_back(Ja[k][cam_idx[idx][t]]);
         }
       }
     }
@@ -1194,15 +1188,42 @@ class BaOracle {
   std::vector<double> res, Jc, Ji, Jp, grad, scale;
   double x_cost = 0.0, gradient_max_norm = 0.0;
   int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0, n_cg_iterations = 0;
-  // position priors (bundle_adjuster.cc:160-163, position_error.h:44-80): residual sqrt_info * (prior - position), no loss;
-  // prior_r / prior_J hold the 3 residuals and the 3 x cam_td tangent Jacobian of every camera that has one
+  // Camera prior residual blocks, no loss function: position (bundle_adjuster.cc:160-163, position_error.h:44-80)
+  // sqrt_info * (prior - position), and gravity (:165-168, gravity_error.h:44-86) sqrt_info * (R(aa) (0,0,-1) - prior), differentiated
+  // with Jets like ceres::AutoDiffCostFunction does. prior_n[c] rows (0, 3 or 6), prior_r their residuals, prior_J the rows x cam_td
+  // tangent Jacobian (stride 6) as of the last Evaluate with want_jac.
+  std::vector<int> prior_n;
   std::vector<double> prior_r, prior_J;
-  bool HasPrior(int c) const { return P.cam_has_position_prior && P.cam_position_prior && P.cam_position_prior_sqrt_info && P.cam_has_position_prior[c] && cam_td[c] > 0; }
-  void PriorResidual(const State& s, int c, double r[3]) const {
-    const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)c;
-    const double* pr = P.cam_position_prior + 3 * (size_t)c;
-    const double d[3] = {pr[0] - s.cam[(size_t)c * 6], pr[1] - s.cam[(size_t)c * 6 + 1], pr[2] - s.cam[(size_t)c * 6 + 2]};
-    for (int k = 0; k < 3; ++k) r[k] = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
+  bool HasPositionPrior(int c) const { return P.cam_has_position_prior && P.cam_position_prior && P.cam_position_prior_sqrt_info && P.cam_has_position_prior[c] && cam_td[c] > 0; }
+  bool HasGravityPrior(int c) const { return P.cam_has_gravity_prior && P.cam_gravity_prior && P.cam_gravity_prior_sqrt_info && P.cam_has_gravity_prior[c] && cam_td[c] > 0; }
+  bool AnyPrior() const { return P.cam_has_position_prior || P.cam_has_gravity_prior; }
+  // residuals r[<= 6] and ambient Jacobian Ja[row][6] of camera c's prior blocks at state s; returns the number of rows
+  int PriorRows(const State& s, int c, double* r, double (*Ja)[6]) const {
+    int n = 0;
+    if (HasPositionPrior(c)) {
+      const double* A = P.cam_position_prior_sqrt_info + 9 * (size_t)c;
+      const double* pr = P.cam_position_prior + 3 * (size_t)c;
+      const double d[3] = {pr[0] - s.cam[(size_t)c * 6], pr[1] - s.cam[(size_t)c * 6 + 1], pr[2] - s.cam[(size_t)c * 6 + 2]};
+      for (int k = 0; k < 3; ++k, ++n) {
+        r[n] = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
+        for (int a = 0; a < 6; ++a) Ja[n][a] = a < 3 ? -A[3 * k + a] : 0.0;
+      }
+    }
+    if (HasGravityPrior(c)) {
+      const double* A = P.cam_gravity_prior_sqrt_info + 9 * (size_t)c;
+      const double* gp = P.cam_gravity_prior + 3 * (size_t)c;
+      typedef Jet<3> J3;
+      const J3 aa[3] = {J3(s.cam[(size_t)c * 6 + 3], 0), J3(s.cam[(size_t)c * 6 + 4], 1), J3(s.cam[(size_t)c * 6 + 5], 2)};
+      const J3 gw[3] = {J3(0.0), J3(0.0), J3(-1.0)};
+      J3 gc[3];
+      AngleAxisRotatePoint(aa, gw, gc);
+      for (int k = 0; k < 3; ++k, ++n) {
+        J3 res = J3(A[3 * k]) * (gc[0] - gp[0]) + J3(A[3 * k + 1]) * (gc[1] - gp[1]) + J3(A[3 * k + 2]) * (gc[2] - gp[2]);
+        r[n] = res.a;
+        for (int a = 0; a < 6; ++a) Ja[n][a] = a < 3 ? 0.0 : res.v[a - 3];
+      }
+    }
+    return n;
   }
 };
 

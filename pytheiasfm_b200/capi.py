@@ -58,6 +58,7 @@ class ThbBaProblem(C.Structure):
         ("obs_cam", C.c_void_p), ("obs_pt", C.c_void_p), ("obs_xy", C.c_void_p),
         ("obs_sqrt_info", C.c_void_p),
         ("cam_has_position_prior", C.c_void_p), ("cam_position_prior", C.c_void_p), ("cam_position_prior_sqrt_info", C.c_void_p),
+        ("cam_has_gravity_prior", C.c_void_p), ("cam_gravity_prior", C.c_void_p), ("cam_gravity_prior_sqrt_info", C.c_void_p),
     ]
 
 
@@ -316,6 +317,7 @@ class HostBaProblem:
         ("pts", np.float64), ("pt_const", np.uint8),
         ("obs_cam", np.int32), ("obs_pt", np.int32), ("obs_xy", np.float64), ("obs_sqrt_info", np.float64),
         ("cam_has_position_prior", np.uint8), ("cam_position_prior", np.float64), ("cam_position_prior_sqrt_info", np.float64),
+        ("cam_has_gravity_prior", np.uint8), ("cam_gravity_prior", np.float64), ("cam_gravity_prior_sqrt_info", np.float64),
     ]
 
     def __init__(self, arrays):

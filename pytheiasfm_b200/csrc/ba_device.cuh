@@ -61,6 +61,14 @@ __device__ __forceinline__ void rot_apply(const double w[3], double a, double b,
   y[2] = v[2] + a * c2 + b * (w[2] * wv - th2 * v[2]);
 }
 
+// Camera prior residual blocks (no loss): r[3] and the 3 x 6 ambient Jacobian, from the packed prior [sqrt information (9,
+// row-major) | prior (3)] and the camera record (CAMD doubles: w, a, b, A, B, C).
+//   position (position_error.h:44-80): r = A (prior - C),                 J = [-A | 0]
+//   gravity  (gravity_error.h:44-86):  r = A (R(w) (0,0,-1) - prior),     J = [0 | A d(R g)/dw], d(R g)/dw = -[q]x J_l(w) with q = R g
+//                                      (ceres' first-order branch: q = g, J_l = I), the chain eval_obs uses for the reprojection blocks
+__device__ __forceinline__ void cam_prior_position(const double* pr, const double* rec, double r[3], double J[3][6]);
+__device__ __forceinline__ void cam_prior_gravity(const double* pr, const double* rec, double r[3], double J[3][6]);
+
 struct BaState {  // one set of parameter values (current x, or the candidate)
   double* cam;
   double* camd;
@@ -375,6 +383,36 @@ __device__ __forceinline__ void cam_derive_record(const double* __restrict__ cam
 }
 
 // Small SPD inverse by Cholesky, N in {3,4}; returns false if not positive definite.
+__device__ __forceinline__ void cam_prior_position(const double* pr, const double* rec, double r[3], double J[3][6]) {
+  const double d[3] = {pr[9] - rec[CD_C], pr[10] - rec[CD_C + 1], pr[11] - rec[CD_C + 2]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    r[k] = pr[3 * k] * d[0] + pr[3 * k + 1] * d[1] + pr[3 * k + 2] * d[2];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { J[k][a] = -pr[3 * k + a]; J[k][3 + a] = 0.0; }
+  }
+}
+__device__ __forceinline__ void cam_prior_gravity(const double* pr, const double* rec, double r[3], double J[3][6]) {
+  const double* w = rec + CD_W;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double g[3] = {0.0, 0.0, -1.0};
+  double q[3];
+  rot_apply(w, rec[CD_A], rec[CD_B], th2, g, q);
+  const bool small = rec[CD_JA] == 0.0;
+  const double q0 = small ? g[0] : q[0], q1 = small ? g[1] : q[1], q2 = small ? g[2] : q[2];
+  const double d[3] = {q[0] - pr[9], q[1] - pr[10], q[2] - pr[11]};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double a0 = pr[3 * k], a1 = pr[3 * k + 1], a2 = pr[3 * k + 2];
+    r[k] = a0 * d[0] + a1 * d[1] + a2 * d[2];
+    const double G[3] = {-(a1 * q2 - a2 * q1), -(a2 * q0 - a0 * q2), -(a0 * q1 - a1 * q0)};  // A_k (-[q]x)
+    double GM[3];
+    rot_apply(w, -rec[CD_JA], rec[CD_JB], th2, G, GM);                                         // ... J_l
+    J[k][0] = J[k][1] = J[k][2] = 0.0;
+    J[k][3] = GM[0]; J[k][4] = GM[1]; J[k][5] = GM[2];
+  }
+}
+
 template <int N>
 __device__ __forceinline__ bool spd_inverse(const double* A /*row-major NxN, lower used*/, double* Ainv) {
   double L[N][N];

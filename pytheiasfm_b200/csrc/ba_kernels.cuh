@@ -399,20 +399,24 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
     red[0][k] = red[0][k] + red[1][k] + red[2][k] + red[3][k];
   }
   __syncthreads();
-  if (has_prior && has_prior[c] && !(K.cam_const[c] & THB_CAM_CONST_POSITION) && threadIdx.x == 0) {  // constant position: a constant of the cost
-    // position prior (position_error.h:44-80): r = A (prior - C), J = -A on the position columns (scaled like every column)
-    const double* A = prior + 12 * (size_t)c;
-    const double d[3] = {A[9] - S.cam[6 * (size_t)c], A[10] - S.cam[6 * (size_t)c + 1], A[11] - S.cam[6 * (size_t)c + 2]};
-    double r[3], J[3][3];
-    for (int k = 0; k < 3; ++k) {
-      r[k] = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
-      for (int a = 0; a < 3; ++a) J[k][a] = -A[3 * k + a] * cs[6 * c + a];
-    }
-    for (int a = 0; a < 3; ++a) {
-      const double b = J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
-      red[0][21 + a] += b; red[0][27 + a] += b;
-      red[0][33 + a] += J[0][a] * J[0][a] + J[1][a] * J[1][a] + J[2][a] * J[2][a];
-      for (int b2 = 0; b2 <= a; ++b2) red[0][a * (a + 1) / 2 + b2] += J[0][a] * J[0][b2] + J[1][a] * J[1][b2] + J[2][a] * J[2][b2];
+  if (has_prior && has_prior[c] && threadIdx.x == 0) {
+    // prior residual blocks of the camera (ba_device.cuh::cam_prior_*): J^T J, J^T r and the column norms of J diag(scale) join
+    // the camera's block. bit 0: position, bit 1: gravity; constant coordinates have no columns (their prior is a constant of the cost).
+    const int cc = K.cam_const[c];
+    double cscale[6];
+    for (int a = 0; a < 6; ++a) cscale[a] = (cc & (a < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) ? 0.0 : cs[6 * c + a];
+    for (int kind = 0; kind < 2; ++kind) {
+      if (!(has_prior[c] & (1 << kind))) continue;
+      double r[3], J[3][6];
+      if (kind == 0) cam_prior_position(prior + 24 * (size_t)c, S.camd + (size_t)c * CAMD, r, J);
+      else cam_prior_gravity(prior + 24 * (size_t)c + 12, S.camd + (size_t)c * CAMD, r, J);
+      for (int k = 0; k < 3; ++k) for (int a = 0; a < 6; ++a) J[k][a] *= cscale[a];
+      for (int a = 0; a < 6; ++a) {
+        const double b = J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
+        red[0][21 + a] += b; red[0][27 + a] += b;
+        red[0][33 + a] += J[0][a] * J[0][a] + J[1][a] * J[1][a] + J[2][a] * J[2][a];
+        for (int b2 = 0; b2 <= a; ++b2) red[0][a * (a + 1) / 2 + b2] += J[0][a] * J[0][b2] + J[1][a] * J[1][b2] + J[2][a] * J[2][b2];
+      }
     }
   }
   __syncthreads();
@@ -1145,16 +1149,21 @@ __global__ void k_eval_ambient(BaConst K, BaState S, ObsSoA O, double* __restric
       for (int k = 0; k < KS; ++k) jintr[(2 * (size_t)i + a) * KS + k] = k < 9 ? ji[a * 9 + k] : 0.0;
 }
 
-// position priors: cost 0.5 |A (prior - C)|^2 of every free camera that has one, added to a cost slot
+__global__ void k_prior_flags(int nc, const uint8_t* __restrict__ has_pos, const uint8_t* __restrict__ has_grav, uint8_t* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nc) out[c] = (uint8_t)((has_pos[c] ? 1 : 0) | (has_grav[c] ? 2 : 0));
+}
+
+// camera priors: cost 0.5 |r|^2 of the prior blocks of every camera that is not fully constant, added to a cost slot
 __global__ void k_prior_cost(int nc, const uint8_t* __restrict__ has_prior, const double* __restrict__ prior, const uint8_t* __restrict__ cam_const,
-                             const double* __restrict__ cam, double* __restrict__ slot) {
+                             const double* __restrict__ camd, double* __restrict__ slot) {
   __shared__ double red[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
   if (c < nc && has_prior[c] && cam_const[c] != THB_CAM_CONST_ALL) {
-    const double* A = prior + 12 * (size_t)c;
-    const double d[3] = {A[9] - cam[6 * (size_t)c], A[10] - cam[6 * (size_t)c + 1], A[11] - cam[6 * (size_t)c + 2]};
-    for (int k = 0; k < 3; ++k) { const double r = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2]; v += 0.5 * r * r; }
+    double r[3], J[3][6];
+    if (has_prior[c] & 1) { cam_prior_position(prior + 24 * (size_t)c, camd + (size_t)c * CAMD, r, J); v += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); }
+    if (has_prior[c] & 2) { cam_prior_gravity(prior + 24 * (size_t)c + 12, camd + (size_t)c * CAMD, r, J); v += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); }
   }
   v = block_sum(v, red);
   if (threadIdx.x == 0 && v != 0.0) atomicAdd(slot, v);
@@ -1162,18 +1171,24 @@ __global__ void k_prior_cost(int nc, const uint8_t* __restrict__ has_prior, cons
 
 // their share of the model cost change -(J s)^T (r + J s / 2) with s = -y (scaled space)
 __global__ void k_prior_mcc(int nc, const uint8_t* __restrict__ has_prior, const double* __restrict__ prior, const uint8_t* __restrict__ cam_const,
-                            const double* __restrict__ cam, const double* __restrict__ cs, const double* __restrict__ yred, double* __restrict__ scal) {
+                            const double* __restrict__ camd, const double* __restrict__ cs, const double* __restrict__ yred, double* __restrict__ scal) {
   __shared__ double red[32];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   double v = 0.0;
-  if (c < nc && has_prior[c] && !(cam_const[c] & THB_CAM_CONST_POSITION)) {
-    const double* A = prior + 12 * (size_t)c;
-    const double d[3] = {A[9] - cam[6 * (size_t)c], A[10] - cam[6 * (size_t)c + 1], A[11] - cam[6 * (size_t)c + 2]};
-    const double u[3] = {cs[6 * c] * yred[6 * c], cs[6 * c + 1] * yred[6 * c + 1], cs[6 * c + 2] * yred[6 * c + 2]};
-    for (int k = 0; k < 3; ++k) {
-      const double r = A[3 * k] * d[0] + A[3 * k + 1] * d[1] + A[3 * k + 2] * d[2];
-      const double m = A[3 * k] * u[0] + A[3 * k + 1] * u[1] + A[3 * k + 2] * u[2];  // J s = (-A diag(cs)) (-y)
-      v += -(m * (r + 0.5 * m));
+  if (c < nc && has_prior[c] && cam_const[c] != THB_CAM_CONST_ALL) {
+    const int cc = cam_const[c];
+    double u[6];  // -(scaled step) per coordinate: J s = -sum_a J[k][a] scale_a y_a
+    for (int a = 0; a < 6; ++a) u[a] = (cc & (a < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) ? 0.0 : cs[6 * c + a] * yred[6 * c + a];
+    for (int kind = 0; kind < 2; ++kind) {
+      if (!(has_prior[c] & (1 << kind))) continue;
+      double r[3], J[3][6];
+      if (kind == 0) cam_prior_position(prior + 24 * (size_t)c, camd + (size_t)c * CAMD, r, J);
+      else cam_prior_gravity(prior + 24 * (size_t)c + 12, camd + (size_t)c * CAMD, r, J);
+      for (int k = 0; k < 3; ++k) {
+        double m = 0.0;
+        for (int a = 0; a < 6; ++a) m -= J[k][a] * u[a];
+        v += -(m * (r[k] + 0.5 * m));
+      }
     }
   }
   v = block_sum(v, red);

@@ -133,8 +133,8 @@ struct ThbBaSession {
   // owned device memory
   int *d_cam_group = nullptr, *d_intr_model = nullptr, *d_intr_slot = nullptr;
   uint8_t *d_cam_const = nullptr, *d_pt_const = nullptr;
-  uint8_t* d_has_prior = nullptr;  // position priors (ThbBaProblem::cam_has_position_prior), nullptr when the problem has none
-  double* d_prior = nullptr;       // [nc][12]: sqrt information (9, row-major), prior position (3)
+  uint8_t* d_has_prior = nullptr;  // camera priors: bit 0 position, bit 1 gravity (ThbBaProblem::cam_has_*_prior); nullptr when the problem has none
+  double* d_prior = nullptr;       // [nc][24]: position [sqrt information (9, row-major) | prior (3)], gravity [likewise]
   uint16_t* d_intr_const = nullptr;
   int *d_op_cam = nullptr, *d_op_pt = nullptr, *d_oc_cam = nullptr, *d_oc_pt = nullptr;
   double2 *d_op_xy = nullptr, *d_op_si = nullptr, *d_oc_xy = nullptr, *d_oc_si = nullptr;
@@ -325,7 +325,7 @@ void DispatchCamPass(ThbBaSession* s, double inv_radius) {
 // position priors are residual blocks of their own: their cost joins whatever slot the reprojection blocks were summed into
 void AddPriorCost(ThbBaSession* s, const BaState& st, int slot) {
   if (!s->d_has_prior) return;
-  k_prior_cost<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, st.cam, s->d_scal + slot);
+  k_prior_cost<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, st.camd, s->d_scal + slot);
   ++s->sum.gpu_launches;
 }
 
@@ -491,7 +491,7 @@ int SolveAndStep(ThbBaSession* s) {
     }
     s->sum.gpu_launches += 3;
     if (s->d_has_prior) {
-      k_prior_mcc<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, s->X.cam, s->d_cs, s->chol.x, s->d_scal);
+      k_prior_mcc<<<cdiv(s->nc, 128), 128, 0, s->st>>>(s->nc, s->d_has_prior, s->d_prior, s->d_cam_const, s->X.camd, s->d_cs, s->chol.x, s->d_scal);
       ++s->sum.gpu_launches;
     }
   }
@@ -847,12 +847,26 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, P->cam_group, sizeof(int) * nc, kin, st));
   if (P->cam_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, P->cam_const, nc, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_const, 0, std::max(nc, 1), st));
-  if (P->cam_has_position_prior && nc > 0) {  // position priors: packed [sqrt information (9) | prior (3)] per camera
-    if (!P->cam_position_prior || !P->cam_position_prior_sqrt_info) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_has_position_prior without prior / sqrt information arrays"); }
-    THB_TRY(M.Get(&s->d_has_prior, nc)); THB_TRY(M.Get(&s->d_prior, (size_t)nc * 12));
-    THB_TRY_CUDA(cudaMemcpyAsync(s->d_has_prior, P->cam_has_position_prior, nc, kin, st));
-    THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior, 12 * sizeof(double), P->cam_position_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
-    THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 9, 12 * sizeof(double), P->cam_position_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
+  if ((P->cam_has_position_prior || P->cam_has_gravity_prior) && nc > 0) {  // camera priors, packed per camera (see d_prior)
+    if ((P->cam_has_position_prior && (!P->cam_position_prior || !P->cam_position_prior_sqrt_info)) ||
+        (P->cam_has_gravity_prior && (!P->cam_gravity_prior || !P->cam_gravity_prior_sqrt_info))) {
+      FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_has_*_prior without prior / sqrt information arrays");
+    }
+    uint8_t *d_hp = nullptr, *d_hg = nullptr;
+    THB_TRY(M.Get(&s->d_has_prior, nc)); THB_TRY(M.Get(&s->d_prior, (size_t)nc * 24)); THB_TRY(M.Get(&d_hp, nc)); THB_TRY(M.Get(&d_hg, nc));
+    THB_TRY_CUDA(cudaMemsetAsync(s->d_prior, 0, sizeof(double) * 24 * nc, st));
+    THB_TRY_CUDA(cudaMemsetAsync(d_hp, 0, nc, st)); THB_TRY_CUDA(cudaMemsetAsync(d_hg, 0, nc, st));
+    if (P->cam_has_position_prior) {
+      THB_TRY_CUDA(cudaMemcpyAsync(d_hp, P->cam_has_position_prior, nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior, 24 * sizeof(double), P->cam_position_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 9, 24 * sizeof(double), P->cam_position_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
+    }
+    if (P->cam_has_gravity_prior) {
+      THB_TRY_CUDA(cudaMemcpyAsync(d_hg, P->cam_has_gravity_prior, nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 12, 24 * sizeof(double), P->cam_gravity_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 21, 24 * sizeof(double), P->cam_gravity_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
+    }
+    k_prior_flags<<<cdiv(nc, 256), 256, 0, st>>>(nc, d_hp, d_hg, s->d_has_prior);
   }
   if (P->pt_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, P->pt_const, np, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_const, 0, std::max(np, 1), st));

@@ -31,7 +31,7 @@ constexpr int IC_VALS = 29;  // 21 (J^T J lower) + 6 (J^T r) + cost + failures
 
 template <int PD, bool WANT_J>
 __device__ __forceinline__ void inner_cam_pass(const BaConst& K, const BaState& S, const ObsSoA& O, int c, int q0, int q1, const double* rec,
-                                               const double* scale, double (*red)[IC_VALS], double* tot, const double* prior = nullptr) {
+                                               const double* scale, double (*red)[IC_VALS], double* tot, const double* prior = nullptr, int prior_kinds = 0) {
   double v[IC_VALS];
 #pragma unroll
   for (int k = 0; k < IC_VALS; ++k) v[k] = 0.0;
@@ -72,19 +72,20 @@ __device__ __forceinline__ void inner_cam_pass(const BaConst& K, const BaState& 
     tot[threadIdx.x] = s;
   }
   __syncthreads();
-  if (prior && threadIdx.x == 0) {  // the camera's position prior is one more residual block of this parameter block
-    const double d[3] = {prior[9] - rec[CD_C], prior[10] - rec[CD_C + 1], prior[11] - rec[CD_C + 2]};
-    double r[3], J[3][3];
-    for (int k = 0; k < 3; ++k) {
-      r[k] = prior[3 * k] * d[0] + prior[3 * k + 1] * d[1] + prior[3 * k + 2] * d[2];
-      for (int a = 0; a < 3; ++a) J[k][a] = WANT_J ? -prior[3 * k + a] * scale[a] : 0.0;
-    }
-    tot[27] += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
-    if (WANT_J)
-      for (int a = 0; a < 3; ++a) {
-        tot[21 + a] += J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
-        for (int b = 0; b <= a; ++b) tot[a * (a + 1) / 2 + b] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+  if (prior && threadIdx.x == 0) {  // the camera's prior blocks are residual blocks of this parameter block as well
+    for (int kind = 0; kind < 2; ++kind) {
+      if (!(prior_kinds & (1 << kind))) continue;
+      double r[3], J[3][6];
+      if (kind == 0) cam_prior_position(prior, rec, r, J); else cam_prior_gravity(prior + 12, rec, r, J);
+      tot[27] += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+      if (WANT_J) {
+        for (int k = 0; k < 3; ++k) for (int a = 0; a < 6; ++a) J[k][a] *= scale[a];
+        for (int a = 0; a < 6; ++a) {
+          tot[21 + a] += J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
+          for (int b = 0; b <= a; ++b) tot[a * (a + 1) / 2 + b] += J[0][a] * J[0][b] + J[1][a] * J[1][b] + J[2][a] * J[2][b];
+        }
       }
+    }
   }
   if (prior) __syncthreads();
 }
@@ -107,15 +108,16 @@ __global__ void __launch_bounds__(IC_THREADS) k_inner_cam(BaConst K, BaState S, 
   __syncthreads();
   if (t == 0) cam_derive_record(x, rec);
   __syncthreads();
-  const double* prior = (has_prior && has_prior[c]) ? prior_all + 12 * (size_t)c : nullptr;
-  inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior);  // column norms of the unscaled Jacobian
+  const int prior_kinds = has_prior ? has_prior[c] : 0;
+  const double* prior = prior_kinds ? prior_all + 24 * (size_t)c : nullptr;
+  inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior, prior_kinds);  // column norms of the unscaled Jacobian
   if (tot[28] > 0.0) return;  // IterationZero failed: the block stays as it is
   if (t == 0) {
     int e = 0;
     for (int a = 0; a < 6; ++a) { e += a; scale[a] = scale[a] == 0.0 ? 0.0 : 1.0 / (1.0 + sqrt(tot[e])); ++e; }
   }
   __syncthreads();
-  inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior);
+  inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior, prior_kinds);
   // trust-region state (thread 0)
   double H[21], g[6], diag[6], x_cost = tot[27], x_norm = 0.0, radius = P.radius0, decrease_factor = 2.0, mcc = 0.0;
   bool step_ok = true, reuse_diag = false;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(IC_THREADS) k_inner_cam(BaConst K, BaState S, 
     }
     __syncthreads();
     if (s_go == 0) break;
-    inner_cam_pass<PD, false>(K, S, O, c, q0, q1, rec, scale, red, tot, prior);
+    inner_cam_pass<PD, false>(K, S, O, c, q0, q1, rec, scale, red, tot, prior, prior_kinds);
     if (t == 0) {
       int go = 1;  // 1: next trust-region iteration without a new Jacobian, 2: accepted, 0: converged
       const double cand_cost = tot[28] > 0.0 ? 1.7976931348623157e308 : tot[27];
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(IC_THREADS) k_inner_cam(BaConst K, BaState S, 
     __syncthreads();  // thread 0 rewrites s_go at the top of the next round: everybody has read it by now
     if (go2 == 0) break;
     if (go2 == 2) {
-      inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior);
+      inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior, prior_kinds);
       if (tot[28] > 0.0) break;  // EvaluateGradientAndJacobian failed: FAILURE, x keeps the accepted point
       if (t == 0) {
         for (int k = 0; k < 21; ++k) H[k] = tot[k];

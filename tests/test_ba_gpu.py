@@ -557,6 +557,49 @@ def _with_position_priors(prob, gt, bias, weight, every=1, seed=0):
     return capi.HostBaProblem(a)
 
 
+def _with_gravity_priors(prob, gt, weight, tilt=0.0, every=1, seed=0):
+    rng = np.random.default_rng(seed)
+    a = dict(prob.a)
+    nc = prob.num_cameras
+    has = np.zeros(nc, np.uint8); has[::every] = 1
+    g = np.zeros((nc, 3)); info = np.zeros((nc, 9))
+    for c in range(nc):
+        R = synthetic.rotmat_from_rotvec(gt["cam_ext"][c, 3:] + tilt * rng.normal(size=3))
+        g[c] = R @ np.array([0.0, 0.0, -1.0])
+        info[c] = (weight * (np.eye(3) + 0.1 * rng.normal(size=(3, 3)))).reshape(9)
+    a["cam_has_gravity_prior"] = has; a["cam_gravity_prior"] = g; a["cam_gravity_prior_sqrt_info"] = info
+    return capi.HostBaProblem(a)
+
+
+@pytest.mark.parametrize("case", ["gravity", "gravity_inner_position", "gravity_const_orientation", "gravity_covariance"])
+def test_gravity_priors_match_oracle(lib, oracle, case):
+    """BundleAdjustmentOptions::use_gravity_priors (bundle_adjuster.cc:165-168, gravity_error.h:44-86): residual
+    sqrt_info * (R(aa) (0,0,-1) - prior), nonlinear in the orientation, differentiated on the device through the SO(3) left
+    Jacobian and in the oracle with Jets. Alone, together with position priors and inner iterations, next to constant
+    orientations, and in the covariance."""
+    prob, gt = synthetic.config_c1()
+    o = capi.default_options(lib)
+    if case == "gravity_const_orientation":
+        prob.a["cam_const"][2::4] = capi.CAM_CONST_ORIENTATION
+    pp = _with_gravity_priors(prob, gt, weight=200.0, tilt=0.02, every=1 if case != "gravity_const_orientation" else 2, seed=6)
+    if case == "gravity_inner_position":
+        o.use_inner_iterations = 1
+        pp = _with_position_priors(pp, gt, bias=0.2, weight=20.0, every=3, seed=7)
+    if case == "gravity_covariance":
+        pp.a["pt_const"][:] = 1
+        pp = capi.HostBaProblem(pp.a)
+        rc, cc, co, pc, po = _gpu_covariance(lib, pp, o)
+        orc, occ, oco, opc, opo = oracle.ba_covariance(pp, o)
+        assert rc == orc == 0
+        np.testing.assert_array_equal(co, oco)
+        np.testing.assert_allclose(cc, occ, rtol=1e-8, atol=1e-18)
+        return
+    g, orc, pg, po = _compare_solves(lib, oracle, pp, o)
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], rtol=0, atol=1e-6)
+    plain = gpu_solve(lib, capi.HostBaProblem({k: v for k, v in pp.a.items() if "prior" not in k}), o)
+    assert g["initial_cost"] > plain["initial_cost"] and g["final_cost"] > plain["final_cost"]
+
+
 @pytest.mark.parametrize("case", ["c1", "inner", "pcg", "const_position_huber", "views_covariance"])
 def test_position_priors_match_oracle(lib, oracle, case):
     """BundleAdjustmentOptions::use_position_priors (bundle_adjuster.cc:160-163, position_error.h:44-80): 3 residuals
