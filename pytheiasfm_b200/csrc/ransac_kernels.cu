@@ -1,4 +1,7 @@
-// Hot path 2: RANSAC two-view relative-pose verification, one CTA per image pair, whole RANSAC on device.
+// Hot path 2: RANSAC two-view verification, whole loop on the device. Two schedules of the same loop, bit-identical results:
+// k_ransac (one persistent CTA per image pair, all phases fused; LO-RANSAC; large batches) and k_rs_* (one kernel per phase over
+// all active pairs, batches up to 2 048 pairs). Estimators: relative pose (five-point), absolute pose (P3P), homography (4-point);
+// samplers: RandomSampler (RANSAC) and ProsacSampler (PROSAC). two_view.cuh builds EstimateTwoViewInfo / VerifyMatches on top.
 //
 // Stands behind theia::EstimateRelativePose (sfm/estimators/estimate_relative_pose.cc:159-172) =
 // SampleConsensusEstimator<RelativePoseEstimator>::Estimate (solvers/sample_consensus_estimator.h:299-415)
@@ -8,9 +11,9 @@
 // adaptive iteration bound). It is replayed exactly: iterations are processed in batches of BI = 128 —
 //   draw   : one thread advances a bit-exact mt19937 + libstdc++ uniform_int_distribution (Lemire) and the
 //            partial Fisher-Yates permutation, 5 indices per iteration
-//   solve  : one THREAD per hypothesis runs the five-point solver (FP64 SIMT is issue-bound, so 32 hypotheses
-//            per warp cost the same as one) and the essential-matrix decomposition + cheirality vote; the
-//            candidate models go to a per-CTA scratch area in global memory (L2)
+//   solve  : one THREAD per hypothesis runs the five-point solver and the essential-matrix decomposition + cheirality
+//            vote (~1.5 M cycles of dependent FP64 / local-memory latency each, profiles/r02_ransac_schedule_ab.txt); the
+//            candidate models go to a scratch area in global memory (L2)
 //   score  : one WARP per model scores every correspondence (cheirality-gated Sampson), read through L1
 //            (a pair's 64 KB stays cached between models), lane-strided, warp-shuffle reduction; a model
 //            whose partial cost already reaches the best cost known at batch start is abandoned (it can
