@@ -263,7 +263,7 @@ typedef struct ThbRansacParams {
                               /* only (BundleAdjustTwoViewsAngular); THB_E_UNSUPPORTED for absolute pose, a no-op upstream  */
                               /* for homographies (Estimator::RefineModel default)                                          */
   int32_t lo_start_iterations;
-  int32_t ransac_type;        /* RansacType: RANSAC (0) or PROSAC (1, data sorted by quality; solvers/prosac_sampler.cc); LMED / EXHAUSTIVE unsupported */
+  int32_t ransac_type;        /* RansacType: RANSAC (0), PROSAC (1, data sorted by quality; solvers/prosac_sampler.cc) or LMED (2, solvers/lmed.h + lmed_quality_measurement.h: cost = median of the squared residuals, not with use_lo); EXHAUSTIVE (3) is rejected: its sampler CHECK-aborts for sample sizes other than 2 in the reference too */
   int32_t use_tdd_test;       /* RansacParameters::use_Tdd_test: ComputeMaxIterations counts SampleSize + 1 draws */
                               /* (sample_consensus_estimator.h:272-279); the test itself is unimplemented upstream */
   int32_t reserved0;

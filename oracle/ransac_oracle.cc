@@ -788,9 +788,34 @@ int ComputeMaxIterations(const ThbRansacParams& P, double min_sample_size, doubl
   return std::max(static_cast<double>(P.min_iterations), std::min(num_iterations, static_cast<double>(P.max_iterations)));
 }
 
+// LmedQualityMeasurement::ComputeCost (solvers/lmed_quality_measurement.h:58-118): the cost is the median of the SQUARED
+// residuals (the estimators' residuals are squared distances already; the reference squares them again), taken with
+// std::nth_element exactly as there - the upper median for an even count, the mean of the two middle values for an odd one -
+// and the inliers are the data below OpenCV's robust threshold 2.5 * 1.4826 * (1 + 5 / (n - m)) * sqrt(median).
+inline double LmedCost(const std::vector<double>& residuals, int min_sample_size, std::vector<int>* inliers) {
+  std::vector<double> sq(residuals.size());
+  for (size_t i = 0; i < residuals.size(); ++i) sq[i] = residuals[i] * residuals[i];
+  std::nth_element(sq.begin(), sq.begin() + sq.size() / 2, sq.end());
+  double median = sq[sq.size() / 2];
+  if ((sq.size() % 2) != 0) {
+    std::nth_element(sq.begin(), sq.begin() + (sq.size() / 2) - 1, sq.end());
+    median = 0.5 * (sq[(sq.size() / 2) - 1] + median);
+  }
+  const double inlier_threshold = 2.5 * 1.4826 * (1 + 5.0 / (residuals.size() - min_sample_size)) * std::sqrt(median);
+  const double squared_inlier_threshold = inlier_threshold * inlier_threshold;
+  for (size_t i = 0; i < residuals.size(); ++i)
+    if ((residuals[i] * residuals[i]) < squared_inlier_threshold) inliers->push_back(static_cast<int>(i));
+  return median;
+}
+
 template <class Est>
 double Score(const ThbRansacParams& P, const double* data, int n, const Model& m, std::vector<int>* inliers) {
   inliers->clear();
+  if (P.ransac_type == 2) {  // RansacType::LMED (solvers/lmed.h:65-72)
+    std::vector<double> residuals(n);
+    for (int i = 0; i < n; ++i) residuals[i] = Est::Error(m, data + Est::D * (size_t)i);
+    return LmedCost(residuals, Est::S, inliers);
+  }
   double cost = 0.0;
   for (int i = 0; i < n; ++i) {
     const double r = Est::Error(m, data + Est::D * (size_t)i);
@@ -1064,7 +1089,7 @@ int RunBatch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult* 
   if (!b || !p || !results) return THB_E_INVALID_ARGUMENT;
   if (!(p->error_thresh > 0) || !(p->failure_probability > 0 && p->failure_probability < 1) || p->min_inlier_ratio < 0 ||
       p->min_inlier_ratio > 1 || p->max_iterations < p->min_iterations) return THB_E_INVALID_ARGUMENT;
-  if ((p->use_lo && !Est::HAS_LO) || (p->ransac_type != 0 && p->ransac_type != 1)) return THB_E_UNSUPPORTED;
+  if ((p->use_lo && !Est::HAS_LO) || p->ransac_type < 0 || p->ransac_type > 2 || (p->ransac_type == 2 && p->use_lo)) return THB_E_UNSUPPORTED;
   const int nt = threads > 0 ? threads : omp_get_max_threads();
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
   for (int i = 0; i < b->num_pairs; ++i) {

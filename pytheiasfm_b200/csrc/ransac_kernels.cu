@@ -1,7 +1,7 @@
 // Hot path 2: RANSAC two-view verification, whole loop on the device. Two schedules of the same loop, bit-identical results:
 // k_ransac (one persistent CTA per image pair, all phases fused; LO-RANSAC; large batches) and k_rs_* (one kernel per phase over
 // all active pairs, batches up to 2 048 pairs). Estimators: relative pose (five-point), absolute pose (P3P), homography (4-point);
-// samplers: RandomSampler (RANSAC) and ProsacSampler (PROSAC). two_view.cuh builds EstimateTwoViewInfo / VerifyMatches on top.
+// samplers: RandomSampler (RANSAC, LMED) and ProsacSampler (PROSAC); quality measurements: inlier support, MLE, LMED (median). two_view.cuh builds EstimateTwoViewInfo / VerifyMatches on top.
 //
 // Stands behind theia::EstimateRelativePose (sfm/estimators/estimate_relative_pose.cc:159-172) =
 // SampleConsensusEstimator<RelativePoseEstimator>::Estimate (solvers/sample_consensus_estimator.h:299-415)
@@ -968,6 +968,104 @@ __device__ void score_model(const ThbRansacParams& P, const double* __restrict__
   *ninl_out = ninl;
 }
 
+// LmedQualityMeasurement::ComputeCost (solvers/lmed_quality_measurement.h:58-118), warp-wide: cost = median of the SQUARED
+// residuals (upper median for an even count, mean of the two middle values for an odd one - the reference's nth_element code taken
+// literally), inliers = data with residual^2 below (2.5 * 1.4826 * (1 + 5 / (n - m)) * sqrt(median))^2. The order statistic is found
+// by an MSB-first radix select on the bit patterns of |r| (monotone for non-negative doubles, and squaring keeps the order, so the
+// k-th smallest r^2 is the square of the k-th smallest |r|): 8 passes of 8 bits, each pass RE-EVALUATES the residuals (a Sampson
+// error is ~40 flops; the correspondences stay in L1) and histograms the next byte of the keys that match the prefix found so far
+// in 256 shared-memory counters per warp. No residual array is stored, so n is unbounded. `hist`: 256 counters of this warp.
+template <class Est>
+__device__ void score_model_lmed(const double* __restrict__ data, int n, const Model& m, unsigned* __restrict__ hist,
+                                 uint8_t* __restrict__ mask, double* cost_out, int* ninl_out, unsigned* scored) {
+  const int lane = threadIdx.x & 31;
+  double E[9], R[9], p[3];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) { E[k] = m.E[k]; R[k] = m.R[k]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) p[k] = m.p[k];
+  const int steps = (n + 31) / 32;
+  auto residual = [&](int i) {
+    double d[Est::D];
+#pragma unroll
+    for (int k = 0; k < Est::D; ++k) d[k] = data[(size_t)i * Est::D + k];
+    return Est::error(E, R, p, d);
+  };
+  unsigned long long prefix = 0;
+  unsigned rank = (unsigned)(n / 2);  // 0-based rank of the element nth_element puts at size / 2
+  for (int shift = 56; shift >= 0; shift -= 8) {
+    const unsigned long long himask = shift == 56 ? 0ull : ~0ull << (shift + 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) hist[lane * 8 + k] = 0;
+    __syncwarp();
+    for (int s = 0; s < steps; ++s) {
+      const int i = s * 32 + lane;
+      if (i < n) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(fabs(residual(i)));
+        if (((key ^ prefix) & himask) == 0) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+      }
+    }
+    __syncwarp();
+    unsigned c[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { c[k] = hist[lane * 8 + k]; sum += c[k]; }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const unsigned excl = incl - sum;
+    const bool mine = excl <= rank && rank < incl;
+    unsigned bin = 0, nrank = 0;
+    if (mine) {
+      unsigned acc = excl;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (rank >= acc && rank < acc + c[k]) { bin = lane * 8 + k; nrank = rank - acc; }
+        acc += c[k];
+      }
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, mine)) - 1;
+    bin = __shfl_sync(0xffffffffu, bin, src);
+    rank = __shfl_sync(0xffffffffu, nrank, src);
+    prefix |= (unsigned long long)bin << shift;
+    __syncwarp();
+  }
+  const double vk = __longlong_as_double((long long)prefix);
+  double median = vk * vk;
+  if (n & 1) {  // the element at size / 2 - 1: the largest value below vk, or vk itself when it has duplicates there
+    int below = 0;
+    double vmax = 0.0;
+    for (int s = 0; s < steps; ++s) {
+      const int i = s * 32 + lane;
+      if (i < n) {
+        const double r = fabs(residual(i));
+        if (r < vk) { ++below; vmax = fmax(vmax, r); }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { below += __shfl_xor_sync(0xffffffffu, below, o); vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o)); }
+    const double vlo = below >= n / 2 ? vmax : vk;
+    median = 0.5 * (vlo * vlo + median);
+    *scored += n;
+  }
+  const double inlier_threshold = 2.5 * 1.4826 * (1 + 5.0 / (double)(n - Est::S)) * sqrt(median);
+  const double squared_inlier_threshold = inlier_threshold * inlier_threshold;
+  int ninl = 0;
+  for (int s = 0; s < steps; ++s) {
+    const int i = s * 32 + lane;
+    if (i < n) {
+      const double r = residual(i);
+      const bool inl = (r * r) < squared_inlier_threshold;
+      ninl += inl ? 1 : 0;
+      if (mask) mask[i] = inl ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ninl += __shfl_xor_sync(0xffffffffu, ninl, o);
+  *scored += 9u * (unsigned)n;
+  *cost_out = median;
+  *ninl_out = ninl;
+}
+
 struct RansacShared {
   Model best;
   int nmodels[BI];
@@ -1346,7 +1444,7 @@ __global__ void __launch_bounds__(RT, Est::SOLVE_CTAS) k_rs_solve(int na, const 
 }
 
 // score: warp (a, b) scores the models of hypothesis b of active pair a; consecutive warps share the pair's correspondences
-template <class Est, int WARPS, int CTAS>
+template <class Est, int WARPS, int CTAS, bool LMED = false>
 __global__ void __launch_bounds__(32 * WARPS, CTAS) k_rs_score(const ThbRansacParams P, const int* __restrict__ active, PairState* __restrict__ states,
                                                      const double* __restrict__ corr_all, const Model* __restrict__ model_ws,
                                                      const int* __restrict__ nmodels, double* __restrict__ cost_ws, int* __restrict__ ninl_ws) {
@@ -1363,7 +1461,12 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) k_rs_score(const ThbRansacPa
   for (int k = 0; k < nm; ++k) {
     const size_t m = ((size_t)slot * BI + b) * MAXM + k;
     double cost; int ninl;
-    score_model<Est>(Pl, corr, S.n, model_ws[m], bail, nullptr, &cost, &ninl, &scored);
+    if constexpr (LMED) {
+      __shared__ unsigned hist[WARPS * 256];
+      score_model_lmed<Est>(corr, S.n, model_ws[m], hist + w * 256, nullptr, &cost, &ninl, &scored);
+    } else {
+      score_model<Est>(Pl, corr, S.n, model_ws[m], bail, nullptr, &cost, &ninl, &scored);
+    }
     if (lane == 0) { cost_ws[m] = cost; ninl_ws[m] = ninl; }
   }
   if (lane == 0) { atomicAdd(&S.stat_data, (unsigned long long)scored); atomicAdd(&S.stat_models, (unsigned long long)nm); }
@@ -1409,7 +1512,7 @@ __global__ void __launch_bounds__(64) k_rs_scan(const ThbRansacParams P, int na,
 }
 
 // final inliers of the best model and the result record (sample_consensus_estimator.h:396-414), one warp per pair
-template <class Est>
+template <class Est, bool LMED = false>
 __global__ void __launch_bounds__(128) k_rs_final(const ThbRansacParams P, int count, PairState* __restrict__ states, const double* __restrict__ corr_all,
                                                   const uint32_t* __restrict__ seed, ThbRelPoseResult* __restrict__ results,
                                                   uint8_t* __restrict__ mask_all, unsigned long long* __restrict__ stats,
@@ -1422,7 +1525,12 @@ __global__ void __launch_bounds__(128) k_rs_final(const ThbRansacParams P, int c
   Pl.error_thresh = S.thresh;
   const double* corr = corr_all + (size_t)S.off * Est::D;
   double f_cost = 0.0; int f_ninl = 0; unsigned f_scored = 0;
-  score_model<Est>(Pl, corr, S.n, S.best, DBL_MAX, mask_all ? mask_all + S.off : nullptr, &f_cost, &f_ninl, &f_scored);
+  if constexpr (LMED) {
+    __shared__ unsigned hist[4 * 256];
+    score_model_lmed<Est>(corr, S.n, S.best, hist + (threadIdx.x >> 5) * 256, mask_all ? mask_all + S.off : nullptr, &f_cost, &f_ninl, &f_scored);
+  } else {
+    score_model<Est>(Pl, corr, S.n, S.best, DBL_MAX, mask_all ? mask_all + S.off : nullptr, &f_cost, &f_ninl, &f_scored);
+  }
   if (lane == 0) {
     ThbRelPoseResult* out = results + S.pair;
     if (stats) {
@@ -1579,7 +1687,8 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
                 v[v.size() * 9 / 10], v[v.size() * 99 / 100], v.back(), cmean, cta_max[cta_max.size() / 2], cta_max.back());
       }
       cudaEventRecord(ev[2], st);
-      k_rs_score<Est, 4, 6><<<na * (BI / 4), 128, 0, st>>>(p, act, d_states, d_corr, d_models, d_nm, d_cost, d_ninl);
+      if (p.ransac_type == 2) k_rs_score<Est, 4, 6, true><<<na * (BI / 4), 128, 0, st>>>(p, act, d_states, d_corr, d_models, d_nm, d_cost, d_ninl);
+      else k_rs_score<Est, 4, 6><<<na * (BI / 4), 128, 0, st>>>(p, act, d_states, d_corr, d_models, d_nm, d_cost, d_ninl);
       cudaEventRecord(ev[3], st);
       cudaMemsetAsync(d_count + (1 - cur), 0, sizeof(int), st);
       k_rs_scan<Est><<<(na + 63) / 64, 64, 0, st>>>(p, na, act, d_states, d_models, d_nm, d_cost, d_ninl, nxt, d_count + (1 - cur));
@@ -1590,7 +1699,8 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
       ++num_rounds;
     }
     if (rc != THB_OK) break;
-    k_rs_final<Est><<<(count + 3) / 4, 128, 0, st>>>(p, count, d_states, d_corr, d_seed, d_res, d_mask, d_stats, d_rng, rng_mode);
+    if (p.ransac_type == 2) k_rs_final<Est, true><<<(count + 3) / 4, 128, 0, st>>>(p, count, d_states, d_corr, d_seed, d_res, d_mask, d_stats, d_rng, rng_mode);
+    else k_rs_final<Est><<<(count + 3) / 4, 128, 0, st>>>(p, count, d_states, d_corr, d_seed, d_res, d_mask, d_stats, d_rng, rng_mode);
   }
   for (auto& e : ev) cudaEventDestroy(e);
   if (rc != THB_OK) THB_FAIL(rc, "round-synchronous RANSAC: CUDA error");
@@ -1614,7 +1724,7 @@ int launch_ransac(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, co
      // 10 000 pairs 215 vs 208 ms - there the fused kernel's mix of phases per SM wins). THB_RANSAC_MODE=fused|rounds forces one.
     const char* m = getenv("THB_RANSAC_MODE");  // read per call: tests switch it
     const int mode = !m ? 0 : std::string(m) == "fused" ? 1 : std::string(m) == "rounds" ? 2 : 0;
-    const bool rounds = mode == 2 || (mode == 0 && np <= 2048);
+    const bool rounds = mode == 2 || (mode == 0 && np <= 2048) || p.ransac_type == 2;  // LMED scoring lives in k_rs_score only
     if (!(p.use_lo && Est::HAS_LO) && rounds)
       return launch_ransac_rounds<Est>(st, B, p, np, d_off, d_corr, d_seed, total, d_res, d_mask, d_thresh, d_rng, rng_mode, d_skip);
   }
@@ -1657,7 +1767,8 @@ int run_batch(const ThbPairBatch* b, const ThbRansacParams* p, ThbRelPoseResult*
     // HomographyEstimator has no RefineModel: the reference's LO branch is a `continue` that only skips the iteration-bound update
     THB_FAIL(THB_E_UNSUPPORTED, "use_lo is only implemented for the relative-pose estimator");
   }
-  if (p->ransac_type != 0 && p->ransac_type != 1) THB_FAIL(THB_E_UNSUPPORTED, "RansacType::RANSAC and PROSAC are implemented (LMED, EXHAUSTIVE are not)");
+  if (p->ransac_type < 0 || p->ransac_type > 2) THB_FAIL(THB_E_UNSUPPORTED, "RansacType::RANSAC, PROSAC and LMED are implemented (EXHAUSTIVE is not)");
+  if (p->ransac_type == 2 && p->use_lo) THB_FAIL(THB_E_UNSUPPORTED, "use_lo with RansacType::LMED is not implemented");
   if (b->num_pairs < 0 || (b->memory_space != THB_MEM_HOST && b->memory_space != THB_MEM_DEVICE)) THB_FAIL(THB_E_INVALID_ARGUMENT, "bad batch");
   if (b->num_pairs == 0) return THB_OK;
   if (!b->pair_offset || !b->seed) THB_FAIL(THB_E_INVALID_ARGUMENT, "null batch array");

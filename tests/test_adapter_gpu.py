@@ -259,6 +259,13 @@ def test_EstimateRelativePose():
     ok_lo, pose_lo, summary_lo = pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.RANSAC, corrs)
     assert ok_lo and summary_lo.num_lo_iterations >= 1
     assert np.rad2deg(np.arccos(np.clip((np.trace(pose_lo.rotation @ R.T) - 1) / 2, -1, 1))) < 1.0
+    params.use_lo = False
+    for variant in (pt.sfm.RansacType.PROSAC, pt.sfm.RansacType.LMED):     # create_and_initialize_ransac_variant.h:52-86
+        ok_v, pose_v, summary_v = pt.sfm.EstimateRelativePose(params, variant, corrs)
+        assert ok_v and len(summary_v.inliers) > 100
+        assert np.rad2deg(np.arccos(np.clip((np.trace(pose_v.rotation @ R.T) - 1) / 2, -1, 1))) < 2.0
+    with pytest.raises(Exception):
+        pt.sfm.EstimateRelativePose(params, pt.sfm.RansacType.EXHAUSTIVE, corrs)   # the reference's sampler CHECK-aborts (sample size != 2)
 
 
 def test_PoseFromThreePoints_and_EstimateCalibratedAbsolutePose():

@@ -323,5 +323,50 @@ def test_prosac_needs_fewer_iterations_on_quality_sorted_data(oracle):
     assert rc == rc2 == 0 and (res2["success"] == 1).all()
     assert res2["num_iterations"].mean() < 0.8 * res["num_iterations"].mean()   # the confidence bound still asks for ~150 iterations
     assert (res2["num_inliers"] >= 0.9 * res["num_inliers"]).all()
-    params.ransac_type = 2
+    params.ransac_type = 3   # EXHAUSTIVE
     assert oracle.ransac_relpose_batch(sorted_batch, params)[0] == capi.THB_E_UNSUPPORTED
+
+
+def lmed_reference(residuals, min_sample_size):
+    """numpy restatement of LmedQualityMeasurement::ComputeCost (solvers/lmed_quality_measurement.h:58-118), written from the sorted
+    array instead of nth_element: upper median for an even count, mean of the two middle values for an odd one."""
+    sq = np.sort(residuals * residuals)
+    n = len(sq)
+    median = sq[n // 2] if n % 2 == 0 else 0.5 * (sq[n // 2 - 1] + sq[n // 2])
+    thr = 2.5 * 1.4826 * (1 + 5.0 / (n - min_sample_size)) * np.sqrt(median)
+    return median, (residuals * residuals) < thr * thr
+
+
+def in_front(c, R, pos):
+    """IsTriangulatedPointInFrontOfCameras (triangulation.cc:216-232): RelativePoseEstimator::Error returns the largest double for a
+    correspondence that triangulates behind a camera."""
+    d1 = np.array([c[0], c[1], 1.0]); d2 = R.T @ np.array([c[2], c[3], 1.0])
+    return (d2 @ d2) * (d1 @ pos) - (d1 @ d2) * (d2 @ pos) > 0 and (d1 @ d2) * (d1 @ pos) - (d1 @ d1) * (d2 @ pos) > 0
+
+
+@pytest.mark.parametrize("n", [400, 401])
+def test_lmed_cost_and_inliers(oracle, n):
+    """RansacType::LMED (solvers/lmed.h:65-72): the reported cost is the median of the squared residuals of the returned model and
+    the inliers are those below the robust threshold derived from it, for even and odd data counts; with 70 % inliers the minimiser
+    of the median is a model supported by the true inliers."""
+    batch, gts = synthetic.make_pair_batch(6, n=n, inlier_ratio=0.7, seed=21, base_seed=400)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    params.ransac_type = 2
+    rc, res, mask = oracle.ransac_relpose_batch(batch, params)
+    assert rc == 0 and (res["success"] == 1).all()
+    for p in range(batch.num_pairs):
+        a, b = int(batch.pair_offset[p]), int(batch.pair_offset[p + 1])
+        c = batch.corr[a:b]
+        E = res["essential_matrix"][p].reshape(3, 3)
+        R = res["rotation"][p].reshape(3, 3); pos = res["position"][p]
+        r = np.array([sampson(E, c[i, :2], c[i, 2:]) if in_front(c[i], R, pos) else np.finfo(np.float64).max for i in range(b - a)])
+        with np.errstate(over="ignore"):
+            median, inl = lmed_reference(r, 5)
+        assert abs(res["best_cost"][p] - median) <= 1e-9 * median
+        flips = np.nonzero(inl != mask[a:b].astype(bool))[0]     # numpy's Sampson error differs from the oracle's by ulps
+        assert len(flips) <= 1
+        assert res["num_inliers"][p] == mask[a:b].sum()
+        truth = gts[p][2]
+        assert (mask[a:b].astype(bool) & truth).sum() >= 0.8 * truth.sum()    # the threshold is a heuristic on the median, not the noise level
+    params.use_lo = 1
+    assert oracle.ransac_relpose_batch(batch, params)[0] == capi.THB_E_UNSUPPORTED

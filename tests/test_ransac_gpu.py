@@ -360,9 +360,49 @@ def test_prosac_sampler_matches_oracle(lib, oracle, monkeypatch):
         for f in ("essential_matrix", "rotation", "position"):
             assert np.array_equal(res[f], ores[f], equal_nan=True), f
     assert ores["num_iterations"].mean() < ref_res["num_iterations"].mean()
-    params.ransac_type = 2
+    params.ransac_type = 3   # EXHAUSTIVE
     b = batch.struct()
     assert lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None) == capi.THB_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n", [600, 601, 37])
+def test_lmed_matches_oracle(lib, oracle, n):
+    """RansacType::LMED (solvers/lmed.h:65-72, lmed_quality_measurement.h:58-118): the median of the squared residuals found by the
+    warp radix select equals the oracle's nth_element median bit for bit (even and odd counts, a count below one warp step), hence
+    identical best models, iteration counts and inlier masks; all three estimators."""
+    batch, _ = synthetic.make_pair_batch(20, n=n, inlier_ratio=0.7, seed=5, base_seed=4100)
+    params = synthetic.c4_params(oracle.ransac_default_params())
+    params.ransac_type = 2
+    rc, ores, omask = oracle.ransac_relpose_batch(batch, params)
+    assert rc == 0
+    res, mask = gpu_ransac(lib, batch, params)
+    np.testing.assert_array_equal(res["num_iterations"], ores["num_iterations"])
+    np.testing.assert_array_equal(res["best_cost"], ores["best_cost"])
+    np.testing.assert_array_equal(mask, omask)
+    np.testing.assert_array_equal(res["num_inliers"], ores["num_inliers"])
+    for f in ("essential_matrix", "rotation", "position"):
+        assert np.array_equal(res[f], ores[f], equal_nan=True), f
+    params.use_lo = 1
+    b = batch.struct()
+    assert lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None) == capi.THB_E_UNSUPPORTED
+
+
+@pytest.mark.parametrize("kind", ["abspose", "homography"])
+def test_lmed_homography_and_absolute_pose_match_oracle(lib, oracle, kind):
+    """LMED through the other two estimators (P3P: up to 4 models per sample; homography), odd data count."""
+    make = synthetic.make_abspose_batch if kind == "abspose" else synthetic.make_homography_batch
+    batch, _ = make(12, n=301, inlier_ratio=0.75, seed=9, base_seed=5200)
+    def mk(p):
+        p = synthetic.c4_params(p); p.ransac_type = 2
+        return p
+    rc, ores, omask = oracle.ransac_batch(kind, batch, mk(oracle.ransac_default_params()))
+    assert rc == 0
+    res, mask = gpu_ransac(lib, batch, mk(capi.ThbRansacParams()), kind=kind)
+    np.testing.assert_array_equal(res["num_iterations"], ores["num_iterations"])
+    np.testing.assert_array_equal(res["best_cost"], ores["best_cost"])
+    np.testing.assert_array_equal(mask, omask)
+    for f in ("essential_matrix", "rotation", "position"):
+        assert np.array_equal(res[f], ores[f], equal_nan=True), f
 
 
 def test_distributed_front_end_single_rank(lib, oracle):
