@@ -200,7 +200,9 @@ def test_inner_iterations_coordinate_descent(oracle):
     ra = oracle.ba_solve(a, o)
     o.use_inner_iterations = 1
     rb = oracle.ba_solve(b, o)
-    assert ra["iter_cost"] == rb["iter_cost"]
+    # (the oracle's OpenMP cost reduction sums in thread order: equal up to the last ulps, not bit for bit)
+    assert len(ra["iter_cost"]) == len(rb["iter_cost"])
+    np.testing.assert_allclose(ra["iter_cost"], rb["iter_cost"], rtol=1e-12)
 
 
 def test_iterative_schur_reaches_the_exact_minimum(oracle):
