@@ -16,7 +16,7 @@
 //            (16 flop per byte of C traffic)
 // The right-hand side rides along as one extra (padded) tile-row of the matrix, so the forward
 // substitution is a by-product; the backward substitution is ONE kernel: a CTA per 64-column
-// block, waiting on per-block ready flags, x_b = inv(L_bb)^T (y_b - sum_{k>b} L_kb^T x_k).
+// block, polling the tagged words x_k is published in, x_b = inv(L_bb)^T (y_b - sum_{k>b} L_kb^T x_k).
 #include "dense_chol.cuh"
 
 #include <algorithm>
@@ -1266,35 +1266,56 @@ __global__ void __launch_bounds__(128, 2) chol_ll_kernel(double* __restrict__ A,
 // CTA handles 64-column blocks b = nblk-1-blockIdx.x, then b - gridDim.x, ... (descending, so that a
 // CTA never waits on a block owned by a CTA that is not yet resident).
 //   x_b = inv(L_bb)^T ( y_b - sum_{k>b} L[k-block rows, b-block cols]^T x_k )
-// ready[k] is set (release) once x_k has been written to y[k*64 ..).
+// The 94 blocks are a serial chain, so the hand-off is what is timed: x_k is published as TAGGED words (each 32-bit half of
+// a value travels in its own 8-byte word next to the tag of this solve - single-copy atomic, the NCCL LL idea), and a consumer
+// polls the data itself: one L2 round trip per link instead of flag poll + barrier + data load, and no fence / flag store on
+// the producer side (r02: 0.285 -> see DESIGN 3.1). Tags are the solve's epoch, so the buffer is never cleared.
+__device__ __forceinline__ ulonglong2 ld_tagged(const ulonglong2* p) {
+  ulonglong2 v;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_tagged(ulonglong2* p, double value, unsigned tag) {
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(value), tg = (unsigned long long)tag << 32;
+  const unsigned long long lo = (bits & 0xffffffffull) | tg, hi = (bits >> 32) | tg;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
 __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double* __restrict__ A, int ld, int nblk,
                                                              const double* __restrict__ dinv, double* __restrict__ y,
-                                                             int* __restrict__ ready) {
+                                                             ulonglong2* __restrict__ xt, unsigned tag, int* __restrict__ fail) {
   extern __shared__ double sdi[];  // inv(L_bb), 64 x 65
   __shared__ double xk[NB];
   __shared__ double part[4][NB];
   const int t = threadIdx.x, col = t & 63, rg = t >> 6;  // 4 row groups of 16 rows
   for (int b = nblk - 1 - blockIdx.x; b >= 0; b -= gridDim.x) {
     for (int e = t; e < NB * NB; e += 256) sdi[(e / NB) * (NB + 1) + (e % NB)] = dinv[(size_t)b * NB * NB + e];
+    const double yb = t < NB ? y[b * NB + t] : 0.0;
     double acc = 0.0;
     for (int k = nblk - 1; k > b; --k) {
-      // the L block does not depend on x: issue its loads before waiting for x_k
+      // the L block does not depend on x: its loads are in flight while x_k is polled
       const double* Lkb = A + (size_t)(k * NB + rg * 16) * ld + b * NB + col;
       double l[16];
 #pragma unroll
       for (int r = 0; r < 16; ++r) l[r] = Lkb[(size_t)r * ld];
-      if (t == 0) {
-        while (atomicAdd(&ready[k], 0) == 0) { __nanosleep(20); }
-        __threadfence();
-      }
-      __syncthreads();
-      const double* xs = y + k * NB + rg * 16;
+      const ulonglong2* xs = xt + k * NB + rg * 16;
+      ulonglong2 w[16];
+      int spins = 0;
+      for (;;) {
 #pragma unroll
-      for (int r = 0; r < 16; ++r) acc += l[r] * __ldcg(xs + r);
+        for (int r = 0; r < 16; ++r) w[r] = ld_tagged(xs + r);
+        bool ok = true;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) ok = ok && (unsigned)(w[r].x >> 32) == tag && (unsigned)(w[r].y >> 32) == tag;
+        if (ok) break;
+        if (++spins > (1 << 22)) { atomicExch(fail, 2); break; }  // a lost producer: report it like a failed factorisation
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        acc += l[r] * __longlong_as_double((long long)((w[r].x & 0xffffffffull) | (w[r].y << 32)));
     }
     part[rg][col] = acc;
     __syncthreads();
-    if (t < NB) xk[t] = y[b * NB + t] - (part[0][t] + part[1][t] + part[2][t] + part[3][t]);
+    if (t < NB) xk[t] = yb - (part[0][t] + part[1][t] + part[2][t] + part[3][t]);
     __syncthreads();
     // (inv^T y)_c = sum_r inv[r][c] y_r, rows split over the 4 groups
     double v = 0.0;
@@ -1302,10 +1323,12 @@ __global__ void __launch_bounds__(256) chol_backsolve_kernel(const double* __res
     for (int r = 0; r < 16; ++r) v += sdi[(rg * 16 + r) * (NB + 1) + col] * xk[rg * 16 + r];
     part[rg][col] = v;
     __syncthreads();
-    if (t < NB) y[b * NB + t] = part[0][t] + part[1][t] + part[2][t] + part[3][t];
-    __threadfence();
-    __syncthreads();
-    if (t == 0) atomicExch(&ready[b], 1);
+    if (t < NB) {
+      const double xb = part[0][t] + part[1][t] + part[2][t] + part[3][t];
+      st_tagged(xt + b * NB + t, xb, tag);
+      y[b * NB + t] = xb;
+    }
+    __syncthreads();  // part / sdi are rewritten by the next block
   }
 }
 
@@ -1336,7 +1359,9 @@ int DenseChol::Init(int n_, cudaStream_t st) {
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&A), sizeof(double) * (size_t)rows_total * ld, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&dinv), sizeof(double) * (size_t)nblk * NB * NB, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&x), sizeof(double) * n_pad, st));
-  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&ready), sizeof(int) * nblk, st));
+  THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&xtag), sizeof(ulonglong2) * n_pad, st));
+  THB_CUDA_CHECK(cudaMemsetAsync(xtag, 0, sizeof(ulonglong2) * n_pad, st));
+  epoch = 0;
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&rdiag), sizeof(double) * n_pad, st));
   THB_CUDA_CHECK(cudaMallocAsync(reinterpret_cast<void**>(&dscr), sizeof(double) * 2 * NB * NB, st));
   {  // tile tasks of the left-looking kernel: block column J has ceil((row blocks from the diagonal down) / 2) tiles
@@ -1396,12 +1421,12 @@ void DenseChol::Free(cudaStream_t st) {
   if (A) cudaFreeAsync(A, st);
   if (dinv) cudaFreeAsync(dinv, st);
   if (x) cudaFreeAsync(x, st);
-  if (ready) cudaFreeAsync(ready, st);
+  if (xtag) cudaFreeAsync(xtag, st);
   if (rdiag) cudaFreeAsync(rdiag, st);
   if (dscr) cudaFreeAsync(dscr, st);
   if (ll_sync) cudaFreeAsync(ll_sync, st);
   if (ll_cols) cudaFreeAsync(ll_cols, st);
-  A = dinv = x = rdiag = dscr = nullptr; ready = nullptr; ll_sync = ll_cols = nullptr;
+  A = dinv = x = rdiag = dscr = nullptr; xtag = nullptr; ll_sync = ll_cols = nullptr;
   if (s2) { cudaStreamDestroy(s2); s2 = nullptr; }
   if (ev_start) { cudaEventDestroy(ev_start); ev_start = nullptr; }
   for (int i = 0; i < 4; ++i) {
@@ -1469,8 +1494,8 @@ int DenseChol::FactorAndSolve(cudaStream_t st, int* fail_flag, int* launches) {
   }
   chol_ll_check_kernel<<<1, 1, 0, st>>>(ll_sync, fail_flag);
   chol_copy_row_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(A + (size_t)n_pad * ld, x, n_pad);
-  THB_CUDA_CHECK(cudaMemsetAsync(ready, 0, sizeof(int) * nblk, st));
-  chol_backsolve_kernel<<<std::min(nblk, num_sms), 256, kBackSmem, st>>>(A, ld, nblk, dinv, x, ready);
+  if (++epoch == 0) epoch = 1;  // tag 0 is the cleared buffer
+  chol_backsolve_kernel<<<std::min(nblk, num_sms), 256, kBackSmem, st>>>(A, ld, nblk, dinv, x, xtag, epoch, fail_flag);
   *launches += 4;
   THB_CUDA_CHECK(cudaGetLastError());
   return THB_OK;
@@ -1507,8 +1532,8 @@ int DenseChol::FactorLegacy(cudaStream_t st, int* fail_flag, int* launches) {
   THB_CUDA_CHECK(cudaStreamWaitEvent(st, ev_pp[(nob - 1) & 3], 0));
   chol_inverse_kernel<<<nblk, 256, kInvSmem, st>>>(A, ld, dinv);
   chol_copy_row_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(A + (size_t)n_pad * ld, x, n_pad);
-  THB_CUDA_CHECK(cudaMemsetAsync(ready, 0, sizeof(int) * nblk, st));
-  chol_backsolve_kernel<<<std::min(nblk, num_sms), 256, kBackSmem, st>>>(A, ld, nblk, dinv, x, ready);
+  if (++epoch == 0) epoch = 1;  // tag 0 is the cleared buffer
+  chol_backsolve_kernel<<<std::min(nblk, num_sms), 256, kBackSmem, st>>>(A, ld, nblk, dinv, x, xtag, epoch, fail_flag);
   *launches += 3;
   THB_CUDA_CHECK(cudaGetLastError());
   return THB_OK;

@@ -15,7 +15,8 @@ struct DenseChol {
   double* rdiag = nullptr; // 1 / L_kk
   double* dscr = nullptr;  // two 64 x 64 copies of the next diagonal blocks (input of the fused diag + panel kernel)
   double* x = nullptr;     // n_pad solution
-  int* ready = nullptr;    // per-64-block flags of the backward substitution
+  ulonglong2* xtag = nullptr;  // backward substitution: x published as tagged words (value halves + the solve's epoch)
+  unsigned epoch = 0;
   int* ll_sync = nullptr;  // task counter + progress counters of the left-looking tile kernel
   int* ll_cols = nullptr;  // first task index of every 64-column block (+ total)
   int ll_grid = 0, ll_sync_ints = 0;
