@@ -111,6 +111,11 @@ typedef struct ThbBaProblem {
   const uint8_t* cam_has_gravity_prior;       /* [num_cameras]   View::HasGravityPrior()                           */
   const double* cam_gravity_prior;            /* [num_cameras*3] View::GetGravityPrior()                           */
   const double* cam_gravity_prior_sqrt_info;  /* [num_cameras*9] View::GetGravityPriorSqrtInformation(), row-major  */
+  /* BundleAdjustmentOptions::use_orientation_priors (bundle_adjuster.cc:170-172, orientation_error.h:44-80): the 3 residuals
+   * sqrt_info * log(exp(angle_axis) * exp(orientation_prior)^-1) (SO(3) logarithm, Sophus) on the camera orientation, no loss. */
+  const uint8_t* cam_has_orientation_prior;       /* [num_cameras]   View::HasOrientationPrior()                          */
+  const double* cam_orientation_prior;            /* [num_cameras*3] View::GetOrientationPrior() (angle-axis)             */
+  const double* cam_orientation_prior_sqrt_info;  /* [num_cameras*9] View::GetOrientationPriorSqrtInformation(), row-major */
 } ThbBaProblem;
 
 /* BundleAdjustmentOptions (bundle_adjustment.h:87-167) restricted to what reaches

@@ -344,18 +344,18 @@ class BaOracle {
       for (int t = 0; t < nth; ++t)
         for (int k = 0; k < n_red; ++k) grad[n_pt_tan + k] += gth[t][k];
     if (!only_fixed && AnyPrior()) {
-      if (want_jac) { prior_n.assign(nc, 0); prior_r.assign((size_t)nc * 6, 0.0); prior_J.assign((size_t)nc * 36, 0.0); }
+      if (want_jac) { prior_n.assign(nc, 0); prior_r.assign((size_t)nc * kPriorRows, 0.0); prior_J.assign((size_t)nc * kPriorRows * 6, 0.0); }
       for (int c = 0; c < nc; ++c) {
-        double r[6], Ja[6][6];
+        double r[kPriorRows], Ja[kPriorRows][6];
         const int n = PriorRows(s, c, r, Ja);
         for (int k = 0; k < n; ++k) total += 0.5 * r[k] * r[k];
         if (!want_jac) continue;
         prior_n[c] = n;
         for (int k = 0; k < n; ++k) {
-          prior_r[(size_t)c * 6 + k] = r[k];
+          prior_r[(size_t)c * kPriorRows + k] = r[k];
           for (int t = 0; t < cam_td[c]; ++t) {
             const double j = Ja[k][cam_idx[c][t]];
-            prior_J[(size_t)c * 36 + k * 6 + t] = j;
+            prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + t] = j;
             grad[cam_off[c] + t] += j * r[k];
           }
         }
@@ -381,14 +381,14 @@ class BaOracle {
   void ScalePriorColumns() {
     if (prior_J.empty()) return;
     for (int c = 0; c < nc; ++c)
-      for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) prior_J[(size_t)c * 36 + k * 6 + t] *= scale[cam_off[c] + t];
+      for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + t] *= scale[cam_off[c] + t];
   }
 
   void SquaredColumnNorm(std::vector<double>* out) const {
     out->assign(n_tan, 0.0);
     if (!prior_J.empty())
       for (int c = 0; c < nc; ++c)
-        for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) { const double v = prior_J[(size_t)c * 36 + k * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
+        for (int k = 0; k < prior_n[c]; ++k) for (int t = 0; t < cam_td[c]; ++t) { const double v = prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + t]; (*out)[cam_off[c] + t] += v * v; }
     for (int i = 0; i < no; ++i) {
       if (fixed[i]) continue;
       const int c = P.obs_cam[i], g = P.cam_group[c], p = P.obs_pt[i];
@@ -478,9 +478,9 @@ class BaOracle {
         const int o = cam_off[c] - n_pt_tan;
         for (int k = 0; k < prior_n[c]; ++k)
           for (int a = 0; a < cam_td[c]; ++a) {
-            const double ja = prior_J[(size_t)c * 36 + k * 6 + a];
-            rhs[o + a] += ja * prior_r[(size_t)c * 6 + k];
-            for (int b = 0; b <= a; ++b) S[(size_t)(o + a) * nr + o + b] += ja * prior_J[(size_t)c * 36 + k * 6 + b];
+            const double ja = prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + a];
+            rhs[o + a] += ja * prior_r[(size_t)c * kPriorRows + k];
+            for (int b = 0; b <= a; ++b) S[(size_t)(o + a) * nr + o + b] += ja * prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + b];
           }
       }
     std::vector<omp_lock_t> locks(std::max(1, nc + ng));
@@ -658,7 +658,7 @@ class BaOracle {
         for (int c = 0; c < nc; ++c)
           for (int k = 0; k < prior_n[c]; ++k)
             for (int u = 0; u < cam_td[c]; ++u)
-              for (int v = 0; v < cam_td[c]; ++v) N[(size_t)c * 36 + u * cam_td[c] + v] += prior_J[(size_t)c * 36 + k * 6 + u] * prior_J[(size_t)c * 36 + k * 6 + v];
+              for (int v = 0; v < cam_td[c]; ++v) N[(size_t)c * 36 + u * cam_td[c] + v] += prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + u] * prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + v];
       for (int c = 0; c < nc; ++c) {
         const int d = cam_td[c];
         if (!d || !count[c]) continue;
@@ -822,8 +822,8 @@ class BaOracle {
       for (int c = 0; c < nc; ++c)
         for (int k = 0; k < prior_n[c]; ++k) {
           double m = 0.0;
-          for (int t = 0; t < cam_td[c]; ++t) m += prior_J[(size_t)c * 36 + k * 6 + t] * step[cam_off[c] + t];
-          acc += -(m * (prior_r[(size_t)c * 6 + k] + m / 2.0));
+          for (int t = 0; t < cam_td[c]; ++t) m += prior_J[(size_t)c * (kPriorRows * 6) + k * 6 + t] * step[cam_off[c] + t];
+          acc += -(m * (prior_r[(size_t)c * kPriorRows + k] + m / 2.0));
         }
     return acc;
   }
@@ -892,7 +892,7 @@ class BaOracle {
       for (int a = 0; a < 2; ++a) for (int k = 0; k < dim; ++k) (*J_out)[((size_t)2 * q + a) * dim + k] = t[a][k];
     }
     if (kind == BLK_CAM && AnyPrior()) {  // the camera's prior blocks are residual blocks of this parameter block as well
-      double r[6], Ja[6][6];
+      double r[kPriorRows], Ja[kPriorRows][6];
       const int n = PriorRows(s, idx, r, Ja);
       for (int k = 0; k < n; ++k) {
         total += 0.5 * r[k] * r[k];
@@ -1189,15 +1189,18 @@ class BaOracle {
   double x_cost = 0.0, gradient_max_norm = 0.0;
   int n_jac_eval = 0, n_cost_eval = 0, n_solves = 0, n_cg_iterations = 0;
   // Camera prior residual blocks, no loss function: position (bundle_adjuster.cc:160-163, position_error.h:44-80)
-  // sqrt_info * (prior - position), and gravity (:165-168, gravity_error.h:44-86) sqrt_info * (R(aa) (0,0,-1) - prior), differentiated
-  // with Jets like ceres::AutoDiffCostFunction does. prior_n[c] rows (0, 3 or 6), prior_r their residuals, prior_J the rows x cam_td
+  // sqrt_info * (prior - position), gravity (:165-168, gravity_error.h:44-86) sqrt_info * (R(aa) (0,0,-1) - prior) and orientation (:170-172,
+  // orientation_error.h:44-80) sqrt_info * log(exp(aa) exp(prior)^-1), differentiated
+  // with Jets like ceres::AutoDiffCostFunction does. prior_n[c] rows (0, 3, 6 or 9), prior_r their residuals, prior_J the rows x cam_td
   // tangent Jacobian (stride 6) as of the last Evaluate with want_jac.
+  static constexpr int kPriorRows = 9;  // position, gravity, orientation: 3 rows each
   std::vector<int> prior_n;
   std::vector<double> prior_r, prior_J;
   bool HasPositionPrior(int c) const { return P.cam_has_position_prior && P.cam_position_prior && P.cam_position_prior_sqrt_info && P.cam_has_position_prior[c] && cam_td[c] > 0; }
   bool HasGravityPrior(int c) const { return P.cam_has_gravity_prior && P.cam_gravity_prior && P.cam_gravity_prior_sqrt_info && P.cam_has_gravity_prior[c] && cam_td[c] > 0; }
-  bool AnyPrior() const { return P.cam_has_position_prior || P.cam_has_gravity_prior; }
-  // residuals r[<= 6] and ambient Jacobian Ja[row][6] of camera c's prior blocks at state s; returns the number of rows
+  bool HasOrientationPrior(int c) const { return P.cam_has_orientation_prior && P.cam_orientation_prior && P.cam_orientation_prior_sqrt_info && P.cam_has_orientation_prior[c] && cam_td[c] > 0; }
+  bool AnyPrior() const { return P.cam_has_position_prior || P.cam_has_gravity_prior || P.cam_has_orientation_prior; }
+  // residuals r[<= 9] and ambient Jacobian Ja[row][6] of camera c's prior blocks at state s; returns the number of rows
   int PriorRows(const State& s, int c, double* r, double (*Ja)[6]) const {
     int n = 0;
     if (HasPositionPrior(c)) {
@@ -1223,7 +1226,62 @@ class BaOracle {
         for (int a = 0; a < 6; ++a) Ja[n][a] = a < 3 ? 0.0 : res.v[a - 3];
       }
     }
+    if (HasOrientationPrior(c)) {  // bundle_adjuster.cc:170-172, orientation_error.h:44-80
+      const double* A = P.cam_orientation_prior_sqrt_info + 9 * (size_t)c;
+      const double* op = P.cam_orientation_prior + 3 * (size_t)c;
+      typedef Jet<3> J3;
+      const J3 aa[3] = {J3(s.cam[(size_t)c * 6 + 3], 0), J3(s.cam[(size_t)c * 6 + 4], 1), J3(s.cam[(size_t)c * 6 + 5], 2)};
+      const J3 pa[3] = {J3(op[0]), J3(op[1]), J3(op[2])};
+      J3 qa[4], qb[4], q[4], e[3];
+      So3Exp(aa, qa);
+      So3Exp(pa, qb);
+      qb[1] = -qb[1]; qb[2] = -qb[2]; qb[3] = -qb[3];
+      So3Mul(qa, qb, q);
+      So3Log(q, e);
+      for (int k = 0; k < 3; ++k, ++n) {
+        J3 res = J3(A[3 * k]) * e[0] + J3(A[3 * k + 1]) * e[1] + J3(A[3 * k + 2]) * e[2];
+        r[n] = res.a;
+        for (int a = 0; a < 6; ++a) Ja[n][a] = a < 3 ? 0.0 : res.v[a - 3];
+      }
+    }
     return n;
+  }
+  // Sophus::SO3 (so3.hpp, a third-party dependency absent from /root/reference: restated from its published source, PARITY
+  // UNPINNED): exp to a unit quaternion (w, x, y, z) with the Taylor branch below |omega|^2 < 1e-20, the group product with its
+  // first-order renormalisation, log with the atan2 branch on the sign of w.
+  template <typename T> static void So3Exp(const T w[3], T q[4]) {
+    const T th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    T imag, real;
+    if (th2 < 1e-10 * 1e-10) {
+      const T th4 = th2 * th2;
+      imag = T(0.5) - T(1.0 / 48.0) * th2 + T(1.0 / 3840.0) * th4;
+      real = T(1.0) - T(1.0 / 8.0) * th2 + T(1.0 / 384.0) * th4;
+    } else {
+      const T th = sqrt_(th2), half = T(0.5) * th;
+      imag = sin_(half) / th;
+      real = cos_(half);
+    }
+    q[0] = real; q[1] = imag * w[0]; q[2] = imag * w[1]; q[3] = imag * w[2];
+  }
+  template <typename T> static void So3Mul(const T a[4], const T b[4], T q[4]) {
+    q[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+    q[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+    q[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+    q[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+    const T n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    if (n2 != 1.0) { const T sc = T(2.0) / (T(1.0) + n2); for (int k = 0; k < 4; ++k) q[k] = q[k] * sc; }
+  }
+  template <typename T> static void So3Log(const T q[4], T e[3]) {
+    const T n2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    T f;
+    if (n2 < 1e-10 * 1e-10) {
+      f = T(2.0) / q[0] - T(2.0 / 3.0) * n2 / (q[0] * q[0] * q[0]);
+    } else {
+      const T n = sqrt_(n2);
+      const T at = q[0] < 0.0 ? atan2_(-n, -q[0]) : atan2_(n, q[0]);
+      f = T(2.0) * at / n;
+    }
+    for (int k = 0; k < 3; ++k) e[k] = f * q[1 + k];
   }
 };
 

@@ -59,6 +59,7 @@ class ThbBaProblem(C.Structure):
         ("obs_sqrt_info", C.c_void_p),
         ("cam_has_position_prior", C.c_void_p), ("cam_position_prior", C.c_void_p), ("cam_position_prior_sqrt_info", C.c_void_p),
         ("cam_has_gravity_prior", C.c_void_p), ("cam_gravity_prior", C.c_void_p), ("cam_gravity_prior_sqrt_info", C.c_void_p),
+        ("cam_has_orientation_prior", C.c_void_p), ("cam_orientation_prior", C.c_void_p), ("cam_orientation_prior_sqrt_info", C.c_void_p),
     ]
 
 
@@ -318,6 +319,7 @@ class HostBaProblem:
         ("obs_cam", np.int32), ("obs_pt", np.int32), ("obs_xy", np.float64), ("obs_sqrt_info", np.float64),
         ("cam_has_position_prior", np.uint8), ("cam_position_prior", np.float64), ("cam_position_prior_sqrt_info", np.float64),
         ("cam_has_gravity_prior", np.uint8), ("cam_gravity_prior", np.float64), ("cam_gravity_prior_sqrt_info", np.float64),
+        ("cam_has_orientation_prior", np.uint8), ("cam_orientation_prior", np.float64), ("cam_orientation_prior_sqrt_info", np.float64),
     ]
 
     def __init__(self, arrays):

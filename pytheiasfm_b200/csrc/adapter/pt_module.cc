@@ -196,6 +196,9 @@ struct View {
   bool has_gravity_prior = false;                        // view.h: gravity direction in the camera frame (IMU)
   double gravity_prior[3] = {0, 0, -1};
   double gravity_prior_sqrt_info[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool has_orientation_prior = false;                    // view.h:95-99: angle-axis orientation prior
+  double orientation_prior[3] = {0, 0, 0};
+  double orientation_prior_sqrt_info[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   std::vector<TrackId> TrackIds() const { return track_order; }
   const Feature* GetFeature(TrackId t) const { auto it = features.find(t); return it == features.end() ? nullptr : &it->second; }
 };
@@ -290,7 +293,8 @@ struct Flat {
   std::vector<int32_t> cam_group, intr_model, obs_cam, obs_pt;
   std::vector<uint8_t> has_prior; std::vector<double> prior, prior_sqrt_info;   // position priors of the AddView cameras
   std::vector<uint8_t> has_gprior; std::vector<double> gprior, gprior_sqrt_info;  // gravity priors
-  bool any_prior = false, any_gprior = false;
+  std::vector<uint8_t> has_oprior; std::vector<double> oprior, oprior_sqrt_info;  // orientation priors
+  bool any_prior = false, any_gprior = false, any_oprior = false;
 };
 
 // SetSolverOptions, bundle_adjuster.cc:63-89
@@ -321,8 +325,8 @@ struct CovOut {
 BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vector<ViewId>& views, const std::vector<TrackId>& tracks,
                               Reconstruction* r, bool force_no_inner, CovOut* cov = nullptr) {
   if (o.use_inverse_depth_parametrization) throw std::runtime_error("use_inverse_depth_parametrization is not implemented");
-  if (o.use_orientation_priors || o.use_depth_priors || o.orthographic_camera)
-    throw std::runtime_error("orientation / depth prior residuals and orthographic cameras are not implemented (position and gravity priors are)");
+  if (o.use_depth_priors || o.orthographic_camera)
+    throw std::runtime_error("depth prior residuals and orthographic cameras are not implemented (position, gravity and orientation priors are)");
   Flat f;
   const std::unordered_set<ViewId> vset(views.begin(), views.end());
   const std::unordered_set<TrackId> tset(tracks.begin(), tracks.end());
@@ -347,6 +351,11 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     f.gprior.insert(f.gprior.end(), view.gravity_prior, view.gravity_prior + 3);
     f.gprior_sqrt_info.insert(f.gprior_sqrt_info.end(), view.gravity_prior_sqrt_info, view.gravity_prior_sqrt_info + 9);
     f.any_gprior |= gprior;
+    const bool oprior = free_cam && o.use_orientation_priors && view.has_orientation_prior;  // bundle_adjuster.cc:170-172
+    f.has_oprior.push_back(oprior ? 1 : 0);
+    f.oprior.insert(f.oprior.end(), view.orientation_prior, view.orientation_prior + 3);
+    f.oprior_sqrt_info.insert(f.oprior_sqrt_info.end(), view.orientation_prior_sqrt_info, view.orientation_prior_sqrt_info + 9);
+    f.any_oprior |= oprior;
     Intrinsics* in = view.camera.intr.get();
     if (!f.group_index.count(in)) {
       f.group_index[in] = (int)f.groups.size(); f.groups.push_back(in);
@@ -419,6 +428,7 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   p.obs_cam = f.obs_cam.data(); p.obs_pt = f.obs_pt.data(); p.obs_xy = f.obs_xy.data(); p.obs_sqrt_info = f.obs_si.data();
   if (f.any_prior) { p.cam_has_position_prior = f.has_prior.data(); p.cam_position_prior = f.prior.data(); p.cam_position_prior_sqrt_info = f.prior_sqrt_info.data(); }
   if (f.any_gprior) { p.cam_has_gravity_prior = f.has_gprior.data(); p.cam_gravity_prior = f.gprior.data(); p.cam_gravity_prior_sqrt_info = f.gprior_sqrt_info.data(); }
+  if (f.any_oprior) { p.cam_has_orientation_prior = f.has_oprior.data(); p.cam_orientation_prior = f.oprior.data(); p.cam_orientation_prior_sqrt_info = f.oprior_sqrt_info.data(); }
   const ThbBaOptions opt = MapOptions(o, force_no_inner);
   ThbBaSummary s;
   int rc;
@@ -906,6 +916,15 @@ PYBIND11_MODULE(_pt, m) {
         v.has_gravity_prior = true;
       })
       .def("HasGravityPrior", [](const View& v) { return v.has_gravity_prior; })
+      .def("SetOrientationPrior", [](View& v, const Vec& prior, const py::array_t<double, py::array::c_style | py::array::forcecast>& sqrt_information) {
+        CopyVec(prior, v.orientation_prior, 3, "orientation prior");
+        if (sqrt_information.ndim() != 2 || sqrt_information.shape(0) != 3 || sqrt_information.shape(1) != 3) throw std::invalid_argument("sqrt information must be 3 x 3");
+        std::copy_n(sqrt_information.data(), 9, v.orientation_prior_sqrt_info);
+        v.has_orientation_prior = true;
+      })
+      .def("HasOrientationPrior", [](const View& v) { return v.has_orientation_prior; })
+      .def("GetOrientationPrior", [](const View& v) { py::array_t<double> a(3); std::copy_n(v.orientation_prior, 3, a.mutable_data()); return a; })
+      .def("GetOrientationPriorSqrtInformation", [](const View& v) { py::array_t<double> a({3, 3}); std::copy_n(v.orientation_prior_sqrt_info, 9, a.mutable_data()); return a; })
       .def("GetGravityPrior", [](const View& v) { py::array_t<double> a(3); std::copy_n(v.gravity_prior, 3, a.mutable_data()); return a; })
       .def("GetGravityPriorSqrtInformation", [](const View& v) { py::array_t<double> a({3, 3}); std::copy_n(v.gravity_prior_sqrt_info, 9, a.mutable_data()); return a; })
       .def("GetPositionPrior", [](const View& v) { py::array_t<double> a(3); std::copy_n(v.position_prior, 3, a.mutable_data()); return a; })

@@ -66,8 +66,15 @@ __device__ __forceinline__ void rot_apply(const double w[3], double a, double b,
 //   position (position_error.h:44-80): r = A (prior - C),                 J = [-A | 0]
 //   gravity  (gravity_error.h:44-86):  r = A (R(w) (0,0,-1) - prior),     J = [0 | A d(R g)/dw], d(R g)/dw = -[q]x J_l(w) with q = R g
 //                                      (ceres' first-order branch: q = g, J_l = I), the chain eval_obs uses for the reprojection blocks
+//   orientation (orientation_error.h:44-80): r = A log(exp(w) exp(prior)^-1) (Sophus SO3: unit quaternions), J = [0 | A J_l^-1(e) J_l(w)]
+//                                      with e = the SO(3) logarithm: exp(w + d) = exp(J_l(w) d) exp(w) and log(exp(u) E) = e + J_l^-1(e) u
+// Packed per camera: PRIOR_STRIDE doubles = 12 per kind (kind 0 position, 1 gravity, 2 orientation); has_prior bit = 1 << kind.
+constexpr int PRIOR_STRIDE = 36, PRIOR_KINDS = 3;
 __device__ __forceinline__ void cam_prior_position(const double* pr, const double* rec, double r[3], double J[3][6]);
 __device__ __forceinline__ void cam_prior_gravity(const double* pr, const double* rec, double r[3], double J[3][6]);
+__device__ __forceinline__ void cam_prior_orientation(const double* pr, const double* rec, double r[3], double J[3][6]);
+// the prior block `kind` of a camera; `pr_cam` = the camera's PRIOR_STRIDE doubles
+__device__ __forceinline__ void cam_prior_eval(int kind, const double* pr_cam, const double* rec, double r[3], double J[3][6]);
 
 struct BaState {  // one set of parameter values (current x, or the candidate)
   double* cam;
@@ -411,6 +418,73 @@ __device__ __forceinline__ void cam_prior_gravity(const double* pr, const double
     J[k][0] = J[k][1] = J[k][2] = 0.0;
     J[k][3] = GM[0]; J[k][4] = GM[1]; J[k][5] = GM[2];
   }
+}
+
+// Sophus::SO3::exp (so3.hpp): unit quaternion (w, x, y, z) of a rotation vector, Taylor branch below |w|^2 < 1e-20
+__device__ __forceinline__ void so3_exp_quat(const double w[3], double q[4]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  if (th2 < 1e-10 * 1e-10) {
+    const double th4 = th2 * th2;
+    imag = 0.5 - (1.0 / 48.0) * th2 + (1.0 / 3840.0) * th4;
+    real = 1.0 - (1.0 / 8.0) * th2 + (1.0 / 384.0) * th4;
+  } else {
+    const double th = sqrt(th2), half = 0.5 * th;
+    imag = sin(half) / th;
+    real = cos(half);
+  }
+  q[0] = real; q[1] = imag * w[0]; q[2] = imag * w[1]; q[3] = imag * w[2];
+}
+__device__ __forceinline__ void cam_prior_orientation(const double* pr, const double* rec, double r[3], double J[3][6]) {
+  const double* w = rec + CD_W;
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double qa[4], qb[4];
+  so3_exp_quat(w, qa);
+  so3_exp_quat(pr + 9, qb);
+  qb[1] = -qb[1]; qb[2] = -qb[2]; qb[3] = -qb[3];  // inverse of a unit quaternion
+  double q[4] = {qa[0] * qb[0] - qa[1] * qb[1] - qa[2] * qb[2] - qa[3] * qb[3],
+                 qa[0] * qb[1] + qa[1] * qb[0] + qa[2] * qb[3] - qa[3] * qb[2],
+                 qa[0] * qb[2] - qa[1] * qb[3] + qa[2] * qb[0] + qa[3] * qb[1],
+                 qa[0] * qb[3] + qa[1] * qb[2] - qa[2] * qb[1] + qa[3] * qb[0]};
+  const double n2q = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  if (n2q != 1.0) { const double sc = 2.0 / (1.0 + n2q); q[0] *= sc; q[1] *= sc; q[2] *= sc; q[3] *= sc; }  // SO3::operator* renormalisation
+  // SO3::log: e = 2 atan(|v| / w) v / |v|
+  const double n2 = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  double f;
+  if (n2 < 1e-10 * 1e-10) {
+    f = 2.0 / q[0] - (2.0 / 3.0) * n2 / (q[0] * q[0] * q[0]);
+  } else {
+    const double n = sqrt(n2);
+    const double at = q[0] < 0.0 ? atan2(-n, -q[0]) : atan2(n, q[0]);
+    f = 2.0 * at / n;
+  }
+  const double e[3] = {f * q[1], f * q[2], f * q[3]};
+  const double ph2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
+  // J_l^-1(e) = I - [e]x / 2 + c [e]x^2, c = 1 / ph^2 - (1 + cos ph) / (2 ph sin ph) (series below 1e-2: the closed form cancels)
+  double c;
+  if (ph2 < 1e-4) {
+    c = 1.0 / 12.0 + ph2 / 720.0 + ph2 * ph2 / 30240.0;
+  } else {
+    const double ph = sqrt(ph2);
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    c = 1.0 / ph2 - (1.0 + cs) / (2.0 * ph * sn);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double g[3] = {pr[3 * k], pr[3 * k + 1], pr[3 * k + 2]};
+    r[k] = g[0] * e[0] + g[1] * e[1] + g[2] * e[2];
+    double t1[3], t2[3];
+    rot_apply(e, 0.5, c, ph2, g, t1);                       // (J_l^-1(e))^T A_k^T
+    rot_apply(w, -rec[CD_JA], rec[CD_JB], th2, t1, t2);     // J_l(w)^T ...
+    J[k][0] = J[k][1] = J[k][2] = 0.0;
+    J[k][3] = t2[0]; J[k][4] = t2[1]; J[k][5] = t2[2];
+  }
+}
+__device__ __forceinline__ void cam_prior_eval(int kind, const double* pr_cam, const double* rec, double r[3], double J[3][6]) {
+  if (kind == 0) cam_prior_position(pr_cam, rec, r, J);
+  else if (kind == 1) cam_prior_gravity(pr_cam + 12, rec, r, J);
+  else cam_prior_orientation(pr_cam + 24, rec, r, J);
 }
 
 template <int N>

@@ -401,15 +401,14 @@ __global__ void __launch_bounds__(128) k_cam_pass(BaConst K, BaState S, ObsSoA O
   __syncthreads();
   if (has_prior && has_prior[c] && threadIdx.x == 0) {
     // prior residual blocks of the camera (ba_device.cuh::cam_prior_*): J^T J, J^T r and the column norms of J diag(scale) join
-    // the camera's block. bit 0: position, bit 1: gravity; constant coordinates have no columns (their prior is a constant of the cost).
+    // the camera's block. bit 0: position, bit 1: gravity, bit 2: orientation; constant coordinates have no columns (their prior is a constant of the cost).
     const int cc = K.cam_const[c];
     double cscale[6];
     for (int a = 0; a < 6; ++a) cscale[a] = (cc & (a < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) ? 0.0 : cs[6 * c + a];
-    for (int kind = 0; kind < 2; ++kind) {
+    for (int kind = 0; kind < PRIOR_KINDS; ++kind) {
       if (!(has_prior[c] & (1 << kind))) continue;
       double r[3], J[3][6];
-      if (kind == 0) cam_prior_position(prior + 24 * (size_t)c, S.camd + (size_t)c * CAMD, r, J);
-      else cam_prior_gravity(prior + 24 * (size_t)c + 12, S.camd + (size_t)c * CAMD, r, J);
+      cam_prior_eval(kind, prior + PRIOR_STRIDE * (size_t)c, S.camd + (size_t)c * CAMD, r, J);
       for (int k = 0; k < 3; ++k) for (int a = 0; a < 6; ++a) J[k][a] *= cscale[a];
       for (int a = 0; a < 6; ++a) {
         const double b = J[0][a] * r[0] + J[1][a] * r[1] + J[2][a] * r[2];
@@ -1149,9 +1148,10 @@ __global__ void k_eval_ambient(BaConst K, BaState S, ObsSoA O, double* __restric
       for (int k = 0; k < KS; ++k) jintr[(2 * (size_t)i + a) * KS + k] = k < 9 ? ji[a * 9 + k] : 0.0;
 }
 
-__global__ void k_prior_flags(int nc, const uint8_t* __restrict__ has_pos, const uint8_t* __restrict__ has_grav, uint8_t* __restrict__ out) {
+__global__ void k_prior_flags(int nc, const uint8_t* __restrict__ has_pos, const uint8_t* __restrict__ has_grav, const uint8_t* __restrict__ has_ori,
+                              uint8_t* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < nc) out[c] = (uint8_t)((has_pos[c] ? 1 : 0) | (has_grav[c] ? 2 : 0));
+  if (c < nc) out[c] = (uint8_t)((has_pos[c] ? 1 : 0) | (has_grav[c] ? 2 : 0) | (has_ori[c] ? 4 : 0));
 }
 
 // camera priors: cost 0.5 |r|^2 of the prior blocks of every camera that is not fully constant, added to a cost slot
@@ -1162,8 +1162,11 @@ __global__ void k_prior_cost(int nc, const uint8_t* __restrict__ has_prior, cons
   double v = 0.0;
   if (c < nc && has_prior[c] && cam_const[c] != THB_CAM_CONST_ALL) {
     double r[3], J[3][6];
-    if (has_prior[c] & 1) { cam_prior_position(prior + 24 * (size_t)c, camd + (size_t)c * CAMD, r, J); v += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); }
-    if (has_prior[c] & 2) { cam_prior_gravity(prior + 24 * (size_t)c + 12, camd + (size_t)c * CAMD, r, J); v += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); }
+    for (int kind = 0; kind < PRIOR_KINDS; ++kind) {
+      if (!(has_prior[c] & (1 << kind))) continue;
+      cam_prior_eval(kind, prior + PRIOR_STRIDE * (size_t)c, camd + (size_t)c * CAMD, r, J);
+      v += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    }
   }
   v = block_sum(v, red);
   if (threadIdx.x == 0 && v != 0.0) atomicAdd(slot, v);
@@ -1179,11 +1182,10 @@ __global__ void k_prior_mcc(int nc, const uint8_t* __restrict__ has_prior, const
     const int cc = cam_const[c];
     double u[6];  // -(scaled step) per coordinate: J s = -sum_a J[k][a] scale_a y_a
     for (int a = 0; a < 6; ++a) u[a] = (cc & (a < 3 ? THB_CAM_CONST_POSITION : THB_CAM_CONST_ORIENTATION)) ? 0.0 : cs[6 * c + a] * yred[6 * c + a];
-    for (int kind = 0; kind < 2; ++kind) {
+    for (int kind = 0; kind < PRIOR_KINDS; ++kind) {
       if (!(has_prior[c] & (1 << kind))) continue;
       double r[3], J[3][6];
-      if (kind == 0) cam_prior_position(prior + 24 * (size_t)c, camd + (size_t)c * CAMD, r, J);
-      else cam_prior_gravity(prior + 24 * (size_t)c + 12, camd + (size_t)c * CAMD, r, J);
+      cam_prior_eval(kind, prior + PRIOR_STRIDE * (size_t)c, camd + (size_t)c * CAMD, r, J);
       for (int k = 0; k < 3; ++k) {
         double m = 0.0;
         for (int a = 0; a < 6; ++a) m -= J[k][a] * u[a];

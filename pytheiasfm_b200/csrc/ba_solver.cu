@@ -133,8 +133,8 @@ struct ThbBaSession {
   // owned device memory
   int *d_cam_group = nullptr, *d_intr_model = nullptr, *d_intr_slot = nullptr;
   uint8_t *d_cam_const = nullptr, *d_pt_const = nullptr;
-  uint8_t* d_has_prior = nullptr;  // camera priors: bit 0 position, bit 1 gravity (ThbBaProblem::cam_has_*_prior); nullptr when the problem has none
-  double* d_prior = nullptr;       // [nc][24]: position [sqrt information (9, row-major) | prior (3)], gravity [likewise]
+  uint8_t* d_has_prior = nullptr;  // camera priors: bit 0 position, bit 1 gravity, bit 2 orientation (ThbBaProblem::cam_has_*_prior); nullptr when the problem has none
+  double* d_prior = nullptr;       // [nc][PRIOR_STRIDE]: position [sqrt information (9, row-major) | prior (3)], gravity, orientation [likewise]
   uint16_t* d_intr_const = nullptr;
   int *d_op_cam = nullptr, *d_op_pt = nullptr, *d_oc_cam = nullptr, *d_oc_pt = nullptr;
   double2 *d_op_xy = nullptr, *d_op_si = nullptr, *d_oc_xy = nullptr, *d_oc_si = nullptr;
@@ -847,26 +847,27 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_group, P->cam_group, sizeof(int) * nc, kin, st));
   if (P->cam_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_cam_const, P->cam_const, nc, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_const, 0, std::max(nc, 1), st));
-  if ((P->cam_has_position_prior || P->cam_has_gravity_prior) && nc > 0) {  // camera priors, packed per camera (see d_prior)
+  if ((P->cam_has_position_prior || P->cam_has_gravity_prior || P->cam_has_orientation_prior) && nc > 0) {  // camera priors, packed per camera (see d_prior)
     if ((P->cam_has_position_prior && (!P->cam_position_prior || !P->cam_position_prior_sqrt_info)) ||
-        (P->cam_has_gravity_prior && (!P->cam_gravity_prior || !P->cam_gravity_prior_sqrt_info))) {
+        (P->cam_has_gravity_prior && (!P->cam_gravity_prior || !P->cam_gravity_prior_sqrt_info)) ||
+        (P->cam_has_orientation_prior && (!P->cam_orientation_prior || !P->cam_orientation_prior_sqrt_info))) {
       FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_has_*_prior without prior / sqrt information arrays");
     }
-    uint8_t *d_hp = nullptr, *d_hg = nullptr;
-    THB_TRY(M.Get(&s->d_has_prior, nc)); THB_TRY(M.Get(&s->d_prior, (size_t)nc * 24)); THB_TRY(M.Get(&d_hp, nc)); THB_TRY(M.Get(&d_hg, nc));
-    THB_TRY_CUDA(cudaMemsetAsync(s->d_prior, 0, sizeof(double) * 24 * nc, st));
-    THB_TRY_CUDA(cudaMemsetAsync(d_hp, 0, nc, st)); THB_TRY_CUDA(cudaMemsetAsync(d_hg, 0, nc, st));
-    if (P->cam_has_position_prior) {
-      THB_TRY_CUDA(cudaMemcpyAsync(d_hp, P->cam_has_position_prior, nc, kin, st));
-      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior, 24 * sizeof(double), P->cam_position_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
-      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 9, 24 * sizeof(double), P->cam_position_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
+    uint8_t* d_h[3] = {nullptr, nullptr, nullptr};
+    THB_TRY(M.Get(&s->d_has_prior, nc)); THB_TRY(M.Get(&s->d_prior, (size_t)nc * PRIOR_STRIDE));
+    THB_TRY_CUDA(cudaMemsetAsync(s->d_prior, 0, sizeof(double) * PRIOR_STRIDE * nc, st));
+    const uint8_t* has[3] = {P->cam_has_position_prior, P->cam_has_gravity_prior, P->cam_has_orientation_prior};
+    const double* info[3] = {P->cam_position_prior_sqrt_info, P->cam_gravity_prior_sqrt_info, P->cam_orientation_prior_sqrt_info};
+    const double* prior[3] = {P->cam_position_prior, P->cam_gravity_prior, P->cam_orientation_prior};
+    for (int kind = 0; kind < PRIOR_KINDS; ++kind) {
+      THB_TRY(M.Get(&d_h[kind], nc));
+      THB_TRY_CUDA(cudaMemsetAsync(d_h[kind], 0, nc, st));
+      if (!has[kind]) continue;
+      THB_TRY_CUDA(cudaMemcpyAsync(d_h[kind], has[kind], nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 12 * kind, PRIOR_STRIDE * sizeof(double), info[kind], 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
+      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 12 * kind + 9, PRIOR_STRIDE * sizeof(double), prior[kind], 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
     }
-    if (P->cam_has_gravity_prior) {
-      THB_TRY_CUDA(cudaMemcpyAsync(d_hg, P->cam_has_gravity_prior, nc, kin, st));
-      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 12, 24 * sizeof(double), P->cam_gravity_prior_sqrt_info, 9 * sizeof(double), 9 * sizeof(double), nc, kin, st));
-      THB_TRY_CUDA(cudaMemcpy2DAsync(s->d_prior + 21, 24 * sizeof(double), P->cam_gravity_prior, 3 * sizeof(double), 3 * sizeof(double), nc, kin, st));
-    }
-    k_prior_flags<<<cdiv(nc, 256), 256, 0, st>>>(nc, d_hp, d_hg, s->d_has_prior);
+    k_prior_flags<<<cdiv(nc, 256), 256, 0, st>>>(nc, d_h[0], d_h[1], d_h[2], s->d_has_prior);
   }
   if (P->pt_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, P->pt_const, np, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_const, 0, std::max(np, 1), st));

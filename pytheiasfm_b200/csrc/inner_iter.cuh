@@ -73,10 +73,10 @@ __device__ __forceinline__ void inner_cam_pass(const BaConst& K, const BaState& 
   }
   __syncthreads();
   if (prior && threadIdx.x == 0) {  // the camera's prior blocks are residual blocks of this parameter block as well
-    for (int kind = 0; kind < 2; ++kind) {
+    for (int kind = 0; kind < PRIOR_KINDS; ++kind) {
       if (!(prior_kinds & (1 << kind))) continue;
       double r[3], J[3][6];
-      if (kind == 0) cam_prior_position(prior, rec, r, J); else cam_prior_gravity(prior + 12, rec, r, J);
+      cam_prior_eval(kind, prior, rec, r, J);
       tot[27] += 0.5 * (r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
       if (WANT_J) {
         for (int k = 0; k < 3; ++k) for (int a = 0; a < 6; ++a) J[k][a] *= scale[a];
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(IC_THREADS) k_inner_cam(BaConst K, BaState S, 
   if (t == 0) cam_derive_record(x, rec);
   __syncthreads();
   const int prior_kinds = has_prior ? has_prior[c] : 0;
-  const double* prior = prior_kinds ? prior_all + 24 * (size_t)c : nullptr;
+  const double* prior = prior_kinds ? prior_all + PRIOR_STRIDE * (size_t)c : nullptr;
   inner_cam_pass<PD, true>(K, S, O, c, q0, q1, rec, scale, red, tot, prior, prior_kinds);  // column norms of the unscaled Jacobian
   if (tot[28] > 0.0) return;  // IterationZero failed: the block stays as it is
   if (t == 0) {

@@ -175,6 +175,35 @@ def test_position_priors_through_the_adapter(gen):
         np.testing.assert_allclose(gen.recon.View(v).Camera().GetPosition(), before[v] + shift, atol=2e-2)
 
 
+def test_orientation_priors_through_the_adapter(gen):
+    """View.SetOrientationPrior + BundleAdjustmentOptions.use_orientation_priors (orientation_error.h:44-80): strong priors on
+    the views of BundleAdjustViews (tracks constant) hold the orientations at the priors although the reprojection errors pull
+    them back; without the option the priors are ignored."""
+    from scipy.spatial.transform import Rotation
+    vids = gen.recon.ViewIds()
+    rng = np.random.default_rng(3)
+    prior = {}
+    for v in vids:
+        view = gen.recon.View(v)
+        assert not view.HasOrientationPrior()
+        prior[v] = (Rotation.from_rotvec(0.01 * rng.normal(size=3)) * Rotation.from_rotvec(view.Camera().GetOrientationAsAngleAxis())).as_rotvec()
+        view.SetOrientationPrior(prior[v], 1e6 * np.eye(3))
+        assert view.HasOrientationPrior()
+        np.testing.assert_allclose(view.GetOrientationPrior(), prior[v])
+    before = {v: gen.recon.View(v).Camera().GetOrientationAsAngleAxis().copy() for v in vids}
+    opts = pt.sfm.BundleAdjustmentOptions()
+    assert pt.sfm.BundleAdjustViews(gen.recon, opts, vids).success
+    assert max(np.abs(gen.recon.View(v).Camera().GetOrientationAsAngleAxis() - before[v]).max() for v in vids) < 1e-3   # ignored
+    opts.use_orientation_priors = True
+    assert pt.sfm.BundleAdjustViews(gen.recon, opts, vids).success
+    for v in vids:
+        err = (Rotation.from_rotvec(gen.recon.View(v).Camera().GetOrientationAsAngleAxis()) * Rotation.from_rotvec(prior[v]).inv()).magnitude()
+        assert err < 1e-4
+    opts.use_depth_priors = True
+    with pytest.raises(Exception):
+        pt.sfm.BundleAdjustViews(gen.recon, opts, vids)
+
+
 def test_BundleAdjustPartialViewsConstant(gen):
     """bundle_adjustment.cc:146-186: the constant views keep their pose, the variable views and all tracks are refined."""
     vids = gen.recon.ViewIds()

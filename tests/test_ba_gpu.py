@@ -600,6 +600,49 @@ def test_gravity_priors_match_oracle(lib, oracle, case):
     assert g["initial_cost"] > plain["initial_cost"] and g["final_cost"] > plain["final_cost"]
 
 
+def _with_orientation_priors(prob, gt, weight, tilt=0.0, every=1, seed=0):
+    rng = np.random.default_rng(seed)
+    a = dict(prob.a)
+    nc = prob.num_cameras
+    has = np.zeros(nc, np.uint8); has[::every] = 1
+    a["cam_has_orientation_prior"] = has
+    a["cam_orientation_prior"] = gt["cam_ext"][:, 3:] + tilt * rng.normal(size=(nc, 3))
+    a["cam_orientation_prior_sqrt_info"] = np.stack([(weight * (np.eye(3) + 0.1 * rng.normal(size=(3, 3)))).reshape(9) for _ in range(nc)])
+    return capi.HostBaProblem(a)
+
+
+@pytest.mark.parametrize("case", ["orientation", "orientation_inner_all_priors", "orientation_const", "orientation_pcg", "orientation_covariance"])
+def test_orientation_priors_match_oracle(lib, oracle, case):
+    """BundleAdjustmentOptions::use_orientation_priors (bundle_adjuster.cc:170-172, orientation_error.h:44-80): residual
+    sqrt_info * log(exp(w) exp(prior)^-1); on the device through unit quaternions with the analytic Jacobian
+    A J_l^-1(e) J_l(w), in the oracle through Jets over the restated Sophus code. Alone, with all three prior kinds and inner
+    iterations, next to constant orientations, with the iterative solver, and in the covariance."""
+    prob, gt = synthetic.config_c1()
+    o = capi.default_options(lib)
+    if case == "orientation_const":
+        prob.a["cam_const"][1::3] = capi.CAM_CONST_ORIENTATION
+    pp = _with_orientation_priors(prob, gt, weight=60.0, tilt=0.03, every=2 if case == "orientation_const" else 1, seed=16)
+    if case == "orientation_inner_all_priors":
+        o.use_inner_iterations = 1
+        pp = _with_position_priors(pp, gt, bias=0.2, weight=20.0, every=3, seed=7)
+        pp = _with_gravity_priors(pp, gt, weight=100.0, tilt=0.02, every=2, seed=8)
+    if case == "orientation_pcg":
+        o.linear_solver = capi.SOLVER_SCHUR_PCG
+    if case == "orientation_covariance":
+        pp.a["pt_const"][:] = 1
+        pp = capi.HostBaProblem(pp.a)
+        rc, cc, co, pc, po = _gpu_covariance(lib, pp, o)
+        orc, occ, oco, opc, opo = oracle.ba_covariance(pp, o)
+        assert rc == orc == 0
+        np.testing.assert_array_equal(co, oco)
+        np.testing.assert_allclose(cc, occ, rtol=1e-8, atol=1e-18)
+        return
+    g, orc, pg, po = _compare_solves(lib, oracle, pp, o)
+    np.testing.assert_allclose(pg.a["cam_ext"], po.a["cam_ext"], rtol=0, atol=1e-6)
+    plain = gpu_solve(lib, capi.HostBaProblem({k: v for k, v in pp.a.items() if "prior" not in k}), o)
+    assert g["initial_cost"] > plain["initial_cost"] and g["final_cost"] > plain["final_cost"]
+
+
 @pytest.mark.parametrize("case", ["c1", "inner", "pcg", "const_position_huber", "views_covariance"])
 def test_position_priors_match_oracle(lib, oracle, case):
     """BundleAdjustmentOptions::use_position_priors (bundle_adjuster.cc:160-163, position_error.h:44-80): 3 residuals

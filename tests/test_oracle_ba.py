@@ -266,3 +266,37 @@ def test_position_priors_fix_the_gauge(oracle):
     prior_cost = 0.5 * np.sum((50.0 * (a["cam_position_prior"] - prob.a["cam_ext"][:, :3])) ** 2)
     np.testing.assert_allclose(c1["final_cost"] - c0["final_cost"], prior_cost, rtol=1e-9)
     assert c1["num_iterations"] == c0["num_iterations"]
+
+
+def test_orientation_priors_against_scipy(oracle):
+    """use_orientation_priors (bundle_adjuster.cc:170-172, orientation_error.h:44-80): residual sqrt_info * log(exp(w) exp(prior)^-1).
+    The restated Sophus exp / product / log gives the rotation vector scipy computes for R(w) R(prior)^T (initial cost difference
+    to the problem without priors), and strong priors pull the orientations onto them."""
+    from scipy.spatial.transform import Rotation
+    prob, gt = synthetic.config_c1()
+    rng = np.random.default_rng(12)
+    nc = prob.num_cameras
+    a = dict(prob.a)
+    prior = gt["cam_ext"][:, 3:] + 0.03 * rng.normal(size=(nc, 3))
+    info = np.stack([(40.0 * (np.eye(3) + 0.1 * rng.normal(size=(3, 3)))).reshape(9) for _ in range(nc)])
+    a["cam_has_orientation_prior"] = np.ones(nc, np.uint8)
+    a["cam_orientation_prior"] = prior
+    a["cam_orientation_prior_sqrt_info"] = info
+    o = oracle.default_options()
+    base = oracle.ba_solve(prob.copy(), o)
+    pp = capi.HostBaProblem(a)
+    w0 = pp.a["cam_ext"][:, 3:].copy()
+    s = oracle.ba_solve(pp, o)
+    assert s["rc"] == 0 and s["success"] == 1
+    e = (Rotation.from_rotvec(w0) * Rotation.from_rotvec(prior).inv()).as_rotvec()
+    expected = 0.5 * sum(np.sum((info[c].reshape(3, 3) @ e[c]) ** 2) for c in range(nc))
+    np.testing.assert_allclose(s["initial_cost"] - base["initial_cost"], expected, rtol=1e-9)
+    assert np.all(np.diff(s["iter_cost"]) <= 0)
+    a["cam_orientation_prior_sqrt_info"] = info * 1e4          # priors that outweigh the reprojection errors
+    strong = capi.HostBaProblem(a)
+    s2 = oracle.ba_solve(strong, o)
+    assert s2["rc"] == 0 and s2["success"] == 1
+    after = (Rotation.from_rotvec(strong.a["cam_ext"][:, 3:]) * Rotation.from_rotvec(prior).inv()).magnitude()
+    before = (Rotation.from_rotvec(w0) * Rotation.from_rotvec(prior).inv()).magnitude()
+    assert after.max() < 0.05 * before.max()
+
