@@ -794,6 +794,12 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
 #define THB_TRY(expr) do { rc = (expr); if (rc != THB_OK) { FreeSession(s); return rc; } } while (0)
 #define THB_TRY_CUDA(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { SetLastError(std::string(#expr) + ": " + cudaGetErrorString(_e)); FreeSession(s); return THB_E_CUDA; } } while (0)
 
+  // THB_SETUP_PROF=1: host-side time stamps of the setup phases (debugging aid, stderr)
+  const bool setup_prof = getenv("THB_SETUP_PROF") != nullptr;
+  std::vector<std::pair<const char*, double>> marks;
+  auto mark = [&](const char* name) {
+    if (setup_prof) marks.emplace_back(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s->t_create).count());
+  };
   // ---- device memory (stream-ordered, pooled) ----
   ConfigurePoolOnce();
   s->arena.st = s->st;
@@ -872,6 +878,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   if (P->pt_const) THB_TRY_CUDA(cudaMemcpyAsync(s->d_pt_const, P->pt_const, np, kin, st));
   else THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_const, 0, std::max(np, 1), st));
 
+  mark("alloc + copies enqueued");
   // ---- structure: validation, constness, the two observation orders (histogram + scan + stable radix sort) ----
   THB_TRY_CUDA(cudaMemsetAsync(s->d_pt_start, 0, sizeof(int) * (np + 1), st));
   THB_TRY_CUDA(cudaMemsetAsync(s->d_cam_start, 0, sizeof(int) * (nc + 1), st));
@@ -888,6 +895,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   for (int g = 0; g < ng; ++g)
     if (num_intrinsics(h_intr_model[g]) < 0) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "camera model not on the hot path"); }
   THB_TRY_CUDA(cudaStreamSynchronize(st));
+  mark("sync 1 (counts, validation)");
   if (h_setup[SF_BAD_GROUP]) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "cam_group out of range"); }
   if (h_setup[SF_BAD_INDEX]) { FreeSession(s); THB_FAIL(THB_E_INVALID_ARGUMENT, "observation index out of range"); }
   THB_TRY(GroupByKey(raw_pt, no, np, s->d_pt_start, d_perm, st));
@@ -900,6 +908,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   THB_TRY_CUDA(cudaMemcpyAsync(used.data(), d_used, sizeof(int) * ng, cudaMemcpyDeviceToHost, st));
   THB_TRY_CUDA(cudaMemcpyAsync(h_setup, d_setup, sizeof(int) * SF_COUNT, cudaMemcpyDeviceToHost, st));
   THB_TRY_CUDA(cudaStreamSynchronize(st));
+  mark("sync 2 (sorts, gathers, pt_start D2H)");
   s->model = ng > 0 ? h_intr_model[0] : THB_MODEL_PINHOLE;
   for (int g = 1; g < ng; ++g) if (h_intr_model[g] != s->model) s->model = -1;
   // variable intrinsics groups: observed by at least one residual and with at least one free coordinate
@@ -936,7 +945,9 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
     THB_TRY(M.Get(&s->d_ji, (size_t)no * 2 * NI));
     THB_TRY(M.Get(&s->d_zt, (size_t)np * s->nvg * 2 * NI * s->PD));
   }
+  mark("chunks on host");
   THB_TRY(s->chol.Init(std::max(1, s->n_red), st));
+  mark("chol.Init");
   s->use_pcg = O->linear_solver == THB_SOLVER_SCHUR_PCG;
   if (s->use_pcg) {  // SCHUR_JACOBI: one diagonal block per camera and per shared intrinsics block
     std::vector<int2> blocks;
@@ -975,6 +986,7 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   // they would still contribute zero Jacobian columns here, so only the cost bookkeeping differs.
   THB_TRY_CUDA(cudaMemcpyAsync(h_setup, d_setup, sizeof(int) * SF_COUNT, cudaMemcpyDeviceToHost, st));
   THB_TRY_CUDA(cudaStreamSynchronize(st));  // also: the host vectors above may now go out of scope
+  mark("sync 3 (slots)");
   if (h_setup[SF_HAS_FIXED] && s->any_variable) { FreeSession(s); THB_FAIL(THB_E_UNSUPPORTED, "observations whose camera, intrinsics and point are all constant are not supported in a problem with free blocks"); }
   s->Op = ObsSoA{s->d_op_cam, s->d_op_pt, s->d_op_xy, s->d_op_si};
   s->Oc = ObsSoA{s->d_oc_cam, s->d_oc_pt, s->d_oc_xy, s->d_oc_si};
@@ -1033,6 +1045,12 @@ int ValidateAndCreate(const ThbBaProblem* P, const ThbBaOptions* O, void* stream
   s->sum.initial_cost = s->x_cost + s->fixed_cost;
   s->step_is_successful = true; s->iteration = 0;
   LogIter(s);
+  mark("iteration zero");
+  if (setup_prof) {
+    fprintf(stderr, "THB_SETUP_PROF");
+    for (auto& m : marks) fprintf(stderr, " | %s %.3f", m.first, m.second);
+    fprintf(stderr, "\n");
+  }
   s->t_solve_start = std::chrono::steady_clock::now();
   s->sum.setup_time_in_seconds = std::chrono::duration<double>(s->t_solve_start - s->t_create).count();
   *out = s;

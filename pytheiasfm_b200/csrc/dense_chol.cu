@@ -1405,6 +1405,7 @@ int DenseChol::Init(int n_, cudaStream_t st) {
     if (per_sm < 1) THB_FAIL(THB_E_CUDA, "chol_ll_kernel does not fit an SM");
     ll_grid = std::min(per_sm * num_sms, h_cols[nblk]);
   }
+  if (!legacy) return THB_OK;  // the second stream and the event rings belong to the r01 schedule only
   // the latency-bound diag/panel chain is the critical path: its CTAs must win free SM slots against the trailing update
   int prio_lo = 0, prio_hi = 0;
   THB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
