@@ -17,6 +17,10 @@ namespace thb {
 namespace {
 
 constexpr int TV_THREADS = 256;
+#ifndef THB_TV_CTAS
+#define THB_TV_CTAS 1
+#endif
+constexpr int TV_CTAS = THB_TV_CTAS;  // resident verification CTAs per SM; 2 (128 registers, 1.3 KB stack) measured slower: 22.8 vs 20 ms on the C5 batch
 
 // ComputeResolutionScaledThreshold (reconstruction_estimator_utils.cc:97-110)
 __device__ __host__ inline double resolution_scaled_threshold(double threshold_pixels, int w, int h) {
@@ -154,7 +158,7 @@ struct TvShared {
 
 // d_res / d_mask: result and inlier flags of the relative-pose RANSAC on the normalised correspondences. pts0 / pts1: two
 // point buffers [total * 4]; pscale [total * 4]; tri [total] (1 = triangulated match).
-__global__ void __launch_bounds__(TV_THREADS) k_tv_verify(const long long* __restrict__ off_all, const double* __restrict__ px_all,
+__global__ void __launch_bounds__(TV_THREADS, TV_CTAS) k_tv_verify(const long long* __restrict__ off_all, const double* __restrict__ px_all,
                                                           const ThbViewIntrinsics* __restrict__ i1, const ThbViewIntrinsics* __restrict__ i2,
                                                           ThbTwoViewOptions O, const ThbRelPoseResult* __restrict__ res_all,
                                                           const uint8_t* __restrict__ inl_all, const ThbRelPoseResult* __restrict__ hom_all,
