@@ -25,6 +25,10 @@
 #include <stdexcept>
 #include <string>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <thread>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -286,6 +290,7 @@ struct BundleAdjustmentSummary {  // bundle_adjustment.h:170-178
 
 struct Flat {
   std::vector<ViewId> view_ids; std::unordered_map<ViewId, int> view_index;
+  std::vector<const Track*> track_ptrs;  // the Track objects behind track_ids (scatter without hash lookups)
   std::vector<TrackId> track_ids; std::unordered_map<TrackId, int> track_index;
   std::vector<Intrinsics*> groups; std::unordered_map<Intrinsics*, int> group_index;
   std::vector<double> cam_ext, intr, pts, obs_xy, obs_si;
@@ -328,8 +333,11 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   if (o.use_depth_priors || o.orthographic_camera)
     throw std::runtime_error("depth prior residuals and orthographic cameras are not implemented (position, gravity and orientation priors are)");
   Flat f;
+  const bool prof = getenv("THB_ADAPTER_PROF") != nullptr;   // host time stamps of gather / solve / scatter on stderr
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_gather = 0.0, t_solve = 0.0;
   const std::unordered_set<ViewId> vset(views.begin(), views.end());
-  const std::unordered_set<TrackId> tset(tracks.begin(), tracks.end());
   auto add_view = [&](ViewId v, bool free_cam) {
     auto it = f.view_index.find(v);
     if (it != f.view_index.end()) return it->second;
@@ -374,7 +382,7 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
     if (tr.flat_epoch == epoch) { if (free_pt) f.pt_const[tr.flat_index] = 0; return tr.flat_index; }
     const int idx = (int)f.track_ids.size();
     tr.flat_epoch = epoch; tr.flat_index = idx;
-    f.track_ids.push_back(t);
+    f.track_ids.push_back(t); f.track_ptrs.push_back(&tr);
     f.pts.insert(f.pts.end(), tr.point, tr.point + 4);
     f.pt_const.push_back(free_pt ? 0 : 1);
     return idx;
@@ -392,15 +400,59 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   }
   bool all_views_optimised = vset.size() >= r->views.size();
   if (all_views_optimised) for (const auto& kv : r->views) if (!vset.count(kv.first)) { all_views_optimised = false; break; }
-  for (ViewId v : views) {                                                 // AddView
-    auto vi = r->views.find(v);
+  // AddView. The two hash lookups per observation (track, feature) are the cost of this function (1M observations: ~120 ms on one
+  // thread), and they are read-only: host threads resolve them view by view into pointer lists, the index assignment - which has to
+  // see the observations in view order - then only walks those lists.
+  struct Resolved { View* view = nullptr; std::vector<const Track*> tracks; std::vector<double> xysi; };  // per observation: x, y, 1/sigma_x, 1/sigma_y
+  std::vector<Resolved> resolved(views.size());
+  for (size_t i = 0; i < views.size(); ++i) {
+    auto vi = r->views.find(views[i]);
     if (vi == r->views.end()) throw std::invalid_argument("unknown view id");   // the reference CHECK-aborts (bundle_adjuster.cc:117)
-    if (!vi->second.estimated) continue;
-    const int ci = add_view(v, true);
-    for (TrackId t : vi->second.track_order) {
-      const Track& tr = r->tracks.at(t);
+    resolved[i].view = &vi->second;
+  }
+  {
+    std::atomic<size_t> next{0};
+    std::atomic<bool> missing{false};
+    auto work = [&]() {
+      for (size_t i = next++; i < views.size(); i = next++) {
+        Resolved& rv = resolved[i];
+        if (!rv.view->estimated) continue;
+        const auto& order = rv.view->track_order;
+        rv.tracks.resize(order.size()); rv.xysi.resize(4 * order.size());
+        for (size_t k = 0; k < order.size(); ++k) {
+          auto ti = r->tracks.find(order[k]);
+          auto fi = rv.view->features.find(order[k]);
+          if (ti == r->tracks.end() || fi == rv.view->features.end()) { missing = true; return; }
+          rv.tracks[k] = &ti->second;
+          const Feature& feat = fi->second;
+          double* q = &rv.xysi[4 * k];
+          q[0] = feat.point[0]; q[1] = feat.point[1];
+          q[2] = 1.0 / std::sqrt(feat.cov[0]); q[3] = 1.0 / std::sqrt(feat.cov[3]);   // reprojection_error.h:96-103
+        }
+      }
+    };
+    size_t total = 0;
+    for (const Resolved& rv : resolved) total += rv.view->track_order.size();
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = total < 50000 ? 1 : std::min<size_t>({(size_t)(hw ? hw : 1), (size_t)16, views.size()});
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < nthreads; ++k) pool.emplace_back(work);
+    work();
+    for (std::thread& th : pool) th.join();
+    if (missing) throw std::out_of_range("a view lists a track that the reconstruction or the view's features do not hold");
+  }
+  for (size_t i = 0; i < views.size(); ++i) {
+    const Resolved& rv = resolved[i];
+    if (!rv.view->estimated) continue;
+    const int ci = add_view(views[i], true);
+    const auto& order = rv.view->track_order;
+    for (size_t k = 0; k < order.size(); ++k) {
+      const Track& tr = *rv.tracks[k];
       if (!tr.estimated) continue;
-      add_obs(ci, add_track(t, tr, false), vi->second.features.at(t));
+      const double* q = &rv.xysi[4 * k];
+      f.obs_cam.push_back(ci); f.obs_pt.push_back(add_track(order[k], tr, false));
+      f.obs_xy.push_back(q[0]); f.obs_xy.push_back(q[1]);
+      f.obs_si.push_back(q[2]); f.obs_si.push_back(q[3]);
     }
   }
   for (TrackId t : tracks) {                                               // AddTrack
@@ -432,10 +484,12 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   const ThbBaOptions opt = MapOptions(o, force_no_inner);
   ThbBaSummary s;
   int rc;
+  t_gather = since();
   {
     py::gil_scoped_release nogil;
     rc = thb_ba_solve(&p, &opt, &s, nullptr);
   }
+  t_solve = since();
   if (rc == THB_E_NUMERICAL) return out;                                   // ceres FAILURE -> summary.success = false
   Check(rc);
   out.success = s.success != 0;
@@ -443,8 +497,9 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   out.setup_time_in_seconds = s.setup_time_in_seconds; out.solve_time_in_seconds = s.solve_time_in_seconds;
   if (!out.success) return out;
   for (size_t i = 0; i < f.view_ids.size(); ++i) std::copy_n(&f.cam_ext[6 * i], 6, r->views.at(f.view_ids[i]).camera.ext);
-  for (size_t i = 0; i < f.track_ids.size(); ++i) std::copy_n(&f.pts[4 * i], 4, r->tracks.at(f.track_ids[i]).point);
+  for (size_t i = 0; i < f.track_ids.size(); ++i) std::copy_n(&f.pts[4 * i], 4, const_cast<Track*>(f.track_ptrs[i])->point);
   for (size_t g = 0; g < f.groups.size(); ++g) std::copy_n(&f.intr[THB_INTR_STRIDE * g], THB_INTR_STRIDE, f.groups[g]->params);
+  if (prof) fprintf(stderr, "THB_ADAPTER_PROF gather %.2f ms, thb_ba_solve %.2f ms, scatter %.2f ms (%d observations)\n", t_gather, t_solve - t_gather, since() - t_solve, p.num_observations);
   if (cov) {  // ceres::Covariance at the refined parameters (p still points at them)
     std::vector<double> cc(36 * f.view_ids.size()), pc(9 * f.track_ids.size());
     std::vector<uint8_t> cok(f.view_ids.size()), pok(f.track_ids.size());
@@ -470,15 +525,25 @@ BundleAdjustmentSummary RunBa(const BundleAdjustmentOptions& o, const std::vecto
   return out;
 }
 
-// UpdateInverseDepth (bundle_adjustment.cc:69-83)
+// UpdateInverseDepth (bundle_adjustment.cc:69-83); tracks are independent: host threads above 50 000 of them
 void UpdateInverseDepth(const std::vector<TrackId>& ids, Reconstruction* r) {
-  for (TrackId t : ids) {
-    auto it = r->tracks.find(t);
-    if (it == r->tracks.end() || !it->second.estimated) continue;
-    auto vi = r->views.find(it->second.reference_view);
-    if (vi == r->views.end()) continue;
-    it->second.inverse_depth = 1.0 / vi->second.camera.ProjectRaw(it->second.point, nullptr);
-  }
+  auto range = [&](size_t i0, size_t i1) {
+    for (size_t i = i0; i < i1; ++i) {
+      auto it = r->tracks.find(ids[i]);
+      if (it == r->tracks.end() || !it->second.estimated) continue;
+      auto vi = r->views.find(it->second.reference_view);
+      if (vi == r->views.end()) continue;
+      it->second.inverse_depth = 1.0 / vi->second.camera.ProjectRaw(it->second.point, nullptr);
+    }
+  };
+  const unsigned hw = std::thread::hardware_concurrency();
+  const size_t nthreads = ids.size() < 50000 ? 1 : std::min<size_t>((size_t)(hw ? hw : 1), (size_t)16);
+  if (nthreads <= 1) { range(0, ids.size()); return; }
+  std::vector<std::thread> pool;
+  const size_t per = (ids.size() + nthreads - 1) / nthreads;
+  for (size_t k = 1; k < nthreads; ++k) pool.emplace_back(range, std::min(ids.size(), k * per), std::min(ids.size(), (k + 1) * per));
+  range(0, std::min(ids.size(), per));
+  for (std::thread& th : pool) th.join();
 }
 std::vector<TrackId> TracksOfViews(const std::vector<ViewId>& vs, Reconstruction* r) {
   std::vector<TrackId> out;
