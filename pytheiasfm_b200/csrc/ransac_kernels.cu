@@ -1387,6 +1387,7 @@ __global__ void __launch_bounds__(128) k_rs_init(const ThbRansacParams P, int pa
     S.stat_samples = 0; S.stat_models = 0; S.stat_data = 0;
     memset(&S.best, 0, sizeof(Model));
     if (P.ransac_type == 1) prosac_init(&S.prosac, n, Est::S);
+    atomicMax(&counters[2], n);
     if (S.it0 >= S.max_iterations) S.num_iterations = S.it0;  // finished before the first round
     else active[atomicAdd(&counters[0], 1)] = slot;
   }
@@ -1451,29 +1452,41 @@ __device__ __forceinline__ int mt_uniform_int_strided(uint32_t* mt, int& idx, in
   }
   return lo + (int)(product >> 32);
 }
-template <class Est>
-__global__ void __launch_bounds__(32) k_rs_draw_staged(int na, const int* __restrict__ active, PairState* __restrict__ states,
-                                                       int* __restrict__ idx_ws, int* __restrict__ samples) {
-  __shared__ uint32_t st[624 * MT_STRIDE];
-  const int lane = threadIdx.x, a0 = blockIdx.x * DRAW_PAIRS;
+// STAGE_IDX: the pairs' index permutations (RandomSampler's persistent shuffle, n ints per pair) are staged as well when 16 of them
+// fit next to the generators; the drawing lane then writes its swaps through to global memory (fire and forget) and nothing is
+// copied back but the generator states. Otherwise the permutation entries are read from global memory (two L2 trips per draw).
+template <class Est, bool STAGE_IDX>
+__global__ void __launch_bounds__(256) k_rs_draw_staged(int na, const int* __restrict__ active, PairState* __restrict__ states,
+                                                        int* __restrict__ idx_ws, int* __restrict__ samples, int idx_stride) {
+  extern __shared__ uint32_t draw_smem[];
+  uint32_t* st = draw_smem;                                            // [624][MT_STRIDE]
+  int* sx = reinterpret_cast<int*>(draw_smem + 624 * MT_STRIDE);       // [DRAW_PAIRS][idx_stride]
+  const int t = threadIdx.x, a0 = blockIdx.x * DRAW_PAIRS;
   const int cnt = min(DRAW_PAIRS, na - a0);
   for (int p = 0; p < cnt; ++p) {
-    const uint32_t* src = states[active[a0 + p]].rng.mt;
-    for (int i = lane; i < 624; i += 32) st[i * MT_STRIDE + p] = src[i];
+    const PairState& Sp = states[active[a0 + p]];
+    for (int i = t; i < 624; i += blockDim.x) st[i * MT_STRIDE + p] = Sp.rng.mt[i];
+    if (STAGE_IDX) {
+      const int* src = idx_ws + Sp.off;
+      for (int i = t; i < Sp.n; i += blockDim.x) sx[p * idx_stride + i] = src[i];
+    }
   }
-  __syncwarp();
-  if (lane < cnt) {
-    const int slot = active[a0 + lane];
+  __syncthreads();
+  if (t < cnt) {
+    const int slot = active[a0 + t];
     PairState& S = states[slot];
     const int n = S.n, nit = min(BI, S.max_iterations - S.it0);
     int* sidx = idx_ws + S.off;
+    int* sl = sx + t * idx_stride;
     int* out = samples + (size_t)slot * BI * 5;
-    uint32_t* mt = st + lane;
+    uint32_t* mt = st + t;
     int idx = S.rng.idx;
     for (int b = 0; b < nit; ++b)
       for (int i = 0; i < Est::S; ++i) {
         const int j = mt_uniform_int_strided(mt, idx, i, n - 1);
-        const int u = sidx[i], c = sidx[j];
+        int u, c;
+        if (STAGE_IDX) { u = sl[i]; c = sl[j]; sl[i] = c; sl[j] = u; }
+        else { u = sidx[i]; c = sidx[j]; }
         sidx[i] = c; sidx[j] = u;
         out[b * 5 + i] = c;
       }
@@ -1481,10 +1494,10 @@ __global__ void __launch_bounds__(32) k_rs_draw_staged(int na, const int* __rest
     S.nit = nit;
     S.stat_samples += nit;
   }
-  __syncwarp();
+  __syncthreads();
   for (int p = 0; p < cnt; ++p) {
     uint32_t* dst = states[active[a0 + p]].rng.mt;
-    for (int i = lane; i < 624; i += 32) dst[i] = st[i * MT_STRIDE + p];
+    for (int i = t; i < 624; i += blockDim.x) dst[i] = st[i * MT_STRIDE + p];
   }
 }
 
@@ -1718,8 +1731,9 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
   int* d_ninl = B.get<int>((size_t)C * BI * MAXM);
   int* d_nm = B.get<int>((size_t)C * BI);
   int* d_active = B.get<int>((size_t)2 * C);
-  int* d_count = B.get<int>(2);
+  int* d_count = B.get<int>(3);  // active pairs of the current / next round, largest n of the chunk
   unsigned long long* d_stats = B.get<unsigned long long>(10);
+  constexpr size_t kDrawStateBytes = sizeof(uint32_t) * 624 * MT_STRIDE;
   if (!d_idx || !d_states || !d_samples || !d_models || !d_cost || !d_ninl || !d_nm || !d_active || !d_count || !d_stats) THB_FAIL(THB_E_CUDA, "cudaMalloc failed");
   THB_CUDA_CHECK(cudaMemsetAsync(d_stats, 0, sizeof(unsigned long long) * 10, st));
   cudaEvent_t ev[5];
@@ -1733,16 +1747,23 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
   int rc = THB_OK, num_rounds = 0;
   for (int pair0 = 0; pair0 < np && rc == THB_OK; pair0 += C) {
     const int count = std::min(C, np - pair0);
-    cudaMemsetAsync(d_count, 0, sizeof(int) * 2, st);
+    cudaMemsetAsync(d_count, 0, sizeof(int) * 3, st);
     k_rs_init<Est><<<count, 128, 0, st>>>(p, pair0, count, d_off, d_seed, d_res, d_mask, d_idx, d_states, d_active, d_count, d_thresh, d_rng, rng_mode, d_skip);
-    int na = 0, cur = 0;
-    if (cudaMemcpyAsync(&na, d_count, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = THB_E_CUDA; break; }
+    int na = 0, cur = 0, h_cnt[3] = {0, 0, 0};
+    if (cudaMemcpyAsync(h_cnt, d_count, sizeof(int) * 3, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { rc = THB_E_CUDA; break; }
+    na = h_cnt[0];
+    // the sampler's permutations of 16 pairs next to their generators in shared memory, if the largest pair of the chunk allows it
+    const int idx_stride = h_cnt[2] | 1;
+    const size_t draw_smem = kDrawStateBytes + sizeof(int) * (size_t)DRAW_PAIRS * idx_stride;
+    const bool stage_idx = draw_smem <= 200 * 1024;
+    if (stage_idx && cudaFuncSetAttribute(k_rs_draw_staged<Est, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)draw_smem) != cudaSuccess) { rc = THB_E_CUDA; break; }
     while (na > 0) {
       int* act = d_active + (size_t)cur * C;
       int* nxt = d_active + (size_t)(1 - cur) * C;
       cudaEventRecord(ev[0], st);
       if (p.ransac_type == 1) k_rs_draw<Est><<<(na + 63) / 64, 64, 0, st>>>(p.ransac_type, na, act, d_states, d_idx, d_samples);
-      else k_rs_draw_staged<Est><<<(na + DRAW_PAIRS - 1) / DRAW_PAIRS, 32, 0, st>>>(na, act, d_states, d_idx, d_samples);
+      else if (stage_idx) k_rs_draw_staged<Est, true><<<(na + DRAW_PAIRS - 1) / DRAW_PAIRS, 256, draw_smem, st>>>(na, act, d_states, d_idx, d_samples, idx_stride);
+      else k_rs_draw_staged<Est, false><<<(na + DRAW_PAIRS - 1) / DRAW_PAIRS, 32, kDrawStateBytes, st>>>(na, act, d_states, d_idx, d_samples, 0);
       cudaEventRecord(ev[1], st);
       k_rs_solve<Est><<<na, RT, 0, st>>>(na, act, d_states, d_corr, d_samples, d_models, d_nm, d_prof);
       if (d_prof) {  // THB_RS_PROF: distribution of the per-hypothesis solve time (SM cycles)
