@@ -1455,6 +1455,7 @@ __device__ __forceinline__ int mt_uniform_int_strided(uint32_t* mt, int& idx, in
 // STAGE_IDX: the pairs' index permutations (RandomSampler's persistent shuffle, n ints per pair) are staged as well when 16 of them
 // fit next to the generators; the drawing lane then writes its swaps through to global memory (fire and forget) and nothing is
 // copied back but the generator states. Otherwise the permutation entries are read from global memory (two L2 trips per draw).
+__device__ long long g_draw_prof[4];  // THB_TV_TIMING: cycles of block 0 (copy in, draws, copy out) of the last draw launch
 template <class Est, bool STAGE_IDX>
 __global__ void __launch_bounds__(256) k_rs_draw_staged(int na, const int* __restrict__ active, PairState* __restrict__ states,
                                                         int* __restrict__ idx_ws, int* __restrict__ samples, int idx_stride) {
@@ -1463,6 +1464,7 @@ __global__ void __launch_bounds__(256) k_rs_draw_staged(int na, const int* __res
   int* sx = reinterpret_cast<int*>(draw_smem + 624 * MT_STRIDE);       // [DRAW_PAIRS][idx_stride]
   const int t = threadIdx.x, a0 = blockIdx.x * DRAW_PAIRS;
   const int cnt = min(DRAW_PAIRS, na - a0);
+  const long long c0 = clock64();
   for (int p = 0; p < cnt; ++p) {
     const PairState& Sp = states[active[a0 + p]];
     for (int i = t; i < 624; i += blockDim.x) st[i * MT_STRIDE + p] = Sp.rng.mt[i];
@@ -1472,6 +1474,7 @@ __global__ void __launch_bounds__(256) k_rs_draw_staged(int na, const int* __res
     }
   }
   __syncthreads();
+  const long long c1 = clock64();
   if (t < cnt) {
     const int slot = active[a0 + t];
     PairState& S = states[slot];
@@ -1495,10 +1498,12 @@ __global__ void __launch_bounds__(256) k_rs_draw_staged(int na, const int* __res
     S.stat_samples += nit;
   }
   __syncthreads();
+  const long long c2 = clock64();
   for (int p = 0; p < cnt; ++p) {
     uint32_t* dst = states[active[a0 + p]].rng.mt;
     for (int i = t; i < 624; i += blockDim.x) dst[i] = st[i * MT_STRIDE + p];
   }
+  if (blockIdx.x == 0 && t == 0) { g_draw_prof[0] = c1 - c0; g_draw_prof[1] = c2 - c1; g_draw_prof[2] = clock64() - c2; }
 }
 
 // solve: thread (a, b) = hypothesis b of active pair a
@@ -1799,6 +1804,11 @@ int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int
   THB_CUDA_CHECK(cudaGetLastError());
   THB_CUDA_CHECK(cudaMemcpyAsync(&g_last_stats, d_stats, sizeof(ThbRansacStats), cudaMemcpyDeviceToHost, st));
   THB_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (getenv("THB_TV_TIMING")) {
+    long long dp[4] = {0, 0, 0, 0};
+    cudaMemcpyFromSymbol(dp, g_draw_prof, sizeof(dp));
+    fprintf(stderr, "  last draw launch, block 0: copy in %lld, draws %lld, copy out %lld cycles\n", dp[0], dp[1], dp[2]);
+  }
   if (getenv("THB_TV_TIMING"))
     fprintf(stderr, "  rounds<S=%d>: %d pairs, %d rounds, draw %.2f solve %.2f score %.2f scan %.2f ms\n", Est::S, np, num_rounds, phase_ms[0], phase_ms[1], phase_ms[2], phase_ms[3]);
   // phase shares: device time of the phase kernels in nanoseconds (the fused kernel reports CTA cycles in the same fields)
