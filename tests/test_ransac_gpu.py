@@ -365,11 +365,12 @@ def test_prosac_sampler_matches_oracle(lib, oracle, monkeypatch):
     assert lib.thb_ransac_relpose_batch(C.byref(b), C.byref(params), res.ctypes.data_as(C.c_void_p), mask.ctypes.data_as(C.c_void_p), None) == capi.THB_E_UNSUPPORTED
 
 
-@pytest.mark.parametrize("n", [600, 601, 37])
+@pytest.mark.parametrize("n", [600, 601, 37, 5])
 def test_lmed_matches_oracle(lib, oracle, n):
     """RansacType::LMED (solvers/lmed.h:65-72, lmed_quality_measurement.h:58-118): the median of the squared residuals found by the
     warp radix select equals the oracle's nth_element median bit for bit (even and odd counts, a count below one warp step), hence
-    identical best models, iteration counts and inlier masks; all three estimators."""
+    identical best models, iteration counts and inlier masks; n = 5 is the minimal data set (n - m = 0: the reference's threshold divides
+    by zero and becomes infinite - restated as such)."""
     batch, _ = synthetic.make_pair_batch(20, n=n, inlier_ratio=0.7, seed=5, base_seed=4100)
     params = synthetic.c4_params(oracle.ransac_default_params())
     params.ransac_type = 2
