@@ -1726,8 +1726,9 @@ template <class Est>
 int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, const long long* d_off, const double* d_corr,
                          const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
                          uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
-  constexpr int kChunk = 4096;
-  const int C = std::min(np, kChunk);
+  constexpr int kChunk = 4096;  // bounds the per-hypothesis scratch; equal chunks: the last rounds of a chunk run few pairs, a short last chunk would be all tail
+  const int nchunks = (np + kChunk - 1) / kChunk;
+  const int C = (np + nchunks - 1) / nchunks;
   int* d_idx = B.get<int>((size_t)total);
   PairState* d_states = B.get<PairState>((size_t)C);
   int* d_samples = B.get<int>((size_t)C * BI * 5);
@@ -1822,11 +1823,12 @@ int launch_ransac(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, co
                   const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
                   uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
   {  // Small batches cannot fill the GPU with one CTA per pair: the round-synchronous kernels spread a pair over many CTAs
-     // (measured, C4-shaped pairs: 1 pair 2.5 vs ~6 ms, 16 pairs 4.7 vs 7.1 ms, 148 pairs 7.9 vs 9.4 ms, 1000 pairs 27.5 vs 29.1 ms;
-     // 10 000 pairs 215 vs 208 ms - there the fused kernel's mix of phases per SM wins). THB_RANSAC_MODE=fused|rounds forces one.
+     // (measured at the end of r02, C4-shaped pairs, rounds vs fused: 1 pair 2.5 vs ~6 ms, 16 pairs 4.4 vs 7.1 ms, 148 pairs 7.3 vs 9.4 ms,
+     // 1 250 pairs 28.1 vs 32.9 ms, 2 500 pairs 52.5 vs 57.1 ms, 5 000 pairs 107.2 vs 108.9 ms; 10 000 pairs 212.1 vs 208.8 ms - there the
+     // fused kernel's mix of phases per SM wins). THB_RANSAC_MODE=fused|rounds forces one.
     const char* m = getenv("THB_RANSAC_MODE");  // read per call: tests switch it
     const int mode = !m ? 0 : std::string(m) == "fused" ? 1 : std::string(m) == "rounds" ? 2 : 0;
-    const bool rounds = mode == 2 || (mode == 0 && np <= 2048) || p.ransac_type == 2;  // LMED scoring lives in k_rs_score only
+    const bool rounds = mode == 2 || (mode == 0 && np <= 6000) || p.ransac_type == 2;  // LMED scoring lives in k_rs_score only
     if (!(p.use_lo && Est::HAS_LO) && rounds)
       return launch_ransac_rounds<Est>(st, B, p, np, d_off, d_corr, d_seed, total, d_res, d_mask, d_thresh, d_rng, rng_mode, d_skip);
   }

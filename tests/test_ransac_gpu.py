@@ -194,6 +194,25 @@ def test_minimal_solvers_match_oracle_bit_for_bit(lib, oracle):
     assert np.array_equal(F, Fo)
 
 
+def test_round_schedule_over_several_chunks(lib, monkeypatch):
+    """More pairs than one chunk of the round-synchronous schedule holds (4 096): the batch is cut into equal chunks; records and
+    masks still equal the fused kernel's bit for bit, ragged sizes included."""
+    rng = np.random.default_rng(77)
+    lists = []
+    for i in range(4300):
+        c, _, _, _ = synthetic.make_pair(rng, n=int(rng.integers(6, 40)), inlier_ratio=0.8)
+        lists.append(c)
+    batch = capi.HostPairBatch(lists, 9000 + np.arange(len(lists)))
+    params = synthetic.c4_params(capi.ThbRansacParams()); params.max_iterations = 60
+    out = {}
+    for mode in ("fused", "rounds"):
+        monkeypatch.setenv("THB_RANSAC_MODE", mode)
+        out[mode] = gpu_ransac(lib, batch, params)
+    assert out["fused"][0].tobytes() == out["rounds"][0].tobytes()
+    np.testing.assert_array_equal(out["fused"][1], out["rounds"][1])
+    assert (out["rounds"][0]["success"] == 1).all()
+
+
 @pytest.mark.parametrize("kind", ["abspose", "homography"])
 def test_abspose_and_homography_ransac_identical_inlier_sets(lib, oracle, kind):
     if kind == "abspose":
