@@ -1726,7 +1726,7 @@ template <class Est>
 int launch_ransac_rounds(cudaStream_t st, Bufs& B, const ThbRansacParams& p, int np, const long long* d_off, const double* d_corr,
                          const uint32_t* d_seed, long long total, ThbRelPoseResult* d_res, uint8_t* d_mask, const double* d_thresh,
                          uint32_t* d_rng, int rng_mode, const uint8_t* d_skip) {
-  constexpr int kChunk = 4096;  // bounds the per-hypothesis scratch; equal chunks: the last rounds of a chunk run few pairs, a short last chunk would be all tail
+  constexpr int kChunk = 4096;  // (16384 measured: 10 000 pairs in one chunk 212.5 vs 212.1 ms in three - no gain, 4x the scratch) bounds the per-hypothesis scratch; equal chunks: the last rounds of a chunk run few pairs, a short last chunk would be all tail
   const int nchunks = (np + kChunk - 1) / kChunk;
   const int C = (np + nchunks - 1) / nchunks;
   int* d_idx = B.get<int>((size_t)total);
